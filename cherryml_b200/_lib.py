@@ -1,0 +1,120 @@
+"""ctypes binding of the C ABI declared in ``include/cherryml_b200.h``.
+
+There is no CPU fallback: if the shared library is missing, or a call fails, this module
+raises.  PyTorch is used by the callers only to own device memory and streams.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcherryml_b200.so")
+
+# numpy dtypes of the two descriptor structs (must match include/cherryml_b200.h)
+FAM_DESC_DTYPE = np.dtype(
+    [
+        ("msa_off", np.int64),
+        ("row_stride", np.int32),
+        ("n_chunks", np.int32),
+        ("aux_off", np.int32),
+        ("aux_cnt", np.int32),
+        ("rate_off", np.int32),
+        ("n_rates", np.int32),
+    ],
+    align=True,
+)
+TILE_DTYPE = np.dtype(
+    [
+        ("fam", np.int32),
+        ("pair_begin", np.int32),
+        ("n_pairs", np.int32),
+        ("reserved", np.int32),
+    ],
+    align=True,
+)
+assert FAM_DESC_DTYPE.itemsize == 32 and TILE_DTYPE.itemsize == 16
+
+NO_BUCKET = 255
+INVALID_RESIDUE = 255
+MAX_BUCKETS = 254
+
+
+class CherryError(RuntimeError):
+    pass
+
+
+_P = c_void_p
+_SIGNATURES = {
+    "cherry_last_error": (c_char_p, []),
+    "cherry_version": (c_char_p, []),
+    "cherry_launch_count": (c_int64, []),
+    "cherry_reset_launch_count": (None, []),
+    "cherry_build_bucket_table": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, _P]),
+    "cherry_count_lg": (c_int, [_P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "cherry_count_co": (c_int, [_P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "cherry_symmetrize_lg": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "cherry_symmetrize_co": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "cherry_count_lg_host": (
+        c_int,
+        [_P, c_int64, _P, c_int, _P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int,
+         _P, c_int, c_int, c_int, c_int, _P, _P, _P],
+    ),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names ``include/cherryml_b200.h`` declares (kept in sync by tests/test_abi.py)."""
+    return sorted(_SIGNATURES.keys())
+
+
+def load():
+    """Load the library (once).  Raises ``CherryError`` if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CherryError(
+            f"{LIB_PATH} not found: the CUDA library has not been built. Run "
+            "`python -m cherryml_b200.csrc.build` (or __graft_entry__.build()). "
+            "cherryml_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().cherry_last_error().decode("utf-8", "replace")
+        raise CherryError(f"{what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().cherry_launch_count())
+
+
+def reset_launch_count() -> None:
+    load().cherry_reset_launch_count()
+
+
+def ptr(t) -> int:
+    """Device (or host) address of a torch tensor / numpy array; 0 for None."""
+    if t is None:
+        return 0
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+def current_stream_ptr() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,168 @@
+"""``count_transitions`` / ``count_co_transitions``: drop-in stage functions.
+
+Same names, keyword arguments, defaults, output files and caching behaviour as the
+reference's ``cherryml/counting/_count_transitions.py:201-379`` and
+``_count_co_transitions.py:227-412``; the work itself is the sm_100a counting kernels.
+
+``use_cpp_implementation`` keeps its meaning as the choice of numerical "personality":
+``True`` (default) reproduces the C++ binary (branch lengths rounded through float32 as
+by ``std::stof``, ``_count_transitions.cpp:247``; ``result.txt`` in the C++ writer's
+layout with 6 significant digits, ``.cpp:524-548``), ``False`` reproduces the Python
+implementation (fp64 branch lengths, pandas-style ``result.txt``).  Both run on the GPU.
+``num_processes`` and the ``cpp_command_line_*`` arguments are accepted and ignored.
+Extra keyword arguments (all excluded from the cache key): ``device``,
+``process_group`` (torch.distributed group: families are striped over ranks exactly like
+the reference stripes them over MPI ranks, ``.cpp:624-629``, and the raw integer
+histograms are all-reduced), ``result_style`` (override the writer layout).
+"""
+import logging
+import os
+import time
+from typing import Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from .. import caching
+from ..io import write_count_matrices_array
+from ..utils import get_process_args
+from ._device import count_batch
+from ._ingest import build_co_batch, build_lg_batch
+
+logger = logging.getLogger(__name__)
+
+# In-process hand-off to the fit: output dir -> (grid fp64 [K], states, counts fp64 device tensor)
+_DEVICE_RESULTS: Dict[str, Tuple[np.ndarray, List[str], torch.Tensor]] = {}
+
+
+def device_result(output_count_matrices_dir: str):
+    """Counts of a ``count_*`` call made in this process, still resident on the device."""
+    return _DEVICE_RESULTS.get(os.path.realpath(output_count_matrices_dir))
+
+
+def _rank_world(process_group):
+    if process_group is None:
+        return 0, 1
+    import torch.distributed as dist
+
+    return dist.get_rank(process_group), dist.get_world_size(process_group)
+
+
+def _finish(counts_dev, grid, states, out_dir, style, start_time, num_processes, rank):
+    _DEVICE_RESULTS[os.path.realpath(out_dir)] = (grid, list(states), counts_dev)
+    if rank == 0:
+        counts = counts_dev.cpu().numpy()
+        write_count_matrices_array(
+            grid.tolist(), states, counts, os.path.join(out_dir, "result.txt"), style
+        )
+        with open(os.path.join(out_dir, "profiling.txt"), "w") as f:
+            f.write(
+                f"Total time: {time.time() - start_time} seconds with "
+                f"{num_processes} processes.\n"
+            )
+
+
+@caching.cached_computation(
+    exclude_args=[
+        "num_processes",
+        "use_cpp_implementation",
+        "cpp_command_line_prefix",
+        "cpp_command_line_suffix",
+        "device",
+        "process_group",
+        "result_style",
+    ],
+    output_dirs=["output_count_matrices_dir"],
+    write_extra_log_files=True,
+)
+def count_transitions(
+    tree_dir: str,
+    msa_dir: str,
+    site_rates_dir: str,
+    families: List[str],
+    amino_acids: List[str],
+    quantization_points: List[Union[str, float]],
+    edge_or_cherry: str,
+    output_count_matrices_dir: Optional[str] = None,
+    num_processes: int = 1,
+    use_cpp_implementation: bool = True,
+    cpp_command_line_prefix: str = "",
+    cpp_command_line_suffix: str = "",
+    device: str = "cuda",
+    process_group=None,
+    result_style: Optional[str] = None,
+) -> None:
+    """Count single-site transitions into a ``K x S x S`` tensor (see module docstring)."""
+    if edge_or_cherry.startswith("cherry++__"):
+        edge_or_cherry = "cherry++"
+    start_time = time.time()
+    logger.info(f"Starting on {len(families)} families")
+    os.makedirs(output_count_matrices_dir, exist_ok=True)
+    quantization_points = [float(q) for q in quantization_points]
+    rank, world = _rank_world(process_group)
+    batch = build_lg_batch(
+        tree_dir, msa_dir, site_rates_dir, get_process_args(rank, world, list(families)),
+        amino_acids, edge_or_cherry, float32_branch_lengths=bool(use_cpp_implementation),
+    )
+    counts = count_batch(
+        batch, quantization_points, len(amino_acids), directed=(edge_or_cherry == "edge"),
+        device=device, process_group=process_group,
+    )
+    style = result_style or ("cpp" if use_cpp_implementation else "python")
+    _finish(counts, np.array(sorted(quantization_points)), list(amino_acids),
+            output_count_matrices_dir, style, start_time, num_processes, rank)
+    logger.info("Done!")
+
+
+@caching.cached_computation(
+    exclude_args=[
+        "num_processes",
+        "use_cpp_implementation",
+        "cpp_command_line_prefix",
+        "cpp_command_line_suffix",
+        "device",
+        "process_group",
+        "result_style",
+    ],
+    output_dirs=["output_count_matrices_dir"],
+    write_extra_log_files=True,
+)
+def count_co_transitions(
+    tree_dir: str,
+    msa_dir: str,
+    contact_map_dir: str,
+    families: List[str],
+    amino_acids: List[str],
+    quantization_points: List[Union[str, float]],
+    edge_or_cherry: str,
+    minimum_distance_for_nontrivial_contact: int,
+    output_count_matrices_dir: Optional[str] = None,
+    num_processes: int = 1,
+    use_cpp_implementation: bool = True,
+    cpp_command_line_prefix: str = "",
+    cpp_command_line_suffix: str = "",
+    device: str = "cuda",
+    process_group=None,
+    result_style: Optional[str] = None,
+) -> None:
+    """Count transitions of contacting site pairs into a ``K x S^2 x S^2`` tensor."""
+    if edge_or_cherry.startswith("cherry++__"):
+        edge_or_cherry = "cherry++"
+    start_time = time.time()
+    os.makedirs(output_count_matrices_dir, exist_ok=True)
+    quantization_points = [float(q) for q in quantization_points]
+    rank, world = _rank_world(process_group)
+    batch = build_co_batch(
+        tree_dir, msa_dir, contact_map_dir, get_process_args(rank, world, list(families)),
+        amino_acids, edge_or_cherry, minimum_distance_for_nontrivial_contact,
+        float32_branch_lengths=bool(use_cpp_implementation),
+    )
+    counts = count_batch(
+        batch, quantization_points, len(amino_acids), directed=(edge_or_cherry == "edge"),
+        device=device, process_group=process_group,
+    )
+    pair_states = [a + b for a in amino_acids for b in amino_acids]
+    style = result_style or ("cpp" if use_cpp_implementation else "python")
+    _finish(counts, np.array(sorted(quantization_points)), pair_states,
+            output_count_matrices_dir, style, start_time, num_processes, rank)
+    logger.info("Done!")

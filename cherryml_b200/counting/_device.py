@@ -1,0 +1,194 @@
+"""Run the counting kernels on an encoded batch (device side of the counting stage).
+
+PyTorch owns the device buffers and the stream; all compute is the CUDA library behind
+the C ABI (``include/cherryml_b200.h``).  No CPU fallback.
+"""
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ._ingest import CountBatch
+
+# (pairs x contacts) per co-transition launch is kept below this so no uint32 cell can wrap
+_CO_MAX_ITEMS_PER_LAUNCH = (1 << 32) - 1
+
+
+@dataclass
+class DeviceBatch:
+    kind: str
+    msa: torch.Tensor
+    fams: torch.Tensor
+    pair_a: torch.Tensor
+    pair_b: torch.Tensor
+    pair_t: torch.Tensor
+    pair_fam: torch.Tensor
+    rate_vals: torch.Tensor
+    aux: torch.Tensor
+    tiles: torch.Tensor
+    r_pad: int
+    n_pairs: int
+    n_tiles: int
+    n_sites_examined: int
+    tile_items: Optional[np.ndarray] = None  # host copy, co only: items per tile
+
+    def nbytes(self) -> int:
+        return sum(
+            t.numel() * t.element_size()
+            for t in (self.msa, self.fams, self.pair_a, self.pair_b, self.pair_t,
+                      self.pair_fam, self.rate_vals, self.aux, self.tiles)
+        )
+
+
+def _as_device(arr: np.ndarray, device, pin: bool = False) -> torch.Tensor:
+    raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+    t = torch.from_numpy(raw)
+    if pin:
+        t = t.pin_memory()
+    return t.to(device, non_blocking=pin)
+
+
+def to_device(batch: CountBatch, device="cuda") -> DeviceBatch:
+    """Upload a host batch.  Tensors are raw byte tensors; the kernels see typed pointers."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.CherryError("cherryml_b200 counting runs on CUDA devices only")
+    _lib.load()
+    tile_items = None
+    if batch.kind == "co" and batch.tiles.shape[0]:
+        tile_items = batch.tiles["n_pairs"].astype(np.int64) * batch.fams["aux_cnt"][
+            batch.tiles["fam"]
+        ].astype(np.int64)
+    return DeviceBatch(
+        kind=batch.kind,
+        msa=_as_device(batch.msa, device),
+        fams=_as_device(batch.fams, device),
+        pair_a=_as_device(batch.pair_a, device),
+        pair_b=_as_device(batch.pair_b, device),
+        pair_t=_as_device(batch.pair_t, device),
+        pair_fam=_as_device(batch.pair_fam, device),
+        rate_vals=_as_device(batch.rate_vals, device),
+        aux=_as_device(batch.aux, device),
+        tiles=_as_device(batch.tiles, device),
+        r_pad=batch.r_pad,
+        n_pairs=batch.n_pairs,
+        n_tiles=int(batch.tiles.shape[0]),
+        n_sites_examined=batch.n_sites_examined,
+        tile_items=tile_items,
+    )
+
+
+def sorted_grid(quantization_points: Sequence[float]) -> np.ndarray:
+    grid = np.array(sorted(float(q) for q in quantization_points), dtype=np.float64)
+    if grid.size == 0:
+        raise ValueError("quantization_points is empty")
+    if grid.size > _lib.MAX_BUCKETS:
+        raise _lib.CherryError(
+            f"{grid.size} quantization points: at most {_lib.MAX_BUCKETS} are supported"
+        )
+    return grid
+
+
+def build_bucket_table(dev: DeviceBatch, grid_dev: torch.Tensor, K: int) -> torch.Tensor:
+    lib = _lib.load()
+    tab = torch.empty(max(1, dev.n_pairs * dev.r_pad), dtype=torch.uint8, device=dev.msa.device)
+    if dev.n_pairs:
+        rc = lib.cherry_build_bucket_table(
+            _lib.ptr(dev.pair_t), _lib.ptr(dev.pair_fam), _lib.ptr(dev.fams),
+            _lib.ptr(dev.rate_vals), _lib.ptr(grid_dev), K, dev.n_pairs, dev.r_pad,
+            _lib.ptr(tab), _lib.current_stream_ptr(),
+        )
+        _lib.check(rc, "cherry_build_bucket_table")
+    return tab
+
+
+def count_raw(
+    dev: DeviceBatch,
+    grid_dev: torch.Tensor,
+    K: int,
+    S: int,
+    tab: Optional[torch.Tensor] = None,
+    out: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """Raw directed integer histogram on the device.
+
+    LG: uint64 ``[K,S,S]`` (returned as an int64 tensor); co: uint32 ``[K,S*S,S*S]``
+    (returned as an int32 tensor).  ``out`` is accumulated into when given.
+    """
+    lib = _lib.load()
+    device = dev.msa.device
+    if tab is None:
+        tab = build_bucket_table(dev, grid_dev, K)
+    stream = _lib.current_stream_ptr()
+    if dev.kind == "lg":
+        if out is None:
+            out = torch.zeros((K, S, S), dtype=torch.int64, device=device)
+        if dev.n_tiles:
+            rc = lib.cherry_count_lg(
+                _lib.ptr(dev.msa), _lib.ptr(dev.fams), _lib.ptr(dev.pair_a), _lib.ptr(dev.pair_b),
+                _lib.ptr(tab), dev.r_pad, _lib.ptr(dev.aux), _lib.ptr(dev.tiles), dev.n_tiles,
+                K, S, _lib.ptr(out), stream,
+            )
+            _lib.check(rc, "cherry_count_lg")
+        return out
+    n = S * S
+    if out is None:
+        out = torch.zeros((K, n, n), dtype=torch.int32, device=device)
+    if dev.n_tiles:
+        total_items = int(dev.tile_items.sum()) if dev.tile_items is not None else 0
+        if total_items > _CO_MAX_ITEMS_PER_LAUNCH:
+            raise _lib.CherryError(
+                f"{total_items} (pair, contact) items in one batch could wrap a uint32 cell; "
+                "split the families into several batches"
+            )
+        rc = lib.cherry_count_co(
+            _lib.ptr(dev.msa), _lib.ptr(dev.fams), _lib.ptr(dev.pair_a), _lib.ptr(dev.pair_b),
+            _lib.ptr(tab), dev.r_pad, _lib.ptr(dev.aux), _lib.ptr(dev.tiles), dev.n_tiles,
+            K, S, _lib.ptr(out), stream,
+        )
+        _lib.check(rc, "cherry_count_co")
+    return out
+
+
+def symmetrize(raw: torch.Tensor, kind: str, K: int, S: int, directed: bool) -> torch.Tensor:
+    """fp64 count tensor with the reference's 0.5 / 0.25 weights applied (exact)."""
+    lib = _lib.load()
+    stream = _lib.current_stream_ptr()
+    if kind == "lg":
+        out = torch.empty((K, S, S), dtype=torch.float64, device=raw.device)
+        rc = lib.cherry_symmetrize_lg(_lib.ptr(raw), K, S, int(directed), _lib.ptr(out), stream)
+        _lib.check(rc, "cherry_symmetrize_lg")
+    else:
+        n = S * S
+        out = torch.empty((K, n, n), dtype=torch.float64, device=raw.device)
+        rc = lib.cherry_symmetrize_co(_lib.ptr(raw), K, S, int(directed), _lib.ptr(out), stream)
+        _lib.check(rc, "cherry_symmetrize_co")
+    return out
+
+
+def count_batch(
+    batch: CountBatch,
+    quantization_points: Sequence[float],
+    num_states: int,
+    directed: bool,
+    device="cuda",
+    process_group=None,
+) -> torch.Tensor:
+    """Encoded host batch -> symmetrised fp64 count tensor on the device.
+
+    With ``process_group`` (torch.distributed, one process per GPU) each rank passes the
+    batch of ITS families; the raw integer histograms are summed with one all-reduce, so
+    the result is bit-identical for any number of ranks.
+    """
+    grid = sorted_grid(quantization_points)
+    K = int(grid.size)
+    dev = to_device(batch, device)
+    grid_dev = torch.from_numpy(grid).to(dev.msa.device)
+    raw = count_raw(dev, grid_dev, K, num_states)
+    if process_group is not None:
+        import torch.distributed as dist
+
+        dist.all_reduce(raw, op=dist.ReduceOp.SUM, group=process_group)
+    return symmetrize(raw, batch.kind, K, num_states, directed)

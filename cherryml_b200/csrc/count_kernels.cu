@@ -1,0 +1,354 @@
+// Transition counting for sm_100a: bucket table, LG (single-site) histogram, co-transition
+// (pair-of-sites) histogram and the symmetrisation epilogues.
+//
+// Reference semantics (songlab-cal/CherryML v0.2.0):
+//   quantisation  cherryml/utils.py:35-56  ==  counting/_count_transitions.cpp:295-307
+//   LG loop       counting/_count_transitions.cpp:368-381 (cherry++), :444-506 (edge/cherry)
+//   co loop       counting/_count_co_transitions.cpp:358-383, :469-531
+// The reference adds 0.5 (or 0.25) to two (or four) cells per site; here each site adds ONE
+// to a raw directed integer histogram and the halves/quarters are applied once at the end
+// (cherry_symmetrize_*), which is exact because every addend is a multiple of 0.25.
+//
+// Layout in HBM: residues are uint8 alphabet indices (255 = skip) in one
+// flat buffer; a family's rows are 16-byte aligned with a row stride that is a multiple of
+// 16; LG columns are sorted by site-rate category and each category is padded to a
+// multiple of 4 sites, so that every aligned 32-bit word of a row has ONE category and the
+// bucket of (pair, word) is a single byte lookup tab[pair][category].
+#include "common.cuh"
+
+namespace {
+
+constexpr int kCountThreads = 1024;  // one CTA per SM, 32 warps to cover HBM latency
+constexpr int kMaxSmemBytes = 227 * 1024;
+
+__device__ __forceinline__ uint4 ld_stream16(const uint8_t* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// fp64 nearest-grid-point in relative error; -1 outside the grid.  Same expression, same
+// rounding as the host definition (IEEE div.rn.f64, no contraction is possible here).
+__device__ __forceinline__ int quantize_bucket(double t, const double* __restrict__ q, int K) {
+  if (t < q[0] || t > q[K - 1]) return -1;
+  int lo = 0, hi = K;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (q[mid] < t) lo = mid + 1; else hi = mid;
+  }
+  if (lo == 0) return 0;
+  double left = q[lo - 1], right = q[lo];
+  double el = __dsub_rn(__ddiv_rn(t, left), 1.0);
+  double er = __dsub_rn(__ddiv_rn(right, t), 1.0);
+  return (el < er) ? lo - 1 : lo;
+}
+
+__global__ void bucket_table_kernel(const double* __restrict__ pair_t,
+                                    const int32_t* __restrict__ pair_fam,
+                                    const cherry_fam_desc* __restrict__ fams,
+                                    const double* __restrict__ rate_vals,
+                                    const double* __restrict__ grid, int K, int64_t n_pairs,
+                                    int r_pad, uint8_t* __restrict__ tab) {
+  extern __shared__ double sgrid[];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) sgrid[i] = grid[i];
+  __syncthreads();
+  int64_t total = n_pairs * r_pad;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = idx / r_pad;
+    int r = (int)(idx - p * r_pad);
+    const cherry_fam_desc fd = fams[pair_fam[p]];
+    uint8_t out = CHERRY_NO_BUCKET;
+    if (r < fd.n_rates) {
+      double t = __dmul_rn(pair_t[p], rate_vals[fd.rate_off + r]);
+      int b = quantize_bucket(t, sgrid, K);
+      if (b >= 0) out = (uint8_t)b;
+    }
+    tab[idx] = out;
+  }
+}
+
+template <bool SMEM>
+__device__ __forceinline__ void add_bin(uint32_t* h32, unsigned long long* h64, int idx) {
+  if (SMEM) atomicAdd(h32 + idx, 1u);
+  else atomicAdd(h64 + idx, 1ull);
+}
+
+// One aligned 32-bit word = 4 sites of one rate category.
+template <bool SMEM>
+__device__ __forceinline__ void count_word(uint32_t* h32, unsigned long long* h64, uint32_t wa,
+                                           uint32_t wb, uint32_t bucket, int S, int SS,
+                                           uint32_t S4) {
+  if (bucket == CHERRY_NO_BUCKET) return;
+  uint32_t m = __vcmpltu4(wa, S4) & __vcmpltu4(wb, S4);  // 0xff per site with both residues valid
+  if (m == 0) return;
+  const int base = (int)bucket * SS;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (m & (0x80u << (8 * k))) {
+      int x = (wa >> (8 * k)) & 0xff;
+      int y = (wb >> (8 * k)) & 0xff;
+      add_bin<SMEM>(h32, h64, base + x * S + y);
+    }
+  }
+}
+
+template <bool SMEM>
+__device__ __forceinline__ void count_item(uint32_t* h32, unsigned long long* h64, const uint4& va,
+                                           const uint4& vb, const uint2& g,
+                                           const uint8_t* __restrict__ trow, int S, int SS,
+                                           uint32_t S4) {
+  uint32_t b0 = __ldg(trow + (g.x & 0xffffu));
+  uint32_t b1 = __ldg(trow + (g.x >> 16));
+  uint32_t b2 = __ldg(trow + (g.y & 0xffffu));
+  uint32_t b3 = __ldg(trow + (g.y >> 16));
+  count_word<SMEM>(h32, h64, va.x, vb.x, b0, S, SS, S4);
+  count_word<SMEM>(h32, h64, va.y, vb.y, b1, S, SS, S4);
+  count_word<SMEM>(h32, h64, va.z, vb.z, b2, S, SS, S4);
+  count_word<SMEM>(h32, h64, va.w, vb.w, b3, S, SS, S4);
+}
+
+// Persistent: gridDim.x CTAs stride over tiles.  A work item is one 16-byte chunk (16
+// sites) of one pair; consecutive threads take consecutive chunks, so a warp reads runs of
+// contiguous bytes from the two rows.  SMEM=true: the whole [K][S][S] histogram lives in
+// shared memory as uint32 and is flushed once; SMEM=false (histogram too large): global
+// uint64 atomics.
+template <bool SMEM>
+__global__ void __launch_bounds__(kCountThreads, 1)
+count_lg_kernel(const uint8_t* __restrict__ msa, const cherry_fam_desc* __restrict__ fams,
+                const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b,
+                const uint8_t* __restrict__ tab, int r_pad,
+                const uint16_t* __restrict__ group_cat, const cherry_tile* __restrict__ tiles,
+                int n_tiles, int K, int S, unsigned long long* __restrict__ counts) {
+  extern __shared__ uint32_t hist[];
+  const int SS = S * S;
+  const int nbins = K * SS;
+  const int tid = threadIdx.x;
+  const uint32_t S4 = (uint32_t)S * 0x01010101u;
+  if (SMEM) {
+    for (int i = tid; i < nbins; i += kCountThreads) hist[i] = 0;
+    __syncthreads();
+  }
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const cherry_tile tl = tiles[tile];
+    const cherry_fam_desc fd = fams[tl.fam];
+    const uint8_t* __restrict__ base = msa + fd.msa_off;
+    const uint16_t* __restrict__ gc = group_cat + fd.aux_off;
+    const uint32_t nch = (uint32_t)fd.n_chunks;
+    const uint32_t n_items = (uint32_t)tl.n_pairs * nch;
+    const int64_t stride = fd.row_stride;
+    for (uint32_t i = tid; i < n_items; i += 2 * kCountThreads) {
+      // two items in flight per thread
+      const uint32_t i1 = i + kCountThreads;
+      const bool has1 = i1 < n_items;
+      uint32_t pl0 = i / nch, ch0 = i - pl0 * nch;
+      uint32_t pl1 = has1 ? i1 / nch : pl0, ch1 = has1 ? i1 - pl1 * nch : ch0;
+      const int p0 = tl.pair_begin + (int)pl0, p1 = tl.pair_begin + (int)pl1;
+      const int a0 = __ldg(pair_a + p0), b0 = __ldg(pair_b + p0);
+      const int a1 = __ldg(pair_a + p1), b1 = __ldg(pair_b + p1);
+      uint4 va0 = ld_stream16(base + a0 * stride + ch0 * 16);
+      uint4 vb0 = ld_stream16(base + b0 * stride + ch0 * 16);
+      uint4 va1 = ld_stream16(base + a1 * stride + ch1 * 16);
+      uint4 vb1 = ld_stream16(base + b1 * stride + ch1 * 16);
+      uint2 g0 = __ldg(reinterpret_cast<const uint2*>(gc + ch0 * 4));
+      uint2 g1 = __ldg(reinterpret_cast<const uint2*>(gc + ch1 * 4));
+      count_item<SMEM>(hist, counts, va0, vb0, g0, tab + (int64_t)p0 * r_pad, S, SS, S4);
+      if (has1)
+        count_item<SMEM>(hist, counts, va1, vb1, g1, tab + (int64_t)p1 * r_pad, S, SS, S4);
+    }
+  }
+  if (SMEM) {
+    __syncthreads();
+    for (int i = tid; i < nbins; i += kCountThreads) {
+      uint32_t v = hist[i];
+      if (v) atomicAdd(counts + i, (unsigned long long)v);
+    }
+  }
+}
+
+// Co-transitions: a work item is (pair, contact).  Consecutive threads take consecutive
+// contacts of one pair, i.e. a warp gathers bytes from the same two rows (L1 hits) and
+// issues one L2 reduction per item into the [K][S^2][S^2] uint32 histogram.
+__global__ void __launch_bounds__(256)
+count_co_kernel(const uint8_t* __restrict__ msa, const cherry_fam_desc* __restrict__ fams,
+                const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b,
+                const uint8_t* __restrict__ tab, int r_pad, const int2* __restrict__ contacts,
+                const cherry_tile* __restrict__ tiles, int n_tiles, int K, int S,
+                uint32_t* __restrict__ counts) {
+  const uint32_t n = (uint32_t)(S * S);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const cherry_tile tl = tiles[tile];
+    const cherry_fam_desc fd = fams[tl.fam];
+    const uint32_t nc = (uint32_t)fd.aux_cnt;
+    if (nc == 0) continue;
+    const uint8_t* __restrict__ base = msa + fd.msa_off;
+    const int2* __restrict__ cs = contacts + fd.aux_off;
+    const int64_t stride = fd.row_stride;
+    const uint32_t n_items = (uint32_t)tl.n_pairs * nc;
+    for (uint32_t i = threadIdx.x; i < n_items; i += blockDim.x) {
+      const uint32_t pl = i / nc, ci = i - pl * nc;
+      const int p = tl.pair_begin + (int)pl;
+      const uint32_t bucket = __ldg(tab + (int64_t)p * r_pad);
+      if (bucket == CHERRY_NO_BUCKET) continue;
+      const int2 ij = __ldg(cs + ci);
+      const uint8_t* ra = base + __ldg(pair_a + p) * stride;
+      const uint8_t* rb = base + __ldg(pair_b + p) * stride;
+      const uint32_t xi = __ldg(ra + ij.x), xj = __ldg(ra + ij.y);
+      const uint32_t yi = __ldg(rb + ij.x), yj = __ldg(rb + ij.y);
+      if (xi < (uint32_t)S && xj < (uint32_t)S && yi < (uint32_t)S && yj < (uint32_t)S) {
+        const size_t s = xi * S + xj, e = yi * S + yj;
+        atomicAdd(counts + ((size_t)bucket * n + s) * n + e, 1u);
+      }
+    }
+  }
+}
+
+__global__ void symmetrize_lg_kernel(const unsigned long long* __restrict__ raw, int K, int S,
+                                     int directed, double* __restrict__ out) {
+  const int SS = S * S;
+  const int total = K * SS;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += gridDim.x * blockDim.x) {
+    int k = idx / SS, r = idx - k * SS;
+    int x = r / S, y = r - x * S;
+    unsigned long long a = raw[idx];
+    if (directed) {
+      out[idx] = (double)a;
+    } else {
+      unsigned long long b = raw[k * SS + y * S + x];
+      out[idx] = 0.5 * (double)(a + b);
+    }
+  }
+}
+
+__global__ void symmetrize_co_kernel(const uint32_t* __restrict__ raw, int K, int S, int directed,
+                                     double* __restrict__ out) {
+  const size_t n = (size_t)S * S;
+  const size_t total = (size_t)K * n * n;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    size_t k = idx / (n * n), r = idx - k * n * n;
+    size_t s = r / n, e = r - s * n;
+    size_t st = (s % S) * S + s / S, et = (e % S) * S + e / S;  // the two sites swapped
+    const uint32_t* R = raw + k * n * n;
+    unsigned long long v = (unsigned long long)R[s * n + e] + R[st * n + et];
+    if (directed) {
+      out[idx] = 0.5 * (double)v;
+    } else {
+      v += (unsigned long long)R[e * n + s] + R[et * n + st];
+      out[idx] = 0.25 * (double)v;
+    }
+  }
+}
+
+int check_count_args(const void* msa, const void* fams, const void* pa, const void* pb,
+                     const void* tab, const void* tiles, const void* counts, int n_tiles, int K,
+                     int S, int r_pad) {
+  if (!msa || !fams || !pa || !pb || !tab || !tiles || !counts)
+    return cherry::fail(CHERRY_EINVAL, "count: null pointer argument");
+  if (n_tiles < 0 || r_pad <= 0) return cherry::fail(CHERRY_EINVAL, "count: bad n_tiles/r_pad");
+  if (K <= 0 || K > CHERRY_MAX_BUCKETS)
+    return cherry::fail(CHERRY_ELIMIT, "count: K=%d outside 1..%d", K, CHERRY_MAX_BUCKETS);
+  if (S <= 0 || S > 255) return cherry::fail(CHERRY_ELIMIT, "count: S=%d outside 1..255", S);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cherry_build_bucket_table(const double* pair_t, const int32_t* pair_fam,
+                              const cherry_fam_desc* fams, const double* rate_vals,
+                              const double* grid, int K, int64_t n_pairs, int r_pad,
+                              uint8_t* tab, void* stream) {
+  if (!pair_t || !pair_fam || !fams || !rate_vals || !grid || !tab)
+    return cherry::fail(CHERRY_EINVAL, "bucket_table: null pointer argument");
+  if (K <= 0 || K > CHERRY_MAX_BUCKETS)
+    return cherry::fail(CHERRY_ELIMIT, "bucket_table: K=%d outside 1..%d", K, CHERRY_MAX_BUCKETS);
+  if (n_pairs < 0 || r_pad <= 0) return cherry::fail(CHERRY_EINVAL, "bucket_table: bad sizes");
+  if (n_pairs == 0) return 0;
+  int64_t total = n_pairs * r_pad;
+  int blocks = (int)((total + 255) / 256);
+  int cap = cherry::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  bucket_table_kernel<<<blocks, 256, K * sizeof(double), (cudaStream_t)stream>>>(
+      pair_t, pair_fam, fams, rate_vals, grid, K, n_pairs, r_pad, tab);
+  CHERRY_LAUNCH_CHECK("bucket_table_kernel");
+  return 0;
+}
+
+int cherry_count_lg(const uint8_t* msa, const cherry_fam_desc* fams, const int32_t* pair_a,
+                    const int32_t* pair_b, const uint8_t* tab, int r_pad,
+                    const uint16_t* group_cat, const cherry_tile* tiles, int n_tiles, int K,
+                    int S, unsigned long long* counts, void* stream) {
+  int rc = check_count_args(msa, fams, pair_a, pair_b, tab, tiles, counts, n_tiles, K, S, r_pad);
+  if (rc) return rc;
+  if (!group_cat) return cherry::fail(CHERRY_EINVAL, "count_lg: null group_cat");
+  if (n_tiles == 0) return 0;
+  const size_t hist_bytes = (size_t)K * S * S * sizeof(uint32_t);
+  int grid = cherry::sm_count();
+  if (grid > n_tiles) grid = n_tiles;
+  if (hist_bytes <= (size_t)kMaxSmemBytes) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    CHERRY_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+      CHERRY_CUDA(cudaFuncSetAttribute(count_lg_kernel<true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
+      attr_set[dev] = true;
+    }
+    count_lg_kernel<true><<<grid, kCountThreads, hist_bytes, (cudaStream_t)stream>>>(
+        msa, fams, pair_a, pair_b, tab, r_pad, group_cat, tiles, n_tiles, K, S, counts);
+  } else {
+    count_lg_kernel<false><<<grid, kCountThreads, 0, (cudaStream_t)stream>>>(
+        msa, fams, pair_a, pair_b, tab, r_pad, group_cat, tiles, n_tiles, K, S, counts);
+  }
+  CHERRY_LAUNCH_CHECK("count_lg_kernel");
+  return 0;
+}
+
+int cherry_count_co(const uint8_t* msa, const cherry_fam_desc* fams, const int32_t* pair_a,
+                    const int32_t* pair_b, const uint8_t* tab, int r_pad,
+                    const int32_t* contacts, const cherry_tile* tiles, int n_tiles, int K,
+                    int S, uint32_t* counts, void* stream) {
+  int rc = check_count_args(msa, fams, pair_a, pair_b, tab, tiles, counts, n_tiles, K, S, r_pad);
+  if (rc) return rc;
+  if (!contacts) return cherry::fail(CHERRY_EINVAL, "count_co: null contacts");
+  if (S > 64) return cherry::fail(CHERRY_ELIMIT, "count_co: S=%d > 64", S);
+  if (n_tiles == 0) return 0;
+  int grid = cherry::sm_count() * 8;
+  if (grid > n_tiles) grid = n_tiles;
+  count_co_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      msa, fams, pair_a, pair_b, tab, r_pad, reinterpret_cast<const int2*>(contacts), tiles,
+      n_tiles, K, S, counts);
+  CHERRY_LAUNCH_CHECK("count_co_kernel");
+  return 0;
+}
+
+int cherry_symmetrize_lg(const unsigned long long* raw, int K, int S, int directed, double* out,
+                         void* stream) {
+  if (!raw || !out) return cherry::fail(CHERRY_EINVAL, "symmetrize_lg: null pointer");
+  if (K <= 0 || S <= 0) return cherry::fail(CHERRY_EINVAL, "symmetrize_lg: bad sizes");
+  int total = K * S * S;
+  int blocks = (total + 255) / 256;
+  symmetrize_lg_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(raw, K, S, directed, out);
+  CHERRY_LAUNCH_CHECK("symmetrize_lg_kernel");
+  return 0;
+}
+
+int cherry_symmetrize_co(const uint32_t* raw, int K, int S, int directed, double* out,
+                         void* stream) {
+  if (!raw || !out) return cherry::fail(CHERRY_EINVAL, "symmetrize_co: null pointer");
+  if (K <= 0 || S <= 0) return cherry::fail(CHERRY_EINVAL, "symmetrize_co: bad sizes");
+  size_t total = (size_t)K * S * S * S * S;
+  size_t want = (total + 255) / 256;
+  int cap = cherry::sm_count() * 16;
+  int blocks = (int)(want < (size_t)cap ? want : (size_t)cap);
+  symmetrize_co_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(raw, K, S, directed, out);
+  CHERRY_LAUNCH_CHECK("symmetrize_co_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,437 @@
+"""Text formats either side of the hot path (host side, Python).
+
+These mirror the on-disk formats of the reference's ``cherryml/io`` package so that the
+directories a CherryML user already has can be consumed and produced unchanged:
+
+* MSA ``family.txt``          -- ``io/_msa.py:51-73``
+* tree ("N nodes / M edges")  -- ``io/_tree.py:214-265`` (children keep edge-line order)
+* site rates                  -- ``io/_site_rates.py:5-26``
+* contact map                 -- ``io/_contact_map.py:6-28``
+* count matrices result.txt   -- ``io/_count_matrices.py:8-81`` and the C++ writer
+                                  ``counting/_count_transitions.cpp:524-548``
+* rate / mask matrices        -- ``io/_rate_matrix.py:37-76``
+"""
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+# --------------------------------------------------------------------------- trees
+class Tree:
+    """Rooted tree with ordered children (order = order of the edge lines)."""
+
+    def __init__(self) -> None:
+        self._children: Dict[str, List[Tuple[str, float]]] = {}
+        self._parent: Dict[str, Tuple[str, float]] = {}
+        self._edges: List[Tuple[str, str, float]] = []
+
+    def add_node(self, v: str) -> None:
+        self._children[v] = []
+
+    def add_nodes(self, nodes: Sequence[str]) -> None:
+        for v in nodes:
+            self.add_node(v)
+
+    def add_edge(self, u: str, v: str, length: float) -> None:
+        if v in self._parent:
+            raise Exception(
+                f"Node {v} already has a parent ({self._parent[v][0]}), cannot "
+                f"also have parent {u} - graph is not a tree."
+            )
+        self._children[u].append((v, length))
+        self._parent[v] = (u, length)
+        self._edges.append((u, v, length))
+
+    def add_edges(self, edges) -> None:
+        for u, v, length in edges:
+            self.add_edge(u, v, length)
+
+    def edges(self) -> List[Tuple[str, str, float]]:
+        return self._edges[:]
+
+    def is_node(self, v: str) -> bool:
+        return v in self._children
+
+    def nodes(self) -> List[str]:
+        return list(self._children.keys())
+
+    def root(self) -> str:
+        roots = [u for u in self._children if u not in self._parent]
+        if len(roots) != 1:
+            raise Exception(f"Tree should have one root, but found: {roots}")
+        return roots[0]
+
+    def children(self, u: str) -> List[Tuple[str, float]]:
+        return list(self._children[u])
+
+    def is_leaf(self, u: str) -> bool:
+        return len(self._children[u]) == 0
+
+    def is_root(self, u: str) -> bool:
+        return u not in self._parent
+
+    def num_nodes(self) -> int:
+        return len(self._children)
+
+    def num_edges(self) -> int:
+        return len(self._edges)
+
+    def parent(self, u: str) -> Tuple[str, float]:
+        return self._parent[u]
+
+    def leaves(self) -> List[str]:
+        return [u for u in self._children if not self._children[u]]
+
+    def internal_nodes(self) -> List[str]:
+        return [u for u in self._children if self._children[u]]
+
+    def preorder_traversal(self) -> List[str]:
+        res, stack = [], [self.root()]
+        while stack:
+            v = stack.pop()
+            res.append(v)
+            stack.extend(c for c, _ in reversed(self._children[v]))
+        return res
+
+
+def read_tree(tree_path: str) -> Tree:
+    with open(tree_path, "r") as f:
+        lines = f.read().strip().split("\n")
+    try:
+        n, s = lines[0].split(" ")
+        if s != "nodes":
+            raise Exception
+        n = int(n)
+    except Exception:
+        raise Exception(
+            f"Tree file: {tree_path} should start with '[num_nodes] nodes'. "
+            f"It started with: '{lines[0]}'"
+        )
+    tree = Tree()
+    for i in range(1, n + 1):
+        tree.add_node(lines[i])
+    try:
+        m, s = lines[n + 1].split(" ")
+        if s != "edges":
+            raise Exception
+        m = int(m)
+    except Exception:
+        raise Exception(
+            f"Tree file: {tree_path} should have line '[num_edges] edges' at "
+            f"position {n + 1}, but it had line: '{lines[n + 1]}'"
+        )
+    if len(lines) != n + 1 + m + 1:
+        raise Exception(
+            f"Tree file: {tree_path} should have {m} edges, but it has "
+            f"{len(lines) - n - 2} edges instead."
+        )
+    for i in range(n + 2, n + 2 + m):
+        try:
+            u, v, length = lines[i].split(" ")
+            length = float(length)
+        except Exception:
+            raise Exception(
+                f"Tree file: {tree_path} should have line '[u] [v] [length]' at"
+                f" position {i}, but it had line: '{lines[i]}'"
+            )
+        if not tree.is_node(u) or not tree.is_node(v):
+            raise Exception(
+                f"In Tree file {tree_path}: {u} and {v} should be nodes in the"
+                f" tree, but the nodes are: {tree.nodes()}"
+            )
+        tree.add_edge(u, v, length)
+    return tree
+
+
+def write_tree(tree: Tree, tree_path: str) -> None:
+    out = [f"{tree.num_nodes()} nodes\n"]
+    out += [f"{v}\n" for v in tree.nodes()]
+    out.append(f"{tree.num_edges()} edges\n")
+    out += [f"{u} {v} {d}\n" for u, v, d in tree.edges()]
+    _makedirs_for(tree_path)
+    with open(tree_path, "w") as f:
+        f.write("".join(out))
+
+
+# ----------------------------------------------------------------------------- MSAs
+def read_msa(msa_path: str) -> Dict[str, str]:
+    with open(msa_path, "r") as f:
+        lines = f.read().strip().split("\n")
+    if len(lines) % 2 != 0:
+        raise Exception(f"The MSA at {msa_path} should have an even number of lines")
+    msa = {}
+    for i in range(len(lines) // 2):
+        if not lines[2 * i].startswith(">"):
+            raise Exception(
+                f"MSA at {msa_path}: at line {2 * i} expected '>[seq_name]' but"
+                f" found {lines[2 * i]}"
+            )
+        msa[lines[2 * i][1:]] = lines[2 * i + 1]
+    return msa
+
+
+def write_msa(msa: Dict[str, str], msa_path: str) -> None:
+    _makedirs_for(msa_path)
+    with open(msa_path, "w") as f:
+        f.write("".join(f">{k}\n{msa[k]}\n" for k in sorted(msa.keys())))
+
+
+# ----------------------------------------------------------------------- site rates
+def read_site_rates(site_rates_path: str) -> List[float]:
+    lines = open(site_rates_path).read().strip().split("\n")
+    try:
+        num_sites, s = lines[0].split(" ")
+        if s != "sites":
+            raise Exception
+        num_sites = int(num_sites)
+    except Exception:
+        raise Exception(
+            f"Site rates file: {site_rates_path} should start with line "
+            f"'[num_sites] sites', but started with: {lines[0]} instead."
+        )
+    try:
+        res = list(map(float, lines[1].split(" ")))
+    except Exception:
+        raise Exception(f"Could nor read site rates in file: {site_rates_path}")
+    if len(res) != num_sites:
+        raise Exception(
+            f"Site rates file: {site_rates_path} was supposed to have "
+            f"{num_sites} sites, but it has {len(res)}"
+        )
+    return res
+
+
+def write_site_rates(site_rates: Sequence[float], site_rates_path: str) -> None:
+    _makedirs_for(site_rates_path)
+    with open(site_rates_path, "w") as f:
+        f.write(f"{len(site_rates)} sites\n" + " ".join(map(str, site_rates)))
+
+
+# --------------------------------------------------------------------- contact maps
+def read_contact_map(contact_map_path: str) -> np.ndarray:
+    lines = open(contact_map_path).read().strip().split("\n")
+    try:
+        num_sites, s = lines[0].split(" ")
+        if s != "sites":
+            raise Exception
+        num_sites = int(num_sites)
+    except Exception:
+        raise Exception(
+            f"Contact map file should start with line '[num_sites] sites', "
+            f"but started with: {lines[0]} instead."
+        )
+    if len(lines) != num_sites + 1:
+        raise Exception(
+            f"Contact Map at: {contact_map_path} should have {num_sites} rows, "
+            f"but has {len(lines) - 1}"
+        )
+    rows = np.frombuffer("".join(lines[1:]).encode("ascii"), dtype=np.uint8)
+    if rows.size != num_sites * num_sites:
+        raise Exception(f"Contact Map at: {contact_map_path} is not square")
+    return (rows.reshape(num_sites, num_sites) - ord("0")).astype(int)
+
+
+def write_contact_map(contact_map: np.ndarray, contact_map_path: str) -> None:
+    _makedirs_for(contact_map_path)
+    with open(contact_map_path, "w") as f:
+        f.write(f"{contact_map.shape[0]} sites\n")
+        np.savetxt(f, contact_map, delimiter="", fmt="%i")
+
+
+# ------------------------------------------------------------------- count matrices
+def read_count_matrices_array(
+    count_matrices_path: str,
+) -> Tuple[np.ndarray, List[str], np.ndarray]:
+    """Parse ``result.txt`` into ``(q[K], states[S], counts[K,S,S])`` (fp64).
+
+    Accepts both writers' output (the pandas one and the C++ one, whose header line
+    starts with a tab and ends with a trailing tab).
+    """
+    with open(count_matrices_path, "r") as f:
+        lines = f.read().strip().split("\n")
+    num_matrices, s = lines[0].strip().split(" ")
+    if s != "matrices":
+        raise Exception(
+            f"In file {count_matrices_path}, expected line '[num_matrices] "
+            f"matrices', but found: '{lines[0]}'"
+        )
+    num_states, s = lines[1].strip().split(" ")
+    if s != "states":
+        raise Exception(
+            f"In file {count_matrices_path}, expected line '[num_states] "
+            f"states', but found: '{lines[1]}'"
+        )
+    K, S = int(num_matrices), int(num_states)
+    q = np.zeros(K)
+    counts = np.zeros((K, S, S))
+    states: List[str] = []
+    pos = 2
+    for k in range(K):
+        q[k] = float(lines[pos])
+        hdr = lines[pos + 1].strip().split()
+        if len(hdr) != S:
+            raise Exception(
+                f"Error reading count matrices file: {count_matrices_path}\n"
+                f"Expected {S} states in line {pos + 1}, but instead "
+                f"found {len(hdr)} states: {hdr}"
+            )
+        states = hdr
+        block = " ".join(
+            " ".join(lines[pos + 2 + i].split()[1:]) for i in range(S)
+        )
+        vals = np.array(block.split(), dtype=np.float64)
+        if vals.size != S * S:
+            raise Exception(f"Could not read count matrices. Matrix {k} is ragged")
+        counts[k] = vals.reshape(S, S)
+        pos += 2 + S
+    return q, states, counts
+
+
+def read_count_matrices(count_matrices_path: str):
+    """Drop-in for ``cherryml.io.read_count_matrices``: ``List[(q, DataFrame)]``."""
+    import pandas as pd
+
+    q, states, counts = read_count_matrices_array(count_matrices_path)
+    return [
+        (float(q[k]), pd.DataFrame(counts[k], index=states, columns=states))
+        for k in range(len(q))
+    ]
+
+
+def _fmt_py(x: float) -> str:
+    return repr(float(x))
+
+
+def _fmt_cpp(x: float) -> str:
+    # ostream << double at default precision == printf("%g")
+    return "%g" % x
+
+
+def write_count_matrices_array(
+    q: Sequence[float],
+    states: Sequence[str],
+    counts: np.ndarray,
+    count_matrices_path: str,
+    style: str = "python",
+) -> None:
+    """Write ``result.txt``.
+
+    ``style="python"`` reproduces the pandas ``to_csv(sep="\\t")`` layout with full
+    ``repr`` floats (``io/_count_matrices.py:66-81``); ``style="cpp"`` reproduces the
+    C++ binary's layout with 6 significant digits (``_count_transitions.cpp:524-548``).
+    """
+    _makedirs_for(count_matrices_path)
+    K, S = len(q), len(states)
+    out = [f"{K} matrices\n{S} states\n"]
+    if style == "python":
+        header = "\t" + "\t".join(states) + "\n"
+        for k in range(K):
+            out.append(f"{_fmt_py(q[k])}\n")
+            out.append(header)
+            rows = counts[k].tolist()
+            for i in range(S):
+                out.append(states[i] + "\t" + "\t".join(map(repr, rows[i])) + "\n")
+    elif style == "cpp":
+        header = "\t" + "".join(s + "\t" for s in states) + "\n"
+        for k in range(K):
+            out.append(f"{_fmt_cpp(q[k])}\n")
+            out.append(header)
+            rows = counts[k].tolist()
+            for i in range(S):
+                out.append(
+                    states[i] + "\t" + "\t".join("%g" % v for v in rows[i]) + "\n"
+                )
+    else:
+        raise ValueError(f"Unknown style: {style}")
+    with open(count_matrices_path, "w") as f:
+        f.write("".join(out))
+
+
+def write_count_matrices(count_matrices, count_matrices_path: str) -> None:
+    """Drop-in for ``cherryml.io.write_count_matrices`` (list of ``(q, DataFrame)``)."""
+    q = [x[0] for x in count_matrices]
+    states = list(count_matrices[0][1].index)
+    counts = np.stack([np.asarray(x[1], dtype=np.float64) for x in count_matrices])
+    write_count_matrices_array(q, states, counts, count_matrices_path, "python")
+
+
+# ------------------------------------------------------------- rate / mask matrices
+def _read_labelled_table(path: str) -> Tuple[List[str], List[str], np.ndarray]:
+    with open(path, "r") as f:
+        lines = [ln for ln in f.read().split("\n") if ln.strip() != ""]
+    cols = lines[0].split()
+    rows, data = [], []
+    for ln in lines[1:]:
+        toks = ln.split()
+        rows.append(toks[0])
+        data.append([float("nan") if t == "_" else float(t) for t in toks[1:]])
+    arr = np.array(data, dtype=np.float64)
+    if arr.ndim != 2 or arr.shape[1] != len(cols):
+        raise Exception(f"Malformed matrix file: {path}")
+    return rows, cols, arr
+
+
+def read_rate_matrix(rate_matrix_path: str):
+    import pandas as pd
+
+    rows, cols, arr = _read_labelled_table(rate_matrix_path)
+    return pd.DataFrame(arr, index=rows, columns=cols)
+
+
+def read_mask_matrix(mask_matrix_path: str):
+    import pandas as pd
+
+    rows, cols, arr = _read_labelled_table(mask_matrix_path)
+    return pd.DataFrame(arr.astype(int), index=rows, columns=cols)
+
+
+def read_probability_distribution(path: str):
+    import pandas as pd
+
+    rows, cols, arr = _read_labelled_table(path)
+    if arr.shape[1] != 1:
+        raise Exception(
+            f"Probability distribution at {path} should be one-dimensional."
+        )
+    if abs(arr.sum() - 1.0) > 1e-6:
+        raise Exception(
+            f"Probability distribution at {path} should add to 1.0, with a "
+            "tolerance of 1e-6."
+        )
+    return pd.DataFrame(arr, index=rows, columns=cols)
+
+
+def write_rate_matrix(
+    rate_matrix: np.ndarray, states: Sequence[str], rate_matrix_path: str
+) -> None:
+    """Tab-separated labelled square table, floats printed like pandas (repr of the
+    stored dtype, so an fp32 matrix prints with fp32 digits as in the reference)."""
+    _makedirs_for(rate_matrix_path)
+    arr = np.asarray(rate_matrix)
+    out = ["\t" + "\t".join(states) + "\n"]
+    for i, s in enumerate(states):
+        # str() of a numpy scalar is the shortest round-trip repr of ITS dtype
+        out.append(s + "\t" + "\t".join(str(v) for v in arr[i]) + "\n")
+    with open(rate_matrix_path, "w") as f:
+        f.write("".join(out))
+
+
+def write_probability_distribution(
+    probability_distribution: np.ndarray, states: Sequence[str], path: str
+) -> None:
+    p = np.asarray(probability_distribution).reshape(-1)
+    if len(states) != p.shape[0]:
+        raise Exception(
+            f"probability_distribution has shape {p.shape}, inconsistent with "
+            f"states: {states}"
+        )
+    _makedirs_for(path)
+    with open(path, "w") as f:
+        f.write("state\tprob\n" + "".join(f"{s}\t{v!r}\n" for s, v in zip(states, p.tolist())))
+
+
+def _makedirs_for(path: str) -> None:
+    d = os.path.dirname(path)
+    if d != "" and not os.path.exists(d):
+        os.makedirs(d, exist_ok=True)

@@ -1,0 +1,129 @@
+/* cherryml_b200 -- C ABI of the B200-native CherryML hot path.
+ *
+ * Every entry point takes plain pointers and sizes.  Unless a name ends in `_host`, all
+ * data pointers are DEVICE pointers owned by the caller (PyTorch allocates them), no
+ * entry point allocates device memory, work is enqueued on `stream` (a cudaStream_t
+ * passed as void*) and the call returns without synchronising.  Return value: 0 on
+ * success, a negative CHERRY_E* code otherwise; cherry_last_error() gives the message
+ * of the last failure on the calling thread.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference
+ * checkout, songlab-cal/CherryML v0.2.0):
+ *
+ *   cherry_build_bucket_table  quantization_idx(), cherryml/utils.py:35-56 ==
+ *                              counting/_count_transitions.cpp:295-307, evaluated once
+ *                              per (pair, rate category) instead of once per site.
+ *   cherry_count_lg            the per-site loop of _dfs()/_map_func(),
+ *                              counting/_count_transitions.cpp:368-381, 444-506 and
+ *                              counting/_count_transitions.py:96-126, 129-186; the CLI
+ *                              it was reached through is _count_transitions.py:295-310.
+ *   cherry_count_co            the per-contact loop, counting/_count_co_transitions.cpp
+ *                              :358-383, 469-531 (CLI: _count_co_transitions.py:324-340).
+ *   cherry_symmetrize_lg/_co   the "+= 0.5 twice" / "+= 0.25 four times" updates of the
+ *                              same loops, applied once to the raw directed histogram,
+ *                              and the rank-0 text-file reduction (.cpp:654-671).
+ *   cherry_fit_*               RateMatrix.forward (estimation/_ratelearn/rate.py:167-188),
+ *                              the epoch body of train_quantization
+ *                              (estimation/_ratelearn/trainer.py:156-187: matrix_exp,
+ *                              log, sum, backward, optimizer.step, best-iterate) and
+ *                              torch.optim.Adam as configured at ratelearner.py:123-126.
+ *   cherry_expm_batched        matrix_exponential_pytorch, markov_chain/_markov_chain.py
+ *                              :22-53.
+ */
+#ifndef CHERRYML_B200_H
+#define CHERRYML_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHERRY_OK 0
+#define CHERRY_EINVAL (-1)  /* bad argument (null pointer, size out of range) */
+#define CHERRY_ECUDA (-2)   /* CUDA runtime error; message has the cudaError string */
+#define CHERRY_ELIMIT (-3)  /* size beyond what the kernels support (e.g. K > 254) */
+
+#define CHERRY_INVALID_RESIDUE 255u /* any byte >= num_states is skipped */
+#define CHERRY_NO_BUCKET 255u       /* bucket-table entry for "outside the grid" */
+#define CHERRY_MAX_BUCKETS 254
+
+/* One MSA family inside the flat residue buffer.  32 bytes. */
+typedef struct cherry_fam_desc {
+  int64_t msa_off;    /* byte offset of the family's row 0 in the residue buffer (16-aligned) */
+  int32_t row_stride; /* bytes per row, a multiple of 16; bytes past the real sites are 255 */
+  int32_t n_chunks;   /* row_stride / 16 */
+  int32_t aux_off;    /* LG: first entry of this family in group_cat[] (one per 4 sites);
+                         co-transitions: first entry of this family in contacts[] */
+  int32_t aux_cnt;    /* LG: row_stride / 4; co-transitions: number of contacting pairs */
+  int32_t rate_off;   /* first entry of this family in rate_vals[] */
+  int32_t n_rates;    /* number of distinct site-rate values (co-transitions: 1) */
+} cherry_fam_desc;
+
+/* A tile is a run of consecutive pairs of one family: {family, first_pair, n_pairs, 0}. */
+typedef struct cherry_tile {
+  int32_t fam;
+  int32_t pair_begin; /* index into pair_a / pair_b / bucket table */
+  int32_t n_pairs;
+  int32_t reserved;
+} cherry_tile;
+
+const char* cherry_last_error(void);
+const char* cherry_version(void);
+/* Number of kernels this library has launched since load (or the last reset). */
+int64_t cherry_launch_count(void);
+void cherry_reset_launch_count(void);
+
+/* ---------------------------------------------------------------- counting */
+
+/* tab[p * r_pad + r] = bucket of (pair_t[p] * rate_vals[fams[pair_fam[p]].rate_off + r])
+ * for r < n_rates of that family, CHERRY_NO_BUCKET otherwise.  grid: K ascending fp64
+ * quantization points.  fp64 throughout, bit-identical to the host definition. */
+int cherry_build_bucket_table(const double* pair_t, const int32_t* pair_fam,
+                              const cherry_fam_desc* fams, const double* rate_vals,
+                              const double* grid, int K, int64_t n_pairs, int r_pad,
+                              uint8_t* tab, void* stream);
+
+/* counts[b][x][y] += #sites of all pairs with bucket b, residue x on row pair_a, residue y
+ * on row pair_b (raw, directed).  group_cat[fam.aux_off + g] is the rate category of
+ * sites 4g..4g+3 of the family's (category-sorted, 4-aligned) columns.
+ * counts: uint64 [K][S][S], accumulated into (caller zeroes it). */
+int cherry_count_lg(const uint8_t* msa, const cherry_fam_desc* fams, const int32_t* pair_a,
+                    const int32_t* pair_b, const uint8_t* tab, int r_pad,
+                    const uint16_t* group_cat, const cherry_tile* tiles, int n_tiles, int K,
+                    int S, unsigned long long* counts, void* stream);
+
+/* counts[b][S*xi+xj][S*yi+yj] += 1 for every (pair, contact (i,j)) with bucket b = tab[p*r_pad].
+ * contacts: int32 [n][2].  counts: uint32 [K][S*S][S*S], accumulated into; the caller keeps
+ * (pairs x contacts) per call below 2^32 so that no cell can wrap. */
+int cherry_count_co(const uint8_t* msa, const cherry_fam_desc* fams, const int32_t* pair_a,
+                    const int32_t* pair_b, const uint8_t* tab, int r_pad,
+                    const int32_t* contacts, const cherry_tile* tiles, int n_tiles, int K,
+                    int S, uint32_t* counts, void* stream);
+
+/* out (fp64 [K][S][S]) = directed ? raw : (raw + raw^T) / 2. */
+int cherry_symmetrize_lg(const unsigned long long* raw, int K, int S, int directed,
+                         double* out, void* stream);
+/* n = S*S; Pi(S*i+j) = S*j+i.  out (fp64 [K][n][n]) =
+ * directed ? (R + Pi R Pi^T)/2 : (R + R^T + Pi R Pi^T + Pi R^T Pi^T)/4. */
+int cherry_symmetrize_co(const uint32_t* raw, int K, int S, int directed, double* out,
+                         void* stream);
+
+/* Host-buffer entry point (end-to-end path): every pointer is a HOST pointer (pinned
+ * memory makes the copies asynchronous).  Copies the batch to the device in family
+ * segments overlapped with counting, and writes the symmetrised fp64 counts [K][S][S]
+ * to counts_out on the host.  Synchronises before returning. */
+int cherry_count_lg_host(const uint8_t* msa, int64_t msa_bytes, const cherry_fam_desc* fams,
+                         int n_fams, const int32_t* pair_a, const int32_t* pair_b,
+                         const double* pair_t, const int32_t* pair_fam, int64_t n_pairs,
+                         const double* rate_vals, int64_t n_rate_vals,
+                         const uint16_t* group_cat, int64_t n_groups,
+                         const cherry_tile* tiles, int n_tiles, const double* grid, int K,
+                         int S, int r_pad, int directed, double* counts_out,
+                         int64_t* h2d_bytes, int64_t* d2h_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHERRYML_B200_H */
