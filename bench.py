@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path on synthetic Pfam-shaped data (BASELINE.json config 3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one counting pass over one batch: bucket table + LG transition histogram of
+F families x 1024 sequences x 300 sites into K=100 time buckets (+ the all-reduce of the raw
+integer histogram when N > 1, + symmetrisation).  Per-GPU work is fixed (weak scaling: every
+rank counts its own F families).  ``value`` = transitions examined per second with the batch
+resident in HBM; ``e2e`` = the same through the host-buffer C-ABI entry point
+(pinned host arrays -> H2D -> kernels -> D2H).  One JSON line is printed by rank 0.
+
+``--impl reference`` times the reference's own CPU implementation (the unmodified C++
+program compiled into oracle/_ref, one process per host core on the reference's own family
+striping; the C port of the oracle if the binary is absent) on a bounded sample of the same
+workload.
+"""
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "cherry transitions counted/s"
+UNIT = "transitions/s"
+N_SEQS, N_SITES, N_CATS, K_BUCKETS, N_STATES = 1024, 300, 4, 100, 20
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--families", type=int, default=16384, help="families per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-families", type=int, default=0, help="families in the CPU sample (0 = 2 per core, >= 32)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fit", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(families):
+    return (f"synthetic Pfam-scale LG: {families} families x {N_SEQS} seqs x {N_SITES} sites per GPU, "
+            f"{K_BUCKETS} time buckets, {N_CATS} site-rate categories")
+
+
+# ------------------------------------------------------------------ clocks sampling
+class ClockSampler:
+    """Samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-i", str(self.gpu_index), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons),
+            "samples": len(sm),
+        }
+
+
+# ------------------------------------------------------------ CPU reference / baseline
+def cpu_reference_run(n_families, seed=0, workdir=None):
+    """Time the reference's CPU counting on a bounded sample of the workload.
+
+    Returns dict(value, unit, cores, kind, sample, seconds).  Text rendering of the sample is
+    written before the timer starts (the reference consumes text); the timed region is the
+    reference programs themselves, text parsing included, as the reference does it."""
+    import numpy as np
+
+    from cherryml_b200.synthetic import (as_count_batch, quantization_grid, synthetic_lg,
+                                         write_text_rendering)
+    from cherryml_b200.utils import amino_acids
+
+    cores = os.cpu_count() or 1
+    grid = quantization_grid()
+    syn = synthetic_lg(n_families, N_SEQS, N_SITES, N_CATS, seed=seed, device="cpu")
+    examined = syn["n_sites_examined"]
+    ref_bin = os.path.join(REPO, "oracle", "_ref", "count_transitions")
+    if os.path.exists(ref_bin) and os.access(ref_bin, os.X_OK):
+        tmp = workdir or tempfile.mkdtemp(prefix="cherry_ref_")
+        try:
+            names = write_text_rendering(syn, tmp)
+            procs_n = min(cores, n_families)
+            cmds = []
+            for r in range(procs_n):
+                fam_r = names[r::procs_n]  # the reference's MPI striping (.cpp:624-629)
+                fpath = os.path.join(tmp, f"families_{r}.txt")
+                with open(fpath, "w") as f:
+                    f.write(" ".join(fam_r))
+                out = os.path.join(tmp, f"out_{r}")
+                os.makedirs(out, exist_ok=True)
+                cmds.append([ref_bin, os.path.join(tmp, "tree_dir"), os.path.join(tmp, "msa_dir"),
+                             os.path.join(tmp, "site_rates_dir"), str(len(fam_r)), str(N_STATES),
+                             str(len(grid)), fpath, *amino_acids, *[str(q) for q in grid], "cherry++", out])
+            t0 = time.perf_counter()
+            procs = [subprocess.Popen(c, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for c in cmds]
+            rcs = [p.wait() for p in procs]
+            seconds = time.perf_counter() - t0
+            if any(rcs):
+                raise RuntimeError(f"reference binary failed: {rcs}")
+            # sanity: the reference's summed output equals the oracle on the same sample
+            from oracle.counting_oracle import read_count_matrices_text
+            from oracle.native import count_batch_oracle
+
+            total = sum(read_count_matrices_text(os.path.join(tmp, f"out_{r}", "result.txt"))[2]
+                        for r in range(procs_n))
+            # the C++ program reads branch lengths as float32: compare totals only loosely
+            exp = count_batch_oracle(as_count_batch(syn), grid, N_STATES, False)
+            if abs(total.sum() - exp.sum()) > 1e-3 * exp.sum():
+                raise RuntimeError("reference output disagrees with the oracle on the sample")
+        finally:
+            if workdir is None:
+                shutil.rmtree(tmp, ignore_errors=True)
+        kind, used = "reference", procs_n
+        sample = (f"{n_families} of the workload's families ({examined} transitions), unmodified reference "
+                  f"C++ program, {procs_n} processes on the reference's family striping, text parsing included")
+    else:
+        from oracle.native import count_batch_oracle
+
+        batch = as_count_batch(syn)
+        t0 = time.perf_counter()
+        count_batch_oracle(batch, grid, N_STATES, False)
+        seconds = time.perf_counter() - t0
+        kind, used = "port", 1
+        sample = (f"{n_families} of the workload's families ({examined} transitions), scalar C port of the "
+                  "reference loop on pre-encoded arrays (no text parsing), 1 thread")
+    return {"value": examined / seconds, "unit": UNIT, "cores": used, "kind": kind, "sample": sample,
+            "seconds": seconds}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_fam = args.cpu_families or max(32, 2 * cores)
+    for _ in range(args.warmup):
+        cpu_reference_run(min(n_fam, max(8, cores)))
+    times, values, last = [], [], None
+    for _ in range(args.steps):
+        last = cpu_reference_run(n_fam)
+        times.append(last["seconds"])
+        values.append(last["value"])
+    value = sum(values) / len(values)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(args.families), "sample_families_per_step": n_fam},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"],
+                         "sample": last["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from cherryml_b200 import _lib
+    from cherryml_b200.counting._device import (build_bucket_table, count_lg_host, count_raw, sorted_grid,
+                                                 symmetrize)
+    from cherryml_b200.synthetic import as_count_batch, as_device_batch, quantization_grid, synthetic_lg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    lib = _lib.load()
+
+    F = args.families
+    grid = quantization_grid()
+    K, S = len(grid), N_STATES
+    syn = synthetic_lg(F, N_SEQS, N_SITES, N_CATS, seed=1000 + rank, device=device)
+    dev = as_device_batch(syn, device)
+    grid_dev = torch.from_numpy(sorted_grid(grid)).to(device)
+    examined = syn["n_sites_examined"]
+    stride = syn["shape"]["stride"]
+    n_pairs = dev.n_pairs
+    # algorithmic bytes of one counting launch: residues read once, site->category
+    # groups once per family, pair descriptors + bucket-table row per pair, one histogram flush
+    alg_bytes = (dev.msa.numel() + F * (stride // 4) * 2 + n_pairs * (8 + dev.r_pad) + K * S * S * 8)
+
+    raw = torch.zeros((K, S, S), dtype=torch.int64, device=device)
+    stream = torch.cuda.current_stream()
+
+    def step(ev=None):
+        raw.zero_()
+        tab = build_bucket_table(dev, grid_dev, K)
+        if ev is not None:
+            ev[0].record(stream)
+        count_raw(dev, grid_dev, K, S, tab=tab, out=raw)
+        if ev is not None:
+            ev[1].record(stream)
+        if world > 1:
+            dist.all_reduce(raw, op=dist.ReduceOp.SUM)
+        return symmetrize(raw, "lg", K, S, directed=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        counts = step()
+    barrier()
+    # parity gate inside the bench: a 32-family slice of this rank's batch against the oracle
+    parity = None
+    if rank == 0:
+        import copy
+
+        from oracle.native import count_batch_oracle
+
+        d3 = copy.copy(dev)
+        d3.n_tiles = 32 * (dev.n_tiles // F)
+        got = symmetrize(count_raw(d3, grid_dev, K, S), "lg", K, S, False).cpu().numpy()
+        host_slice = as_count_batch(dict(syn, msa=syn["msa"][: 32 * N_SEQS * stride]))
+        exp = count_batch_oracle(host_slice, grid, S, False, pair_slice=slice(0, 32 * (N_SEQS // 2)))
+        parity = bool(np.array_equal(got, exp))
+        if not parity:
+            raise SystemExit("bench.py: GPU counts differ from the oracle on the sample slice")
+
+    sampler = ClockSampler(local_rank)
+    _lib.reset_launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t_start.record(stream)
+    for i in range(args.steps):
+        counts = step(evs[i])
+    t_end.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.launch_count()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    if world > 1:
+        t = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, kernel_ms = float(t[0]), float(t[1])
+    ms_per_step = elapsed_ms / args.steps
+    value = examined * world / (ms_per_step * 1e-3)
+    counted = float(counts.sum().item())
+
+    # ---- e2e: host buffers through the C-ABI host entry point
+    e2e = None
+    host = as_count_batch(syn)
+    pinned = {}
+    for name in ("msa", "pair_a", "pair_b", "pair_t", "pair_fam"):
+        t = torch.from_numpy(getattr(host, name)).pin_memory()
+        pinned[name] = t
+        setattr(host, name, t.numpy())
+    for _ in range(2):
+        out, h2d, d2h = count_lg_host(host, grid, S, False)
+    if rank == 0 and world == 1:
+        assert np.array_equal(out, counts.cpu().numpy()), "host path and device path disagree"
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        out, h2d, d2h = count_lg_host(host, grid, S, False)
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e = {"value": examined * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
+           "note": "cherry_count_lg_host: pinned host arrays -> segmented H2D overlapped with counting -> D2H"}
+    del pinned
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "count_lg_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms}
+    traffic_file = os.path.join(REPO, "profiles", "count_lg_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(F), "l2": "inputs (>5 GB per GPU) larger than L2, no flush needed",
+                   "transitions_examined_per_step": examined * world,
+                   "transitions_counted_per_step_rank0": counted, "parity_slice_vs_oracle": parity},
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if not args.no_fit:
+        try:
+            from cherryml_b200.estimation import bench_fit
+
+            line["fit"] = bench_fit(device)
+        except ImportError:
+            pass
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        cb = cpu_reference_run(args.cpu_families or max(32, 2 * cores))
+        cb.pop("seconds", None)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

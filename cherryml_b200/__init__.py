@@ -1,0 +1,11 @@
+"""cherryml_b200: B200-native (sm_100a) implementation of CherryML's hot path.
+
+Transition counting into quantized-time count tensors and the batched matrix-exponential
+composite-likelihood fit of the rate matrix, behind CherryML's own Python API.  All compute
+runs in hand-written CUDA kernels reached through a C ABI (``include/cherryml_b200.h``);
+there is no CPU fallback.
+"""
+__version__ = "0.1.0"
+
+from . import caching  # noqa: F401
+from .counting import count_co_transitions, count_transitions  # noqa: F401

@@ -1,0 +1,1 @@
+from ._count_transitions import count_co_transitions, count_transitions, device_result  # noqa: F401

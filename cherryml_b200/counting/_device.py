@@ -192,3 +192,32 @@ def count_batch(
 
         dist.all_reduce(raw, op=dist.ReduceOp.SUM, group=process_group)
     return symmetrize(raw, batch.kind, K, num_states, directed)
+
+
+def count_lg_host(batch: CountBatch, quantization_points: Sequence[float], num_states: int,
+                  directed: bool):
+    """End-to-end LG counting from HOST buffers through ``cherry_count_lg_host``.
+
+    ``batch`` arrays may be numpy arrays or (pinned) CPU torch tensors viewed as numpy.
+    Returns ``(counts fp64 [K,S,S] numpy, h2d_bytes, d2h_bytes)``.  The copies, the kernels
+    and the read-back all happen inside the call.
+    """
+    import ctypes
+
+    if batch.kind != "lg":
+        raise ValueError("count_lg_host takes an LG batch")
+    lib = _lib.load()
+    grid = sorted_grid(quantization_points)
+    K, S = int(grid.size), int(num_states)
+    out = np.empty((K, S, S), dtype=np.float64)
+    h2d, d2h = ctypes.c_int64(0), ctypes.c_int64(0)
+    rc = lib.cherry_count_lg_host(
+        _lib.ptr(batch.msa), int(batch.msa.size), _lib.ptr(batch.fams), int(batch.fams.shape[0]),
+        _lib.ptr(batch.pair_a), _lib.ptr(batch.pair_b), _lib.ptr(batch.pair_t), _lib.ptr(batch.pair_fam),
+        int(batch.pair_a.shape[0]), _lib.ptr(batch.rate_vals), int(batch.rate_vals.shape[0]),
+        _lib.ptr(batch.aux), int(batch.aux.shape[0]), _lib.ptr(batch.tiles), int(batch.tiles.shape[0]),
+        _lib.ptr(grid), K, S, int(batch.r_pad), int(directed), _lib.ptr(out),
+        ctypes.addressof(h2d), ctypes.addressof(d2h),
+    )
+    _lib.check(rc, "cherry_count_lg_host")
+    return out, int(h2d.value), int(d2h.value)

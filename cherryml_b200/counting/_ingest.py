@@ -291,11 +291,15 @@ def encode_lg_family(
     pairs = extract_pairs(tree, edge_or_cherry, float32_branch_lengths)
     names, a, b, t = _rows_for_pairs(pairs)
     enc = _encode_rows(msa, names, lut, name)
-    L = len(site_rates)
-    if enc.shape[0] and enc.shape[1] != L:
+    if enc.shape[0] and enc.shape[1] > len(site_rates):
         raise Exception(
-            f"Family {name}: MSA has {enc.shape[1]} sites but there are {L} site rates"
+            f"Family {name}: MSA has {enc.shape[1]} sites but there are only "
+            f"{len(site_rates)} site rates"
         )
+    if enc.shape[0]:
+        # the reference indexes site_rates by MSA position, so surplus rates are ignored
+        site_rates = list(site_rates)[: enc.shape[1]]
+    L = len(site_rates)
     vals, dest, group_cat, stride = lg_column_layout(site_rates) if L else (
         np.ones(1), np.zeros(0, dtype=np.int64), np.zeros(4, dtype=np.uint16), 16)
     rows = np.full((enc.shape[0], stride), INVALID_RESIDUE, dtype=np.uint8)

@@ -1,0 +1,215 @@
+"""GPU parity tests for counting: the CUDA path (through the C ABI and the public stage
+functions) against the reference goldens and the oracle.  Bit-exact: integer/byte work."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from cherryml_b200 import _lib, caching
+from cherryml_b200.counting import count_co_transitions, count_transitions, device_result
+from cherryml_b200.counting._device import (count_batch, count_lg_host, count_raw, sorted_grid,
+                                             symmetrize, to_device)
+from cherryml_b200.io import read_count_matrices_array
+from cherryml_b200.synthetic import (as_count_batch, as_device_batch, quantization_grid, synthetic_co,
+                                     synthetic_lg)
+from cherryml_b200.utils import amino_acids
+from oracle.counting_oracle import read_count_matrices_text
+from oracle.native import count_batch_oracle
+from tests.test_oracle_counting import CO_CASES, GRID_CO, GRID_LG, LG_CASES, MEDIUM3, MODES
+
+
+@pytest.mark.parametrize("case", LG_CASES, ids=lambda c: f"{c[0]}-{c[4]}")
+@pytest.mark.parametrize("use_cpp", [True, False])
+def test_count_transitions_reference_tiny_goldens(golden_counting, tmp_path, case, use_cpp):
+    ds, fams, aa, grid, mode, gdir = case
+    root = os.path.join(golden_counting, ds)
+    out = str(tmp_path / "out")
+    count_transitions(
+        tree_dir=f"{root}/tree_dir", msa_dir=f"{root}/msa_dir", site_rates_dir=f"{root}/site_rates_dir",
+        families=fams, amino_acids=aa, quantization_points=grid, edge_or_cherry=mode,
+        output_count_matrices_dir=out, num_processes=3, use_cpp_implementation=use_cpp,
+    )
+    q, states, counts = read_count_matrices_array(os.path.join(out, "result.txt"))
+    gq, gstates, gcounts = read_count_matrices_text(os.path.join(golden_counting, ds, gdir, "result.txt"))
+    assert np.allclose(q, gq) and states == gstates
+    assert np.array_equal(counts, gcounts)
+    assert open(os.path.join(out, "profiling.txt")).read().split()[2].replace(".", "").replace("e-", "").isdigit()
+
+
+@pytest.mark.parametrize("case", CO_CASES, ids=lambda c: f"{c[0]}-{c[4]}")
+def test_count_co_transitions_reference_tiny_goldens(golden_counting, tmp_path, case):
+    ds, fams, aa, grid, mode, gdir = case
+    root = os.path.join(golden_counting, ds)
+    out = str(tmp_path / "out")
+    count_co_transitions(
+        tree_dir=f"{root}/tree_dir", msa_dir=f"{root}/msa_dir", contact_map_dir=f"{root}/contact_map_dir",
+        families=fams, amino_acids=aa, quantization_points=grid, edge_or_cherry=mode,
+        minimum_distance_for_nontrivial_contact=2, output_count_matrices_dir=out, num_processes=2,
+    )
+    q, states, counts = read_count_matrices_array(os.path.join(out, "result.txt"))
+    gq, gstates, gcounts = read_count_matrices_text(os.path.join(golden_counting, ds, gdir, "result.txt"))
+    assert np.allclose(q, gq) and states == gstates
+    assert np.array_equal(counts, gcounts)
+
+
+@pytest.mark.parametrize("mode,tag,msa_sub", MODES)
+@pytest.mark.parametrize("personality", ["cpp", "py"])
+def test_count_transitions_medium3_vs_reference_run(golden_counting, tmp_path, mode, tag, msa_sub, personality):
+    m3 = os.path.join(golden_counting, "medium3")
+    out = str(tmp_path / "out")
+    count_transitions(
+        tree_dir=f"{m3}/tree_dir", msa_dir=f"{m3}/{msa_sub}", site_rates_dir=f"{m3}/site_rates_dir",
+        families=MEDIUM3, amino_acids=amino_acids, quantization_points=GRID_LG, edge_or_cherry=mode,
+        output_count_matrices_dir=out, use_cpp_implementation=(personality == "cpp"),
+    )
+    golden_path = f"{m3}/ref{personality}_count_matrices_dir_{tag}/result.txt"
+    _, _, gcounts = read_count_matrices_text(golden_path)
+    _, _, counts = read_count_matrices_array(os.path.join(out, "result.txt"))
+    assert np.array_equal(counts, gcounts)
+    # the written file is byte-identical to what the reference program wrote
+    assert open(os.path.join(out, "result.txt")).read() == open(golden_path).read()
+    grid, states, dev = device_result(out)
+    assert np.array_equal(dev.cpu().numpy(), gcounts)
+
+
+@pytest.mark.parametrize("mode,tag,msa_sub", MODES)
+def test_count_co_transitions_medium3_vs_reference_run(golden_counting, tmp_path, mode, tag, msa_sub):
+    m3 = os.path.join(golden_counting, "medium3")
+    out = str(tmp_path / "out")
+    count_co_transitions(
+        tree_dir=f"{m3}/tree_dir", msa_dir=f"{m3}/{msa_sub}", contact_map_dir=f"{m3}/contact_map_dir",
+        families=MEDIUM3, amino_acids=amino_acids, quantization_points=GRID_CO, edge_or_cherry=mode,
+        minimum_distance_for_nontrivial_contact=7, output_count_matrices_dir=out,
+    )
+    gcounts = np.load(f"{m3}/refcpp_count_co_matrices_dir_{tag}/result.npz")["counts"]
+    _, _, dev = device_result(out)
+    assert np.array_equal(dev.cpu().numpy(), gcounts)
+    _, _, counts = read_count_matrices_array(os.path.join(out, "result.txt"))
+    assert np.array_equal(counts, gcounts)  # every cell < 1e6, so 6 significant digits are exact
+
+
+def test_cache_dir_semantics(golden_counting, tmp_path):
+    root = os.path.join(golden_counting, "tiny")
+    kw = dict(tree_dir=f"{root}/tree_dir", msa_dir=f"{root}/msa_dir", site_rates_dir=f"{root}/site_rates_dir",
+              families=["fam1", "fam2", "fam3"], amino_acids=["I", "L", "S", "T"],
+              quantization_points=[1.99, 10.01], edge_or_cherry="cherry")
+    with pytest.raises(caching.CacheUsageError):
+        count_transitions(kw["tree_dir"], **{k: v for k, v in kw.items() if k != "tree_dir"})
+    caching.set_cache_dir(str(tmp_path / "cache"))
+    try:
+        res = count_transitions(**kw)
+        out = res["output_count_matrices_dir"]
+        assert os.path.exists(os.path.join(out, "result.success"))
+        mtime = os.path.getmtime(os.path.join(out, "result.txt"))
+        res2 = count_transitions(**kw, num_processes=7)  # excluded arg: same key, cached
+        assert res2 == res and os.path.getmtime(os.path.join(out, "result.txt")) == mtime
+    finally:
+        caching.set_cache_dir(None)
+
+
+@pytest.mark.parametrize("n_cats,K", [(4, 100), (20, 129), (1, 7)])
+def test_lg_synthetic_vs_oracle(n_cats, K):
+    grid = quantization_grid(lo=-(K // 2), hi=K - K // 2 - 1)
+    assert len(grid) == K
+    syn = synthetic_lg(48, 256, 300, n_cats, seed=11)
+    batch = as_count_batch(syn)
+    exp = count_batch_oracle(batch, grid, 20, False)
+    got = count_batch(batch, grid, 20, directed=False).cpu().numpy()
+    assert np.array_equal(got, exp)
+    got_dir = count_batch(batch, grid, 20, directed=True).cpu().numpy()
+    assert np.array_equal(got_dir, count_batch_oracle(batch, grid, 20, True))
+    host, h2d, d2h = count_lg_host(batch, grid, 20, False)
+    assert np.array_equal(host, exp) and h2d > batch.msa.size and d2h == exp.nbytes
+
+
+def test_lg_histogram_too_large_for_shared_memory_falls_back_to_global_atomics():
+    grid = [float("%.8f" % (0.001 * 1.05**i)) for i in range(200)]  # 200*400*4 B = 320 KB > 227 KB
+    syn = synthetic_lg(8, 128, 150, 4, seed=5)
+    batch = as_count_batch(syn)
+    got = count_batch(batch, grid, 20, directed=False).cpu().numpy()
+    assert np.array_equal(got, count_batch_oracle(batch, grid, 20, False))
+
+
+def test_lg_ragged_shapes_and_small_alphabet():
+    """Families of different sizes in one batch, 4-letter alphabet (others become skips)."""
+    from cherryml_b200.counting._ingest import _BatchBuilder, lg_column_layout
+
+    rng = np.random.default_rng(2)
+    builder = _BatchBuilder("lg")
+    for f, (n_rows, L) in enumerate([(2, 1), (6, 17), (40, 333), (10, 64), (2, 1500)]):
+        rates = rng.choice([0.25, 1.0, 3.0], size=L)
+        vals, dest, group_cat, stride = lg_column_layout(rates)
+        rows = np.full((n_rows, stride), 255, dtype=np.uint8)
+        rows[:, dest] = rng.integers(0, 6, size=(n_rows, L)).astype(np.uint8)  # 4,5 are invalid for S=4
+        a = np.arange(0, n_rows, 2, dtype=np.int32)
+        builder.add_family(f"f{f}", rows, a, a + 1, rng.lognormal(-0.5, 1.0, len(a)), vals, group_cat, stride // 4, L)
+    batch = builder.finish()
+    grid = [0.05 * 1.3**i for i in range(20)]
+    got = count_batch(batch, grid, 4, directed=False).cpu().numpy()
+    assert np.array_equal(got, count_batch_oracle(batch, grid, 4, False))
+    assert got.sum() > 0
+
+
+def test_empty_batch():
+    from cherryml_b200.counting._ingest import _BatchBuilder
+
+    for kind, shape in (("lg", (3, 20, 20)), ("co", (3, 400, 400))):
+        got = count_batch(_BatchBuilder(kind).finish(), [0.1, 1.0, 2.0], 20, directed=False)
+        assert tuple(got.shape) == shape and float(got.sum()) == 0.0
+
+
+def test_co_synthetic_vs_oracle():
+    grid = quantization_grid()
+    syn = synthetic_co(24, 128, 200, seed=13)
+    batch = as_count_batch(syn)
+    for directed in (False, True):
+        got = count_batch(batch, grid, 20, directed=directed).cpu().numpy()
+        assert np.array_equal(got, count_batch_oracle(batch, grid, 20, directed))
+
+
+def test_too_many_quantization_points_is_an_error():
+    syn = synthetic_lg(2, 8, 32, 4, seed=1)
+    with pytest.raises(_lib.CherryError):
+        count_batch(as_count_batch(syn), [0.001 * 1.01**i for i in range(300)], 20, directed=False)
+
+
+def test_full_size_properties_lg():
+    """BASELINE config-3 shape on one GPU slice (2048 families x 1024 x 300): size-independent
+    properties -- conservation (every valid, in-grid site counted once), symmetry, linearity
+    over a split of the families, and agreement of a 64-family slice with the oracle."""
+    grid = quantization_grid()
+    K = len(grid)
+    syn = synthetic_lg(2048, 1024, 300, 4, seed=3, device="cuda")
+    dev = as_device_batch(syn, "cuda")
+    grid_dev = torch.from_numpy(sorted_grid(grid)).cuda()
+    raw = count_raw(dev, grid_dev, K, 20)
+    total = int(raw.sum().item())
+    # conservation, computed independently with torch ops on the device
+    n_pairs, stride = 512, syn["shape"]["stride"]
+    rows = syn["msa"].view(2048, n_pairs, 2, stride)
+    valid = (rows[:, :, 0, :] < 20) & (rows[:, :, 1, :] < 20)
+    rates = torch.from_numpy(syn["rate_vals"][:4]).cuda()
+    cat = torch.from_numpy(syn["aux"][: stride // 4].astype(np.int64)).cuda().repeat_interleave(4)
+    tt = syn["pair_t"].view(2048, n_pairs, 1) * rates[cat].view(1, 1, stride)
+    in_grid = (tt >= grid[0]) & (tt <= grid[-1])
+    assert total == int((valid & in_grid).sum().item())
+    sym = symmetrize(raw, "lg", K, 20, directed=False)
+    assert torch.equal(sym, sym.transpose(1, 2)) and float(sym.sum().item()) == float(total)
+    # linearity: counts(first half of the tiles) + counts(second half) == counts(all)
+    import copy
+    half = dev.n_tiles // 2
+    d1, d2 = copy.copy(dev), copy.copy(dev)
+    d1.n_tiles = half
+    d2.tiles, d2.n_tiles = dev.tiles[half * 16:], dev.n_tiles - half
+    assert torch.equal(count_raw(d1, grid_dev, K, 20) + count_raw(d2, grid_dev, K, 20), raw)
+    # a 64-family slice against the oracle
+    batch = as_count_batch(syn)
+    sl = slice(0, 64 * n_pairs)
+    exp = count_batch_oracle(batch, grid, 20, False, pair_slice=sl)
+    d3 = copy.copy(dev)
+    d3.n_tiles = 64 * (dev.n_tiles // 2048)
+    got = symmetrize(count_raw(d3, grid_dev, K, 20), "lg", K, 20, False).cpu().numpy()
+    assert np.array_equal(got, exp)
