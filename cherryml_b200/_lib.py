@@ -37,7 +37,7 @@ TILE_DTYPE = np.dtype(
 assert FAM_DESC_DTYPE.itemsize == 32 and TILE_DTYPE.itemsize == 16
 
 NO_BUCKET = 255
-INVALID_RESIDUE = 255
+# The skip code of a residue byte is the number of states S itself (bytes are in [0, S]).
 MAX_BUCKETS = 254
 
 
@@ -54,6 +54,7 @@ _SIGNATURES = {
     "cherry_build_bucket_table": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, _P]),
     "cherry_count_lg": (c_int, [_P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P]),
     "cherry_count_co": (c_int, [_P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "cherry_validate_residues": (c_int, [_P, c_int64, c_int, _P, _P]),
     "cherry_symmetrize_lg": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "cherry_symmetrize_co": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "cherry_count_lg_host": (

@@ -91,6 +91,22 @@ def sorted_grid(quantization_points: Sequence[float]) -> np.ndarray:
     return grid
 
 
+def validate_residues(msa: torch.Tensor, num_states: int) -> None:
+    """Raise unless every residue byte is <= num_states (the skip code)."""
+    lib = _lib.load()
+    n = msa.numel() // 16 * 16
+    flag = torch.zeros(1, dtype=torch.int32, device=msa.device)
+    rc = lib.cherry_validate_residues(_lib.ptr(msa), n, int(num_states), _lib.ptr(flag),
+                                      _lib.current_stream_ptr())
+    _lib.check(rc, "cherry_validate_residues")
+    bad_tail = bool((msa[n:] > num_states).any().item()) if n < msa.numel() else False
+    if int(flag.item()) != 0 or bad_tail:
+        raise _lib.CherryError(
+            f"residue buffer holds bytes > {num_states}: encode with the same alphabet that is "
+            "passed to the counting call (skip code == number of states)"
+        )
+
+
 def build_bucket_table(dev: DeviceBatch, grid_dev: torch.Tensor, K: int) -> torch.Tensor:
     lib = _lib.load()
     tab = torch.empty(max(1, dev.n_pairs * dev.r_pad), dtype=torch.uint8, device=dev.msa.device)
@@ -185,6 +201,7 @@ def count_batch(
     grid = sorted_grid(quantization_points)
     K = int(grid.size)
     dev = to_device(batch, device)
+    validate_residues(dev.msa, num_states)
     grid_dev = torch.from_numpy(grid).to(dev.msa.device)
     raw = count_raw(dev, grid_dev, K, num_states)
     if process_group is not None:

@@ -23,7 +23,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .._lib import FAM_DESC_DTYPE, INVALID_RESIDUE, TILE_DTYPE
+from .._lib import FAM_DESC_DTYPE, TILE_DTYPE
 from ..io import Tree, read_contact_map, read_msa, read_site_rates, read_tree
 
 TARGET_CHUNKS_PER_TILE = 16384  # ~16 loop trips of a 1024-thread CTA
@@ -97,9 +97,10 @@ def contacting_pairs(contact_map: np.ndarray, minimum_distance: int) -> np.ndarr
 
 
 def alphabet_lut(states: Sequence[str]) -> np.ndarray:
-    lut = np.full(256, INVALID_RESIDUE, dtype=np.uint8)
-    if len(states) > 255:
-        raise ValueError("at most 255 states are supported")
+    if len(states) > 254:
+        raise ValueError("at most 254 states are supported")
+    # every byte that is not a state maps to the skip code S == len(states)
+    lut = np.full(256, len(states), dtype=np.uint8)
     for i, s in enumerate(states):
         if len(s) != 1 or ord(s) > 255:
             raise ValueError(f"states must be single one-byte characters, got {s!r}")
@@ -211,7 +212,7 @@ class _BatchBuilder:
             r_pad = 4
         msa = cat(self.msa_parts, np.uint8)
         if msa.size == 0:
-            msa = np.full(16, INVALID_RESIDUE, dtype=np.uint8)
+            msa = np.zeros(16, dtype=np.uint8)
         return CountBatch(
             kind=self.kind,
             msa=msa,
@@ -302,7 +303,7 @@ def encode_lg_family(
     L = len(site_rates)
     vals, dest, group_cat, stride = lg_column_layout(site_rates) if L else (
         np.ones(1), np.zeros(0, dtype=np.int64), np.zeros(4, dtype=np.uint16), 16)
-    rows = np.full((enc.shape[0], stride), INVALID_RESIDUE, dtype=np.uint8)
+    rows = np.full((enc.shape[0], stride), int(lut.max()), dtype=np.uint8)
     if enc.shape[0] and L:
         rows[:, dest] = enc
     builder.add_family(name, rows, a, b, t, vals, group_cat, stride // 4, L)
@@ -327,7 +328,7 @@ def encode_co_family(
     if len(contacts) and contacts.max() >= L:
         raise Exception(f"Family {name}: contact map is larger than the MSA")
     stride = max(16, (L + 15) // 16 * 16)
-    rows = np.full((enc.shape[0], stride), INVALID_RESIDUE, dtype=np.uint8)
+    rows = np.full((enc.shape[0], stride), int(lut.max()), dtype=np.uint8)
     if enc.shape[0]:
         rows[:, :L] = enc
     builder.add_family(name, rows, a, b, t, np.ones(1), contacts, len(contacts), len(contacts))

@@ -70,19 +70,11 @@ __global__ void bucket_table_kernel(const double* __restrict__ pair_t,
   }
 }
 
-template <bool SMEM>
-__device__ __forceinline__ void add_bin(uint32_t* h32, unsigned long long* h64, int idx) {
-  if (SMEM) atomicAdd(h32 + idx, 1u);
-  else atomicAdd(h64 + idx, 1ull);
-}
-
-// One aligned 32-bit word = 4 sites of one rate category.
-template <bool SMEM>
-__device__ __forceinline__ void count_word(uint32_t* h32, unsigned long long* h64, uint32_t wa,
-                                           uint32_t wb, uint32_t bucket, int S, int SS,
-                                           uint32_t S4) {
+// ---- global-atomics fallback (histogram larger than shared memory) ----
+__device__ __forceinline__ void count_word_global(unsigned long long* h64, uint32_t wa, uint32_t wb,
+                                                  uint32_t bucket, int S, int SS, uint32_t S4) {
   if (bucket == CHERRY_NO_BUCKET) return;
-  uint32_t m = __vcmpltu4(wa, S4) & __vcmpltu4(wb, S4);  // 0xff per site with both residues valid
+  uint32_t m = __vcmpltu4(wa, S4) & __vcmpltu4(wb, S4);
   if (m == 0) return;
   const int base = (int)bucket * SS;
 #pragma unroll
@@ -90,32 +82,73 @@ __device__ __forceinline__ void count_word(uint32_t* h32, unsigned long long* h6
     if (m & (0x80u << (8 * k))) {
       int x = (wa >> (8 * k)) & 0xff;
       int y = (wb >> (8 * k)) & 0xff;
-      add_bin<SMEM>(h32, h64, base + x * S + y);
+      atomicAdd(h64 + base + x * S + y, 1ull);
     }
   }
 }
 
-template <bool SMEM>
-__device__ __forceinline__ void count_item(uint32_t* h32, unsigned long long* h64, const uint4& va,
+// ---- shared-memory path: branch-free per site ----
+// One aligned 32-bit word = 4 sites of one rate category.  The shared histogram has S+1
+// states per axis: the skip code of a residue byte is S itself (gap, unknown letter,
+// padding; the encoder guarantees no byte exceeds S), so EVERY site does an unconditional
+// increment (which ptxas turns into ATOMS.POPC.INC) and the junk row/column is dropped at
+// flush time.  Per site: two byte extracts, two multiply-adds, one shared-memory
+// reduction; no branch, no validity test.
+// `sbase` = 32-bit shared address of the histogram; row4 = 4*(S+1), bucket4 = 4*(S+1)^2.
+__device__ __forceinline__ void count_word_smem(uint32_t sbase, uint32_t wa, uint32_t wb,
+                                                uint32_t bucket, uint32_t row4, uint32_t bucket4,
+                                                uint32_t S4) {
+  if (bucket == CHERRY_NO_BUCKET) return;
+  const uint32_t rowbase = sbase + bucket * bucket4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t x = __byte_perm(wa, 0, 0x4440 | k);
+    const uint32_t y = __byte_perm(wb, 0, 0x4440 | k);
+    const uint32_t addr = rowbase + x * row4 + y * 4u;
+    asm volatile("red.shared.add.u32 [%0], 1;" : : "r"(addr) : "memory");
+  }
+}
+
+// R4: the bucket-table row is exactly 4 bytes (<= 4 rate categories): one 32-bit load and a
+// byte select per word instead of four byte loads.
+template <bool SMEM, bool R4>
+__device__ __forceinline__ void count_item(uint32_t sbase, unsigned long long* h64, const uint4& va,
                                            const uint4& vb, const uint2& g,
                                            const uint8_t* __restrict__ trow, int S, int SS,
-                                           uint32_t S4) {
-  uint32_t b0 = __ldg(trow + (g.x & 0xffffu));
-  uint32_t b1 = __ldg(trow + (g.x >> 16));
-  uint32_t b2 = __ldg(trow + (g.y & 0xffffu));
-  uint32_t b3 = __ldg(trow + (g.y >> 16));
-  count_word<SMEM>(h32, h64, va.x, vb.x, b0, S, SS, S4);
-  count_word<SMEM>(h32, h64, va.y, vb.y, b1, S, SS, S4);
-  count_word<SMEM>(h32, h64, va.z, vb.z, b2, S, SS, S4);
-  count_word<SMEM>(h32, h64, va.w, vb.w, b3, S, SS, S4);
+                                           uint32_t row4, uint32_t bucket4, uint32_t S4) {
+  uint32_t b0, b1, b2, b3;
+  if (R4) {
+    const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(trow));
+    b0 = __byte_perm(t, 0, 0x4440u | (g.x & 0xffffu));
+    b1 = __byte_perm(t, 0, 0x4440u | (g.x >> 16));
+    b2 = __byte_perm(t, 0, 0x4440u | (g.y & 0xffffu));
+    b3 = __byte_perm(t, 0, 0x4440u | (g.y >> 16));
+  } else {
+    b0 = __ldg(trow + (g.x & 0xffffu));
+    b1 = __ldg(trow + (g.x >> 16));
+    b2 = __ldg(trow + (g.y & 0xffffu));
+    b3 = __ldg(trow + (g.y >> 16));
+  }
+  if (SMEM) {
+    count_word_smem(sbase, va.x, vb.x, b0, row4, bucket4, S4);
+    count_word_smem(sbase, va.y, vb.y, b1, row4, bucket4, S4);
+    count_word_smem(sbase, va.z, vb.z, b2, row4, bucket4, S4);
+    count_word_smem(sbase, va.w, vb.w, b3, row4, bucket4, S4);
+  } else {
+    count_word_global(h64, va.x, vb.x, b0, S, SS, S4);
+    count_word_global(h64, va.y, vb.y, b1, S, SS, S4);
+    count_word_global(h64, va.z, vb.z, b2, S, SS, S4);
+    count_word_global(h64, va.w, vb.w, b3, S, SS, S4);
+  }
 }
 
 // Persistent: gridDim.x CTAs stride over tiles.  A work item is one 16-byte chunk (16
 // sites) of one pair; consecutive threads take consecutive chunks, so a warp reads runs of
-// contiguous bytes from the two rows.  SMEM=true: the whole [K][S][S] histogram lives in
-// shared memory as uint32 and is flushed once; SMEM=false (histogram too large): global
-// uint64 atomics.
-template <bool SMEM>
+// contiguous bytes from the two rows.  Each thread keeps (pair, chunk) of its two in-flight
+// items and advances them incrementally (no division in the loop).  SMEM=true: the whole
+// [K][S][S] histogram lives in shared memory as uint32 and is flushed once; SMEM=false
+// (histogram too large): global uint64 atomics.
+template <bool SMEM, bool R4>
 __global__ void __launch_bounds__(kCountThreads, 1)
 count_lg_kernel(const uint8_t* __restrict__ msa, const cherry_fam_desc* __restrict__ fams,
                 const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b,
@@ -124,9 +157,12 @@ count_lg_kernel(const uint8_t* __restrict__ msa, const cherry_fam_desc* __restri
                 int n_tiles, int K, int S, unsigned long long* __restrict__ counts) {
   extern __shared__ uint32_t hist[];
   const int SS = S * S;
-  const int nbins = K * SS;
+  const int S1 = S + 1;
+  const int nbins = K * S1 * S1;  // shared histogram: S+1 states per axis (state S = skip)
   const int tid = threadIdx.x;
   const uint32_t S4 = (uint32_t)S * 0x01010101u;
+  const uint32_t row4 = 4u * S1, bucket4 = 4u * S1 * S1;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(hist);
   if (SMEM) {
     for (int i = tid; i < nbins; i += kCountThreads) hist[i] = 0;
     __syncthreads();
@@ -139,30 +175,37 @@ count_lg_kernel(const uint8_t* __restrict__ msa, const cherry_fam_desc* __restri
     const uint32_t nch = (uint32_t)fd.n_chunks;
     const uint32_t n_items = (uint32_t)tl.n_pairs * nch;
     const int64_t stride = fd.row_stride;
+    // per-thread (pair, chunk) cursors for items tid and tid + T, each advancing by 2T
+    const uint32_t dq = (2 * kCountThreads) / nch, dr = (2 * kCountThreads) - dq * nch;
+    uint32_t pl0 = (uint32_t)tid / nch, ch0 = (uint32_t)tid - pl0 * nch;
+    uint32_t pl1 = (uint32_t)(tid + kCountThreads) / nch, ch1 = (uint32_t)(tid + kCountThreads) - pl1 * nch;
     for (uint32_t i = tid; i < n_items; i += 2 * kCountThreads) {
-      // two items in flight per thread
-      const uint32_t i1 = i + kCountThreads;
-      const bool has1 = i1 < n_items;
-      uint32_t pl0 = i / nch, ch0 = i - pl0 * nch;
-      uint32_t pl1 = has1 ? i1 / nch : pl0, ch1 = has1 ? i1 - pl1 * nch : ch0;
-      const int p0 = tl.pair_begin + (int)pl0, p1 = tl.pair_begin + (int)pl1;
+      const bool has1 = i + kCountThreads < n_items;
+      const uint32_t q1 = has1 ? pl1 : pl0, c1 = has1 ? ch1 : ch0;
+      const int p0 = tl.pair_begin + (int)pl0, p1 = tl.pair_begin + (int)q1;
       const int a0 = __ldg(pair_a + p0), b0 = __ldg(pair_b + p0);
       const int a1 = __ldg(pair_a + p1), b1 = __ldg(pair_b + p1);
       uint4 va0 = ld_stream16(base + a0 * stride + ch0 * 16);
       uint4 vb0 = ld_stream16(base + b0 * stride + ch0 * 16);
-      uint4 va1 = ld_stream16(base + a1 * stride + ch1 * 16);
-      uint4 vb1 = ld_stream16(base + b1 * stride + ch1 * 16);
+      uint4 va1 = ld_stream16(base + a1 * stride + c1 * 16);
+      uint4 vb1 = ld_stream16(base + b1 * stride + c1 * 16);
       uint2 g0 = __ldg(reinterpret_cast<const uint2*>(gc + ch0 * 4));
-      uint2 g1 = __ldg(reinterpret_cast<const uint2*>(gc + ch1 * 4));
-      count_item<SMEM>(hist, counts, va0, vb0, g0, tab + (int64_t)p0 * r_pad, S, SS, S4);
+      uint2 g1 = __ldg(reinterpret_cast<const uint2*>(gc + c1 * 4));
+      count_item<SMEM, R4>(sbase, counts, va0, vb0, g0, tab + (int64_t)p0 * r_pad, S, SS, row4, bucket4, S4);
       if (has1)
-        count_item<SMEM>(hist, counts, va1, vb1, g1, tab + (int64_t)p1 * r_pad, S, SS, S4);
+        count_item<SMEM, R4>(sbase, counts, va1, vb1, g1, tab + (int64_t)p1 * r_pad, S, SS, row4, bucket4, S4);
+      pl0 += dq; ch0 += dr;
+      if (ch0 >= nch) { ch0 -= nch; ++pl0; }
+      pl1 += dq; ch1 += dr;
+      if (ch1 >= nch) { ch1 -= nch; ++pl1; }
     }
   }
   if (SMEM) {
     __syncthreads();
-    for (int i = tid; i < nbins; i += kCountThreads) {
-      uint32_t v = hist[i];
+    for (int i = tid; i < K * SS; i += kCountThreads) {
+      const int b = i / SS, r = i - b * SS;
+      const int x = r / S, y = r - x * S;
+      const uint32_t v = hist[(b * S1 + x) * S1 + y];
       if (v) atomicAdd(counts + i, (unsigned long long)v);
     }
   }
@@ -203,6 +246,18 @@ count_co_kernel(const uint8_t* __restrict__ msa, const cherry_fam_desc* __restri
       }
     }
   }
+}
+
+// flag[0] |= 1 if any residue byte exceeds S (contract violation).
+__global__ void validate_residues_kernel(const uint4* __restrict__ msa, int64_t n_vec, uint32_t S4,
+                                         int* __restrict__ flag) {
+  bool bad = false;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_vec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = msa[i];
+    bad |= (__vcmpgtu4(v.x, S4) | __vcmpgtu4(v.y, S4) | __vcmpgtu4(v.z, S4) | __vcmpgtu4(v.w, S4)) != 0;
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
 __global__ void symmetrize_lg_kernel(const unsigned long long* __restrict__ raw, int K, int S,
@@ -251,7 +306,7 @@ int check_count_args(const void* msa, const void* fams, const void* pa, const vo
   if (n_tiles < 0 || r_pad <= 0) return cherry::fail(CHERRY_EINVAL, "count: bad n_tiles/r_pad");
   if (K <= 0 || K > CHERRY_MAX_BUCKETS)
     return cherry::fail(CHERRY_ELIMIT, "count: K=%d outside 1..%d", K, CHERRY_MAX_BUCKETS);
-  if (S <= 0 || S > 255) return cherry::fail(CHERRY_ELIMIT, "count: S=%d outside 1..255", S);
+  if (S <= 0 || S > 254) return cherry::fail(CHERRY_ELIMIT, "count: S=%d outside 1..254", S);
   return 0;
 }
 
@@ -287,22 +342,29 @@ int cherry_count_lg(const uint8_t* msa, const cherry_fam_desc* fams, const int32
   if (rc) return rc;
   if (!group_cat) return cherry::fail(CHERRY_EINVAL, "count_lg: null group_cat");
   if (n_tiles == 0) return 0;
-  const size_t hist_bytes = (size_t)K * S * S * sizeof(uint32_t);
+  const size_t hist_bytes = (size_t)K * (S + 1) * (S + 1) * sizeof(uint32_t);
   int grid = cherry::sm_count();
   if (grid > n_tiles) grid = n_tiles;
+  const bool r4 = (r_pad == 4);
   if (hist_bytes <= (size_t)kMaxSmemBytes) {
     static bool attr_set[64] = {false};
     int dev = 0;
     CHERRY_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !attr_set[dev]) {
-      CHERRY_CUDA(cudaFuncSetAttribute(count_lg_kernel<true>,
+      CHERRY_CUDA(cudaFuncSetAttribute(count_lg_kernel<true, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
+      CHERRY_CUDA(cudaFuncSetAttribute(count_lg_kernel<true, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
       attr_set[dev] = true;
     }
-    count_lg_kernel<true><<<grid, kCountThreads, hist_bytes, (cudaStream_t)stream>>>(
-        msa, fams, pair_a, pair_b, tab, r_pad, group_cat, tiles, n_tiles, K, S, counts);
+    if (r4)
+      count_lg_kernel<true, true><<<grid, kCountThreads, hist_bytes, (cudaStream_t)stream>>>(
+          msa, fams, pair_a, pair_b, tab, r_pad, group_cat, tiles, n_tiles, K, S, counts);
+    else
+      count_lg_kernel<true, false><<<grid, kCountThreads, hist_bytes, (cudaStream_t)stream>>>(
+          msa, fams, pair_a, pair_b, tab, r_pad, group_cat, tiles, n_tiles, K, S, counts);
   } else {
-    count_lg_kernel<false><<<grid, kCountThreads, 0, (cudaStream_t)stream>>>(
+    count_lg_kernel<false, false><<<grid, kCountThreads, 0, (cudaStream_t)stream>>>(
         msa, fams, pair_a, pair_b, tab, r_pad, group_cat, tiles, n_tiles, K, S, counts);
   }
   CHERRY_LAUNCH_CHECK("count_lg_kernel");
@@ -324,6 +386,21 @@ int cherry_count_co(const uint8_t* msa, const cherry_fam_desc* fams, const int32
       msa, fams, pair_a, pair_b, tab, r_pad, reinterpret_cast<const int2*>(contacts), tiles,
       n_tiles, K, S, counts);
   CHERRY_LAUNCH_CHECK("count_co_kernel");
+  return 0;
+}
+
+int cherry_validate_residues(const uint8_t* msa, int64_t n_bytes, int S, int* flag, void* stream) {
+  if (!msa || !flag) return cherry::fail(CHERRY_EINVAL, "validate_residues: null pointer");
+  if (S <= 0 || S > 254 || n_bytes < 0 || (n_bytes % 16) != 0)
+    return cherry::fail(CHERRY_EINVAL, "validate_residues: bad S or size (must be a multiple of 16)");
+  if (n_bytes == 0) return 0;
+  const int64_t n_vec = n_bytes / 16;
+  int64_t want = (n_vec + 255) / 256;
+  int cap = cherry::sm_count() * 16;
+  int blocks = (int)(want < cap ? want : cap);
+  validate_residues_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(msa), n_vec, (uint32_t)S * 0x01010101u, flag);
+  CHERRY_LAUNCH_CHECK("validate_residues_kernel");
   return 0;
 }
 

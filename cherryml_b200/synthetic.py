@@ -18,7 +18,9 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
-from ._lib import FAM_DESC_DTYPE, INVALID_RESIDUE, TILE_DTYPE
+from ._lib import FAM_DESC_DTYPE, TILE_DTYPE
+
+SKIP = 20  # skip code of a residue byte == number of states (20 amino acids)
 from .counting._ingest import TARGET_CHUNKS_PER_TILE, TARGET_ITEMS_PER_CO_TILE, CountBatch
 from .utils import amino_acids
 
@@ -58,7 +60,7 @@ def _lg_layout(n_sites: int, n_cats: int):
 def _residue_rows(n_fams, n_seqs, n_sites, stride, cols, gen, device, gap_frac, mut_frac, fam_chunk=128):
     """uint8 [n_fams * n_seqs * stride] with rows (2i, 2i+1) forming cherries."""
     n_pairs = n_seqs // 2
-    out = torch.full((n_fams * n_seqs * stride,), INVALID_RESIDUE, dtype=torch.uint8, device=device)
+    out = torch.full((n_fams * n_seqs * stride,), SKIP, dtype=torch.uint8, device=device)
     view = out.view(n_fams, n_pairs, 2, stride)
     cols_t = torch.as_tensor(cols, device=device, dtype=torch.long)
     for f0 in range(0, n_fams, fam_chunk):
@@ -68,7 +70,7 @@ def _residue_rows(n_fams, n_seqs, n_sites, stride, cols, gen, device, gap_frac, 
         fresh = torch.randint(0, 20, shape, dtype=torch.uint8, device=device, generator=gen)
         mutate = torch.rand(shape, device=device, generator=gen) < mut_frac
         b = torch.where(mutate, fresh, a)
-        gap = torch.tensor(INVALID_RESIDUE, dtype=torch.uint8, device=device)
+        gap = torch.tensor(SKIP, dtype=torch.uint8, device=device)
         a = torch.where(torch.rand(shape, device=device, generator=gen) < gap_frac, gap, a)
         b = torch.where(torch.rand(shape, device=device, generator=gen) < gap_frac, gap, b)
         view[f0:f1, :, 0, :].index_copy_(2, cols_t, a)

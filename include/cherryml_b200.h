@@ -45,14 +45,16 @@ extern "C" {
 #define CHERRY_ECUDA (-2)   /* CUDA runtime error; message has the cudaError string */
 #define CHERRY_ELIMIT (-3)  /* size beyond what the kernels support (e.g. K > 254) */
 
-#define CHERRY_INVALID_RESIDUE 255u /* any byte >= num_states is skipped */
+/* Residue bytes are alphabet indices 0..S-1; the byte value S (== num_states) means "skip"
+ * (gap, unknown letter, padding).  No byte may exceed S: the LG kernel indexes an
+ * (S+1)-state shared-memory histogram with it without clamping. */
 #define CHERRY_NO_BUCKET 255u       /* bucket-table entry for "outside the grid" */
 #define CHERRY_MAX_BUCKETS 254
 
 /* One MSA family inside the flat residue buffer.  32 bytes. */
 typedef struct cherry_fam_desc {
   int64_t msa_off;    /* byte offset of the family's row 0 in the residue buffer (16-aligned) */
-  int32_t row_stride; /* bytes per row, a multiple of 16; bytes past the real sites are 255 */
+  int32_t row_stride; /* bytes per row, a multiple of 16; bytes past the real sites are S (skip) */
   int32_t n_chunks;   /* row_stride / 16 */
   int32_t aux_off;    /* LG: first entry of this family in group_cat[] (one per 4 sites);
                          co-transitions: first entry of this family in contacts[] */
@@ -101,6 +103,11 @@ int cherry_count_co(const uint8_t* msa, const cherry_fam_desc* fams, const int32
                     const int32_t* pair_b, const uint8_t* tab, int r_pad,
                     const int32_t* contacts, const cherry_tile* tiles, int n_tiles, int K,
                     int S, uint32_t* counts, void* stream);
+
+/* Sets flag[0] (device int, caller zeroes it) to 1 if any of the n_bytes (multiple of 16)
+ * residue bytes exceeds S.  Optional guard for buffers that did not come from this
+ * package's encoder. */
+int cherry_validate_residues(const uint8_t* msa, int64_t n_bytes, int S, int* flag, void* stream);
 
 /* out (fp64 [K][S][S]) = directed ? raw : (raw + raw^T) / 2. */
 int cherry_symmetrize_lg(const unsigned long long* raw, int K, int S, int directed,

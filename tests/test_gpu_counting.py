@@ -142,8 +142,8 @@ def test_lg_ragged_shapes_and_small_alphabet():
     for f, (n_rows, L) in enumerate([(2, 1), (6, 17), (40, 333), (10, 64), (2, 1500)]):
         rates = rng.choice([0.25, 1.0, 3.0], size=L)
         vals, dest, group_cat, stride = lg_column_layout(rates)
-        rows = np.full((n_rows, stride), 255, dtype=np.uint8)
-        rows[:, dest] = rng.integers(0, 6, size=(n_rows, L)).astype(np.uint8)  # 4,5 are invalid for S=4
+        rows = np.full((n_rows, stride), 4, dtype=np.uint8)
+        rows[:, dest] = rng.integers(0, 5, size=(n_rows, L)).astype(np.uint8)  # 4 == S is the skip code
         a = np.arange(0, n_rows, 2, dtype=np.int32)
         builder.add_family(f"f{f}", rows, a, a + 1, rng.lognormal(-0.5, 1.0, len(a)), vals, group_cat, stride // 4, L)
     batch = builder.finish()
@@ -151,6 +151,15 @@ def test_lg_ragged_shapes_and_small_alphabet():
     got = count_batch(batch, grid, 4, directed=False).cpu().numpy()
     assert np.array_equal(got, count_batch_oracle(batch, grid, 4, False))
     assert got.sum() > 0
+
+
+def test_out_of_range_residue_is_rejected():
+    syn = synthetic_lg(2, 8, 32, 4, seed=1)
+    batch = as_count_batch(syn)
+    batch.msa = batch.msa.copy()
+    batch.msa[37] = 21  # > S
+    with pytest.raises(_lib.CherryError, match="bytes > 20"):
+        count_batch(batch, quantization_grid(), 20, directed=False)
 
 
 def test_empty_batch():
