@@ -57,6 +57,10 @@ _SIGNATURES = {
     "cherry_validate_residues": (c_int, [_P, c_int64, c_int, _P, _P]),
     "cherry_symmetrize_lg": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "cherry_symmetrize_co": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "cherry_fit_workspace_bytes": (c_int, [c_int, c_int, c_int, _P]),
+    "cherry_fit_init": (c_int, [_P, _P]),
+    "cherry_fit_run": (c_int, [_P, c_int, _P]),
+    "cherry_fit_loss_grad": (c_int, [_P, _P]),
     "cherry_count_lg_host": (
         c_int,
         [_P, c_int64, _P, c_int, _P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int,

@@ -1,0 +1,105 @@
+// C-ABI entry points of the fit (include/cherryml_b200.h), dispatching on the state-space
+// size: S <= 32 -> fit_small.cu (shared-memory resident), larger -> fit_large.cu.
+#include "fit_internal.cuh"
+
+namespace {
+
+int check_args(const cherry_fit_args* a, bool training) {
+  if (!a) return cherry::fail(CHERRY_EINVAL, "fit: null args");
+  if (a->S <= 0 || a->K <= 0 || a->n_problems <= 0) return cherry::fail(CHERRY_EINVAL, "fit: bad sizes");
+  if (!a->t || !a->C || !a->Q || !a->dQ_part || !a->loss_part || !a->status_flag)
+    return cherry::fail(CHERRY_EINVAL, "fit: null pointer argument");
+  if (training && (!a->mask || !a->sumC || !a->theta || !a->adam_m || !a->adam_v || !a->Q_best || !a->Q_last ||
+                   !a->best_loss || !a->loss_trace || !a->epoch_counter))
+    return cherry::fail(CHERRY_EINVAL, "fit: null pointer argument (training state)");
+  return 0;
+}
+
+int one_epoch(const cherry_fit_args& a, cudaStream_t stream) {
+  int rc;
+  if (a.S <= cherry::kSmallFitMaxS) {
+    if ((rc = cherry::fit_small_expm(a, stream))) return rc;
+    return cherry::fit_small_update(a, 1, stream);
+  }
+  if ((rc = cherry::fit_large_expm(a, stream))) return rc;
+  return cherry::fit_large_update(a, 1, stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cherry_fit_workspace_bytes(int S, int K, int n_problems, size_t* bytes) {
+  if (!bytes) return cherry::fail(CHERRY_EINVAL, "fit_workspace_bytes: null pointer");
+  if (S <= 0 || K <= 0 || n_problems <= 0) return cherry::fail(CHERRY_EINVAL, "fit_workspace_bytes: bad sizes");
+  if (S <= cherry::kSmallFitMaxS) {
+    int ns = 0, sp = 0;
+    size_t sb = 0, smem = 0;
+    int rc = cherry::fit_small_workspace(S, &ns, &sp, &sb, &smem);
+    if (rc) return rc;
+    *bytes = (size_t)sp * sb * n_problems * K;
+    return 0;
+  }
+  return cherry::fit_large_workspace_bytes(S, K, n_problems, bytes);
+}
+
+int cherry_fit_init(const cherry_fit_args* a, void* stream) {
+  if (!a || !a->mask || !a->theta || !a->Q || !a->epoch_counter)
+    return cherry::fail(CHERRY_EINVAL, "fit_init: null pointer argument");
+  if (a->S <= cherry::kSmallFitMaxS) return cherry::fit_small_update(*a, 0, (cudaStream_t)stream);
+  return cherry::fit_large_update(*a, 0, (cudaStream_t)stream);
+}
+
+int cherry_fit_loss_grad(const cherry_fit_args* a, void* stream) {
+  int rc = check_args(a, false);
+  if (rc) return rc;
+  if (a->S <= cherry::kSmallFitMaxS) return cherry::fit_small_expm(*a, (cudaStream_t)stream);
+  return cherry::fit_large_expm(*a, (cudaStream_t)stream);
+}
+
+int cherry_fit_run(const cherry_fit_args* a, int num_epochs, void* stream_) {
+  int rc = check_args(a, true);
+  if (rc) return rc;
+  if (num_epochs < 0) return cherry::fail(CHERRY_EINVAL, "fit_run: negative num_epochs");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  CHERRY_CUDA(cudaStreamIsCapturing(stream, &cap));
+  const int chunk = 32;
+  int done = 0;
+  // Epoch bodies take all their inputs from device memory (epoch counters included), so a
+  // captured chunk can be replayed unchanged.  The legacy default stream cannot capture.
+  if (cap == cudaStreamCaptureStatusNone && stream != nullptr && num_epochs >= 2 * chunk) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    CHERRY_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    const long long before = cherry::g_launches.load();
+    for (int e = 0; e < chunk && rc == 0; ++e) rc = one_epoch(*a, stream);
+    const long long per_chunk = cherry::g_launches.load() - before;
+    cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    CHERRY_CUDA(ce);
+    cherry::g_launches.fetch_sub(per_chunk);  // capture records, it does not launch
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    if (ce != cudaSuccess) {
+      cudaGraphDestroy(graph);
+      return cherry::check_cuda(ce, "cudaGraphInstantiate");
+    }
+    while (num_epochs - done >= chunk) {
+      ce = cudaGraphLaunch(exec, stream);
+      if (ce != cudaSuccess) break;
+      cherry::count_launch((int)per_chunk);
+      done += chunk;
+    }
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    CHERRY_CUDA(ce);
+  }
+  for (; done < num_epochs; ++done)
+    if ((rc = one_epoch(*a, stream))) return rc;
+  return 0;
+}
+
+}  // extern "C"

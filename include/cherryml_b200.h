@@ -130,6 +130,53 @@ int cherry_count_lg_host(const uint8_t* msa, int64_t msa_bytes, const cherry_fam
                          int S, int r_pad, int directed, double* counts_out,
                          int64_t* h2d_bytes, int64_t* d2h_bytes);
 
+/* ------------------------------------------------------------------- fit */
+
+/* Everything the fit keeps on the device.  One "problem" is one rate matrix with its K time
+ * buckets; n_problems > 1 is the batched per-site fit (independent problems, same S and K).
+ * theta[p] = {S pi logits, S(S-1)/2 upper-diagonal entries in row-major order}; Q(theta) is
+ * the "pande_reversible" parameterisation (reference rate.py:167-188).  All arrays fp64. */
+typedef struct cherry_fit_args {
+  int S, K, n_problems;
+  const double* t;     /* [n_problems*K] bucket times */
+  const double* C;     /* [n_problems*K][S][S] count matrices */
+  const double* mask;  /* [S][S] 0/1 */
+  const double* sumC;  /* [n_problems] sum of C per problem */
+  double* theta;       /* [n_problems][S + S(S-1)/2] */
+  double* adam_m;      /* same shape as theta, zero at start */
+  double* adam_v;
+  double* Q;           /* [n_problems][S][S] current rate matrix */
+  double* Q_best;      /* [n_problems][S][S] */
+  double* Q_last;      /* [n_problems][S][S] Q the most recent loss was evaluated at */
+  double* best_loss;   /* [n_problems] (+inf at start) */
+  double* loss_trace;  /* [loss_trace_epochs][n_problems] */
+  int loss_trace_epochs;
+  double* snapshots;   /* [n_snapshots][S][S]: Q of problem 0 at epochs 1, 2, 4, ... (or NULL) */
+  int n_snapshots;
+  double* dQ_part;     /* workspace [n_problems*K][S][S] */
+  double* loss_part;   /* workspace [n_problems*K] */
+  double* workspace;   /* see cherry_fit_workspace_bytes */
+  size_t workspace_bytes;
+  int* epoch_counter;  /* [n_problems] epochs completed (zero at start) */
+  int* status_flag;    /* [1] set non-zero by a kernel that ran out of workspace */
+  double lr_pi, lr_upper, beta1, beta2, eps;
+  int do_adam;             /* 1: Adam (torch semantics), 0: plain SGD */
+  int loss_normalization;  /* divide loss and gradient by sumC */
+  int best_mode;           /* 0: trainer.py:179 (first epoch always taken); 1: best starts at +inf */
+} cherry_fit_args;
+
+/* Bytes of `workspace` the fit needs for these sizes (0 is a valid answer). */
+int cherry_fit_workspace_bytes(int S, int K, int n_problems, size_t* bytes);
+/* Q = Q(theta) for every problem (call once before the first epoch). */
+int cherry_fit_init(const cherry_fit_args* args, void* stream);
+/* Run `num_epochs` epochs: P_k = expm(t_k Q), loss = -sum C.log P / sumC, best-iterate and
+ * snapshot bookkeeping, exact gradient, optimiser step, next Q.  No host synchronisation;
+ * epochs are replayed from a CUDA graph in chunks unless `stream` is already capturing. */
+int cherry_fit_run(const cherry_fit_args* args, int num_epochs, void* stream);
+/* One evaluation without an optimiser step (tests, evaluation): writes loss_part[p*K+k] =
+ * -<C_k, log expm(t_k Q_p)> and dQ_part[p*K+k] = its gradient with respect to Q_p. */
+int cherry_fit_loss_grad(const cherry_fit_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

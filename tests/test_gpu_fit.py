@@ -1,0 +1,150 @@
+"""GPU parity tests for the fit (S <= 32 path): the CUDA engine against the fp64 oracle
+(tolerance 1e-6 relative, BASELINE.json north_star) and against what the unmodified fp32
+reference produced (tolerance 1e-4 relative)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from cherryml_b200 import _lib, caching
+from cherryml_b200.estimation import (FitEngine, RateMatrixLearner, quantized_transitions_mle, random_theta,
+                                      theta_from_initialization)
+from cherryml_b200.io import read_mask_matrix, read_rate_matrix
+from oracle.fit_oracle import fit_oracle, loss_and_grad_oracle
+from tests.test_oracle_fit import FIT, INP, LG_COUNTS, SMALL_CASES, TOY, load_case
+
+REL_FP64 = 1e-6   # vs the fp64 oracle (north_star: 1e-6 relative in fp64)
+REL_FP32 = 1e-4   # vs the reference as shipped (north_star: 1e-4 in fp32)
+
+
+def random_rate_matrix(S, rng, scale=1.0):
+    Q = rng.random((S, S)) * scale
+    np.fill_diagonal(Q, 0)
+    np.fill_diagonal(Q, -Q.sum(axis=1))
+    return Q
+
+
+@pytest.mark.parametrize("S", [2, 3, 4, 8, 20, 21, 32])
+def test_loss_and_gradient_match_the_oracle(S):
+    """Times span 9 orders of magnitude: exercises every Taylor degree and up to ~15 squarings."""
+    rng = np.random.default_rng(S)
+    K = 24
+    times = np.exp(rng.uniform(np.log(1e-7), np.log(60.0), K))
+    Q = random_rate_matrix(S, rng)
+    counts = rng.integers(0, 200, size=(K, S, S)).astype(np.float64)
+    counts[rng.random(counts.shape) < 0.3] = 0.0
+    eng = FitEngine(times, counts, random_theta(S), num_epochs=0)
+    eng.Q.copy_(torch.from_numpy(Q)[None])
+    loss, grad = eng.loss_and_grad()
+    exp_loss, exp_grad = loss_and_grad_oracle(Q, times, counts)
+    assert abs(float(loss[0]) - exp_loss) < 1e-10 * abs(exp_loss)
+    g = grad[0].cpu().numpy()
+    assert np.max(np.abs(g - exp_grad)) < 1e-9 * np.max(np.abs(exp_grad))
+
+
+def _run_engine(q, counts, init, mask, g, do_adam=True):
+    S = counts.shape[-1]
+    m = np.ones((S, S)) if mask is None else mask
+    theta0 = theta_from_initialization(init, m) if init is not None else random_theta(S)
+    eng = FitEngine(q, counts, theta0, mask=mask, num_epochs=int(g["num_epochs"]), learning_rate=float(g["lr"]),
+                    do_adam=do_adam)
+    eng.run()
+    return eng.results()
+
+
+@pytest.mark.parametrize("name", sorted(SMALL_CASES))
+def test_fit_matches_fp64_oracle_and_reference_run(name):
+    q, _, counts, init, mask, g = load_case(name)
+    do_adam = "sgd" not in name
+    res = _run_engine(q, counts, init, mask, g, do_adam)
+    ref = fit_oracle(q, counts, mask, init, float(g["lr"]), int(g["num_epochs"]), do_adam=do_adam,
+                     dtype=torch.float64)
+    assert np.max(np.abs(res["loss"] - ref["loss"]) / np.abs(ref["loss"])) < REL_FP64
+    for key in ref:
+        if key.startswith("Q_"):
+            scale = np.max(np.abs(ref[key]))
+            assert np.max(np.abs(res[key] - ref[key])) < REL_FP64 * scale, key
+    # the reference as shipped (fp32 expm)
+    assert np.max(np.abs(res["loss"] - g["loss"]) / np.abs(g["loss"])) < REL_FP32
+    for key in ("Q_1", "Q_last", "Q_best"):
+        scale = np.max(np.abs(g[key]))
+        assert np.max(np.abs(res[key] - g[key])) < REL_FP32 * scale, key
+    assert np.max(np.abs(res["Q_best"] - g["result"])) < REL_FP32 * np.max(np.abs(g["result"]))
+
+
+def test_quantized_transitions_mle_stage_function(tmp_path):
+    out = str(tmp_path / "mle")
+    quantized_transitions_mle(
+        count_matrices_path=LG_COUNTS, initialization_path=os.path.join(INP, "equ.txt"), mask_path=None,
+        output_rate_matrix_dir=out, stationary_distribution_path=None,
+        rate_matrix_parameterization="pande_reversible", device="cuda", learning_rate=1e-1, num_epochs=200,
+        do_adam=True,
+    )
+    g = np.load(os.path.join(FIT, "lg20_init_equ", "reference_run.npz"))
+    for name in ("result", "Q_1", "Q_2", "Q_4", "Q_128", "Q_best", "Q_last"):
+        Q = read_rate_matrix(os.path.join(out, name + ".txt"))
+        assert list(Q.index) == list(Q.columns) and len(Q) == 20
+        assert np.max(np.abs(Q.to_numpy() - g[name])) < REL_FP32 * np.max(np.abs(g[name])), name
+    import pandas as pd
+
+    df = pd.read_csv(os.path.join(out, "df_res.txt"))
+    assert list(df.columns[1:]) == ["nuc_norm", "frob_norm", "loss", "time", "epoch", "frob_norm_diag",
+                                    "frob_norm_offdiag"]
+    assert np.max(np.abs(df["loss"].to_numpy() - g["loss"]) / g["loss"]) < REL_FP32
+    assert float(open(os.path.join(out, "profiling.txt")).read().split()[2]) > 0
+
+
+def test_mask_pattern_and_incompatible_initialisation(tmp_path):
+    """The reference's own fit tests (quantized_transitions_mle_test.py:39-67, 94-104, 130-139)."""
+    with pytest.raises(ValueError):
+        quantized_transitions_mle(
+            count_matrices_path=TOY, initialization_path=os.path.join(INP, "3x3_pande_reversible_initialization.txt"),
+            mask_path=os.path.join(INP, "3x3_mask.txt"), output_rate_matrix_dir=str(tmp_path / "a"), num_epochs=3)
+    out = str(tmp_path / "b")
+    quantized_transitions_mle(
+        count_matrices_path=TOY, initialization_path=os.path.join(INP, "3x3_pande_reversible_initialization_mask.txt"),
+        mask_path=os.path.join(INP, "3x3_mask.txt"), output_rate_matrix_dir=out, num_epochs=3)
+    mask = read_mask_matrix(os.path.join(INP, "3x3_mask.txt")).to_numpy()
+    Q = read_rate_matrix(os.path.join(out, "result.txt")).to_numpy()
+    assert np.all((np.abs(Q) > 1e-8) == (mask == 1))
+    out = str(tmp_path / "c")
+    quantized_transitions_mle(
+        count_matrices_path=LG_COUNTS, initialization_path=None, mask_path=os.path.join(INP, "20x20_random_mask.txt"),
+        output_rate_matrix_dir=out, num_epochs=3)
+    mask = read_mask_matrix(os.path.join(INP, "20x20_random_mask.txt")).to_numpy()
+    Q = read_rate_matrix(os.path.join(out, "result.txt")).to_numpy()
+    assert np.all((np.abs(Q) > 1e-8) == (mask == 1))
+
+
+def test_batched_independent_problems_match_single_problem_runs():
+    """The per-site batch (n_problems > 1): every problem evolves exactly as if run alone."""
+    rng = np.random.default_rng(5)
+    P, K, S = 7, 9, 20
+    times = np.exp(rng.uniform(np.log(0.01), np.log(3.0), (P, K)))
+    counts = rng.integers(0, 30, size=(P, K, S, S)).astype(np.float64)
+    theta0 = np.stack([random_theta(S, seed=s) for s in range(P)])
+    eng = FitEngine(times, counts, theta0, num_epochs=25, best_mode=1, lr_upper=0.2)
+    eng.run()
+    res = eng.results()
+    for p in (0, 3, 6):
+        single = FitEngine(times[p], counts[p], theta0[p], num_epochs=25, best_mode=1, lr_upper=0.2)
+        single.run()
+        r1 = single.results()
+        assert np.array_equal(r1["loss"], res["loss_per_problem"][:, p])
+        assert np.array_equal(r1["Q_best"], res["Q_best"][p])
+
+
+def test_loss_decreases_and_graph_replay_equals_eager():
+    q, _, counts, init, mask, g = load_case("lg20_init_lg")
+    theta0 = theta_from_initialization(init, np.ones((20, 20)))
+    a = FitEngine(q, counts, theta0, num_epochs=100)
+    a.run()  # >= 64 epochs: replayed from a CUDA graph in chunks of 32
+    b = FitEngine(q, counts, theta0, num_epochs=100)
+    for _ in range(100):
+        b.run(1)  # one epoch per call: plain launches
+    ra, rb = a.results(), b.results()
+    assert np.array_equal(ra["loss"], rb["loss"]) and np.array_equal(ra["Q_best"], rb["Q_best"])
+    assert ra["loss"][-1] < ra["loss"][0]
