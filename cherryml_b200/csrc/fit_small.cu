@@ -433,7 +433,7 @@ int fit_small_expm(const cherry_fit_args& a, cudaStream_t stream) {
   CHERRY_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
     CHERRY_CUDA(cudaFuncSetAttribute(expm_loss_grad_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     227 * 1024));
+                                     226 * 1024));  // 227 KB minus this kernel's static shared memory
     attr_set[dev] = true;
   }
   expm_loss_grad_small<<<a.n_problems * a.K, kSmallThreads, smem, stream>>>(
