@@ -1,17 +1,817 @@
-// Composite-likelihood fit for large state spaces (the 400 x 400 co-evolution model).
-// Placeholder until the batched DMMA GEMM chain lands: every entry point fails loudly.
+// Composite-likelihood fit for large state spaces (S > 32; the 400 x 400 co-evolution model).
+//
+// One epoch evaluates, for all K time buckets at once,
+//     P_k = expm(t_k Q),   loss = -sum_k <C_k, log P_k>,   dloss/dQ
+// with a schedule built around two facts: every bucket exponentiates the SAME matrix, and Q is
+// a rate matrix, so B = Q + mu I (mu = max |Q_ii|) is entrywise non-negative.
+//
+//   expm(t Q) = [ e^{-tau mu} T_m(tau B) ]^(2^s),   tau = t / 2^s,   ||tau B||_inf = tau mu <= theta
+//
+//   1. powers B^2..B^m are formed ONCE per epoch (log-depth schedule of batched GEMMs), so the
+//      degree-m Taylor polynomial of every bucket is a weighted sum of shared matrices (one
+//      elementwise pass for all buckets, no GEMM per bucket); all terms are non-negative, so
+//      small transition probabilities keep full relative accuracy before the log;
+//   2. only buckets with tau mu > theta need squarings: s_k batched 400^3 GEMMs per bucket,
+//      run level by level over the buckets that are still active;
+//   3. the backward pass is the exact adjoint of 1-2: per squaring two GEMMs fused into one
+//      launch (concatenated K), the bucket adjoints are folded into m weighted sums, and the
+//      adjoint of the power schedule yields dloss/dB = dloss/dQ.
+// Every GEMM is a hand-written FP64 tensor-core kernel (DMMA m8n8k4, cp.async pipeline,
+// 80x80 CTA tiles, split-K for the small-batch power levels).  All matrices are stored padded
+// to a multiple of 80 with zero padding, so the GEMM has no edge handling.
+//
+// Replaces torch.matrix_exp + log + sum + autograd.backward + Adam of the reference's
+// train_quantization (estimation/_ratelearn/trainer.py:156-187) for S = 400.
+#include <vector>
+
+#include "fit_common.cuh"
 #include "fit_internal.cuh"
+
+namespace {
+
+constexpr int kDeg = 18;          // Taylor degree of the shared-power polynomial
+constexpr double kTheta = 1.09;   // tau*mu bound: 1.09^19/19! ~ 4e-17 (all terms non-negative)
+constexpr int kSStore = 8;        // squarings kept per bucket: covers t*mu up to 1.09 * 2^8 = 279
+constexpr int BT = 80, BK = 16, NSTAGE = 3, GEMM_THREADS = 128;
+constexpr int LD_ROW = 20;        // tile stored [80][16]: k contiguous
+constexpr int LD_COL = 84;        // tile stored [16][80]: m (or n) contiguous
+constexpr int TILE_ELEMS = BT * LD_ROW;  // 1600 >= 16 * 84
+constexpr int EW_THREADS = 256;
+
+struct GemmTerm {
+  const double* A;
+  const double* B;
+  int ta, tb;
+};
+struct GemmTask {
+  double* C;
+  const int* cond;  // active iff cond == nullptr || *cond > level
+  int term_begin, n_terms, accumulate, level;
+};
+struct Group {
+  int task_begin, n_tasks, ksplit;
+};
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// tile with the k index contiguous in global memory: 80 rows x 16 doubles -> [80][LD_ROW]
+__device__ __forceinline__ void load_row_tile(double* s, const double* g, int ldg, int row0, int col0) {
+  for (int c = threadIdx.x; c < BT * 8; c += GEMM_THREADS) {
+    const int row = c >> 3, seg = c & 7;
+    cp_async16(s + row * LD_ROW + seg * 2, g + (size_t)(row0 + row) * ldg + col0 + seg * 2);
+  }
+}
+// tile with the m/n index contiguous in global memory: 16 rows x 80 doubles -> [16][LD_COL]
+__device__ __forceinline__ void load_col_tile(double* s, const double* g, int ldg, int row0, int col0) {
+  for (int c = threadIdx.x; c < BK * 40; c += GEMM_THREADS) {
+    const int row = c / 40, seg = c - row * 40;
+    cp_async16(s + row * LD_COL + seg * 2, g + (size_t)(row0 + row) * ldg + col0 + seg * 2);
+  }
+}
+
+template <bool TA, bool TB>
+__device__ __forceinline__ void compute_chunk(const double* As, const double* Bs, double (&acc)[5][5][2],
+                                              int rbase, int cbase, int g, int tg) {
+#pragma unroll
+  for (int kk = 0; kk < BK; kk += 4) {
+    double a[5], b[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int row = rbase + 8 * i + g;
+      a[i] = TA ? As[(kk + tg) * LD_COL + row] : As[row * LD_ROW + kk + tg];
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int col = cbase + 8 * j + g;
+      b[j] = TB ? Bs[col * LD_ROW + kk + tg] : Bs[(kk + tg) * LD_COL + col];
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+
+// C_task = sum over the task's terms of op(A) op(B)  (+ C_task if accumulate).  Square Sp x Sp
+// matrices, Sp a multiple of 80.  grid = (tiles, n_tasks, ksplit); with ksplit > 1 the CTA
+// writes its partial product to `partial[(task*ksplit + z)]` and splitk_reduce_kernel finishes.
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_tasks_kernel(const GemmTask* __restrict__ tasks, const GemmTerm* __restrict__ terms, int Sp,
+                  int ksplit, double* __restrict__ partial) {
+  extern __shared__ double smem[];
+  const GemmTask task = tasks[blockIdx.y];
+  if (task.cond != nullptr && *task.cond <= task.level) return;
+  const int tiles_n = Sp / BT;
+  const int m0 = (blockIdx.x / tiles_n) * BT, n0 = (blockIdx.x % tiles_n) * BT;
+  const int cpt = Sp / BK;  // k chunks per term
+  const int total = task.n_terms * cpt;
+  const int z = blockIdx.z;
+  const int c_begin = (int)((long long)total * z / ksplit), c_end = (int)((long long)total * (z + 1) / ksplit);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const int rbase = (warp >> 1) * 40, cbase = (warp & 1) * 40;
+  double acc[5][5][2];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  auto issue = [&](int c, int stage) {
+    const GemmTerm t = terms[task.term_begin + c / cpt];
+    const int k0 = (c % cpt) * BK;
+    double* As = smem + (size_t)stage * 2 * TILE_ELEMS;
+    double* Bs = As + TILE_ELEMS;
+    if (t.ta) load_col_tile(As, t.A, Sp, k0, m0); else load_row_tile(As, t.A, Sp, m0, k0);
+    if (t.tb) load_row_tile(Bs, t.B, Sp, n0, k0); else load_col_tile(Bs, t.B, Sp, k0, n0);
+  };
+  const int n_chunks = c_end - c_begin;
+#pragma unroll
+  for (int s = 0; s < NSTAGE - 1; ++s) {
+    if (s < n_chunks) issue(c_begin + s, s);
+    cp_async_commit();
+  }
+  for (int i = 0; i < n_chunks; ++i) {
+    cp_async_wait<NSTAGE - 2>();
+    __syncthreads();
+    const int nxt = i + NSTAGE - 1;
+    if (nxt < n_chunks) issue(c_begin + nxt, nxt % NSTAGE);
+    cp_async_commit();
+    const GemmTerm t = terms[task.term_begin + (c_begin + i) / cpt];
+    const double* As = smem + (size_t)(i % NSTAGE) * 2 * TILE_ELEMS;
+    const double* Bs = As + TILE_ELEMS;
+    if (t.ta) {
+      if (t.tb) compute_chunk<true, true>(As, Bs, acc, rbase, cbase, g, tg);
+      else compute_chunk<true, false>(As, Bs, acc, rbase, cbase, g, tg);
+    } else {
+      if (t.tb) compute_chunk<false, true>(As, Bs, acc, rbase, cbase, g, tg);
+      else compute_chunk<false, false>(As, Bs, acc, rbase, cbase, g, tg);
+    }
+  }
+  cp_async_wait<0>();
+  double* out = (ksplit == 1) ? task.C
+                              : partial + ((size_t)blockIdx.y * ksplit + z) * (size_t)Sp * Sp;
+  const bool add_old = (ksplit == 1) && task.accumulate;
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      double2* p = reinterpret_cast<double2*>(out + (size_t)(m0 + rbase + 8 * i + g) * Sp + n0 + cbase + 8 * j + 2 * tg);
+      double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+      if (add_old) {
+        const double2 o = *p;
+        v.x += o.x;
+        v.y += o.y;
+      }
+      *p = v;
+    }
+}
+
+// grid = (blocks over elements, n_tasks): C = (accumulate ? C : 0) + sum_z partial[task][z], z ascending
+__global__ void splitk_reduce_kernel(const GemmTask* __restrict__ tasks, int ksplit, size_t n_p,
+                                     const double* __restrict__ partial) {
+  const GemmTask task = tasks[blockIdx.y];
+  if (task.cond != nullptr && *task.cond <= task.level) return;
+  const double* base = partial + (size_t)blockIdx.y * ksplit * n_p;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n_p; e += (size_t)gridDim.x * blockDim.x) {
+    double v = task.accumulate ? task.C[e] : 0.0;
+    for (int z = 0; z < ksplit; ++z) v += base[(size_t)z * n_p + e];
+    task.C[e] = v;
+  }
+}
+
+// ---------------------------------------------------------------- per-epoch small kernels
+struct LargeScalars {   // lives in the workspace
+  unsigned long long norm_bits;  // max row abs sum of B (bit pattern of a non-negative double)
+  double mu;
+  double pad[6];
+};
+
+// grid = Sp rows / 4; B = pad(Q) + mu I, row abs sums -> atomicMax (order independent)
+__global__ void build_B_kernel(const double* __restrict__ Q, int S, int Sp, double* __restrict__ B,
+                               LargeScalars* __restrict__ sc) {
+  __shared__ double red[EW_THREADS / 32];
+  double mx = 0.0;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) mx = fmax(mx, fabs(Q[(size_t)i * S + i]));
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  double mu = red[0];
+  for (int w = 1; w < EW_THREADS / 32; ++w) mu = fmax(mu, red[w]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) sc->mu = mu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * (EW_THREADS / 32) + warp; row < Sp; row += gridDim.x * (EW_THREADS / 32)) {
+    double rs = 0.0;
+    for (int j = lane; j < Sp; j += 32) {
+      double v = 0.0;
+      if (row < S && j < S) v = Q[(size_t)row * S + j] + (row == j ? mu : 0.0);
+      B[(size_t)row * Sp + j] = v;
+      rs += fabs(v);
+    }
+    for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    if (lane == 0) atomicMax(&sc->norm_bits, (unsigned long long)__double_as_longlong(rs));
+  }
+}
+
+// one CTA: per bucket s_k, tau_k and the weights w[k][j] = e^{-tau mu} tau^j / j!, j = 0..m
+__global__ void coef_kernel(const double* __restrict__ t, int K, LargeScalars* __restrict__ sc,
+                            int* __restrict__ s_arr, double* __restrict__ w, double* __restrict__ tau_arr,
+                            int* __restrict__ status_flag) {
+  const double norm = __longlong_as_double((long long)sc->norm_bits);
+  const double mu = sc->mu;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const double a = fabs(t[k]) * norm;
+    int s = 0;
+    if (a > kTheta && a < 1e300) s = (int)ceil(log2(a / kTheta));
+    if (s > kSStore) {
+      atomicExch(status_flag, 2);
+      s = kSStore;
+    }
+    const double tau = ldexp(t[k], -s);
+    s_arr[k] = s;
+    tau_arr[k] = tau;
+    const double e = exp(-tau * mu);
+    double c = e;
+    for (int j = 0; j <= kDeg; ++j) {
+      w[(size_t)k * (kDeg + 1) + j] = c;
+      c *= tau / (double)(j + 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) sc->norm_bits = 0ull;  // ready for the next epoch's atomicMax
+}
+
+// X0_k = sum_j w[k][j] B^j for every bucket; one thread per matrix element keeps the m power
+// values in registers and streams over the buckets.  powers[j-1] = B^j, j = 1..m.
+__global__ void __launch_bounds__(EW_THREADS)
+poly_eval_kernel(const double* __restrict__ powers, size_t n_p, int S, int Sp, int K,
+                 const double* __restrict__ w, double* __restrict__ X0) {
+  extern __shared__ double sw[];  // [K][m+1]
+  for (int i = threadIdx.x; i < K * (kDeg + 1); i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (e >= n_p) return;
+  const int row = (int)(e / Sp), col = (int)(e - (size_t)row * Sp);
+  double pw[kDeg];
+#pragma unroll
+  for (int j = 0; j < kDeg; ++j) pw[j] = powers[(size_t)j * n_p + e];
+  const double diag = (row == col && row < S) ? 1.0 : 0.0;
+  for (int k = 0; k < K; ++k) {
+    const double* wk = sw + k * (kDeg + 1);
+    double v = wk[0] * diag;
+#pragma unroll
+    for (int j = 0; j < kDeg; ++j) v = fma(wk[j + 1], pw[j], v);
+    X0[(size_t)k * n_p + e] = v;
+  }
+}
+
+// grid = (blocks, K): loss partials and G_k = -C_k / P_k into chain slot s_k + 1.
+// P_k = X0_k if s_k == 0 else chain slot s_k.
+__global__ void __launch_bounds__(EW_THREADS)
+loss_grad_kernel(const double* __restrict__ C, int S, int Sp, size_t n_p, const int* __restrict__ s_arr,
+                 const double* __restrict__ X0, double* __restrict__ chain, int slots_per_bucket,
+                 double* __restrict__ loss_partial) {
+  __shared__ double red[EW_THREADS / 32];
+  const int k = blockIdx.y, s = s_arr[k];
+  const double* P = (s == 0) ? X0 + (size_t)k * n_p
+                             : chain + ((size_t)k * slots_per_bucket + (s - 1)) * n_p;
+  double* G = chain + ((size_t)k * slots_per_bucket + s) * n_p;  // slot s+1 (slots are 1-based)
+  const double* Ck = C + (size_t)k * S * S;
+  double part = 0.0;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n_p; e += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(e / Sp), col = (int)(e - (size_t)row * Sp);
+    double gval = 0.0;
+    if (row < S && col < S) {
+      const double c = Ck[(size_t)row * S + col];
+      if (c != 0.0) {
+        const double p = P[e];
+        part -= c * log(p);
+        gval = -c / p;
+      }
+    }
+    G[e] = gval;
+  }
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int wdx = 0; wdx < EW_THREADS / 32; ++wdx) tot += red[wdx];
+    loss_partial[(size_t)k * gridDim.x + blockIdx.x] = tot;
+  }
+}
+
+__global__ void loss_reduce_kernel(const double* __restrict__ loss_partial, int K, int nblocks,
+                                   double* __restrict__ loss_part) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+    double tot = 0.0;
+    for (int b = 0; b < nblocks; ++b) tot += loss_partial[(size_t)k * nblocks + b];
+    loss_part[k] = tot;
+  }
+}
+
+// Pbar_j = sum_k w[k][j] * X0bar_k (chain slot 1 of bucket k), j = 1..m; buckets in order.
+__global__ void __launch_bounds__(EW_THREADS)
+accumulate_M_kernel(const double* __restrict__ chain, int slots_per_bucket, size_t n_p, int K,
+                    const double* __restrict__ w, double* __restrict__ Pbar) {
+  extern __shared__ double sw[];
+  for (int i = threadIdx.x; i < K * (kDeg + 1); i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (e >= n_p) return;
+  double acc[kDeg];
+#pragma unroll
+  for (int j = 0; j < kDeg; ++j) acc[j] = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const double x = chain[((size_t)k * slots_per_bucket) * n_p + e];
+    const double* wk = sw + k * (kDeg + 1);
+#pragma unroll
+    for (int j = 0; j < kDeg; ++j) acc[j] = fma(wk[j + 1], x, acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < kDeg; ++j) Pbar[(size_t)j * n_p + e] = acc[j];
+}
+
+__global__ void unpad_kernel(const double* __restrict__ src, int S, int Sp, double* __restrict__ dst) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < S * S; e += gridDim.x * blockDim.x) {
+    const int i = e / S, j = e - i * S;
+    dst[e] = src[(size_t)i * Sp + j];
+  }
+}
+
+// ------------------------------------------------------------------ parameter update (large S)
+struct LargeUpdateArgs {
+  int S, K;
+  const double* mask;
+  double* theta;
+  double* adam_m;
+  double* adam_v;
+  double* Q;
+  double* Q_best;
+  double* Q_last;
+  double* best_loss;
+  double* loss_trace;
+  int loss_trace_epochs;
+  double* snapshots;
+  int n_snapshots;
+  const double* G;          // dL/dQ unnormalised [S][S]
+  const double* loss_part;  // [K]
+  const double* sumC;
+  int* epoch_counter;
+  double* grad_theta;  // [S + S(S-1)/2]
+  double* dpi;         // [S]
+  double* pibuf;       // [S] softmax(pi logits) of the CURRENT theta, written by the rows kernel
+  double lr_pi, lr_upper, beta1, beta2, eps;
+  int do_adam, loss_normalization, best_mode;
+};
+
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < EW_THREADS / 32; ++w) t += red[w];
+  return t;
+}
+__device__ __forceinline__ double block_max_256(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = red[0];
+  for (int w = 1; w < EW_THREADS / 32; ++w) t = fmax(t, red[w]);
+  return t;
+}
+// sqrt(softmax(theta[0..S))) into sr[] (shared)
+__device__ __forceinline__ void softmax_sqrt(const double* theta, int S, double* sr, double* red) {
+  double mx = -INFINITY;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) mx = fmax(mx, theta[i]);
+  mx = block_max_256(mx, red);
+  double se = 0.0;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) se += exp(theta[i] - mx);
+  se = block_sum_256(se, red);
+  for (int i = threadIdx.x; i < S; i += blockDim.x) sr[i] = sqrt(exp(theta[i] - mx) / se);
+  __syncthreads();
+}
+__device__ __forceinline__ double upper_param(const double* theta, int S, int i, int j) {
+  const int lo = i < j ? i : j, hi = i < j ? j : i;
+  return theta[S + cherry::triu_index(lo, hi, S)];
+}
+
+// grid = S (one CTA per state i): bookkeeping copies of row i of the current Q, dL/dr_i, and the
+// gradients of the upper-diagonal parameters of row i.  Nothing that other CTAs read is written.
+__global__ void __launch_bounds__(EW_THREADS) large_update_rows_kernel(LargeUpdateArgs a) {
+  extern __shared__ double sr[];  // [S] sqrt(pi)
+  __shared__ double red[EW_THREADS / 32];
+  const int S = a.S, i = blockIdx.x;
+  const int epoch = a.epoch_counter[0];
+  const double scale = a.loss_normalization ? 1.0 / a.sumC[0] : 1.0;
+  // loss of this epoch (every CTA recomputes it in the same order -> same value)
+  double lp = 0.0;
+  for (int k = 0; k < a.K; ++k) lp += a.loss_part[k];
+  lp *= scale;
+  const bool improved = (epoch == 0 && a.best_mode == 0) ? true : (lp < a.best_loss[0]);
+  const bool snap = a.snapshots && ((epoch & (epoch + 1)) == 0);
+  int snap_idx = 0;
+  if (snap) {
+    int e1 = epoch + 1;
+    while (e1 > 1) { e1 >>= 1; ++snap_idx; }
+  }
+  for (int j = threadIdx.x; j < S; j += blockDim.x) {
+    const double q = a.Q[(size_t)i * S + j];
+    a.Q_last[(size_t)i * S + j] = q;
+    if (improved) a.Q_best[(size_t)i * S + j] = q;
+    if (snap && snap_idx < a.n_snapshots) a.snapshots[((size_t)snap_idx * S + i) * S + j] = q;
+  }
+  softmax_sqrt(a.theta, S, sr, red);
+  const double ri = sr[i];
+  const double gii = a.G[(size_t)i * S + i];
+  double col = 0.0, row = 0.0;
+  for (int j = threadIdx.x; j < S; j += blockDim.x) {
+    if (j == i) continue;
+    const double u = upper_param(a.theta, S, i, j);
+    const double sp = cherry::softplus_d(u), sg = cherry::softplus_grad_d(u);
+    const double m_ij = a.mask[(size_t)i * S + j], m_ji = a.mask[(size_t)j * S + i];
+    const double dM_ij = (a.G[(size_t)i * S + j] - gii) * scale;
+    const double dM_ji = (a.G[(size_t)j * S + i] - a.G[(size_t)j * S + j]) * scale;
+    const double rj = sr[j];
+    col += dM_ji * (m_ji * sp) / rj;
+    row += dM_ij * (m_ij * sp) * rj;
+    if (j > i) {
+      const double ds_ij = dM_ij * rj / ri, ds_ji = dM_ji * ri / rj;
+      a.grad_theta[S + cherry::triu_index(i, j, S)] = sg * (m_ij * ds_ij + m_ji * ds_ji);
+    }
+  }
+  col = block_sum_256(col, red);
+  row = block_sum_256(row, red);
+  if (threadIdx.x == 0) {
+    a.dpi[i] = (col - row / (ri * ri)) / (2.0 * ri);
+    a.pibuf[i] = ri * ri;
+  }
+}
+
+// grid-stride over all parameters: softmax backward for the logits, then the optimiser step.
+__global__ void __launch_bounds__(EW_THREADS) large_update_step_kernel(LargeUpdateArgs a) {
+  extern __shared__ double sr[];
+  __shared__ double red[EW_THREADS / 32];
+  const int S = a.S, n_theta = S + S * (S - 1) / 2;
+  const int epoch = a.epoch_counter[0];
+  // pi comes from pibuf (written by the rows kernel), NOT from theta: other CTAs of this very
+  // kernel are updating the logits while we read.
+  for (int i = threadIdx.x; i < S; i += blockDim.x) sr[i] = a.pibuf[i];
+  __syncthreads();
+  double dot = 0.0;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) dot += sr[i] * a.dpi[i];
+  dot = block_sum_256(dot, red);
+  const int step = epoch + 1;
+  const double bc1 = 1.0 - pow(a.beta1, (double)step), bc2s = sqrt(1.0 - pow(a.beta2, (double)step));
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_theta; idx += gridDim.x * blockDim.x) {
+    double g, lr;
+    if (idx < S) {
+      g = sr[idx] * (a.dpi[idx] - dot);
+      lr = a.lr_pi;
+    } else {
+      g = a.grad_theta[idx];
+      lr = a.lr_upper;
+    }
+    cherry::optimizer_step(a.theta[idx], a.adam_m[idx], a.adam_v[idx], g, lr, a.do_adam, a.beta1, a.beta2,
+                           a.eps, bc1, bc2s);
+  }
+}
+
+// grid = S: row i of Q(theta) (mode 1: after the step).  CTA 0 also closes the epoch's bookkeeping.
+__global__ void __launch_bounds__(EW_THREADS) large_build_Q_kernel(LargeUpdateArgs a, int mode) {
+  extern __shared__ double sr[];
+  __shared__ double red[EW_THREADS / 32];
+  const int S = a.S, i = blockIdx.x;
+  softmax_sqrt(a.theta, S, sr, red);
+  const double ri = sr[i];
+  double rs = 0.0;
+  for (int j = threadIdx.x; j < S; j += blockDim.x) {
+    if (j == i) continue;
+    const double u = upper_param(a.theta, S, i, j);
+    const double v = a.mask[(size_t)i * S + j] * cherry::softplus_d(u) * sr[j] / ri;
+    a.Q[(size_t)i * S + j] = v;
+    rs += v;
+  }
+  rs = block_sum_256(rs, red);
+  if (threadIdx.x == 0) a.Q[(size_t)i * S + i] = -rs;
+  if (mode == 1 && i == 0 && threadIdx.x == 0) {
+    const int epoch = a.epoch_counter[0];
+    const double scale = a.loss_normalization ? 1.0 / a.sumC[0] : 1.0;
+    double lp = 0.0;
+    for (int k = 0; k < a.K; ++k) lp += a.loss_part[k];
+    lp *= scale;
+    if (epoch < a.loss_trace_epochs) a.loss_trace[epoch] = lp;
+    const bool improved = (epoch == 0 && a.best_mode == 0) ? true : (lp < a.best_loss[0]);
+    if (improved) a.best_loss[0] = lp;
+    a.epoch_counter[0] = epoch + 1;
+  }
+}
+
+// ------------------------------------------------------------------------------ the plan
+struct Plan {
+  int S, Sp, K, tiles;
+  size_t n_p;
+  // workspace offsets in bytes
+  size_t off_scalars, off_s, off_tau, off_w, off_loss_partial, off_grad_theta, off_dpi, off_pibuf, off_tasks, off_terms;
+  size_t off_P, off_Pbar, off_X0, off_chain, off_partial, total_bytes;
+  int slots_per_bucket;   // chain slots 1..kSStore+1
+  int loss_blocks;
+  int n_partial;
+  std::vector<GemmTask> tasks;   // device pointers filled relative to base
+  std::vector<GemmTerm> terms;
+  std::vector<Group> pow_fwd, sq_fwd, sq_bwd, pow_bwd;
+};
+
+size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+int choose_ksplit(int n_tasks, int tiles, int chunks_per_task) {
+  int want = (296 + n_tasks * tiles - 1) / (n_tasks * tiles);
+  int cap = chunks_per_task / 4;
+  if (cap < 1) cap = 1;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return want;
+}
+
+// Builds the layout and (if base != nullptr) the task lists with absolute device pointers.
+void make_plan(Plan& p, int S, int K, char* base) {
+  p.S = S;
+  p.K = K;
+  p.Sp = (S + BT - 1) / BT * BT;
+  p.tiles = (p.Sp / BT) * (p.Sp / BT);
+  p.n_p = (size_t)p.Sp * p.Sp;
+  p.slots_per_bucket = kSStore + 1;
+  p.loss_blocks = (int)((p.n_p + EW_THREADS * 8 - 1) / (EW_THREADS * 8));
+  const size_t mat = p.n_p * sizeof(double);
+  const int n_theta = S + S * (S - 1) / 2;
+  // upper bounds on descriptor counts: powers (2m tasks, 4m terms) + squarings (2 * kSStore * K tasks, 3x terms)
+  const size_t max_tasks = 4 * kDeg + 2 * (size_t)kSStore * K + 16;
+  const size_t max_terms = 8 * kDeg + 3 * (size_t)kSStore * K + 16;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off = align256(off + bytes); return o; };
+  p.off_scalars = carve(sizeof(LargeScalars));
+  p.off_s = carve(sizeof(int) * K);
+  p.off_tau = carve(sizeof(double) * K);
+  p.off_w = carve(sizeof(double) * K * (kDeg + 1));
+  p.off_loss_partial = carve(sizeof(double) * K * p.loss_blocks);
+  p.off_grad_theta = carve(sizeof(double) * n_theta);
+  p.off_dpi = carve(sizeof(double) * S);
+  p.off_pibuf = carve(sizeof(double) * S);
+  p.off_tasks = carve(sizeof(GemmTask) * max_tasks);
+  p.off_terms = carve(sizeof(GemmTerm) * max_terms);
+  p.off_P = carve(mat * kDeg);
+  p.off_Pbar = carve(mat * kDeg);
+  p.off_X0 = carve(mat * K);
+  p.off_chain = carve(mat * K * p.slots_per_bucket);
+  // split-K partial buffers: sized below once the groups are known (upper bound first)
+  p.n_partial = 40;
+  p.off_partial = carve(mat * p.n_partial);
+  p.total_bytes = off;
+  if (!base) return;
+
+  auto Pj = [&](int j) { return reinterpret_cast<double*>(base + p.off_P) + (size_t)(j - 1) * p.n_p; };
+  auto Pbar = [&](int j) { return reinterpret_cast<double*>(base + p.off_Pbar) + (size_t)(j - 1) * p.n_p; };
+  auto X0 = [&](int k) { return reinterpret_cast<double*>(base + p.off_X0) + (size_t)k * p.n_p; };
+  auto chain = [&](int k, int slot) {  // slot 1..kSStore+1
+    return reinterpret_cast<double*>(base + p.off_chain) + ((size_t)k * p.slots_per_bucket + (slot - 1)) * p.n_p;
+  };
+  const int* s_arr = reinterpret_cast<const int*>(base + p.off_s);
+  const int cpt = p.Sp / BK;
+  auto begin_group = [&]() { Group g; g.task_begin = (int)p.tasks.size(); g.n_tasks = 0; g.ksplit = 1; return g; };
+  auto add_task = [&](Group& g, double* C, const int* cond, int level, int accumulate,
+                      std::initializer_list<GemmTerm> ts) {
+    GemmTask t;
+    t.C = C; t.cond = cond; t.level = level; t.accumulate = accumulate;
+    t.term_begin = (int)p.terms.size(); t.n_terms = (int)ts.size();
+    for (const GemmTerm& x : ts) p.terms.push_back(x);
+    p.tasks.push_back(t);
+    g.n_tasks++;
+  };
+  // ---- powers forward: level with base b: P_{b+r} = P_b P_r, r = 1..min(b, m-b)
+  for (int b = 1; b < kDeg; b *= 2) {
+    Group g = begin_group();
+    for (int r = 1; r <= b && b + r <= kDeg; ++r)
+      add_task(g, Pj(b + r), nullptr, 0, 0, {GemmTerm{Pj(b), Pj(r), 0, 0}});
+    g.ksplit = choose_ksplit(g.n_tasks, p.tiles, cpt);
+    p.pow_fwd.push_back(g);
+  }
+  // ---- squarings forward, level i: X_{i+1} = X_i X_i for buckets with s_k > i
+  for (int i = 0; i < kSStore; ++i) {
+    Group g = begin_group();
+    for (int k = 0; k < K; ++k) {
+      double* Xi = (i == 0) ? X0(k) : chain(k, i);
+      add_task(g, chain(k, i + 1), s_arr + k, i, 0, {GemmTerm{Xi, Xi, 0, 0}});
+    }
+    p.sq_fwd.push_back(g);
+  }
+  // ---- squarings backward, level i: Xbar_i = Xbar_{i+1} X_i^T + X_i^T Xbar_{i+1} -> slot i+1
+  for (int i = kSStore - 1; i >= 0; --i) {
+    Group g = begin_group();
+    for (int k = 0; k < K; ++k) {
+      double* Xi = (i == 0) ? X0(k) : chain(k, i);
+      double* Xb = chain(k, i + 2);
+      add_task(g, chain(k, i + 1), s_arr + k, i, 0, {GemmTerm{Xb, Xi, 0, 1}, GemmTerm{Xi, Xb, 1, 0}});
+    }
+    p.sq_bwd.push_back(g);
+  }
+  // ---- powers backward, levels in reverse.  For P_{b+r} = P_b P_r:
+  //      Pbar_r += P_b^T Pbar_{b+r}  (r != b),   Pbar_b += sum_r Pbar_{b+r} P_r^T (+ P_b^T Pbar_{2b})
+  std::vector<int> bases;
+  for (int b = 1; b < kDeg; b *= 2) bases.push_back(b);
+  for (int li = (int)bases.size() - 1; li >= 0; --li) {
+    const int b = bases[li];
+    const int rmax = (b + b <= kDeg) ? b : kDeg - b;
+    Group g1 = begin_group();
+    for (int r = 1; r <= rmax; ++r)
+      if (r != b) add_task(g1, Pbar(r), nullptr, 0, 1, {GemmTerm{Pj(b), Pbar(b + r), 1, 0}});
+    if (g1.n_tasks) {
+      g1.ksplit = choose_ksplit(g1.n_tasks, p.tiles, cpt);
+      p.pow_bwd.push_back(g1);
+    }
+    Group g2 = begin_group();
+    {
+      GemmTask t;
+      t.C = Pbar(b); t.cond = nullptr; t.level = 0; t.accumulate = 1;
+      t.term_begin = (int)p.terms.size();
+      for (int r = 1; r <= rmax; ++r) p.terms.push_back(GemmTerm{Pbar(b + r), Pj(r), 0, 1});
+      if (rmax == b) p.terms.push_back(GemmTerm{Pj(b), Pbar(2 * b), 1, 0});
+      t.n_terms = (int)p.terms.size() - t.term_begin;
+      p.tasks.push_back(t);
+      g2.n_tasks = 1;
+      g2.ksplit = choose_ksplit(1, p.tiles, cpt * t.n_terms);
+    }
+    p.pow_bwd.push_back(g2);
+  }
+}
+
+int launch_group(const Plan& p, const Group& g, char* base, cudaStream_t stream) {
+  const GemmTask* tasks = reinterpret_cast<const GemmTask*>(base + p.off_tasks) + g.task_begin;
+  const GemmTerm* terms = reinterpret_cast<const GemmTerm*>(base + p.off_terms);
+  double* partial = reinterpret_cast<double*>(base + p.off_partial);
+  if (g.ksplit > 1 && g.n_tasks * g.ksplit > p.n_partial)
+    return cherry::fail(CHERRY_ELIMIT, "fit_large: split-K partial buffer too small");
+  const size_t smem = (size_t)NSTAGE * 2 * TILE_ELEMS * sizeof(double);
+  dim3 grid(p.tiles, g.n_tasks, g.ksplit);
+  gemm_tasks_kernel<<<grid, GEMM_THREADS, smem, stream>>>(tasks, terms, p.Sp, g.ksplit, partial);
+  CHERRY_LAUNCH_CHECK("gemm_tasks_kernel");
+  if (g.ksplit > 1) {
+    int bx = (int)((p.n_p + EW_THREADS * 4 - 1) / (EW_THREADS * 4));
+    splitk_reduce_kernel<<<dim3(bx, g.n_tasks), EW_THREADS, 0, stream>>>(tasks, g.ksplit, p.n_p, partial);
+    CHERRY_LAUNCH_CHECK("splitk_reduce_kernel");
+  }
+  return 0;
+}
+
+int ensure_gemm_attr() {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  CHERRY_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    CHERRY_CUDA(cudaFuncSetAttribute(gemm_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     NSTAGE * 2 * TILE_ELEMS * (int)sizeof(double)));
+    attr_set[dev] = true;
+  }
+  return 0;
+}
+
+void fill_update_args(LargeUpdateArgs& u, const cherry_fit_args& a, const Plan& p, char* base) {
+  u.S = a.S; u.K = a.K; u.mask = a.mask; u.theta = a.theta; u.adam_m = a.adam_m; u.adam_v = a.adam_v;
+  u.Q = a.Q; u.Q_best = a.Q_best; u.Q_last = a.Q_last; u.best_loss = a.best_loss;
+  u.loss_trace = a.loss_trace; u.loss_trace_epochs = a.loss_trace_epochs; u.snapshots = a.snapshots;
+  u.n_snapshots = a.n_snapshots; u.G = a.dQ_part; u.loss_part = a.loss_part; u.sumC = a.sumC;
+  u.epoch_counter = a.epoch_counter;
+  u.grad_theta = reinterpret_cast<double*>(base + p.off_grad_theta);
+  u.dpi = reinterpret_cast<double*>(base + p.off_dpi);
+  u.pibuf = reinterpret_cast<double*>(base + p.off_pibuf);
+  u.lr_pi = a.lr_pi; u.lr_upper = a.lr_upper; u.beta1 = a.beta1; u.beta2 = a.beta2; u.eps = a.eps;
+  u.do_adam = a.do_adam; u.loss_normalization = a.loss_normalization; u.best_mode = a.best_mode;
+}
+
+int check_large(const cherry_fit_args& a, Plan& p) {
+  if (a.n_problems != 1)
+    return cherry::fail(CHERRY_ELIMIT, "fit: batched problems are supported for S <= %d only", cherry::kSmallFitMaxS);
+  make_plan(p, a.S, a.K, nullptr);
+  if (!a.workspace || a.workspace_bytes < p.total_bytes)
+    return cherry::fail(CHERRY_EINVAL, "fit: workspace of %zu bytes required, got %zu", p.total_bytes,
+                        a.workspace_bytes);
+  return 0;
+}
+
+}  // namespace
 
 namespace cherry {
 
-int fit_large_workspace_bytes(int S, int, int, size_t*) {
-  return fail(CHERRY_ELIMIT, "fit: S=%d > %d is not implemented yet", S, kSmallFitMaxS);
+int fit_large_workspace_bytes(int S, int K, int n_problems, size_t* bytes) {
+  if (n_problems != 1) return fail(CHERRY_ELIMIT, "fit: batched problems are supported for S <= %d only", kSmallFitMaxS);
+  Plan p;
+  make_plan(p, S, K, nullptr);
+  *bytes = p.total_bytes;
+  return 0;
 }
-int fit_large_expm(const cherry_fit_args& a, cudaStream_t) {
-  return fail(CHERRY_ELIMIT, "fit: S=%d > %d is not implemented yet", a.S, kSmallFitMaxS);
+
+// Uploads the GEMM task lists (absolute pointers into this workspace).  Synchronous.
+int fit_large_prepare(const cherry_fit_args& a, cudaStream_t stream) {
+  Plan p;
+  int rc = check_large(a, p);
+  if (rc) return rc;
+  char* base = reinterpret_cast<char*>(a.workspace);
+  make_plan(p, a.S, a.K, base);
+  CHERRY_CUDA(cudaStreamSynchronize(stream));
+  CHERRY_CUDA(cudaMemcpy(base + p.off_tasks, p.tasks.data(), p.tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice));
+  CHERRY_CUDA(cudaMemcpy(base + p.off_terms, p.terms.data(), p.terms.size() * sizeof(GemmTerm), cudaMemcpyHostToDevice));
+  CHERRY_CUDA(cudaMemset(base + p.off_scalars, 0, sizeof(LargeScalars)));
+  // chain slots are read as "Xbar" for inactive levels never; but slot 1 of every bucket is
+  // always written by loss_grad (s = 0) or the backward chain, so no clearing is needed.
+  return 0;
 }
-int fit_large_update(const cherry_fit_args& a, int, cudaStream_t) {
-  return fail(CHERRY_ELIMIT, "fit: S=%d > %d is not implemented yet", a.S, kSmallFitMaxS);
+
+int fit_large_expm(const cherry_fit_args& a, cudaStream_t stream) {
+  Plan p;
+  int rc = check_large(a, p);
+  if (rc) return rc;
+  if ((rc = ensure_gemm_attr())) return rc;
+  char* base = reinterpret_cast<char*>(a.workspace);
+  make_plan(p, a.S, a.K, base);  // host-side group table (cheap); device copies were uploaded by prepare
+  LargeScalars* sc = reinterpret_cast<LargeScalars*>(base + p.off_scalars);
+  int* s_arr = reinterpret_cast<int*>(base + p.off_s);
+  double* tau = reinterpret_cast<double*>(base + p.off_tau);
+  double* w = reinterpret_cast<double*>(base + p.off_w);
+  double* loss_partial = reinterpret_cast<double*>(base + p.off_loss_partial);
+  double* P = reinterpret_cast<double*>(base + p.off_P);
+  double* Pbar = reinterpret_cast<double*>(base + p.off_Pbar);
+  double* X0 = reinterpret_cast<double*>(base + p.off_X0);
+  double* chain = reinterpret_cast<double*>(base + p.off_chain);
+  const int eb = (int)((p.n_p + EW_THREADS - 1) / EW_THREADS);
+  const size_t wsmem = sizeof(double) * a.K * (kDeg + 1);
+  if (wsmem > 200 * 1024) return fail(CHERRY_ELIMIT, "fit_large: K=%d too large for the weight table", a.K);
+
+  build_B_kernel<<<(p.Sp + 7) / 8, EW_THREADS, 0, stream>>>(a.Q, a.S, p.Sp, P, sc);
+  CHERRY_LAUNCH_CHECK("build_B_kernel");
+  coef_kernel<<<1, 256, 0, stream>>>(a.t, a.K, sc, s_arr, w, tau, a.status_flag);
+  CHERRY_LAUNCH_CHECK("coef_kernel");
+  for (const Group& g : p.pow_fwd)
+    if ((rc = launch_group(p, g, base, stream))) return rc;
+  static bool ew_attr[64] = {false};
+  {
+    int dev = 0;
+    CHERRY_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !ew_attr[dev]) {
+      CHERRY_CUDA(cudaFuncSetAttribute(poly_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CHERRY_CUDA(cudaFuncSetAttribute(accumulate_M_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      ew_attr[dev] = true;
+    }
+  }
+  poly_eval_kernel<<<eb, EW_THREADS, wsmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, X0);
+  CHERRY_LAUNCH_CHECK("poly_eval_kernel");
+  for (const Group& g : p.sq_fwd)
+    if ((rc = launch_group(p, g, base, stream))) return rc;
+  loss_grad_kernel<<<dim3(p.loss_blocks, a.K), EW_THREADS, 0, stream>>>(a.C, a.S, p.Sp, p.n_p, s_arr, X0, chain,
+                                                                        p.slots_per_bucket, loss_partial);
+  CHERRY_LAUNCH_CHECK("loss_grad_kernel");
+  loss_reduce_kernel<<<1, 256, 0, stream>>>(loss_partial, a.K, p.loss_blocks, a.loss_part);
+  CHERRY_LAUNCH_CHECK("loss_reduce_kernel");
+  for (const Group& g : p.sq_bwd)
+    if ((rc = launch_group(p, g, base, stream))) return rc;
+  accumulate_M_kernel<<<eb, EW_THREADS, wsmem, stream>>>(chain, p.slots_per_bucket, p.n_p, a.K, w, Pbar);
+  CHERRY_LAUNCH_CHECK("accumulate_M_kernel");
+  for (const Group& g : p.pow_bwd)
+    if ((rc = launch_group(p, g, base, stream))) return rc;
+  unpad_kernel<<<(a.S * a.S + 255) / 256, 256, 0, stream>>>(Pbar, a.S, p.Sp, a.dQ_part);
+  CHERRY_LAUNCH_CHECK("unpad_kernel");
+  return 0;
+}
+
+int fit_large_update(const cherry_fit_args& a, int mode, cudaStream_t stream) {
+  Plan p;
+  int rc = check_large(a, p);
+  if (rc) return rc;
+  char* base = reinterpret_cast<char*>(a.workspace);
+  if (mode == 0 && (rc = fit_large_prepare(a, stream))) return rc;
+  LargeUpdateArgs u;
+  fill_update_args(u, a, p, base);
+  const size_t smem = sizeof(double) * a.S;
+  if (mode == 1) {
+    large_update_rows_kernel<<<a.S, EW_THREADS, smem, stream>>>(u);
+    CHERRY_LAUNCH_CHECK("large_update_rows_kernel");
+    const int n_theta = a.S + a.S * (a.S - 1) / 2;
+    large_update_step_kernel<<<(n_theta + EW_THREADS - 1) / EW_THREADS, EW_THREADS, smem, stream>>>(u);
+    CHERRY_LAUNCH_CHECK("large_update_step_kernel");
+  }
+  large_build_Q_kernel<<<a.S, EW_THREADS, smem, stream>>>(u, mode);
+  CHERRY_LAUNCH_CHECK("large_build_Q_kernel");
+  return 0;
 }
 
 }  // namespace cherry

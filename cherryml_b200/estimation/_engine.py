@@ -134,7 +134,9 @@ class FitEngine:
         self.loss_trace = torch.full((max(1, self.num_epochs), P), float("nan"), **f64)
         self.n_snapshots = (int(math.floor(math.log2(self.num_epochs))) + 1) if (self.num_epochs >= 1 and P == 1) else 0
         self.snapshots = torch.zeros((max(1, self.n_snapshots), S, S), **f64)
-        self.dQ_part = torch.zeros((P * K, S, S), **f64)
+        # S <= 32: one gradient piece per bucket (reduced in fixed order by the update kernel);
+        # larger S: the large path reduces internally and leaves the total in dQ_part[0]
+        self.dQ_part = torch.zeros((P * K if S <= 32 else P, S, S), **f64)
         self.loss_part = torch.zeros((P * K,), **f64)
         nbytes = ctypes.c_size_t(0)
         _lib.check(self.lib.cherry_fit_workspace_bytes(S, K, P, ctypes.byref(nbytes)), "cherry_fit_workspace_bytes")

@@ -102,6 +102,14 @@ def main():
     co_counts = os.path.join(tempfile.mkdtemp(), "co_counts.txt")
     write_counts_txt(co_counts, z["q"], pair_states, z["counts"])
 
+    # the two 400x400 inputs of the co-evolution cases, kept as one compressed archive
+    from cherryml_b200.io import read_mask_matrix, read_rate_matrix
+
+    np.savez_compressed(
+        os.path.join(inputs, "co400_inputs.npz"),
+        coevolution=read_rate_matrix(os.path.join(REF, "data/rate_matrices/coevolution/coevolution.txt")).to_numpy(),
+        aa_coevolution_mask=read_mask_matrix(os.path.join(REF, "data/mask_matrices/aa_coevolution_mask.txt")).to_numpy().astype(np.int8),
+    )
     run_case("toy3_init", f"{inputs}/matrices_toy.txt", f"{inputs}/3x3_pande_reversible_initialization.txt", None, 60)
     run_case("toy3_init_mask", f"{inputs}/matrices_toy.txt", f"{inputs}/3x3_pande_reversible_initialization_mask.txt",
              f"{inputs}/3x3_mask.txt", 60)

@@ -148,3 +148,67 @@ def test_loss_decreases_and_graph_replay_equals_eager():
     ra, rb = a.results(), b.results()
     assert np.array_equal(ra["loss"], rb["loss"]) and np.array_equal(ra["Q_best"], rb["Q_best"])
     assert ra["loss"][-1] < ra["loss"][0]
+
+
+# ----------------------------------------------------------------- large state spaces (S > 32)
+CO_COUNTS = os.path.join(os.path.dirname(FIT), "counting/medium3/refcpp_count_co_matrices_dir_cherries_plus_plus/result.npz")
+
+
+@pytest.mark.parametrize("S,K", [(36, 6), (64, 5), (100, 7), (400, 4)])
+def test_large_loss_and_gradient_match_the_oracle(S, K):
+    rng = np.random.default_rng(S)
+    times = np.exp(rng.uniform(np.log(1e-5), np.log(40.0), K))
+    times[0], times[-1] = 1e-6, 55.0  # no squaring / many squarings
+    Q = random_rate_matrix(S, rng, scale=2.0 / S)
+    counts = rng.integers(0, 50, size=(K, S, S)).astype(np.float64)
+    counts[rng.random(counts.shape) < 0.5] = 0.0
+    eng = FitEngine(times, counts, random_theta(S), num_epochs=0)
+    eng.Q.copy_(torch.from_numpy(Q)[None])
+    loss, grad = eng.loss_and_grad()
+    exp_loss, exp_grad = loss_and_grad_oracle(Q, times, counts)
+    assert abs(float(loss[0]) - exp_loss) < 1e-10 * abs(exp_loss)
+    g = grad[0].cpu().numpy()
+    assert np.max(np.abs(g - exp_grad)) < 1e-9 * np.max(np.abs(exp_grad))
+
+
+def _co_inputs():
+    z = np.load(CO_COUNTS)
+    return z["q"], z["counts"]
+
+
+@pytest.mark.parametrize("name,init,mask", [
+    ("co400_init", "coevolution", None),
+    ("co400_noinit_mask", None, "aa_coevolution_mask"),
+])
+def test_large_fit_matches_fp64_oracle_and_reference_run(name, init, mask):
+    q, counts = _co_inputs()
+    g = np.load(os.path.join(FIT, name, "reference_run.npz"))
+    big = np.load(os.path.join(FIT, "inputs", "co400_inputs.npz"))
+    init_a = big["coevolution"] if init else None
+    mask_a = big["aa_coevolution_mask"].astype(np.float64) if mask else None
+    n = int(g["num_epochs"])
+    res = _run_engine(q, counts, init_a, mask_a, g)
+    ref = fit_oracle(q, counts, mask_a, init_a, float(g["lr"]), n, dtype=torch.float64)
+    assert np.max(np.abs(res["loss"] - ref["loss"]) / np.abs(ref["loss"])) < REL_FP64
+    for key in ("Q_1", "Q_2", "Q_4", "Q_best", "Q_last"):
+        scale = np.max(np.abs(ref[key]))
+        assert np.max(np.abs(res[key] - ref[key])) < REL_FP64 * scale, key
+    assert np.max(np.abs(res["loss"] - g["loss"]) / np.abs(g["loss"])) < REL_FP32
+    for key in ("Q_1", "Q_last", "result"):
+        mine = res["Q_best"] if key == "result" else res[key]
+        assert np.max(np.abs(mine - g[key])) < REL_FP32 * np.max(np.abs(g[key])), key
+
+
+def test_large_fit_small_padded_case_vs_oracle():
+    """S = 36 (six-letter alphabet pairs): padded to 80 internally; 12 epochs of Adam."""
+    rng = np.random.default_rng(9)
+    S, K = 36, 8
+    times = np.exp(rng.uniform(np.log(0.01), np.log(5.0), K))
+    counts = rng.integers(0, 40, size=(K, S, S)).astype(np.float64)
+    theta0 = random_theta(S)
+    eng = FitEngine(times, counts, theta0, num_epochs=12)
+    eng.run()
+    res = eng.results()
+    ref = fit_oracle(times, counts, None, None, 0.1, 12, dtype=torch.float64)
+    assert np.max(np.abs(res["loss"] - ref["loss"]) / np.abs(ref["loss"])) < REL_FP64
+    assert np.max(np.abs(res["Q_best"] - ref["Q_best"])) < REL_FP64 * np.max(np.abs(ref["Q_best"]))
