@@ -368,7 +368,7 @@ def run_ours(args):
         try:
             from cherryml_b200.estimation import bench_fit
 
-            line["fit"] = bench_fit(device)
+            line["fit"] = bench_fit(device, lg_times=grid, lg_counts=counts)
         except ImportError:
             pass
     if world == 1 and not args.no_cpu_baseline:

@@ -61,6 +61,7 @@ _SIGNATURES = {
     "cherry_fit_init": (c_int, [_P, _P]),
     "cherry_fit_run": (c_int, [_P, c_int, _P]),
     "cherry_fit_loss_grad": (c_int, [_P, _P]),
+    "cherry_fit_schedule": (c_int, [_P, _P, _P, _P]),
     "cherry_count_lg_host": (
         c_int,
         [_P, c_int64, _P, c_int, _P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int,

@@ -57,6 +57,15 @@ int cherry_fit_loss_grad(const cherry_fit_args* a, void* stream) {
   return cherry::fit_large_expm(*a, (cudaStream_t)stream);
 }
 
+int cherry_fit_schedule(const cherry_fit_args* a, int* squarings_out, double* mu_out, int* degree_out) {
+  if (!a || !squarings_out) return cherry::fail(CHERRY_EINVAL, "fit_schedule: null pointer");
+  if (a->S <= cherry::kSmallFitMaxS)
+    return cherry::fail(CHERRY_EINVAL, "fit_schedule: only the large-S path (S > %d) records its schedule",
+                        cherry::kSmallFitMaxS);
+  if (degree_out) *degree_out = cherry::kLargeDegree;
+  return cherry::fit_large_read_schedule(*a, squarings_out, mu_out);
+}
+
 int cherry_fit_run(const cherry_fit_args* a, int num_epochs, void* stream_) {
   int rc = check_args(a, true);
   if (rc) return rc;

@@ -793,6 +793,22 @@ int fit_large_expm(const cherry_fit_args& a, cudaStream_t stream) {
   return 0;
 }
 
+// Host copy of the per-bucket squaring counts of the most recent evaluation (synchronises).
+int fit_large_read_schedule(const cherry_fit_args& a, int* s_out, double* mu_out) {
+  Plan p;
+  int rc = check_large(a, p);
+  if (rc) return rc;
+  char* base = reinterpret_cast<char*>(a.workspace);
+  CHERRY_CUDA(cudaDeviceSynchronize());
+  CHERRY_CUDA(cudaMemcpy(s_out, base + p.off_s, sizeof(int) * a.K, cudaMemcpyDeviceToHost));
+  if (mu_out) {
+    LargeScalars sc;
+    CHERRY_CUDA(cudaMemcpy(&sc, base + p.off_scalars, sizeof(sc), cudaMemcpyDeviceToHost));
+    *mu_out = sc.mu;
+  }
+  return 0;
+}
+
 int fit_large_update(const cherry_fit_args& a, int mode, cudaStream_t stream) {
   Plan p;
   int rc = check_large(a, p);

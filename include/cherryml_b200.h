@@ -177,6 +177,12 @@ int cherry_fit_run(const cherry_fit_args* args, int num_epochs, void* stream);
  * -<C_k, log expm(t_k Q_p)> and dQ_part[p*K+k] = its gradient with respect to Q_p. */
 int cherry_fit_loss_grad(const cherry_fit_args* args, void* stream);
 
+/* Large-S path only (S > 32): host copy of the squarings s_k chosen for every bucket in the most
+ * recent evaluation, the diagonal shift mu and the Taylor degree m.  One evaluation runs
+ * (m-1) + sum_k s_k products of S x S matrices forward and twice that backward; bench.py uses
+ * this to turn kernel time into executed FLOP/s.  Synchronises the device. */
+int cherry_fit_schedule(const cherry_fit_args* args, int* squarings_out, double* mu_out, int* degree_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,23 @@
+"""JTT-IPW initialiser against the reference's hand-verified goldens
+(tests/estimation_tests/jtt_ipw_test.py:11-74; goldens copied to tests/golden/jtt)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from cherryml_b200.estimation._jtt_ipw import jtt_ipw_from_counts
+from cherryml_b200.io import read_count_matrices_array, read_mask_matrix
+from tests.conftest import GOLDEN
+
+INP = os.path.join(GOLDEN, "fit", "inputs")
+
+
+@pytest.mark.parametrize("use_ipw", [True, False])
+@pytest.mark.parametrize("masked", [False, True])
+def test_jtt_ipw_toy_goldens(use_ipw, masked):
+    q, _, counts = read_count_matrices_array(os.path.join(INP, "matrices_toy.txt"))
+    mask = read_mask_matrix(os.path.join(INP, "3x3_mask.txt")).to_numpy() if masked else None
+    got = jtt_ipw_from_counts(q, torch.from_numpy(counts), mask=mask, use_ipw=use_ipw)
+    name = f"Q1_JTT{'-IPW' if use_ipw else ''}_on_toy_matrix{'_mask' if masked else ''}.txt"
+    np.testing.assert_almost_equal(got, np.loadtxt(os.path.join(GOLDEN, "jtt", name)))
