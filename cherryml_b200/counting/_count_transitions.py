@@ -48,7 +48,7 @@ def _rank_world(process_group):
     return dist.get_rank(process_group), dist.get_world_size(process_group)
 
 
-def _finish(counts_dev, grid, states, out_dir, style, start_time, num_processes, rank):
+def _finish(counts_dev, grid, states, out_dir, style, start_time, num_processes, rank, process_group=None):
     _DEVICE_RESULTS[os.path.realpath(out_dir)] = (grid, list(states), counts_dev)
     if rank == 0:
         counts = counts_dev.cpu().numpy()
@@ -60,6 +60,10 @@ def _finish(counts_dev, grid, states, out_dir, style, start_time, num_processes,
                 f"Total time: {time.time() - start_time} seconds with "
                 f"{num_processes} processes.\n"
             )
+    if process_group is not None:
+        import torch.distributed as dist
+
+        dist.barrier(process_group)  # result.txt exists before any rank returns
 
 
 @caching.cached_computation(
@@ -110,7 +114,7 @@ def count_transitions(
     )
     style = result_style or ("cpp" if use_cpp_implementation else "python")
     _finish(counts, np.array(sorted(quantization_points)), list(amino_acids),
-            output_count_matrices_dir, style, start_time, num_processes, rank)
+            output_count_matrices_dir, style, start_time, num_processes, rank, process_group)
     logger.info("Done!")
 
 
@@ -164,5 +168,5 @@ def count_co_transitions(
     pair_states = [a + b for a in amino_acids for b in amino_acids]
     style = result_style or ("cpp" if use_cpp_implementation else "python")
     _finish(counts, np.array(sorted(quantization_points)), pair_states,
-            output_count_matrices_dir, style, start_time, num_processes, rank)
+            output_count_matrices_dir, style, start_time, num_processes, rank, process_group)
     logger.info("Done!")
