@@ -40,11 +40,19 @@ __device__ __forceinline__ int quantize_bucket(double t, const double* __restric
   }
   if (lo == 0) return 0;
   double left = q[lo - 1], right = q[lo];
+  // The reference compares t/left - 1 < right/t - 1.  In exact arithmetic that is
+  // t*t < left*right; both quotients are ~1.0x, so their rounding can only flip the outcome
+  // when the two sides agree to ~1e-15.  Decide by the products when the margin is clear
+  // (>= 1e-12 relative) and only otherwise evaluate the reference expression itself.
+  const double tt = __dmul_rn(t, t), lr = __dmul_rn(left, right);
+  if (fabs(tt - lr) > 1e-12 * lr) return (tt < lr) ? lo - 1 : lo;
   double el = __dsub_rn(__ddiv_rn(t, left), 1.0);
   double er = __dsub_rn(__ddiv_rn(right, t), 1.0);
   return (el < er) ? lo - 1 : lo;
 }
 
+// One thread per pair: all r_pad entries of its row (r_pad is a multiple of 4, the row is
+// written as 32-bit words).
 __global__ void bucket_table_kernel(const double* __restrict__ pair_t,
                                     const int32_t* __restrict__ pair_fam,
                                     const cherry_fam_desc* __restrict__ fams,
@@ -54,19 +62,26 @@ __global__ void bucket_table_kernel(const double* __restrict__ pair_t,
   extern __shared__ double sgrid[];
   for (int i = threadIdx.x; i < K; i += blockDim.x) sgrid[i] = grid[i];
   __syncthreads();
-  int64_t total = n_pairs * r_pad;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t p = idx / r_pad;
-    int r = (int)(idx - p * r_pad);
-    const cherry_fam_desc fd = fams[pair_fam[p]];
-    uint8_t out = CHERRY_NO_BUCKET;
-    if (r < fd.n_rates) {
-      double t = __dmul_rn(pair_t[p], rate_vals[fd.rate_off + r]);
-      int b = quantize_bucket(t, sgrid, K);
-      if (b >= 0) out = (uint8_t)b;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_pairs;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    const cherry_fam_desc* fd = fams + pair_fam[p];
+    const int n_rates = fd->n_rates;
+    const double* __restrict__ rv = rate_vals + fd->rate_off;
+    const double t0 = pair_t[p];
+    uint32_t* __restrict__ row = reinterpret_cast<uint32_t*>(tab + p * r_pad);
+    for (int r0 = 0; r0 < r_pad; r0 += 4) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t out = CHERRY_NO_BUCKET;
+        if (r0 + k < n_rates) {
+          const int b = quantize_bucket(__dmul_rn(t0, rv[r0 + k]), sgrid, K);
+          if (b >= 0) out = (uint32_t)b;
+        }
+        word |= out << (8 * k);
+      }
+      row[r0 >> 2] = word;
     }
-    tab[idx] = out;
   }
 }
 
@@ -324,8 +339,8 @@ int cherry_build_bucket_table(const double* pair_t, const int32_t* pair_fam,
     return cherry::fail(CHERRY_ELIMIT, "bucket_table: K=%d outside 1..%d", K, CHERRY_MAX_BUCKETS);
   if (n_pairs < 0 || r_pad <= 0) return cherry::fail(CHERRY_EINVAL, "bucket_table: bad sizes");
   if (n_pairs == 0) return 0;
-  int64_t total = n_pairs * r_pad;
-  int blocks = (int)((total + 255) / 256);
+  if (r_pad % 4 != 0) return cherry::fail(CHERRY_EINVAL, "bucket_table: r_pad must be a multiple of 4");
+  int blocks = (int)((n_pairs + 255) / 256);
   int cap = cherry::sm_count() * 8;
   if (blocks > cap) blocks = cap;
   bucket_table_kernel<<<blocks, 256, K * sizeof(double), (cudaStream_t)stream>>>(

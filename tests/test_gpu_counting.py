@@ -222,3 +222,26 @@ def test_full_size_properties_lg():
     d3.n_tiles = 64 * (dev.n_tiles // 2048)
     got = symmetrize(count_raw(d3, grid_dev, K, 20), "lg", K, 20, False).cpu().numpy()
     assert np.array_equal(got, exp)
+
+
+def test_bucket_table_at_bucket_boundaries():
+    """t*rate exactly at / one ulp around the geometric midpoints and the grid points: the
+    product-based fast comparison must fall back to the reference expression where needed."""
+    from cherryml_b200.counting._device import build_bucket_table
+    from oracle.native import quantization_idx_c
+
+    grid = np.array(sorted(GRID_LG))
+    mids = np.sqrt(grid[:-1] * grid[1:])
+    ts = np.concatenate([mids, np.nextafter(mids, 0), np.nextafter(mids, np.inf), grid, np.nextafter(grid, 0),
+                         np.nextafter(grid, np.inf), 0.5 * (grid[:-1] + grid[1:]),
+                         np.exp(np.random.default_rng(0).uniform(np.log(grid[0] / 2), np.log(grid[-1] * 2), 5000))])
+    syn = synthetic_lg(1, 2 * len(ts), 16, 4, seed=0)
+    syn["pair_t"] = torch.from_numpy(ts.copy())
+    rates = np.array([1.0, 0.5, 3.0, 1.0 / 3.0])
+    syn["rate_vals"] = rates.copy()
+    dev = as_device_batch(syn, "cuda")
+    tab = build_bucket_table(dev, torch.from_numpy(grid).cuda(), len(grid)).cpu().numpy().reshape(len(ts), 4)
+    for i, t in enumerate(ts):
+        for r in range(4):
+            exp = quantization_idx_c(t * rates[r], grid)
+            assert tab[i, r] == (255 if exp < 0 else exp), (t, rates[r])
