@@ -57,6 +57,15 @@ int cherry_fit_loss_grad(const cherry_fit_args* a, void* stream) {
   return cherry::fit_large_expm(*a, (cudaStream_t)stream);
 }
 
+int cherry_gemm_f64_batched(const double* A, const double* B, double* C, int n, int batch, int trans_a,
+                            int trans_b, int accumulate, int ksplit, void* desc, double* partial,
+                            void* stream) {
+  return cherry::gemm_f64_batched(A, B, C, n, batch, trans_a, trans_b, accumulate, ksplit, desc, partial,
+                                  (cudaStream_t)stream);
+}
+
+size_t cherry_gemm_desc_bytes(int batch) { return cherry::gemm_desc_bytes(batch < 1 ? 1 : batch); }
+
 int cherry_fit_schedule(const cherry_fit_args* a, int* squarings_out, double* mu_out, int* degree_out) {
   if (!a || !squarings_out) return cherry::fail(CHERRY_EINVAL, "fit_schedule: null pointer");
   if (a->S <= cherry::kSmallFitMaxS)

@@ -793,6 +793,49 @@ int fit_large_expm(const cherry_fit_args& a, cudaStream_t stream) {
   return 0;
 }
 
+// Stand-alone batched GEMM through the same kernel (unit tests and the DMMA micro-benchmark):
+// C[b] = op(A[b]) op(B[b]) (+ C[b]) for `batch` square n x n matrices (n a multiple of 80),
+// consecutive in memory.  `desc` is a device scratch of cherry_gemm_desc_bytes(batch) bytes;
+// `partial` is needed only when ksplit > 1 (batch * ksplit * n * n doubles).  The descriptor
+// upload is synchronous; the launch itself is asynchronous on `stream`.
+int gemm_f64_batched(const double* A, const double* B, double* C, int n, int batch, int ta, int tb,
+                     int accumulate, int ksplit, void* desc, double* partial, cudaStream_t stream) {
+  if (!A || !B || !C || !desc) return fail(CHERRY_EINVAL, "gemm: null pointer argument");
+  if (n <= 0 || n % BT != 0 || batch <= 0 || ksplit < 1) return fail(CHERRY_EINVAL, "gemm: n must be a positive multiple of %d", BT);
+  if (ksplit > 1 && !partial) return fail(CHERRY_EINVAL, "gemm: split-K needs a partial buffer");
+  int rc = ensure_gemm_attr();
+  if (rc) return rc;
+  std::vector<GemmTask> tasks(batch);
+  std::vector<GemmTerm> terms(batch);
+  const size_t nn = (size_t)n * n;
+  for (int b = 0; b < batch; ++b) {
+    terms[b] = GemmTerm{A + b * nn, B + b * nn, ta, tb};
+    tasks[b].C = C + b * nn; tasks[b].cond = nullptr; tasks[b].term_begin = b; tasks[b].n_terms = 1;
+    tasks[b].accumulate = accumulate; tasks[b].level = 0;
+  }
+  char* d = reinterpret_cast<char*>(desc);
+  const size_t task_bytes = align256(sizeof(GemmTask) * batch);
+  CHERRY_CUDA(cudaStreamSynchronize(stream));
+  CHERRY_CUDA(cudaMemcpy(d, tasks.data(), sizeof(GemmTask) * batch, cudaMemcpyHostToDevice));
+  CHERRY_CUDA(cudaMemcpy(d + task_bytes, terms.data(), sizeof(GemmTerm) * batch, cudaMemcpyHostToDevice));
+  const GemmTask* dt = reinterpret_cast<const GemmTask*>(d);
+  const GemmTerm* dm = reinterpret_cast<const GemmTerm*>(d + task_bytes);
+  const size_t smem = (size_t)NSTAGE * 2 * TILE_ELEMS * sizeof(double);
+  dim3 grid((n / BT) * (n / BT), batch, ksplit);
+  gemm_tasks_kernel<<<grid, GEMM_THREADS, smem, stream>>>(dt, dm, n, ksplit, partial);
+  CHERRY_LAUNCH_CHECK("gemm_tasks_kernel");
+  if (ksplit > 1) {
+    int bx = (int)((nn + EW_THREADS * 4 - 1) / (EW_THREADS * 4));
+    splitk_reduce_kernel<<<dim3(bx, batch), EW_THREADS, 0, stream>>>(dt, ksplit, nn, partial);
+    CHERRY_LAUNCH_CHECK("splitk_reduce_kernel");
+  }
+  return 0;
+}
+
+size_t gemm_desc_bytes(int batch) {
+  return align256(sizeof(GemmTask) * (size_t)batch) + align256(sizeof(GemmTerm) * (size_t)batch);
+}
+
 // Host copy of the per-bucket squaring counts of the most recent evaluation (synchronises).
 int fit_large_read_schedule(const cherry_fit_args& a, int* s_out, double* mu_out) {
   Plan p;

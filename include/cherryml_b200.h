@@ -177,6 +177,17 @@ int cherry_fit_run(const cherry_fit_args* args, int num_epochs, void* stream);
  * -<C_k, log expm(t_k Q_p)> and dQ_part[p*K+k] = its gradient with respect to Q_p. */
 int cherry_fit_loss_grad(const cherry_fit_args* args, void* stream);
 
+/* The FP64 tensor-core GEMM of the large-S fit, stand-alone (unit tests, micro-benchmark):
+ * C[b] = op(A[b]) op(B[b]) (+ C[b] if accumulate), b < batch, square n x n row-major matrices
+ * stored back to back, n a multiple of 80.  desc: device scratch of
+ * cherry_gemm_desc_bytes(batch) bytes; partial: batch*ksplit*n*n doubles, needed iff ksplit > 1.
+ * This is what torch.matmul does inside torch.matrix_exp in the reference
+ * (estimation/_ratelearn/trainer.py:170-172). */
+int cherry_gemm_f64_batched(const double* A, const double* B, double* C, int n, int batch, int trans_a,
+                            int trans_b, int accumulate, int ksplit, void* desc, double* partial,
+                            void* stream);
+size_t cherry_gemm_desc_bytes(int batch);
+
 /* Large-S path only (S > 32): host copy of the squarings s_k chosen for every bucket in the most
  * recent evaluation, the diagonal shift mu and the Taylor degree m.  One evaluation runs
  * (m-1) + sum_k s_k products of S x S matrices forward and twice that backward; bench.py uses

@@ -216,3 +216,19 @@ def test_large_fit_small_padded_case_vs_oracle():
     ref = fit_oracle(times, counts, None, None, 0.1, 12, dtype=torch.float64)
     assert np.max(np.abs(res["loss"] - ref["loss"]) / np.abs(ref["loss"])) < REL_FP64
     assert np.max(np.abs(res["Q_best"] - ref["Q_best"])) < REL_FP64 * np.max(np.abs(ref["Q_best"]))
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("n,batch,ksplit", [(80, 3, 1), (160, 2, 2), (400, 2, 1), (400, 1, 5)])
+def test_dmma_gemm_matches_cublas(ta, tb, n, batch, ksplit):
+    from cherryml_b200.estimation._gemm import gemm_f64_batched
+
+    gen = torch.Generator(device="cuda").manual_seed(n + batch)
+    A = torch.randn(batch, n, n, dtype=torch.float64, device="cuda", generator=gen)
+    B = torch.randn(batch, n, n, dtype=torch.float64, device="cuda", generator=gen)
+    C0 = torch.randn(batch, n, n, dtype=torch.float64, device="cuda", generator=gen)
+    ref = torch.matmul(A.transpose(1, 2) if ta else A, B.transpose(1, 2) if tb else B)
+    got = gemm_f64_batched(A, B, ta, tb, ksplit=ksplit)
+    assert torch.allclose(got, ref, rtol=1e-12, atol=1e-11)
+    acc = gemm_f64_batched(A, B, ta, tb, C=C0.clone(), ksplit=ksplit)
+    assert torch.allclose(acc, ref + C0, rtol=1e-12, atol=1e-11)
