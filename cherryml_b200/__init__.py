@@ -9,3 +9,9 @@ __version__ = "0.1.0"
 
 from . import caching  # noqa: F401
 from .counting import count_co_transitions, count_transitions  # noqa: F401
+from .estimation import jtt_ipw, quantized_transitions_mle  # noqa: F401
+from ._public_api import (  # noqa: F401
+    cherryml_public_api,
+    coevolution_end_to_end_with_cherryml_optimizer,
+    lg_end_to_end_with_cherryml_optimizer,
+)

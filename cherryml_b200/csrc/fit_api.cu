@@ -57,6 +57,14 @@ int cherry_fit_loss_grad(const cherry_fit_args* a, void* stream) {
   return cherry::fit_large_expm(*a, (cudaStream_t)stream);
 }
 
+int cherry_expm_batched(const cherry_fit_args* a, double* P_out, void* stream) {
+  if (!a || !P_out) return cherry::fail(CHERRY_EINVAL, "expm_batched: null pointer argument");
+  if (a->S <= 0 || a->K <= 0 || a->n_problems <= 0 || !a->t || !a->Q || !a->status_flag)
+    return cherry::fail(CHERRY_EINVAL, "expm_batched: S, K, n_problems, t, Q and status_flag are required");
+  if (a->S <= cherry::kSmallFitMaxS) return cherry::fit_small_expm(*a, (cudaStream_t)stream, P_out);
+  return cherry::fit_large_forward_only(*a, P_out, (cudaStream_t)stream);
+}
+
 int cherry_gemm_f64_batched(const double* A, const double* B, double* C, int n, int batch, int trans_a,
                             int trans_b, int accumulate, int ksplit, void* desc, double* partial,
                             void* stream) {

@@ -341,6 +341,18 @@ accumulate_M_kernel(const double* __restrict__ chain, int slots_per_bucket, size
   for (int j = 0; j < kDeg; ++j) Pbar[(size_t)j * n_p + e] = acc[j];
 }
 
+// grid = (blocks, K): P_out[k] (S x S, unpadded) = X0_k if s_k == 0 else chain slot s_k
+__global__ void extract_P_kernel(const int* __restrict__ s_arr, const double* __restrict__ X0,
+                                 const double* __restrict__ chain, int slots_per_bucket, size_t n_p, int S,
+                                 int Sp, double* __restrict__ P_out) {
+  const int k = blockIdx.y, s = s_arr[k];
+  const double* P = (s == 0) ? X0 + (size_t)k * n_p : chain + ((size_t)k * slots_per_bucket + (s - 1)) * n_p;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < S * S; e += gridDim.x * blockDim.x) {
+    const int i = e / S, j = e - i * S;
+    P_out[(size_t)k * S * S + e] = P[(size_t)i * Sp + j];
+  }
+}
+
 __global__ void unpad_kernel(const double* __restrict__ src, int S, int Sp, double* __restrict__ dst) {
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < S * S; e += gridDim.x * blockDim.x) {
     const int i = e / S, j = e - i * S;
@@ -737,7 +749,19 @@ int fit_large_prepare(const cherry_fit_args& a, cudaStream_t stream) {
   return 0;
 }
 
-int fit_large_expm(const cherry_fit_args& a, cudaStream_t stream) {
+static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double* P_out);
+
+int fit_large_expm(const cherry_fit_args& a, cudaStream_t stream) { return fit_large_impl(a, stream, nullptr); }
+
+// expm(t_k Q) for every bucket into P_out [K][S][S]; prepares the workspace itself (synchronous).
+int fit_large_forward_only(const cherry_fit_args& a, double* P_out, cudaStream_t stream) {
+  if (!P_out) return fail(CHERRY_EINVAL, "expm: null output pointer");
+  int rc = fit_large_prepare(a, stream);
+  if (rc) return rc;
+  return fit_large_impl(a, stream, P_out);
+}
+
+static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double* P_out) {
   Plan p;
   int rc = check_large(a, p);
   if (rc) return rc;
@@ -777,6 +801,12 @@ int fit_large_expm(const cherry_fit_args& a, cudaStream_t stream) {
   CHERRY_LAUNCH_CHECK("poly_eval_kernel");
   for (const Group& g : p.sq_fwd)
     if ((rc = launch_group(p, g, base, stream))) return rc;
+  if (P_out != nullptr) {
+    extract_P_kernel<<<dim3((a.S * a.S + 255) / 256, a.K), 256, 0, stream>>>(s_arr, X0, chain, p.slots_per_bucket,
+                                                                             p.n_p, a.S, p.Sp, P_out);
+    CHERRY_LAUNCH_CHECK("extract_P_kernel");
+    return 0;
+  }
   loss_grad_kernel<<<dim3(p.loss_blocks, a.K), EW_THREADS, 0, stream>>>(a.C, a.S, p.Sp, p.n_p, s_arr, X0, chain,
                                                                         p.slots_per_bucket, loss_partial);
   CHERRY_LAUNCH_CHECK("loss_grad_kernel");

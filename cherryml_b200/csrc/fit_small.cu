@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(kSmallThreads)
 expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__ tall,
                      const double* __restrict__ Call, int S, int K, int n_smem_slots,
                      double* __restrict__ spill_all, int spill_slots, double* __restrict__ dQ_part,
-                     double* __restrict__ loss_part, int* __restrict__ overflow_flag) {
+                     double* __restrict__ loss_part, int* __restrict__ overflow_flag,
+                     double* __restrict__ P_out) {
   extern __shared__ double smem[];
   __shared__ double red[kSmallThreads / 32];
   __shared__ int sh_m, sh_s;
@@ -165,8 +166,15 @@ expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__
     mm<false, false, false>(slot(sX + i + 1), slot(sX + i), slot(sX + i), nt, ld);
     __syncthreads();
   }
-  // ---- loss and dL/dP (unnormalised): loss_k = -sum C log P, G = -C / P, skipping C == 0
   double* P = slot(sX + s);
+  if (P_out != nullptr) {  // forward only: hand back expm(t Q)
+    for (int e = tid; e < S * S; e += kSmallThreads) {
+      const int i = e / S, j = e - i * S;
+      P_out[(size_t)b * S * S + e] = P[i * ld + j];
+    }
+    return;
+  }
+  // ---- loss and dL/dP (unnormalised): loss_k = -sum C log P, G = -C / P, skipping C == 0
   double* G = slot(sG0);
   double part = 0.0;
   for (int e = tid; e < slot_elems; e += kSmallThreads) {
@@ -420,7 +428,7 @@ int fit_small_workspace(int S, int* n_smem_slots, int* spill_slots, size_t* slot
   return 0;
 }
 
-int fit_small_expm(const cherry_fit_args& a, cudaStream_t stream) {
+int fit_small_expm(const cherry_fit_args& a, cudaStream_t stream, double* P_out) {
   int ns = 0, sp = 0;
   size_t sb = 0, smem = 0;
   int rc = fit_small_workspace(a.S, &ns, &sp, &sb, &smem);
@@ -437,7 +445,8 @@ int fit_small_expm(const cherry_fit_args& a, cudaStream_t stream) {
     attr_set[dev] = true;
   }
   expm_loss_grad_small<<<a.n_problems * a.K, kSmallThreads, smem, stream>>>(
-      a.Q, a.t, a.C, a.S, a.K, ns, a.workspace, sp, a.dQ_part, a.loss_part, a.status_flag);
+      a.Q, a.t, a.C, a.S, a.K, ns, reinterpret_cast<double*>(a.workspace), sp, a.dQ_part, a.loss_part,
+      a.status_flag, P_out);
   CHERRY_LAUNCH_CHECK("expm_loss_grad_small");
   return 0;
 }

@@ -42,3 +42,57 @@ def jtt_ipw_from_counts(
     res = M[:, None] * ctps
     res = res - torch.diag(torch.diagonal(res)) - torch.diag(M)
     return res.cpu().numpy()
+
+
+def _jtt_ipw_stage():
+    import logging
+    import os
+    import time
+
+    from .. import caching
+    from ..io import read_count_matrices_array, read_mask_matrix, write_rate_matrix
+
+    logger = logging.getLogger(__name__)
+
+    @caching.cached_computation(output_dirs=["output_rate_matrix_dir"], write_extra_log_files=True)
+    def jtt_ipw(
+        count_matrices_path: str,
+        mask_path: Optional[str],
+        use_ipw: bool,
+        output_rate_matrix_dir: str,
+        normalize: bool = False,
+        max_time: Optional[float] = None,
+        pseudocounts: float = 1e-8,
+        symmetrize_count_matrices: bool = True,
+    ) -> None:
+        """JTT-IPW estimator; drop-in for the reference's ``cherryml.estimation.jtt_ipw``
+        (``estimation/_jtt_ipw.py:28-125``): same arguments, writes ``result.txt`` and
+        ``profiling.txt`` into ``output_rate_matrix_dir``."""
+        start_time = time.time()
+        logger.info("Starting")
+        from ..counting import device_result
+
+        resident = device_result(os.path.dirname(count_matrices_path))
+        if resident is not None and os.path.basename(count_matrices_path) == "result.txt":
+            q, states, counts = resident
+        else:
+            q, states, counts_np = read_count_matrices_array(count_matrices_path)
+            dev = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+            counts = torch.from_numpy(counts_np).to(dev)
+        mask = read_mask_matrix(mask_path).to_numpy() if mask_path is not None else None
+        res = jtt_ipw_from_counts(q, counts, mask=mask, use_ipw=use_ipw, pseudocounts=pseudocounts,
+                                  symmetrize_count_matrices=symmetrize_count_matrices, max_time=max_time)
+        if normalize:
+            from ._engine import solve_stationary_dist
+
+            pi = solve_stationary_dist(res)
+            res = res / (pi @ -np.diag(res))
+        write_rate_matrix(res, states, os.path.join(output_rate_matrix_dir, "result.txt"))
+        logger.info("Done!")
+        with open(os.path.join(output_rate_matrix_dir, "profiling.txt"), "w") as f:
+            f.write(f"Total time: {time.time() - start_time} seconds\n")
+
+    return jtt_ipw
+
+
+jtt_ipw = _jtt_ipw_stage()

@@ -1,0 +1,100 @@
+"""``matrix_exponential`` and friends: drop-in for the part of the reference's
+``cherryml/markov_chain/_markov_chain.py`` that sits on the hot path (:22-168).
+
+``matrix_exponential(exponents, Q, fact, reversible, device)`` returns the fp64 numpy array
+``[len(exponents), S, S]`` with ``res[i] = expm(exponents[i] * Q)``.  Both of the reference's
+back ends (``torch.matrix_exp`` and the eigendecomposition of a reversible model) compute the
+same mathematical object; here both are served by the CUDA expm of the fit
+(``cherry_expm_batched``: Taylor + scaling-and-squaring on the FP64 tensor pipe).  ``device`` is
+accepted for compatibility; the computation always runs on a CUDA device.
+"""
+import ctypes
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..estimation._engine import FitArgs, solve_stationary_dist
+
+
+def compute_stationary_distribution(rate_matrix: np.ndarray) -> np.ndarray:
+    return solve_stationary_dist(np.asarray(rate_matrix, dtype=np.float64))
+
+
+def compute_mutation_rate(rate_matrix: np.ndarray) -> float:
+    pi = compute_stationary_distribution(rate_matrix)
+    return float(pi @ -np.diag(rate_matrix))
+
+
+def normalized(rate_matrix: np.ndarray) -> np.ndarray:
+    return rate_matrix / compute_mutation_rate(rate_matrix)
+
+
+class FactorizedReversibleModel:
+    """Same factorisation object as the reference's (``_markov_chain.py:56-89``):
+    ``exp(tQ) = P2 @ U @ diag(exp(t D)) @ U_t @ P1``."""
+
+    def __init__(self, Q: np.ndarray) -> None:
+        Q = np.asarray(Q, dtype=np.float64)
+        pi = compute_stationary_distribution(Q)
+        P1 = np.diag(np.sqrt(pi))
+        P2 = np.diag(np.sqrt(1 / pi))
+        D, U = np.linalg.eigh(P1 @ Q @ P2)
+        self.P2, self.U, self.D, self.U_t, self.P1 = P2, U, D, U.transpose(), P1
+
+    def get_factorization(self):
+        return (self.P2, self.U, self.D, self.U_t, self.P1)
+
+    def rate_matrix(self) -> np.ndarray:
+        return self.P2 @ self.U @ np.diag(self.D) @ self.U_t @ self.P1
+
+
+def expm_batched(Q, exponents, device="cuda") -> torch.Tensor:
+    """``[K, S, S]`` CUDA fp64 tensor of ``expm(exponents[k] * Q)``."""
+    lib = _lib.load()
+    dev = torch.device(device if str(device).startswith("cuda") else "cuda")
+    Qt = torch.as_tensor(np.asarray(Q, dtype=np.float64)).to(dev).contiguous()
+    t = torch.as_tensor(np.asarray(exponents, dtype=np.float64).reshape(-1)).to(dev).contiguous()
+    S, K = int(Qt.shape[-1]), int(t.numel())
+    if K == 0:
+        return torch.zeros((0, S, S), dtype=torch.float64, device=dev)
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(lib.cherry_fit_workspace_bytes(S, K, 1, ctypes.byref(nbytes)), "cherry_fit_workspace_bytes")
+    ws = torch.empty(max(8, nbytes.value), dtype=torch.uint8, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    out = torch.empty((K, S, S), dtype=torch.float64, device=dev)
+    a = FitArgs()
+    a.S, a.K, a.n_problems = S, K, 1
+    a.t, a.Q = _lib.ptr(t), _lib.ptr(Qt)
+    a.workspace, a.workspace_bytes = _lib.ptr(ws), nbytes.value
+    a.status_flag = _lib.ptr(flag)
+    with torch.cuda.device(dev):
+        _lib.check(lib.cherry_expm_batched(ctypes.byref(a), _lib.ptr(out), _lib.current_stream_ptr()),
+                   "cherry_expm_batched")
+    if int(flag.item()) != 0:
+        raise _lib.CherryError("expm: exponent * rate is beyond the supported range (t * max|Q_ii| > 279)")
+    return out
+
+
+def matrix_exponential_pytorch(exponents: List[float], Q: np.ndarray, device: str) -> np.ndarray:
+    return expm_batched(Q, exponents, device).cpu().numpy()
+
+
+def matrix_exponential_reversible(exponents: List[float], fact: FactorizedReversibleModel, device: str) -> np.ndarray:
+    return expm_batched(fact.rate_matrix(), exponents, device).cpu().numpy()
+
+
+def matrix_exponential(exponents, Q: Optional[np.ndarray], fact: Optional[FactorizedReversibleModel],
+                       reversible: bool, device) -> np.ndarray:
+    if reversible:
+        return matrix_exponential_reversible(exponents, fact, device)
+    return matrix_exponential_pytorch(exponents, Q, device)
+
+
+def chain_product(rate_matrix_1: np.ndarray, rate_matrix_2: np.ndarray) -> np.ndarray:
+    """Rate matrix of two independent sites, state (i, j) -> index i*n + j
+    (reference ``_markov_chain.py:216-239``): Q1 (+) Q2 = Q1 x I + I x Q2."""
+    n = rate_matrix_1.shape[0]
+    eye = np.eye(n)
+    return np.kron(rate_matrix_1, eye) + np.kron(eye, rate_matrix_2)

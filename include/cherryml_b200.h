@@ -177,6 +177,11 @@ int cherry_fit_run(const cherry_fit_args* args, int num_epochs, void* stream);
  * -<C_k, log expm(t_k Q_p)> and dQ_part[p*K+k] = its gradient with respect to Q_p. */
 int cherry_fit_loss_grad(const cherry_fit_args* args, void* stream);
 
+/* P_out[p*K + k] = expm(t[p*K + k] * Q[p]) (fp64 [S][S] each) with the fit's forward algorithm.
+ * Only S, K, n_problems, t, Q, workspace(+bytes, as for the fit) and status_flag of `args` are
+ * read.  Replaces matrix_exponential_pytorch (reference markov_chain/_markov_chain.py:22-53). */
+int cherry_expm_batched(const cherry_fit_args* args, double* P_out, void* stream);
+
 /* The FP64 tensor-core GEMM of the large-S fit, stand-alone (unit tests, micro-benchmark):
  * C[b] = op(A[b]) op(B[b]) (+ C[b] if accumulate), b < batch, square n x n row-major matrices
  * stored back to back, n a multiple of 80.  desc: device scratch of

@@ -1,0 +1,84 @@
+"""BASELINE.json configs 1 and 2 end to end through ``cherryml_public_api`` on the reference's
+demo data (tests/golden/demo_data.tar.xz), against what the UNMODIFIED reference produced
+through its own public API (tests/golden/make_golden_e2e.py -> tests/golden/e2e/*.npz):
+counts bit-exact, JTT-IPW initialisation to rounding, per-epoch losses and the learned rate
+matrix within the fp32 tolerance of the north star (the reference computes its expm in fp32)."""
+import os
+import tarfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from cherryml_b200 import caching, cherryml_public_api
+from cherryml_b200.io import read_count_matrices_array, read_rate_matrix
+from tests.conftest import GOLDEN
+
+
+@pytest.fixture(scope="module")
+def demo(tmp_path_factory):
+    root = tmp_path_factory.mktemp("demo")
+    with tarfile.open(os.path.join(GOLDEN, "demo_data.tar.xz")) as tf:
+        tf.extractall(root)
+    yield str(root)
+    caching.set_cache_dir(None)
+
+
+def _only(path):
+    (h,) = os.listdir(path)
+    return os.path.join(path, h)
+
+
+def test_lg_demo_matches_reference_public_api(demo, tmp_path):
+    g = np.load(os.path.join(GOLDEN, "e2e", "lg.npz"))
+    cache, out = str(tmp_path / "cache"), str(tmp_path / "learned.txt")
+    cherryml_public_api(
+        output_path=out, model_name="LG", msa_dir=f"{demo}/msas", tree_dir=f"{demo}/trees",
+        site_rates_dir=f"{demo}/site_rates", cache_dir=cache, num_processes_counting=1,
+        use_cpp_counting_implementation=False, num_epochs=500,
+    )
+    q, states, counts = read_count_matrices_array(
+        os.path.join(_only(f"{cache}/count_transitions"), "output_count_matrices_dir", "result.txt"))
+    assert np.array_equal(q, g["q"]) and np.array_equal(counts, g["counts"])  # bit-exact
+    jtt = read_rate_matrix(os.path.join(_only(f"{cache}/jtt_ipw"), "output_rate_matrix_dir", "result.txt")).to_numpy()
+    assert np.max(np.abs(jtt - g["jtt_ipw"])) < 1e-12 * np.max(np.abs(g["jtt_ipw"]))
+    import pandas as pd
+
+    mle = os.path.join(_only(f"{cache}/quantized_transitions_mle"), "output_rate_matrix_dir")
+    loss = pd.read_csv(os.path.join(mle, "df_res.txt"))["loss"].to_numpy()
+    assert np.max(np.abs(loss - g["loss"]) / np.abs(g["loss"])) < 1e-4
+    learned = read_rate_matrix(out).to_numpy()
+    # the reference returns the best of 500 fp32 iterates; near convergence consecutive
+    # iterates differ by more than fp32 rounding, so the matrix tolerance is absolute-ish
+    assert np.max(np.abs(learned - g["learned"])) < 2e-3 * np.max(np.abs(g["learned"]))
+    last = read_rate_matrix(os.path.join(mle, "Q_last.txt")).to_numpy()
+    assert list(read_rate_matrix(out).index) == states and last.shape == (20, 20)
+
+
+def test_coevolution_demo_matches_reference_public_api(demo, tmp_path):
+    g = np.load(os.path.join(GOLDEN, "e2e", "coevolution.npz"))
+    cache, out = str(tmp_path / "cache"), str(tmp_path / "learned.txt")
+    n_epochs = len(g["loss"])
+    cherryml_public_api(
+        output_path=out, model_name="co-evolution", msa_dir=f"{demo}/msas", contact_map_dir=f"{demo}/contact_maps",
+        tree_dir=f"{demo}/trees", cache_dir=cache, num_processes_counting=1, num_processes_optimization=8,
+        use_cpp_counting_implementation=False, num_epochs=n_epochs,
+    )
+    from cherryml_b200.counting import device_result
+
+    cdir = os.path.join(_only(f"{cache}/count_co_transitions"), "output_count_matrices_dir")
+    q, states, counts_dev = device_result(cdir)
+    counts = counts_dev.cpu().numpy()
+    gold = np.zeros(tuple(g["counts_shape"]))
+    gold[tuple(g["counts_idx"])] = g["counts_val"]
+    assert np.array_equal(np.asarray(q), g["q"]) and np.array_equal(counts, gold)  # bit-exact
+    jtt = read_rate_matrix(os.path.join(_only(f"{cache}/jtt_ipw"), "output_rate_matrix_dir", "result.txt")).to_numpy()
+    assert np.max(np.abs(jtt - g["jtt_ipw"])) < 1e-12 * np.max(np.abs(g["jtt_ipw"]))
+    import pandas as pd
+
+    mle = os.path.join(_only(f"{cache}/quantized_transitions_mle"), "output_rate_matrix_dir")
+    loss = pd.read_csv(os.path.join(mle, "df_res.txt"))["loss"].to_numpy()
+    assert np.max(np.abs(loss - g["loss"]) / np.abs(g["loss"])) < 1e-4
+    learned = read_rate_matrix(out).to_numpy()
+    assert np.max(np.abs(learned - g["learned"])) < 1e-4 * np.max(np.abs(g["learned"]))
