@@ -122,6 +122,8 @@ def cached_computation(
             if cache_dir is None:
                 return func(**kwargs)
             unhashed = list(exclude_args) + list(output_dirs)
+            for od in output_dirs:  # output dirs may be required parameters: bind them as None
+                kwargs.setdefault(od, None)
             binding = signature(func).bind(**kwargs)
             binding.apply_defaults()
             for arg in exclude_args_if_default:

@@ -54,8 +54,8 @@ def expm_batched(Q, exponents, device="cuda") -> torch.Tensor:
     """``[K, S, S]`` CUDA fp64 tensor of ``expm(exponents[k] * Q)``."""
     lib = _lib.load()
     dev = torch.device(device if str(device).startswith("cuda") else "cuda")
-    Qt = torch.as_tensor(np.asarray(Q, dtype=np.float64)).to(dev).contiguous()
-    t = torch.as_tensor(np.asarray(exponents, dtype=np.float64).reshape(-1)).to(dev).contiguous()
+    Qt = torch.from_numpy(np.array(Q, dtype=np.float64)).to(dev).contiguous()
+    t = torch.from_numpy(np.array(exponents, dtype=np.float64).reshape(-1)).to(dev).contiguous()
     S, K = int(Qt.shape[-1]), int(t.numel())
     if K == 0:
         return torch.zeros((0, S, S), dtype=torch.float64, device=dev)
