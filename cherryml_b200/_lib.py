@@ -55,6 +55,7 @@ _SIGNATURES = {
     "cherry_count_lg": (c_int, [_P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P]),
     "cherry_count_co": (c_int, [_P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P]),
     "cherry_validate_residues": (c_int, [_P, c_int64, c_int, _P, _P]),
+    "cherry_count_per_site": (c_int, [_P, _P, _P, c_int64, c_int, c_int64, _P, c_int, c_int, _P, _P]),
     "cherry_symmetrize_lg": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "cherry_symmetrize_co": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "cherry_fit_workspace_bytes": (c_int, [c_int, c_int, c_int, _P]),

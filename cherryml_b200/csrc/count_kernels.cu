@@ -263,6 +263,27 @@ count_co_kernel(const uint8_t* __restrict__ msa, const cherry_fam_desc* __restri
   }
 }
 
+// Per-site counting (SiteRM): one CTA per cherry; the cherry's bucket is quantised once (fp64,
+// same expression as everywhere else), then every site l adds one to counts[l][b][x][y].
+__global__ void __launch_bounds__(256)
+count_per_site_kernel(const uint8_t* __restrict__ xa, const uint8_t* __restrict__ xb,
+                      const double* __restrict__ t, const double* __restrict__ grid, int B, int L,
+                      int64_t row_stride, int S, unsigned long long* __restrict__ counts) {
+  __shared__ int sb;
+  const int64_t c = blockIdx.x;
+  if (threadIdx.x == 0) sb = quantize_bucket(t[c], grid, B);
+  __syncthreads();
+  const int b = sb;
+  if (b < 0) return;
+  const uint8_t* ra = xa + c * row_stride;
+  const uint8_t* rb = xb + c * row_stride;
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    const unsigned x = ra[l], y = rb[l];
+    if (x < (unsigned)S && y < (unsigned)S)
+      atomicAdd(counts + (((size_t)l * B + b) * S + x) * S + y, 1ull);
+  }
+}
+
 // flag[0] |= 1 if any residue byte exceeds S (contract violation).
 __global__ void validate_residues_kernel(const uint4* __restrict__ msa, int64_t n_vec, uint32_t S4,
                                          int* __restrict__ flag) {
@@ -401,6 +422,20 @@ int cherry_count_co(const uint8_t* msa, const cherry_fam_desc* fams, const int32
       msa, fams, pair_a, pair_b, tab, r_pad, reinterpret_cast<const int2*>(contacts), tiles,
       n_tiles, K, S, counts);
   CHERRY_LAUNCH_CHECK("count_co_kernel");
+  return 0;
+}
+
+int cherry_count_per_site(const uint8_t* xa, const uint8_t* xb, const double* t, int64_t n_cherries,
+                          int L, int64_t row_stride, const double* grid, int B, int S,
+                          unsigned long long* counts, void* stream) {
+  if (!xa || !xb || !t || !grid || !counts) return cherry::fail(CHERRY_EINVAL, "count_per_site: null pointer");
+  if (L <= 0 || B <= 0 || S <= 0 || S > 254 || row_stride < L || n_cherries < 0)
+    return cherry::fail(CHERRY_EINVAL, "count_per_site: bad sizes");
+  if (n_cherries == 0) return 0;
+  if (n_cherries > 0x7fffffff) return cherry::fail(CHERRY_ELIMIT, "count_per_site: too many cherries");
+  count_per_site_kernel<<<(unsigned)n_cherries, 256, 0, (cudaStream_t)stream>>>(xa, xb, t, grid, B, L, row_stride,
+                                                                                S, counts);
+  CHERRY_LAUNCH_CHECK("count_per_site_kernel");
   return 0;
 }
 

@@ -104,6 +104,15 @@ int cherry_count_co(const uint8_t* msa, const cherry_fam_desc* fams, const int32
                     const int32_t* contacts, const cherry_tile* tiles, int n_tiles, int K,
                     int S, uint32_t* counts, void* stream);
 
+/* Per-site counting (SiteRM): counts[l][b][x][y] += 1 for every cherry c and site l, where
+ * b = bucket of t[c] on `grid` (B ascending points), x = xa[c*row_stride + l], y = xb[...];
+ * cherries outside the grid and residues >= S are skipped.  counts: uint64 [L][B][S][S],
+ * accumulated into; symmetrise with cherry_symmetrize_lg(K = L*B).  Replaces
+ * _get_raw_count_matrices, reference _siterm/_site_specific_rate_matrix.py:189-261. */
+int cherry_count_per_site(const uint8_t* xa, const uint8_t* xb, const double* t, int64_t n_cherries,
+                          int L, int64_t row_stride, const double* grid, int B, int S,
+                          unsigned long long* counts, void* stream);
+
 /* Sets flag[0] (device int, caller zeroes it) to 1 if any of the n_bytes (multiple of 16)
  * residue bytes exceeds S.  Optional guard for buffers that did not come from this
  * package's encoder. */

@@ -47,3 +47,53 @@ def test_recovers_the_true_rate_matrices():
     g = np.load(os.path.join(G, "dna_noinit.npz"))
     r = quantized_transitions_mle_vectorized_over_sites(g["counts"], g["times"], num_epochs=100, initialization=None)
     assert np.mean((g["Q_true"] - r["res"]) ** 2) < 1e-3
+
+
+def _ref_raw_counts(transitions, q, alphabet, include_reverse=True):
+    """Literal restatement of the reference loop (_site_specific_rate_matrix.py:189-261) for the test."""
+    from oracle.counting_oracle import quantization_idx
+
+    a2i = {c: i for i, c in enumerate(alphabet)}
+    L, B, S = len(transitions[0][0]), len(q), len(alphabet)
+    out = np.zeros((L, B, S, S))
+    qa = np.array(q)
+    for x, y, t in transitions:
+        b = quantization_idx(t, qa)
+        if b is None:
+            continue
+        for l in range(L):
+            xl, yl = a2i.get(x[l], -1), a2i.get(y[l], -1)
+            if xl >= 0 and yl >= 0:
+                out[l, b, xl, yl] += 1.0
+    return (out + out.transpose(0, 1, 3, 2)) / 2.0 if include_reverse else out
+
+
+def test_per_site_counts_reference_example():
+    """The reference's in-module test (test_get_raw_count_matrices, :264-322)."""
+    from cherryml_b200.siterm import get_raw_count_matrices
+
+    transitions = [("AG", "BH", 0.35 + 0.36), ("EG", "FH", 0.49 + 0.410), ("CG", "DG", 0.17 + 0.28 + 0.01 + 0.02)]
+    alphabet = ["-", "A", "B", "C", "D", "E", "F", "G", "H", "I", "J", "K", "L", "M"]
+    q = [0.40, 0.80, 2.0]
+    for rev in (True, False):
+        got = get_raw_count_matrices(transitions, q, alphabet, include_reverse_transitions=rev)
+        assert got.shape == (2, 3, 14, 14)
+        assert np.array_equal(got, _ref_raw_counts(transitions, q, alphabet, rev))
+    a2i = {c: i for i, c in enumerate(alphabet)}
+    got = get_raw_count_matrices(transitions, q, alphabet)
+    assert got[0, 0, a2i["C"], a2i["D"]] == 0.5 and got[1, 0, a2i["G"], a2i["G"]] == 1.0
+    assert got[1, 1, a2i["G"], a2i["H"]] == 1.0 and got.sum() == 6.0
+
+
+def test_per_site_counts_random():
+    from cherryml_b200.siterm import get_raw_count_matrices
+
+    rng = np.random.default_rng(1)
+    alphabet = list("ARNDCQEGHILKMFPSTWYV")
+    letters = np.array(alphabet + ["-", "X"])
+    L, n = 331, 19
+    transitions = [("".join(rng.choice(letters, L)), "".join(rng.choice(letters, L)), float(t))
+                   for t in np.exp(rng.uniform(np.log(1e-3), np.log(30.0), n))]
+    q = [0.03 * 1.1 ** (8 * i) for i in range(-8, 9)]
+    got = get_raw_count_matrices(transitions, q, alphabet)
+    assert np.array_equal(got, _ref_raw_counts(transitions, q, alphabet))
