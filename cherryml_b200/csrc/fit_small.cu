@@ -22,7 +22,7 @@ namespace {
 using cherry::kMaxDegree;
 using cherry::kMaxSquarings;
 
-constexpr int kSmallThreads = 256;
+constexpr int kSmallThreads = 512;  // 16 warps: one 8x8 output tile per warp up to S = 32
 constexpr int kMaxSmallS = 32;
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
@@ -36,26 +36,40 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 //   A: lane -> (row = lane/4, k = lane%4);  B: (k = lane%4, col = lane/4);
 //   C: (row = lane/4, cols = 2*(lane%4), +1).
 // ld = spad + 4 makes all four access patterns bank-conflict free.
+// Latency matters more than throughput here (a bucket is a dependent chain of ~50 tiny
+// products): every warp owns one output tile, all operand fragments of the tile are loaded up
+// front (independent loads), and the k-steps alternate between two accumulators to halve the
+// DMMA dependency chain.
 template <bool TA, bool TB, bool ACC>
 __device__ __forceinline__ void mm(double* D, const double* A, const double* B, int nt, int ld) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tg = lane & 3;
-  const int spad = nt * 8;
+  constexpr int kMaxSteps = kMaxSmallS / 4;  // 8 k-steps of 4
+  const int nsteps = nt * 2;
   for (int tile = warp; tile < nt * nt; tile += kSmallThreads / 32) {
     const int r0 = (tile / nt) * 8, c0 = (tile % nt) * 8;
-    double d0 = 0.0, d1 = 0.0;
-    for (int k0 = 0; k0 < spad; k0 += 4) {
-      const double a = TA ? A[(k0 + tg) * ld + r0 + g] : A[(r0 + g) * ld + k0 + tg];
-      const double b = TB ? B[(c0 + g) * ld + k0 + tg] : B[(k0 + tg) * ld + c0 + g];
-      dmma884(d0, d1, a, b);
+    double a[kMaxSteps], b[kMaxSteps];
+#pragma unroll
+    for (int st = 0; st < kMaxSteps; ++st) {
+      if (st < nsteps) {
+        const int k0 = st * 4;
+        a[st] = TA ? A[(k0 + tg) * ld + r0 + g] : A[(r0 + g) * ld + k0 + tg];
+        b[st] = TB ? B[(c0 + g) * ld + k0 + tg] : B[(k0 + tg) * ld + c0 + g];
+      }
     }
     double* out = D + (r0 + g) * ld + c0 + 2 * tg;
+    double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
     if (ACC) {
-      d0 += out[0];
-      d1 += out[1];
+      d0 = out[0];
+      d1 = out[1];
     }
-    out[0] = d0;
-    out[1] = d1;
+#pragma unroll
+    for (int st = 0; st < kMaxSteps; st += 2) {
+      if (st < nsteps) dmma884(d0, d1, a[st], b[st]);
+      if (st + 1 < nsteps) dmma884(e0, e1, a[st + 1], b[st + 1]);
+    }
+    out[0] = d0 + e0;
+    out[1] = d1 + e1;
   }
 }
 
@@ -273,13 +287,24 @@ __global__ void __launch_bounds__(kSmallThreads) fit_update_small(UpdateArgs a) 
     // ---- reduce the per-bucket pieces in bucket order
     const double scale = a.loss_normalization ? 1.0 / a.sumC[p] : 1.0;
     for (int e = tid; e < SS; e += kSmallThreads) {
+      // loads of 8 buckets in flight, added in bucket order (same result as a plain loop)
       double acc = 0.0;
-      for (int k = 0; k < a.K; ++k) acc += a.dQ_part[((size_t)p * a.K + k) * SS + e];
+      const double* src = a.dQ_part + (size_t)p * a.K * SS + e;
+      for (int k0 = 0; k0 < a.K; k0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (k0 + j < a.K) ? src[(size_t)(k0 + j) * SS] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += v[j];
+      }
       G[e] = acc * scale;
     }
+    // stage the per-bucket losses in shared memory (parallel loads), then add them in order
+    for (int k = tid; k < a.K && k < SS; k += kSmallThreads) sv[k] = a.loss_part[(size_t)p * a.K + k];
+    __syncthreads();
     double lp = 0.0;
     if (tid == 0) {
-      for (int k = 0; k < a.K; ++k) lp += a.loss_part[(size_t)p * a.K + k];
+      for (int k = 0; k < a.K; ++k) lp += (k < SS) ? sv[k] : a.loss_part[(size_t)p * a.K + k];
       lp *= scale;
       if (epoch < a.num_epochs_total) a.loss_trace[(size_t)epoch * a.n_problems + p] = lp;
       const double best = a.best_loss[p];
