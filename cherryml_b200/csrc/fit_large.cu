@@ -22,6 +22,7 @@
 //
 // Replaces torch.matrix_exp + log + sum + autograd.backward + Adam of the reference's
 // train_quantization (estimation/_ratelearn/trainer.py:156-187) for S = 400.
+#include <cstdlib>
 #include <vector>
 
 #include "fit_common.cuh"
@@ -103,21 +104,12 @@ __device__ __forceinline__ void compute_chunk(const double* As, const double* Bs
   }
 }
 
-// C_task = sum over the task's terms of op(A) op(B)  (+ C_task if accumulate).  Square Sp x Sp
-// matrices, Sp a multiple of 80.  grid = (tiles, n_tasks, ksplit); with ksplit > 1 the CTA
-// writes its partial product to `partial[(task*ksplit + z)]` and splitk_reduce_kernel finishes.
-__global__ void __launch_bounds__(GEMM_THREADS)
-gemm_tasks_kernel(const GemmTask* __restrict__ tasks, const GemmTerm* __restrict__ terms, int Sp,
-                  int ksplit, double* __restrict__ partial) {
-  extern __shared__ double smem[];
-  const GemmTask task = tasks[blockIdx.y];
-  if (task.cond != nullptr && *task.cond <= task.level) return;
-  const int tiles_n = Sp / BT;
-  const int m0 = (blockIdx.x / tiles_n) * BT, n0 = (blockIdx.x % tiles_n) * BT;
-  const int cpt = Sp / BK;  // k chunks per term
-  const int total = task.n_terms * cpt;
-  const int z = blockIdx.z;
-  const int c_begin = (int)((long long)total * z / ksplit), c_end = (int)((long long)total * (z + 1) / ksplit);
+// Core of every GEMM here: one 80x80 output tile, accumulated over k chunks [c_begin, c_end) of
+// the concatenated terms, 3-stage cp.async pipeline, result (+ old value) stored to `out`.
+template <typename TermFn>
+__device__ __forceinline__ void gemm_tile(TermFn get_term, int Sp, int m0, int n0, int c_begin, int c_end,
+                                          double* smem, double* out, bool add_old) {
+  const int cpt = Sp / BK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const int rbase = (warp >> 1) * 40, cbase = (warp & 1) * 40;
   double acc[5][5][2];
@@ -125,9 +117,8 @@ gemm_tasks_kernel(const GemmTask* __restrict__ tasks, const GemmTerm* __restrict
   for (int i = 0; i < 5; ++i)
 #pragma unroll
     for (int j = 0; j < 5; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
   auto issue = [&](int c, int stage) {
-    const GemmTerm t = terms[task.term_begin + c / cpt];
+    const GemmTerm t = get_term(c / cpt);
     const int k0 = (c % cpt) * BK;
     double* As = smem + (size_t)stage * 2 * TILE_ELEMS;
     double* Bs = As + TILE_ELEMS;
@@ -146,7 +137,7 @@ gemm_tasks_kernel(const GemmTask* __restrict__ tasks, const GemmTerm* __restrict
     const int nxt = i + NSTAGE - 1;
     if (nxt < n_chunks) issue(c_begin + nxt, nxt % NSTAGE);
     cp_async_commit();
-    const GemmTerm t = terms[task.term_begin + (c_begin + i) / cpt];
+    const GemmTerm t = get_term((c_begin + i) / cpt);
     const double* As = smem + (size_t)(i % NSTAGE) * 2 * TILE_ELEMS;
     const double* Bs = As + TILE_ELEMS;
     if (t.ta) {
@@ -158,9 +149,6 @@ gemm_tasks_kernel(const GemmTask* __restrict__ tasks, const GemmTerm* __restrict
     }
   }
   cp_async_wait<0>();
-  double* out = (ksplit == 1) ? task.C
-                              : partial + ((size_t)blockIdx.y * ksplit + z) * (size_t)Sp * Sp;
-  const bool add_old = (ksplit == 1) && task.accumulate;
 #pragma unroll
   for (int i = 0; i < 5; ++i)
 #pragma unroll
@@ -174,6 +162,112 @@ gemm_tasks_kernel(const GemmTask* __restrict__ tasks, const GemmTerm* __restrict
       }
       *p = v;
     }
+}
+
+// C_task = sum over the task's terms of op(A) op(B)  (+ C_task if accumulate).  Square Sp x Sp
+// matrices, Sp a multiple of 80.  grid = (tiles, n_tasks, ksplit); with ksplit > 1 the CTA
+// writes its partial product to `partial[(task*ksplit + z)]` and splitk_reduce_kernel finishes.
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_tasks_kernel(const GemmTask* __restrict__ tasks, const GemmTerm* __restrict__ terms, int Sp,
+                  int ksplit, double* __restrict__ partial) {
+  extern __shared__ double smem[];
+  const GemmTask task = tasks[blockIdx.y];
+  if (task.cond != nullptr && *task.cond <= task.level) return;
+  const int tiles_n = Sp / BT;
+  const int m0 = (blockIdx.x / tiles_n) * BT, n0 = (blockIdx.x % tiles_n) * BT;
+  const int total = task.n_terms * (Sp / BK);
+  const int z = blockIdx.z;
+  const int c_begin = (int)((long long)total * z / ksplit), c_end = (int)((long long)total * (z + 1) / ksplit);
+  double* out = (ksplit == 1) ? task.C
+                              : partial + ((size_t)blockIdx.y * ksplit + z) * (size_t)Sp * Sp;
+  gemm_tile([&](int idx) { return terms[task.term_begin + idx]; }, Sp, m0, n0, c_begin, c_end, smem, out,
+            (ksplit == 1) && task.accumulate);
+}
+
+// ----------------------------------------------------------- dataflow squaring chains
+// All squaring levels of all buckets in ONE persistent launch.  coef_kernel publishes, per
+// level, the list of buckets that are still active; CTAs pull (level, bucket, tile) items from
+// an atomic queue in level-major order and, instead of a grid-wide barrier per level, wait only
+// for the 25 tiles of the SAME bucket at the previous level (per-bucket completion counters).
+// Items are dequeued in dependency order and every dequeued item is being executed by a
+// resident CTA, so the waits cannot deadlock.
+struct SqSchedule {
+  int queue[2];                        // work counters: forward, backward
+  int n_levels;                        // max_k s_k
+  int level_off[kSStore + 1];          // prefix sums of active buckets per level
+  int pad[4];
+  // followed in memory by: int active[kSStore][K]; int done_fwd[K][kSStore]; int done_bwd[K][kSStore + 1]
+};
+__device__ __forceinline__ int* sq_active(SqSchedule* s) { return reinterpret_cast<int*>(s + 1); }
+__device__ __forceinline__ int* sq_done_fwd(SqSchedule* s, int K) { return sq_active(s) + kSStore * K; }
+__device__ __forceinline__ int* sq_done_bwd(SqSchedule* s, int K) { return sq_done_fwd(s, K) + kSStore * K; }
+
+// Bounded spin (about a second): a scheduling bug must surface as an error flag, not as a hung GPU.
+__device__ __forceinline__ void wait_counter(const int* ctr, int target, int* status_flag) {
+  if (threadIdx.x == 0) {
+    unsigned spins = 0;
+    while (*reinterpret_cast<const volatile int*>(ctr) < target) {
+      __nanosleep(64);
+      if (++spins > (1u << 24)) {
+        atomicExch(status_flag, 3);
+        break;
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(GEMM_THREADS)
+squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__ s_arr, int K, int Sp,
+                         double* __restrict__ X0, double* __restrict__ chain, int slots_per_bucket,
+                         int* __restrict__ status_flag) {
+  extern __shared__ double smem[];
+  __shared__ int s_item;
+  const int tiles_n = Sp / BT, tiles = tiles_n * tiles_n;
+  const size_t n_p = (size_t)Sp * Sp;
+  const int n_levels = sched->n_levels;
+  const int total_buckets = sched->level_off[n_levels];
+  const int total_items = total_buckets * tiles;
+  const int* active = sq_active(sched);
+  int* done_fwd = sq_done_fwd(sched, K);
+  int* done_bwd = sq_done_bwd(sched, K);
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = atomicAdd(&sched->queue[BWD ? 1 : 0], 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= total_items) return;
+    const int bidx_linear = item / tiles, tile = item - bidx_linear * tiles;
+    // forward walks the levels upwards, backward downwards
+    const int pos = BWD ? (total_buckets - 1 - bidx_linear) : bidx_linear;
+    int level = 0;
+    while (level + 1 < n_levels && sched->level_off[level + 1] <= pos) ++level;
+    const int k = active[level * K + (pos - sched->level_off[level])];
+    const int m0 = (tile / tiles_n) * BT, n0 = (tile % tiles_n) * BT;
+    double* Xi = (level == 0) ? X0 + (size_t)k * n_p : chain + ((size_t)k * slots_per_bucket + (level - 1)) * n_p;
+    double* out = chain + ((size_t)k * slots_per_bucket + level) * n_p;  // slot level+1
+    if (!BWD) {
+      if (level > 0) wait_counter(done_fwd + k * kSStore + (level - 1), tiles, status_flag);
+      const GemmTerm t0{Xi, Xi, 0, 0};
+      gemm_tile([&](int) { return t0; }, Sp, m0, n0, 0, Sp / BK, smem, out, false);
+      __threadfence();  // every thread publishes its part of the tile before the counter moves
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(done_fwd + k * kSStore + level, 1);
+    } else {
+      // Xbar_{level+1} lives in slot level+2; it is either G (written by loss_grad_kernel before
+      // this launch) or the output of this kernel at level+1 of the same bucket.
+      double* Xb = chain + ((size_t)k * slots_per_bucket + (level + 1)) * n_p;
+      // done_bwd[k][l] counts finished tiles of backward level l of bucket k
+      if (level + 1 < s_arr[k]) wait_counter(done_bwd + k * (kSStore + 1) + (level + 1), tiles, status_flag);
+      const GemmTerm t0{Xb, Xi, 0, 1}, t1{Xi, Xb, 1, 0};
+      gemm_tile([&](int idx) { return idx == 0 ? t0 : t1; }, Sp, m0, n0, 0, 2 * (Sp / BK), smem, out, false);
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(done_bwd + k * (kSStore + 1) + level, 1);
+    }
+  }
 }
 
 // grid = (blocks over elements, n_tasks): C = (accumulate ? C : 0) + sum_z partial[task][z], z ascending
@@ -225,7 +319,7 @@ __global__ void build_B_kernel(const double* __restrict__ Q, int S, int Sp, doub
 // one CTA: per bucket s_k, tau_k and the weights w[k][j] = e^{-tau mu} tau^j / j!, j = 0..m
 __global__ void coef_kernel(const double* __restrict__ t, int K, LargeScalars* __restrict__ sc,
                             int* __restrict__ s_arr, double* __restrict__ w, double* __restrict__ tau_arr,
-                            int* __restrict__ status_flag) {
+                            int* __restrict__ status_flag, SqSchedule* __restrict__ sched) {
   const double norm = __longlong_as_double((long long)sc->norm_bits);
   const double mu = sc->mu;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
@@ -248,6 +342,28 @@ __global__ void coef_kernel(const double* __restrict__ t, int K, LargeScalars* _
   }
   __syncthreads();
   if (threadIdx.x == 0) sc->norm_bits = 0ull;  // ready for the next epoch's atomicMax
+  // ---- schedule of the dataflow squaring kernels: active buckets per level, counters reset
+  int* active = sq_active(sched);
+  int* done_fwd = sq_done_fwd(sched, K);
+  int* done_bwd = sq_done_bwd(sched, K);
+  for (int i = threadIdx.x; i < K * kSStore; i += blockDim.x) done_fwd[i] = 0;
+  for (int i = threadIdx.x; i < K * (kSStore + 1); i += blockDim.x) done_bwd[i] = 0;
+  if (threadIdx.x == 0) {
+    int off = 0, n_levels = 0;
+    for (int lvl = 0; lvl < kSStore; ++lvl) {
+      sched->level_off[lvl] = off;
+      int n = 0;
+      for (int k = 0; k < K; ++k)
+        if (s_arr[k] > lvl) active[lvl * K + n++] = k;
+      if (n > 0) n_levels = lvl + 1;
+      off += n;
+    }
+    sched->level_off[kSStore] = off;
+    // level_off beyond n_levels all equal `off`; the kernels read level_off[n_levels]
+    sched->n_levels = n_levels;
+    sched->queue[0] = 0;
+    sched->queue[1] = 0;
+  }
 }
 
 // X0_k = sum_j w[k][j] B^j for every bucket; one thread per matrix element keeps the m power
@@ -536,7 +652,7 @@ struct Plan {
   int S, Sp, K, tiles;
   size_t n_p;
   // workspace offsets in bytes
-  size_t off_scalars, off_s, off_tau, off_w, off_loss_partial, off_grad_theta, off_dpi, off_pibuf, off_tasks, off_terms;
+  size_t off_sched, off_scalars, off_s, off_tau, off_w, off_loss_partial, off_grad_theta, off_dpi, off_pibuf, off_tasks, off_terms;
   size_t off_P, off_Pbar, off_X0, off_chain, off_partial, total_bytes;
   int slots_per_bucket;   // chain slots 1..kSStore+1
   int loss_blocks;
@@ -574,6 +690,7 @@ void make_plan(Plan& p, int S, int K, char* base) {
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off = align256(off + bytes); return o; };
   p.off_scalars = carve(sizeof(LargeScalars));
+  p.off_sched = carve(sizeof(SqSchedule) + sizeof(int) * ((size_t)kSStore * K * 2 + (size_t)K * (kSStore + 1)));
   p.off_s = carve(sizeof(int) * K);
   p.off_tau = carve(sizeof(double) * K);
   p.off_w = carve(sizeof(double) * K * (kDeg + 1));
@@ -693,6 +810,10 @@ int ensure_gemm_attr() {
   if (dev < 64 && !attr_set[dev]) {
     CHERRY_CUDA(cudaFuncSetAttribute(gemm_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      NSTAGE * 2 * TILE_ELEMS * (int)sizeof(double)));
+    CHERRY_CUDA(cudaFuncSetAttribute(squaring_dataflow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     NSTAGE * 2 * TILE_ELEMS * (int)sizeof(double)));
+    CHERRY_CUDA(cudaFuncSetAttribute(squaring_dataflow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     NSTAGE * 2 * TILE_ELEMS * (int)sizeof(double)));
     attr_set[dev] = true;
   }
   return 0;
@@ -783,7 +904,8 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
 
   build_B_kernel<<<(p.Sp + 7) / 8, EW_THREADS, 0, stream>>>(a.Q, a.S, p.Sp, P, sc);
   CHERRY_LAUNCH_CHECK("build_B_kernel");
-  coef_kernel<<<1, 256, 0, stream>>>(a.t, a.K, sc, s_arr, w, tau, a.status_flag);
+  SqSchedule* sched = reinterpret_cast<SqSchedule*>(base + p.off_sched);
+  coef_kernel<<<1, 256, 0, stream>>>(a.t, a.K, sc, s_arr, w, tau, a.status_flag, sched);
   CHERRY_LAUNCH_CHECK("coef_kernel");
   for (const Group& g : p.pow_fwd)
     if ((rc = launch_group(p, g, base, stream))) return rc;
@@ -799,8 +921,17 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   }
   poly_eval_kernel<<<eb, EW_THREADS, wsmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, X0);
   CHERRY_LAUNCH_CHECK("poly_eval_kernel");
-  for (const Group& g : p.sq_fwd)
-    if ((rc = launch_group(p, g, base, stream))) return rc;
+  static const bool level_sync = getenv("CHERRY_FIT_LEVEL_SYNC") != nullptr;  // A/B switch
+  const size_t gemm_smem = (size_t)NSTAGE * 2 * TILE_ELEMS * sizeof(double);
+  const int persistent_grid = 2 * sm_count();
+  if (level_sync) {
+    for (const Group& g : p.sq_fwd)
+      if ((rc = launch_group(p, g, base, stream))) return rc;
+  } else {
+    squaring_dataflow_kernel<false><<<persistent_grid, GEMM_THREADS, gemm_smem, stream>>>(
+        sched, s_arr, a.K, p.Sp, X0, chain, p.slots_per_bucket, a.status_flag);
+    CHERRY_LAUNCH_CHECK("squaring_dataflow_kernel<fwd>");
+  }
   if (P_out != nullptr) {
     extract_P_kernel<<<dim3((a.S * a.S + 255) / 256, a.K), 256, 0, stream>>>(s_arr, X0, chain, p.slots_per_bucket,
                                                                              p.n_p, a.S, p.Sp, P_out);
@@ -812,8 +943,14 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   CHERRY_LAUNCH_CHECK("loss_grad_kernel");
   loss_reduce_kernel<<<1, 256, 0, stream>>>(loss_partial, a.K, p.loss_blocks, a.loss_part);
   CHERRY_LAUNCH_CHECK("loss_reduce_kernel");
-  for (const Group& g : p.sq_bwd)
-    if ((rc = launch_group(p, g, base, stream))) return rc;
+  if (level_sync) {
+    for (const Group& g : p.sq_bwd)
+      if ((rc = launch_group(p, g, base, stream))) return rc;
+  } else {
+    squaring_dataflow_kernel<true><<<persistent_grid, GEMM_THREADS, gemm_smem, stream>>>(
+        sched, s_arr, a.K, p.Sp, X0, chain, p.slots_per_bucket, a.status_flag);
+    CHERRY_LAUNCH_CHECK("squaring_dataflow_kernel<bwd>");
+  }
   accumulate_M_kernel<<<eb, EW_THREADS, wsmem, stream>>>(chain, p.slots_per_bucket, p.n_p, a.K, w, Pbar);
   CHERRY_LAUNCH_CHECK("accumulate_M_kernel");
   for (const Group& g : p.pow_bwd)

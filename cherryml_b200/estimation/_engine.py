@@ -201,7 +201,7 @@ class FitEngine:
 
     def check_status(self) -> None:
         if int(self.status_flag.item()) != 0:
-            raise _lib.CherryError("fit kernel ran out of workspace (rate matrix norm beyond the supported range)")
+            raise _lib.CherryError(f"fit kernel reported status {int(self.status_flag.item())} (1/2: rate matrix norm beyond the supported range, 3: internal scheduling timeout)")
 
     def results(self) -> Dict[str, np.ndarray]:
         """Synchronise and fetch: loss trace, Q snapshots (single problem), best and last Q."""
