@@ -33,7 +33,9 @@ namespace {
 constexpr int kDeg = 18;          // Taylor degree of the shared-power polynomial
 constexpr double kTheta = 1.09;   // tau*mu bound: 1.09^19/19! ~ 4e-17 (all terms non-negative)
 constexpr int kSStore = 8;        // squarings kept per bucket: covers t*mu up to 1.09 * 2^8 = 279
-constexpr int BT = 80, BK = 16, NSTAGE = 3, GEMM_THREADS = 128;
+constexpr int BT = 80, BK = 16, NSTAGE = 3;
+constexpr int KGROUPS = 2;                 // warp groups splitting every k chunk (halves tile latency)
+constexpr int GEMM_THREADS = 128 * KGROUPS;
 constexpr int LD_ROW = 20;        // tile stored [80][16]: k contiguous
 constexpr int LD_COL = 84;        // tile stored [16][80]: m (or n) contiguous
 constexpr int TILE_ELEMS = BT * LD_ROW;  // 1600 >= 16 * 84
@@ -83,9 +85,10 @@ __device__ __forceinline__ void load_col_tile(double* s, const double* g, int ld
 
 template <bool TA, bool TB>
 __device__ __forceinline__ void compute_chunk(const double* As, const double* Bs, double (&acc)[5][5][2],
-                                              int rbase, int cbase, int g, int tg) {
+                                              int rbase, int cbase, int g, int tg, int kgroup) {
 #pragma unroll
-  for (int kk = 0; kk < BK; kk += 4) {
+  for (int kq = 0; kq < BK / 4 / KGROUPS; ++kq) {
+    const int kk = (kq * KGROUPS + kgroup) * 4;  // this warp group's k-steps of the chunk
     double a[5], b[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
@@ -111,7 +114,8 @@ __device__ __forceinline__ void gemm_tile(TermFn get_term, int Sp, int m0, int n
                                           double* smem, double* out, bool add_old) {
   const int cpt = Sp / BK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
-  const int rbase = (warp >> 1) * 40, cbase = (warp & 1) * 40;
+  const int kgroup = warp >> 2, wq = warp & 3;  // 4 warps (2x2 quadrants of 40x40) per k group
+  const int rbase = (wq >> 1) * 40, cbase = (wq & 1) * 40;
   double acc[5][5][2];
 #pragma unroll
   for (int i = 0; i < 5; ++i)
@@ -141,14 +145,39 @@ __device__ __forceinline__ void gemm_tile(TermFn get_term, int Sp, int m0, int n
     const double* As = smem + (size_t)(i % NSTAGE) * 2 * TILE_ELEMS;
     const double* Bs = As + TILE_ELEMS;
     if (t.ta) {
-      if (t.tb) compute_chunk<true, true>(As, Bs, acc, rbase, cbase, g, tg);
-      else compute_chunk<true, false>(As, Bs, acc, rbase, cbase, g, tg);
+      if (t.tb) compute_chunk<true, true>(As, Bs, acc, rbase, cbase, g, tg, kgroup);
+      else compute_chunk<true, false>(As, Bs, acc, rbase, cbase, g, tg, kgroup);
     } else {
-      if (t.tb) compute_chunk<false, true>(As, Bs, acc, rbase, cbase, g, tg);
-      else compute_chunk<false, false>(As, Bs, acc, rbase, cbase, g, tg);
+      if (t.tb) compute_chunk<false, true>(As, Bs, acc, rbase, cbase, g, tg, kgroup);
+      else compute_chunk<false, false>(As, Bs, acc, rbase, cbase, g, tg, kgroup);
     }
   }
   cp_async_wait<0>();
+  if (KGROUPS > 1) {
+    // fold the k groups: groups 1.. park their accumulators in the (now idle) pipeline buffers,
+    // group 0 adds them.  Layout [value][thread of group] keeps the accesses conflict free.
+    __syncthreads();
+    double* park = smem;  // 50 * 128 doubles = 51 KB <= NSTAGE * 2 * TILE_ELEMS * 8 B
+    const int tq = threadIdx.x & 127;
+    if (kgroup == 1) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          park[((i * 5 + j) * 2 + 0) * 128 + tq] = acc[i][j][0];
+          park[((i * 5 + j) * 2 + 1) * 128 + tq] = acc[i][j][1];
+        }
+    }
+    __syncthreads();
+    if (kgroup != 0) return;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        acc[i][j][0] += park[((i * 5 + j) * 2 + 0) * 128 + tq];
+        acc[i][j][1] += park[((i * 5 + j) * 2 + 1) * 128 + tq];
+      }
+  }
 #pragma unroll
   for (int i = 0; i < 5; ++i)
 #pragma unroll
@@ -923,7 +952,7 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   CHERRY_LAUNCH_CHECK("poly_eval_kernel");
   static const bool level_sync = getenv("CHERRY_FIT_LEVEL_SYNC") != nullptr;  // A/B switch
   const size_t gemm_smem = (size_t)NSTAGE * 2 * TILE_ELEMS * sizeof(double);
-  const int persistent_grid = 2 * sm_count();
+  const int persistent_grid = sm_count();  // 8 warps per CTA, one CTA per SM
   if (level_sync) {
     for (const Group& g : p.sq_fwd)
       if ((rc = launch_group(p, g, base, stream))) return rc;
