@@ -20,6 +20,6 @@ int fit_large_read_schedule(const cherry_fit_args& a, int* s_out, double* mu_out
 int gemm_f64_batched(const double* A, const double* B, double* C, int n, int batch, int ta, int tb,
                      int accumulate, int ksplit, void* desc, double* partial, cudaStream_t stream);
 size_t gemm_desc_bytes(int batch);
-constexpr int kLargeDegree = 18;  // keep in sync with fit_large.cu
+constexpr int kLargeDegree = 24;  // keep in sync with fit_large.cu
 
 }  // namespace cherry

@@ -30,11 +30,11 @@
 
 namespace {
 
-constexpr int kDeg = 18;          // Taylor degree of the shared-power polynomial
-constexpr double kTheta = 1.09;   // tau*mu bound: 1.09^19/19! ~ 4e-17 (all terms non-negative)
-constexpr int kSStore = 8;        // squarings kept per bucket: covers t*mu up to 1.09 * 2^8 = 279
+constexpr int kDeg = 24;          // Taylor degree of the shared-power polynomial
+constexpr double kTheta = 2.2;    // tau*mu bound: 2.2^25/25! ~ 2e-17 (all terms non-negative)
+constexpr int kSStore = 8;        // squarings kept per bucket: covers t*mu up to 2.2 * 2^8 = 563
 constexpr int BT = 80, BK = 16, NSTAGE = 3;
-constexpr int KGROUPS = 2;                 // warp groups splitting every k chunk (halves tile latency)
+constexpr int KGROUPS = 1;  // >1: warp groups split every k chunk (lower tile latency, measured 30% less throughput)
 constexpr int GEMM_THREADS = 128 * KGROUPS;
 constexpr int LD_ROW = 20;        // tile stored [80][16]: k contiguous
 constexpr int LD_COL = 84;        // tile stored [16][80]: m (or n) contiguous
@@ -377,15 +377,23 @@ __global__ void coef_kernel(const double* __restrict__ t, int K, LargeScalars* _
   int* done_bwd = sq_done_bwd(sched, K);
   for (int i = threadIdx.x; i < K * kSStore; i += blockDim.x) done_fwd[i] = 0;
   for (int i = threadIdx.x; i < K * (kSStore + 1); i += blockDim.x) done_bwd[i] = 0;
+  __shared__ int ss[256], level_n[kSStore];
+  for (int k = threadIdx.x; k < K; k += blockDim.x) ss[k] = s_arr[k];
+  __syncthreads();
+  if (threadIdx.x < kSStore) {  // one thread per level builds that level's list
+    const int lvl = threadIdx.x;
+    int n = 0;
+    for (int k = 0; k < K; ++k)
+      if (ss[k] > lvl) active[lvl * K + n++] = k;
+    level_n[lvl] = n;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     int off = 0, n_levels = 0;
     for (int lvl = 0; lvl < kSStore; ++lvl) {
       sched->level_off[lvl] = off;
-      int n = 0;
-      for (int k = 0; k < K; ++k)
-        if (s_arr[k] > lvl) active[lvl * K + n++] = k;
-      if (n > 0) n_levels = lvl + 1;
-      off += n;
+      if (level_n[lvl] > 0) n_levels = lvl + 1;
+      off += level_n[lvl];
     }
     sched->level_off[kSStore] = off;
     // level_off beyond n_levels all equal `off`; the kernels read level_off[n_levels]
@@ -419,14 +427,100 @@ poly_eval_kernel(const double* __restrict__ powers, size_t n_p, int S, int Sp, i
   }
 }
 
+// Fused Taylor pass (training): one thread per matrix element, the m power values in registers.
+//   buckets WITHOUT squarings (most of them): P_k(e) is the polynomial itself, so the loss term
+//     and the bucket's whole contribution to the power adjoints, Pbar_j(e) += w[k][j] * (-C/P),
+//     are formed on the spot -- nothing is stored per bucket, and an element with C_k(e) == 0
+//     costs only the load of C;
+//   buckets WITH squarings: X0_k(e) is stored for the squaring chain.
+// Outputs: Pbar_j (j = 1..m) initialised with the no-squaring buckets' contributions, X0 of
+// the squared buckets, one loss partial per block.
+__global__ void __launch_bounds__(EW_THREADS)
+taylor_fused_kernel(const double* __restrict__ powers, size_t n_p, int S, int Sp, int K,
+                    const double* __restrict__ w, const int* __restrict__ s_arr,
+                    const double* __restrict__ C, double* __restrict__ X0, double* __restrict__ Pbar,
+                    double* __restrict__ loss_partial_fused) {
+  extern __shared__ double sw[];  // [K][m+1] weights, then int lists
+  __shared__ double red[EW_THREADS / 32];
+  __shared__ int n_zero, n_sq;
+  int* zlist = reinterpret_cast<int*>(sw + (size_t)K * (kDeg + 1));  // buckets with s == 0
+  int* qlist = zlist + K;                                              // buckets with s > 0
+  for (int i = threadIdx.x; i < K * (kDeg + 1); i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x == 0) {
+    int nz = 0, nq = 0;
+    for (int k = 0; k < K; ++k) {
+      if (s_arr[k] == 0) zlist[nz++] = k; else qlist[nq++] = k;
+    }
+    n_zero = nz;
+    n_sq = nq;
+  }
+  __syncthreads();
+  const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const bool in_range = e < n_p;
+  const size_t ee = in_range ? e : 0;
+  const int row = (int)(ee / Sp), col = (int)(ee - (size_t)row * Sp);
+  const bool real = in_range && row < S && col < S;
+  const double diag = (row == col && row < S) ? 1.0 : 0.0;
+  double pw[kDeg], acc[kDeg];
+#pragma unroll
+  for (int j = 0; j < kDeg; ++j) {
+    pw[j] = in_range ? powers[(size_t)j * n_p + ee] : 0.0;
+    acc[j] = 0.0;
+  }
+  double part = 0.0;
+  const size_t cidx = (size_t)row * S + col;
+  const size_t SS = (size_t)S * S;
+  // ---- buckets without squarings: 4 count loads in flight
+  for (int i0 = 0; i0 < n_zero; i0 += 4) {
+    double c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) c[u] = (real && i0 + u < n_zero) ? C[(size_t)zlist[i0 + u] * SS + cidx] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (c[u] != 0.0) {
+        const double* wk = sw + zlist[i0 + u] * (kDeg + 1);
+        double v = wk[0] * diag;
+#pragma unroll
+        for (int j = 0; j < kDeg; ++j) v = fma(wk[j + 1], pw[j], v);
+        part -= c[u] * log(v);
+        const double g = -c[u] / v;
+#pragma unroll
+        for (int j = 0; j < kDeg; ++j) acc[j] = fma(wk[j + 1], g, acc[j]);
+      }
+    }
+  }
+  // ---- buckets with squarings: store X0
+  if (in_range) {
+    for (int i = 0; i < n_sq; ++i) {
+      const int k = qlist[i];
+      const double* wk = sw + k * (kDeg + 1);
+      double v = wk[0] * diag;
+#pragma unroll
+      for (int j = 0; j < kDeg; ++j) v = fma(wk[j + 1], pw[j], v);
+      X0[(size_t)k * n_p + e] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < kDeg; ++j) Pbar[(size_t)j * n_p + e] = acc[j];
+  }
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int wdx = 0; wdx < EW_THREADS / 32; ++wdx) tot += red[wdx];
+    loss_partial_fused[blockIdx.x] = tot;
+  }
+}
+
 // grid = (blocks, K): loss partials and G_k = -C_k / P_k into chain slot s_k + 1.
 // P_k = X0_k if s_k == 0 else chain slot s_k.
 __global__ void __launch_bounds__(EW_THREADS)
 loss_grad_kernel(const double* __restrict__ C, int S, int Sp, size_t n_p, const int* __restrict__ s_arr,
                  const double* __restrict__ X0, double* __restrict__ chain, int slots_per_bucket,
-                 double* __restrict__ loss_partial) {
+                 double* __restrict__ loss_partial, int skip_unsquared) {
   __shared__ double red[EW_THREADS / 32];
   const int k = blockIdx.y, s = s_arr[k];
+  if (skip_unsquared && s == 0) return;  // handled by taylor_fused_kernel
   const double* P = (s == 0) ? X0 + (size_t)k * n_p
                              : chain + ((size_t)k * slots_per_bucket + (s - 1)) * n_p;
   double* G = chain + ((size_t)k * slots_per_bucket + s) * n_p;  // slot s+1 (slots are 1-based)
@@ -455,19 +549,36 @@ loss_grad_kernel(const double* __restrict__ C, int S, int Sp, size_t n_p, const 
   }
 }
 
+// One CTA.  loss_part[k] = sum of the bucket's block partials (squared buckets only when the
+// fused pass handled the rest); the fused pass' total is added to loss_part[0].  Fixed orders.
 __global__ void loss_reduce_kernel(const double* __restrict__ loss_partial, int K, int nblocks,
-                                   double* __restrict__ loss_part) {
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+                                   double* __restrict__ loss_part, const int* __restrict__ s_arr,
+                                   const double* __restrict__ fused_partial, int n_fused) {
+  __shared__ double sh[256];
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
     double tot = 0.0;
-    for (int b = 0; b < nblocks; ++b) tot += loss_partial[(size_t)k * nblocks + b];
+    if (n_fused == 0 || s_arr[k] > 0)
+      for (int b = 0; b < nblocks; ++b) tot += loss_partial[(size_t)k * nblocks + b];
     loss_part[k] = tot;
+  }
+  if (n_fused > 0) {
+    double v = 0.0;
+    for (int b = threadIdx.x; b < n_fused; b += blockDim.x) v += fused_partial[b];
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int i = 0; i < (int)blockDim.x; ++i) tot += sh[i];
+      loss_part[0] += tot;
+    }
   }
 }
 
 // Pbar_j = sum_k w[k][j] * X0bar_k (chain slot 1 of bucket k), j = 1..m; buckets in order.
 __global__ void __launch_bounds__(EW_THREADS)
 accumulate_M_kernel(const double* __restrict__ chain, int slots_per_bucket, size_t n_p, int K,
-                    const double* __restrict__ w, double* __restrict__ Pbar) {
+                    const double* __restrict__ w, double* __restrict__ Pbar,
+                    const int* __restrict__ s_arr, int squared_only) {
   extern __shared__ double sw[];
   for (int i = threadIdx.x; i < K * (kDeg + 1); i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -475,8 +586,9 @@ accumulate_M_kernel(const double* __restrict__ chain, int slots_per_bucket, size
   if (e >= n_p) return;
   double acc[kDeg];
 #pragma unroll
-  for (int j = 0; j < kDeg; ++j) acc[j] = 0.0;
+  for (int j = 0; j < kDeg; ++j) acc[j] = squared_only ? Pbar[(size_t)j * n_p + e] : 0.0;
   for (int k = 0; k < K; ++k) {
+    if (squared_only && s_arr[k] == 0) continue;  // already folded in by taylor_fused_kernel
     const double x = chain[((size_t)k * slots_per_bucket) * n_p + e];
     const double* wk = sw + k * (kDeg + 1);
 #pragma unroll
@@ -723,7 +835,7 @@ void make_plan(Plan& p, int S, int K, char* base) {
   p.off_s = carve(sizeof(int) * K);
   p.off_tau = carve(sizeof(double) * K);
   p.off_w = carve(sizeof(double) * K * (kDeg + 1));
-  p.off_loss_partial = carve(sizeof(double) * K * p.loss_blocks);
+  p.off_loss_partial = carve(sizeof(double) * ((size_t)K * p.loss_blocks + (p.n_p + EW_THREADS - 1) / EW_THREADS));
   p.off_grad_theta = carve(sizeof(double) * n_theta);
   p.off_dpi = carve(sizeof(double) * S);
   p.off_pibuf = carve(sizeof(double) * S);
@@ -945,14 +1057,25 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
     if (dev < 64 && !ew_attr[dev]) {
       CHERRY_CUDA(cudaFuncSetAttribute(poly_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CHERRY_CUDA(cudaFuncSetAttribute(accumulate_M_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       ew_attr[dev] = true;
     }
   }
-  poly_eval_kernel<<<eb, EW_THREADS, wsmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, X0);
-  CHERRY_LAUNCH_CHECK("poly_eval_kernel");
+  static const bool unfused = getenv("CHERRY_FIT_UNFUSED") != nullptr;  // A/B switch
+  const bool fused = (P_out == nullptr) && !unfused;
+  double* fused_partial = loss_partial + (size_t)a.K * p.loss_blocks;
+  if (fused) {
+    const size_t fsmem = wsmem + 2 * sizeof(int) * a.K;
+    taylor_fused_kernel<<<eb, EW_THREADS, fsmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, s_arr, a.C, X0, Pbar,
+                                                           fused_partial);
+    CHERRY_LAUNCH_CHECK("taylor_fused_kernel");
+  } else {
+    poly_eval_kernel<<<eb, EW_THREADS, wsmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, X0);
+    CHERRY_LAUNCH_CHECK("poly_eval_kernel");
+  }
   static const bool level_sync = getenv("CHERRY_FIT_LEVEL_SYNC") != nullptr;  // A/B switch
   const size_t gemm_smem = (size_t)NSTAGE * 2 * TILE_ELEMS * sizeof(double);
-  const int persistent_grid = sm_count();  // 8 warps per CTA, one CTA per SM
+  const int persistent_grid = (KGROUPS == 1 ? 2 : 1) * sm_count();  // all CTAs co-resident
   if (level_sync) {
     for (const Group& g : p.sq_fwd)
       if ((rc = launch_group(p, g, base, stream))) return rc;
@@ -968,9 +1091,10 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
     return 0;
   }
   loss_grad_kernel<<<dim3(p.loss_blocks, a.K), EW_THREADS, 0, stream>>>(a.C, a.S, p.Sp, p.n_p, s_arr, X0, chain,
-                                                                        p.slots_per_bucket, loss_partial);
+                                                                        p.slots_per_bucket, loss_partial, fused ? 1 : 0);
   CHERRY_LAUNCH_CHECK("loss_grad_kernel");
-  loss_reduce_kernel<<<1, 256, 0, stream>>>(loss_partial, a.K, p.loss_blocks, a.loss_part);
+  loss_reduce_kernel<<<1, 256, 0, stream>>>(loss_partial, a.K, p.loss_blocks, a.loss_part, s_arr, fused_partial,
+                                            fused ? eb : 0);
   CHERRY_LAUNCH_CHECK("loss_reduce_kernel");
   if (level_sync) {
     for (const Group& g : p.sq_bwd)
@@ -980,7 +1104,8 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
         sched, s_arr, a.K, p.Sp, X0, chain, p.slots_per_bucket, a.status_flag);
     CHERRY_LAUNCH_CHECK("squaring_dataflow_kernel<bwd>");
   }
-  accumulate_M_kernel<<<eb, EW_THREADS, wsmem, stream>>>(chain, p.slots_per_bucket, p.n_p, a.K, w, Pbar);
+  accumulate_M_kernel<<<eb, EW_THREADS, wsmem, stream>>>(chain, p.slots_per_bucket, p.n_p, a.K, w, Pbar, s_arr,
+                                                         fused ? 1 : 0);
   CHERRY_LAUNCH_CHECK("accumulate_M_kernel");
   for (const Group& g : p.pow_bwd)
     if ((rc = launch_group(p, g, base, stream))) return rc;
