@@ -1,5 +1,7 @@
 // C-ABI entry points of the fit (include/cherryml_b200.h), dispatching on the state-space
 // size: S <= 32 -> fit_small.cu (shared-memory resident), larger -> fit_large.cu.
+#include <cstdlib>
+
 #include "fit_internal.cuh"
 
 namespace {
@@ -53,6 +55,8 @@ int cherry_fit_init(const cherry_fit_args* a, void* stream) {
 int cherry_fit_loss_grad(const cherry_fit_args* a, void* stream) {
   int rc = check_args(a, false);
   if (rc) return rc;
+  if (a->S > cherry::kSmallFitMaxS && getenv("CHERRY_FIT_TIMELINE"))
+    return cherry::fit_large_timeline(*a, (cudaStream_t)stream);
   if (a->S <= cherry::kSmallFitMaxS) return cherry::fit_small_expm(*a, (cudaStream_t)stream);
   return cherry::fit_large_expm(*a, (cudaStream_t)stream);
 }

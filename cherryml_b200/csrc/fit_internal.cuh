@@ -16,6 +16,7 @@ int fit_large_workspace_bytes(int S, int K, int n_problems, size_t* bytes);
 int fit_large_expm(const cherry_fit_args& a, cudaStream_t stream);   // loss_part + dQ_total in dQ_part[0]
 int fit_large_forward_only(const cherry_fit_args& a, double* P_out, cudaStream_t stream);
 int fit_large_update(const cherry_fit_args& a, int mode, cudaStream_t stream);
+int fit_large_timeline(const cherry_fit_args& a, cudaStream_t stream);
 int fit_large_read_schedule(const cherry_fit_args& a, int* s_out, double* mu_out);
 int gemm_f64_batched(const double* A, const double* B, double* C, int n, int batch, int ta, int tb,
                      int accumulate, int ksplit, void* desc, double* partial, cudaStream_t stream);

@@ -806,8 +806,9 @@ struct Plan {
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 int choose_ksplit(int n_tasks, int tiles, int chunks_per_task) {
-  int want = (296 + n_tasks * tiles - 1) / (n_tasks * tiles);
-  int cap = chunks_per_task / 4;
+  static const int target = getenv("CHERRY_FIT_KSPLIT_TARGET") ? atoi(getenv("CHERRY_FIT_KSPLIT_TARGET")) : 296;
+  int want = (target + n_tasks * tiles - 1) / (n_tasks * tiles);
+  int cap = chunks_per_task / 2;
   if (cap < 1) cap = 1;
   if (want > cap) want = cap;
   if (want < 1) want = 1;
@@ -846,7 +847,7 @@ void make_plan(Plan& p, int S, int K, char* base) {
   p.off_X0 = carve(mat * K);
   p.off_chain = carve(mat * K * p.slots_per_bucket);
   // split-K partial buffers: sized below once the groups are known (upper bound first)
-  p.n_partial = 40;
+  p.n_partial = 96;
   p.off_partial = carve(mat * p.n_partial);
   p.total_bytes = off;
   if (!base) return;
@@ -1013,6 +1014,21 @@ int fit_large_prepare(const cherry_fit_args& a, cudaStream_t stream) {
 
 static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double* P_out);
 
+// Optional phase timeline (debug / profiling): when g_timeline is non-null, fit_large_impl records
+// an event after every phase of one evaluation.
+struct Timeline {
+  static constexpr int kMax = 16;
+  cudaEvent_t ev[kMax];
+  const char* name[kMax];
+  int n = 0;
+};
+static Timeline* g_timeline = nullptr;
+static void mark(const char* name, cudaStream_t stream) {
+  if (!g_timeline || g_timeline->n >= Timeline::kMax) return;
+  cudaEventRecord(g_timeline->ev[g_timeline->n], stream);
+  g_timeline->name[g_timeline->n++] = name;
+}
+
 int fit_large_expm(const cherry_fit_args& a, cudaStream_t stream) { return fit_large_impl(a, stream, nullptr); }
 
 // expm(t_k Q) for every bucket into P_out [K][S][S]; prepares the workspace itself (synchronous).
@@ -1043,13 +1059,16 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   const size_t wsmem = sizeof(double) * a.K * (kDeg + 1);
   if (wsmem > 200 * 1024) return fail(CHERRY_ELIMIT, "fit_large: K=%d too large for the weight table", a.K);
 
+  mark("start", stream);
   build_B_kernel<<<(p.Sp + 7) / 8, EW_THREADS, 0, stream>>>(a.Q, a.S, p.Sp, P, sc);
   CHERRY_LAUNCH_CHECK("build_B_kernel");
   SqSchedule* sched = reinterpret_cast<SqSchedule*>(base + p.off_sched);
   coef_kernel<<<1, 256, 0, stream>>>(a.t, a.K, sc, s_arr, w, tau, a.status_flag, sched);
   CHERRY_LAUNCH_CHECK("coef_kernel");
+  mark("build_B+coef", stream);
   for (const Group& g : p.pow_fwd)
     if ((rc = launch_group(p, g, base, stream))) return rc;
+  mark("powers_fwd", stream);
   static bool ew_attr[64] = {false};
   {
     int dev = 0;
@@ -1073,6 +1092,7 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
     poly_eval_kernel<<<eb, EW_THREADS, wsmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, X0);
     CHERRY_LAUNCH_CHECK("poly_eval_kernel");
   }
+  mark("taylor_fused", stream);
   static const bool level_sync = getenv("CHERRY_FIT_LEVEL_SYNC") != nullptr;  // A/B switch
   const size_t gemm_smem = (size_t)NSTAGE * 2 * TILE_ELEMS * sizeof(double);
   const int persistent_grid = (KGROUPS == 1 ? 2 : 1) * sm_count();  // all CTAs co-resident
@@ -1084,6 +1104,7 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
         sched, s_arr, a.K, p.Sp, X0, chain, p.slots_per_bucket, a.status_flag);
     CHERRY_LAUNCH_CHECK("squaring_dataflow_kernel<fwd>");
   }
+  mark("squarings_fwd", stream);
   if (P_out != nullptr) {
     extract_P_kernel<<<dim3((a.S * a.S + 255) / 256, a.K), 256, 0, stream>>>(s_arr, X0, chain, p.slots_per_bucket,
                                                                              p.n_p, a.S, p.Sp, P_out);
@@ -1096,6 +1117,7 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   loss_reduce_kernel<<<1, 256, 0, stream>>>(loss_partial, a.K, p.loss_blocks, a.loss_part, s_arr, fused_partial,
                                             fused ? eb : 0);
   CHERRY_LAUNCH_CHECK("loss_reduce_kernel");
+  mark("loss_grad", stream);
   if (level_sync) {
     for (const Group& g : p.sq_bwd)
       if ((rc = launch_group(p, g, base, stream))) return rc;
@@ -1104,13 +1126,40 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
         sched, s_arr, a.K, p.Sp, X0, chain, p.slots_per_bucket, a.status_flag);
     CHERRY_LAUNCH_CHECK("squaring_dataflow_kernel<bwd>");
   }
+  mark("squarings_bwd", stream);
   accumulate_M_kernel<<<eb, EW_THREADS, wsmem, stream>>>(chain, p.slots_per_bucket, p.n_p, a.K, w, Pbar, s_arr,
                                                          fused ? 1 : 0);
   CHERRY_LAUNCH_CHECK("accumulate_M_kernel");
+  mark("accumulate_M", stream);
   for (const Group& g : p.pow_bwd)
     if ((rc = launch_group(p, g, base, stream))) return rc;
+  mark("powers_bwd", stream);
   unpad_kernel<<<(a.S * a.S + 255) / 256, 256, 0, stream>>>(Pbar, a.S, p.Sp, a.dQ_part);
   CHERRY_LAUNCH_CHECK("unpad_kernel");
+  mark("unpad", stream);
+  return 0;
+}
+
+// One evaluation with an event after every phase; prints the phase durations to stderr.
+int fit_large_timeline(const cherry_fit_args& a, cudaStream_t stream) {
+  Timeline tl;
+  for (int i = 0; i < Timeline::kMax; ++i) CHERRY_CUDA(cudaEventCreate(&tl.ev[i]));
+  int rc = fit_large_impl(a, stream, nullptr);  // warm
+  if (rc) return rc;
+  g_timeline = &tl;
+  rc = fit_large_impl(a, stream, nullptr);
+  g_timeline = nullptr;
+  if (rc) return rc;
+  CHERRY_CUDA(cudaStreamSynchronize(stream));
+  float total = 0.f;
+  for (int i = 1; i < tl.n; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, tl.ev[i - 1], tl.ev[i]);
+    fprintf(stderr, "[timeline] %-14s %8.1f us\n", tl.name[i], ms * 1e3f);
+    total += ms;
+  }
+  fprintf(stderr, "[timeline] %-14s %8.1f us\n", "total", total * 1e3f);
+  for (int i = 0; i < Timeline::kMax; ++i) cudaEventDestroy(tl.ev[i]);
   return 0;
 }
 
