@@ -198,8 +198,9 @@ __device__ __forceinline__ void gemm_tile(TermFn get_term, int Sp, int m0, int n
 // writes its partial product to `partial[(task*ksplit + z)]` and splitk_reduce_kernel finishes.
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_tasks_kernel(const GemmTask* __restrict__ tasks, const GemmTerm* __restrict__ terms, int Sp,
-                  int ksplit, double* __restrict__ partial) {
+                  int ksplit, double* __restrict__ partial, int* __restrict__ arrive) {
   extern __shared__ double smem[];
+  __shared__ int s_last;
   const GemmTask task = tasks[blockIdx.y];
   if (task.cond != nullptr && *task.cond <= task.level) return;
   const int tiles_n = Sp / BT;
@@ -211,6 +212,38 @@ gemm_tasks_kernel(const GemmTask* __restrict__ tasks, const GemmTerm* __restrict
                               : partial + ((size_t)blockIdx.y * ksplit + z) * (size_t)Sp * Sp;
   gemm_tile([&](int idx) { return terms[task.term_begin + idx]; }, Sp, m0, n0, c_begin, c_end, smem, out,
             (ksplit == 1) && task.accumulate);
+  if (ksplit == 1 || arrive == nullptr) return;
+  // Split-K without a second launch: the CTA that arrives last at this tile adds the ksplit
+  // partial tiles in z order (so the result does not depend on who is last) and writes C.
+  __threadfence();
+  __syncthreads();
+  int* ctr = arrive + blockIdx.y * gridDim.x + blockIdx.x;
+  if (threadIdx.x == 0) {
+    const int old = atomicAdd(ctr, 1);
+    s_last = (old == ksplit - 1);
+    if (s_last) *ctr = 0;  // ready for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const size_t n_p = (size_t)Sp * Sp;
+  const double* base = partial + (size_t)blockIdx.y * ksplit * n_p;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const int wq = warp & 3, rbase = (wq >> 1) * 40, cbase = (wq & 1) * 40;
+  if (warp >= 4) return;
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const size_t pos = (size_t)(m0 + rbase + 8 * i + g) * Sp + n0 + cbase + 8 * j + 2 * tg;
+      double2 v = task.accumulate ? *reinterpret_cast<const double2*>(task.C + pos) : make_double2(0.0, 0.0);
+      for (int zz = 0; zz < ksplit; ++zz) {
+        const double2 pz = __ldcg(reinterpret_cast<const double2*>(base + (size_t)zz * n_p + pos));
+        v.x += pz.x;
+        v.y += pz.y;
+      }
+      *reinterpret_cast<double2*>(task.C + pos) = v;
+    }
 }
 
 // ----------------------------------------------------------- dataflow squaring chains
@@ -793,7 +826,7 @@ struct Plan {
   int S, Sp, K, tiles;
   size_t n_p;
   // workspace offsets in bytes
-  size_t off_sched, off_scalars, off_s, off_tau, off_w, off_loss_partial, off_grad_theta, off_dpi, off_pibuf, off_tasks, off_terms;
+  size_t off_arrive, off_sched, off_scalars, off_s, off_tau, off_w, off_loss_partial, off_grad_theta, off_dpi, off_pibuf, off_tasks, off_terms;
   size_t off_P, off_Pbar, off_X0, off_chain, off_partial, total_bytes;
   int slots_per_bucket;   // chain slots 1..kSStore+1
   int loss_blocks;
@@ -832,6 +865,7 @@ void make_plan(Plan& p, int S, int K, char* base) {
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off = align256(off + bytes); return o; };
   p.off_scalars = carve(sizeof(LargeScalars));
+  p.off_arrive = carve(sizeof(int) * 64 * (size_t)p.tiles);
   p.off_sched = carve(sizeof(SqSchedule) + sizeof(int) * ((size_t)kSStore * K * 2 + (size_t)K * (kSStore + 1)));
   p.off_s = carve(sizeof(int) * K);
   p.off_tau = carve(sizeof(double) * K);
@@ -935,9 +969,13 @@ int launch_group(const Plan& p, const Group& g, char* base, cudaStream_t stream)
     return cherry::fail(CHERRY_ELIMIT, "fit_large: split-K partial buffer too small");
   const size_t smem = (size_t)NSTAGE * 2 * TILE_ELEMS * sizeof(double);
   dim3 grid(p.tiles, g.n_tasks, g.ksplit);
-  gemm_tasks_kernel<<<grid, GEMM_THREADS, smem, stream>>>(tasks, terms, p.Sp, g.ksplit, partial);
+  // A/B switch: the in-kernel "last CTA reduces" variant measured SLOWER (one CTA per tile re-reads
+  // ksplit partial tiles at low memory parallelism), so the separate reduce launch is the default.
+  static const bool separate_reduce = getenv("CHERRY_FIT_FUSED_REDUCE") == nullptr;
+  int* arrive = (separate_reduce || g.n_tasks > 64) ? nullptr : reinterpret_cast<int*>(base + p.off_arrive);
+  gemm_tasks_kernel<<<grid, GEMM_THREADS, smem, stream>>>(tasks, terms, p.Sp, g.ksplit, partial, arrive);
   CHERRY_LAUNCH_CHECK("gemm_tasks_kernel");
-  if (g.ksplit > 1) {
+  if (g.ksplit > 1 && arrive == nullptr) {
     int bx = (int)((p.n_p + EW_THREADS * 4 - 1) / (EW_THREADS * 4));
     splitk_reduce_kernel<<<dim3(bx, g.n_tasks), EW_THREADS, 0, stream>>>(tasks, g.ksplit, p.n_p, partial);
     CHERRY_LAUNCH_CHECK("splitk_reduce_kernel");
@@ -1007,6 +1045,7 @@ int fit_large_prepare(const cherry_fit_args& a, cudaStream_t stream) {
   CHERRY_CUDA(cudaMemcpy(base + p.off_tasks, p.tasks.data(), p.tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice));
   CHERRY_CUDA(cudaMemcpy(base + p.off_terms, p.terms.data(), p.terms.size() * sizeof(GemmTerm), cudaMemcpyHostToDevice));
   CHERRY_CUDA(cudaMemset(base + p.off_scalars, 0, sizeof(LargeScalars)));
+  CHERRY_CUDA(cudaMemset(base + p.off_arrive, 0, sizeof(int) * 64 * (size_t)p.tiles));
   // chain slots are read as "Xbar" for inactive levels never; but slot 1 of every bucket is
   // always written by loss_grad (s = 0) or the backward chain, so no clearing is needed.
   return 0;
@@ -1192,7 +1231,7 @@ int gemm_f64_batched(const double* A, const double* B, double* C, int n, int bat
   const GemmTerm* dm = reinterpret_cast<const GemmTerm*>(d + task_bytes);
   const size_t smem = (size_t)NSTAGE * 2 * TILE_ELEMS * sizeof(double);
   dim3 grid((n / BT) * (n / BT), batch, ksplit);
-  gemm_tasks_kernel<<<grid, GEMM_THREADS, smem, stream>>>(dt, dm, n, ksplit, partial);
+  gemm_tasks_kernel<<<grid, GEMM_THREADS, smem, stream>>>(dt, dm, n, ksplit, partial, nullptr);
   CHERRY_LAUNCH_CHECK("gemm_tasks_kernel");
   if (ksplit > 1) {
     int bx = (int)((nn + EW_THREADS * 4 - 1) / (EW_THREADS * 4));
