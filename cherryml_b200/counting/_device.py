@@ -33,6 +33,7 @@ class DeviceBatch:
     n_tiles: int
     n_sites_examined: int
     tile_items: Optional[np.ndarray] = None  # host copy, co only: items per tile
+    max_row_stride: int = 0  # co only
 
     def nbytes(self) -> int:
         return sum(
@@ -70,13 +71,15 @@ def to_device(batch: CountBatch, device="cuda") -> DeviceBatch:
         pair_t=_as_device(batch.pair_t, device),
         pair_fam=_as_device(batch.pair_fam, device),
         rate_vals=_as_device(batch.rate_vals, device),
-        aux=_as_device(batch.aux, device),
+        # the co-transition kernels read contact-paired rows, not the contact list
+        aux=_as_device(batch.aux if batch.kind == "lg" else np.zeros(0, np.int32), device),
         tiles=_as_device(batch.tiles, device),
         r_pad=batch.r_pad,
         n_pairs=batch.n_pairs,
         n_tiles=int(batch.tiles.shape[0]),
         n_sites_examined=batch.n_sites_examined,
         tile_items=tile_items,
+        max_row_stride=int(batch.fams["row_stride"].max()) if batch.fams.shape[0] else 16,
     )
 
 
@@ -159,10 +162,15 @@ def count_raw(
                 f"{total_items} (pair, contact) items in one batch could wrap a uint32 cell; "
                 "split the families into several batches"
             )
+        order = torch.empty(dev.n_pairs, dtype=torch.int32, device=device)
+        ws = torch.empty(2 * (K + 2), dtype=torch.int32, device=device)
+        rc = lib.cherry_sort_pairs_by_bucket(_lib.ptr(tab), dev.r_pad, dev.n_pairs, K,
+                                             _lib.ptr(order), _lib.ptr(ws), stream)
+        _lib.check(rc, "cherry_sort_pairs_by_bucket")
         rc = lib.cherry_count_co(
             _lib.ptr(dev.msa), _lib.ptr(dev.fams), _lib.ptr(dev.pair_a), _lib.ptr(dev.pair_b),
-            _lib.ptr(tab), dev.r_pad, _lib.ptr(dev.aux), _lib.ptr(dev.tiles), dev.n_tiles,
-            K, S, _lib.ptr(out), stream,
+            _lib.ptr(dev.pair_fam), _lib.ptr(order), _lib.ptr(ws), dev.n_pairs,
+            dev.max_row_stride, K, S, _lib.ptr(out), stream,
         )
         _lib.check(rc, "cherry_count_co")
     return out

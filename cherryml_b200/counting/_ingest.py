@@ -15,7 +15,8 @@ happens on the GPU.  What is mirrored from the reference:
 
 Layout produced (see DESIGN.md "Data layout in HBM"): one flat uint8 residue buffer; per
 family a descriptor; rows 16-byte aligned; for LG the columns are sorted by site-rate
-category with every category padded to a multiple of 4 sites.
+category with every category padded to a multiple of 4 sites; for co-transitions the rows
+are contact-paired (bytes 2c, 2c+1 = the two sites of contact c).
 """
 import os
 from dataclasses import dataclass, field
@@ -96,6 +97,19 @@ def contacting_pairs(contact_map: np.ndarray, minimum_distance: int) -> np.ndarr
     return np.stack([ii[keep], jj[keep]], axis=1).astype(np.int32)
 
 
+def contact_paired_rows(enc: np.ndarray, contacts: np.ndarray, skip: int) -> np.ndarray:
+    """Rows in the co-transition kernels' layout: bytes ``2c`` and ``2c+1`` are the residues at
+    the two sites of contact ``c``; padded with the skip code to a multiple of 16 bytes.  The
+    kernel then streams 4 bytes per (pair, contact) and never gathers."""
+    n_rows, P = enc.shape[0], len(contacts)
+    stride = max(16, (2 * P + 15) // 16 * 16)
+    rows = np.full((n_rows, stride), skip, dtype=np.uint8)
+    if n_rows and P:
+        rows[:, 0 : 2 * P : 2] = enc[:, contacts[:, 0]]
+        rows[:, 1 : 2 * P : 2] = enc[:, contacts[:, 1]]
+    return rows
+
+
 def alphabet_lut(states: Sequence[str]) -> np.ndarray:
     if len(states) > 254:
         raise ValueError("at most 254 states are supported")
@@ -120,7 +134,7 @@ class CountBatch:
     pair_t: np.ndarray  # float64 [P]
     pair_fam: np.ndarray  # int32 [P]
     rate_vals: np.ndarray  # float64 flat (LG: distinct site rates per family; co: 1.0)
-    aux: np.ndarray  # LG: uint16 group categories; co: int32 [n,2] contacts
+    aux: np.ndarray  # LG: uint16 group categories; co: int32 [n,2] contacts (host only)
     tiles: np.ndarray  # TILE_DTYPE [T]
     r_pad: int
     n_sites_examined: int = 0  # (pair, site) or (pair, contact) items, before validity
@@ -327,10 +341,7 @@ def encode_co_family(
     L = enc.shape[1] if enc.shape[0] else contact_map.shape[0]
     if len(contacts) and contacts.max() >= L:
         raise Exception(f"Family {name}: contact map is larger than the MSA")
-    stride = max(16, (L + 15) // 16 * 16)
-    rows = np.full((enc.shape[0], stride), int(lut.max()), dtype=np.uint8)
-    if enc.shape[0]:
-        rows[:, :L] = enc
+    rows = contact_paired_rows(enc, contacts, int(lut.max()))
     builder.add_family(name, rows, a, b, t, np.ones(1), contacts, len(contacts), len(contacts))
 
 

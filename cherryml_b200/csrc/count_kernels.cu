@@ -1,5 +1,5 @@
-// Transition counting for sm_100a: bucket table, LG (single-site) histogram, co-transition
-// (pair-of-sites) histogram and the symmetrisation epilogues.
+// Transition counting for sm_100a: bucket table, LG (single-site) histogram, per-site
+// histogram and the symmetrisation epilogues (co-transition counting: count_co.cu).
 //
 // Reference semantics (songlab-cal/CherryML v0.2.0):
 //   quantisation  cherryml/utils.py:35-56  ==  counting/_count_transitions.cpp:295-307
@@ -226,43 +226,6 @@ count_lg_kernel(const uint8_t* __restrict__ msa, const cherry_fam_desc* __restri
   }
 }
 
-// Co-transitions: a work item is (pair, contact).  Consecutive threads take consecutive
-// contacts of one pair, i.e. a warp gathers bytes from the same two rows (L1 hits) and
-// issues one L2 reduction per item into the [K][S^2][S^2] uint32 histogram.
-__global__ void __launch_bounds__(256)
-count_co_kernel(const uint8_t* __restrict__ msa, const cherry_fam_desc* __restrict__ fams,
-                const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b,
-                const uint8_t* __restrict__ tab, int r_pad, const int2* __restrict__ contacts,
-                const cherry_tile* __restrict__ tiles, int n_tiles, int K, int S,
-                uint32_t* __restrict__ counts) {
-  const uint32_t n = (uint32_t)(S * S);
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const cherry_tile tl = tiles[tile];
-    const cherry_fam_desc fd = fams[tl.fam];
-    const uint32_t nc = (uint32_t)fd.aux_cnt;
-    if (nc == 0) continue;
-    const uint8_t* __restrict__ base = msa + fd.msa_off;
-    const int2* __restrict__ cs = contacts + fd.aux_off;
-    const int64_t stride = fd.row_stride;
-    const uint32_t n_items = (uint32_t)tl.n_pairs * nc;
-    for (uint32_t i = threadIdx.x; i < n_items; i += blockDim.x) {
-      const uint32_t pl = i / nc, ci = i - pl * nc;
-      const int p = tl.pair_begin + (int)pl;
-      const uint32_t bucket = __ldg(tab + (int64_t)p * r_pad);
-      if (bucket == CHERRY_NO_BUCKET) continue;
-      const int2 ij = __ldg(cs + ci);
-      const uint8_t* ra = base + __ldg(pair_a + p) * stride;
-      const uint8_t* rb = base + __ldg(pair_b + p) * stride;
-      const uint32_t xi = __ldg(ra + ij.x), xj = __ldg(ra + ij.y);
-      const uint32_t yi = __ldg(rb + ij.x), yj = __ldg(rb + ij.y);
-      if (xi < (uint32_t)S && xj < (uint32_t)S && yi < (uint32_t)S && yj < (uint32_t)S) {
-        const size_t s = xi * S + xj, e = yi * S + yj;
-        atomicAdd(counts + ((size_t)bucket * n + s) * n + e, 1u);
-      }
-    }
-  }
-}
-
 // Per-site counting (SiteRM): one CTA per cherry; the cherry's bucket is quantised once (fp64,
 // same expression as everywhere else), then every site l adds one to counts[l][b][x][y].
 __global__ void __launch_bounds__(256)
@@ -404,24 +367,6 @@ int cherry_count_lg(const uint8_t* msa, const cherry_fam_desc* fams, const int32
         msa, fams, pair_a, pair_b, tab, r_pad, group_cat, tiles, n_tiles, K, S, counts);
   }
   CHERRY_LAUNCH_CHECK("count_lg_kernel");
-  return 0;
-}
-
-int cherry_count_co(const uint8_t* msa, const cherry_fam_desc* fams, const int32_t* pair_a,
-                    const int32_t* pair_b, const uint8_t* tab, int r_pad,
-                    const int32_t* contacts, const cherry_tile* tiles, int n_tiles, int K,
-                    int S, uint32_t* counts, void* stream) {
-  int rc = check_count_args(msa, fams, pair_a, pair_b, tab, tiles, counts, n_tiles, K, S, r_pad);
-  if (rc) return rc;
-  if (!contacts) return cherry::fail(CHERRY_EINVAL, "count_co: null contacts");
-  if (S > 64) return cherry::fail(CHERRY_ELIMIT, "count_co: S=%d > 64", S);
-  if (n_tiles == 0) return 0;
-  int grid = cherry::sm_count() * 8;
-  if (grid > n_tiles) grid = n_tiles;
-  count_co_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      msa, fams, pair_a, pair_b, tab, r_pad, reinterpret_cast<const int2*>(contacts), tiles,
-      n_tiles, K, S, counts);
-  CHERRY_LAUNCH_CHECK("count_co_kernel");
   return 0;
 }
 

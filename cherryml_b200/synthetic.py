@@ -141,9 +141,6 @@ def synthetic_co(
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
     n_pairs = n_seqs // 2
-    stride = max(16, (n_sites + 15) // 16 * 16)
-    msa = _residue_rows(n_fams, n_seqs, n_sites, stride, np.arange(n_sites), gen, device, gap_frac, mut_frac)
-    pair_a, pair_b, pair_t, pair_fam = _pair_arrays(n_fams, n_pairs, gen, device)
     rng = np.random.default_rng(seed)
     perm = np.argsort(rng.random((n_fams, n_sites)), axis=1)
     half = n_sites // 2
@@ -152,6 +149,15 @@ def synthetic_co(
     keep = (j - i) >= min_dist
     cnt = keep.sum(axis=1)
     contacts = np.stack([i[keep], j[keep]], axis=1).astype(np.int32)  # row-major == family order
+    # Rows are contact-paired (bytes 2c, 2c+1 = the two sites of contact c).  Residues are
+    # i.i.d. over sites, so the rows are drawn directly in that layout; bytes past a
+    # family's 2*cnt are the skip code.
+    n_cols = 2 * int(cnt.max()) if n_fams else 0
+    stride = max(16, (n_cols + 15) // 16 * 16)
+    msa = _residue_rows(n_fams, n_seqs, n_cols, stride, np.arange(n_cols), gen, device, gap_frac, mut_frac)
+    live = torch.arange(stride, device=device)[None, :] < torch.as_tensor(2 * cnt, device=device)[:, None]
+    msa.view(n_fams, n_seqs, stride).masked_fill_(~live[:, None, :], SKIP)
+    pair_a, pair_b, pair_t, pair_fam = _pair_arrays(n_fams, n_pairs, gen, device)
     fams = np.zeros(n_fams, dtype=FAM_DESC_DTYPE)
     f = np.arange(n_fams, dtype=np.int64)
     fams["msa_off"] = f * n_seqs * stride
@@ -203,6 +209,7 @@ def as_device_batch(syn: dict, device="cuda"):
         rate_vals=dev(np.asarray(syn["rate_vals"], dtype=np.float64)), aux=dev(syn["aux"]),
         tiles=dev(syn["tiles"]), r_pad=syn["r_pad"], n_pairs=int(syn["pair_a"].shape[0]),
         n_tiles=int(syn["tiles"].shape[0]), n_sites_examined=syn["n_sites_examined"], tile_items=tile_items,
+        max_row_stride=int(syn["fams"]["row_stride"].max()) if len(syn["fams"]) else 16,
     )
 
 
@@ -229,15 +236,20 @@ def write_text_rendering(
         os.makedirs(os.path.join(out_dir, sub), exist_ok=True)
     if batch.kind == "lg":
         _, cols, cat_of_site, _ = _lg_layout(n_sites, shape["n_rate_cats"])
-    else:
-        cols = np.arange(n_sites)
     names = []
     for f in fam_ids:
         fd = batch.fams[f]
         name = f"fam{f:06d}"
         names.append(name)
-        rows = batch.msa[fd["msa_off"] : fd["msa_off"] + n_seqs * stride].reshape(n_seqs, stride)[:, cols]
-        text = table[rows]
+        rows = batch.msa[fd["msa_off"] : fd["msa_off"] + n_seqs * stride].reshape(n_seqs, stride)
+        if batch.kind == "lg":
+            text = table[rows[:, cols]]
+        else:
+            # contact-paired rows -> site order; sites in no contact are never read: gaps
+            cs = batch.aux[fd["aux_off"] : fd["aux_off"] + fd["aux_cnt"]]
+            text = np.full((n_seqs, n_sites), ord("-"), dtype=np.uint8)
+            text[:, cs[:, 0]] = table[rows[:, 0 : 2 * len(cs) : 2]]
+            text[:, cs[:, 1]] = table[rows[:, 1 : 2 * len(cs) : 2]]
         with open(os.path.join(out_dir, "msa_dir", name + ".txt"), "w") as fh:
             fh.write("".join(f">seq{r}\n{text[r].tobytes().decode('ascii')}\n" for r in range(n_seqs)))
         t = batch.pair_t[f * n_pairs : (f + 1) * n_pairs]

@@ -62,7 +62,9 @@ void oracle_count_lg(const uint8_t* msa, const fam_desc* fams, const int32_t* pa
   }
 }
 
-/* counts: double [K][S*S][S*S], accumulated into.  contacts: int32 [n][2]. */
+/* counts: double [K][S*S][S*S], accumulated into.  Rows are contact-paired: bytes 2k, 2k+1
+ * of a row are the residues at the two sites of the family's k-th contact (the encoder's
+ * layout, cherryml_b200/counting/_ingest.py contact_paired_rows); `contacts` is unused. */
 void oracle_count_co(const uint8_t* msa, const fam_desc* fams, const int32_t* pair_a,
                      const int32_t* pair_b, const double* pair_t, const int32_t* pair_fam,
                      int64_t n_pairs, const int32_t* contacts, const double* grid, int K, int S,
@@ -76,8 +78,8 @@ void oracle_count_co(const uint8_t* msa, const fam_desc* fams, const int32_t* pa
     const uint8_t* rb = msa + fd->msa_off + (int64_t)pair_b[p] * fd->row_stride;
     double* c = counts + (size_t)b * n * n;
     for (int k = 0; k < fd->aux_cnt; ++k) {
-      int i = contacts[2 * (fd->aux_off + k)], j = contacts[2 * (fd->aux_off + k) + 1];
-      unsigned xi = ra[i], xj = ra[j], yi = rb[i], yj = rb[j];
+      (void)contacts;
+      unsigned xi = ra[2 * k], xj = ra[2 * k + 1], yi = rb[2 * k], yj = rb[2 * k + 1];
       if (xi >= (unsigned)S || xj >= (unsigned)S || yi >= (unsigned)S || yj >= (unsigned)S) continue;
       size_t s = xi * S + xj, e = yi * S + yj, sr = xj * S + xi, er = yj * S + yi;
       if (directed) {

@@ -16,7 +16,10 @@ _lib = None
 def _load():
     global _lib
     if _lib is None:
-        if not os.path.exists(C_LIB):
+        src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "count_encoded.c")
+        if not os.path.exists(C_LIB) or (
+            os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(C_LIB)
+        ):
             build_c_oracle()
         _lib = ctypes.CDLL(C_LIB)
         _lib.oracle_quantization_idx.restype = ctypes.c_int

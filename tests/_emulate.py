@@ -54,7 +54,10 @@ def emulate_count(batch, grid, S):
                     continue
                 ra = batch.msa[fd["msa_off"] + batch.pair_a[p] * stride :][:stride].astype(np.int64)
                 rb = batch.msa[fd["msa_off"] + batch.pair_b[p] * stride :][:stride].astype(np.int64)
-                xi, xj, yi, yj = ra[cs[:, 0]], ra[cs[:, 1]], rb[cs[:, 0]], rb[cs[:, 1]]
+                assert stride % 16 == 0 and 2 * len(cs) <= stride
+                assert np.all(ra[2 * len(cs):] == S) and np.all(rb[2 * len(cs):] == S)
+                # contact-paired rows: bytes 2c, 2c+1 = residues at the two sites of contact c
+                xi, xj, yi, yj = ra[0:2 * len(cs):2], ra[1:2 * len(cs):2], rb[0:2 * len(cs):2], rb[1:2 * len(cs):2]
                 ok = (xi < S) & (xj < S) & (yi < S) & (yj < S)
                 np.add.at(raw[b], (xi[ok] * S + xj[ok], yi[ok] * S + yj[ok]), 1)
     assert np.all(seen_pairs == 1), "every pair must be covered by exactly one tile"

@@ -179,6 +179,96 @@ def test_co_synthetic_vs_oracle():
         assert np.array_equal(got, count_batch_oracle(batch, grid, 20, directed))
 
 
+def test_sort_pairs_by_bucket():
+    """The device counting sort groups the pairs by bucket; pairs outside the grid go last."""
+    rng = np.random.default_rng(4)
+    for n_pairs, K, r_pad in ((1, 3, 4), (777, 7, 4), (100_003, 129, 8), (5000, 254, 4)):
+        tab = np.full((n_pairs, r_pad), 255, dtype=np.uint8)
+        tab[:, 0] = rng.integers(0, K + 3, n_pairs)  # K..K+2 never occur in a real table, 255 does
+        tab[tab[:, 0] >= K, 0] = 255
+        tab_d = torch.from_numpy(tab).cuda()
+        order = torch.empty(n_pairs, dtype=torch.int32, device="cuda")
+        ws = torch.empty(2 * (K + 2), dtype=torch.int32, device="cuda")
+        rc = _lib.load().cherry_sort_pairs_by_bucket(_lib.ptr(tab_d), r_pad, n_pairs, K, _lib.ptr(order),
+                                                     _lib.ptr(ws), _lib.current_stream_ptr())
+        _lib.check(rc, "sort")
+        order, ws = order.cpu().numpy(), ws.cpu().numpy()
+        b = np.minimum(tab[:, 0].astype(np.int64), K)
+        assert np.array_equal(np.sort(order), np.arange(n_pairs))
+        assert np.array_equal(ws[: K + 2], np.concatenate([[0], np.cumsum(np.bincount(b, minlength=K + 1))]))
+        assert np.all(np.diff(b[order]) >= 0)
+
+
+def test_co_ragged_families_and_small_alphabets():
+    """Families with 0 .. 3000 contacts, odd row counts, pairs outside the grid, S = 3 and
+    S = 20 (shared-memory histogram) and S = 24 (global reductions only)."""
+    from cherryml_b200.counting._ingest import _BatchBuilder, contact_paired_rows
+
+    for S in (3, 20, 24):
+        rng = np.random.default_rng(S)
+        builder = _BatchBuilder("co")
+        for f, (n_rows, L, P) in enumerate([(2, 9, 0), (6, 17, 3), (40, 333, 160), (11, 64, 31), (2, 7000, 3000),
+                                            (300, 40, 20)]):
+            enc = rng.integers(0, S + 1, size=(n_rows, L)).astype(np.uint8)  # S is the skip code
+            enc[1::2] = np.where(rng.random((len(enc[1::2]), L)) < 0.6, enc[0 : 2 * len(enc[1::2]) : 2], enc[1::2])
+            contacts = np.stack([rng.integers(0, L, P), rng.integers(0, L, P)], axis=1).astype(np.int32)
+            rows = contact_paired_rows(enc, contacts, S)
+            a = np.arange(0, n_rows - 1, 2, dtype=np.int32)
+            t = rng.lognormal(-0.5, 1.5, len(a))
+            builder.add_family(f"f{f}", rows, a, a + 1, t, np.ones(1), contacts, P, P)
+        batch = builder.finish()
+        grid = [0.05 * 1.3**i for i in range(15)]
+        for directed in (False, True):
+            got = count_batch(batch, grid, S, directed=directed).cpu().numpy()
+            assert np.array_equal(got, count_batch_oracle(batch, grid, S, directed))
+        assert got.sum() > 0
+
+
+def test_co_row_longer_than_a_stage_is_an_error():
+    from cherryml_b200.counting._ingest import _BatchBuilder, contact_paired_rows
+
+    builder = _BatchBuilder("co")
+    P = 11000  # 22000 bytes per row > 20480
+    contacts = np.zeros((P, 2), dtype=np.int32)
+    rows = contact_paired_rows(np.zeros((2, 4), dtype=np.uint8), contacts, 20)
+    builder.add_family("f", rows, np.array([0]), np.array([1]), np.array([0.5]), np.ones(1), contacts, P, P)
+    with pytest.raises(_lib.CherryError, match="exceeds"):
+        count_batch(builder.finish(), [0.1, 1.0], 20, directed=False)
+
+
+def test_full_size_properties_co():
+    """BASELINE config-4 shape on a slice (1024 families x 1024 x 300, perfect matching):
+    conservation, the symmetries of the symmetrised tensor, and a 16-family slice vs the oracle."""
+    grid = quantization_grid()
+    K = len(grid)
+    n_fams, n_pairs = 1024, 512
+    syn = synthetic_co(n_fams, 1024, 300, seed=5, device="cuda")
+    dev = as_device_batch(syn, "cuda")
+    grid_dev = torch.from_numpy(sorted_grid(grid)).cuda()
+    raw = count_raw(dev, grid_dev, K, 20)
+    total = int(raw.sum(dtype=torch.int64).item())
+    stride = syn["shape"]["stride"]
+    rows = syn["msa"].view(n_fams, n_pairs, 2, stride // 2, 2)
+    valid = (rows < 20).all(dim=4).all(dim=2)  # [fam, pair, contact]
+    in_grid = ((syn["pair_t"] >= grid[0]) & (syn["pair_t"] <= grid[-1])).view(n_fams, n_pairs, 1)
+    assert total == int((valid & in_grid).sum().item())
+    sym = symmetrize(raw, "co", K, 20, directed=False)
+    assert torch.equal(sym, sym.transpose(1, 2)) and float(sym.sum().item()) == float(total)
+    perm = (torch.arange(400, device="cuda") % 20) * 20 + torch.arange(400, device="cuda") // 20
+    assert torch.equal(sym, sym[:, perm][:, :, perm])
+    # counting twice into the same buffer doubles every cell (accumulate semantics)
+    raw2 = count_raw(dev, grid_dev, K, 20, out=raw.clone())
+    assert torch.equal(raw2, 2 * raw)
+    import copy
+    batch = as_count_batch(syn)
+    sl = slice(0, 16 * n_pairs)
+    exp = count_batch_oracle(batch, grid, 20, False, pair_slice=sl)
+    d3 = copy.copy(dev)
+    d3.n_pairs = 16 * n_pairs
+    got = symmetrize(count_raw(d3, grid_dev, K, 20), "co", K, 20, False).cpu().numpy()
+    assert np.array_equal(got, exp)
+
+
 def test_too_many_quantization_points_is_an_error():
     syn = synthetic_lg(2, 8, 32, 4, seed=1)
     with pytest.raises(_lib.CherryError):
