@@ -163,14 +163,17 @@ def count_raw(
                 "split the families into several batches"
             )
         order = torch.empty(dev.n_pairs, dtype=torch.int32, device=device)
+        recs = torch.empty(dev.n_pairs * 16, dtype=torch.uint8, device=device)
         ws = torch.empty(2 * (K + 2), dtype=torch.int32, device=device)
-        rc = lib.cherry_sort_pairs_by_bucket(_lib.ptr(tab), dev.r_pad, dev.n_pairs, K,
-                                             _lib.ptr(order), _lib.ptr(ws), stream)
+        rc = lib.cherry_sort_pairs_by_bucket(
+            _lib.ptr(tab), dev.r_pad, dev.n_pairs, K, _lib.ptr(dev.fams), _lib.ptr(dev.pair_a),
+            _lib.ptr(dev.pair_b), _lib.ptr(dev.pair_fam), _lib.ptr(order), _lib.ptr(recs), _lib.ptr(ws),
+            stream,
+        )
         _lib.check(rc, "cherry_sort_pairs_by_bucket")
         rc = lib.cherry_count_co(
-            _lib.ptr(dev.msa), _lib.ptr(dev.fams), _lib.ptr(dev.pair_a), _lib.ptr(dev.pair_b),
-            _lib.ptr(dev.pair_fam), _lib.ptr(order), _lib.ptr(ws), dev.n_pairs,
-            dev.max_row_stride, K, S, _lib.ptr(out), stream,
+            _lib.ptr(dev.msa), _lib.ptr(recs), _lib.ptr(ws), dev.n_pairs, dev.max_row_stride, K, S,
+            _lib.ptr(out), stream,
         )
         _lib.check(rc, "cherry_count_co")
     return out

@@ -26,10 +26,12 @@
 
 namespace {
 
-constexpr int kCoThreads = 512;
-constexpr int kCoStages = 3;
-constexpr int kCoRegionBytes = 20 * 1024;   // per stage: this many bytes of a-rows and of b-rows
-constexpr int kCoMaxPairsPerStage = 64;     // two warp passes of the producer
+constexpr int kCoConsumerWarps = 24;
+constexpr int kCoProducerWarps = 2;
+constexpr int kCoThreads = (kCoConsumerWarps + kCoProducerWarps) * 32;
+constexpr int kCoStages = 4;
+constexpr int kCoRegionBytes = 16 * 1024;   // per stage: this many bytes of a-rows and of b-rows
+constexpr int kCoMaxPairsPerStage = 32 * kCoProducerWarps;  // one warp pass per producer warp
 constexpr int kCoSmemLimit = 227 * 1024;
 
 // ------------------------------------------------------------------ counting sort by bucket
@@ -63,8 +65,18 @@ __global__ void co_bucket_scan_kernel(int K, int32_t* __restrict__ ws) {
   ws[K + 1] = acc;
 }
 
+// Scatter: besides the pair index, every sorted position gets a 16-byte record with
+// everything the counting kernel's producer needs -- {byte offset of row a, (offset of row
+// b - offset of row a) / 16, row stride} -- so that the producer's only global access is one
+// coalesced load per lane (the indirections pair -> family -> descriptor happen here, in
+// parallel over all pairs).
 __global__ void co_bucket_scatter_kernel(const uint8_t* __restrict__ tab, int r_pad, int64_t n_pairs,
-                                         int K, int32_t* __restrict__ ws, int32_t* __restrict__ order) {
+                                         int K, const cherry_fam_desc* __restrict__ fams,
+                                         const int32_t* __restrict__ pair_a,
+                                         const int32_t* __restrict__ pair_b,
+                                         const int32_t* __restrict__ pair_fam,
+                                         int32_t* __restrict__ ws, int32_t* __restrict__ order,
+                                         cherry_co_rec* __restrict__ recs) {
   __shared__ int cnt[256];
   __shared__ int base[256];
   const int64_t per_block = (n_pairs + gridDim.x - 1) / gridDim.x;
@@ -85,7 +97,20 @@ __global__ void co_bucket_scatter_kernel(const uint8_t* __restrict__ tab, int r_
     if ((int)threadIdx.x <= K && cnt[threadIdx.x])
       base[threadIdx.x] = atomicAdd(&ws[K + 2 + threadIdx.x], cnt[threadIdx.x]);
     __syncthreads();
-    if (b >= 0) order[base[b] + rank] = (int32_t)p;
+    if (b >= 0) {
+      const int dst = base[b] + rank;
+      order[dst] = (int32_t)p;
+      if (recs) {
+        const cherry_fam_desc* fd = fams + pair_fam[p];
+        const int64_t stride = fd->row_stride;
+        const int64_t oa = fd->msa_off + pair_a[p] * stride, ob = fd->msa_off + pair_b[p] * stride;
+        cherry_co_rec r;
+        r.off_a = oa;
+        r.delta_b16 = (int32_t)((ob - oa) / 16);
+        r.stride = (int32_t)stride;
+        recs[dst] = r;
+      }
+    }
     __syncthreads();
   }
 }
@@ -97,8 +122,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -111,11 +136,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE_%=:\n"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-// 1-D bulk copy global -> shared (TMA engine, no tensor map); 16-byte aligned, size % 16 == 0.
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+// 16-byte asynchronous copy global -> shared (LDGSTS), bypassing L1.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// The mbarrier gets one arrival (already counted at init: .noinc) once all cp.async issued
+// by this thread so far have completed.
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() {  // named barrier 1: the consumer warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(kCoConsumerWarps * 32) : "memory");
 }
 
 struct CoStageMeta {
@@ -123,75 +154,86 @@ struct CoStageMeta {
   int bucket;
 };
 
-// One (pair, contact): bytes (xi, xj) of row a and (yi, yj) of row b in the low 16 bits of
-// ha / hb.  `hist` = shared histogram (I then J), counts_b = this bucket's global cells.
+// One (pair, contact): (xi, xj) = bytes (0, 1) of ha, (yi, yj) = bytes (0, 1) of hb (the upper
+// halves are ignored).  The shared histogram has S1 = S+1 states per axis, so a skip byte
+// (== S) on a near-diagonal item lands in a junk cell that the flush drops -- no validity
+// test on the hot path; only the rare both-sites-changed items test it before their L2
+// reduction.  I at hist, J at hist + 4*S1^3; row4 = 4*S1, plane4 = 4*S1*S1.
 template <bool SMEM>
-__device__ __forceinline__ void co_contact(uint32_t ha, uint32_t hb, uint32_t S, uint32_t S3,
-                                           uint32_t hist, uint32_t* __restrict__ counts_b) {
-  const uint32_t xi = ha & 0xffu, xj = (ha >> 8) & 0xffu;
-  const uint32_t yi = hb & 0xffu, yj = (hb >> 8) & 0xffu;
-  if (xi >= S || xj >= S || yi >= S || yj >= S) return;
-  if (SMEM && xj == yj) {
-    const uint32_t idx = (xi * S + yi) * S + xj;
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist + idx * 4u) : "memory");
-  } else if (SMEM && xi == yi) {
-    const uint32_t idx = S3 + (xj * S + yj) * S + xi;
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist + idx * 4u) : "memory");
+__device__ __forceinline__ void co_contact(uint32_t ha, uint32_t hb, uint32_t S, uint32_t row4,
+                                           uint32_t plane4, uint32_t hist, uint32_t histJ,
+                                           uint32_t* __restrict__ counts_b) {
+  const uint32_t d = ha ^ hb;
+  const bool eqi = (d & 0x00ffu) == 0, eqj = (d & 0xff00u) == 0;
+  if (SMEM && (eqi || eqj)) {
+    // eqj: I[xi][yi][xj] -> (p, q, r) = (a0, b0, a1);  else J[xj][yj][xi] -> (a1, b1, a0)
+    const uint32_t w = __byte_perm(ha, hb, eqj ? 0x4041u : 0x4150u);  // bytes: r, q, p, (unused)
+    const uint32_t lo = __dp4a(w, 0x00000004u | (row4 << 8), eqj ? hist : histJ);  // 4r + row4*q + base
+    const uint32_t addr = __byte_perm(w, 0, 0x4442u) * plane4 + lo;
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
   } else {
-    const uint32_t n = S * S;
-    atomicAdd(counts_b + (size_t)(xi * S + xj) * n + (yi * S + yj), 1u);
+    const uint32_t xi = ha & 0xffu, xj = (ha >> 8) & 0xffu;
+    const uint32_t yi = hb & 0xffu, yj = (hb >> 8) & 0xffu;
+    if (xi < S && xj < S && yi < S && yj < S) {
+      const uint32_t n = S * S;
+      atomicAdd(counts_b + (size_t)(xi * S + xj) * n + (yi * S + yj), 1u);
+    }
   }
 }
 
 template <bool SMEM>
-__device__ __forceinline__ void co_flush(uint32_t* hist, int S, uint32_t* __restrict__ counts_b) {
+__device__ __forceinline__ void co_flush(uint32_t* hist, int S, int tid, uint32_t* __restrict__ counts_b) {
   if (!SMEM) return;
-  const int S3 = S * S * S, n = S * S;
-  for (int i = threadIdx.x; i < 2 * S3; i += kCoThreads) {
+  const int S1 = S + 1, T = S1 * S1 * S1, n = S * S;
+  for (int i = tid; i < 2 * T; i += kCoConsumerWarps * 32) {
     const uint32_t v = hist[i];
     if (v == 0) continue;
     hist[i] = 0;
-    int r = i < S3 ? i : i - S3;
-    const int c = r % S;
-    r /= S;
-    const int q = r % S, p = r / S;
+    int r = i < T ? i : i - T;
+    const int c = r % S1;
+    r /= S1;
+    const int q = r % S1, p = r / S1;
+    if (c >= S || q >= S || p >= S) continue;  // junk cells (an item with a skip byte)
     // I[p=xi][q=yi][c=xj]: (xi,xj)->(yi,xj);  J[p=xj][q=yj][c=xi]: (xi,xj)->(xi,yj)
-    const int s = i < S3 ? p * S + c : c * S + p;
-    const int e = i < S3 ? q * S + c : c * S + q;
+    const int s = i < T ? p * S + c : c * S + p;
+    const int e = i < T ? q * S + c : c * S + q;
     atomicAdd(counts_b + (size_t)s * n + e, v);
   }
 }
 
-// Persistent kernel: CTA c owns the sorted pairs [c*n_valid/G, (c+1)*n_valid/G).  Warp 0
-// is also the producer: it walks its range, packs up to 64 pairs of ONE bucket into a stage
-// (a-rows back to back in region A, b-rows at the same offsets in region B) with one bulk
-// copy per row, and publishes {bytes, bucket}.  All warps consume: item = 8 bytes of region
-// A + the same 8 bytes of region B = 4 contacts; no per-item pair lookup is needed because
-// the whole stage has one bucket and the padding bytes are skip codes.
+// Persistent, warp-specialised: CTA c owns the sorted pairs [c*n_valid/G, (c+1)*n_valid/G).
+// The last two warps are producers: they walk the range, pack up to 64 pairs of ONE bucket
+// into a stage (a-rows back to back in region A, b-rows at the same offsets in region B)
+// with 16-byte cp.async copies, and publish {bytes, bucket}; full/empty mbarriers decouple
+// them from the consumer warps by kCoStages stages.  (v2 used one cp.async.bulk per row: a
+// 304-byte bulk copy per lane serialises in the uniform datapath, 7 us per 39 KB stage.)  Consumers: item = 8 bytes of region A + the
+// same 8 bytes of region B = 4 contacts; no per-item pair lookup is needed because the whole
+// stage has one bucket and padding bytes are skip codes.
 template <bool SMEM>
 __global__ void __launch_bounds__(kCoThreads, 1)
-count_co_sorted_kernel(const uint8_t* __restrict__ msa, const cherry_fam_desc* __restrict__ fams,
-                       const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b,
-                       const int32_t* __restrict__ pair_fam, const int32_t* __restrict__ order,
+count_co_sorted_kernel(const uint8_t* __restrict__ msa, const cherry_co_rec* __restrict__ recs,
                        const int32_t* __restrict__ bucket_start, int K, int S,
                        uint32_t* __restrict__ counts) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) unsigned long long bars[kCoStages];
+  __shared__ __align__(8) unsigned long long full_bar[kCoStages];
+  __shared__ __align__(8) unsigned long long empty_bar[kCoStages];
   __shared__ CoStageMeta meta[kCoStages];
   __shared__ int sbstart[CHERRY_MAX_BUCKETS + 2];
 
   const int tid = threadIdx.x;
-  const int S3 = S * S * S;
+  const int S1 = S + 1, T = S1 * S1 * S1;
   const size_t cells = (size_t)S * S * S * S;
   uint8_t* stage_base = smem;  // kCoStages * 2 * kCoRegionBytes
   uint32_t* hist = reinterpret_cast<uint32_t*>(smem + (size_t)kCoStages * 2 * kCoRegionBytes);
-  const uint32_t hist_s = smem_u32(hist);
 
   for (int i = tid; i <= K + 1; i += kCoThreads) sbstart[i] = bucket_start[i];
   if (SMEM)
-    for (int i = tid; i < 2 * S3; i += kCoThreads) hist[i] = 0;
+    for (int i = tid; i < 2 * T; i += kCoThreads) hist[i] = 0;
   if (tid == 0) {
-    for (int s = 0; s < kCoStages; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    for (int s = 0; s < kCoStages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 2 * kCoProducerWarps * 32);
+      mbar_init(smem_u32(&empty_bar[s]), kCoConsumerWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -200,79 +242,109 @@ count_co_sorted_kernel(const uint8_t* __restrict__ msa, const cherry_fam_desc* _
   const int r0 = (int)(n_valid * blockIdx.x / gridDim.x);
   const int r1 = (int)(n_valid * (blockIdx.x + 1) / gridDim.x);
 
-  // producer state (warp 0, uniform across its lanes)
-  int pos = r0, pb = 0;
-  auto produce = [&](int s) {
-    const int lane = tid & 31;
-    const uint32_t bar = smem_u32(&bars[s]);
-    if (pos >= r1) {
-      if (lane == 0) {
-        meta[s].nbytes = -1;
-        meta[s].bucket = -1;
-        mbar_arrive_expect_tx(bar, 0);
+  if (tid >= kCoConsumerWarps * 32) {
+    // ------------------------------------------------------------ producer warps
+    // Both producer warps walk the range in lockstep (same loads, same scan, no
+    // communication); warp w issues the copies of pass w of every stage.  Copies are
+    // 16-byte cp.async (LDGSTS), one warp instruction per 512 bytes of a row; each thread
+    // then hands its copies to the stage's mbarrier (cp.async.mbarrier.arrive.noinc).
+    const int lane = tid & 31, pw = (tid >> 5) - kCoConsumerWarps;
+    int pos = r0, pb = 0;
+    for (int k = 0;; ++k) {
+      const int s = k % kCoStages;
+      if (k >= kCoStages) mbar_wait(smem_u32(&empty_bar[s]), (uint32_t)(((k / kCoStages) - 1) & 1));
+      const uint32_t bar = smem_u32(&full_bar[s]);
+      if (pos >= r1) {
+        if (pw == 0 && lane == 0) {
+          meta[s].nbytes = -1;
+          meta[s].bucket = -1;
+        }
+        __syncwarp();
+        mbar_arrive(bar);  // two arrivals per producer thread and stage, as below
+        mbar_arrive(bar);
+        break;
       }
-      return;
-    }
-    while (sbstart[pb + 1] <= pos) ++pb;  // bucket of position pos
-    const int limit = min(r1, sbstart[pb + 1]);
-    const uint32_t regA = smem_u32(stage_base + (size_t)s * 2 * kCoRegionBytes);
-    const uint32_t regB = regA + kCoRegionBytes;
-    int used = 0;
+      while (sbstart[pb + 1] <= pos) ++pb;  // bucket of position pos
+      const int limit = min(r1, sbstart[pb + 1]);
+      const uint32_t regA = smem_u32(stage_base + (size_t)s * 2 * kCoRegionBytes);
+      const uint32_t regB = regA + kCoRegionBytes;
+      if (pos + kCoMaxPairsPerStage + lane < r1)  // next stage's records: into L2 now
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(recs + pos + kCoMaxPairsPerStage + lane));
+      int used = 0;
 #pragma unroll 1
-    for (int pass = 0; pass < kCoMaxPairsPerStage / 32; ++pass) {
-      const int idx = pos + lane;
-      const bool in = idx < limit;
-      int stride = 0;
-      const uint8_t *ra = nullptr, *rb = nullptr;
-      if (in) {
-        const int o = __ldg(order + idx);
-        const cherry_fam_desc* fd = fams + __ldg(pair_fam + o);
-        stride = fd->row_stride;
-        const uint8_t* base = msa + fd->msa_off;
-        ra = base + (int64_t)__ldg(pair_a + o) * stride;
-        rb = base + (int64_t)__ldg(pair_b + o) * stride;
-      }
-      int incl = stride;  // inclusive warp scan of the strides
+      for (int pass = 0; pass < kCoProducerWarps; ++pass) {
+        const int idx = pos + lane;
+        const bool in = idx < limit;
+        int stride = 0;
+        const uint8_t* ra = msa;
+        int delta16 = 0;
+        if (in) {
+          const int4 rec = __ldg(reinterpret_cast<const int4*>(recs) + idx);
+          ra = msa + (((int64_t)(uint32_t)rec.y << 32) | (uint32_t)rec.x);
+          delta16 = rec.z;
+          stride = rec.w;
+        }
+        int incl = stride;  // inclusive warp scan of the strides
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += v;
+        }
+        const bool take = in && (used + incl <= kCoRegionBytes);
+        const int ntake = __popc(__ballot_sync(0xffffffffu, take));  // a prefix of the lanes
+        if (pass == pw) {
+          // a quad of lanes per pair: 64 contiguous bytes (two full sectors) of each row per
+          // step, 8 pairs per sub-step; the row addresses come from the lane holding the pair
+          const uint32_t off = (uint32_t)(used + incl - stride);
+          const int q = lane >> 2, c0 = (lane & 3) * 16;
+#pragma unroll 1
+          for (int g0 = 0; g0 < ntake; g0 += 8) {
+            const int g = g0 + q;
+            const uint64_t ga = __shfl_sync(0xffffffffu, (uint64_t)ra, g & 31);
+            const int gd = __shfl_sync(0xffffffffu, delta16, g & 31);
+            const int gs = __shfl_sync(0xffffffffu, stride, g & 31);
+            const uint32_t go = __shfl_sync(0xffffffffu, off, g & 31);
+            if (g < ntake) {
+              const uint8_t* pa = reinterpret_cast<const uint8_t*>(ga) + c0;
+              const uint8_t* pbrow = pa + (int64_t)gd * 16;
+              uint32_t da = regA + go + c0;
+              for (int c = c0; c < gs; c += 64) {
+                cp_async16(da, pa);
+                cp_async16(da + kCoRegionBytes, pbrow);
+                da += 64; pa += 64; pbrow += 64;
+              }
+            }
+          }
+        }
+        if (ntake > 0) used += __shfl_sync(0xffffffffu, incl, ntake - 1);
+        pos += ntake;
+        if (ntake < 32) break;
       }
-      const bool take = in && (used + incl <= kCoRegionBytes);
-      const uint32_t tmask = __ballot_sync(0xffffffffu, take);
-      const int ntake = __popc(tmask);  // a prefix of the lanes (strides are positive)
-      if (take) {
-        const uint32_t off = (uint32_t)(used + incl - stride);
-        bulk_g2s(regA + off, ra, (uint32_t)stride, bar);
-        bulk_g2s(regB + off, rb, (uint32_t)stride, bar);
+      if (pw == 0 && lane == 0) {
+        meta[s].nbytes = used;
+        meta[s].bucket = pb;
       }
-      const int taken_bytes = __shfl_sync(0xffffffffu, incl, ntake > 0 ? ntake - 1 : 0);
-      if (ntake > 0) used += taken_bytes;
-      pos += ntake;
-      if (ntake < 32) break;
+      __syncwarp();
+      cp_async_mbar_arrive_noinc(bar);  // fires when this thread's copies have landed
+      mbar_arrive(bar);                 // orders the meta store; count = 2 per producer thread
     }
-    __syncwarp();
-    if (lane == 0) {
-      meta[s].nbytes = used;
-      meta[s].bucket = pb;
-      mbar_arrive_expect_tx(bar, 2u * (uint32_t)used);
-    }
-  };
+    return;
+  }
 
-  if (tid < 32)
-    for (int s = 0; s < kCoStages; ++s) produce(s);
-
+  // -------------------------------------------------------------- consumer warps
+  const uint32_t hist_s = smem_u32(hist), histJ_s = hist_s + 4u * T;
+  const uint32_t row4 = 4u * S1, plane4 = 4u * S1 * S1;
   int cur_bucket = -1;
   for (int k = 0;; ++k) {
     const int s = k % kCoStages;
-    mbar_wait(smem_u32(&bars[s]), (uint32_t)((k / kCoStages) & 1));
+    mbar_wait(smem_u32(&full_bar[s]), (uint32_t)((k / kCoStages) & 1));
     const int nbytes = meta[s].nbytes, bucket = meta[s].bucket;
     if (nbytes < 0) break;
     if (bucket != cur_bucket) {
-      // the end-of-stage barrier below already ordered all increments of the old bucket
       if (cur_bucket >= 0) {
-        co_flush<SMEM>(hist, S, counts + (size_t)cur_bucket * cells);
-        __syncthreads();
+        consumer_sync();  // all increments of the old bucket are done
+        co_flush<SMEM>(hist, S, tid, counts + (size_t)cur_bucket * cells);
+        consumer_sync();
       }
       cur_bucket = bucket;
     }
@@ -280,19 +352,19 @@ count_co_sorted_kernel(const uint8_t* __restrict__ msa, const cherry_fam_desc* _
     const uint8_t* regA = stage_base + (size_t)s * 2 * kCoRegionBytes;
     const uint8_t* regB = regA + kCoRegionBytes;
     const int n_items = nbytes >> 3;
-    for (int i = tid; i < n_items; i += kCoThreads) {
+    for (int i = tid; i < n_items; i += kCoConsumerWarps * 32) {
       const uint2 a = *reinterpret_cast<const uint2*>(regA + 8 * i);
       const uint2 b = *reinterpret_cast<const uint2*>(regB + 8 * i);
-      co_contact<SMEM>(a.x, b.x, S, S3, hist_s, counts_b);
-      co_contact<SMEM>(a.x >> 16, b.x >> 16, S, S3, hist_s, counts_b);
-      co_contact<SMEM>(a.y, b.y, S, S3, hist_s, counts_b);
-      co_contact<SMEM>(a.y >> 16, b.y >> 16, S, S3, hist_s, counts_b);
+      co_contact<SMEM>(a.x, b.x, S, row4, plane4, hist_s, histJ_s, counts_b);
+      co_contact<SMEM>(a.x >> 16, b.x >> 16, S, row4, plane4, hist_s, histJ_s, counts_b);
+      co_contact<SMEM>(a.y, b.y, S, row4, plane4, hist_s, histJ_s, counts_b);
+      co_contact<SMEM>(a.y >> 16, b.y >> 16, S, row4, plane4, hist_s, histJ_s, counts_b);
     }
-    __syncthreads();  // everyone is done with this stage's buffers and meta
-    if (tid < 32) produce(s);
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(smem_u32(&empty_bar[s]));  // this warp is done with the stage
   }
-  __syncthreads();
-  if (cur_bucket >= 0) co_flush<SMEM>(hist, S, counts + (size_t)cur_bucket * cells);
+  consumer_sync();
+  if (cur_bucket >= 0) co_flush<SMEM>(hist, S, tid, counts + (size_t)cur_bucket * cells);
 }
 
 }  // namespace
@@ -300,8 +372,12 @@ count_co_sorted_kernel(const uint8_t* __restrict__ msa, const cherry_fam_desc* _
 extern "C" {
 
 int cherry_sort_pairs_by_bucket(const uint8_t* tab, int r_pad, int64_t n_pairs, int K,
-                                int32_t* order, int32_t* ws, void* stream) {
+                                const cherry_fam_desc* fams, const int32_t* pair_a,
+                                const int32_t* pair_b, const int32_t* pair_fam, int32_t* order,
+                                cherry_co_rec* recs, int32_t* ws, void* stream) {
   if (!tab || !order || !ws) return cherry::fail(CHERRY_EINVAL, "sort_pairs_by_bucket: null pointer");
+  if (recs && (!fams || !pair_a || !pair_b || !pair_fam))
+    return cherry::fail(CHERRY_EINVAL, "sort_pairs_by_bucket: recs needs fams, pair_a, pair_b, pair_fam");
   if (K <= 0 || K > CHERRY_MAX_BUCKETS)
     return cherry::fail(CHERRY_ELIMIT, "sort_pairs_by_bucket: K=%d outside 1..%d", K, CHERRY_MAX_BUCKETS);
   if (r_pad <= 0 || n_pairs < 0 || n_pairs > 0x7fffffff)
@@ -316,20 +392,20 @@ int cherry_sort_pairs_by_bucket(const uint8_t* tab, int r_pad, int64_t n_pairs, 
   CHERRY_LAUNCH_CHECK("co_bucket_hist_kernel");
   co_bucket_scan_kernel<<<1, 1, 0, st>>>(K, ws);
   CHERRY_LAUNCH_CHECK("co_bucket_scan_kernel");
-  co_bucket_scatter_kernel<<<blocks, 256, 0, st>>>(tab, r_pad, n_pairs, K, ws, order);
+  co_bucket_scatter_kernel<<<blocks, 256, 0, st>>>(tab, r_pad, n_pairs, K, fams, pair_a, pair_b, pair_fam,
+                                                  ws, order, recs);
   CHERRY_LAUNCH_CHECK("co_bucket_scatter_kernel");
   return 0;
 }
 
-int cherry_count_co(const uint8_t* msa, const cherry_fam_desc* fams, const int32_t* pair_a,
-                    const int32_t* pair_b, const int32_t* pair_fam, const int32_t* order,
-                    const int32_t* bucket_start, int64_t n_pairs, int max_row_stride, int K, int S,
-                    uint32_t* counts, void* stream) {
-  if (!msa || !fams || !pair_a || !pair_b || !pair_fam || !order || !bucket_start || !counts)
+int cherry_count_co(const uint8_t* msa, const cherry_co_rec* recs, const int32_t* bucket_start,
+                    int64_t n_pairs, int max_row_stride, int K, int S, uint32_t* counts,
+                    void* stream) {
+  if (!msa || !recs || !bucket_start || !counts)
     return cherry::fail(CHERRY_EINVAL, "count_co: null pointer argument");
   if (K <= 0 || K > CHERRY_MAX_BUCKETS)
     return cherry::fail(CHERRY_ELIMIT, "count_co: K=%d outside 1..%d", K, CHERRY_MAX_BUCKETS);
-  if (S <= 0 || S > 64) return cherry::fail(CHERRY_ELIMIT, "count_co: S=%d outside 1..64", S);
+  if (S <= 0 || S > 62) return cherry::fail(CHERRY_ELIMIT, "count_co: S=%d outside 1..62", S);
   if (max_row_stride <= 0 || max_row_stride % 16 != 0)
     return cherry::fail(CHERRY_EINVAL, "count_co: max_row_stride must be a positive multiple of 16");
   if (max_row_stride > kCoRegionBytes)
@@ -337,7 +413,7 @@ int cherry_count_co(const uint8_t* msa, const cherry_fam_desc* fams, const int32
                         max_row_stride, max_row_stride / 2, kCoRegionBytes);
   if (n_pairs == 0) return 0;
   const size_t stage_bytes = (size_t)kCoStages * 2 * kCoRegionBytes;
-  const size_t hist_bytes = 2 * (size_t)S * S * S * sizeof(uint32_t);
+  const size_t hist_bytes = 2 * (size_t)(S + 1) * (S + 1) * (S + 1) * sizeof(uint32_t);
   const bool smem_hist = stage_bytes + hist_bytes + 4096 <= (size_t)kCoSmemLimit;
   const size_t dyn = stage_bytes + (smem_hist ? hist_bytes : 0);
   static bool attr_set[64] = {false};
@@ -353,10 +429,10 @@ int cherry_count_co(const uint8_t* msa, const cherry_fam_desc* fams, const int32
   const int grid = cherry::sm_count();
   if (smem_hist)
     count_co_sorted_kernel<true><<<grid, kCoThreads, dyn, (cudaStream_t)stream>>>(
-        msa, fams, pair_a, pair_b, pair_fam, order, bucket_start, K, S, counts);
+        msa, recs, bucket_start, K, S, counts);
   else
     count_co_sorted_kernel<false><<<grid, kCoThreads, dyn, (cudaStream_t)stream>>>(
-        msa, fams, pair_a, pair_b, pair_fam, order, bucket_start, K, S, counts);
+        msa, recs, bucket_start, K, S, counts);
   CHERRY_LAUNCH_CHECK("count_co_sorted_kernel");
   return 0;
 }

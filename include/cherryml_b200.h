@@ -98,27 +98,37 @@ int cherry_count_lg(const uint8_t* msa, const cherry_fam_desc* fams, const int32
                     const uint16_t* group_cat, const cherry_tile* tiles, int n_tiles, int K,
                     int S, unsigned long long* counts, void* stream);
 
+/* One sorted pair as the co-transition kernel's producer reads it.  16 bytes. */
+typedef struct cherry_co_rec {
+  int64_t off_a;     /* byte offset of the pair's row a in the residue buffer */
+  int32_t delta_b16; /* (offset of row b - offset of row a) / 16 */
+  int32_t stride;    /* bytes per row */
+} cherry_co_rec;
+
 /* Counting sort of the pairs by their bucket tab[p * r_pad] (co-transitions: one bucket per
  * pair).  order: int32 [n_pairs] (out) = pair indices grouped by bucket, ascending bucket.
+ * recs: [n_pairs] (out, may be NULL) = the row addresses of order[]'s pairs, resolved here
+ * through pair_fam / fams / pair_a / pair_b.
  * ws: int32 [2 * (K + 2)] (out / scratch): ws[b] = first position of bucket b in order[],
  * ws[K] = number of pairs inside the grid (the pairs outside it follow), ws[K + 1] = n_pairs.
  * The order inside a bucket is unspecified (the counts do not depend on it). */
 int cherry_sort_pairs_by_bucket(const uint8_t* tab, int r_pad, int64_t n_pairs, int K,
-                                int32_t* order, int32_t* ws, void* stream);
+                                const cherry_fam_desc* fams, const int32_t* pair_a,
+                                const int32_t* pair_b, const int32_t* pair_fam, int32_t* order,
+                                cherry_co_rec* recs, int32_t* ws, void* stream);
 
 /* counts[b][S*xi+xj][S*yi+yj] += 1 for every (pair, contact c) with b = the pair's bucket,
- * (xi, xj) = bytes (2c, 2c+1) of row pair_a and (yi, yj) = the same bytes of row pair_b:
- * rows of a co-transition batch are CONTACT-PAIRED (bytes 2c, 2c+1 = residues at the two
- * sites of the family's c-th contacting pair, padded with the skip code S to row_stride).
- * order / bucket_start: outputs of cherry_sort_pairs_by_bucket (bucket_start = ws).
- * max_row_stride: upper bound of fams[].row_stride over the batch (<= 20480).
+ * (xi, xj) = bytes (2c, 2c+1) of row a and (yi, yj) = the same bytes of row b: rows of a
+ * co-transition batch are CONTACT-PAIRED (bytes 2c, 2c+1 = residues at the two sites of
+ * the family's c-th contacting pair, padded with the skip code S to row_stride).
+ * recs / bucket_start: outputs of cherry_sort_pairs_by_bucket (bucket_start = ws).
+ * max_row_stride: upper bound of the row strides in the batch (<= 16384).
  * counts: uint32 [K][S*S][S*S], accumulated into; the caller keeps (pairs x contacts) per
  * call below 2^32 so that no cell can wrap.
  * Replaces the per-contact loop of counting/_count_co_transitions.cpp:358-383, 469-531. */
-int cherry_count_co(const uint8_t* msa, const cherry_fam_desc* fams, const int32_t* pair_a,
-                    const int32_t* pair_b, const int32_t* pair_fam, const int32_t* order,
-                    const int32_t* bucket_start, int64_t n_pairs, int max_row_stride, int K,
-                    int S, uint32_t* counts, void* stream);
+int cherry_count_co(const uint8_t* msa, const cherry_co_rec* recs, const int32_t* bucket_start,
+                    int64_t n_pairs, int max_row_stride, int K, int S, uint32_t* counts,
+                    void* stream);
 
 /* Per-site counting (SiteRM): counts[l][b][x][y] += 1 for every cherry c and site l, where
  * b = bucket of t[c] on `grid` (B ascending points), x = xa[c*row_stride + l], y = xb[...];

@@ -20,18 +20,19 @@ dev = as_device_batch(synthetic_co(fams, 1024, 300, seed=11, device=device), dev
 tab = build_bucket_table(dev, gd, K)
 lib = _lib.load()
 order = torch.empty(dev.n_pairs, dtype=torch.int32, device=device)
+recs = torch.empty(dev.n_pairs * 16, dtype=torch.uint8, device=device)
 ws = torch.empty(2 * (K + 2), dtype=torch.int32, device=device)
 raw = torch.zeros((K, 400, 400), dtype=torch.int32, device=device)
 st = _lib.current_stream_ptr()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 for it in range(reps + 1):
     ev[0].record()
-    _lib.check(lib.cherry_sort_pairs_by_bucket(_lib.ptr(tab), dev.r_pad, dev.n_pairs, K, _lib.ptr(order),
-                                               _lib.ptr(ws), st), "sort")
+    _lib.check(lib.cherry_sort_pairs_by_bucket(_lib.ptr(tab), dev.r_pad, dev.n_pairs, K, _lib.ptr(dev.fams),
+                                               _lib.ptr(dev.pair_a), _lib.ptr(dev.pair_b), _lib.ptr(dev.pair_fam),
+                                               _lib.ptr(order), _lib.ptr(recs), _lib.ptr(ws), st), "sort")
     ev[1].record()
-    _lib.check(lib.cherry_count_co(_lib.ptr(dev.msa), _lib.ptr(dev.fams), _lib.ptr(dev.pair_a),
-                                   _lib.ptr(dev.pair_b), _lib.ptr(dev.pair_fam), _lib.ptr(order), _lib.ptr(ws),
-                                   dev.n_pairs, dev.max_row_stride, K, 20, _lib.ptr(raw), st), "count")
+    _lib.check(lib.cherry_count_co(_lib.ptr(dev.msa), _lib.ptr(recs), _lib.ptr(ws), dev.n_pairs,
+                                   dev.max_row_stride, K, 20, _lib.ptr(raw), st), "count")
     ev[2].record()
     torch.cuda.synchronize()
     if it == 0:

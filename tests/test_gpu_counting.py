@@ -189,8 +189,9 @@ def test_sort_pairs_by_bucket():
         tab_d = torch.from_numpy(tab).cuda()
         order = torch.empty(n_pairs, dtype=torch.int32, device="cuda")
         ws = torch.empty(2 * (K + 2), dtype=torch.int32, device="cuda")
-        rc = _lib.load().cherry_sort_pairs_by_bucket(_lib.ptr(tab_d), r_pad, n_pairs, K, _lib.ptr(order),
-                                                     _lib.ptr(ws), _lib.current_stream_ptr())
+        rc = _lib.load().cherry_sort_pairs_by_bucket(_lib.ptr(tab_d), r_pad, n_pairs, K, 0, 0, 0, 0,
+                                                     _lib.ptr(order), 0, _lib.ptr(ws),
+                                                     _lib.current_stream_ptr())
         _lib.check(rc, "sort")
         order, ws = order.cpu().numpy(), ws.cpu().numpy()
         b = np.minimum(tab[:, 0].astype(np.int64), K)
@@ -228,7 +229,7 @@ def test_co_row_longer_than_a_stage_is_an_error():
     from cherryml_b200.counting._ingest import _BatchBuilder, contact_paired_rows
 
     builder = _BatchBuilder("co")
-    P = 11000  # 22000 bytes per row > 20480
+    P = 9000  # 18000 bytes per row > 16384
     contacts = np.zeros((P, 2), dtype=np.int32)
     rows = contact_paired_rows(np.zeros((2, 4), dtype=np.uint8), contacts, 20)
     builder.add_family("f", rows, np.array([0]), np.array([1]), np.array([0.5]), np.ones(1), contacts, P, P)
