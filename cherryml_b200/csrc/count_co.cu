@@ -27,11 +27,13 @@
 namespace {
 
 constexpr int kCoConsumerWarps = 24;
-constexpr int kCoProducerWarps = 2;
+constexpr int kCoProducerWarps = 4;
 constexpr int kCoThreads = (kCoConsumerWarps + kCoProducerWarps) * 32;
-constexpr int kCoStages = 4;
-constexpr int kCoRegionBytes = 16 * 1024;   // per stage: this many bytes of a-rows and of b-rows
-constexpr int kCoMaxPairsPerStage = 32 * kCoProducerWarps;  // one warp pass per producer warp
+constexpr int kCoMaxStages = 8;
+constexpr int kCoMaxPairsPerStage = 64;     // two passes of a producer warp
+constexpr int kCoMaxRowBytes = 16 * 1024;   // longest supported row (8192 contacts per family)
+constexpr int kCoRegionTarget = 18 * 1024;  // aim for regions of about this size ...
+constexpr int kCoStageBudget = 144 * 1024;  // ... within this much shared memory for all stages
 constexpr int kCoSmemLimit = 227 * 1024;
 
 // ------------------------------------------------------------------ counting sort by bucket
@@ -125,16 +127,19 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Spinning warps would take issue slots from the counting warps: back off between polls.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
 // 16-byte asynchronous copy global -> shared (LDGSTS), bypassing L1.
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -150,35 +155,51 @@ __device__ __forceinline__ void consumer_sync() {  // named barrier 1: the consu
 }
 
 struct CoStageMeta {
-  int nbytes;  // bytes per region in this stage; -1 = no more work
-  int bucket;
+  int nbytes;        // bytes per region in this stage
+  int n_pairs;       // pairs in this stage
+  int bucket_first;  // bucket of the first / last pair (equal in all but ~K stages of a launch)
+  int bucket_last;
 };
 
-// One (pair, contact): (xi, xj) = bytes (0, 1) of ha, (yi, yj) = bytes (0, 1) of hb (the upper
-// halves are ignored).  The shared histogram has S1 = S+1 states per axis, so a skip byte
-// (== S) on a near-diagonal item lands in a junk cell that the flush drops -- no validity
-// test on the hot path; only the rare both-sites-changed items test it before their L2
-// reduction.  I at hist, J at hist + 4*S1^3; row4 = 4*S1, plane4 = 4*S1*S1.
+// Two (pair, contact) items = one 32-bit word of row a (bytes xi0 xj0 xi1 xj1) and the same
+// word of row b.  An item goes to the shared histogram when at most one site changed:
+// I[xi][yi][xj] (site j unchanged) at hist, J[xj][yj][xi] (site i unchanged) at hist + 4*S1^3.
+// The shared histogram has S1 = S+1 states per axis and those two cells name all four bytes
+// (the unchanged site's byte stands for both rows), so an item with a skip byte lands in a
+// junk cell that the flush drops: no validity test on the hot path.  Items with BOTH sites
+// changed are tested; the valid ones (6 % on Pfam-like data) set their bit in the returned
+// mask and are handled after the fast path of the whole 8-byte item, once.
+//   vmask = (0x80 - S) * 0x01010101: (byte + 0x80 - S) has bit 7 set iff byte == S.
 template <bool SMEM>
-__device__ __forceinline__ void co_contact(uint32_t ha, uint32_t hb, uint32_t S, uint32_t row4,
-                                           uint32_t plane4, uint32_t hist, uint32_t histJ,
-                                           uint32_t* __restrict__ counts_b) {
-  const uint32_t d = ha ^ hb;
-  const bool eqi = (d & 0x00ffu) == 0, eqj = (d & 0xff00u) == 0;
-  if (SMEM && (eqi || eqj)) {
-    // eqj: I[xi][yi][xj] -> (p, q, r) = (a0, b0, a1);  else J[xj][yj][xi] -> (a1, b1, a0)
-    const uint32_t w = __byte_perm(ha, hb, eqj ? 0x4041u : 0x4150u);  // bytes: r, q, p, (unused)
-    const uint32_t lo = __dp4a(w, 0x00000004u | (row4 << 8), eqj ? hist : histJ);  // 4r + row4*q + base
-    const uint32_t addr = __byte_perm(w, 0, 0x4442u) * plane4 + lo;
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
-  } else {
-    const uint32_t xi = ha & 0xffu, xj = (ha >> 8) & 0xffu;
-    const uint32_t yi = hb & 0xffu, yj = (hb >> 8) & 0xffu;
-    if (xi < S && xj < S && yi < S && yj < S) {
-      const uint32_t n = S * S;
-      atomicAdd(counts_b + (size_t)(xi * S + xj) * n + (yi * S + yj), 1u);
+__device__ __forceinline__ uint32_t co_word(uint32_t wa, uint32_t wb, uint32_t vmask, uint32_t coef,
+                                            uint32_t plane4, uint32_t hist, uint32_t histJ) {
+  const uint32_t d = wa ^ wb;
+  const uint32_t v = ((wa + vmask) | (wb + vmask)) & 0x80808080u;
+  uint32_t slow = 0;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const uint32_t m_i = 0xffu << (16 * c), m_j = 0xff00u << (16 * c), m_c = 0xffffu << (16 * c);
+    const bool eqj = (d & m_j) == 0;
+    const bool near = eqj || (d & m_i) == 0;
+    if (SMEM && near) {
+      // eqj: (p, q, r) = (xi, yi, xj);  else (xj, yj, xi);  PRMT nibble n selects byte n of {wa, wb}
+      const uint32_t sel = c == 0 ? (eqj ? 0x4041u : 0x4150u) : (eqj ? 0x4263u : 0x4372u);
+      const uint32_t w = __byte_perm(wa, wb, sel);                      // bytes: r, q, p, (unused)
+      const uint32_t lo = __dp4a(w, coef, eqj ? hist : histJ);          // 4r + 4*S1*q + base
+      const uint32_t addr = __byte_perm(w, 0, 0x4442u) * plane4 + lo;   // + 4*S1*S1*p
+      asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+    } else if ((v & m_c) == 0) {  // both sites changed (or no shared histogram) and all four valid
+      slow |= 1u << c;
     }
   }
+  return slow;
+}
+
+// Both sites changed: one L2 reduction.  h = 16-bit halves (xi | xj << 8), (yi | yj << 8).
+__device__ __forceinline__ void co_slow(uint32_t ha, uint32_t hb, uint32_t S, uint32_t* __restrict__ counts_b) {
+  const uint32_t xi = ha & 0xffu, xj = (ha >> 8) & 0xffu;
+  const uint32_t yi = hb & 0xffu, yj = (hb >> 8) & 0xffu;
+  atomicAdd(counts_b + (size_t)(xi * S + xj) * (S * S) + (yi * S + yj), 1u);
 }
 
 template <bool SMEM>
@@ -201,37 +222,61 @@ __device__ __forceinline__ void co_flush(uint32_t* hist, int S, int tid, uint32_
   }
 }
 
-// Persistent, warp-specialised: CTA c owns the sorted pairs [c*n_valid/G, (c+1)*n_valid/G).
-// The last two warps are producers: they walk the range, pack up to 64 pairs of ONE bucket
-// into a stage (a-rows back to back in region A, b-rows at the same offsets in region B)
-// with 16-byte cp.async copies, and publish {bytes, bucket}; full/empty mbarriers decouple
-// them from the consumer warps by kCoStages stages.  (v2 used one cp.async.bulk per row: a
-// 304-byte bulk copy per lane serialises in the uniform datapath, 7 us per 39 KB stage.)  Consumers: item = 8 bytes of region A + the
-// same 8 bytes of region B = 4 contacts; no per-item pair lookup is needed because the whole
-// stage has one bucket and padding bytes are skip codes.
+// A valid item of a pair whose bucket is not the one in shared memory (only in the ~K stages
+// of a launch that straddle a bucket boundary), or any valid item when there is no shared
+// histogram: straight to L2.
+__device__ __forceinline__ void co_direct(uint32_t ha, uint32_t hb, uint32_t S, uint32_t* __restrict__ counts_b) {
+  const uint32_t xi = ha & 0xffu, xj = (ha >> 8) & 0xffu;
+  const uint32_t yi = hb & 0xffu, yj = (hb >> 8) & 0xffu;
+  if (xi < S && xj < S && yi < S && yj < S)
+    atomicAdd(counts_b + (size_t)(xi * S + xj) * (S * S) + (yi * S + yj), 1u);
+}
+
+// Persistent, warp-specialised.  CTA c owns the sorted pairs [r0, r1) = [c*n_valid/grid,
+// (c+1)*n_valid/grid); stage k of the CTA is the G consecutive pairs starting at r0 + k*G
+// (G = pairs per stage <= 64, chosen by the host so that G rows of the longest family fit a
+// region).  Stage boundaries depend on nothing but k, so the kCoProducerWarps producer warps
+// work independently: warp w fills stages w, w + P, ...: one coalesced 16-byte record load
+// per lane and pass (= per pair), a warp scan of the row strides (rows are packed back to
+// back: a-rows in region A, b-rows at the same offsets in region B), then 16-byte cp.async
+// copies with a quad of lanes per pair (64 contiguous bytes of each row per step), handed
+// to the stage's mbarrier with cp.async.mbarrier.arrive.noinc.
+// Consumers see the CTA's stages as ONE stream of 256-byte chunks (32 items of 8 bytes of
+// region A + the same 8 bytes of region B = 4 contacts per lane); consumer warp w takes
+// chunks w, w + C, ... of that stream, walking from stage to stage on its own (wait full,
+// arrive empty), so no lane idles at a stage's end beyond its last partial chunk.  No
+// per-item pair lookup: a stage has one bucket and padding bytes are skip codes.  The ~K
+// stages of a launch that straddle a bucket boundary look the pair up per item and send
+// the items of the other buckets straight to L2.
+// History: v2 issued one cp.async.bulk per row -- a 304-byte bulk copy per lane serialises
+// in the uniform datapath (7 us per 39 KB stage); v3's two lock-step producer warps were
+// bound by their own dependent-issue latency; v4 split every stage over all consumer
+// threads (1.6 items per thread and stage: rounding up idled a fifth of the lanes).
 template <bool SMEM>
 __global__ void __launch_bounds__(kCoThreads, 1)
 count_co_sorted_kernel(const uint8_t* __restrict__ msa, const cherry_co_rec* __restrict__ recs,
-                       const int32_t* __restrict__ bucket_start, int K, int S,
-                       uint32_t* __restrict__ counts) {
+                       const int32_t* __restrict__ bucket_start, int K, int S, int G, int n_stages,
+                       int n_producers, int region_bytes, uint32_t* __restrict__ counts) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) unsigned long long full_bar[kCoStages];
-  __shared__ __align__(8) unsigned long long empty_bar[kCoStages];
-  __shared__ CoStageMeta meta[kCoStages];
+  __shared__ __align__(8) unsigned long long full_bar[kCoMaxStages];
+  __shared__ __align__(8) unsigned long long empty_bar[kCoMaxStages];
+  __shared__ CoStageMeta meta[kCoMaxStages];
+  __shared__ int pair_end[kCoMaxStages][kCoMaxPairsPerStage];  // inclusive prefix of the row strides
+  __shared__ int pair_bucket[kCoMaxStages][kCoMaxPairsPerStage];
   __shared__ int sbstart[CHERRY_MAX_BUCKETS + 2];
 
   const int tid = threadIdx.x;
   const int S1 = S + 1, T = S1 * S1 * S1;
   const size_t cells = (size_t)S * S * S * S;
-  uint8_t* stage_base = smem;  // kCoStages * 2 * kCoRegionBytes
-  uint32_t* hist = reinterpret_cast<uint32_t*>(smem + (size_t)kCoStages * 2 * kCoRegionBytes);
+  uint8_t* stage_base = smem;  // n_stages * 2 * region_bytes
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem + (size_t)n_stages * 2 * region_bytes);
 
   for (int i = tid; i <= K + 1; i += kCoThreads) sbstart[i] = bucket_start[i];
   if (SMEM)
     for (int i = tid; i < 2 * T; i += kCoThreads) hist[i] = 0;
   if (tid == 0) {
-    for (int s = 0; s < kCoStages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 2 * kCoProducerWarps * 32);
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 2 * 32);  // one producer warp, two arrivals per thread
       mbar_init(smem_u32(&empty_bar[s]), kCoConsumerWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -241,127 +286,158 @@ count_co_sorted_kernel(const uint8_t* __restrict__ msa, const cherry_co_rec* __r
   const int64_t n_valid = sbstart[K];
   const int r0 = (int)(n_valid * blockIdx.x / gridDim.x);
   const int r1 = (int)(n_valid * (blockIdx.x + 1) / gridDim.x);
+  const int n_k = (r1 - r0 + G - 1) / G;
+  const int lane = tid & 31;
 
   if (tid >= kCoConsumerWarps * 32) {
     // ------------------------------------------------------------ producer warps
-    // Both producer warps walk the range in lockstep (same loads, same scan, no
-    // communication); warp w issues the copies of pass w of every stage.  Copies are
-    // 16-byte cp.async (LDGSTS), one warp instruction per 512 bytes of a row; each thread
-    // then hands its copies to the stage's mbarrier (cp.async.mbarrier.arrive.noinc).
-    const int lane = tid & 31, pw = (tid >> 5) - kCoConsumerWarps;
-    int pos = r0, pb = 0;
-    for (int k = 0;; ++k) {
-      const int s = k % kCoStages;
-      if (k >= kCoStages) mbar_wait(smem_u32(&empty_bar[s]), (uint32_t)(((k / kCoStages) - 1) & 1));
-      const uint32_t bar = smem_u32(&full_bar[s]);
-      if (pos >= r1) {
-        if (pw == 0 && lane == 0) {
-          meta[s].nbytes = -1;
-          meta[s].bucket = -1;
+    const int pw = (tid >> 5) - kCoConsumerWarps;
+    if (pw >= n_producers) return;
+    const int q = lane >> 2, c0 = (lane & 3) * 16;
+    int pb = 0;
+    // n_producers <= n_stages: the producer of stage k has waited for stage k - P - n_stages
+    // to be consumed, which then implies stage k - 2*n_stages was -- an mbarrier parity wait
+    // is only meaningful when the waiter is less than two phases ahead.
+    for (int k = pw; k < n_k; k += n_producers) {
+      const int s = k % n_stages;
+      const int pos = r0 + k * G;
+      const int n = min(G, r1 - pos);
+      // this stage's records first (the empty-slot wait below then overlaps the loads) ...
+      int stride[2] = {0, 0}, delta16[2] = {0, 0}, incl[2], lb[2];
+      const uint8_t* ra[2] = {msa, msa};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (32 * h + lane < n) {
+          const int4 rec = __ldg(reinterpret_cast<const int4*>(recs) + pos + 32 * h + lane);
+          ra[h] = msa + (((int64_t)(uint32_t)rec.y << 32) | (uint32_t)rec.x);
+          delta16[h] = rec.z;
+          stride[h] = rec.w;
         }
-        __syncwarp();
-        mbar_arrive(bar);  // two arrivals per producer thread and stage, as below
-        mbar_arrive(bar);
-        break;
       }
-      while (sbstart[pb + 1] <= pos) ++pb;  // bucket of position pos
-      const int limit = min(r1, sbstart[pb + 1]);
-      const uint32_t regA = smem_u32(stage_base + (size_t)s * 2 * kCoRegionBytes);
-      const uint32_t regB = regA + kCoRegionBytes;
-      if (pos + kCoMaxPairsPerStage + lane < r1)  // next stage's records: into L2 now
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(recs + pos + kCoMaxPairsPerStage + lane));
-      int used = 0;
-#pragma unroll 1
-      for (int pass = 0; pass < kCoProducerWarps; ++pass) {
-        const int idx = pos + lane;
-        const bool in = idx < limit;
-        int stride = 0;
-        const uint8_t* ra = msa;
-        int delta16 = 0;
-        if (in) {
-          const int4 rec = __ldg(reinterpret_cast<const int4*>(recs) + idx);
-          ra = msa + (((int64_t)(uint32_t)rec.y << 32) | (uint32_t)rec.x);
-          delta16 = rec.z;
-          stride = rec.w;
-        }
-        int incl = stride;  // inclusive warp scan of the strides
+      // ... and the next one's into L2
+      if (pos + n_producers * G + 2 * lane < r1)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(recs + pos + n_producers * G + 2 * lane));
+      while (sbstart[pb + 1] <= pos) ++pb;  // bucket of the first pair
+      int carry = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        lb[h] = pb;  // bucket of this lane's pair
+        if (32 * h + lane < n)
+          while (sbstart[lb[h] + 1] <= pos + 32 * h + lane) ++lb[h];
+        int v = stride[h];  // inclusive warp scan of the strides
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += v;
+          const int u = __shfl_up_sync(0xffffffffu, v, d);
+          if (lane >= d) v += u;
         }
-        const bool take = in && (used + incl <= kCoRegionBytes);
-        const int ntake = __popc(__ballot_sync(0xffffffffu, take));  // a prefix of the lanes
-        if (pass == pw) {
-          // a quad of lanes per pair: 64 contiguous bytes (two full sectors) of each row per
-          // step, 8 pairs per sub-step; the row addresses come from the lane holding the pair
-          const uint32_t off = (uint32_t)(used + incl - stride);
-          const int q = lane >> 2, c0 = (lane & 3) * 16;
+        incl[h] = carry + v;
+        carry = __shfl_sync(0xffffffffu, incl[h], 31);
+      }
+      const int used = carry;
+      const int last_bucket = __shfl_sync(0xffffffffu, n > 32 ? lb[1] : lb[0], (n - 1) & 31);
+      if (k >= n_stages) mbar_wait(smem_u32(&empty_bar[s]), (uint32_t)(((k / n_stages) - 1) & 1));
+      const uint32_t bar = smem_u32(&full_bar[s]);
+      const uint32_t regA = smem_u32(stage_base + (size_t)s * 2 * region_bytes);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t off = (uint32_t)(incl[h] - stride[h]);
+        const int nh = min(32, n - 32 * h);
 #pragma unroll 1
-          for (int g0 = 0; g0 < ntake; g0 += 8) {
-            const int g = g0 + q;
-            const uint64_t ga = __shfl_sync(0xffffffffu, (uint64_t)ra, g & 31);
-            const int gd = __shfl_sync(0xffffffffu, delta16, g & 31);
-            const int gs = __shfl_sync(0xffffffffu, stride, g & 31);
-            const uint32_t go = __shfl_sync(0xffffffffu, off, g & 31);
-            if (g < ntake) {
-              const uint8_t* pa = reinterpret_cast<const uint8_t*>(ga) + c0;
-              const uint8_t* pbrow = pa + (int64_t)gd * 16;
-              uint32_t da = regA + go + c0;
-              for (int c = c0; c < gs; c += 64) {
-                cp_async16(da, pa);
-                cp_async16(da + kCoRegionBytes, pbrow);
-                da += 64; pa += 64; pbrow += 64;
-              }
+        for (int g0 = 0; g0 < nh; g0 += 8) {
+          const int g = g0 + q;
+          const uint64_t ga = __shfl_sync(0xffffffffu, (uint64_t)ra[h], g & 31);
+          const int gd = __shfl_sync(0xffffffffu, delta16[h], g & 31);
+          const int gs = __shfl_sync(0xffffffffu, stride[h], g & 31);
+          const uint32_t go = __shfl_sync(0xffffffffu, off, g & 31);
+          if (g < nh) {
+            const uint8_t* pa = reinterpret_cast<const uint8_t*>(ga) + c0;
+            const uint8_t* pbrow = pa + (int64_t)gd * 16;
+            uint32_t da = regA + go + c0;
+            for (int c = c0; c < gs; c += 64) {
+              cp_async16(da, pa);
+              cp_async16(da + region_bytes, pbrow);
+              da += 64; pa += 64; pbrow += 64;
             }
           }
         }
-        if (ntake > 0) used += __shfl_sync(0xffffffffu, incl, ntake - 1);
-        pos += ntake;
-        if (ntake < 32) break;
+        pair_end[s][32 * h + lane] = incl[h];
+        pair_bucket[s][32 * h + lane] = lb[h];
       }
-      if (pw == 0 && lane == 0) {
+      if (lane == 0) {
         meta[s].nbytes = used;
-        meta[s].bucket = pb;
+        meta[s].n_pairs = n;
+        meta[s].bucket_first = pb;
+        meta[s].bucket_last = last_bucket;
       }
       __syncwarp();
       cp_async_mbar_arrive_noinc(bar);  // fires when this thread's copies have landed
-      mbar_arrive(bar);                 // orders the meta store; count = 2 per producer thread
+      mbar_arrive(bar);                 // orders the meta stores
     }
     return;
   }
 
   // -------------------------------------------------------------- consumer warps
   const uint32_t hist_s = smem_u32(hist), histJ_s = hist_s + 4u * T;
-  const uint32_t row4 = 4u * S1, plane4 = 4u * S1 * S1;
+  const uint32_t plane4 = 4u * S1 * S1, coef = 0x00000004u | ((4u * S1) << 8);
+  const uint32_t vmask = (0x80u - (uint32_t)S) * 0x01010101u;
+  const int warp = tid >> 5;
   int cur_bucket = -1;
-  for (int k = 0;; ++k) {
-    const int s = k % kCoStages;
-    mbar_wait(smem_u32(&full_bar[s]), (uint32_t)((k / kCoStages) & 1));
-    const int nbytes = meta[s].nbytes, bucket = meta[s].bucket;
-    if (nbytes < 0) break;
-    if (bucket != cur_bucket) {
+  int c = warp;  // this warp's next chunk, relative to the first chunk of stage k
+  for (int k = 0; k < n_k; ++k) {
+    const int s = k % n_stages;
+    mbar_wait(smem_u32(&full_bar[s]), (uint32_t)((k / n_stages) & 1));
+    const CoStageMeta m = meta[s];
+    if (m.bucket_first != cur_bucket) {
+      // every consumer warp walks every stage in order, so they all get here for stage k
       if (cur_bucket >= 0) {
         consumer_sync();  // all increments of the old bucket are done
         co_flush<SMEM>(hist, S, tid, counts + (size_t)cur_bucket * cells);
         consumer_sync();
       }
-      cur_bucket = bucket;
+      cur_bucket = m.bucket_first;
     }
-    uint32_t* __restrict__ counts_b = counts + (size_t)bucket * cells;
-    const uint8_t* regA = stage_base + (size_t)s * 2 * kCoRegionBytes;
-    const uint8_t* regB = regA + kCoRegionBytes;
-    const int n_items = nbytes >> 3;
-    for (int i = tid; i < n_items; i += kCoConsumerWarps * 32) {
+    const int n_items = m.nbytes >> 3, n_chunks = (n_items + 31) >> 5;
+    const uint8_t* regA = stage_base + (size_t)s * 2 * region_bytes;
+    const uint8_t* regB = regA + region_bytes;
+    uint32_t* __restrict__ counts_b = counts + (size_t)cur_bucket * cells;
+    const bool mixed = m.bucket_first != m.bucket_last;
+    for (; c < n_chunks; c += kCoConsumerWarps) {
+      const int i = c * 32 + lane;
+      if (i >= n_items) continue;
       const uint2 a = *reinterpret_cast<const uint2*>(regA + 8 * i);
       const uint2 b = *reinterpret_cast<const uint2*>(regB + 8 * i);
-      co_contact<SMEM>(a.x, b.x, S, row4, plane4, hist_s, histJ_s, counts_b);
-      co_contact<SMEM>(a.x >> 16, b.x >> 16, S, row4, plane4, hist_s, histJ_s, counts_b);
-      co_contact<SMEM>(a.y, b.y, S, row4, plane4, hist_s, histJ_s, counts_b);
-      co_contact<SMEM>(a.y >> 16, b.y >> 16, S, row4, plane4, hist_s, histJ_s, counts_b);
+      if (SMEM && !mixed) {
+        uint32_t slow = co_word<SMEM>(a.x, b.x, vmask, coef, plane4, hist_s, histJ_s);
+        slow |= co_word<SMEM>(a.y, b.y, vmask, coef, plane4, hist_s, histJ_s) << 2;
+        if (slow) {
+          if (slow & 1u) co_slow(a.x, b.x, S, counts_b);
+          if (slow & 2u) co_slow(a.x >> 16, b.x >> 16, S, counts_b);
+          if (slow & 4u) co_slow(a.y, b.y, S, counts_b);
+          if (slow & 8u) co_slow(a.y >> 16, b.y >> 16, S, counts_b);
+        }
+      } else {
+        int g = 0;  // the pair this item belongs to: first g with pair_end[g] > 8*i
+        while (pair_end[s][g] <= 8 * i) ++g;
+        const int bucket = pair_bucket[s][g];
+        if (SMEM && bucket == cur_bucket) {
+          uint32_t slow = co_word<SMEM>(a.x, b.x, vmask, coef, plane4, hist_s, histJ_s);
+          slow |= co_word<SMEM>(a.y, b.y, vmask, coef, plane4, hist_s, histJ_s) << 2;
+          if (slow & 1u) co_slow(a.x, b.x, S, counts_b);
+          if (slow & 2u) co_slow(a.x >> 16, b.x >> 16, S, counts_b);
+          if (slow & 4u) co_slow(a.y, b.y, S, counts_b);
+          if (slow & 8u) co_slow(a.y >> 16, b.y >> 16, S, counts_b);
+        } else {
+          uint32_t* __restrict__ cb = counts + (size_t)bucket * cells;
+          co_direct(a.x, b.x, S, cb);
+          co_direct(a.x >> 16, b.x >> 16, S, cb);
+          co_direct(a.y, b.y, S, cb);
+          co_direct(a.y >> 16, b.y >> 16, S, cb);
+        }
+      }
     }
+    c -= n_chunks;
     __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(smem_u32(&empty_bar[s]));  // this warp is done with the stage
+    if (lane == 0) mbar_arrive(smem_u32(&empty_bar[s]));  // this warp is done with the stage
   }
   consumer_sync();
   if (cur_bucket >= 0) co_flush<SMEM>(hist, S, tid, counts + (size_t)cur_bucket * cells);
@@ -408,31 +484,40 @@ int cherry_count_co(const uint8_t* msa, const cherry_co_rec* recs, const int32_t
   if (S <= 0 || S > 62) return cherry::fail(CHERRY_ELIMIT, "count_co: S=%d outside 1..62", S);
   if (max_row_stride <= 0 || max_row_stride % 16 != 0)
     return cherry::fail(CHERRY_EINVAL, "count_co: max_row_stride must be a positive multiple of 16");
-  if (max_row_stride > kCoRegionBytes)
+  if (max_row_stride > kCoMaxRowBytes)
     return cherry::fail(CHERRY_ELIMIT, "count_co: a row of %d bytes (%d contacts) exceeds the %d-byte stage",
-                        max_row_stride, max_row_stride / 2, kCoRegionBytes);
+                        max_row_stride, max_row_stride / 2, kCoMaxRowBytes);
   if (n_pairs == 0) return 0;
-  const size_t stage_bytes = (size_t)kCoStages * 2 * kCoRegionBytes;
+  // G pairs per stage (one producer-warp pass), packed rows: a region holds G rows of the
+  // longest family; as many stages as fit the budget.
+  int G = kCoRegionTarget / max_row_stride;
+  if (G > kCoMaxPairsPerStage) G = kCoMaxPairsPerStage;
+  if (G < 1) G = 1;
+  const int region_bytes = G * max_row_stride;
+  int n_stages = kCoStageBudget / (2 * region_bytes);
+  if (n_stages > kCoMaxStages) n_stages = kCoMaxStages;
+  const int n_producers = n_stages < kCoProducerWarps ? n_stages : kCoProducerWarps;
+  const size_t stage_bytes = (size_t)n_stages * 2 * region_bytes;
   const size_t hist_bytes = 2 * (size_t)(S + 1) * (S + 1) * (S + 1) * sizeof(uint32_t);
-  const bool smem_hist = stage_bytes + hist_bytes + 4096 <= (size_t)kCoSmemLimit;
+  const bool smem_hist = stage_bytes + hist_bytes + 8192 <= (size_t)kCoSmemLimit;
   const size_t dyn = stage_bytes + (smem_hist ? hist_bytes : 0);
   static bool attr_set[64] = {false};
   int dev = 0;
   CHERRY_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
     CHERRY_CUDA(cudaFuncSetAttribute(count_co_sorted_kernel<true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kCoSmemLimit - 4096));
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kCoSmemLimit - 8192));
     CHERRY_CUDA(cudaFuncSetAttribute(count_co_sorted_kernel<false>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kCoSmemLimit - 4096));
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kCoSmemLimit - 8192));
     attr_set[dev] = true;
   }
   const int grid = cherry::sm_count();
   if (smem_hist)
     count_co_sorted_kernel<true><<<grid, kCoThreads, dyn, (cudaStream_t)stream>>>(
-        msa, recs, bucket_start, K, S, counts);
+        msa, recs, bucket_start, K, S, G, n_stages, n_producers, region_bytes, counts);
   else
     count_co_sorted_kernel<false><<<grid, kCoThreads, dyn, (cudaStream_t)stream>>>(
-        msa, recs, bucket_start, K, S, counts);
+        msa, recs, bucket_start, K, S, G, n_stages, n_producers, region_bytes, counts);
   CHERRY_LAUNCH_CHECK("count_co_sorted_kernel");
   return 0;
 }
