@@ -102,35 +102,55 @@ __device__ __forceinline__ void count_word_global(unsigned long long* h64, uint3
   }
 }
 
-// ---- shared-memory path: branch-free per site ----
-// One aligned 32-bit word = 4 sites of one rate category.  The shared histogram has S+1
-// states per axis: the skip code of a residue byte is S itself (gap, unknown letter,
-// padding; the encoder guarantees no byte exceeds S), so EVERY site does an unconditional
-// increment (which ptxas turns into ATOMS.POPC.INC) and the junk row/column is dropped at
-// flush time.  Per site: two byte extracts, two multiply-adds, one shared-memory
-// reduction; no branch, no validity test.
-// `sbase` = 32-bit shared address of the histogram; row4 = 4*(S+1), bucket4 = 4*(S+1)^2.
+// ---- shared-memory path: branch-free, predicated per site ----
+// One aligned 32-bit word = 4 sites of one rate category (one bucket).  Validity of the 8
+// residue bytes is ONE byte-parallel test: bytes are <= S (the skip code), so
+// (byte + 0x80 - S) has bit 7 set iff the byte is the skip code; a word whose bucket is
+// outside the grid gets all four bits set.  Per site: two IDP.4A (address = row base +
+// 4*S*x + 4*y straight from the packed words, coefficient bytes select the site), one
+// select, one shared-memory reduction (ATOMS.POPC.INC).  Skipped sites (a quarter of the
+// lanes on Pfam-like data) all hit one junk word after the histogram, where they merge into
+// a single access: fewer bank conflicts per instruction than v2's (S+1)-state junk rows and
+// columns (3.4 -> ~2.9 wavefronts), which is the kernel's limiter.
+// `sbase` = 32-bit shared address of the histogram [K][S][S]; bucket4 = 4*S*S;
+// junk = sbase + 4*K*S*S.
+// DP4A needs 4*S <= 255; otherwise the address is built with PRMT + IMAD.
+struct LgCoef {
+  uint32_t a[4], b[4];  // a[k] = (4*S) << 8k, b[k] = 4 << 8k
+};
+
+template <bool DP4A>
 __device__ __forceinline__ void count_word_smem(uint32_t sbase, uint32_t wa, uint32_t wb,
                                                 uint32_t bucket, uint32_t row4, uint32_t bucket4,
-                                                uint32_t S4) {
-  if (bucket == CHERRY_NO_BUCKET) return;
+                                                uint32_t vm, uint32_t junk, const LgCoef& cf) {
+  uint32_t v = ((wa + vm) | (wb + vm)) & 0x80808080u;
+  if (bucket == CHERRY_NO_BUCKET) v = 0x80808080u;
   const uint32_t rowbase = sbase + bucket * bucket4;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const uint32_t x = __byte_perm(wa, 0, 0x4440 | k);
-    const uint32_t y = __byte_perm(wb, 0, 0x4440 | k);
-    const uint32_t addr = rowbase + x * row4 + y * 4u;
-    asm volatile("red.shared.add.u32 [%0], 1;" : : "r"(addr) : "memory");
+    uint32_t addr;
+    if (DP4A) {
+      addr = __dp4a(wb, cf.b[k], __dp4a(wa, cf.a[k], rowbase));
+    } else {
+      const uint32_t x = __byte_perm(wa, 0, 0x4440 | k);
+      const uint32_t y = __byte_perm(wb, 0, 0x4440 | k);
+      addr = rowbase + x * row4 + y * 4u;
+    }
+    // ATOMS.POPC.INC cannot be predicated (ptxas branches around it), so skipped sites are
+    // redirected to ONE junk word instead: equal addresses merge into a single access.
+    if (v & (0x80u << (8 * k))) addr = junk;
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
   }
 }
 
 // R4: the bucket-table row is exactly 4 bytes (<= 4 rate categories): one 32-bit load and a
 // byte select per word instead of four byte loads.
-template <bool SMEM, bool R4>
+template <bool SMEM, bool R4, bool DP4A>
 __device__ __forceinline__ void count_item(uint32_t sbase, unsigned long long* h64, const uint4& va,
                                            const uint4& vb, const uint2& g,
                                            const uint8_t* __restrict__ trow, int S, int SS,
-                                           uint32_t row4, uint32_t bucket4, uint32_t S4) {
+                                           uint32_t row4, uint32_t bucket4, uint32_t S4, uint32_t vm,
+                                           uint32_t junk, const LgCoef& cf) {
   uint32_t b0, b1, b2, b3;
   if (R4) {
     const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(trow));
@@ -145,10 +165,10 @@ __device__ __forceinline__ void count_item(uint32_t sbase, unsigned long long* h
     b3 = __ldg(trow + (g.y >> 16));
   }
   if (SMEM) {
-    count_word_smem(sbase, va.x, vb.x, b0, row4, bucket4, S4);
-    count_word_smem(sbase, va.y, vb.y, b1, row4, bucket4, S4);
-    count_word_smem(sbase, va.z, vb.z, b2, row4, bucket4, S4);
-    count_word_smem(sbase, va.w, vb.w, b3, row4, bucket4, S4);
+    count_word_smem<DP4A>(sbase, va.x, vb.x, b0, row4, bucket4, vm, junk, cf);
+    count_word_smem<DP4A>(sbase, va.y, vb.y, b1, row4, bucket4, vm, junk, cf);
+    count_word_smem<DP4A>(sbase, va.z, vb.z, b2, row4, bucket4, vm, junk, cf);
+    count_word_smem<DP4A>(sbase, va.w, vb.w, b3, row4, bucket4, vm, junk, cf);
   } else {
     count_word_global(h64, va.x, vb.x, b0, S, SS, S4);
     count_word_global(h64, va.y, vb.y, b1, S, SS, S4);
@@ -163,7 +183,7 @@ __device__ __forceinline__ void count_item(uint32_t sbase, unsigned long long* h
 // items and advances them incrementally (no division in the loop).  SMEM=true: the whole
 // [K][S][S] histogram lives in shared memory as uint32 and is flushed once; SMEM=false
 // (histogram too large): global uint64 atomics.
-template <bool SMEM, bool R4>
+template <bool SMEM, bool R4, bool DP4A>
 __global__ void __launch_bounds__(kCountThreads, 1)
 count_lg_kernel(const uint8_t* __restrict__ msa, const cherry_fam_desc* __restrict__ fams,
                 const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b,
@@ -172,14 +192,22 @@ count_lg_kernel(const uint8_t* __restrict__ msa, const cherry_fam_desc* __restri
                 int n_tiles, int K, int S, unsigned long long* __restrict__ counts) {
   extern __shared__ uint32_t hist[];
   const int SS = S * S;
-  const int S1 = S + 1;
-  const int nbins = K * S1 * S1;  // shared histogram: S+1 states per axis (state S = skip)
+  const int nbins = K * SS;
   const int tid = threadIdx.x;
   const uint32_t S4 = (uint32_t)S * 0x01010101u;
-  const uint32_t row4 = 4u * S1, bucket4 = 4u * S1 * S1;
-  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(hist);
+  const uint32_t row4 = 4u * S, bucket4 = 4u * SS;
+  const uint32_t vm = (0x80u - (uint32_t)S) * 0x01010101u;  // S <= 127 on this path
+  LgCoef cf;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    cf.a[k] = (row4 & 0xffu) << (8 * k);
+    cf.b[k] = 4u << (8 * k);
+  }
+  uint32_t sbase = (uint32_t)__cvta_generic_to_shared(hist);
+  asm volatile("" : "+r"(sbase));  // keep it in a register (ptxas re-derives it per use otherwise)
+  const uint32_t junk = sbase + 4u * (uint32_t)nbins;
   if (SMEM) {
-    for (int i = tid; i < nbins; i += kCountThreads) hist[i] = 0;
+    for (int i = tid; i <= nbins; i += kCountThreads) hist[i] = 0;
     __syncthreads();
   }
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -206,9 +234,11 @@ count_lg_kernel(const uint8_t* __restrict__ msa, const cherry_fam_desc* __restri
       uint4 vb1 = ld_stream16(base + b1 * stride + c1 * 16);
       uint2 g0 = __ldg(reinterpret_cast<const uint2*>(gc + ch0 * 4));
       uint2 g1 = __ldg(reinterpret_cast<const uint2*>(gc + c1 * 4));
-      count_item<SMEM, R4>(sbase, counts, va0, vb0, g0, tab + (int64_t)p0 * r_pad, S, SS, row4, bucket4, S4);
+      count_item<SMEM, R4, DP4A>(sbase, counts, va0, vb0, g0, tab + (int64_t)p0 * r_pad, S, SS, row4, bucket4,
+                                 S4, vm, junk, cf);
       if (has1)
-        count_item<SMEM, R4>(sbase, counts, va1, vb1, g1, tab + (int64_t)p1 * r_pad, S, SS, row4, bucket4, S4);
+        count_item<SMEM, R4, DP4A>(sbase, counts, va1, vb1, g1, tab + (int64_t)p1 * r_pad, S, SS, row4,
+                                   bucket4, S4, vm, junk, cf);
       pl0 += dq; ch0 += dr;
       if (ch0 >= nch) { ch0 -= nch; ++pl0; }
       pl1 += dq; ch1 += dr;
@@ -218,9 +248,7 @@ count_lg_kernel(const uint8_t* __restrict__ msa, const cherry_fam_desc* __restri
   if (SMEM) {
     __syncthreads();
     for (int i = tid; i < K * SS; i += kCountThreads) {
-      const int b = i / SS, r = i - b * SS;
-      const int x = r / S, y = r - x * S;
-      const uint32_t v = hist[(b * S1 + x) * S1 + y];
+      const uint32_t v = hist[i];
       if (v) atomicAdd(counts + i, (unsigned long long)v);
     }
   }
@@ -341,31 +369,37 @@ int cherry_count_lg(const uint8_t* msa, const cherry_fam_desc* fams, const int32
   if (rc) return rc;
   if (!group_cat) return cherry::fail(CHERRY_EINVAL, "count_lg: null group_cat");
   if (n_tiles == 0) return 0;
-  const size_t hist_bytes = (size_t)K * (S + 1) * (S + 1) * sizeof(uint32_t);
+  const size_t hist_bytes = ((size_t)K * S * S + 4) * sizeof(uint32_t);  // + the junk word
   int grid = cherry::sm_count();
   if (grid > n_tiles) grid = n_tiles;
   const bool r4 = (r_pad == 4);
-  if (hist_bytes <= (size_t)kMaxSmemBytes) {
+  cudaStream_t st = (cudaStream_t)stream;
+#define CHERRY_LG_LAUNCH(SM, R, D, SH)                                                          \
+  count_lg_kernel<SM, R, D><<<grid, kCountThreads, SH, st>>>(msa, fams, pair_a, pair_b, tab,    \
+                                                              r_pad, group_cat, tiles, n_tiles, K, S, counts)
+  if (hist_bytes <= (size_t)kMaxSmemBytes && S <= 127) {
     static bool attr_set[64] = {false};
     int dev = 0;
     CHERRY_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !attr_set[dev]) {
-      CHERRY_CUDA(cudaFuncSetAttribute(count_lg_kernel<true, true>,
+      CHERRY_CUDA(cudaFuncSetAttribute(count_lg_kernel<true, true, true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
-      CHERRY_CUDA(cudaFuncSetAttribute(count_lg_kernel<true, false>,
+      CHERRY_CUDA(cudaFuncSetAttribute(count_lg_kernel<true, false, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
+      CHERRY_CUDA(cudaFuncSetAttribute(count_lg_kernel<true, false, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
       attr_set[dev] = true;
     }
-    if (r4)
-      count_lg_kernel<true, true><<<grid, kCountThreads, hist_bytes, (cudaStream_t)stream>>>(
-          msa, fams, pair_a, pair_b, tab, r_pad, group_cat, tiles, n_tiles, K, S, counts);
+    if (4 * S > 255)
+      CHERRY_LG_LAUNCH(true, false, false, hist_bytes);
+    else if (r4)
+      CHERRY_LG_LAUNCH(true, true, true, hist_bytes);
     else
-      count_lg_kernel<true, false><<<grid, kCountThreads, hist_bytes, (cudaStream_t)stream>>>(
-          msa, fams, pair_a, pair_b, tab, r_pad, group_cat, tiles, n_tiles, K, S, counts);
+      CHERRY_LG_LAUNCH(true, false, true, hist_bytes);
   } else {
-    count_lg_kernel<false, false><<<grid, kCountThreads, 0, (cudaStream_t)stream>>>(
-        msa, fams, pair_a, pair_b, tab, r_pad, group_cat, tiles, n_tiles, K, S, counts);
+    CHERRY_LG_LAUNCH(false, false, false, 0);
   }
+#undef CHERRY_LG_LAUNCH
   CHERRY_LAUNCH_CHECK("count_lg_kernel");
   return 0;
 }
