@@ -334,6 +334,15 @@ def run_ours(args):
            "note": "cherry_count_lg_host: pinned host arrays -> segmented H2D overlapped with counting -> D2H"}
     del pinned
 
+    # ---- the fit (every rank takes part when N > 1: bucket-sharded co-evolution fit)
+    fit = None
+    if not args.no_fit:
+        from cherryml_b200.estimation import bench_fit
+
+        del dev, syn, host
+        torch.cuda.empty_cache()
+        fit = bench_fit(device, lg_times=grid, lg_counts=counts,
+                        process_group=dist.group.WORLD if world > 1 else None)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -364,13 +373,8 @@ def run_ours(args):
                    "transitions_counted_per_step_rank0": counted, "parity_slice_vs_oracle": parity},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
-    if not args.no_fit:
-        try:
-            from cherryml_b200.estimation import bench_fit
-
-            line["fit"] = bench_fit(device, lg_times=grid, lg_counts=counts)
-        except ImportError:
-            pass
+    if fit is not None:
+        line["fit"] = fit
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         cb = cpu_reference_run(args.cpu_families or max(32, 2 * cores))

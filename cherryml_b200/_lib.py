@@ -63,6 +63,8 @@ _SIGNATURES = {
     "cherry_fit_init": (c_int, [_P, _P]),
     "cherry_fit_run": (c_int, [_P, c_int, _P]),
     "cherry_fit_loss_grad": (c_int, [_P, _P]),
+    "cherry_fit_epoch_local": (c_int, [_P, _P, _P]),
+    "cherry_fit_epoch_update": (c_int, [_P, _P, _P]),
     "cherry_fit_schedule": (c_int, [_P, _P, _P, _P]),
     "cherry_expm_batched": (c_int, [_P, _P, _P]),
     "cherry_gemm_f64_batched": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),

@@ -27,9 +27,53 @@ int one_epoch(const cherry_fit_args& a, cudaStream_t stream) {
   return cherry::fit_large_update(a, 1, stream);
 }
 
+// packed[p][e] = sum_k dQ_part[p*K + k][e] (bucket order), packed[P*S*S + p] = sum_k loss_part.
+// For the large path dQ_part[0] already is the total over this rank's buckets.
+__global__ void fit_pack_partials_kernel(const double* __restrict__ dQ_part, const double* __restrict__ loss_part,
+                                         int SS, int K, int P, int dq_pieces, double* __restrict__ packed) {
+  const int p = blockIdx.y;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < SS; e += gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    const double* src = dQ_part + (size_t)p * dq_pieces * SS + e;
+    for (int k = 0; k < dq_pieces; ++k) acc += src[(size_t)k * SS];
+    packed[(size_t)p * SS + e] = acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double lp = 0.0;
+    for (int k = 0; k < K; ++k) lp += loss_part[(size_t)p * K + k];
+    packed[(size_t)P * SS + p] = lp;
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int cherry_fit_epoch_local(const cherry_fit_args* a, double* packed, void* stream_) {
+  int rc = check_args(a, false);
+  if (rc) return rc;
+  if (!packed) return cherry::fail(CHERRY_EINVAL, "fit_epoch_local: null packed buffer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool small = a->S <= cherry::kSmallFitMaxS;
+  if (!small && a->n_problems != 1)
+    return cherry::fail(CHERRY_EINVAL, "fit_epoch_local: the large path fits one problem");
+  rc = small ? cherry::fit_small_expm(*a, stream) : cherry::fit_large_expm(*a, stream);
+  if (rc) return rc;
+  const int SS = a->S * a->S;
+  dim3 grid((SS + 255) / 256 > 64 ? 64 : (SS + 255) / 256, a->n_problems);
+  fit_pack_partials_kernel<<<grid, 256, 0, stream>>>(a->dQ_part, a->loss_part, SS, a->K, a->n_problems,
+                                                      small ? a->K : 1, packed);
+  CHERRY_LAUNCH_CHECK("fit_pack_partials_kernel");
+  return 0;
+}
+
+int cherry_fit_epoch_update(const cherry_fit_args* a, const double* packed, void* stream) {
+  int rc = check_args(a, true);
+  if (rc) return rc;
+  if (!packed) return cherry::fail(CHERRY_EINVAL, "fit_epoch_update: null packed buffer");
+  if (a->S <= cherry::kSmallFitMaxS) return cherry::fit_small_update(*a, 1, (cudaStream_t)stream, packed);
+  return cherry::fit_large_update(*a, 1, (cudaStream_t)stream, packed);
+}
 
 int cherry_fit_workspace_bytes(int S, int K, int n_problems, size_t* bytes) {
   if (!bytes) return cherry::fail(CHERRY_EINVAL, "fit_workspace_bytes: null pointer");

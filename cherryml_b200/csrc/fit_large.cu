@@ -1261,7 +1261,7 @@ int fit_large_read_schedule(const cherry_fit_args& a, int* s_out, double* mu_out
   return 0;
 }
 
-int fit_large_update(const cherry_fit_args& a, int mode, cudaStream_t stream) {
+int fit_large_update(const cherry_fit_args& a, int mode, cudaStream_t stream, const double* reduced) {
   Plan p;
   int rc = check_large(a, p);
   if (rc) return rc;
@@ -1269,6 +1269,11 @@ int fit_large_update(const cherry_fit_args& a, int mode, cudaStream_t stream) {
   if (mode == 0 && (rc = fit_large_prepare(a, stream))) return rc;
   LargeUpdateArgs u;
   fill_update_args(u, a, p, base);
+  if (reduced) {  // gradient and loss already summed over the buckets of all ranks
+    u.K = 1;
+    u.G = reduced;
+    u.loss_part = reduced + (size_t)a.S * a.S;
+  }
   const size_t smem = sizeof(double) * a.S;
   if (mode == 1) {
     large_update_rows_kernel<<<a.S, EW_THREADS, smem, stream>>>(u);

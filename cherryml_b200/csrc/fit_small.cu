@@ -476,7 +476,7 @@ int fit_small_expm(const cherry_fit_args& a, cudaStream_t stream, double* P_out)
   return 0;
 }
 
-int fit_small_update(const cherry_fit_args& f, int mode, cudaStream_t stream) {
+int fit_small_update(const cherry_fit_args& f, int mode, cudaStream_t stream, const double* reduced) {
   UpdateArgs a;
   a.S = f.S; a.K = f.K; a.n_problems = f.n_problems; a.num_epochs_total = f.loss_trace_epochs;
   a.mask = f.mask; a.theta = f.theta; a.adam_m = f.adam_m; a.adam_v = f.adam_v; a.Q = f.Q;
@@ -486,6 +486,11 @@ int fit_small_update(const cherry_fit_args& f, int mode, cudaStream_t stream) {
   a.lr_pi = f.lr_pi; a.lr_upper = f.lr_upper; a.beta1 = f.beta1; a.beta2 = f.beta2; a.eps = f.eps;
   a.do_adam = f.do_adam; a.loss_normalization = f.loss_normalization; a.best_mode = f.best_mode;
   a.mode = mode;
+  if (reduced) {  // one pre-reduced piece per problem
+    a.K = 1;
+    a.dQ_part = reduced;
+    a.loss_part = reduced + (size_t)f.n_problems * f.S * f.S;
+  }
   const size_t smem = (size_t)(4 * f.S * f.S + 4 * f.S) * sizeof(double);
   fit_update_small<<<f.n_problems, kSmallThreads, smem, stream>>>(a);
   CHERRY_LAUNCH_CHECK("fit_update_small");

@@ -31,15 +31,26 @@ def measure_fp64_gemm_peak(device, n: int = 4096, reps: int = 5) -> float:
     return 2.0 * n**3 / (best * 1e-3) / 1e12
 
 
-def timed_fit(times, counts: torch.Tensor, num_epochs: int, mask=None) -> Dict:
-    """JTT-IPW initialisation + `num_epochs` Adam epochs + results back on the host."""
-    device = counts.device
+def _sync(device, process_group):
+    if process_group is not None:
+        import torch.distributed as dist
+
+        dist.barrier(group=process_group)
     torch.cuda.synchronize(device)
+
+
+def timed_fit(times, counts: torch.Tensor, num_epochs: int, mask=None, process_group=None) -> Dict:
+    """JTT-IPW initialisation + `num_epochs` Adam epochs + results back on the host.  With a
+    process group the buckets are sharded over its ranks (one all-reduce per epoch) and the
+    times are the maximum over the ranks."""
+    device = counts.device
+    _sync(device, process_group)
     t0 = time.perf_counter()
     init = jtt_ipw_from_counts(times, counts, mask=mask)
     S = counts.shape[-1]
     theta0 = theta_from_initialization(init, np.ones((S, S)) if mask is None else mask)
-    eng = FitEngine(np.asarray(times), counts, theta0, mask=mask, num_epochs=num_epochs, device=device)
+    eng = FitEngine(np.asarray(times), counts, theta0, mask=mask, num_epochs=num_epochs, device=device,
+                    process_group=process_group, rate_scale=float(np.max(-np.diag(init))))
     torch.cuda.synchronize(device)
     t_setup = time.perf_counter()
     _lib.reset_launch_count()
@@ -49,11 +60,22 @@ def timed_fit(times, counts: torch.Tensor, num_epochs: int, mask=None) -> Dict:
     e1.record()
     res = eng.results()
     t1 = time.perf_counter()
+    secs = [t1 - t0, t_setup - t0, e0.elapsed_time(e1) * 1e-3]
+    n_ranks = 1
+    if process_group is not None:
+        import torch.distributed as dist
+
+        tt = torch.tensor(secs, dtype=torch.float64, device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX, group=process_group)
+        secs = [float(x) for x in tt]
+        n_ranks = dist.get_world_size(process_group)
     out = {
-        "S": int(S), "K": int(len(times)), "num_epochs": int(num_epochs),
-        "seconds_end_to_end": t1 - t0, "seconds_setup_init": t_setup - t0,
-        "seconds_device_epochs": e0.elapsed_time(e1) * 1e-3,
-        "ms_per_epoch": e0.elapsed_time(e1) / max(1, num_epochs),
+        "S": int(S), "K": int(len(times)), "num_epochs": int(num_epochs), "n_gpus": n_ranks,
+        "sharding": "replica" if n_ranks == 1 else f"buckets over {n_ranks} ranks, one all-reduce of [dL/dQ | loss] per epoch",
+        "buckets_this_rank": int(eng.K),
+        "seconds_end_to_end": secs[0], "seconds_setup_init": secs[1],
+        "seconds_device_epochs": secs[2],
+        "ms_per_epoch": secs[2] * 1e3 / max(1, num_epochs),
         "loss_first": float(res["loss"][0]), "loss_last": float(res["loss"][-1]),
         "gpu_launches": _lib.launch_count(),
     }
@@ -62,11 +84,11 @@ def timed_fit(times, counts: torch.Tensor, num_epochs: int, mask=None) -> Dict:
         mu, deg = ctypes.c_double(0), ctypes.c_int(0)
         _lib.check(_lib.load().cherry_fit_schedule(ctypes.byref(eng.args), s, ctypes.byref(mu), ctypes.byref(deg)),
                    "cherry_fit_schedule")
-        sq = int(sum(s))
+        sq = int(sum(s[: eng.K]))
         products_fwd = (deg.value - 1) + sq
         flops_epoch = 3.0 * products_fwd * 2.0 * S**3
         out.update({
-            "taylor_degree": deg.value, "squarings_total": sq, "squarings_max": int(max(s)),
+            "taylor_degree": deg.value, "squarings_total": sq, "squarings_max": int(max(s[: eng.K])),
             "matrix_products_per_epoch": 3 * products_fwd, "flop_per_epoch": flops_epoch,
             "tflops_executed": flops_epoch * num_epochs / out["seconds_device_epochs"] / 1e12,
             "mu": mu.value,
@@ -75,7 +97,7 @@ def timed_fit(times, counts: torch.Tensor, num_epochs: int, mask=None) -> Dict:
 
 
 def bench_fit(device, lg_times=None, lg_counts: Optional[torch.Tensor] = None, num_epochs: int = 500,
-              co_families: int = 4096) -> Dict:
+              co_families: int = 4096, process_group=None) -> Dict:
     from ..counting._device import count_raw, sorted_grid, symmetrize
     from ..synthetic import as_device_batch, quantization_grid, synthetic_co, synthetic_lg
 
@@ -88,16 +110,24 @@ def bench_fit(device, lg_times=None, lg_counts: Optional[torch.Tensor] = None, n
         gd = torch.from_numpy(sorted_grid(grid)).to(device)
         lg_counts = symmetrize(count_raw(dev, gd, K, 20), "lg", K, 20, False)
         lg_times = grid
+    # 20 x 20: one wave of CTAs, an epoch is latency -- it stays on one GPU (replicas when N > 1)
     timed_fit(lg_times, lg_counts, 64)  # warm-up (module load, graph instantiation paths)
     out["lg_20x20"] = timed_fit(lg_times, lg_counts, num_epochs)
+    rank = 0
+    if process_group is not None:
+        import torch.distributed as dist
+
+        rank = dist.get_rank(process_group)
     # co-evolution counts from synthetic contact-map families (BASELINE config 4 shape)
     from .. import _lib
     from ..counting._device import build_bucket_table
 
     lib = _lib.load()
-    dev = as_device_batch(synthetic_co(co_families, 1024, 300, seed=11, device=device), device)
+    dev = as_device_batch(synthetic_co(co_families, 1024, 300, seed=11 + rank, device=device), device)
     gd = torch.from_numpy(sorted_grid(grid)).to(device)
     raw = count_raw(dev, gd, K, 20)  # warm-up (and the counts the fit below uses)
+    if process_group is not None:  # every rank counted its own families: one all-reduce of the raw histogram
+        dist.all_reduce(raw, op=dist.ReduceOp.SUM, group=process_group)
     co_counts = symmetrize(raw, "co", K, 20, False)
     order = torch.empty(dev.n_pairs, dtype=torch.int32, device=device)
     recs = torch.empty(dev.n_pairs * 16, dtype=torch.uint8, device=device)
@@ -149,8 +179,8 @@ def bench_fit(device, lg_times=None, lg_counts: Optional[torch.Tensor] = None, n
     del order, recs
     del raw, dev
     peak = measure_fp64_gemm_peak(device)
-    timed_fit(grid, co_counts, 4)
-    co = timed_fit(grid, co_counts, num_epochs)
+    timed_fit(grid, co_counts, 4, process_group=process_group)
+    co = timed_fit(grid, co_counts, num_epochs, process_group=process_group)
     co["roofline"] = {"bound": "tensor", "unit": "TFLOP/s", "achieved": co["tflops_executed"], "peak": peak,
                       "frac": co["tflops_executed"] / peak,
                       "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)"}

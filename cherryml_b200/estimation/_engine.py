@@ -73,8 +73,35 @@ def random_theta(S: int, seed: int = 0) -> np.ndarray:
     return np.concatenate([np.log(np.ones(S) / S), upper])
 
 
+def assign_buckets(times: Sequence[float], world_size: int, rate_scale: float = 1.0) -> list:
+    """Partition the K time buckets over ``world_size`` ranks, balanced by estimated cost.
+
+    Cost model: a bucket costs one unit (Taylor evaluation, loss,
+    adjoint) plus one unit per squaring, ``s_k = max(0, ceil(log2(t_k * rate_scale / 1.09)))``
+    with ``rate_scale`` ~ max |Q_ii| of the starting point.  Longest-processing-time greedy,
+    ties broken by bucket index, so every rank computes the same partition.  Returns
+    ``world_size`` sorted index arrays."""
+    t = np.asarray(times, dtype=np.float64).reshape(-1)
+    with np.errstate(divide="ignore"):
+        s = np.maximum(0.0, np.ceil(np.log2(np.maximum(t * rate_scale, 1e-300) / 1.09)))
+    cost = 1.0 + s
+    order = sorted(range(len(t)), key=lambda k: (-cost[k], k))
+    load = [0.0] * world_size
+    parts = [[] for _ in range(world_size)]
+    for k in order:
+        r = min(range(world_size), key=lambda i: (load[i], len(parts[i]), i))
+        parts[r].append(k)
+        load[r] += cost[k]
+    return [np.array(sorted(p), dtype=np.int64) for p in parts]
+
+
 class FitEngine:
-    """Training state of ``n_problems`` independent rate-matrix fits on one GPU."""
+    """Training state of ``n_problems`` independent rate-matrix fits on one GPU.
+
+    With ``process_group`` (torch.distributed, one process per GPU) the K buckets are
+    sharded over the ranks (``assign_buckets``); theta and the optimiser state are
+    replicated and every epoch exchanges ONE all-reduce of ``[dL/dQ | loss]``
+    (``cherry_fit_epoch_local`` / ``cherry_fit_epoch_update``)."""
 
     def __init__(
         self,
@@ -91,6 +118,8 @@ class FitEngine:
         device="cuda",
         betas=(0.9, 0.999),
         eps: float = 1e-8,
+        process_group=None,
+        rate_scale: float = 1.0,
     ):
         self.lib = _lib.load()
         device = torch.device(device)
@@ -110,6 +139,21 @@ class FitEngine:
         S = C.shape[-1]
         if tuple(C.shape) != (P, K, S, S):
             raise ValueError(f"counts shape {tuple(C.shape)} does not match times {times.shape}")
+        self.process_group = process_group
+        self.bucket_index = np.arange(K)
+        if process_group is not None:
+            import torch.distributed as dist
+
+            world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+            if K < world:
+                raise ValueError(f"{K} buckets cannot be sharded over {world} ranks (run replicas instead)")
+            if P != 1 and np.any(times != times[0]):
+                raise ValueError("bucket sharding needs the same time grid for every problem")
+            self.bucket_index = assign_buckets(times[0], world, rate_scale)[rank]
+            sel = torch.from_numpy(self.bucket_index).to(device)
+            times = times[:, self.bucket_index]
+            C = C.index_select(1, sel)
+            K = len(self.bucket_index)
         theta0 = np.asarray(theta0, dtype=np.float64)
         if theta0.ndim == 1:
             theta0 = theta0[None, :]
@@ -124,6 +168,9 @@ class FitEngine:
             np.ones((S, S)) if mask is None else np.ascontiguousarray(mask, dtype=np.float64)
         ).to(device)
         self.sumC = self.C.sum(dim=(1, 2, 3)).contiguous()
+        if process_group is not None:
+            dist.all_reduce(self.sumC, op=dist.ReduceOp.SUM, group=process_group)
+        self.packed = torch.zeros(P * S * S + P, **f64) if process_group is not None else None
         self.theta = torch.from_numpy(theta0).to(device).contiguous()
         self.adam_m = torch.zeros_like(self.theta)
         self.adam_v = torch.zeros_like(self.theta)
@@ -170,6 +217,8 @@ class FitEngine:
         n = self.num_epochs - self.epochs_done if num_epochs is None else int(num_epochs)
         if n <= 0:
             return
+        if self.process_group is not None:
+            return self._run_sharded(n)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream()
             if stream.cuda_stream == 0:
@@ -182,6 +231,18 @@ class FitEngine:
             else:
                 rc = self.lib.cherry_fit_run(ctypes.byref(self.args), n, stream.cuda_stream)
         _lib.check(rc, "cherry_fit_run")
+        self.epochs_done += n
+
+    def _run_sharded(self, n: int) -> None:
+        import torch.distributed as dist
+
+        with torch.cuda.device(self.device):
+            a, packed = ctypes.byref(self.args), _lib.ptr(self.packed)
+            for _ in range(n):
+                st = _lib.current_stream_ptr()
+                _lib.check(self.lib.cherry_fit_epoch_local(a, packed, st), "cherry_fit_epoch_local")
+                dist.all_reduce(self.packed, op=dist.ReduceOp.SUM, group=self.process_group)
+                _lib.check(self.lib.cherry_fit_epoch_update(a, packed, st), "cherry_fit_epoch_update")
         self.epochs_done += n
 
     def loss_and_grad(self):

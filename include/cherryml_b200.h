@@ -208,6 +208,19 @@ int cherry_fit_init(const cherry_fit_args* args, void* stream);
  * snapshot bookkeeping, exact gradient, optimiser step, next Q.  No host synchronisation;
  * epochs are replayed from a CUDA graph in chunks unless `stream` is already capturing. */
 int cherry_fit_run(const cherry_fit_args* args, int num_epochs, void* stream);
+/* Bucket-sharded training over several GPUs (one process per GPU, each with its own subset
+ * of the K buckets in `args`, replicated theta / optimiser state, args->sumC = the sum over
+ * ALL ranks): one epoch is
+ *     cherry_fit_epoch_local(args, packed)    loss and exact gradient of this rank's buckets,
+ *                                             packed = {[n_problems][S][S] gradient totals,
+ *                                             [n_problems] loss totals} (unnormalised)
+ *     all-reduce(SUM) of `packed` over the ranks   (the caller: NCCL via torch.distributed)
+ *     cherry_fit_epoch_update(args, packed)   bookkeeping, optimiser step and next Q from the
+ *                                             reduced totals, identical on every rank.
+ * This is the exchange step of l = sum_k l_k, dl/dQ = sum_k t_k G_k (reference
+ * trainer.py:170-187 evaluates the same sums on one device). */
+int cherry_fit_epoch_local(const cherry_fit_args* args, double* packed, void* stream);
+int cherry_fit_epoch_update(const cherry_fit_args* args, const double* packed, void* stream);
 /* One evaluation without an optimiser step (tests, evaluation): writes loss_part[p*K+k] =
  * -<C_k, log expm(t_k Q_p)> and dQ_part[p*K+k] = its gradient with respect to Q_p. */
 int cherry_fit_loss_grad(const cherry_fit_args* args, void* stream);

@@ -70,3 +70,58 @@ def test_striping_is_a_partition():
         parts = [get_process_args(r, world, fams) for r in range(world)]
         assert sorted(sum(parts, [])) == sorted(fams)
         assert parts[0] == fams[0::world]
+
+
+# ---------------------------------------------------------------- fit: bucket sharding
+def _fit_worker(rank, world, port, out_path):
+    """Each rank evaluates loss and dL/dQ on ITS buckets (fit oracle, CPU), one all-reduce of
+    [dL/dQ | loss] gives every rank the totals -- the exchange step of the sharded fit."""
+    from cherryml_b200.estimation._engine import assign_buckets
+    from cherryml_b200.io import read_count_matrices_array, read_rate_matrix
+    from oracle.fit_oracle import loss_and_grad_oracle
+    from tests.test_oracle_fit import INP, LG_COUNTS
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    q, _, counts = read_count_matrices_array(LG_COUNTS)
+    Q = read_rate_matrix(os.path.join(INP, "lg.txt")).to_numpy()
+    mine = assign_buckets(q, world, rate_scale=float(np.max(-np.diag(Q))))[rank]
+    loss, grad = loss_and_grad_oracle(Q, np.asarray(q)[mine], counts[mine])
+    w = counts[mine].sum()  # the oracle normalises by its own counts: undo, the kernels exchange raw sums
+    packed = torch.from_numpy(np.concatenate([grad.reshape(-1) * w, [loss * w]]))
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+    dist.barrier()
+    if rank == 0:
+        np.save(out_path, packed.numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_bucket_sharded_loss_and_gradient(tmp_path):
+    from cherryml_b200.io import read_count_matrices_array, read_rate_matrix
+    from oracle.fit_oracle import loss_and_grad_oracle
+    from tests.test_oracle_fit import INP, LG_COUNTS
+
+    out = str(tmp_path / "packed.npy")
+    mp.spawn(_fit_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    q, _, counts = read_count_matrices_array(LG_COUNTS)
+    got = np.load(out) / counts.sum()
+    Q = read_rate_matrix(os.path.join(INP, "lg.txt")).to_numpy()
+    loss, grad = loss_and_grad_oracle(Q, q, counts)
+    assert np.allclose(got[-1], loss, rtol=1e-12)
+    assert np.allclose(got[:-1].reshape(20, 20), grad, rtol=1e-10, atol=1e-10 * np.abs(grad).max())
+
+
+def test_assign_buckets_is_a_balanced_partition():
+    from cherryml_b200.estimation._engine import assign_buckets
+    from cherryml_b200.synthetic import quantization_grid
+
+    grid = quantization_grid()
+    for world in (1, 2, 3, 8, 16):
+        parts = assign_buckets(grid, world, rate_scale=1.1)
+        assert sorted(np.concatenate(parts).tolist()) == list(range(len(grid)))
+        cost = 1.0 + np.maximum(0.0, np.ceil(np.log2(np.asarray(grid) * 1.1 / 1.09)))
+        loads = [cost[p].sum() for p in parts]
+        assert max(loads) - min(loads) <= cost.max()
+        again = assign_buckets(grid, world, rate_scale=1.1)  # deterministic: every rank gets the same answer
+        assert all(np.array_equal(a, b) for a, b in zip(parts, again))

@@ -232,3 +232,41 @@ def test_dmma_gemm_matches_cublas(ta, tb, n, batch, ksplit):
     assert torch.allclose(got, ref, rtol=1e-12, atol=1e-11)
     acc = gemm_f64_batched(A, B, ta, tb, C=C0.clone(), ksplit=ksplit)
     assert torch.allclose(acc, ref + C0, rtol=1e-12, atol=1e-11)
+
+
+@pytest.mark.parametrize("S,K", [(20, 24), (48, 6)])
+def test_bucket_sharded_epochs_equal_the_single_gpu_run(S, K):
+    """The sharded epoch (local loss/gradient -> ONE all-reduce of [dL/dQ | loss] -> update) on a
+    1-rank NCCL group must reproduce the graph-replayed single-GPU run: same kernels, same
+    reduction order.  (World size 2 is covered on CPU by tests/test_dist_gloo.py and on the GPU
+    by ``bench.py --gpus 2``.)"""
+    import socket
+
+    import torch.distributed as dist
+
+    created = False
+    if not dist.is_initialized():
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+        created = True
+    try:
+        rng = np.random.default_rng(S)
+        times = np.exp(rng.uniform(np.log(1e-3), np.log(8.0), K))
+        counts = rng.integers(0, 200, size=(K, S, S)).astype(np.float64)
+        counts = counts + counts.transpose(0, 2, 1)
+        theta0 = random_theta(S)
+        a = FitEngine(times, counts, theta0, num_epochs=70)
+        a.run()
+        ra = a.results()
+        b = FitEngine(times, counts, theta0, num_epochs=70, process_group=dist.group.WORLD)
+        b.run()
+        rb = b.results()
+        assert np.allclose(ra["loss"], rb["loss"], rtol=1e-12, atol=0)
+        assert np.allclose(ra["Q_best"], rb["Q_best"], rtol=1e-9, atol=1e-12)
+        assert np.allclose(ra["Q_last"], rb["Q_last"], rtol=1e-9, atol=1e-12)
+    finally:
+        if created:
+            dist.destroy_process_group()
