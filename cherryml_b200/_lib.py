@@ -69,12 +69,32 @@ _SIGNATURES = {
     "cherry_expm_batched": (c_int, [_P, _P, _P]),
     "cherry_gemm_f64_batched": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "cherry_gemm_desc_bytes": (ctypes.c_size_t, [c_int]),
+    "cherry_ingest_lg": (c_int, [c_char_p, c_char_p, c_char_p, _P, c_int, _P, c_int, c_char_p, c_int, c_int,
+                                 c_int, _P]),
+    "cherry_ingest_co": (c_int, [c_char_p, c_char_p, c_char_p, _P, c_int, _P, c_int, c_char_p, c_int, c_int,
+                                 c_int, c_int, _P]),
+    "cherry_ingest_free": (None, [_P]),
     "cherry_count_lg_host": (
         c_int,
         [_P, c_int64, _P, c_int, _P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int,
          _P, c_int, c_int, c_int, c_int, _P, _P, _P],
     ),
 }
+
+class IngestResult(ctypes.Structure):
+    """``cherry_ingest_result`` of include/cherryml_b200.h."""
+
+    _fields_ = [
+        ("kind", c_int32), ("pinned", c_int32), ("msa_bytes", c_int64), ("msa", c_void_p),
+        ("n_fams", c_int32), ("r_pad", c_int32), ("fams", c_void_p),
+        ("n_pairs", c_int64), ("pair_a", c_void_p), ("pair_b", c_void_p), ("pair_t", c_void_p),
+        ("pair_fam", c_void_p),
+        ("n_rate_vals", c_int64), ("rate_vals", c_void_p),
+        ("n_aux", c_int64), ("aux", c_void_p),
+        ("n_tiles", c_int32), ("max_row_stride", c_int32), ("tiles", c_void_p),
+        ("n_items_examined", c_int64),
+    ]
+
 
 _lib = None
 

@@ -9,11 +9,14 @@ reference's ``cherryml/counting/_count_transitions.py:201-379`` and
 by ``std::stof``, ``_count_transitions.cpp:247``; ``result.txt`` in the C++ writer's
 layout with 6 significant digits, ``.cpp:524-548``), ``False`` reproduces the Python
 implementation (fp64 branch lengths, pandas-style ``result.txt``).  Both run on the GPU.
-``num_processes`` and the ``cpp_command_line_*`` arguments are accepted and ignored.
+``num_processes`` sizes the host ingest thread pool; the ``cpp_command_line_*`` arguments
+are accepted and ignored.
 Extra keyword arguments (all excluded from the cache key): ``device``,
 ``process_group`` (torch.distributed group: families are striped over ranks exactly like
 the reference stripes them over MPI ranks, ``.cpp:624-629``, and the raw integer
-histograms are all-reduced), ``result_style`` (override the writer layout).
+histograms are all-reduced), ``result_style`` (override the writer layout), ``ingest``
+(``"native"``: the library's multithreaded C++ parser/encoder with ``num_processes`` threads,
+default; ``"python"``: the pure-Python one, same output).
 """
 import logging
 import os
@@ -27,7 +30,7 @@ from .. import caching
 from ..io import write_count_matrices_array
 from ..utils import get_process_args
 from ._device import count_batch
-from ._ingest import build_co_batch, build_lg_batch
+from ._ingest import build_co_batch, build_co_batch_native, build_lg_batch, build_lg_batch_native
 
 logger = logging.getLogger(__name__)
 
@@ -46,6 +49,16 @@ def _rank_world(process_group):
     import torch.distributed as dist
 
     return dist.get_rank(process_group), dist.get_world_size(process_group)
+
+
+def _ingest_threads(num_processes) -> int:
+    """``num_processes`` is the reference's degree of host parallelism for counting (MPI ranks);
+    here it sizes the ingest thread pool, capped by the host's cores."""
+    try:
+        n = int(num_processes)
+    except (TypeError, ValueError):
+        n = 1
+    return max(1, min(n, os.cpu_count() or 1))
 
 
 def _finish(counts_dev, grid, states, out_dir, style, start_time, num_processes, rank, process_group=None):
@@ -75,6 +88,7 @@ def _finish(counts_dev, grid, states, out_dir, style, start_time, num_processes,
         "device",
         "process_group",
         "result_style",
+        "ingest",
     ],
     output_dirs=["output_count_matrices_dir"],
     write_extra_log_files=True,
@@ -95,6 +109,7 @@ def count_transitions(
     device: str = "cuda",
     process_group=None,
     result_style: Optional[str] = None,
+    ingest: str = "native",
 ) -> None:
     """Count single-site transitions into a ``K x S x S`` tensor (see module docstring)."""
     if edge_or_cherry.startswith("cherry++__"):
@@ -104,10 +119,19 @@ def count_transitions(
     os.makedirs(output_count_matrices_dir, exist_ok=True)
     quantization_points = [float(q) for q in quantization_points]
     rank, world = _rank_world(process_group)
-    batch = build_lg_batch(
-        tree_dir, msa_dir, site_rates_dir, get_process_args(rank, world, list(families)),
-        amino_acids, edge_or_cherry, float32_branch_lengths=bool(use_cpp_implementation),
-    )
+    my_families = get_process_args(rank, world, list(families))
+    if ingest == "native":
+        batch = build_lg_batch_native(
+            tree_dir, msa_dir, site_rates_dir, my_families, amino_acids, edge_or_cherry,
+            float32_branch_lengths=bool(use_cpp_implementation), n_threads=_ingest_threads(num_processes),
+        )
+    elif ingest == "python":
+        batch = build_lg_batch(
+            tree_dir, msa_dir, site_rates_dir, my_families, amino_acids, edge_or_cherry,
+            float32_branch_lengths=bool(use_cpp_implementation),
+        )
+    else:
+        raise ValueError(f"Unknown ingest: {ingest!r}")
     counts = count_batch(
         batch, quantization_points, len(amino_acids), directed=(edge_or_cherry == "edge"),
         device=device, process_group=process_group,
@@ -127,6 +151,7 @@ def count_transitions(
         "device",
         "process_group",
         "result_style",
+        "ingest",
     ],
     output_dirs=["output_count_matrices_dir"],
     write_extra_log_files=True,
@@ -148,6 +173,7 @@ def count_co_transitions(
     device: str = "cuda",
     process_group=None,
     result_style: Optional[str] = None,
+    ingest: str = "native",
 ) -> None:
     """Count transitions of contacting site pairs into a ``K x S^2 x S^2`` tensor."""
     if edge_or_cherry.startswith("cherry++__"):
@@ -156,11 +182,20 @@ def count_co_transitions(
     os.makedirs(output_count_matrices_dir, exist_ok=True)
     quantization_points = [float(q) for q in quantization_points]
     rank, world = _rank_world(process_group)
-    batch = build_co_batch(
-        tree_dir, msa_dir, contact_map_dir, get_process_args(rank, world, list(families)),
-        amino_acids, edge_or_cherry, minimum_distance_for_nontrivial_contact,
-        float32_branch_lengths=bool(use_cpp_implementation),
-    )
+    my_families = get_process_args(rank, world, list(families))
+    if ingest == "native":
+        batch = build_co_batch_native(
+            tree_dir, msa_dir, contact_map_dir, my_families, amino_acids, edge_or_cherry,
+            minimum_distance_for_nontrivial_contact, float32_branch_lengths=bool(use_cpp_implementation),
+            n_threads=_ingest_threads(num_processes),
+        )
+    elif ingest == "python":
+        batch = build_co_batch(
+            tree_dir, msa_dir, contact_map_dir, my_families, amino_acids, edge_or_cherry,
+            minimum_distance_for_nontrivial_contact, float32_branch_lengths=bool(use_cpp_implementation),
+        )
+    else:
+        raise ValueError(f"Unknown ingest: {ingest!r}")
     counts = count_batch(
         batch, quantization_points, len(amino_acids), directed=(edge_or_cherry == "edge"),
         device=device, process_group=process_group,

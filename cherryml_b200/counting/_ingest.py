@@ -385,3 +385,107 @@ def build_co_batch(
             float32_branch_lengths,
         )
     return builder.finish()
+
+
+# ------------------------------------------------------------------ native (C++) ingest
+class _NativeHandle:
+    """Keeps a ``cherry_ingest_result`` alive while numpy views of its arrays exist."""
+
+    def __init__(self, lib, ptr):
+        self.lib, self.ptr = lib, ptr
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.cherry_ingest_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def _native_batch(kind: str, call, families: Sequence[str]) -> CountBatch:
+    import ctypes
+
+    from .. import _lib
+
+    lib = _lib.load()
+    res = ctypes.POINTER(_lib.IngestResult)()
+    rc = call(lib, ctypes.byref(res))
+    _lib.check(rc, "cherry_ingest_" + kind)
+    r = res.contents
+    handle = _NativeHandle(lib, ctypes.cast(res, ctypes.c_void_p))
+
+    def arr(addr, n, dtype):
+        if n == 0 or not addr:
+            return np.zeros((0,), dtype=dtype)
+        nbytes = int(n) * np.dtype(dtype).itemsize
+        buf = (ctypes.c_uint8 * nbytes).from_address(addr)
+        buf._cherry_owner = handle  # numpy keeps `buf` alive, `buf` keeps the allocation alive
+        return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    if kind == "lg":
+        aux = arr(r.aux, r.n_aux, np.uint16)
+    else:
+        aux = arr(r.aux, r.n_aux * 2, np.int32).reshape(-1, 2)
+    batch = CountBatch(
+        kind=kind,
+        msa=arr(r.msa, r.msa_bytes, np.uint8),
+        fams=arr(r.fams, r.n_fams, FAM_DESC_DTYPE),
+        pair_a=arr(r.pair_a, r.n_pairs, np.int32),
+        pair_b=arr(r.pair_b, r.n_pairs, np.int32),
+        pair_t=arr(r.pair_t, r.n_pairs, np.float64),
+        pair_fam=arr(r.pair_fam, r.n_pairs, np.int32),
+        rate_vals=arr(r.rate_vals, r.n_rate_vals, np.float64),
+        aux=aux,
+        tiles=arr(r.tiles, r.n_tiles, TILE_DTYPE),
+        r_pad=int(r.r_pad),
+        n_sites_examined=int(r.n_items_examined),
+        family_names=list(families),
+    )
+    batch.msa_pinned = bool(r.pinned)
+    return batch
+
+
+def _c_strings(items: Sequence[str]):
+    import ctypes
+
+    enc = [s.encode("utf-8") for s in items]
+    return (ctypes.c_char_p * max(1, len(enc)))(*enc) if enc else (ctypes.c_char_p * 1)()
+
+
+def default_ingest_threads() -> int:
+    return max(1, min(64, os.cpu_count() or 1))
+
+
+def build_lg_batch_native(
+    tree_dir: str, msa_dir: str, site_rates_dir: str, families: Sequence[str], states: Sequence[str],
+    edge_or_cherry: str, float32_branch_lengths: bool, n_threads: Optional[int] = None, pinned: bool = False,
+) -> CountBatch:
+    """``build_lg_batch`` done by the library's multithreaded C++ ingest (``cherry_ingest_lg``)."""
+    fam_c, st_c = _c_strings(families), _c_strings(states)
+    nt = n_threads or default_ingest_threads()
+
+    def call(lib, out):
+        return lib.cherry_ingest_lg(
+            tree_dir.encode(), msa_dir.encode(), site_rates_dir.encode(), fam_c, len(families), st_c,
+            len(states), edge_or_cherry.encode(), int(float32_branch_lengths), nt, int(pinned), out)
+
+    return _native_batch("lg", call, families)
+
+
+def build_co_batch_native(
+    tree_dir: str, msa_dir: str, contact_map_dir: str, families: Sequence[str], states: Sequence[str],
+    edge_or_cherry: str, minimum_distance: int, float32_branch_lengths: bool,
+    n_threads: Optional[int] = None, pinned: bool = False,
+) -> CountBatch:
+    """``build_co_batch`` done by the library's multithreaded C++ ingest (``cherry_ingest_co``)."""
+    fam_c, st_c = _c_strings(families), _c_strings(states)
+    nt = n_threads or default_ingest_threads()
+
+    def call(lib, out):
+        return lib.cherry_ingest_co(
+            tree_dir.encode(), msa_dir.encode(), contact_map_dir.encode(), fam_c, len(families), st_c,
+            len(states), edge_or_cherry.encode(), int(minimum_distance), int(float32_branch_lengths), nt,
+            int(pinned), out)
+
+    return _native_batch("co", call, families)

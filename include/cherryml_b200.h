@@ -165,6 +165,56 @@ int cherry_count_lg_host(const uint8_t* msa, int64_t msa_bytes, const cherry_fam
                          int S, int r_pad, int directed, double* counts_out,
                          int64_t* h2d_bytes, int64_t* d2h_bytes);
 
+/* ------------------------------------------------------------------ ingest (host) */
+
+/* An encoded batch built by cherry_ingest_lg / cherry_ingest_co: HOST arrays in exactly the
+ * layout the counting entry points take (the library owns them; release with
+ * cherry_ingest_free).  `msa` is page-locked when `pinned` is 1. */
+typedef struct cherry_ingest_result {
+  int32_t kind;        /* 0 = LG, 1 = co-transitions */
+  int32_t pinned;
+  int64_t msa_bytes;
+  uint8_t* msa;
+  int32_t n_fams;
+  int32_t r_pad;
+  cherry_fam_desc* fams;
+  int64_t n_pairs;
+  int32_t* pair_a;
+  int32_t* pair_b;
+  double* pair_t;
+  int32_t* pair_fam;
+  int64_t n_rate_vals;
+  double* rate_vals;
+  int64_t n_aux;       /* LG: entries of group_cat; co: contacting pairs */
+  void* aux;           /* LG: uint16 group_cat[n_aux]; co: int32 contacts[n_aux][2] */
+  int32_t n_tiles;
+  int32_t max_row_stride;
+  cherry_tile* tiles;
+  int64_t n_items_examined; /* (pair, site) or (pair, contact) items before validity */
+} cherry_ingest_result;
+
+/* Parse `<dir>/<family>.txt` of every family with n_threads host threads and encode them
+ * for cherry_count_lg: trees -> leaf pairs (edge_or_cherry = "cherry++", "cherry" or "edge"),
+ * MSAs -> residue rows (alphabet = `states`, n_states one-character strings), site rates ->
+ * rate categories and the category-sorted column layout.  float32_branch_lengths != 0 parses
+ * branch lengths like the reference C++ program (std::stof, _count_transitions.cpp:247).
+ * Replaces read_tree / read_msa / read_site_rates and _dfs of counting/_count_transitions.cpp
+ * (:209-293, :316-390) with the accept/reject behaviour of the Python readers (io/_tree.py
+ * :214-265, io/_msa.py:51-73, io/_site_rates.py:5-26). */
+int cherry_ingest_lg(const char* tree_dir, const char* msa_dir, const char* site_rates_dir,
+                     const char* const* families, int n_fams, const char* const* states,
+                     int n_states, const char* edge_or_cherry, int float32_branch_lengths,
+                     int n_threads, int pinned, cherry_ingest_result** out);
+/* Same for cherry_count_co: contact maps -> contacting pairs (i < j, j - i >=
+ * minimum_distance, map[i][j] == '1'; io/_contact_map.py:6-28, _count_co_transitions.cpp
+ * :433-442) and contact-paired rows. */
+int cherry_ingest_co(const char* tree_dir, const char* msa_dir, const char* contact_map_dir,
+                     const char* const* families, int n_fams, const char* const* states,
+                     int n_states, const char* edge_or_cherry, int minimum_distance,
+                     int float32_branch_lengths, int n_threads, int pinned,
+                     cherry_ingest_result** out);
+void cherry_ingest_free(cherry_ingest_result* result);
+
 /* ------------------------------------------------------------------- fit */
 
 /* Everything the fit keeps on the device.  One "problem" is one rate matrix with its K time

@@ -133,3 +133,102 @@ def test_synthetic_batches_and_text_rendering():
         _, oc = count_co_transitions_oracle(d + "/tree_dir", d + "/msa_dir", d + "/contact_map_dir", names,
                                             amino_acids, grid, "cherry++", 7, False)
         assert np.array_equal(oc, c)
+
+
+# ------------------------------------------------------------ native (C++) ingest == Python ingest
+_BATCH_FIELDS = ("msa", "fams", "pair_a", "pair_b", "pair_t", "pair_fam", "rate_vals", "aux", "tiles")
+
+
+def _assert_same_batch(a, b):
+    for name in _BATCH_FIELDS:
+        x, y = getattr(a, name), getattr(b, name)
+        assert x.dtype == y.dtype and x.shape == y.shape, name
+        assert np.array_equal(x, y), name
+    assert a.r_pad == b.r_pad and a.n_sites_examined == b.n_sites_examined
+    assert a.family_names == b.family_names
+
+
+@pytest.mark.parametrize("case", LG_CASES + CO_CASES, ids=lambda c: f"{c[0]}-{c[4]}-{c[5][:9]}")
+def test_native_ingest_equals_python_ingest_tiny(golden_counting, case):
+    from cherryml_b200.counting._ingest import build_co_batch_native, build_lg_batch_native
+
+    ds, fams, aa, _, mode, gdir = case
+    root = os.path.join(golden_counting, ds)
+    for f32 in (True, False):
+        for nt in (1, 3):
+            if "co_matrices" in gdir:
+                py = build_co_batch(f"{root}/tree_dir", f"{root}/msa_dir", f"{root}/contact_map_dir", fams, aa, mode, 2, f32)
+                nat = build_co_batch_native(f"{root}/tree_dir", f"{root}/msa_dir", f"{root}/contact_map_dir", fams, aa,
+                                            mode, 2, f32, n_threads=nt)
+            else:
+                py = build_lg_batch(f"{root}/tree_dir", f"{root}/msa_dir", f"{root}/site_rates_dir", fams, aa, mode, f32)
+                nat = build_lg_batch_native(f"{root}/tree_dir", f"{root}/msa_dir", f"{root}/site_rates_dir", fams, aa,
+                                            mode, f32, n_threads=nt)
+            _assert_same_batch(py, nat)
+
+
+@pytest.mark.parametrize("mode,tag,msa_sub", MODES)
+def test_native_ingest_equals_python_ingest_medium3(golden_counting, mode, tag, msa_sub):
+    from cherryml_b200.counting._ingest import build_co_batch_native, build_lg_batch_native
+
+    m3 = os.path.join(golden_counting, "medium3")
+    for f32 in (True, False):
+        _assert_same_batch(
+            build_lg_batch(f"{m3}/tree_dir", f"{m3}/{msa_sub}", f"{m3}/site_rates_dir", MEDIUM3, amino_acids, mode, f32),
+            build_lg_batch_native(f"{m3}/tree_dir", f"{m3}/{msa_sub}", f"{m3}/site_rates_dir", MEDIUM3, amino_acids,
+                                  mode, f32))
+        _assert_same_batch(
+            build_co_batch(f"{m3}/tree_dir", f"{m3}/{msa_sub}", f"{m3}/contact_map_dir", MEDIUM3, amino_acids, mode, 7, f32),
+            build_co_batch_native(f"{m3}/tree_dir", f"{m3}/{msa_sub}", f"{m3}/contact_map_dir", MEDIUM3, amino_acids,
+                                  mode, 7, f32))
+
+
+def test_native_ingest_synthetic_rendering_and_empty_family_list(tmp_path):
+    from cherryml_b200.counting._ingest import build_co_batch_native, build_lg_batch_native
+
+    syn = synthetic_lg(5, 16, 70, 4, seed=3)
+    names = write_text_rendering(syn, str(tmp_path / "lg"))
+    d = str(tmp_path / "lg")
+    _assert_same_batch(
+        build_lg_batch(d + "/tree_dir", d + "/msa_dir", d + "/site_rates_dir", names, amino_acids, "cherry++", False),
+        build_lg_batch_native(d + "/tree_dir", d + "/msa_dir", d + "/site_rates_dir", names, amino_acids, "cherry++",
+                              False, n_threads=4))
+    syn = synthetic_co(4, 12, 60, seed=5)
+    names = write_text_rendering(syn, str(tmp_path / "co"))
+    d = str(tmp_path / "co")
+    _assert_same_batch(
+        build_co_batch(d + "/tree_dir", d + "/msa_dir", d + "/contact_map_dir", names, amino_acids, "cherry++", 7, True),
+        build_co_batch_native(d + "/tree_dir", d + "/msa_dir", d + "/contact_map_dir", names, amino_acids, "cherry++",
+                              7, True, n_threads=2))
+    _assert_same_batch(
+        build_lg_batch(d + "/tree_dir", d + "/msa_dir", d + "/site_rates_dir", [], amino_acids, "cherry++", True),
+        build_lg_batch_native(d + "/tree_dir", d + "/msa_dir", d + "/site_rates_dir", [], amino_acids, "cherry++", True))
+
+
+def test_native_ingest_errors(tmp_path):
+    """Malformed inputs are rejected with the readers' messages (no partial batch)."""
+    from cherryml_b200 import _lib
+    from cherryml_b200.counting._ingest import build_lg_batch_native
+
+    syn = synthetic_lg(2, 8, 20, 2, seed=1)
+    d = str(tmp_path)
+    names = write_text_rendering(syn, d)
+    args = (d + "/tree_dir", d + "/msa_dir", d + "/site_rates_dir")
+    with pytest.raises(_lib.CherryError, match="cannot open"):
+        build_lg_batch_native(*args, names + ["missing"], amino_acids, "cherry++", True)
+    with pytest.raises(_lib.CherryError, match="Unknown edge_or_cherry"):
+        build_lg_batch_native(*args, names, amino_acids, "twig", True)
+    tree = open(f"{d}/tree_dir/{names[0]}.txt").read()
+    open(f"{d}/tree_dir/{names[0]}.txt", "w").write(tree.replace(" nodes", " knots", 1))
+    with pytest.raises(_lib.CherryError, match="should start with"):
+        build_lg_batch_native(*args, names, amino_acids, "cherry++", True)
+    open(f"{d}/tree_dir/{names[0]}.txt", "w").write(tree)
+    msa = open(f"{d}/msa_dir/{names[1]}.txt").read()
+    open(f"{d}/msa_dir/{names[1]}.txt", "w").write(msa.replace(">seq3\n", ">other\n", 1))
+    with pytest.raises(_lib.CherryError, match="not in the MSA"):
+        build_lg_batch_native(*args, names, amino_acids, "cherry++", True)
+    open(f"{d}/msa_dir/{names[1]}.txt", "w").write(msa)
+    rates = open(f"{d}/site_rates_dir/{names[0]}.txt").read()
+    open(f"{d}/site_rates_dir/{names[0]}.txt", "w").write("5 sites\n" + " ".join(rates.split("\n")[1].split(" ")[:5]))
+    with pytest.raises(_lib.CherryError, match="only 5 site rates"):
+        build_lg_batch_native(*args, names, amino_acids, "cherry++", True)
