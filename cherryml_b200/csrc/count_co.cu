@@ -163,61 +163,66 @@ struct CoStageMeta {
 
 // Two (pair, contact) items = one 32-bit word of row a (bytes xi0 xj0 xi1 xj1) and the same
 // word of row b.  An item goes to the shared histogram when at most one site changed:
-// I[xi][yi][xj] (site j unchanged) at hist, J[xj][yj][xi] (site i unchanged) at hist + 4*S1^3.
-// The shared histogram has S1 = S+1 states per axis and those two cells name all four bytes
-// (the unchanged site's byte stands for both rows), so an item with a skip byte lands in a
-// junk cell that the flush drops: no validity test on the hot path.  Items with BOTH sites
-// changed are tested; the valid ones (6 % on Pfam-like data) set their bit in the returned
-// mask and are handled after the fast path of the whole 8-byte item, once.
+// I[xi][yi][xj] (site j unchanged) at hist, J[xi][xj][yj] (site i unchanged) at histJ =
+// hist + 4*S1^3.  The shared histogram has S1 = S+1 states per axis and those two cells name
+// all four bytes (the unchanged site's byte stands for both rows), so an item with a skip
+// byte lands in a junk cell that the flush drops: no validity test on the hot path.
+// Branch-free: one PRMT gathers the contact's four bytes (xi, yi, xj, yj), one IDP.4A with
+// the table's coefficient bytes gives 4*S1*mid + 4*low + base, one IMAD adds 4*S1^2*xi; an
+// item with BOTH sites changed is redirected to one junk word (ATOMS.POPC.INC cannot be
+// predicated; equal addresses merge), and if all four bytes are valid (6 % of the items on
+// Pfam-like data) its bit is set in the returned mask: those go to L2 after the fast path
+// of the whole 8-byte item, once.  w4[c] returns the gathered bytes for that slow path.
 //   vmask = (0x80 - S) * 0x01010101: (byte + 0x80 - S) has bit 7 set iff byte == S.
-template <bool SMEM>
-__device__ __forceinline__ uint32_t co_word(uint32_t wa, uint32_t wb, uint32_t vmask, uint32_t coef,
-                                            uint32_t plane4, uint32_t hist, uint32_t histJ) {
+struct CoConst {
+  uint32_t vmask, coefI, coefJ, plane4, hist, histJ, junk;
+};
+
+__device__ __forceinline__ uint32_t co_word(uint32_t wa, uint32_t wb, const CoConst& k, uint32_t* w4) {
   const uint32_t d = wa ^ wb;
-  const uint32_t v = ((wa + vmask) | (wb + vmask)) & 0x80808080u;
+  const uint32_t v = ((wa + k.vmask) | (wb + k.vmask)) & 0x80808080u;
   uint32_t slow = 0;
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     const uint32_t m_i = 0xffu << (16 * c), m_j = 0xff00u << (16 * c), m_c = 0xffffu << (16 * c);
     const bool eqj = (d & m_j) == 0;
     const bool near = eqj || (d & m_i) == 0;
-    if (SMEM && near) {
-      // eqj: (p, q, r) = (xi, yi, xj);  else (xj, yj, xi);  PRMT nibble n selects byte n of {wa, wb}
-      const uint32_t sel = c == 0 ? (eqj ? 0x4041u : 0x4150u) : (eqj ? 0x4263u : 0x4372u);
-      const uint32_t w = __byte_perm(wa, wb, sel);                      // bytes: r, q, p, (unused)
-      const uint32_t lo = __dp4a(w, coef, eqj ? hist : histJ);          // 4r + 4*S1*q + base
-      const uint32_t addr = __byte_perm(w, 0, 0x4442u) * plane4 + lo;   // + 4*S1*S1*p
-      asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
-    } else if ((v & m_c) == 0) {  // both sites changed (or no shared histogram) and all four valid
-      slow |= 1u << c;
-    }
+    const uint32_t g = __byte_perm(wa, wb, c == 0 ? 0x5140u : 0x7362u);  // bytes: xi, yi, xj, yj
+    w4[c] = g;
+    const uint32_t lo = __dp4a(g, eqj ? k.coefI : k.coefJ, eqj ? k.hist : k.histJ);
+    uint32_t addr = (g & 0xffu) * k.plane4 + lo;
+    if (!near) addr = k.junk;
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+    if (!near && (v & m_c) == 0) slow |= 1u << c;
   }
   return slow;
 }
 
-// Both sites changed: one L2 reduction.  h = 16-bit halves (xi | xj << 8), (yi | yj << 8).
-__device__ __forceinline__ void co_slow(uint32_t ha, uint32_t hb, uint32_t S, uint32_t* __restrict__ counts_b) {
-  const uint32_t xi = ha & 0xffu, xj = (ha >> 8) & 0xffu;
-  const uint32_t yi = hb & 0xffu, yj = (hb >> 8) & 0xffu;
-  atomicAdd(counts_b + (size_t)(xi * S + xj) * (S * S) + (yi * S + yj), 1u);
+// Both sites changed, all four bytes valid: one L2 reduction.  g = bytes (xi, yi, xj, yj);
+// cell = (xi*S + xj) * S^2 + yi*S + yj.
+__device__ __forceinline__ void co_slow(uint32_t g, uint32_t S, uint32_t coef_e, uint32_t* __restrict__ counts_b) {
+  const uint32_t xi = g & 0xffu, xj = __byte_perm(g, 0, 0x4442u);
+  const uint32_t e = __dp4a(g, coef_e, 0u);  // yi*S + yj
+  atomicAdd(counts_b + (size_t)((xi * S + xj) * (S * S) + e), 1u);
 }
 
 template <bool SMEM>
 __device__ __forceinline__ void co_flush(uint32_t* hist, int S, int tid, uint32_t* __restrict__ counts_b) {
   if (!SMEM) return;
   const int S1 = S + 1, T = S1 * S1 * S1, n = S * S;
-  for (int i = tid; i < 2 * T; i += kCoConsumerWarps * 32) {
+  for (int i = tid; i < 2 * T + 1; i += kCoConsumerWarps * 32) {
     const uint32_t v = hist[i];
     if (v == 0) continue;
     hist[i] = 0;
+    if (i >= 2 * T) continue;  // the junk word
     int r = i < T ? i : i - T;
     const int c = r % S1;
     r /= S1;
     const int q = r % S1, p = r / S1;
     if (c >= S || q >= S || p >= S) continue;  // junk cells (an item with a skip byte)
-    // I[p=xi][q=yi][c=xj]: (xi,xj)->(yi,xj);  J[p=xj][q=yj][c=xi]: (xi,xj)->(xi,yj)
-    const int s = i < T ? p * S + c : c * S + p;
-    const int e = i < T ? q * S + c : c * S + q;
+    // I[p=xi][q=yi][c=xj]: (xi,xj)->(yi,xj);  J[p=xi][q=xj][c=yj]: (xi,xj)->(xi,yj)
+    const int s = i < T ? p * S + c : p * S + q;
+    const int e = i < T ? q * S + c : p * S + c;
     atomicAdd(counts_b + (size_t)s * n + e, v);
   }
 }
@@ -273,7 +278,7 @@ count_co_sorted_kernel(const uint8_t* __restrict__ msa, const cherry_co_rec* __r
 
   for (int i = tid; i <= K + 1; i += kCoThreads) sbstart[i] = bucket_start[i];
   if (SMEM)
-    for (int i = tid; i < 2 * T; i += kCoThreads) hist[i] = 0;
+    for (int i = tid; i < 2 * T + 1; i += kCoThreads) hist[i] = 0;
   if (tid == 0) {
     for (int s = 0; s < n_stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 2 * 32);  // one producer warp, two arrivals per thread
@@ -377,9 +382,15 @@ count_co_sorted_kernel(const uint8_t* __restrict__ msa, const cherry_co_rec* __r
   }
 
   // -------------------------------------------------------------- consumer warps
-  const uint32_t hist_s = smem_u32(hist), histJ_s = hist_s + 4u * T;
-  const uint32_t plane4 = 4u * S1 * S1, coef = 0x00000004u | ((4u * S1) << 8);
-  const uint32_t vmask = (0x80u - (uint32_t)S) * 0x01010101u;
+  CoConst kc;
+  kc.hist = smem_u32(hist);
+  kc.histJ = kc.hist + 4u * T;
+  kc.junk = kc.hist + 8u * T;
+  kc.plane4 = 4u * S1 * S1;
+  kc.coefI = ((4u * S1) << 8) | (4u << 16);   // bytes (xi, yi, xj, yj): I = [xi][yi][xj]
+  kc.coefJ = ((4u * S1) << 16) | (4u << 24);  // J = [xi][xj][yj]
+  kc.vmask = (0x80u - (uint32_t)S) * 0x01010101u;
+  const uint32_t coef_e = ((uint32_t)S << 8) | (1u << 24);  // yi*S + yj
   const int warp = tid >> 5;
   int cur_bucket = -1;
   int c = warp;  // this warp's next chunk, relative to the first chunk of stage k
@@ -406,26 +417,25 @@ count_co_sorted_kernel(const uint8_t* __restrict__ msa, const cherry_co_rec* __r
       if (i >= n_items) continue;
       const uint2 a = *reinterpret_cast<const uint2*>(regA + 8 * i);
       const uint2 b = *reinterpret_cast<const uint2*>(regB + 8 * i);
+      uint32_t w4[4];
       if (SMEM && !mixed) {
-        uint32_t slow = co_word<SMEM>(a.x, b.x, vmask, coef, plane4, hist_s, histJ_s);
-        slow |= co_word<SMEM>(a.y, b.y, vmask, coef, plane4, hist_s, histJ_s) << 2;
+        uint32_t slow = co_word(a.x, b.x, kc, w4);
+        slow |= co_word(a.y, b.y, kc, w4 + 2) << 2;
         if (slow) {
-          if (slow & 1u) co_slow(a.x, b.x, S, counts_b);
-          if (slow & 2u) co_slow(a.x >> 16, b.x >> 16, S, counts_b);
-          if (slow & 4u) co_slow(a.y, b.y, S, counts_b);
-          if (slow & 8u) co_slow(a.y >> 16, b.y >> 16, S, counts_b);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (slow & (1u << q)) co_slow(w4[q], S, coef_e, counts_b);
         }
       } else {
         int g = 0;  // the pair this item belongs to: first g with pair_end[g] > 8*i
         while (pair_end[s][g] <= 8 * i) ++g;
         const int bucket = pair_bucket[s][g];
         if (SMEM && bucket == cur_bucket) {
-          uint32_t slow = co_word<SMEM>(a.x, b.x, vmask, coef, plane4, hist_s, histJ_s);
-          slow |= co_word<SMEM>(a.y, b.y, vmask, coef, plane4, hist_s, histJ_s) << 2;
-          if (slow & 1u) co_slow(a.x, b.x, S, counts_b);
-          if (slow & 2u) co_slow(a.x >> 16, b.x >> 16, S, counts_b);
-          if (slow & 4u) co_slow(a.y, b.y, S, counts_b);
-          if (slow & 8u) co_slow(a.y >> 16, b.y >> 16, S, counts_b);
+          uint32_t slow = co_word(a.x, b.x, kc, w4);
+          slow |= co_word(a.y, b.y, kc, w4 + 2) << 2;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (slow & (1u << q)) co_slow(w4[q], S, coef_e, counts_b);
         } else {
           uint32_t* __restrict__ cb = counts + (size_t)bucket * cells;
           co_direct(a.x, b.x, S, cb);
@@ -498,7 +508,7 @@ int cherry_count_co(const uint8_t* msa, const cherry_co_rec* recs, const int32_t
   if (n_stages > kCoMaxStages) n_stages = kCoMaxStages;
   const int n_producers = n_stages < kCoProducerWarps ? n_stages : kCoProducerWarps;
   const size_t stage_bytes = (size_t)n_stages * 2 * region_bytes;
-  const size_t hist_bytes = 2 * (size_t)(S + 1) * (S + 1) * (S + 1) * sizeof(uint32_t);
+  const size_t hist_bytes = (2 * (size_t)(S + 1) * (S + 1) * (S + 1) + 4) * sizeof(uint32_t);  // + junk word
   const bool smem_hist = stage_bytes + hist_bytes + 8192 <= (size_t)kCoSmemLimit;
   const size_t dyn = stage_bytes + (smem_hist ? hist_bytes : 0);
   static bool attr_set[64] = {false};
