@@ -203,7 +203,7 @@ __device__ __forceinline__ uint32_t co_word(uint32_t wa, uint32_t wb, const CoCo
 __device__ __forceinline__ void co_slow(uint32_t g, uint32_t S, uint32_t coef_e, uint32_t* __restrict__ counts_b) {
   const uint32_t xi = g & 0xffu, xj = __byte_perm(g, 0, 0x4442u);
   const uint32_t e = __dp4a(g, coef_e, 0u);  // yi*S + yj
-  atomicAdd(counts_b + (size_t)((xi * S + xj) * (S * S) + e), 1u);
+  atomicAdd(counts_b + (uint32_t)((xi * S + xj) * (S * S) + e), 1u);  // < S^4 <= 2^24: 32-bit offset
 }
 
 template <bool SMEM>
@@ -421,10 +421,13 @@ count_co_sorted_kernel(const uint8_t* __restrict__ msa, const cherry_co_rec* __r
       if (SMEM && !mixed) {
         uint32_t slow = co_word(a.x, b.x, kc, w4);
         slow |= co_word(a.y, b.y, kc, w4 + 2) << 2;
-        if (slow) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (slow & (1u << q)) co_slow(w4[q], S, coef_e, counts_b);
+        // lanes with both-sites-changed items loop over them (typically 0-2 of the 4): the
+        // warp runs max-over-lanes iterations instead of four guarded blocks
+        while (slow) {
+          const uint32_t lo2 = (slow & 1u) ? w4[0] : w4[1], hi2 = (slow & 4u) ? w4[2] : w4[3];
+          const uint32_t g = (slow & 3u) ? lo2 : hi2;
+          slow &= slow - 1;
+          co_slow(g, S, coef_e, counts_b);
         }
       } else {
         int g = 0;  // the pair this item belongs to: first g with pair_end[g] > 8*i
