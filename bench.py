@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--families", type=int, default=16384, help="families per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-families", type=int, default=0, help="families in the CPU sample (0 = 2 per core, >= 32)")
+    ap.add_argument("--cpu-families", type=int, default=0, help="families in the CPU sample (0 = 16 per core, >= 128)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fit", action="store_true")
     return ap.parse_args()
@@ -114,6 +114,31 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------ CPU reference / baseline
+_RENDERED = {}
+
+
+def rendered_sample(n_families, seed=0):
+    """Text rendering of `n_families` of the workload, written once per process (untimed: both
+    the reference programs and our text path start from these files)."""
+    import atexit
+
+    from cherryml_b200.synthetic import synthetic_lg, write_text_rendering
+
+    key = (n_families, seed)
+    if key not in _RENDERED:
+        syn = synthetic_lg(n_families, N_SEQS, N_SITES, N_CATS, seed=seed, device="cpu")
+        tmp = tempfile.mkdtemp(prefix="cherry_txt_")
+        atexit.register(shutil.rmtree, tmp, True)
+        names = write_text_rendering(syn, tmp)
+        _RENDERED[key] = (syn, tmp, names)
+    return _RENDERED[key]
+
+
+def default_cpu_families():
+    """Sample size of the CPU legs: ~1-2 s of reference time per step on the box's cores."""
+    return max(128, 16 * (os.cpu_count() or 1))
+
+
 def cpu_reference_run(n_families, seed=0, workdir=None):
     """Time the reference's CPU counting on a bounded sample of the workload.
 
@@ -128,13 +153,11 @@ def cpu_reference_run(n_families, seed=0, workdir=None):
 
     cores = os.cpu_count() or 1
     grid = quantization_grid()
-    syn = synthetic_lg(n_families, N_SEQS, N_SITES, N_CATS, seed=seed, device="cpu")
+    syn, tmp, names = rendered_sample(n_families, seed)
     examined = syn["n_sites_examined"]
     ref_bin = os.path.join(REPO, "oracle", "_ref", "count_transitions")
     if os.path.exists(ref_bin) and os.access(ref_bin, os.X_OK):
-        tmp = workdir or tempfile.mkdtemp(prefix="cherry_ref_")
         try:
-            names = write_text_rendering(syn, tmp)
             procs_n = min(cores, n_families)
             cmds = []
             for r in range(procs_n):
@@ -143,6 +166,7 @@ def cpu_reference_run(n_families, seed=0, workdir=None):
                 with open(fpath, "w") as f:
                     f.write(" ".join(fam_r))
                 out = os.path.join(tmp, f"out_{r}")
+                shutil.rmtree(out, ignore_errors=True)
                 os.makedirs(out, exist_ok=True)
                 cmds.append([ref_bin, os.path.join(tmp, "tree_dir"), os.path.join(tmp, "msa_dir"),
                              os.path.join(tmp, "site_rates_dir"), str(len(fam_r)), str(N_STATES),
@@ -160,12 +184,12 @@ def cpu_reference_run(n_families, seed=0, workdir=None):
             total = sum(read_count_matrices_text(os.path.join(tmp, f"out_{r}", "result.txt"))[2]
                         for r in range(procs_n))
             # the C++ program reads branch lengths as float32: compare totals only loosely
-            exp = count_batch_oracle(as_count_batch(syn), grid, N_STATES, False)
-            if abs(total.sum() - exp.sum()) > 1e-3 * exp.sum():
+            if "oracle_total" not in syn:
+                syn["oracle_total"] = float(count_batch_oracle(as_count_batch(syn), grid, N_STATES, False).sum())
+            if abs(total.sum() - syn["oracle_total"]) > 1e-3 * syn["oracle_total"]:
                 raise RuntimeError("reference output disagrees with the oracle on the sample")
         finally:
-            if workdir is None:
-                shutil.rmtree(tmp, ignore_errors=True)
+            pass
         kind, used = "reference", procs_n
         sample = (f"{n_families} of the workload's families ({examined} transitions), unmodified reference "
                   f"C++ program, {procs_n} processes on the reference's family striping, text parsing included")
@@ -194,24 +218,19 @@ def text_e2e_run(n_families, seed=0, reps=3):
 
     cores = os.cpu_count() or 1
     grid = quantization_grid()
-    syn = synthetic_lg(n_families, N_SEQS, N_SITES, N_CATS, seed=seed, device="cpu")
-    tmp = tempfile.mkdtemp(prefix="cherry_txt_")
-    try:
-        names = write_text_rendering(syn, tmp)
-        best, ingest_s = float("inf"), 0.0
-        for _ in range(reps + 1):  # first pass warms the page cache and the CUDA context
-            t0 = time.perf_counter()
-            batch = build_lg_batch_native(os.path.join(tmp, "tree_dir"), os.path.join(tmp, "msa_dir"),
-                                          os.path.join(tmp, "site_rates_dir"), names, amino_acids, "cherry++",
-                                          True, n_threads=cores, pinned=True)
-            t1 = time.perf_counter()
-            count_lg_host(batch, grid, N_STATES, False)
-            t2 = time.perf_counter()
-            if t2 - t0 < best:
-                best, ingest_s = t2 - t0, t1 - t0
-            del batch
-    finally:
-        shutil.rmtree(tmp, ignore_errors=True)
+    syn, tmp, names = rendered_sample(n_families, seed)
+    best, ingest_s = float("inf"), 0.0
+    for _ in range(reps + 1):  # first pass warms the page cache and the CUDA context
+        t0 = time.perf_counter()
+        batch = build_lg_batch_native(os.path.join(tmp, "tree_dir"), os.path.join(tmp, "msa_dir"),
+                                      os.path.join(tmp, "site_rates_dir"), names, amino_acids, "cherry++",
+                                      True, n_threads=cores, pinned=True)
+        t1 = time.perf_counter()
+        count_lg_host(batch, grid, N_STATES, False)
+        t2 = time.perf_counter()
+        if t2 - t0 < best:
+            best, ingest_s = t2 - t0, t1 - t0
+        del batch
     examined = syn["n_sites_examined"]
     return {"value": examined / best, "unit": UNIT, "seconds": best, "seconds_ingest": ingest_s,
             "host_threads": cores,
@@ -224,9 +243,9 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_fam = args.cpu_families or max(32, 2 * cores)
+    n_fam = args.cpu_families or default_cpu_families()
     for _ in range(args.warmup):
-        cpu_reference_run(min(n_fam, max(8, cores)))
+        cpu_reference_run(n_fam)
     times, values, last = [], [], None
     for _ in range(args.steps):
         last = cpu_reference_run(n_fam)
@@ -378,7 +397,8 @@ def run_ours(args):
         del dev, syn, host
         torch.cuda.empty_cache()
         fit = bench_fit(device, lg_times=grid, lg_counts=counts,
-                        process_group=dist.group.WORLD if world > 1 else None)
+                        process_group=dist.group.WORLD if world > 1 else None,
+                        cpu_baseline=(world == 1 and not args.no_cpu_baseline))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -413,7 +433,7 @@ def run_ours(args):
         line["fit"] = fit
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_cpu_fam = args.cpu_families or max(32, 2 * cores)
+        n_cpu_fam = args.cpu_families or default_cpu_families()
         cb = cpu_reference_run(n_cpu_fam)
         cb.pop("seconds", None)
         line["cpu_baseline"] = cb

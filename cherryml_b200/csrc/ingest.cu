@@ -21,7 +21,6 @@
 #include <cstring>
 #include <string>
 #include <thread>
-#include <unordered_map>
 #include <vector>
 
 #include <fcntl.h>
@@ -137,30 +136,99 @@ long long header_count(Span line, const char* word, const std::string& what) {
   return n;
 }
 
-struct TreeData {
-  std::vector<std::string> names;
-  std::unordered_map<std::string, int> index;
-  std::vector<std::vector<std::pair<int, double>>> children;  // edge-line order
-  std::vector<int> parent;
+// Open-addressing hash map from a byte span (a name inside a file buffer) to an int: no
+// allocation per key, which is what dominated the std::unordered_map<std::string, ...> version.
+class SpanMap {
+ public:
+  explicit SpanMap(size_t expected) {
+    size_t cap = 16;
+    while (cap < 2 * expected + 2) cap <<= 1;
+    keys_.assign(cap, Span{nullptr, 0});
+    vals_.assign(cap, -1);
+    mask_ = cap - 1;
+  }
+  // returns the value already stored for `k`, or stores `v` and returns -1
+  int insert(Span k, int v) {
+    size_t i = hash(k) & mask_;
+    while (vals_[i] >= 0) {
+      if (keys_[i].n == k.n && memcmp(keys_[i].p, k.p, k.n) == 0) return vals_[i];
+      i = (i + 1) & mask_;
+    }
+    keys_[i] = k;
+    vals_[i] = v;
+    return -1;
+  }
+  void set(Span k, int v) {  // insert or overwrite (dict semantics: the last one wins)
+    size_t i = hash(k) & mask_;
+    while (vals_[i] >= 0) {
+      if (keys_[i].n == k.n && memcmp(keys_[i].p, k.p, k.n) == 0) { vals_[i] = v; return; }
+      i = (i + 1) & mask_;
+    }
+    keys_[i] = k;
+    vals_[i] = v;
+  }
+  int find(Span k) const {
+    size_t i = hash(k) & mask_;
+    while (vals_[i] >= 0) {
+      if (keys_[i].n == k.n && memcmp(keys_[i].p, k.p, k.n) == 0) return vals_[i];
+      i = (i + 1) & mask_;
+    }
+    return -1;
+  }
+
+ private:
+  static size_t hash(Span k) {
+    uint64_t h = 1469598103934665603ull;  // FNV-1a
+    for (size_t i = 0; i < k.n; ++i) h = (h ^ (unsigned char)k.p[i]) * 1099511628211ull;
+    return (size_t)(h ^ (h >> 29));
+  }
+  std::vector<Span> keys_;
+  std::vector<int> vals_;
+  size_t mask_;
 };
 
-TreeData parse_tree(const std::string& path, bool f32) {
-  const std::string text = read_file(path);
-  const std::vector<Span> lines = strip_lines(text);
-  TreeData t;
+struct TreeData {
+  std::string text;         // the file; names are spans into it
+  std::vector<Span> names;
+  std::vector<int> first_child, next_sibling, last_child;  // children in edge-line order
+  std::vector<double> length;                              // of the edge to the parent
+  std::vector<int> parent;
+  std::vector<int> n_children;
+};
+
+// "u v length" with exactly two single spaces (Python's line.split(" ") giving 3 tokens)
+bool split3(Span line, Span* u, Span* v, Span* w) {
+  const char* sp1 = (const char*)memchr(line.p, ' ', line.n);
+  if (!sp1) return false;
+  const size_t rest = line.n - (size_t)(sp1 + 1 - line.p);
+  const char* sp2 = (const char*)memchr(sp1 + 1, ' ', rest);
+  if (!sp2) return false;
+  const size_t rest2 = line.n - (size_t)(sp2 + 1 - line.p);
+  if (memchr(sp2 + 1, ' ', rest2)) return false;
+  *u = Span{line.p, (size_t)(sp1 - line.p)};
+  *v = Span{sp1 + 1, (size_t)(sp2 - sp1 - 1)};
+  *w = Span{sp2 + 1, rest2};
+  return true;
+}
+
+void parse_tree(const std::string& path, bool f32, TreeData* tp) {
+  TreeData& t = *tp;
+  t.text = read_file(path);
+  const std::vector<Span> lines = strip_lines(t.text);
   const long long n = header_count(lines[0], "nodes", "Tree file: " + path + " should start with '[num_nodes] nodes'");
   if ((long long)lines.size() < n + 2) die("Tree file: " + path + " is truncated");
+  SpanMap index((size_t)n);
   t.names.reserve((size_t)n);
-  for (long long i = 1; i <= n; ++i) {
-    std::string name = lines[(size_t)i].str();
-    auto it = t.index.find(name);
-    if (it == t.index.end()) {  // a repeated name is one node (dict semantics)
-      t.index.emplace(name, (int)t.names.size());
-      t.names.push_back(std::move(name));
-    }
-  }
-  t.children.resize(t.names.size());
-  t.parent.assign(t.names.size(), -1);
+  for (long long i = 1; i <= n; ++i)
+    if (index.insert(lines[(size_t)i], (int)t.names.size()) < 0)  // a repeated name is one node
+      t.names.push_back(lines[(size_t)i]);
+  const size_t nn = t.names.size();
+  t.first_child.assign(nn, -1);
+  t.next_sibling.assign(nn, -1);
+  t.last_child.assign(nn, -1);
+  t.length.assign(nn, 0.0);
+  t.parent.assign(nn, -1);
+  t.n_children.assign(nn, 0);
   const long long m = header_count(lines[(size_t)n + 1], "edges",
                                    "Tree file: " + path + " should have line '[num_edges] edges' at position " +
                                        std::to_string(n + 1));
@@ -168,21 +236,23 @@ TreeData parse_tree(const std::string& path, bool f32) {
     die("Tree file: " + path + " should have " + std::to_string(m) + " edges, but it has " +
         std::to_string((long long)lines.size() - n - 2) + " edges instead.");
   for (long long i = n + 2; i < n + 2 + m; ++i) {
-    std::vector<Span> tok = split_space(lines[(size_t)i]);
+    Span su, sv, sw;
     double len = 0.0;
-    if (tok.size() != 3 || !parse_double(tok[2], f32, &len))
+    if (!split3(lines[(size_t)i], &su, &sv, &sw) || !parse_double(sw, f32, &len))
       die("Tree file: " + path + " should have line '[u] [v] [length]' at position " + std::to_string(i) +
           ", but it had line: '" + lines[(size_t)i].str() + "'");
-    auto iu = t.index.find(tok[0].str()), iv = t.index.find(tok[1].str());
-    if (iu == t.index.end() || iv == t.index.end())
-      die("In Tree file " + path + ": " + tok[0].str() + " and " + tok[1].str() + " should be nodes in the tree");
-    if (t.parent[(size_t)iv->second] >= 0)
-      die("Node " + tok[1].str() + " already has a parent, cannot also have parent " + tok[0].str() +
+    const int u = index.find(su), v = index.find(sv);
+    if (u < 0 || v < 0)
+      die("In Tree file " + path + ": " + su.str() + " and " + sv.str() + " should be nodes in the tree");
+    if (t.parent[(size_t)v] >= 0)
+      die("Node " + sv.str() + " already has a parent, cannot also have parent " + su.str() +
           " - graph is not a tree.");
-    t.children[(size_t)iu->second].push_back({iv->second, len});
-    t.parent[(size_t)iv->second] = iu->second;
+    t.parent[(size_t)v] = u;
+    t.length[(size_t)v] = len;
+    if (t.last_child[(size_t)u] < 0) t.first_child[(size_t)u] = v; else t.next_sibling[(size_t)t.last_child[(size_t)u]] = v;
+    t.last_child[(size_t)u] = v;
+    ++t.n_children[(size_t)u];
   }
-  return t;
 }
 
 struct Pair {
@@ -205,28 +275,30 @@ std::vector<Pair> extract_pairs(const TreeData& t, const std::string& mode, cons
     std::vector<double> res_dist((size_t)n, 0.0);
     std::vector<std::pair<int, bool>> stack;
     stack.push_back({root, false});
-    std::vector<int> leaves_under;
+    std::vector<int> leaves_under, kids;
     std::vector<double> dists_under;
+    pairs.reserve((size_t)n / 4 + 1);
     while (!stack.empty()) {
       auto [v, expanded] = stack.back();
       stack.pop_back();
-      const auto& ch = t.children[(size_t)v];
-      if (ch.empty()) {
+      if (t.first_child[(size_t)v] < 0) {
         res_leaf[(size_t)v] = v;
         res_dist[(size_t)v] = 0.0;
         continue;
       }
       if (!expanded) {
         stack.push_back({v, true});
-        for (auto it = ch.rbegin(); it != ch.rend(); ++it) stack.push_back({it->first, false});
+        kids.clear();
+        for (int c = t.first_child[(size_t)v]; c >= 0; c = t.next_sibling[(size_t)c]) kids.push_back(c);
+        for (auto it = kids.rbegin(); it != kids.rend(); ++it) stack.push_back({*it, false});
         continue;
       }
       leaves_under.clear();
       dists_under.clear();
-      for (const auto& c : ch) {
-        if (res_leaf[(size_t)c.first] >= 0) {
-          leaves_under.push_back(res_leaf[(size_t)c.first]);
-          dists_under.push_back(res_dist[(size_t)c.first] + c.second);
+      for (int c = t.first_child[(size_t)v]; c >= 0; c = t.next_sibling[(size_t)c]) {
+        if (res_leaf[(size_t)c] >= 0) {
+          leaves_under.push_back(res_leaf[(size_t)c]);
+          dists_under.push_back(res_dist[(size_t)c] + t.length[(size_t)c]);
         }
       }
       for (size_t i = 0; i + 1 < leaves_under.size(); i += 2)
@@ -239,18 +311,20 @@ std::vector<Pair> extract_pairs(const TreeData& t, const std::string& mode, cons
       }
     }
     size_t n_leaves = 0;
-    for (int v = 0; v < n; ++v) n_leaves += t.children[(size_t)v].empty() ? 1 : 0;
+    for (int v = 0; v < n; ++v) n_leaves += t.first_child[(size_t)v] < 0 ? 1 : 0;
     if (pairs.size() != n_leaves / 2)
       die("cherry++ produced " + std::to_string(pairs.size()) + " pairs for " + std::to_string(n_leaves) + " leaves");
   } else if (mode == "cherry") {
     for (int v = 0; v < n; ++v) {
-      const auto& ch = t.children[(size_t)v];
-      if (ch.size() == 2 && t.children[(size_t)ch[0].first].empty() && t.children[(size_t)ch[1].first].empty())
-        pairs.push_back(Pair{ch[0].first, ch[1].first, ch[0].second + ch[1].second});
+      if (t.n_children[(size_t)v] != 2) continue;
+      const int c0 = t.first_child[(size_t)v], c1 = t.next_sibling[(size_t)c0];
+      if (t.first_child[(size_t)c0] < 0 && t.first_child[(size_t)c1] < 0)
+        pairs.push_back(Pair{c0, c1, t.length[(size_t)c0] + t.length[(size_t)c1]});
     }
   } else if (mode == "edge") {
     for (int v = 0; v < n; ++v)
-      for (const auto& c : t.children[(size_t)v]) pairs.push_back(Pair{v, c.first, c.second});
+      for (int c = t.first_child[(size_t)v]; c >= 0; c = t.next_sibling[(size_t)c])
+        pairs.push_back(Pair{v, c, t.length[(size_t)c]});
   } else {
     die("Unknown edge_or_cherry: '" + mode + "'");
   }
@@ -259,18 +333,20 @@ std::vector<Pair> extract_pairs(const TreeData& t, const std::string& mode, cons
 
 struct MsaData {
   std::string text;
-  std::unordered_map<std::string, Span> seqs;
+  std::vector<Span> lines;  // name / sequence lines alternate
+  SpanMap index{0};         // name -> index of its sequence line
 };
 
 void parse_msa(const std::string& path, MsaData* m) {
   m->text = read_file(path);
-  const std::vector<Span> lines = strip_lines(m->text);
+  m->lines = strip_lines(m->text);
+  const std::vector<Span>& lines = m->lines;
   if (lines.size() % 2 != 0) die("The MSA at " + path + " should have an even number of lines");
-  m->seqs.reserve(lines.size());
+  m->index = SpanMap(lines.size() / 2);
   for (size_t i = 0; i + 1 < lines.size(); i += 2) {
     if (lines[i].n == 0 || lines[i].p[0] != '>')
       die("MSA at " + path + ": at line " + std::to_string(i) + " expected '>[seq_name]' but found " + lines[i].str());
-    m->seqs[std::string(lines[i].p + 1, lines[i].n - 1)] = lines[i + 1];
+    m->index.set(Span{lines[i].p + 1, lines[i].n - 1}, (int)(i + 1));
   }
 }
 
@@ -367,7 +443,8 @@ void rows_for_pairs(const std::vector<Pair>& pairs, int n_nodes, std::vector<int
 
 void process_family(const Job& job, const std::string& fam, FamilyOut* out) {
   const std::string tree_path = job.tree_dir + "/" + fam + ".txt";
-  const TreeData tree = parse_tree(tree_path, job.f32);
+  TreeData tree;
+  parse_tree(tree_path, job.f32, &tree);
   const std::vector<Pair> pairs = extract_pairs(tree, job.mode, tree_path);
   std::vector<int> row_nodes;
   rows_for_pairs(pairs, (int)tree.names.size(), &row_nodes, out);
@@ -376,10 +453,10 @@ void process_family(const Job& job, const std::string& fam, FamilyOut* out) {
   // sequences of the rows
   std::vector<Span> seqs(row_nodes.size());
   for (size_t r = 0; r < row_nodes.size(); ++r) {
-    auto it = msa.seqs.find(tree.names[(size_t)row_nodes[r]]);
-    if (it == msa.seqs.end())
-      die("Family " + fam + ": node '" + tree.names[(size_t)row_nodes[r]] + "' of the tree is not in the MSA");
-    seqs[r] = it->second;
+    const int li = msa.index.find(tree.names[(size_t)row_nodes[r]]);
+    if (li < 0)
+      die("Family " + fam + ": node '" + tree.names[(size_t)row_nodes[r]].str() + "' of the tree is not in the MSA");
+    seqs[r] = msa.lines[(size_t)li];
   }
   const size_t n_rows = seqs.size();
   const size_t L_msa = n_rows ? seqs[0].n : 0;

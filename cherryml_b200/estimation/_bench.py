@@ -96,8 +96,36 @@ def timed_fit(times, counts: torch.Tensor, num_epochs: int, mask=None, process_g
     return out
 
 
+def cpu_fit_baseline(times, counts: torch.Tensor, num_epochs_full: int, epochs_timed: int) -> Dict:
+    """The reference's CPU fit on this box's host cores, same counts: the torch-CPU port of
+    rate.py + trainer.py (oracle/fit_oracle.py; in fp32 -- the reference's arithmetic -- it
+    reproduces the unmodified reference run bit for bit), all host threads, JTT-IPW init.
+    A bounded number of epochs is timed and scaled linearly to the full run (epochs are
+    identical work)."""
+    import os
+
+    from oracle.fit_oracle import fit_oracle
+
+    cores = os.cpu_count() or 1
+    old = torch.get_num_threads()
+    torch.set_num_threads(cores)
+    try:
+        init = jtt_ipw_from_counts(times, counts)
+        c = counts.cpu().numpy()
+        fit_oracle(times, c, None, init, 0.1, 1, dtype=torch.float32)  # warm-up (thread pools)
+        t0 = time.perf_counter()
+        fit_oracle(times, c, None, init, 0.1, epochs_timed, dtype=torch.float32)
+        dt = time.perf_counter() - t0
+    finally:
+        torch.set_num_threads(old)
+    return {"kind": "port", "cores": cores, "seconds_per_epoch": dt / epochs_timed,
+            "seconds_extrapolated": dt / epochs_timed * num_epochs_full,
+            "sample": f"{epochs_timed} of {num_epochs_full} epochs timed (torch CPU, fp32 expm as the reference, "
+                      f"{cores} threads), scaled linearly"}
+
+
 def bench_fit(device, lg_times=None, lg_counts: Optional[torch.Tensor] = None, num_epochs: int = 500,
-              co_families: int = 4096, process_group=None) -> Dict:
+              co_families: int = 4096, process_group=None, cpu_baseline: bool = False) -> Dict:
     from ..counting._device import count_raw, sorted_grid, symmetrize
     from ..synthetic import as_device_batch, quantization_grid, synthetic_co, synthetic_lg
 
@@ -185,4 +213,10 @@ def bench_fit(device, lg_times=None, lg_counts: Optional[torch.Tensor] = None, n
                       "frac": co["tflops_executed"] / peak,
                       "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)"}
     out["coevo_400x400"] = co
+    if cpu_baseline and rank == 0:
+        try:
+            out["lg_20x20"]["cpu_baseline"] = cpu_fit_baseline(lg_times, lg_counts, num_epochs, 100)
+            out["coevo_400x400"]["cpu_baseline"] = cpu_fit_baseline(grid, co_counts, num_epochs, 2)
+        except Exception as e:  # the extra measurement must not cost the bench line
+            out["cpu_baseline_error"] = str(e)[:200]
     return out
