@@ -50,6 +50,8 @@ struct GemmTask {
   double* C;
   const int* cond;  // active iff cond == nullptr || *cond > level
   int term_begin, n_terms, accumulate, level;
+  int ksplit = 0;        // > 0: this task's own split-K factor (<= the launch's grid.z)
+  int partial_off = -1;  // >= 0: index of this task's first partial matrix (else blockIdx.y * ksplit)
 };
 struct Group {
   int task_begin, n_tasks, ksplit;
@@ -207,9 +209,12 @@ gemm_tasks_kernel(const GemmTask* __restrict__ tasks, const GemmTerm* __restrict
   const int m0 = (blockIdx.x / tiles_n) * BT, n0 = (blockIdx.x % tiles_n) * BT;
   const int total = task.n_terms * (Sp / BK);
   const int z = blockIdx.z;
+  const int launch_ksplit = ksplit;
+  if (task.ksplit > 0) ksplit = task.ksplit;  // tasks of one launch may split K differently
+  if (z >= ksplit) return;
+  const size_t pbase = task.partial_off >= 0 ? (size_t)task.partial_off : (size_t)blockIdx.y * launch_ksplit;
   const int c_begin = (int)((long long)total * z / ksplit), c_end = (int)((long long)total * (z + 1) / ksplit);
-  double* out = (ksplit == 1) ? task.C
-                              : partial + ((size_t)blockIdx.y * ksplit + z) * (size_t)Sp * Sp;
+  double* out = (ksplit == 1) ? task.C : partial + (pbase + z) * (size_t)Sp * Sp;
   gemm_tile([&](int idx) { return terms[task.term_begin + idx]; }, Sp, m0, n0, c_begin, c_end, smem, out,
             (ksplit == 1) && task.accumulate);
   if (ksplit == 1 || arrive == nullptr) return;
@@ -227,7 +232,7 @@ gemm_tasks_kernel(const GemmTask* __restrict__ tasks, const GemmTerm* __restrict
   if (!s_last) return;
   __threadfence();
   const size_t n_p = (size_t)Sp * Sp;
-  const double* base = partial + (size_t)blockIdx.y * ksplit * n_p;
+  const double* base = partial + pbase * n_p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const int wq = warp & 3, rbase = (wq >> 1) * 40, cbase = (wq & 1) * 40;
   if (warp >= 4) return;
@@ -337,7 +342,10 @@ __global__ void splitk_reduce_kernel(const GemmTask* __restrict__ tasks, int ksp
                                      const double* __restrict__ partial) {
   const GemmTask task = tasks[blockIdx.y];
   if (task.cond != nullptr && *task.cond <= task.level) return;
-  const double* base = partial + (size_t)blockIdx.y * ksplit * n_p;
+  const size_t pbase = task.partial_off >= 0 ? (size_t)task.partial_off : (size_t)blockIdx.y * ksplit;
+  if (task.ksplit > 0) ksplit = task.ksplit;
+  if (ksplit == 1) return;  // the GEMM wrote (or accumulated into) C itself
+  const double* base = partial + pbase * n_p;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n_p; e += (size_t)gridDim.x * blockDim.x) {
     double v = task.accumulate ? task.C[e] : 0.0;
     for (int z = 0; z < ksplit; ++z) v += base[(size_t)z * n_p + e];
@@ -831,6 +839,7 @@ struct Plan {
   int slots_per_bucket;   // chain slots 1..kSStore+1
   int loss_blocks;
   int n_partial;
+  bool n_partial_overflow = false;
   std::vector<GemmTask> tasks;   // device pointers filled relative to base
   std::vector<GemmTerm> terms;
   std::vector<Group> pow_fwd, sq_fwd, sq_bwd, pow_bwd;
@@ -938,14 +947,22 @@ void make_plan(Plan& p, int S, int K, char* base) {
   for (int li = (int)bases.size() - 1; li >= 0; --li) {
     const int b = bases[li];
     const int rmax = (b + b <= kDeg) ? b : kDeg - b;
-    Group g1 = begin_group();
+    // The two kinds of products of a level only read adjoints of HIGHER powers and write
+    // different ones (Pbar_r, r < b, vs Pbar_b), so they go into ONE launch; each task splits
+    // K by its own length (the Pbar_b task concatenates up to b + 1 products).
+    Group g = begin_group();
+    int n_small = 0;
     for (int r = 1; r <= rmax; ++r)
-      if (r != b) add_task(g1, Pbar(r), nullptr, 0, 1, {GemmTerm{Pj(b), Pbar(b + r), 1, 0}});
-    if (g1.n_tasks) {
-      g1.ksplit = choose_ksplit(g1.n_tasks, p.tiles, cpt);
-      p.pow_bwd.push_back(g1);
-    }
-    Group g2 = begin_group();
+      if (r != b) ++n_small;
+    const int ks_small = n_small ? choose_ksplit(n_small, p.tiles, cpt) : 1;
+    int poff = 0;
+    for (int r = 1; r <= rmax; ++r)
+      if (r != b) {
+        add_task(g, Pbar(r), nullptr, 0, 1, {GemmTerm{Pj(b), Pbar(b + r), 1, 0}});
+        p.tasks.back().ksplit = ks_small;
+        p.tasks.back().partial_off = poff;
+        poff += ks_small;
+      }
     {
       GemmTask t;
       t.C = Pbar(b); t.cond = nullptr; t.level = 0; t.accumulate = 1;
@@ -953,11 +970,15 @@ void make_plan(Plan& p, int S, int K, char* base) {
       for (int r = 1; r <= rmax; ++r) p.terms.push_back(GemmTerm{Pbar(b + r), Pj(r), 0, 1});
       if (rmax == b) p.terms.push_back(GemmTerm{Pj(b), Pbar(2 * b), 1, 0});
       t.n_terms = (int)p.terms.size() - t.term_begin;
+      t.ksplit = choose_ksplit(1, p.tiles, cpt * t.n_terms);
+      t.partial_off = poff;
+      poff += t.ksplit;
       p.tasks.push_back(t);
-      g2.n_tasks = 1;
-      g2.ksplit = choose_ksplit(1, p.tiles, cpt * t.n_terms);
+      g.n_tasks++;
+      g.ksplit = t.ksplit > ks_small ? t.ksplit : ks_small;
     }
-    p.pow_bwd.push_back(g2);
+    if (poff > p.n_partial) p.n_partial_overflow = true;
+    p.pow_bwd.push_back(g);
   }
 }
 
@@ -965,7 +986,9 @@ int launch_group(const Plan& p, const Group& g, char* base, cudaStream_t stream)
   const GemmTask* tasks = reinterpret_cast<const GemmTask*>(base + p.off_tasks) + g.task_begin;
   const GemmTerm* terms = reinterpret_cast<const GemmTerm*>(base + p.off_terms);
   double* partial = reinterpret_cast<double*>(base + p.off_partial);
-  if (g.ksplit > 1 && g.n_tasks * g.ksplit > p.n_partial)
+  const GemmTask* host_tasks = p.tasks.data() + g.task_begin;
+  const bool own_offsets = g.n_tasks > 0 && !p.tasks.empty() && host_tasks[0].partial_off >= 0;
+  if (p.n_partial_overflow || (!own_offsets && g.ksplit > 1 && g.n_tasks * g.ksplit > p.n_partial))
     return cherry::fail(CHERRY_ELIMIT, "fit_large: split-K partial buffer too small");
   const size_t smem = (size_t)NSTAGE * 2 * TILE_ELEMS * sizeof(double);
   dim3 grid(p.tiles, g.n_tasks, g.ksplit);
