@@ -262,12 +262,17 @@ struct SqSchedule {
   int queue[2];                        // work counters: forward, backward
   int n_levels;                        // max_k s_k
   int level_off[kSStore + 1];          // prefix sums of active buckets per level
-  int pad[4];
-  // followed in memory by: int active[kSStore][K]; int done_fwd[K][kSStore]; int done_bwd[K][kSStore + 1]
+  int ksplit;                          // split-K factor of every tile (few active buckets: more CTAs per tile)
+  int pad[3];
+  // followed in memory by: int active[kSStore][K]; int done_fwd[K][kSStore]; int done_bwd[K][kSStore + 1];
+  // int rank[K] (position of bucket k in level 0's list); int tile_arrive[K][tiles]
 };
 __device__ __forceinline__ int* sq_active(SqSchedule* s) { return reinterpret_cast<int*>(s + 1); }
 __device__ __forceinline__ int* sq_done_fwd(SqSchedule* s, int K) { return sq_active(s) + kSStore * K; }
 __device__ __forceinline__ int* sq_done_bwd(SqSchedule* s, int K) { return sq_done_fwd(s, K) + kSStore * K; }
+__device__ __forceinline__ int* sq_rank(SqSchedule* s, int K) { return sq_done_bwd(s, K) + (kSStore + 1) * K; }
+__device__ __forceinline__ int* sq_tile_arrive(SqSchedule* s, int K) { return sq_rank(s, K) + K; }
+constexpr int kSqPartialSlots = 96;  // matrices in the split-K partial buffer (Plan::n_partial)
 
 // Bounded spin (about a second): a scheduling bug must surface as an error flag, not as a hung GPU.
 __device__ __forceinline__ void wait_counter(const int* ctr, int target, int* status_flag) {
@@ -289,24 +294,59 @@ template <bool BWD>
 __global__ void __launch_bounds__(GEMM_THREADS)
 squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__ s_arr, int K, int Sp,
                          double* __restrict__ X0, double* __restrict__ chain, int slots_per_bucket,
-                         int* __restrict__ status_flag) {
+                         double* __restrict__ partial, int* __restrict__ status_flag) {
   extern __shared__ double smem[];
-  __shared__ int s_item;
+  __shared__ int s_item, s_last;
   const int tiles_n = Sp / BT, tiles = tiles_n * tiles_n;
   const size_t n_p = (size_t)Sp * Sp;
   const int n_levels = sched->n_levels;
   const int total_buckets = sched->level_off[n_levels];
-  const int total_items = total_buckets * tiles;
+  const int ksplit = sched->ksplit;
+  const int total_items = total_buckets * tiles * ksplit;
   const int* active = sq_active(sched);
   int* done_fwd = sq_done_fwd(sched, K);
   int* done_bwd = sq_done_bwd(sched, K);
+  const int* rank = sq_rank(sched, K);
+  int* tile_arrive = sq_tile_arrive(sched, K);
+  // With few active buckets a tile is split over `ksplit` CTAs (a lone CTA runs one 80x80x400
+  // tile at a third of the SM's DMMA rate).  Every CTA writes its partial tile; the one that
+  // arrives last adds them in z order (so the result does not depend on who is last), writes
+  // the tile and moves the bucket's completion counter.
+  auto finish_tile = [&](int k, int tile, int m0, int n0, double* out) -> bool {
+    if (ksplit == 1) return true;
+    __threadfence();
+    __syncthreads();
+    int* ctr = tile_arrive + rank[k] * tiles + tile;
+    if (threadIdx.x == 0) {
+      const int old = atomicAdd(ctr, 1);
+      s_last = (old == ksplit - 1);
+      if (s_last) *ctr = 0;  // ready for the next level / launch
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    const double* pb = partial + (size_t)rank[k] * ksplit * n_p;
+    for (int e = threadIdx.x; e < BT * BT / 2; e += GEMM_THREADS) {
+      const int r = e / (BT / 2), c2 = (e - r * (BT / 2)) * 2;
+      const size_t pos = (size_t)(m0 + r) * Sp + n0 + c2;
+      double2 v = make_double2(0.0, 0.0);
+      for (int zz = 0; zz < ksplit; ++zz) {
+        const double2 pz = __ldcg(reinterpret_cast<const double2*>(pb + (size_t)zz * n_p + pos));
+        v.x += pz.x;
+        v.y += pz.y;
+      }
+      *reinterpret_cast<double2*>(out + pos) = v;
+    }
+    return true;
+  };
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) s_item = atomicAdd(&sched->queue[BWD ? 1 : 0], 1);
     __syncthreads();
     const int item = s_item;
     if (item >= total_items) return;
-    const int bidx_linear = item / tiles, tile = item - bidx_linear * tiles;
+    const int z = item % ksplit, item_t = item / ksplit;
+    const int bidx_linear = item_t / tiles, tile = item_t - bidx_linear * tiles;
     // forward walks the levels upwards, backward downwards
     const int pos = BWD ? (total_buckets - 1 - bidx_linear) : bidx_linear;
     int level = 0;
@@ -318,7 +358,10 @@ squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__
     if (!BWD) {
       if (level > 0) wait_counter(done_fwd + k * kSStore + (level - 1), tiles, status_flag);
       const GemmTerm t0{Xi, Xi, 0, 0};
-      gemm_tile([&](int) { return t0; }, Sp, m0, n0, 0, Sp / BK, smem, out, false);
+      const int total = Sp / BK;
+      double* dst = ksplit == 1 ? out : partial + ((size_t)rank[k] * ksplit + z) * n_p;
+      gemm_tile([&](int) { return t0; }, Sp, m0, n0, total * z / ksplit, total * (z + 1) / ksplit, smem, dst, false);
+      if (!finish_tile(k, tile, m0, n0, out)) continue;
       __threadfence();  // every thread publishes its part of the tile before the counter moves
       __syncthreads();
       if (threadIdx.x == 0) atomicAdd(done_fwd + k * kSStore + level, 1);
@@ -329,7 +372,11 @@ squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__
       // done_bwd[k][l] counts finished tiles of backward level l of bucket k
       if (level + 1 < s_arr[k]) wait_counter(done_bwd + k * (kSStore + 1) + (level + 1), tiles, status_flag);
       const GemmTerm t0{Xb, Xi, 0, 1}, t1{Xi, Xb, 1, 0};
-      gemm_tile([&](int idx) { return idx == 0 ? t0 : t1; }, Sp, m0, n0, 0, 2 * (Sp / BK), smem, out, false);
+      const int total = 2 * (Sp / BK);
+      double* dst = ksplit == 1 ? out : partial + ((size_t)rank[k] * ksplit + z) * n_p;
+      gemm_tile([&](int idx) { return idx == 0 ? t0 : t1; }, Sp, m0, n0, total * z / ksplit,
+                total * (z + 1) / ksplit, smem, dst, false);
+      if (!finish_tile(k, tile, m0, n0, out)) continue;
       __threadfence();
       __syncthreads();
       if (threadIdx.x == 0) atomicAdd(done_bwd + k * (kSStore + 1) + level, 1);
@@ -389,7 +436,8 @@ __global__ void build_B_kernel(const double* __restrict__ Q, int S, int Sp, doub
 // one CTA: per bucket s_k, tau_k and the weights w[k][j] = e^{-tau mu} tau^j / j!, j = 0..m
 __global__ void coef_kernel(const double* __restrict__ t, int K, LargeScalars* __restrict__ sc,
                             int* __restrict__ s_arr, double* __restrict__ w, double* __restrict__ tau_arr,
-                            int* __restrict__ status_flag, SqSchedule* __restrict__ sched) {
+                            int* __restrict__ status_flag, SqSchedule* __restrict__ sched, int tiles,
+                            int n_ctas) {
   const double norm = __longlong_as_double((long long)sc->norm_bits);
   const double mu = sc->mu;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
@@ -418,6 +466,9 @@ __global__ void coef_kernel(const double* __restrict__ t, int K, LargeScalars* _
   int* done_bwd = sq_done_bwd(sched, K);
   for (int i = threadIdx.x; i < K * kSStore; i += blockDim.x) done_fwd[i] = 0;
   for (int i = threadIdx.x; i < K * (kSStore + 1); i += blockDim.x) done_bwd[i] = 0;
+  int* rank = sq_rank(sched, K);
+  int* tile_arrive = sq_tile_arrive(sched, K);
+  for (int i = threadIdx.x; i < K * tiles; i += blockDim.x) tile_arrive[i] = 0;
   __shared__ int ss[256], level_n[kSStore];
   for (int k = threadIdx.x; k < K; k += blockDim.x) ss[k] = s_arr[k];
   __syncthreads();
@@ -425,7 +476,10 @@ __global__ void coef_kernel(const double* __restrict__ t, int K, LargeScalars* _
     const int lvl = threadIdx.x;
     int n = 0;
     for (int k = 0; k < K; ++k)
-      if (ss[k] > lvl) active[lvl * K + n++] = k;
+      if (ss[k] > lvl) {
+        if (lvl == 0) rank[k] = n;
+        active[lvl * K + n++] = k;
+      }
     level_n[lvl] = n;
   }
   __syncthreads();
@@ -441,6 +495,16 @@ __global__ void coef_kernel(const double* __restrict__ t, int K, LargeScalars* _
     sched->n_levels = n_levels;
     sched->queue[0] = 0;
     sched->queue[1] = 0;
+    // split K so that the widest level keeps about n_ctas CTAs busy (at most 4 ways, and within
+    // the partial buffer: one slot per (active bucket, z))
+    int ks = 1;
+    if (level_n[0] > 0) {
+      ks = n_ctas / (level_n[0] * tiles);
+      if (ks > 4) ks = 4;
+      if (ks * level_n[0] > kSqPartialSlots) ks = kSqPartialSlots / level_n[0];
+      if (ks < 1) ks = 1;
+    }
+    sched->ksplit = ks;
   }
 }
 
@@ -875,7 +939,8 @@ void make_plan(Plan& p, int S, int K, char* base) {
   auto carve = [&](size_t bytes) { size_t o = off; off = align256(off + bytes); return o; };
   p.off_scalars = carve(sizeof(LargeScalars));
   p.off_arrive = carve(sizeof(int) * 64 * (size_t)p.tiles);
-  p.off_sched = carve(sizeof(SqSchedule) + sizeof(int) * ((size_t)kSStore * K * 2 + (size_t)K * (kSStore + 1)));
+  p.off_sched = carve(sizeof(SqSchedule) + sizeof(int) * ((size_t)kSStore * K * 2 + (size_t)K * (kSStore + 1) +
+                                                            (size_t)K + (size_t)K * p.tiles));
   p.off_s = carve(sizeof(int) * K);
   p.off_tau = carve(sizeof(double) * K);
   p.off_w = carve(sizeof(double) * K * (kDeg + 1));
@@ -890,7 +955,7 @@ void make_plan(Plan& p, int S, int K, char* base) {
   p.off_X0 = carve(mat * K);
   p.off_chain = carve(mat * K * p.slots_per_bucket);
   // split-K partial buffers: sized below once the groups are known (upper bound first)
-  p.n_partial = 96;
+  p.n_partial = kSqPartialSlots;
   p.off_partial = carve(mat * p.n_partial);
   p.total_bytes = off;
   if (!base) return;
@@ -1125,7 +1190,8 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   build_B_kernel<<<(p.Sp + 7) / 8, EW_THREADS, 0, stream>>>(a.Q, a.S, p.Sp, P, sc);
   CHERRY_LAUNCH_CHECK("build_B_kernel");
   SqSchedule* sched = reinterpret_cast<SqSchedule*>(base + p.off_sched);
-  coef_kernel<<<1, 256, 0, stream>>>(a.t, a.K, sc, s_arr, w, tau, a.status_flag, sched);
+  coef_kernel<<<1, 256, 0, stream>>>(a.t, a.K, sc, s_arr, w, tau, a.status_flag, sched, p.tiles,
+                                     (KGROUPS == 1 ? 2 : 1) * sm_count());
   CHERRY_LAUNCH_CHECK("coef_kernel");
   mark("build_B+coef", stream);
   for (const Group& g : p.pow_fwd)
@@ -1163,7 +1229,8 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
       if ((rc = launch_group(p, g, base, stream))) return rc;
   } else {
     squaring_dataflow_kernel<false><<<persistent_grid, GEMM_THREADS, gemm_smem, stream>>>(
-        sched, s_arr, a.K, p.Sp, X0, chain, p.slots_per_bucket, a.status_flag);
+        sched, s_arr, a.K, p.Sp, X0, chain, p.slots_per_bucket, reinterpret_cast<double*>(base + p.off_partial),
+        a.status_flag);
     CHERRY_LAUNCH_CHECK("squaring_dataflow_kernel<fwd>");
   }
   mark("squarings_fwd", stream);
@@ -1185,7 +1252,8 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
       if ((rc = launch_group(p, g, base, stream))) return rc;
   } else {
     squaring_dataflow_kernel<true><<<persistent_grid, GEMM_THREADS, gemm_smem, stream>>>(
-        sched, s_arr, a.K, p.Sp, X0, chain, p.slots_per_bucket, a.status_flag);
+        sched, s_arr, a.K, p.Sp, X0, chain, p.slots_per_bucket, reinterpret_cast<double*>(base + p.off_partial),
+        a.status_flag);
     CHERRY_LAUNCH_CHECK("squaring_dataflow_kernel<bwd>");
   }
   mark("squarings_bwd", stream);
