@@ -34,7 +34,19 @@ TILE_DTYPE = np.dtype(
     ],
     align=True,
 )
-assert FAM_DESC_DTYPE.itemsize == 32 and TILE_DTYPE.itemsize == 16
+FC_FAMILY_DTYPE = np.dtype(
+    [
+        ("msa_off", np.int64),
+        ("n_seqs", np.int32),
+        ("row_stride", np.int32),
+        ("n_sites", np.int32),
+        ("cherry_off", np.int32),
+        ("site_off", np.int32),
+        ("seq_off", np.int32),
+    ],
+    align=True,
+)
+assert FAM_DESC_DTYPE.itemsize == 32 and TILE_DTYPE.itemsize == 16 and FC_FAMILY_DTYPE.itemsize == 32
 
 NO_BUCKET = 255
 # The skip code of a residue byte is the number of states S itself (bytes are in [0, S]).
@@ -74,6 +86,10 @@ _SIGNATURES = {
     "cherry_ingest_co": (c_int, [c_char_p, c_char_p, c_char_p, _P, c_int, _P, c_int, c_char_p, c_int, c_int,
                                  c_int, c_int, _P]),
     "cherry_ingest_free": (None, [_P]),
+    "cherry_fc_scratch_bytes": (ctypes.c_size_t, [c_int64, c_int64, c_int]),
+    "cherry_fc_pair": (c_int, [_P, _P, c_int, c_int64, c_int, ctypes.c_uint32, _P, _P, _P, _P, ctypes.c_size_t, _P]),
+    "cherry_fc_ble": (c_int, [_P, _P, c_int, c_int64, c_int, _P, _P, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P,
+                              _P, ctypes.c_size_t, _P]),
     "cherry_count_lg_host": (
         c_int,
         [_P, c_int64, _P, c_int, _P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int,

@@ -177,3 +177,108 @@ def cached_computation(
         return wrapper
 
     return decorator
+
+
+def cached_parallel_computation(
+    parallel_arg: str,
+    exclude_args: List[str] = [],
+    exclude_args_if_default: List[str] = [],
+    output_dirs: List[str] = [],
+    write_extra_log_files: bool = False,
+):
+    """Per-item caching (reference ``caching/_cached_parallel_computation.py:162-440``): the call
+    is keyed on everything except ``parallel_arg``; item ``v`` counts as computed when every
+    output dir holds ``v.txt`` and ``v.success``; the function is called with the remaining
+    items only, its outputs are made read-only and given success tokens."""
+
+    def decorator(func):
+        params = signature(func).parameters
+        named = list(exclude_args) + list(exclude_args_if_default) + [parallel_arg] + list(output_dirs)
+        for arg in named:
+            if arg not in params:
+                raise CacheUsageError(
+                    f"{arg} is not an argument to '{func.__name__}'. Fix the "
+                    f"arguments of the caching decorator."
+                )
+        if len(set(named)) != len(named):
+            raise CacheUsageError(
+                "All the function arguments specified in the caching decorator for "
+                f"'{func.__name__}' should be distinct. You provided: {named} "
+            )
+
+        @wraps(func)
+        def wrapper(*args, **kwargs):
+            if len(args) > 0:
+                raise CacheUsageError(
+                    f"Please call {func.__name__} with keyword arguments only. "
+                    f"Positional arguments are not allowed for caching reasons."
+                )
+            kwargs[parallel_arg] = sorted(set(kwargs[parallel_arg]))
+            cache_dir = get_cache_dir()
+            if cache_dir is None:
+                return func(**kwargs)
+            unhashed = list(exclude_args) + [parallel_arg] + list(output_dirs)
+            given_dirs = {od: kwargs.get(od) for od in output_dirs}
+            for od in output_dirs:
+                kwargs[od] = None
+            binding = signature(func).bind(**kwargs)
+            binding.apply_defaults()
+            for arg in exclude_args_if_default:
+                if binding.arguments[arg] == params[arg].default:
+                    unhashed.append(arg)
+            func_dir = _caching_dir(func, unhashed, kwargs, cache_dir)
+            for od in output_dirs:
+                kwargs[od] = given_dirs[od] if given_dirs[od] is not None else os.path.join(func_dir, od)
+            res = {od: kwargs[od] for od in output_dirs}
+
+            def paths(od, v):
+                return os.path.join(kwargs[od], v + ".txt"), os.path.join(kwargs[od], v + ".success")
+
+            todo = [
+                v for v in kwargs[parallel_arg]
+                if not all(os.path.exists(p) for od in output_dirs for p in paths(od, v))
+            ]
+            kwargs[parallel_arg] = todo
+            for od in output_dirs:
+                os.makedirs(kwargs[od], exist_ok=True)
+                if write_extra_log_files:
+                    log = os.path.join(kwargs[od], "_function_binding.log")
+                    if not os.path.exists(log):
+                        logged = dict(kwargs)
+                        for k in unhashed:
+                            if k in logged:
+                                logged[k] = None
+                        b = signature(func).bind(**logged)
+                        b.apply_defaults()
+                        with open(log, "w") as f:
+                            f.write(str(b))
+                        _make_read_only(log)
+            if todo:
+                if _READ_ONLY:
+                    raise CacheUsageError("Cache is in read only mode! Will not call function.")
+                for v in todo:
+                    for od in output_dirs:
+                        for p in paths(od, v):
+                            if os.path.exists(p):
+                                os.chmod(p, 0o666)
+                                os.remove(p)
+                func(**kwargs)
+                for od in output_dirs:
+                    for v in todo:
+                        out, _ = paths(od, v)
+                        if not os.path.exists(out):
+                            raise CacheUsageError(
+                                f"function {func.__name__} should have created and written "
+                                f"output to {out} but the file does not exist."
+                            )
+                for od in output_dirs:
+                    for v in todo:
+                        out, tok = paths(od, v)
+                        _make_read_only(out)
+                        with open(tok, "w") as f:
+                            f.write("SUCCESS\n")
+            return res
+
+        return wrapper
+
+    return decorator

@@ -9,6 +9,7 @@ same mathematical object; here both are served by the CUDA expm of the fit
 accepted for compatibility; the computation always runs on a CUDA device.
 """
 import ctypes
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -98,3 +99,17 @@ def chain_product(rate_matrix_1: np.ndarray, rate_matrix_2: np.ndarray) -> np.nd
     n = rate_matrix_1.shape[0]
     eye = np.eye(n)
     return np.kron(rate_matrix_1, eye) + np.kron(eye, rate_matrix_2)
+
+
+_DATA_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "rate_matrices")
+
+
+def get_lg_path() -> str:
+    """The LG rate matrix (Le & Gascuel 2008), a data file shipped with the package (reference
+    ``_markov_chain.py`` ``get_lg_path``: ``data/rate_matrices/lg.txt``)."""
+    return os.path.join(_DATA_DIR, "lg.txt")
+
+
+def get_equ_path() -> str:
+    """The uniform-exchangeability rate matrix (reference ``get_equ_path``)."""
+    return os.path.join(_DATA_DIR, "equ.txt")

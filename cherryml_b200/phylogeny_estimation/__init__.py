@@ -1,0 +1,2 @@
+"""Tree estimation on the GPU: FastCherries (reference ``cherryml/phylogeny_estimation``)."""
+from ._fast_cherries import fast_cherries, fast_cherries_device  # noqa: F401

@@ -1,0 +1,369 @@
+"""FastCherries tree estimation on the GPU.
+
+``fast_cherries`` keeps the signature, defaults, caching behaviour and output files of the
+reference's ``cherryml/phylogeny_estimation/_fast_cherries.py:191-281``; the C++ program it
+shells out to (``FastCherries/fast_cherries.cpp``) is replaced by two CUDA kernels
+(``cherry_fc_pair``, ``cherry_fc_ble``) that process all families of the call in one launch
+each.  The small set-up computations of ``fast_cherries.cpp:47-215`` (quantization grid, rate
+categories, prior weights) are host scalars; the table of log transition probabilities
+(``io_helpers.cpp:150-176``) is computed on the device with ``cherry_expm_batched``.
+
+There is no CPU fallback: without the CUDA library / a GPU the stage raises.
+"""
+import ctypes
+import math
+import os
+import time
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..caching import cached_parallel_computation
+from ..io import Tree, read_rate_matrix, write_tree
+from ..markov_chain import expm_batched
+
+
+# ----------------------------------------------------------------------------- set-up scalars
+
+def quantization_grid(center: float, step: float, num_steps: int) -> np.ndarray:
+    """``compute_quantization_points`` (io_helpers.cpp:178-194): a chain of multiplications /
+    divisions in x87 extended precision starting at the centre, narrowed to fp64 at the end."""
+    if np.finfo(np.longdouble).nmant != 63:
+        raise _lib.CherryError("FastCherries grid needs an 80-bit numpy longdouble (x86-64)")
+    ext = np.zeros(2 * num_steps + 1, dtype=np.longdouble)
+    ext[num_steps] = center
+    ratio = np.longdouble(step)
+    for i in range(1, num_steps + 1):
+        ext[num_steps + i] = ext[num_steps + i - 1] * ratio
+        ext[num_steps - i] = ext[num_steps - i + 1] / ratio
+    return np.asarray(ext, dtype=np.float64)
+
+
+def ble_rate_categories(num_rate_categories: int) -> np.ndarray:
+    """Geometric ladder from 1/R to R (fast_cherries.cpp:205-213); a single category is 1."""
+    R = int(num_rate_categories)
+    if R < 1:
+        raise ValueError("num_rate_categories must be >= 1")
+    if R == 1:
+        return np.ones(1)
+    first = 1.0 / R
+    ratio = math.pow(R / first, 1.0 / (R - 1))
+    cats = [first]
+    while len(cats) < R:
+        cats.append(cats[-1] * ratio)
+    return np.array(cats)
+
+
+def _log_gamma(a: float) -> float:
+    # Pike & Hill, CACM Algorithm 291 (what fast_cherries.cpp:47-66 uses): push the argument
+    # up to >= 7 by the recurrence, then Stirling's series.
+    shift = 0.0
+    x = a
+    if x < 7:
+        prod = 1.0
+        z = x
+        while z < 7:
+            prod *= z
+            z += 1.0
+        x = z
+        shift = -math.log(prod)
+    inv2 = 1.0 / (x * x)
+    series = (((-.000595238095238 * inv2 + .000793650793651) * inv2 - .002777777777778) * inv2 + .083333333333333) / x
+    return shift + (x - 0.5) * math.log(x) - x + .918938533204673 + series
+
+
+def _gamma_cdf(x: float, shape: float) -> float:
+    """Regularised lower incomplete gamma P(shape, x) by Bhattacharjee's AS 32 (series for small
+    x, continued fraction otherwise) with the 1e-8 stopping rule of fast_cherries.cpp:69-128."""
+    tol, big = 1e-8, 1e30
+    if x == 0:
+        return 0.0
+    if x < 0 or shape <= 0:
+        return -1.0
+    scale = math.exp(shape * math.log(x) - x - _log_gamma(shape))
+    if x <= 1 or x < shape:
+        total, term, denom = 1.0, 1.0, shape
+        while True:
+            denom += 1
+            term *= x / denom
+            total += term
+            if term <= tol:
+                return total * (scale / shape)
+    a = 1 - shape
+    b = a + x + 1
+    n = 0.0
+    p = [1.0, x, x + 1, x * b]
+    cur = p[2] / p[3]
+    while True:
+        a += 1
+        b += 2
+        n += 1
+        an = a * n
+        p4 = b * p[2] - an * p[0]
+        p5 = b * p[3] - an * p[1]
+        if p5 != 0:
+            nxt = p4 / p5
+            gap = abs(cur - nxt)
+            if gap <= tol and gap <= tol * nxt:
+                return 1 - scale * cur
+            cur = nxt
+        p = [p[2], p[3], p4, p5]
+        if abs(p4) >= big:
+            p = [v / big for v in p]
+
+
+def initial_rate_weights(cats: np.ndarray) -> np.ndarray:
+    """CDF of gamma(shape 3, mean 1) at the geometric midpoints of neighbouring categories, last
+    entry 1 (fast_cherries.cpp:137-160)."""
+    shape = 3.0
+    w = [_gamma_cdf(math.sqrt(cats[i - 1] * cats[i]) * shape, shape) for i in range(1, len(cats))]
+    return np.array(w + [1.0])
+
+
+# ----------------------------------------------------------------------------- MSAs -> residue rows
+
+def parse_msa_like_cpp(path: str) -> Tuple[List[str], List[bytes]]:
+    """``read_msa`` of io_helpers.cpp:35-74: a line starting with '>' names a sequence, the
+    line after it is the sequence."""
+    with open(path, "rb") as f:
+        lines = f.read().split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    names: List[str] = []
+    seqs: List[bytes] = []
+    i = 0
+    while i < len(lines):
+        ln = lines[i]
+        if ln[:1] == b">":
+            if i + 1 >= len(lines):
+                break
+            names.append(ln[1:].decode("utf-8", "replace"))
+            seqs.append(lines[i + 1])
+            i += 2
+        else:
+            i += 1
+    return names, seqs
+
+
+def encode_families(msa_paths: Sequence[str], alphabet: Sequence[str]):
+    """-> (names per family, flat uint8 residue buffer, FC_FAMILY_DTYPE array)."""
+    S = len(alphabet)
+    lut = bytearray([S]) * 256
+    for i, ch in enumerate(alphabet):
+        if len(ch) != 1:
+            raise ValueError("FastCherries alphabets are single characters")
+        lut[ord(ch)] = i
+    lut = bytes(lut)
+    fams = np.zeros(len(msa_paths), dtype=_lib.FC_FAMILY_DTYPE)
+    all_names, blocks = [], []
+    off = cherry_off = site_off = seq_off = 0
+    for f, path in enumerate(msa_paths):
+        names, seqs = parse_msa_like_cpp(path)
+        n = len(names)
+        L = len(seqs[0]) if n else 0
+        if any(len(s) != L for s in seqs):
+            raise ValueError(f"MSA {path}: sequences of different lengths")
+        if n > 65535:
+            raise _lib.CherryError(f"MSA {path}: more than 65535 sequences")
+        stride = max(16, (L + 15) // 16 * 16)
+        rows = np.full((n, stride), S, dtype=np.uint8)
+        if n and L:
+            rows[:, :L] = np.frombuffer(b"".join(s.translate(lut) for s in seqs), dtype=np.uint8).reshape(n, L)
+        fams[f] = (off, n, stride, L, cherry_off, site_off, seq_off)
+        blocks.append(rows.reshape(-1))
+        all_names.append(names)
+        off += n * stride
+        cherry_off += n // 2
+        site_off += L
+        seq_off += n
+    buf = np.concatenate(blocks) if blocks else np.zeros(0, dtype=np.uint8)
+    return all_names, buf, fams
+
+
+# ----------------------------------------------------------------------------- device pipeline
+
+def log_transition_table(Q: np.ndarray, grid: np.ndarray, cats: np.ndarray, device) -> torch.Tensor:
+    """fp64 [K][R][S][S] on the device: log P + (log P)^T, P = expm(q_k * rate_r * Q)."""
+    K, R, S = len(grid), len(cats), Q.shape[0]
+    exponents = (grid[:, None] * cats[None, :]).reshape(-1)
+    logp = torch.log(expm_batched(Q, exponents, device))
+    return (logp + logp.transpose(1, 2)).reshape(K, R, S, S).contiguous()
+
+
+def fast_cherries_device(msa: np.ndarray, fams: np.ndarray, S: int, sym_table: torch.Tensor, priors: np.ndarray,
+                         weights: np.ndarray, seed: int, max_iters: int, device="cuda") -> Dict[str, np.ndarray]:
+    """Runs both kernels on an encoded batch.  Returns host arrays: pair_a, pair_b (row indices
+    per cherry, reference emission order), unpaired (per family), len_idx (per cherry),
+    site_cat (per site), iters (per family), and the two kernel times in ms."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    n_fams = len(fams)
+    total_seqs = int(fams["n_seqs"].sum())
+    total_sites = int(fams["n_sites"].sum())
+    n_cherries = int((fams["n_seqs"] // 2).sum())
+    K, R = int(sym_table.shape[0]), int(sym_table.shape[1])
+    with torch.cuda.device(dev):
+        d_msa = torch.from_numpy(msa).to(dev)
+        d_fams = torch.from_numpy(fams.view(np.uint8).reshape(-1)).to(dev)
+        pair_a = torch.empty(max(1, n_cherries), dtype=torch.int32, device=dev)
+        pair_b = torch.empty_like(pair_a)
+        len_idx = torch.zeros_like(pair_a)
+        unpaired = torch.empty(max(1, n_fams), dtype=torch.int32, device=dev)
+        iters = torch.zeros_like(unpaired)
+        site_cat = torch.zeros(max(1, total_sites), dtype=torch.int32, device=dev)
+        nbytes = int(lib.cherry_fc_scratch_bytes(total_seqs, total_sites, n_fams))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        d_priors = torch.from_numpy(np.ascontiguousarray(priors, dtype=np.float64)).to(dev)
+        d_weights = torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float64)).to(dev)
+        stream = _lib.current_stream_ptr()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        _lib.check(
+            lib.cherry_fc_pair(_lib.ptr(d_msa), _lib.ptr(d_fams), n_fams, total_seqs, S, seed & 0xFFFFFFFF,
+                               _lib.ptr(pair_a), _lib.ptr(pair_b), _lib.ptr(unpaired), _lib.ptr(scratch), nbytes,
+                               stream),
+            "cherry_fc_pair",
+        )
+        ev[1].record()
+        _lib.check(
+            lib.cherry_fc_ble(_lib.ptr(d_msa), _lib.ptr(d_fams), n_fams, total_sites, S, _lib.ptr(pair_a),
+                              _lib.ptr(pair_b), _lib.ptr(sym_table), K, R, _lib.ptr(d_priors), _lib.ptr(d_weights),
+                              int(max_iters), _lib.ptr(len_idx), _lib.ptr(site_cat), _lib.ptr(iters),
+                              _lib.ptr(scratch), nbytes, stream),
+            "cherry_fc_ble",
+        )
+        ev[2].record()
+        torch.cuda.synchronize()
+    return {
+        "pair_a": pair_a[:n_cherries].cpu().numpy(),
+        "pair_b": pair_b[:n_cherries].cpu().numpy(),
+        "unpaired": unpaired[:n_fams].cpu().numpy(),
+        "len_idx": len_idx[:n_cherries].cpu().numpy(),
+        "site_cat": site_cat[:total_sites].cpu().numpy(),
+        "iters": iters[:n_fams].cpu().numpy(),
+        "pair_ms": ev[0].elapsed_time(ev[1]),
+        "ble_ms": ev[1].elapsed_time(ev[2]),
+    }
+
+
+def normalise_lengths_and_rates(len_idx: np.ndarray, site_cat: np.ndarray, grid: np.ndarray, cats: np.ndarray):
+    """fast_cherries.cpp:268-279: site rates are rescaled to mean 1 (the mean is a left-to-right
+    fp64 sum) and the branch lengths absorb the factor."""
+    rates = cats[site_cat]
+    if len(rates) == 0:
+        return grid[len_idx], rates
+    mean = float(np.cumsum(rates)[-1]) / len(rates)
+    return grid[len_idx] * mean, rates / mean
+
+
+def _fixed17(x: float) -> str:
+    return "%.17f" % x  # std::fixed << std::setprecision(max_digits10)
+
+
+def cherries_tree(names: Sequence[str], pairs: Sequence[Tuple[int, int]], lengths: Sequence[float],
+                  unpaired: int) -> Tree:
+    """The star-of-cherries tree of _fast_cherries.py:121-141.  The reference round-trips the
+    lengths through the program's '%.17f' text output and builds the tree with ete3, whose new
+    nodes hang at distance 1.0 from their parent."""
+    tree = Tree()
+    tree.add_node("root")
+    for i, ((a, b), length) in enumerate(zip(pairs, lengths)):
+        half = float(_fixed17(length)) / 2.0
+        inner = "internal-" + str(i)
+        tree.add_node(inner)
+        tree.add_edge("root", inner, 1.0)
+        for leaf in (names[a], names[b]):
+            tree.add_node(leaf)
+            tree.add_edge(inner, leaf, half)
+    if unpaired >= 0:
+        tree.add_node(names[unpaired])
+        tree.add_edge("root", names[unpaired], 1.0)
+    return tree
+
+
+def _newick(names, pairs, lengths, unpaired) -> str:
+    parts = []
+    for i, ((a, b), length) in enumerate(zip(pairs, lengths)):
+        half = float(_fixed17(length)) / 2.0
+        parts.append("(%s:%g,%s:%g)internal-%d:1" % (names[a], half, names[b], half, i))
+    if unpaired >= 0:
+        parts.append("%s:1" % names[unpaired])
+    return "(" + ",".join(parts) + ");"
+
+
+@cached_parallel_computation(
+    parallel_arg="families",
+    exclude_args=["num_processes", "device"],
+    exclude_args_if_default=["_version"],
+    output_dirs=[
+        "output_tree_dir",
+        "output_site_rates_dir",
+        "output_likelihood_dir",
+    ],
+    write_extra_log_files=True,
+)
+def fast_cherries(
+    msa_dir: str,
+    families: List[str],
+    rate_matrix_path: str,
+    num_rate_categories: int,
+    max_iters: int,
+    num_processes: int,
+    _version="2",
+    output_tree_dir: Optional[str] = None,
+    output_site_rates_dir: Optional[str] = None,
+    output_likelihood_dir: Optional[str] = None,
+    remake=False,
+    quantization_grid_center=0.03,
+    quantization_grid_step=1.1,
+    quantization_grid_num_steps=64,
+    verbose=True,
+    seed=1234,
+    device: str = "cuda",
+) -> None:
+    """Same contract as the reference stage: per family ``<tree_dir>/<family>.txt`` (tree),
+    ``.newick``, ``.profiling``; ``<site_rates_dir>/<family>.txt``; ``<likelihood_dir>/<family>.txt``
+    (the constant 0.0).  ``num_processes`` and ``remake`` are accepted and ignored (one GPU
+    launch handles every family; there is no binary to rebuild)."""
+    for d in (output_tree_dir, output_site_rates_dir, output_likelihood_dir):
+        os.makedirs(d, exist_ok=True)
+    if not families:
+        return
+    t_start = time.time()
+    rate_matrix = read_rate_matrix(rate_matrix_path)
+    alphabet = list(rate_matrix.columns)
+    Q = rate_matrix.to_numpy(dtype=np.float64)
+    # the reference passes the grid parameters through str() on a command line
+    grid = quantization_grid(float(str(quantization_grid_center)), float(str(quantization_grid_step)),
+                             int(quantization_grid_num_steps))
+    cats = ble_rate_categories(num_rate_categories)
+    weights = initial_rate_weights(cats)
+    priors = np.array([2 * math.log(r) - 3 * r for r in cats])
+    names, msa, fams = encode_families([os.path.join(msa_dir, f + ".txt") for f in families], alphabet)
+    table = log_transition_table(Q, grid, cats, device)
+    out = fast_cherries_device(msa, fams, len(alphabet), table, priors, weights, int(seed), int(max_iters), device)
+    t_device = time.time() - t_start
+    for f, family in enumerate(families):
+        fam = fams[f]
+        c0, c1 = int(fam["cherry_off"]), int(fam["cherry_off"]) + int(fam["n_seqs"]) // 2
+        s0, s1 = int(fam["site_off"]), int(fam["site_off"]) + int(fam["n_sites"])
+        pairs = list(zip(out["pair_a"][c0:c1].tolist(), out["pair_b"][c0:c1].tolist()))
+        lengths, rates = normalise_lengths_and_rates(out["len_idx"][c0:c1], out["site_cat"][s0:s1], grid, cats)
+        unpaired = int(out["unpaired"][f])
+        write_tree(cherries_tree(names[f], pairs, lengths, unpaired), os.path.join(output_tree_dir, family + ".txt"))
+        with open(os.path.join(output_tree_dir, family + ".newick"), "w") as fh:
+            fh.write(_newick(names[f], pairs, lengths, unpaired))
+        with open(os.path.join(output_site_rates_dir, family + ".txt"), "w") as fh:
+            fh.write(f"{len(rates)} sites\n" + "".join(_fixed17(r) + " " for r in rates))
+        with open(os.path.join(output_likelihood_dir, family + ".txt"), "w") as fh:
+            fh.write(str(0.0))
+        share = t_device / len(families)
+        with open(os.path.join(output_tree_dir, family + ".profiling"), "w") as fh:
+            fh.write(
+                f"pairing_time: {out['pair_ms'] * 1e-3 / len(families)}\n"
+                f"ble_time: {out['ble_ms'] * 1e-3 / len(families)}\n"
+                f"cpp_time: {share}\n"
+                f"total_time: {(time.time() - t_start) / len(families)}"
+            )

@@ -29,6 +29,11 @@
  *                              torch.optim.Adam as configured at ratelearner.py:123-126.
  *   cherry_expm_batched        matrix_exponential_pytorch, markov_chain/_markov_chain.py
  *                              :22-53.
+ *   cherry_fc_pair             divide_and_pair(), phylogeny_estimation/FastCherries/
+ *                              pairing_algorithms.cpp:15-175 (called per family at
+ *                              fast_cherries.cpp:240-244).
+ *   cherry_fc_ble              ble(), FastCherries/branch_length_estimation.cpp:10-241
+ *                              (fast_cherries.cpp:258-266).
  */
 #ifndef CHERRYML_B200_H
 #define CHERRYML_B200_H
@@ -296,6 +301,49 @@ size_t cherry_gemm_desc_bytes(int batch);
  * (m-1) + sum_k s_k products of S x S matrices forward and twice that backward; bench.py uses
  * this to turn kernel time into executed FLOP/s.  Synchronises the device. */
 int cherry_fit_schedule(const cherry_fit_args* args, int* squarings_out, double* mu_out, int* degree_out);
+
+/* ------------------------------------------------------------------- FastCherries */
+
+/* One MSA family for the FastCherries kernels: ALL sequences of the MSA in file order, one
+ * row each, residue bytes as for counting (0..S-1, S = skip, rows padded with S).  32 bytes. */
+typedef struct cherry_fc_family {
+  int64_t msa_off;    /* byte offset of row 0 in the residue buffer (16-aligned) */
+  int32_t n_seqs;     /* rows */
+  int32_t row_stride; /* bytes per row, a multiple of 16 */
+  int32_t n_sites;    /* real sites (<= row_stride) */
+  int32_t cherry_off; /* first cherry of this family in pair_a/pair_b/len_idx:
+                         sum of floor(n_seqs / 2) over the families before it */
+  int32_t site_off;   /* first site of this family in site_cat: sum of n_sites before it */
+  int32_t seq_off;    /* sum of n_seqs over the families before it */
+} cherry_fc_family;
+
+/* Device scratch both FastCherries entry points need (they may share one buffer). */
+size_t cherry_fc_scratch_bytes(int64_t total_seqs, int64_t total_sites, int n_fams);
+
+/* Pairs the sequences of every family into floor(n_seqs / 2) cherries by recursive bisection
+ * around two far-apart pivots under the normalised Hamming distance over sites valid in both
+ * sequences.  pair_a/pair_b[fam.cherry_off + c] = row indices of the c-th cherry IN THE ORDER
+ * the reference emits them; unpaired[f] = the left-over row of an odd family, else -1.
+ * The random pivots are std::mt19937(seed) re-seeded per family, drawn like libstdc++'s
+ * std::uniform_int_distribution<size_t> (GCC >= 11).  Exact (integer) reproduction of
+ * divide_and_pair, FastCherries/pairing_algorithms.cpp:79-175. */
+int cherry_fc_pair(const uint8_t* msa, const cherry_fc_family* fams, int n_fams, int64_t total_seqs, int S,
+                   uint32_t seed, int32_t* pair_a, int32_t* pair_b, int32_t* unpaired, void* scratch,
+                   size_t scratch_bytes, void* stream);
+
+/* Branch-length and site-rate estimation by coordinate ascent for every family:
+ * len_idx[cherry] = index into the K-point quantization grid, site_cat[site] = index into the
+ * R rate categories, iters[f] = ascent iterations run (<= max_iters).
+ * sym_table: fp64 [K][R][S][S], log P + (log P)^T with P = expm(q_k * rate_r * Q);
+ * priors: [R] = 2 log(rate_r) - 3 rate_r; init_weights: [R] cumulative gamma-bin weights of the
+ * initial site-rate assignment (fast_cherries.cpp:137-160).  S <= 32, n_seqs <= 65535.
+ * Every likelihood sum is accumulated by one thread in the reference's order, so the
+ * decisions equal the reference's given the same table.
+ * Replaces ble(), FastCherries/branch_length_estimation.cpp:150-241. */
+int cherry_fc_ble(const uint8_t* msa, const cherry_fc_family* fams, int n_fams, int64_t total_sites, int S,
+                  const int32_t* pair_a, const int32_t* pair_b, const double* sym_table, int K, int R,
+                  const double* priors, const double* init_weights, int max_iters, int32_t* len_idx,
+                  int32_t* site_cat, int32_t* iters, void* scratch, size_t scratch_bytes, void* stream);
 
 #ifdef __cplusplus
 }

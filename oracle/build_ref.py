@@ -3,7 +3,10 @@
 * ``oracle/_build/libcount_oracle.so``  -- the C restatement ``oracle/count_encoded.c``.
 * ``oracle/_ref/count_transitions`` and ``oracle/_ref/count_co_transitions`` -- the UNMODIFIED
   reference counting programs, compiled from where they lie under /root/reference with a
-  five-function single-rank ``mpi.h`` stand-in (``oracle/mpishim/mpi.h``).  Built only when
+  five-function single-rank ``mpi.h`` stand-in (``oracle/mpishim/mpi.h``).
+* ``oracle/_ref/fast_cherries`` -- the UNMODIFIED reference FastCherries program
+  (phylogeny_estimation/FastCherries/*.cpp + its matrix_exponential/ sources) with the flags
+  of the reference's own Makefile (-std=c++11 -O3 -finline-functions -funroll-loops).  Built only when
   the reference checkout is present (the build container); the binaries are git-ignored and
   travel to the GPU box with the snapshot.  No reference source is copied into the repo.
 """
@@ -12,6 +15,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_COUNTING = "/root/reference/cherryml/counting"
+REF_FC = "/root/reference/cherryml/phylogeny_estimation/FastCherries"
 REF_DIR = os.path.join(HERE, "_ref")
 C_LIB = os.path.join(HERE, "_build", "libcount_oracle.so")
 
@@ -43,7 +47,22 @@ def build_reference_binaries() -> bool:
                     ["g++", "-std=c++11", "-O3", "-I", os.path.join(HERE, "mpishim"), "-o", out_path, src_path],
                     check=True,
                 )
-    return all(os.path.exists(os.path.join(REF_DIR, out)) for out in names)
+    fc_out = os.path.join(REF_DIR, "fast_cherries")
+    if os.path.isdir(REF_FC):
+        fc_src = [
+            os.path.join(REF_FC, f)
+            for f in (
+                "fast_cherries.cpp", "io_helpers.cpp", "pairing_algorithms.cpp", "branch_length_estimation.cpp",
+                "matrix_exponential/matrix_exponential.cpp", "matrix_exponential/r8lib.cpp",
+                "matrix_exponential/c8lib.cpp",
+            )
+        ]
+        if not _newer(fc_out, *fc_src):
+            subprocess.run(
+                ["g++", "-std=c++11", "-O3", "-finline-functions", "-funroll-loops", "-w", "-o", fc_out, *fc_src],
+                check=True,
+            )
+    return all(os.path.exists(os.path.join(REF_DIR, out)) for out in list(names) + ["fast_cherries"])
 
 
 if __name__ == "__main__":

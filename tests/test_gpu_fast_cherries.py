@@ -1,0 +1,172 @@
+"""FastCherries on the GPU (cherry_fc_pair / cherry_fc_ble through the C ABI) against
+(1) outputs of the UNMODIFIED reference program on the golden cases -- cherries, '%.17f'
+distances and site rates must be identical text -- and (2) the oracle on seeded batches of
+several families per launch, fed the SAME device-computed table: pairs, length indices, rate
+categories and iteration counts bit-exact."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from cherryml_b200 import _lib
+from cherryml_b200.io import read_site_rates, read_tree
+from cherryml_b200.phylogeny_estimation import _fast_cherries as fc
+from tests._fc_cases import expected_outputs, load_cases, msa_text, parse_rate_matrix
+
+CASES = load_cases()
+AA = "ARNDCQEGHILKMFPSTWYV"
+
+
+def _run_files(tmp_path, texts, alphabet, Q, R, max_iters, seed, num_steps):
+    paths = []
+    for i, t in enumerate(texts):
+        p = tmp_path / f"fam{i}.txt"
+        p.write_text(t)
+        paths.append(str(p))
+    grid = fc.quantization_grid(0.03, 1.1, num_steps)
+    cats = fc.ble_rate_categories(R)
+    weights = fc.initial_rate_weights(cats)
+    priors = np.array([2 * math.log(r) - 3 * r for r in cats])
+    names, msa, fams = fc.encode_families(paths, alphabet)
+    table = fc.log_transition_table(Q, grid, cats, "cuda:0")
+    before = _lib.launch_count()
+    out = fc.fast_cherries_device(msa, fams, len(alphabet), table, priors, weights, seed, max_iters, "cuda:0")
+    assert _lib.launch_count() - before == 2
+    return names, msa, fams, table, grid, cats, weights, out
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_matches_reference_program(case, tmp_path):
+    alphabet, Q = parse_rate_matrix(case["rate_matrix_text"])
+    names, msa, fams, table, grid, cats, weights, out = _run_files(
+        tmp_path, [msa_text(case)], alphabet, Q, case["num_rate_categories"], case["max_iters"], case["seed"],
+        case["num_steps"])
+    exp_cherries, exp_dist, exp_rates = expected_outputs(case)
+    got = [(names[0][a], names[0][b]) for a, b in zip(out["pair_a"], out["pair_b"])]
+    assert got == exp_cherries
+    lengths, rates = fc.normalise_lengths_and_rates(out["len_idx"], out["site_cat"], grid, cats)
+    assert ["%.17f" % x for x in lengths] == exp_dist
+    assert ["%.17f" % x for x in rates] == exp_rates
+    n = len(names[0])
+    assert (out["unpaired"][0] >= 0) == (n % 2 == 1)
+
+
+def _random_msa(rng, n, L, gap, mut):
+    root = rng.integers(0, 20, L)
+    rows = []
+    for _ in range(n):
+        r = rows[rng.integers(0, len(rows))].copy() if rows and rng.random() < 0.7 else root.copy()
+        flip = rng.random(L) < mut
+        r[flip] = rng.integers(0, 20, int(flip.sum()))
+        rows.append(r)
+    out = []
+    for i, r in enumerate(rows):
+        s = np.array(list(AA))[r]
+        s[rng.random(L) < gap] = "-"
+        out.append("".join(s))
+    return "".join(f">s{i}\n{s}\n" for i, s in enumerate(out))
+
+
+@pytest.mark.parametrize("R,max_iters", [(1, 50), (4, 50), (20, 50), (20, 2)])
+def test_batch_matches_oracle_on_same_table(tmp_path, R, max_iters):
+    from oracle import fast_cherries_oracle as fo
+
+    rng = np.random.default_rng(100 + R)
+    shapes = [(2, 16), (3, 15), (9, 33), (40, 100), (65, 64), (128, 301), (257, 48), (300, 17), (31, 500), (1, 20),
+              (512, 90)]
+    texts = [_random_msa(rng, n, L, gap=float(rng.uniform(0, 0.4)), mut=float(rng.uniform(0.02, 0.5)))
+             for n, L in shapes]
+    alphabet, Q = parse_rate_matrix(CASES[0]["rate_matrix_text"])
+    names, msa, fams, table, grid, cats, weights, out = _run_files(tmp_path, texts, alphabet, Q, R, max_iters, 99, 64)
+    sym = table.cpu().numpy()
+    for f, (n, L) in enumerate(shapes):
+        fam = fams[f]
+        rows = msa[int(fam["msa_off"]): int(fam["msa_off"]) + n * int(fam["row_stride"])].reshape(n, -1)[:, :L]
+        seqs = rows.astype(np.int64)
+        seqs[seqs == 20] = -1
+        c0, c1 = int(fam["cherry_off"]), int(fam["cherry_off"]) + n // 2
+        s0, s1 = int(fam["site_off"]), int(fam["site_off"]) + L
+        cherries = fo.divide_and_pair(seqs, 99)
+        assert list(zip(out["pair_a"][c0:c1].tolist(), out["pair_b"][c0:c1].tolist())) == cherries, (n, L)
+        paired = {v for c in cherries for v in c}
+        left = [i for i in range(n) if i not in paired]
+        assert int(out["unpaired"][f]) == (left[0] if left else -1)
+        if n < 2:
+            continue
+        # the oracle's ble() adds T + T^T itself: hand it half of the (exactly symmetric) device table
+        len_idx, site_cat, iters = _ble_on_sym(fo, seqs, cherries, sym, cats, weights, max_iters)
+        assert np.array_equal(out["len_idx"][c0:c1], len_idx), (n, L)
+        assert np.array_equal(out["site_cat"][s0:s1], site_cat), (n, L)
+        assert int(out["iters"][f]) == iters
+
+
+def _ble_on_sym(fo, seqs, cherries, sym, cats, weights, max_iters):
+    a = np.array([c[0] for c in cherries])
+    b = np.array([c[1] for c in cherries])
+    xa, xb = seqs[a], seqs[b]
+    site_cat = fo.initial_site_categories(seqs, weights, sym.shape[2])
+    len_idx = fo.branch_length_indices(xa, xb, sym, site_cat)
+    priors = np.array([2 * math.log(r) - 3 * r for r in cats])
+    match, iters = False, 0
+    while not match and max_iters:
+        site_cat = fo.site_rate_indices(xa, xb, sym, len_idx, priors)
+        new_len = fo.branch_length_indices(xa, xb, sym, site_cat)
+        match = bool(np.array_equal(new_len, len_idx))
+        len_idx = new_len
+        max_iters -= 1
+        iters += 1
+    return len_idx, site_cat, iters
+
+
+def test_device_table_close_to_scipy():
+    from oracle import fast_cherries_oracle as fo
+
+    alphabet, Q = parse_rate_matrix(CASES[0]["rate_matrix_text"])
+    grid = fc.quantization_grid(0.03, 1.1, 64)
+    cats = fc.ble_rate_categories(4)
+    dev = fc.log_transition_table(Q, grid, cats, "cuda:0").cpu().numpy()
+    T = fo.log_table_scipy(Q, grid, cats)
+    ref = T + np.swapaxes(T, 2, 3)
+    assert np.array_equal(dev, np.swapaxes(dev, 2, 3))  # exactly symmetric
+    assert np.max(np.abs(dev - ref) / np.abs(ref)) < 1e-10
+
+
+def test_stage_function_outputs_and_cache(tmp_path):
+    from cherryml_b200 import caching
+    from cherryml_b200.phylogeny_estimation import fast_cherries
+
+    case = next(c for c in CASES if c["name"] == "synthetic_n33_L100_R4")
+    msa_dir = tmp_path / "msas"
+    msa_dir.mkdir()
+    (msa_dir / "famA.txt").write_text(case["msa_text"])
+    (msa_dir / "famB.txt").write_text(next(c for c in CASES if c["name"] == "synthetic_n16_L48_R4")["msa_text"])
+    qp = tmp_path / "Q.txt"
+    qp.write_text(case["rate_matrix_text"])
+    caching.set_cache_dir(str(tmp_path / "cache"))
+    try:
+        kw = dict(msa_dir=str(msa_dir), families=["famB", "famA"], rate_matrix_path=str(qp), num_rate_categories=4,
+                  max_iters=50, num_processes=3, verbose=False)
+        res = fast_cherries(**kw)
+        before = _lib.launch_count()
+        res2 = fast_cherries(**kw)  # cached: nothing runs
+        assert res2 == res and _lib.launch_count() == before
+    finally:
+        caching.set_cache_dir(None)
+    exp_cherries, exp_dist, _ = expected_outputs(case)
+    assert open(os.path.join(res["output_site_rates_dir"], "famA.txt")).read() == case["site_rates_file"]
+    assert len(read_site_rates(os.path.join(res["output_site_rates_dir"], "famA.txt"))) == 100
+    tree = read_tree(os.path.join(res["output_tree_dir"], "famA.txt"))
+    inner = [v for v, _ in tree.children("root")]
+    assert inner[:16] == [f"internal-{i}" for i in range(16)] and len(inner) == 17  # 33 leaves: one left over
+    for i, (pair, d) in enumerate(zip(exp_cherries, exp_dist)):
+        kids = tree.children(f"internal-{i}")
+        assert tuple(k for k, _ in kids) == pair
+        assert all(length == float(d) / 2.0 for _, length in kids)
+    assert open(os.path.join(res["output_likelihood_dir"], "famA.txt")).read() == "0.0"
+    for d in res.values():
+        assert os.path.exists(os.path.join(d, "famA.success")) and os.path.exists(os.path.join(d, "famB.success"))
+    prof = open(os.path.join(res["output_tree_dir"], "famA.profiling")).read().split("\n")
+    assert [ln.split()[0] for ln in prof] == ["pairing_time:", "ble_time:", "cpp_time:", "total_time:"]
