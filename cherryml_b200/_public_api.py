@@ -1,17 +1,20 @@
-"""``cherryml_public_api`` and the two end-to-end pipelines, for the part of them that is the
-hot path: trees (and site rates) given -> count -> JTT-IPW -> fit -> rate matrix file.
+"""``cherryml_public_api`` and the two end-to-end pipelines:
+[FastCherries trees ->] count -> JTT-IPW -> fit -> rate matrix file.
 
 Same names, keyword arguments and defaults as the reference's
 ``cherryml/_cherryml_public_api.py:36-252`` and
-``cherryml/estimation_end_to_end/_cherry.py:209-445, 449-584``.  Tree estimation
-(FastTree / PhyML / FastCherries) is outside the hot path: when
-``tree_dir`` (and ``site_rates_dir`` for the LG model) is not given these functions raise
-``NotImplementedError`` instead of shelling out to a tree builder.
+``cherryml/estimation_end_to_end/_cherry.py:209-445, 449-584``.  Of the reference's three tree
+estimators only FastCherries is on the path this package implements (SURVEY.md section 8, row
+f3): with ``tree_estimator_name="FastCherries"`` trees and site rates are estimated on the GPU,
+iterated ``num_iterations`` times for the LG model like the reference does; FastTree / PhyML
+(external programs) raise ``NotImplementedError`` unless ``tree_dir`` (and ``site_rates_dir``
+for the LG model) are given.
 """
 import logging
 import os
 import tempfile
 import time
+from functools import partial
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -19,7 +22,9 @@ import numpy as np
 from . import caching
 from .counting import count_co_transitions, count_transitions, device_result
 from .estimation import jtt_ipw, quantized_transitions_mle
-from .io import read_contact_map, read_rate_matrix, write_contact_map, write_rate_matrix
+from .io import read_contact_map, read_rate_matrix, read_site_rates, write_contact_map, write_rate_matrix
+from .markov_chain import get_equ_path, get_lg_path
+from .phylogeny_estimation import fast_cherries
 from .utils import get_amino_acids, get_families
 
 logger = logging.getLogger(__name__)
@@ -74,10 +79,24 @@ def create_maximal_matching_contact_map(
 
 def _no_tree_estimator(what: str):
     raise NotImplementedError(
-        f"{what}: tree estimation is outside the hot path this package implements; run the "
-        "reference's tree estimator (FastTree / PhyML / FastCherries) and pass tree_dir"
-        " (and site_rates_dir for the LG model)."
+        f"{what}: of the reference's tree estimators only FastCherries is implemented here "
+        "(tree_estimator_name=\"FastCherries\"); FastTree and PhyML are external programs -- run "
+        "them with the reference and pass tree_dir (and site_rates_dir for the LG model)."
     )
+
+
+def _tree_estimation_runtime(tree_estimator_output_dirs: Dict, families: List[str], attribute: str) -> float:
+    """Sum over families of the `<attribute>_time:` line of ``<family>.profiling`` (reference
+    ``_cherry.py:157-191``)."""
+    total = 0.0
+    for family in families:
+        path = os.path.join(tree_estimator_output_dirs["output_tree_dir"], family + ".profiling")
+        if not os.path.exists(path):
+            continue
+        for line in open(path):
+            if line.startswith(attribute + "_time"):
+                total += float(line.split()[1])
+    return total
 
 
 def lg_end_to_end_with_cherryml_optimizer(
@@ -111,7 +130,7 @@ def lg_end_to_end_with_cherryml_optimizer(
             "tree_dir and site_rates_dir must be either both provided or none "
             f"provided. You provided: tree_dir={tree_dir} ; site_rates_dir={site_rates_dir}"
         )
-    if tree_dir is None or num_iterations != 1:
+    if tree_estimator is None and (tree_dir is None or num_iterations != 1):
         _no_tree_estimator("lg_end_to_end_with_cherryml_optimizer")
     if sites_subset_dir is not None:
         raise NotImplementedError("sites_subset_dir is not supported")
@@ -119,40 +138,70 @@ def lg_end_to_end_with_cherryml_optimizer(
     quantization_points = _quantization_points(
         quantization_grid_center, quantization_grid_step, quantization_grid_num_steps)
     res["quantization_points"] = quantization_points
-    res["tree_estimator_output_dirs_0"] = {"output_tree_dir": tree_dir, "output_site_rates_dir": site_rates_dir}
-    count_matrices_dir = count_transitions(
-        tree_dir=tree_dir, msa_dir=msa_dir, site_rates_dir=site_rates_dir, families=families,
-        amino_acids=alphabet[:], quantization_points=quantization_points, edge_or_cherry=edge_or_cherry,
-        num_processes=num_processes_counting, use_cpp_implementation=use_cpp_counting_implementation,
-        cpp_command_line_prefix=cpp_counting_command_line_prefix,
-        cpp_command_line_suffix=cpp_counting_command_line_suffix,
-    )["output_count_matrices_dir"]
-    res["count_matrices_dir_0"] = count_matrices_dir
-    res["time_counting"] = _runtime_from_profiling_file(os.path.join(count_matrices_dir, "profiling.txt"))
-    jtt_ipw_dir = jtt_ipw(
-        count_matrices_path=os.path.join(count_matrices_dir, "result.txt"), mask_path=None, use_ipw=True,
-        normalize=False,
-    )["output_rate_matrix_dir"]
-    res["jtt_ipw_dir_0"] = jtt_ipw_dir
-    res["time_jtt_ipw"] = _runtime_from_profiling_file(os.path.join(jtt_ipw_dir, "profiling.txt"))
-    if optimizer_initialization == "jtt-ipw":
-        initialization_path = os.path.join(jtt_ipw_dir, "result.txt")
-    elif optimizer_initialization == "random":
-        initialization_path = None
-    else:
-        raise ValueError(f"Unknown optimizer_initialization = {optimizer_initialization}")
-    rate_matrix_dir = quantized_transitions_mle(
-        count_matrices_path=os.path.join(count_matrices_dir, "result.txt"),
-        initialization_path=initialization_path, mask_path=None, stationary_distribution_path=None,
-        rate_matrix_parameterization="pande_reversible", device=optimizer_device,
-        learning_rate=learning_rate, num_epochs=num_epochs, do_adam=do_adam,
-        OMP_NUM_THREADS=num_processes_optimization, OPENBLAS_NUM_THREADS=num_processes_optimization,
-    )["output_rate_matrix_dir"]
-    res["rate_matrix_dir_0"] = rate_matrix_dir
-    res["time_optimization"] = _runtime_from_profiling_file(os.path.join(rate_matrix_dir, "profiling.txt"))
-    res["learned_rate_matrix_path"] = os.path.join(rate_matrix_dir, "result.txt")
-    res["time_tree_estimation"] = 0.0
-    res["total_cpu_time"] = res["time_counting"] + res["time_jtt_ipw"] + res["time_optimization"]
+    times = dict(tree=0.0, pairing=0.0, ble=0.0, counting=0.0, jtt_ipw=0.0, optimization=0.0)
+    is_a_pairer = False
+    current_estimate_rate_matrix_path = initial_tree_estimator_rate_matrix_path
+    tree_estimator_output_dirs: Dict = {}
+    for iteration in range(num_iterations):
+        if iteration == 0 and tree_dir is not None and site_rates_dir is not None:
+            tree_estimator_output_dirs = {"output_tree_dir": tree_dir, "output_site_rates_dir": site_rates_dir}
+        else:
+            tree_estimator_output_dirs = tree_estimator(
+                msa_dir=msa_dir, families=families, rate_matrix_path=current_estimate_rate_matrix_path,
+                num_processes=num_processes_tree_estimation,
+            )
+            is_a_pairer = True
+            times["tree"] += _tree_estimation_runtime(tree_estimator_output_dirs, families, "total")
+            times["pairing"] += _tree_estimation_runtime(tree_estimator_output_dirs, families, "pairing")
+            times["ble"] += _tree_estimation_runtime(tree_estimator_output_dirs, families, "ble")
+        res[f"tree_estimator_output_dirs_{iteration}"] = tree_estimator_output_dirs
+        count_matrices_dir = count_transitions(
+            tree_dir=tree_estimator_output_dirs["output_tree_dir"], msa_dir=msa_dir,
+            site_rates_dir=tree_estimator_output_dirs["output_site_rates_dir"], families=families,
+            amino_acids=alphabet[:], quantization_points=quantization_points, edge_or_cherry=edge_or_cherry,
+            num_processes=num_processes_counting, use_cpp_implementation=use_cpp_counting_implementation,
+            cpp_command_line_prefix=cpp_counting_command_line_prefix,
+            cpp_command_line_suffix=cpp_counting_command_line_suffix,
+        )["output_count_matrices_dir"]
+        res[f"count_matrices_dir_{iteration}"] = count_matrices_dir
+        times["counting"] += _runtime_from_profiling_file(os.path.join(count_matrices_dir, "profiling.txt"))
+        jtt_ipw_dir = jtt_ipw(
+            count_matrices_path=os.path.join(count_matrices_dir, "result.txt"), mask_path=None, use_ipw=True,
+            normalize=False,
+        )["output_rate_matrix_dir"]
+        res[f"jtt_ipw_dir_{iteration}"] = jtt_ipw_dir
+        times["jtt_ipw"] += _runtime_from_profiling_file(os.path.join(jtt_ipw_dir, "profiling.txt"))
+        if optimizer_initialization == "jtt-ipw":
+            initialization_path = os.path.join(jtt_ipw_dir, "result.txt")
+        elif optimizer_initialization == "equ":
+            initialization_path = get_equ_path()
+        elif optimizer_initialization == "random":
+            initialization_path = None
+        else:
+            raise ValueError(f"Unknown optimizer_initialization = {optimizer_initialization}")
+        rate_matrix_dir = quantized_transitions_mle(
+            count_matrices_path=os.path.join(count_matrices_dir, "result.txt"),
+            initialization_path=initialization_path, mask_path=None, stationary_distribution_path=None,
+            rate_matrix_parameterization="pande_reversible", device=optimizer_device,
+            learning_rate=learning_rate, num_epochs=num_epochs, do_adam=do_adam,
+            OMP_NUM_THREADS=num_processes_optimization, OPENBLAS_NUM_THREADS=num_processes_optimization,
+        )["output_rate_matrix_dir"]
+        res[f"rate_matrix_dir_{iteration}"] = rate_matrix_dir
+        times["optimization"] += _runtime_from_profiling_file(os.path.join(rate_matrix_dir, "profiling.txt"))
+        current_estimate_rate_matrix_path = os.path.join(rate_matrix_dir, "result.txt")
+    res["learned_rate_matrix_path"] = current_estimate_rate_matrix_path
+    res["all_site_rates"] = [
+        read_site_rates(os.path.join(tree_estimator_output_dirs["output_site_rates_dir"], family + ".txt"))
+        for family in sorted(families)
+    ]
+    res["time_tree_estimation"] = times["tree"]
+    if is_a_pairer:
+        res["time_pairing"] = times["pairing"]
+        res["time_ble"] = times["ble"]
+    res["time_counting"] = times["counting"]
+    res["time_jtt_ipw"] = times["jtt_ipw"]
+    res["time_optimization"] = times["optimization"]
+    res["total_cpu_time"] = times["tree"] + times["counting"] + times["jtt_ipw"] + times["optimization"]
     res["profiling_str"] = (
         "CherryML runtimes:\n"
         f"time_tree_estimation (without parallelization): {res['time_tree_estimation']}\n"
@@ -161,6 +210,8 @@ def lg_end_to_end_with_cherryml_optimizer(
         f"time_optimization: {res['time_optimization']}\n"
         f"total_cpu_time: {res['total_cpu_time']}\n"
     )
+    if is_a_pairer:
+        res["profiling_str"] += f"time_pairing {res['time_pairing']}\ntime_ble {res['time_ble']}"
     return res
 
 
@@ -191,12 +242,17 @@ def coevolution_end_to_end_with_cherryml_optimizer(
     tree_dir: Optional[str] = None,
     alphabet: List[str] = get_amino_acids(),
 ) -> Dict:
-    if tree_dir is None:
+    if tree_dir is None and tree_estimator is None:
         _no_tree_estimator("coevolution_end_to_end_with_cherryml_optimizer")
     res: Dict = {}
     quantization_points = _quantization_points(
         quantization_grid_center, quantization_grid_step, quantization_grid_num_steps)
     res["quantization_points"] = quantization_points
+    if tree_dir is None:
+        tree_dir = tree_estimator(
+            msa_dir=msa_dir, families=families, rate_matrix_path=initial_tree_estimator_rate_matrix_path,
+            num_processes=num_processes_tree_estimation,
+        )["output_tree_dir"]
     res["tree_estimator_output_dirs_0"] = {"output_tree_dir": tree_dir}
     mdnc = minimum_distance_for_nontrivial_contact
     if use_maximal_matching:
@@ -280,9 +336,18 @@ def cherryml_public_api(
     caching.set_cache_dir(cache_dir)
     if families is None:
         families = get_families(msa_dir)
+    if initial_tree_estimator_rate_matrix_path is None:
+        initial_tree_estimator_rate_matrix_path = get_lg_path()
+    if tree_estimator_name == "FastCherries":
+        tree_estimator = partial(fast_cherries, max_iters=50, num_rate_categories=num_rate_categories,
+                                 verbose=False)
+    elif tree_estimator_name in ("FastTree", "PhyML"):
+        tree_estimator = None  # external programs: only usable here with tree_dir given
+    else:
+        raise ValueError(f"Unknown tree_estimator_name: {tree_estimator_name}")
     if model_name == "LG":
         outputs = lg_end_to_end_with_cherryml_optimizer(
-            msa_dir=msa_dir, families=families, tree_estimator=None,
+            msa_dir=msa_dir, families=families, tree_estimator=tree_estimator,
             initial_tree_estimator_rate_matrix_path=initial_tree_estimator_rate_matrix_path,
             num_iterations=num_iterations, quantization_grid_center=quantization_grid_center,
             quantization_grid_step=quantization_grid_step,
@@ -307,7 +372,7 @@ def cherryml_public_api(
         outputs = coevolution_end_to_end_with_cherryml_optimizer(
             msa_dir=msa_dir, contact_map_dir=contact_map_dir,
             minimum_distance_for_nontrivial_contact=minimum_distance_for_nontrivial_contact,
-            coevolution_mask_path=coevolution_mask_path, families=families, tree_estimator=None,
+            coevolution_mask_path=coevolution_mask_path, families=families, tree_estimator=tree_estimator,
             initial_tree_estimator_rate_matrix_path=initial_tree_estimator_rate_matrix_path,
             quantization_grid_center=quantization_grid_center,
             quantization_grid_step=quantization_grid_step,

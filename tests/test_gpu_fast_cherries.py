@@ -170,3 +170,61 @@ def test_stage_function_outputs_and_cache(tmp_path):
         assert os.path.exists(os.path.join(d, "famA.success")) and os.path.exists(os.path.join(d, "famB.success"))
     prof = open(os.path.join(res["output_tree_dir"], "famA.profiling")).read().split("\n")
     assert [ln.split()[0] for ln in prof] == ["pairing_time:", "ble_time:", "cpp_time:", "total_time:"]
+
+
+def test_tree_free_lg_pipeline_counts_match_reference_trees(tmp_path):
+    """FastCherries -> counting -> fit through the public pipeline.  The count matrices must equal
+    those counted on trees / site rates written from the REFERENCE program's golden outputs."""
+    import tarfile
+    from functools import partial
+
+    from cherryml_b200 import caching
+    from cherryml_b200._public_api import _quantization_points, lg_end_to_end_with_cherryml_optimizer
+    from cherryml_b200.counting import count_transitions
+    from cherryml_b200.io import Tree, read_rate_matrix, write_tree
+    from cherryml_b200.markov_chain import get_lg_path
+    from cherryml_b200.phylogeny_estimation import fast_cherries
+    from cherryml_b200.utils import get_amino_acids
+    from tests.conftest import GOLDEN
+
+    fams = ["13gs_1_A", "1a0b_1_A", "1a2t_1_A"]
+    with tarfile.open(os.path.join(GOLDEN, "demo_data.tar.xz")) as tf:
+        tf.extractall(tmp_path, members=[tf.getmember(f"msas/{f}.txt") for f in fams])
+    msa_dir = str(tmp_path / "msas")
+    tree_dir, rates_dir = tmp_path / "ref_trees", tmp_path / "ref_rates"
+    tree_dir.mkdir()
+    rates_dir.mkdir()
+    for f in fams:
+        case = next(c for c in CASES if c["name"] == f"demo_{f}_R20")
+        cherries, dist, _ = expected_outputs(case)
+        tree = Tree()
+        tree.add_node("root")
+        for i, ((a, b), d) in enumerate(zip(cherries, dist)):
+            tree.add_node(f"internal-{i}")
+            tree.add_edge("root", f"internal-{i}", 1.0)
+            for leaf in (a, b):
+                tree.add_node(leaf)
+                tree.add_edge(f"internal-{i}", leaf, float(d) / 2.0)
+        write_tree(tree, str(tree_dir / f"{f}.txt"))
+        (rates_dir / f"{f}.txt").write_text(case["site_rates_file"])
+    caching.set_cache_dir(str(tmp_path / "cache"))
+    try:
+        res = lg_end_to_end_with_cherryml_optimizer(
+            msa_dir=msa_dir, families=fams,
+            tree_estimator=partial(fast_cherries, max_iters=50, num_rate_categories=20, verbose=False),
+            initial_tree_estimator_rate_matrix_path=get_lg_path(), num_iterations=2, num_epochs=40,
+            use_cpp_counting_implementation=False,
+        )
+        ref_counts = count_transitions(
+            tree_dir=str(tree_dir), msa_dir=msa_dir, site_rates_dir=str(rates_dir), families=fams,
+            amino_acids=get_amino_acids(), quantization_points=_quantization_points(0.03, 1.1, 64),
+            edge_or_cherry="cherry++", num_processes=1, use_cpp_implementation=False,
+        )["output_count_matrices_dir"]
+    finally:
+        caching.set_cache_dir(None)
+    ours = open(os.path.join(res["count_matrices_dir_0"], "result.txt")).read()
+    assert ours == open(os.path.join(ref_counts, "result.txt")).read()
+    assert "time_pairing" in res and res["time_ble"] > 0
+    assert res["tree_estimator_output_dirs_1"]["output_tree_dir"] != res["tree_estimator_output_dirs_0"]["output_tree_dir"]
+    Q = read_rate_matrix(res["learned_rate_matrix_path"]).to_numpy()
+    assert Q.shape == (20, 20) and np.allclose(Q.sum(axis=1), 0, atol=1e-5) and (Q - np.diag(np.diag(Q)) >= 0).all()
