@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--cpu-families", type=int, default=0, help="families in the CPU sample (0 = 16 per core, >= 128)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fit", action="store_true")
+    ap.add_argument("--no-fast-cherries", action="store_true")
+    ap.add_argument("--fc-families", type=int, default=2048, help="FastCherries families per GPU")
     return ap.parse_args()
 
 
@@ -399,6 +401,24 @@ def run_ours(args):
         fit = bench_fit(device, lg_times=grid, lg_counts=counts,
                         process_group=dist.group.WORLD if world > 1 else None,
                         cpu_baseline=(world == 1 and not args.no_cpu_baseline))
+    # ---- FastCherries (tree estimation, the step before counting): every rank its own families
+    fcb = None
+    if not args.no_fast_cherries:
+        from cherryml_b200.phylogeny_estimation._bench import bench_fast_cherries
+
+        torch.cuda.empty_cache()
+        fcb = bench_fast_cherries(device, families=args.fc_families, seed=rank,
+                                  cpu_baseline=(world == 1 and rank == 0 and not args.no_cpu_baseline))
+        if world > 1:
+            t = torch.tensor([fcb["pair_kernel_ms"], fcb["ble_kernel_ms"], fcb["e2e_seconds"]], dtype=torch.float64,
+                             device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            fcb["pair_kernel_ms"], fcb["ble_kernel_ms"], fcb["e2e_seconds"] = (float(v) for v in t)
+            fam_all = args.fc_families * world
+            fcb["families_per_s_kernels"] = fam_all / ((fcb["pair_kernel_ms"] + fcb["ble_kernel_ms"]) * 1e-3)
+            fcb["families_per_s_e2e"] = fam_all / fcb["e2e_seconds"]
+            fcb["residues_per_s_e2e"] = fam_all * 1024 * 300 / fcb["e2e_seconds"]
+            fcb["n_gpus"] = world
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -431,6 +451,8 @@ def run_ours(args):
     }
     if fit is not None:
         line["fit"] = fit
+    if fcb is not None:
+        line["fast_cherries"] = fcb
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_cpu_fam = args.cpu_families or default_cpu_families()

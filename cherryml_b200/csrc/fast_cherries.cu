@@ -303,7 +303,8 @@ struct BleArgs {
   const cherry_fc_family* fams;
   const int32_t* pair_a;
   const int32_t* pair_b;
-  const double* sym;      // [K][R][S][S], T + T^T
+  const double2* pair_k;  // [K-1][R][S][S]: {sym[k], sym[k+1]} -- one 16-byte gather per site
+  const double2* pair_r;  // [K][R-1][S][S]: {sym[.][r], sym[.][r+1]}
   const double* priors;   // [R]
   const double* weights;  // [R] cumulative weights of the initial gamma bins
   int32_t* len_idx;       // [cherries]
@@ -330,7 +331,7 @@ __device__ int ble_lengths(const BleArgs& a, const cherry_fc_family& fam, bool c
     int low = 0, high = a.K - 1;
     while (low < high) {
       const int mid = low + (high - low) / 2;
-      const double* t0 = a.sym + (long long)mid * RSS;
+      const double2* t0 = a.pair_k + (long long)mid * RSS;
       double ll_m = 0.0, ll_m1 = 0.0;
       for (int ch = 0; ch < n_chunks; ++ch) {
         const uint4 va = ra[ch], vb = rb[ch];
@@ -342,9 +343,9 @@ __device__ int ble_lengths(const BleArgs& a, const cherry_fc_family& fam, bool c
           for (int k = 0; k < 4; ++k) {
             const int x = (aw[w] >> (8 * k)) & 0xff, y = (bw[w] >> (8 * k)) & 0xff;
             if (x != S && y != S) {
-              const int o = cat[ch * 16 + w * 4 + k] * SS + x * S + y;
-              ll_m += t0[o];
-              ll_m1 += t0[o + RSS];
+              const double2 v = t0[cat[ch * 16 + w * 4 + k] * SS + x * S + y];
+              ll_m += v.x;
+              ll_m1 += v.y;
             }
           }
         }
@@ -364,7 +365,7 @@ __device__ int ble_lengths(const BleArgs& a, const cherry_fc_family& fam, bool c
 // get_site_rates, branch_length_estimation.cpp:110-148, one thread per site.
 __device__ void ble_rates(const BleArgs& a, const cherry_fc_family& fam) {
   const int n_cherries = fam.n_seqs >> 1;
-  const int S = a.S, SS = a.S * a.S, RSS = a.R * SS;
+  const int S = a.S, SS = a.S * a.S, RSS = (a.R - 1) * SS;
   const uint8_t* base = a.msa + fam.msa_off;
   const int32_t* pa = a.pair_a + fam.cherry_off;
   const int32_t* pb = a.pair_b + fam.cherry_off;
@@ -373,15 +374,15 @@ __device__ void ble_rates(const BleArgs& a, const cherry_fc_family& fam) {
     int low = 0, high = a.R - 1;
     while (low < high) {
       const int mid = low + (high - low) / 2;
-      const double* t0 = a.sym + (long long)mid * SS;
+      const double2* t0 = a.pair_r + (long long)mid * SS;
       double ll_m = a.priors[mid], ll_m1 = a.priors[mid + 1];
       for (int c = 0; c < n_cherries; ++c) {
         const int x = base[(long long)pa[c] * fam.row_stride + j];
         const int y = base[(long long)pb[c] * fam.row_stride + j];
         if (x != S && y != S) {
-          const long long o = (long long)li[c] * RSS + x * S + y;
-          ll_m += t0[o];
-          ll_m1 += t0[o + SS];
+          const double2 v = t0[(long long)li[c] * RSS + x * S + y];
+          ll_m += v.x;
+          ll_m1 += v.y;
         }
       }
       if (ll_m > ll_m1) {
@@ -391,6 +392,20 @@ __device__ void ble_rates(const BleArgs& a, const cherry_fc_family& fam) {
       }
     }
     a.site_cat[fam.site_off + j] = low;
+  }
+}
+
+// pair_k[k][r][c] = {sym[k][r][c], sym[k+1][r][c]}, pair_r[k][r][c] = {sym[k][r][c], sym[k][r+1][c]}
+__global__ void fc_pair_tables_kernel(const double* __restrict__ sym, int K, int R, int SS, double2* pair_k,
+                                      double2* pair_r) {
+  const long long n = (long long)K * R * SS;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % SS);
+    const int r = (int)((i / SS) % R);
+    const int k = (int)(i / ((long long)SS * R));
+    const double v = sym[i];
+    if (k + 1 < K) pair_k[i] = make_double2(v, sym[i + (long long)R * SS]);
+    if (r + 1 < R) pair_r[((long long)k * (R - 1) + r) * SS + c] = make_double2(v, sym[i + SS]);
   }
 }
 
@@ -462,10 +477,12 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" {
 
-size_t cherry_fc_scratch_bytes(int64_t total_seqs, int64_t total_sites, int n_fams) {
+size_t cherry_fc_scratch_bytes(int64_t total_seqs, int64_t total_sites, int n_fams, int K, int R, int S) {
   const size_t seqs = (size_t)total_seqs + 2 * (size_t)n_fams + 16;
-  return 5 * 256 + align256(seqs * 4) * 2 + align256(seqs * 8) + align256(seqs) + align256(seqs * sizeof(Frame)) +
-         align256((size_t)total_sites * 8) + 2 * align256((size_t)total_sites * 4) + 3 * 256;
+  const size_t pair = 256 + align256(seqs * 4) * 2 + align256(seqs * 8) + align256(seqs) + align256(seqs * sizeof(Frame));
+  const size_t ble = 256 + align256((size_t)total_sites * 8) + 2 * align256((size_t)total_sites * 4) +
+                     2 * align256((size_t)K * R * S * S * sizeof(double2));
+  return pair > ble ? pair : ble;
 }
 
 int cherry_fc_pair(const uint8_t* msa, const cherry_fc_family* fams, int n_fams, int64_t total_seqs, int S,
@@ -474,7 +491,7 @@ int cherry_fc_pair(const uint8_t* msa, const cherry_fc_family* fams, int n_fams,
   if (n_fams == 0) return CHERRY_OK;
   if (!msa || !fams || !pair_a || !pair_b || !unpaired || !scratch) return cherry::fail(CHERRY_EINVAL, "null pointer");
   if (S < 1 || S > 254) return cherry::fail(CHERRY_ELIMIT, "S=%d out of range", S);
-  if (scratch_bytes < cherry_fc_scratch_bytes(total_seqs, 0, n_fams))
+  if (scratch_bytes < cherry_fc_scratch_bytes(total_seqs, 0, n_fams, 0, 0, 0))
     return cherry::fail(CHERRY_EINVAL, "scratch too small");
   const size_t seqs = (size_t)total_seqs + 2 * (size_t)n_fams + 16;
   char* p = reinterpret_cast<char*>(scratch);
@@ -504,7 +521,7 @@ int cherry_fc_ble(const uint8_t* msa, const cherry_fc_family* fams, int n_fams, 
     return cherry::fail(CHERRY_EINVAL, "null pointer");
   if (S < 1 || S > 32) return cherry::fail(CHERRY_ELIMIT, "FastCherries supports up to 32 states, got %d", S);
   if (K < 1 || R < 1 || max_iters < 0) return cherry::fail(CHERRY_EINVAL, "bad K/R/max_iters");
-  if (scratch_bytes < cherry_fc_scratch_bytes(0, total_sites, n_fams))
+  if (scratch_bytes < cherry_fc_scratch_bytes(0, total_sites, n_fams, K, R, S))
     return cherry::fail(CHERRY_EINVAL, "scratch too small");
   char* p = reinterpret_cast<char*>(align256(reinterpret_cast<size_t>(scratch)));
   BleArgs a;
@@ -512,7 +529,6 @@ int cherry_fc_ble(const uint8_t* msa, const cherry_fc_family* fams, int n_fams, 
   a.fams = fams;
   a.pair_a = pair_a;
   a.pair_b = pair_b;
-  a.sym = sym_table;
   a.priors = priors;
   a.weights = init_weights;
   a.len_idx = len_idx;
@@ -523,6 +539,15 @@ int cherry_fc_ble(const uint8_t* msa, const cherry_fc_family* fams, int n_fams, 
   a.rank = reinterpret_cast<int32_t*>(p);
   p += align256((size_t)total_sites * 4);
   a.cat_by_rank = reinterpret_cast<int32_t*>(p);
+  p += align256((size_t)total_sites * 4);
+  double2* pair_k = reinterpret_cast<double2*>(p);
+  p += align256((size_t)K * R * S * S * sizeof(double2));
+  double2* pair_r = reinterpret_cast<double2*>(p);
+  a.pair_k = pair_k;
+  a.pair_r = pair_r;
+  fc_pair_tables_kernel<<<2 * cherry::sm_count(), 256, 0, (cudaStream_t)stream>>>(sym_table, K, R, S * S, pair_k,
+                                                                                  pair_r);
+  CHERRY_LAUNCH_CHECK("fc_pair_tables_kernel");
   a.S = S;
   a.K = K;
   a.R = R;

@@ -213,7 +213,7 @@ def fast_cherries_device(msa: np.ndarray, fams: np.ndarray, S: int, sym_table: t
         unpaired = torch.empty(max(1, n_fams), dtype=torch.int32, device=dev)
         iters = torch.zeros_like(unpaired)
         site_cat = torch.zeros(max(1, total_sites), dtype=torch.int32, device=dev)
-        nbytes = int(lib.cherry_fc_scratch_bytes(total_seqs, total_sites, n_fams))
+        nbytes = int(lib.cherry_fc_scratch_bytes(total_seqs, total_sites, n_fams, K, R, S))
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         d_priors = torch.from_numpy(np.ascontiguousarray(priors, dtype=np.float64)).to(dev)
         d_weights = torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float64)).to(dev)

@@ -317,8 +317,9 @@ typedef struct cherry_fc_family {
   int32_t seq_off;    /* sum of n_seqs over the families before it */
 } cherry_fc_family;
 
-/* Device scratch both FastCherries entry points need (they may share one buffer). */
-size_t cherry_fc_scratch_bytes(int64_t total_seqs, int64_t total_sites, int n_fams);
+/* Device scratch both FastCherries entry points need (they may share one buffer; K, R, S as
+ * passed to cherry_fc_ble). */
+size_t cherry_fc_scratch_bytes(int64_t total_seqs, int64_t total_sites, int n_fams, int K, int R, int S);
 
 /* Pairs the sequences of every family into floor(n_seqs / 2) cherries by recursive bisection
  * around two far-apart pivots under the normalised Hamming distance over sites valid in both
