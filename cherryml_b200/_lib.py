@@ -46,7 +46,11 @@ FC_FAMILY_DTYPE = np.dtype(
     ],
     align=True,
 )
+LL_NODE_DTYPE = np.dtype(
+    [("depth", np.int32), ("flags", np.int32), ("obs_row", np.int32), ("reserved", np.int32)], align=True
+)
 assert FAM_DESC_DTYPE.itemsize == 32 and TILE_DTYPE.itemsize == 16 and FC_FAMILY_DTYPE.itemsize == 32
+assert LL_NODE_DTYPE.itemsize == 16
 
 NO_BUCKET = 255
 # The skip code of a residue byte is the number of states S itself (bytes are in [0, S]).
@@ -86,6 +90,10 @@ _SIGNATURES = {
     "cherry_ingest_co": (c_int, [c_char_p, c_char_p, c_char_p, _P, c_int, _P, c_int, c_char_p, c_int, c_int,
                                  c_int, c_int, _P]),
     "cherry_ingest_free": (None, [_P]),
+    "cherry_tree_ll_units_per_block": (c_int, [c_int, c_int]),
+    "cherry_tree_ll_scratch_bytes": (ctypes.c_size_t, [c_int, c_int, c_int, c_int]),
+    "cherry_tree_log_likelihood": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P,
+                                           ctypes.c_size_t, _P, _P]),
     "cherry_fc_scratch_bytes": (ctypes.c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int]),
     "cherry_fc_pair": (c_int, [_P, _P, c_int, c_int64, c_int, ctypes.c_uint32, _P, _P, _P, _P, ctypes.c_size_t, _P]),
     "cherry_fc_ble": (c_int, [_P, _P, c_int, c_int64, c_int, _P, _P, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P,

@@ -86,6 +86,19 @@ class Tree:
     def internal_nodes(self) -> List[str]:
         return [u for u in self._children if self._children[u]]
 
+    def postorder_traversal(self) -> List[str]:
+        """Children (in edge order) before their parent; iterative, so deep trees are fine."""
+        res, stack = [], [(self.root(), 0)]
+        while stack:
+            v, k = stack.pop()
+            kids = self._children[v]
+            if k < len(kids):
+                stack.append((v, k + 1))
+                stack.append((kids[k][0], 0))
+            else:
+                res.append(v)
+        return res
+
     def preorder_traversal(self) -> List[str]:
         res, stack = [], [self.root()]
         while stack:
@@ -367,6 +380,8 @@ def _read_labelled_table(path: str) -> Tuple[List[str], List[str], np.ndarray]:
         rows.append(toks[0])
         data.append([float("nan") if t == "_" else float(t) for t in toks[1:]])
     arr = np.array(data, dtype=np.float64)
+    if arr.ndim == 2 and arr.shape[1] == len(cols) - 1:
+        cols = cols[1:]  # the header names the index column too ("state\tprob"), as pandas writes it
     if arr.ndim != 2 or arr.shape[1] != len(cols):
         raise Exception(f"Malformed matrix file: {path}")
     return rows, cols, arr

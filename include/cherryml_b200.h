@@ -34,6 +34,8 @@
  *                              fast_cherries.cpp:240-244).
  *   cherry_fc_ble              ble(), FastCherries/branch_length_estimation.cpp:10-241
  *                              (fast_cherries.cpp:258-266).
+ *   cherry_tree_log_likelihood the pruning loops of dp_likelihood_computation,
+ *                              evaluation/_likelihood.py:239-326.
  */
 #ifndef CHERRYML_B200_H
 #define CHERRYML_B200_H
@@ -345,6 +347,34 @@ int cherry_fc_ble(const uint8_t* msa, const cherry_fc_family* fams, int n_fams, 
                   const int32_t* pair_a, const int32_t* pair_b, const double* sym_table, int K, int R,
                   const double* priors, const double* init_weights, int max_iters, int32_t* len_idx,
                   int32_t* site_cat, int32_t* iters, void* scratch, size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------- tree log-likelihood */
+
+/* One tree node; nodes are passed in POST-ORDER (children, in the tree's child order, before
+ * their parent; the root last).  16 bytes. */
+typedef struct cherry_ll_node {
+  int32_t depth;    /* edges between the node and the root */
+  int32_t flags;    /* bit 0: leaf; bit 1: first child of its parent */
+  int32_t obs_row;  /* leaf: row of `obs`; internal node: -1 */
+  int32_t reserved;
+} cherry_ll_node;
+
+int cherry_tree_ll_units_per_block(int S, int c);
+size_t cherry_tree_ll_scratch_bytes(int S, int c, int n_units, int max_depth);
+
+/* ll_out[u] = log-likelihood of unit u on the tree.  A unit is one site (c = 1, S states) or a
+ * pair of contacting sites (c = 2, S*S states, state = S*i + j).
+ * p_index[i * n_cats + k]: which matrix of P (fp64 [n][Su][Su], row-stochastic, = expm(branch
+ * length * rate_k * Q)) belongs to the edge above node i for rate category k (ignored for the
+ * root); unit_cat[u]: the unit's rate category; obs: uint8 [n_leaves][n_units][c] residues
+ * (S = not in the alphabet: every state is compatible); pi: [Su] root distribution.
+ * Replaces the pruning loops of dp_likelihood_computation, evaluation/_likelihood.py:239-326
+ * (child messages are accumulated in the same order; a pair's value is split over its two
+ * sites by the caller as at :316-319). */
+int cherry_tree_log_likelihood(const cherry_ll_node* nodes, int n_nodes, const int32_t* p_index, int n_cats,
+                               const double* P, const uint8_t* obs, const int32_t* unit_cat, const double* pi,
+                               int S, int c, int n_units, int max_depth, void* scratch, size_t scratch_bytes,
+                               double* ll_out, void* stream);
 
 #ifdef __cplusplus
 }
