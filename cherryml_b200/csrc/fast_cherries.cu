@@ -313,15 +313,28 @@ struct BleArgs {
   long long* total;       // scratch [sites]
   int32_t* rank;          // scratch [sites]
   int32_t* cat_by_rank;   // scratch [sites]
+  uint8_t* cat8;          // scratch: site categories as bytes, 16-byte aligned per family (fc_cat8_offset)
   int S, K, R, max_iters;
 };
 
+__device__ __forceinline__ int byte_of(const uint4& v, int b) {
+  const uint32_t w = b < 4 ? v.x : b < 8 ? v.y : b < 12 ? v.z : v.w;
+  return (w >> (8 * (b & 3))) & 0xff;
+}
+
+// Byte-sized copy of a family's site categories: 16-byte aligned, row_stride entries.
+__device__ __host__ __forceinline__ long long fc_cat8_offset(const cherry_fc_family& fam, int f) {
+  return (((long long)fam.site_off + 15) & ~15LL) + 32LL * f;
+}
+
 // get_branch_lengths, branch_length_estimation.cpp:64-108, one thread per cherry.  Returns
-// whether any length of this thread changed (compare != 0) .
+// whether any length of this thread changed (compare != 0).  The sums run over the sites in
+// ascending order; a site that is invalid in either row adds +0.0 (which leaves an fp64 sum
+// unchanged) instead of being skipped, so eight table gathers can be in flight at once.
 __device__ int ble_lengths(const BleArgs& a, const cherry_fc_family& fam, bool compare) {
   const int n_cherries = fam.n_seqs >> 1, n_chunks = fam.row_stride >> 4;
   const int S = a.S, SS = a.S * a.S, RSS = a.R * SS;
-  const int32_t* cat = a.site_cat + fam.site_off;
+  const uint4* cat16 = reinterpret_cast<const uint4*>(a.cat8 + fc_cat8_offset(fam, blockIdx.x));
   int changed = 0;
   for (int c = threadIdx.x; c < n_cherries; c += blockDim.x) {
     const uint4* ra =
@@ -334,19 +347,22 @@ __device__ int ble_lengths(const BleArgs& a, const cherry_fc_family& fam, bool c
       const double2* t0 = a.pair_k + (long long)mid * RSS;
       double ll_m = 0.0, ll_m1 = 0.0;
       for (int ch = 0; ch < n_chunks; ++ch) {
-        const uint4 va = ra[ch], vb = rb[ch];
-        const uint32_t aw[4] = {va.x, va.y, va.z, va.w};
-        const uint32_t bw[4] = {vb.x, vb.y, vb.z, vb.w};
+        const uint4 va = ra[ch], vb = rb[ch], vc = cat16[ch];
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
+        for (int half = 0; half < 2; ++half) {
+          double2 v[8];
+          bool ok[8];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int x = (aw[w] >> (8 * k)) & 0xff, y = (bw[w] >> (8 * k)) & 0xff;
-            if (x != S && y != S) {
-              const double2 v = t0[cat[ch * 16 + w * 4 + k] * SS + x * S + y];
-              ll_m += v.x;
-              ll_m1 += v.y;
-            }
+          for (int k = 0; k < 8; ++k) {
+            const int b = half * 8 + k;
+            const int x = byte_of(va, b), y = byte_of(vb, b);
+            ok[k] = x != S && y != S;
+            v[k] = t0[ok[k] ? byte_of(vc, b) * SS + x * S + y : 0];
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            ll_m += ok[k] ? v[k].x : 0.0;
+            ll_m1 += ok[k] ? v[k].y : 0.0;
           }
         }
       }
@@ -362,7 +378,8 @@ __device__ int ble_lengths(const BleArgs& a, const cherry_fc_family& fam, bool c
   return changed;
 }
 
-// get_site_rates, branch_length_estimation.cpp:110-148, one thread per site.
+// get_site_rates, branch_length_estimation.cpp:110-148, one thread per site; cherries in
+// ascending order, four in flight.
 __device__ void ble_rates(const BleArgs& a, const cherry_fc_family& fam) {
   const int n_cherries = fam.n_seqs >> 1;
   const int S = a.S, SS = a.S * a.S, RSS = (a.R - 1) * SS;
@@ -370,13 +387,36 @@ __device__ void ble_rates(const BleArgs& a, const cherry_fc_family& fam) {
   const int32_t* pa = a.pair_a + fam.cherry_off;
   const int32_t* pb = a.pair_b + fam.cherry_off;
   const int32_t* li = a.len_idx + fam.cherry_off;
+  uint8_t* cat8 = a.cat8 + fc_cat8_offset(fam, blockIdx.x);
   for (int j = threadIdx.x; j < fam.n_sites; j += blockDim.x) {
     int low = 0, high = a.R - 1;
     while (low < high) {
       const int mid = low + (high - low) / 2;
       const double2* t0 = a.pair_r + (long long)mid * SS;
       double ll_m = a.priors[mid], ll_m1 = a.priors[mid + 1];
-      for (int c = 0; c < n_cherries; ++c) {
+      int c = 0;
+      for (; c + 4 <= n_cherries; c += 4) {
+        int x[4], y[4], l[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          x[u] = base[(long long)pa[c + u] * fam.row_stride + j];
+          y[u] = base[(long long)pb[c + u] * fam.row_stride + j];
+          l[u] = li[c + u];
+        }
+        double2 v[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          ok[u] = x[u] != S && y[u] != S;
+          v[u] = t0[ok[u] ? (long long)l[u] * RSS + x[u] * S + y[u] : 0];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          ll_m += ok[u] ? v[u].x : 0.0;
+          ll_m1 += ok[u] ? v[u].y : 0.0;
+        }
+      }
+      for (; c < n_cherries; ++c) {
         const int x = base[(long long)pa[c] * fam.row_stride + j];
         const int y = base[(long long)pb[c] * fam.row_stride + j];
         if (x != S && y != S) {
@@ -392,6 +432,7 @@ __device__ void ble_rates(const BleArgs& a, const cherry_fc_family& fam) {
       }
     }
     a.site_cat[fam.site_off + j] = low;
+    cat8[j] = (uint8_t)low;
   }
 }
 
@@ -450,7 +491,12 @@ __global__ void __launch_bounds__(kBleThreads) fc_ble_kernel(BleArgs a) {
     }
   }
   __syncthreads();
-  for (int j = tid; j < L; j += nt) site_cat[j] = cat_by_rank[rank[j]];
+  uint8_t* cat8 = a.cat8 + fc_cat8_offset(fam, blockIdx.x);
+  for (int j = tid; j < fam.row_stride; j += nt) {
+    const int cat = j < L ? cat_by_rank[rank[j]] : 0;
+    if (j < L) site_cat[j] = cat;
+    cat8[j] = (uint8_t)cat;
+  }
   __syncthreads();
   // coordinate ascent (branch_length_estimation.cpp:186-227)
   ble_lengths(a, fam, false);
@@ -481,6 +527,7 @@ size_t cherry_fc_scratch_bytes(int64_t total_seqs, int64_t total_sites, int n_fa
   const size_t seqs = (size_t)total_seqs + 2 * (size_t)n_fams + 16;
   const size_t pair = 256 + align256(seqs * 4) * 2 + align256(seqs * 8) + align256(seqs) + align256(seqs * sizeof(Frame));
   const size_t ble = 256 + align256((size_t)total_sites * 8) + 2 * align256((size_t)total_sites * 4) +
+                     align256((size_t)total_sites + 32 * (size_t)n_fams + 64) +
                      2 * align256((size_t)K * R * S * S * sizeof(double2));
   return pair > ble ? pair : ble;
 }
@@ -520,7 +567,7 @@ int cherry_fc_ble(const uint8_t* msa, const cherry_fc_family* fams, int n_fams, 
       !iters || !scratch)
     return cherry::fail(CHERRY_EINVAL, "null pointer");
   if (S < 1 || S > 32) return cherry::fail(CHERRY_ELIMIT, "FastCherries supports up to 32 states, got %d", S);
-  if (K < 1 || R < 1 || max_iters < 0) return cherry::fail(CHERRY_EINVAL, "bad K/R/max_iters");
+  if (K < 1 || R < 1 || R > 255 || max_iters < 0) return cherry::fail(CHERRY_EINVAL, "bad K/R/max_iters");
   if (scratch_bytes < cherry_fc_scratch_bytes(0, total_sites, n_fams, K, R, S))
     return cherry::fail(CHERRY_EINVAL, "scratch too small");
   char* p = reinterpret_cast<char*>(align256(reinterpret_cast<size_t>(scratch)));
@@ -540,6 +587,8 @@ int cherry_fc_ble(const uint8_t* msa, const cherry_fc_family* fams, int n_fams, 
   p += align256((size_t)total_sites * 4);
   a.cat_by_rank = reinterpret_cast<int32_t*>(p);
   p += align256((size_t)total_sites * 4);
+  a.cat8 = reinterpret_cast<uint8_t*>(p);
+  p += align256((size_t)total_sites + 32 * (size_t)n_fams + 64);
   double2* pair_k = reinterpret_cast<double2*>(p);
   p += align256((size_t)K * R * S * S * sizeof(double2));
   double2* pair_r = reinterpret_cast<double2*>(p);
