@@ -67,7 +67,7 @@ def _prune(nodes, max_depth, p_index, n_cats, P, obs, unit_cat, pi, S, c, device
         d_pidx = torch.from_numpy(np.ascontiguousarray(p_index, dtype=np.int32)).to(dev)
         d_obs = torch.from_numpy(np.ascontiguousarray(obs, dtype=np.uint8)).to(dev)
         d_cat = torch.from_numpy(np.ascontiguousarray(unit_cat, dtype=np.int32)).to(dev)
-        d_pi = torch.from_numpy(np.ascontiguousarray(pi, dtype=np.float64).reshape(-1)).to(dev)
+        d_pi = torch.from_numpy(np.array(pi, dtype=np.float64).reshape(-1)).to(dev)
         nbytes = int(lib.cherry_tree_ll_scratch_bytes(S, c, n_units, max_depth))
         scratch = torch.empty(max(8, nbytes), dtype=torch.uint8, device=dev)
         out = torch.empty(n_units, dtype=torch.float64, device=dev)

@@ -97,3 +97,29 @@ def test_per_site_counts_random():
     q = [0.03 * 1.1 ** (8 * i) for i in range(-8, 9)]
     got = get_raw_count_matrices(transitions, q, alphabet)
     assert np.array_equal(got, _ref_raw_counts(transitions, q, alphabet))
+
+
+@pytest.mark.parametrize("name", ["aa", "aa_gap_state"])
+def test_estimate_site_specific_rate_matrices_matches_reference(name):
+    """The whole SiteRM stage (cherry++ transitions -> per-site counts -> pseudocounts ->
+    compaction -> batched fit) against the UNMODIFIED reference function
+    (tests/golden/make_golden_siterm_estimate.py); the reference fits in fp64 here."""
+    import json
+
+    from cherryml_b200.io import Tree
+    from cherryml_b200.siterm import estimate_site_specific_rate_matrices_given_tree_and_site_rates
+
+    g = np.load(os.path.join(G, f"estimate_{name}.npz"))
+    m = json.loads(str(g["meta"]))
+    tree = Tree()
+    tree.add_nodes(m["names"])
+    for i in range(1, len(m["names"])):
+        tree.add_edge(m["names"][m["parent"][i]], m["names"][i], m["length"][i])
+    r = estimate_site_specific_rate_matrices_given_tree_and_site_rates(
+        tree=tree, site_rates=m["rates"], msa=m["msa"], alphabet=m["alphabet"], regularization_strength=m["lam"],
+        regularization_rate_matrix=g["Q0"], quantization_points=m["grid"], optimization_num_epochs=m["epochs"],
+        use_vectorized_cherryml_implementation=True,
+    )
+    assert r["res"].shape == g["res"].shape
+    assert np.max(np.abs(r["res"] - g["res"])) < 1e-6 * np.max(np.abs(g["res"]))
+    assert "time_get_raw_count_matrices" in r and "time_get_pseudocount_matrices" in r
