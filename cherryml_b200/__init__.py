@@ -15,3 +15,4 @@ from ._public_api import (  # noqa: F401
     coevolution_end_to_end_with_cherryml_optimizer,
     lg_end_to_end_with_cherryml_optimizer,
 )
+from .siterm import learn_site_specific_rate_matrices  # noqa: F401,E402

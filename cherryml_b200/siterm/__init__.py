@@ -6,3 +6,10 @@ from ._site_specific import (  # noqa: F401
     get_cherry_transitions,
     get_edge_transitions,
 )
+from ._public_api import (  # noqa: F401
+    estimate_site_rates,
+    get_standard_site_rate_grid,
+    get_standard_site_rate_prior,
+    learn_site_rate_matrices,
+    learn_site_specific_rate_matrices,
+)

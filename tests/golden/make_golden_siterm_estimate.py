@@ -68,5 +68,49 @@ def main():
         print(name, r["res"].shape, float(np.abs(r["res"]).max()))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--public-api" not in sys.argv:
     main()
+
+
+def public_api_golden():
+    """learn_site_rate_matrices with a given tree (site-rate estimation + SiteRM), unmodified
+    reference, non-Cython site-rate path."""
+    from make_golden_fit import import_reference
+    from make_golden_likelihood import random_tree
+
+    import_reference()
+    import pandas as pd
+    from cherryml._siterm._learn_site_rate_matrix import (get_standard_site_rate_grid, get_standard_site_rate_prior,
+                                                           learn_site_rate_matrices)
+    from cherryml.io import Tree, read_rate_matrix
+
+    lg = read_rate_matrix("/root/reference/data/rate_matrices/lg.txt")
+    rng = np.random.default_rng(5)
+    names, parent, length = random_tree(rng, 16)
+    tree = Tree()
+    tree.add_nodes(names)
+    for i in range(1, len(names)):
+        tree.add_edge(names[parent[i]], names[i], length[i])
+    L = 12
+    msa = {}
+    anc = rng.choice(list(AA), L)
+    for lf in [n for n in names if n.startswith("leaf")]:
+        s = anc.copy()
+        flip = rng.random(L) < np.linspace(0.02, 0.9, L)  # slow sites first, fast sites last
+        s[flip] = rng.choice(list(AA), int(flip.sum()))
+        s[rng.random(L) < 0.1] = "-"
+        msa[lf] = "".join(s)
+    r = learn_site_rate_matrices(
+        tree=tree, leaf_states=msa, alphabet=list(AA), regularization_rate_matrix=lg, regularization_strength=0.5,
+        use_vectorized_implementation=True, site_rate_grid=get_standard_site_rate_grid(),
+        site_rate_prior=get_standard_site_rate_prior(), num_epochs=20, use_fast_site_rate_implementation=False,
+        quantization_grid_num_steps=8,
+    )
+    meta = dict(names=names, parent=parent, length=length, msa=msa)
+    np.savez_compressed(os.path.join(OUT, "public_api_tree_given.npz"), res=r["learnt_rate_matrices"],
+                        site_rates=np.array(r["learnt_site_rates"]), meta=json.dumps(meta))
+    print("public api:", r["learnt_rate_matrices"].shape, r["learnt_site_rates"])
+
+
+if __name__ == "__main__" and "--public-api" in sys.argv:
+    public_api_golden()
