@@ -94,6 +94,9 @@ _SIGNATURES = {
     "cherry_tree_ll_scratch_bytes": (ctypes.c_size_t, [c_int, c_int, c_int, c_int]),
     "cherry_tree_log_likelihood": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P,
                                            ctypes.c_size_t, _P, _P]),
+    "cherry_fc_read_msas": (c_int, [_P, c_int, _P, c_int, c_int, c_int, _P]),
+    "cherry_fc_free_msas": (None, [_P]),
+    "cherry_fc_write_outputs": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, c_int]),
     "cherry_fc_scratch_bytes": (ctypes.c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int]),
     "cherry_fc_pair": (c_int, [_P, _P, c_int, c_int64, c_int, ctypes.c_uint32, _P, _P, _P, _P, ctypes.c_size_t, _P]),
     "cherry_fc_ble": (c_int, [_P, _P, c_int, c_int64, c_int, _P, _P, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P,
@@ -117,6 +120,16 @@ class IngestResult(ctypes.Structure):
         ("n_aux", c_int64), ("aux", c_void_p),
         ("n_tiles", c_int32), ("max_row_stride", c_int32), ("tiles", c_void_p),
         ("n_items_examined", c_int64),
+    ]
+
+
+class FcMsas(ctypes.Structure):
+    """``cherry_fc_msas`` of include/cherryml_b200.h."""
+
+    _fields_ = [
+        ("n_fams", c_int32), ("pinned", c_int32), ("msa_bytes", c_int64), ("msa", c_void_p), ("fams", c_void_p),
+        ("total_seqs", c_int64), ("total_sites", c_int64), ("total_cherries", c_int64),
+        ("name_blob", c_void_p), ("name_off", c_void_p),
     ]
 
 

@@ -293,6 +293,73 @@ def _newick(names, pairs, lengths, unpaired) -> str:
     return "(" + ",".join(parts) + ");"
 
 
+def _c_paths(paths: Sequence[Optional[str]]):
+    arr = (ctypes.c_char_p * len(paths))()
+    arr[:] = [None if p is None else p.encode() for p in paths]
+    return arr
+
+
+class NativeMsas:
+    """MSA files read and encoded by the library's host threads (``cherry_fc_read_msas``); the
+    residue buffer is page-locked.  Use as a context manager."""
+
+    def __init__(self, msa_paths: Sequence[str], alphabet: Sequence[str], n_threads: Optional[int] = None,
+                 pinned: bool = True) -> None:
+        lib = _lib.load()
+        self._lib = lib
+        self.n_threads = n_threads or os.cpu_count() or 1
+        handle = ctypes.POINTER(_lib.FcMsas)()
+        _lib.check(lib.cherry_fc_read_msas(_c_paths(msa_paths), len(msa_paths), _c_paths(list(alphabet)),
+                                           len(alphabet), self.n_threads, int(pinned), ctypes.byref(handle)),
+                   "cherry_fc_read_msas")
+        self.handle = handle
+        r = handle.contents
+        self.n_fams = int(r.n_fams)
+        self.msa = np.ctypeslib.as_array(ctypes.cast(r.msa, ctypes.POINTER(ctypes.c_uint8)),
+                                         shape=(max(1, int(r.msa_bytes)),))[: int(r.msa_bytes)]
+        self.fams = np.ctypeslib.as_array(ctypes.cast(r.fams, ctypes.POINTER(ctypes.c_uint8)),
+                                          shape=(max(1, self.n_fams) * 32,))[: self.n_fams * 32].view(
+            _lib.FC_FAMILY_DTYPE)
+
+    def names(self, family_index: int) -> List[str]:
+        r = self.handle.contents
+        fam = self.fams[family_index]
+        s0, n = int(fam["seq_off"]), int(fam["n_seqs"])
+        off = np.ctypeslib.as_array(ctypes.cast(r.name_off, ctypes.POINTER(ctypes.c_int64)),
+                                    shape=(int(r.total_seqs) + 1,))
+        blob = ctypes.string_at(r.name_blob + int(off[s0]), int(off[s0 + n] - off[s0]))
+        base = int(off[s0])
+        return [blob[int(off[s0 + i]) - base: int(off[s0 + i + 1]) - base].decode("utf-8", "replace")
+                for i in range(n)]
+
+    def write_outputs(self, out: Dict[str, np.ndarray], grid: np.ndarray, cats: np.ndarray, tree_paths,
+                      newick_paths, site_rate_paths, likelihood_paths, profiling_paths, profiling: np.ndarray) -> None:
+        c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)  # noqa: E731
+        pa, pb, un = c(out["pair_a"], np.int32), c(out["pair_b"], np.int32), c(out["unpaired"], np.int32)
+        li, sc = c(out["len_idx"], np.int32), c(out["site_cat"], np.int32)
+        g, ct, prof = c(grid, np.float64), c(cats, np.float64), c(profiling, np.float64)
+        _lib.check(
+            self._lib.cherry_fc_write_outputs(
+                self.handle, _lib.ptr(pa), _lib.ptr(pb), _lib.ptr(un), _lib.ptr(li), _lib.ptr(sc), _lib.ptr(g),
+                len(g), _lib.ptr(ct), len(ct), _c_paths(tree_paths), _c_paths(newick_paths),
+                _c_paths(site_rate_paths), _c_paths(likelihood_paths), _c_paths(profiling_paths), _lib.ptr(prof),
+                self.n_threads),
+            "cherry_fc_write_outputs",
+        )
+
+    def close(self) -> None:
+        if self.handle:
+            self.msa = self.fams = None
+            self._lib.cherry_fc_free_msas(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 @cached_parallel_computation(
     parallel_arg="families",
     exclude_args=["num_processes", "device"],
@@ -341,29 +408,18 @@ def fast_cherries(
     cats = ble_rate_categories(num_rate_categories)
     weights = initial_rate_weights(cats)
     priors = np.array([2 * math.log(r) - 3 * r for r in cats])
-    names, msa, fams = encode_families([os.path.join(msa_dir, f + ".txt") for f in families], alphabet)
     table = log_transition_table(Q, grid, cats, device)
-    out = fast_cherries_device(msa, fams, len(alphabet), table, priors, weights, int(seed), int(max_iters), device)
-    t_device = time.time() - t_start
-    for f, family in enumerate(families):
-        fam = fams[f]
-        c0, c1 = int(fam["cherry_off"]), int(fam["cherry_off"]) + int(fam["n_seqs"]) // 2
-        s0, s1 = int(fam["site_off"]), int(fam["site_off"]) + int(fam["n_sites"])
-        pairs = list(zip(out["pair_a"][c0:c1].tolist(), out["pair_b"][c0:c1].tolist()))
-        lengths, rates = normalise_lengths_and_rates(out["len_idx"][c0:c1], out["site_cat"][s0:s1], grid, cats)
-        unpaired = int(out["unpaired"][f])
-        write_tree(cherries_tree(names[f], pairs, lengths, unpaired), os.path.join(output_tree_dir, family + ".txt"))
-        with open(os.path.join(output_tree_dir, family + ".newick"), "w") as fh:
-            fh.write(_newick(names[f], pairs, lengths, unpaired))
-        with open(os.path.join(output_site_rates_dir, family + ".txt"), "w") as fh:
-            fh.write(f"{len(rates)} sites\n" + "".join(_fixed17(r) + " " for r in rates))
-        with open(os.path.join(output_likelihood_dir, family + ".txt"), "w") as fh:
-            fh.write(str(0.0))
-        share = t_device / len(families)
-        with open(os.path.join(output_tree_dir, family + ".profiling"), "w") as fh:
-            fh.write(
-                f"pairing_time: {out['pair_ms'] * 1e-3 / len(families)}\n"
-                f"ble_time: {out['ble_ms'] * 1e-3 / len(families)}\n"
-                f"cpp_time: {share}\n"
-                f"total_time: {(time.time() - t_start) / len(families)}"
-            )
+    join = lambda d, ext: [os.path.join(d, f + ext) for f in families]  # noqa: E731
+    with NativeMsas(join(msa_dir, ".txt"), alphabet) as msas:
+        out = fast_cherries_device(msas.msa, msas.fams, len(alphabet), table, priors, weights, int(seed),
+                                   int(max_iters), device)
+        n = len(families)
+        elapsed = time.time() - t_start
+        profiling = np.empty((n, 4))
+        profiling[:, 0] = out["pair_ms"] * 1e-3 / n
+        profiling[:, 1] = out["ble_ms"] * 1e-3 / n
+        profiling[:, 2] = elapsed / n
+        profiling[:, 3] = elapsed / n
+        msas.write_outputs(out, grid, cats, join(output_tree_dir, ".txt"), join(output_tree_dir, ".newick"),
+                           join(output_site_rates_dir, ".txt"), join(output_likelihood_dir, ".txt"),
+                           join(output_tree_dir, ".profiling"), profiling)

@@ -348,6 +348,39 @@ int cherry_fc_ble(const uint8_t* msa, const cherry_fc_family* fams, int n_fams, 
                   const double* priors, const double* init_weights, int max_iters, int32_t* len_idx,
                   int32_t* site_cat, int32_t* iters, void* scratch, size_t scratch_bytes, void* stream);
 
+/* Host-side text I/O of the FastCherries stage (multithreaded, one family per task). */
+typedef struct cherry_fc_msas {
+  int32_t n_fams;
+  int32_t pinned;          /* msa is page-locked */
+  int64_t msa_bytes;
+  uint8_t* msa;            /* residue rows of all families, as cherry_fc_pair / cherry_fc_ble take them */
+  cherry_fc_family* fams;
+  int64_t total_seqs, total_sites, total_cherries;
+  char* name_blob;         /* sequence names back to back */
+  int64_t* name_off;       /* [total_seqs + 1] offsets into name_blob, sequences in batch order */
+} cherry_fc_msas;
+
+/* Reads and encodes `<paths[f]>` for every family like read_msa of FastCherries/io_helpers.cpp
+ * :35-74 (a line starting with '>' names a sequence, the next line is the sequence; characters
+ * outside `states` become the skip code).  Release with cherry_fc_free_msas. */
+int cherry_fc_read_msas(const char* const* paths, int n_fams, const char* const* states, int n_states,
+                        int n_threads, int pinned, cherry_fc_msas** out);
+void cherry_fc_free_msas(cherry_fc_msas* msas);
+
+/* Writes, per family, what the reference stage leaves behind (any path array except tree_paths
+ * and site_rate_paths may be NULL): the star-of-cherries tree in CherryML's tree format
+ * (phylogeny_estimation/_fast_cherries.py:121-141; branch length = the '%.17f' text of
+ * grid[len_idx] * mean rate, read back and halved, printed like Python's repr), the newick
+ * string, the site rates normalised to mean 1 in '%.17f ' format (io_helpers.cpp:91-103), the
+ * constant likelihood file and the profiling file (4 numbers per family).  All pointers are
+ * HOST pointers. */
+int cherry_fc_write_outputs(const cherry_fc_msas* msas, const int32_t* pair_a, const int32_t* pair_b,
+                            const int32_t* unpaired, const int32_t* len_idx, const int32_t* site_cat,
+                            const double* grid, int K, const double* cats, int R, const char* const* tree_paths,
+                            const char* const* newick_paths, const char* const* site_rate_paths,
+                            const char* const* likelihood_paths, const char* const* profiling_paths,
+                            const double* profiling, int n_threads);
+
 /* ------------------------------------------------------------------- tree log-likelihood */
 
 /* One tree node; nodes are passed in POST-ORDER (children, in the tree's child order, before

@@ -1,0 +1,86 @@
+"""The FastCherries stage's native text I/O (cherry_fc_read_msas / cherry_fc_write_outputs, host
+threads, no GPU) against the plain-Python implementations of the same formats, byte for byte."""
+import os
+
+import numpy as np
+
+from cherryml_b200.io import write_tree
+from cherryml_b200.phylogeny_estimation import _fast_cherries as fc
+
+AA = list("ARNDCQEGHILKMFPSTWYV")
+
+
+def _write_msas(tmp_path, rng, shapes):
+    paths = []
+    for f, (n, L) in enumerate(shapes):
+        rows = []
+        for i in range(n):
+            s = rng.choice(AA + ["-", "X", "a"], L)
+            rows.append(f">fam{f}_s{i} extra\n{''.join(s)}\n")
+        text = "".join(rows)
+        if f % 3 == 1:
+            text = text[:-1]          # no trailing newline
+        if f % 3 == 2:
+            text = "# comment\n" + text + ">dangling_name\n"   # ignored line, name without a sequence
+        p = tmp_path / f"m{f}.txt"
+        p.write_text(text)
+        paths.append(str(p))
+    return paths
+
+
+def test_read_msas_matches_python_encoder(tmp_path):
+    rng = np.random.default_rng(0)
+    paths = _write_msas(tmp_path, rng, [(5, 33), (2, 16), (9, 1), (40, 100), (1, 7), (3, 15)])
+    names, buf, fams = fc.encode_families(paths, AA)
+    with fc.NativeMsas(paths, AA, n_threads=3, pinned=False) as m:
+        assert np.array_equal(m.fams, fams)
+        assert np.array_equal(m.msa, buf)
+        for f in range(len(paths)):
+            assert m.names(f) == names[f]
+
+
+def test_write_outputs_matches_python_writers(tmp_path):
+    rng = np.random.default_rng(1)
+    shapes = [(7, 20), (2, 16), (12, 50), (33, 9)]
+    paths = _write_msas(tmp_path, rng, shapes)
+    grid = fc.quantization_grid(0.03, 1.1, 64)
+    cats = fc.ble_rate_categories(20)
+    with fc.NativeMsas(paths, AA, n_threads=2, pinned=False) as m:
+        fams = m.fams.copy()
+        n_ch = int((fams["n_seqs"] // 2).sum())
+        pair_a = np.zeros(n_ch, dtype=np.int32)
+        pair_b = np.zeros(n_ch, dtype=np.int32)
+        unpaired = np.full(len(paths), -1, dtype=np.int32)
+        for f, (n, _) in enumerate(shapes):
+            perm = rng.permutation(n)
+            c0 = int(fams[f]["cherry_off"])
+            pair_a[c0: c0 + n // 2] = perm[0: 2 * (n // 2): 2]
+            pair_b[c0: c0 + n // 2] = perm[1: 2 * (n // 2): 2]
+            if n % 2:
+                unpaired[f] = perm[-1]
+        # grid indices over the whole range: exercises repr() in fixed and exponent notation
+        len_idx = rng.integers(0, len(grid), n_ch).astype(np.int32)
+        len_idx[:4] = [0, 1, len(grid) - 1, 64]
+        site_cat = rng.integers(0, len(cats), int(fams["n_sites"].sum())).astype(np.int32)
+        out = dict(pair_a=pair_a, pair_b=pair_b, unpaired=unpaired, len_idx=len_idx, site_cat=site_cat)
+        prof = np.abs(rng.standard_normal((len(paths), 4))) * np.array([1e-7, 1e-3, 1.0, 1e17])
+        prof[0] = [0.0, 1e-4, 1e-5, 123456789012345678.0]
+        prof[1] = [1.0, 1e16, 1e15, 0.1]
+        d = tmp_path / "out"
+        d.mkdir()
+        j = lambda ext: [str(d / f"f{f}{ext}") for f in range(len(paths))]  # noqa: E731
+        m.write_outputs(out, grid, cats, j(".tree"), j(".newick"), j(".rates"), j(".ll"), j(".prof"), prof)
+        for f, (n, L) in enumerate(shapes):
+            c0, s0 = int(fams[f]["cherry_off"]), int(fams[f]["site_off"])
+            names = m.names(f)
+            pairs = list(zip(pair_a[c0: c0 + n // 2].tolist(), pair_b[c0: c0 + n // 2].tolist()))
+            lengths, rates = fc.normalise_lengths_and_rates(len_idx[c0: c0 + n // 2], site_cat[s0: s0 + L], grid, cats)
+            ref_tree = str(d / f"ref{f}.tree")
+            write_tree(fc.cherries_tree(names, pairs, lengths, int(unpaired[f])), ref_tree)
+            assert open(j(".tree")[f]).read() == open(ref_tree).read()
+            assert open(j(".newick")[f]).read() == fc._newick(names, pairs, lengths, int(unpaired[f]))
+            assert open(j(".rates")[f]).read() == f"{L} sites\n" + "".join(fc._fixed17(r) + " " for r in rates)
+            assert open(j(".ll")[f]).read() == "0.0"
+            p = prof[f]
+            assert open(j(".prof")[f]).read() == (f"pairing_time: {p[0]}\nble_time: {p[1]}\ncpp_time: {p[2]}\n"
+                                                   f"total_time: {p[3]}")
