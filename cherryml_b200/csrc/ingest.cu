@@ -76,12 +76,14 @@ std::vector<Span> strip_lines(const std::string& text) {
   while (b < e && is_py_space(text[b])) ++b;
   while (e > b && is_py_space(text[e - 1])) --e;
   std::vector<Span> lines;
+  const char* base = text.data();
   size_t s = b;
-  for (size_t i = b; i <= e; ++i) {
-    if (i == e || text[i] == '\n') {
-      lines.push_back(Span{text.data() + s, i - s});
-      s = i + 1;
-    }
+  while (s <= e) {
+    const char* nl = s < e ? (const char*)memchr(base + s, '\n', e - s) : nullptr;
+    const size_t stop = nl ? (size_t)(nl - base) : e;
+    lines.push_back(Span{base + s, stop - s});
+    if (!nl) break;
+    s = stop + 1;
   }
   return lines;
 }
@@ -507,7 +509,23 @@ void process_family(const Job& job, const std::string& fam, FamilyOut* out) {
           out->group_cat[(size_t)g] = (uint16_t)c;
       out->rate_vals = std::move(vals);
       out->rows.assign(n_rows * (size_t)stride, skip);
-      for (size_t r = 0; r < n_rows; ++r) {
+      // four rows per pass over the column permutation (dest[] is loaded once per four stores)
+      size_t r = 0;
+      for (; r + 4 <= n_rows; r += 4) {
+        uint8_t* row = out->rows.data() + r * (size_t)stride;
+        const unsigned char* s0 = reinterpret_cast<const unsigned char*>(seqs[r].p);
+        const unsigned char* s1 = reinterpret_cast<const unsigned char*>(seqs[r + 1].p);
+        const unsigned char* s2 = reinterpret_cast<const unsigned char*>(seqs[r + 2].p);
+        const unsigned char* s3 = reinterpret_cast<const unsigned char*>(seqs[r + 3].p);
+        for (size_t j = 0; j < L; ++j) {
+          uint8_t* d = row + dest[j];
+          d[0] = job.lut[s0[j]];
+          d[(size_t)stride] = job.lut[s1[j]];
+          d[2 * (size_t)stride] = job.lut[s2[j]];
+          d[3 * (size_t)stride] = job.lut[s3[j]];
+        }
+      }
+      for (; r < n_rows; ++r) {
         uint8_t* row = out->rows.data() + r * (size_t)stride;
         const unsigned char* s = reinterpret_cast<const unsigned char*>(seqs[r].p);
         for (size_t j = 0; j < L; ++j) row[dest[j]] = job.lut[s[j]];
