@@ -362,7 +362,7 @@ class NativeMsas:
 
 @cached_parallel_computation(
     parallel_arg="families",
-    exclude_args=["num_processes", "device"],
+    exclude_args=["num_processes", "device", "process_group"],
     exclude_args_if_default=["_version"],
     output_dirs=[
         "output_tree_dir",
@@ -389,13 +389,39 @@ def fast_cherries(
     verbose=True,
     seed=1234,
     device: str = "cuda",
+    process_group=None,
 ) -> None:
     """Same contract as the reference stage: per family ``<tree_dir>/<family>.txt`` (tree),
     ``.newick``, ``.profiling``; ``<site_rates_dir>/<family>.txt``; ``<likelihood_dir>/<family>.txt``
     (the constant 0.0).  ``num_processes`` and ``remake`` are accepted and ignored (one GPU
-    launch handles every family; there is no binary to rebuild)."""
+    launch handles every family; there is no binary to rebuild).
+
+    ``process_group`` (a torch.distributed group, one process per GPU): families are independent,
+    so rank r takes ``families[r::world]`` -- the striping of the reference's worker processes
+    (``get_process_args``, _fast_cherries.py:175-183) -- writes their files, and a barrier makes
+    every file exist before any rank returns.  No data-path collective."""
     for d in (output_tree_dir, output_site_rates_dir, output_likelihood_dir):
         os.makedirs(d, exist_ok=True)
+    if process_group is not None:
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(process_group), dist.get_world_size(process_group)
+        try:
+            _fast_cherries_local(msa_dir, families[rank::world], rate_matrix_path, num_rate_categories, max_iters,
+                                 output_tree_dir, output_site_rates_dir, output_likelihood_dir,
+                                 quantization_grid_center, quantization_grid_step, quantization_grid_num_steps,
+                                 seed, device)
+        finally:
+            dist.barrier(process_group)
+        return
+    _fast_cherries_local(msa_dir, families, rate_matrix_path, num_rate_categories, max_iters, output_tree_dir,
+                         output_site_rates_dir, output_likelihood_dir, quantization_grid_center,
+                         quantization_grid_step, quantization_grid_num_steps, seed, device)
+
+
+def _fast_cherries_local(msa_dir, families, rate_matrix_path, num_rate_categories, max_iters, output_tree_dir,
+                         output_site_rates_dir, output_likelihood_dir, quantization_grid_center,
+                         quantization_grid_step, quantization_grid_num_steps, seed, device) -> None:
     if not families:
         return
     t_start = time.time()

@@ -93,6 +93,27 @@ def main():
     add("synthetic_max_iters_1", synthetic_msa(rng, 40, 60), None, lg, 20, max_iters=1)
     add("synthetic_max_iters_0", synthetic_msa(rng, 40, 60), None, lg, 20, max_iters=0)
     add("synthetic_grid_8", synthetic_msa(rng, 40, 60), None, lg, 4, num_steps=8)
+    # other alphabets: DNA (4 states) and amino acids + a gap STATE (21 states)
+    def labelled(states, M):
+        return "\t" + "\t".join(states) + "\n" + "".join(
+            s + "\t" + "\t".join(repr(float(v)) for v in M[i]) + "\n" for i, s in enumerate(states))
+
+    hky = np.array([[0, 1, 4, 1], [1, 0, 1, 4], [4, 1, 0, 1], [1, 4, 1, 0]], dtype=float) * np.array([0.3, 0.2, 0.2, 0.3])
+    np.fill_diagonal(hky, -hky.sum(axis=1))
+    hky /= -(np.array([0.3, 0.2, 0.2, 0.3]) * np.diag(hky)).sum()
+    dna = synthetic_msa(rng, 30, 200, gap=0.1, mut=0.15)
+    dna = "\n".join(ln if ln.startswith(">") else ln.translate(str.maketrans(AA, "ACGT" * 5)) for ln in dna.split("\n"))
+    add("dna_hky_n30_L200_R4", dna, None, labelled(list("ACGT"), hky), 4)
+    lg_rows = [[float(v) for v in ln.split()[1:]] for ln in lg.strip().split("\n")[1:]]
+    Q21 = np.zeros((21, 21))
+    Q21[:20, :20] = np.array(lg_rows)
+    np.fill_diagonal(Q21, 0)
+    Q21[:20, 20] = 0.03
+    Q21[20, :20] = 0.4
+    np.fill_diagonal(Q21, -Q21.sum(axis=1))
+    add("aa_plus_gap_state_n25_L60_R20", synthetic_msa(rng, 25, 60, gap=0.25), None, labelled(list(AA) + ["-"], Q21), 20)
+    add("long_n12_L1300_R4", synthetic_msa(rng, 12, 1300), None, lg, 4)
+    add("many_n1500_L24_R1", synthetic_msa(rng, 1500, 24, mut=0.08), None, lg, 1)
     import gzip
 
     with gzip.open(os.path.join(OUT, "cases.json.gz"), "wt") as f:

@@ -125,3 +125,47 @@ def test_assign_buckets_is_a_balanced_partition():
         assert max(loads) - min(loads) <= cost.max()
         again = assign_buckets(grid, world, rate_scale=1.1)  # deterministic: every rank gets the same answer
         assert all(np.array_equal(a, b) for a, b in zip(parts, again))
+
+
+def _fc_worker(rank, world, port, msa_dir, out_root, families):
+    """Two ranks run the sharded FastCherries stage with the per-rank GPU work replaced by its
+    oracle (this test is about the striping, the files and the barrier, not the kernels)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cherryml_b200.phylogeny_estimation import _fast_cherries as fc
+
+    seen = []
+
+    def fake_local(msa_dir, fams, rate_matrix_path, R, max_iters, tree_dir, rates_dir, ll_dir, *rest):
+        seen.extend(fams)
+        for f in fams:
+            for d in (tree_dir, rates_dir, ll_dir):
+                with open(os.path.join(d, f + ".txt"), "w") as fh:
+                    fh.write(f"rank {rank}\n")
+
+    fc._fast_cherries_local = fake_local
+    dirs = [os.path.join(out_root, k) for k in ("tree", "rates", "ll")]
+    fc.fast_cherries(msa_dir=msa_dir, families=families, rate_matrix_path="unused", num_rate_categories=4,
+                     max_iters=50, num_processes=1, output_tree_dir=dirs[0], output_site_rates_dir=dirs[1],
+                     output_likelihood_dir=dirs[2], process_group=dist.group.WORLD)
+    # after the call returns on ANY rank, every family's files exist (the barrier)
+    ok = all(os.path.exists(os.path.join(d, f + ".txt")) for d in dirs for f in families)
+    with open(os.path.join(out_root, f"seen_{rank}.txt"), "w") as fh:
+        fh.write(("ok" if ok else "missing") + "\n" + " ".join(seen))
+    dist.destroy_process_group()
+
+
+def test_two_rank_fast_cherries_stage_stripes_families(tmp_path):
+    families = [f"fam{i}" for i in range(7)]
+    mp.spawn(_fc_worker, args=(2, _free_port(), str(tmp_path), str(tmp_path), families), nprocs=2, join=True)
+    seen = []
+    for rank in range(2):
+        status, fams = open(tmp_path / f"seen_{rank}.txt").read().split("\n")
+        assert status == "ok"
+        assert fams.split() == sorted(families)[rank::2]
+        seen += fams.split()
+    assert sorted(seen) == sorted(families)
+    for f in families:
+        owner = sorted(families).index(f) % 2
+        assert open(tmp_path / "tree" / f"{f}.txt").read() == f"rank {owner}\n"

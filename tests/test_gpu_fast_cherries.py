@@ -228,3 +228,44 @@ def test_tree_free_lg_pipeline_counts_match_reference_trees(tmp_path):
     assert res["tree_estimator_output_dirs_1"]["output_tree_dir"] != res["tree_estimator_output_dirs_0"]["output_tree_dir"]
     Q = read_rate_matrix(res["learned_rate_matrix_path"]).to_numpy()
     assert Q.shape == (20, 20) and np.allclose(Q.sum(axis=1), 0, atol=1e-5) and (Q - np.diag(np.diag(Q)) >= 0).all()
+
+
+def test_stage_with_process_group_shards_families(tmp_path):
+    """A one-rank NCCL group drives the sharded code path (stripe, barrier); outputs equal the
+    plain call's."""
+    import torch
+    import torch.distributed as dist
+
+    from cherryml_b200.phylogeny_estimation import fast_cherries
+
+    msa_dir = tmp_path / "msas"
+    msa_dir.mkdir()
+    fams = []
+    for c in CASES:
+        if c["name"] in ("synthetic_n16_L48_R4", "synthetic_n33_L100_R4", "synthetic_n7_L40_R4"):
+            (msa_dir / f"{c['name']}.txt").write_text(c["msa_text"])
+            fams.append(c["name"])
+    qp = tmp_path / "Q.txt"
+    qp.write_text(CASES[0]["rate_matrix_text"])
+    created = not dist.is_initialized()
+    if created:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        kw = dict(msa_dir=str(msa_dir), families=fams, rate_matrix_path=str(qp), num_rate_categories=4, max_iters=50,
+                  num_processes=1, verbose=False)
+        dirs = {}
+        for tag, pg in (("plain", None), ("group", dist.group.WORLD)):
+            dirs[tag] = {k: str(tmp_path / f"{tag}_{k}") for k in ("tree", "rates", "ll")}
+            fast_cherries(output_tree_dir=dirs[tag]["tree"], output_site_rates_dir=dirs[tag]["rates"],
+                          output_likelihood_dir=dirs[tag]["ll"], process_group=pg, **kw)
+    finally:
+        if created:
+            dist.destroy_process_group()
+    for f in fams:
+        for k in ("tree", "rates", "ll"):
+            plain = open(os.path.join(dirs["plain"][k], f + ".txt")).read()
+            assert plain == open(os.path.join(dirs["group"][k], f + ".txt")).read()
+        case = next(c for c in CASES if c["name"] == f)
+        assert open(os.path.join(dirs["group"]["rates"], f + ".txt")).read() == case["site_rates_file"]
