@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--no-fit", action="store_true")
     ap.add_argument("--no-fast-cherries", action="store_true")
     ap.add_argument("--fc-families", type=int, default=2048, help="FastCherries families per GPU")
+    ap.add_argument("--no-likelihood", action="store_true")
     return ap.parse_args()
 
 
@@ -419,6 +420,14 @@ def run_ours(args):
             fcb["families_per_s_e2e"] = fam_all / fcb["e2e_seconds"]
             fcb["residues_per_s_e2e"] = fam_all * 1024 * 300 / fcb["e2e_seconds"]
             fcb["n_gpus"] = world
+    llb = None
+    if rank == 0 and not args.no_likelihood:
+        from cherryml_b200.evaluation._bench import bench_likelihood
+
+        try:
+            llb = bench_likelihood(device, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
+        except Exception as e:  # never lose the bench line over an extra section
+            llb = {"error": str(e)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -453,6 +462,8 @@ def run_ours(args):
         line["fit"] = fit
     if fcb is not None:
         line["fast_cherries"] = fcb
+    if llb is not None:
+        line["tree_likelihood"] = llb
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_cpu_fam = args.cpu_families or default_cpu_families()
