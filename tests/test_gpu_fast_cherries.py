@@ -269,3 +269,44 @@ def test_stage_with_process_group_shards_families(tmp_path):
             assert plain == open(os.path.join(dirs["group"][k], f + ".txt")).read()
         case = next(c for c in CASES if c["name"] == f)
         assert open(os.path.join(dirs["group"]["rates"], f + ".txt")).read() == case["site_rates_file"]
+
+
+def test_tree_free_coevolution_pipeline(tmp_path):
+    """cherryml_public_api(model_name="co-evolution", tree_estimator_name="FastCherries") from MSAs
+    and contact maps alone: trees come from the GPU FastCherries stage; the co-transition counts
+    equal those counted on the trees the stage wrote."""
+    import tarfile
+
+    from cherryml_b200 import caching, cherryml_public_api
+    from cherryml_b200.counting import count_co_transitions
+    from cherryml_b200._public_api import _quantization_points, create_maximal_matching_contact_map
+    from cherryml_b200.io import read_rate_matrix
+    from cherryml_b200.utils import get_amino_acids
+    from tests.conftest import GOLDEN
+
+    fams = ["13gs_1_A", "1a0b_1_A"]
+    with tarfile.open(os.path.join(GOLDEN, "demo_data.tar.xz")) as tf:
+        tf.extractall(tmp_path, members=[tf.getmember(f"{d}/{f}.txt") for d in ("msas", "contact_maps") for f in fams])
+    cache, out = str(tmp_path / "cache"), str(tmp_path / "learned.txt")
+    try:
+        cherryml_public_api(output_path=out, model_name="co-evolution", msa_dir=str(tmp_path / "msas"),
+                            contact_map_dir=str(tmp_path / "contact_maps"), cache_dir=cache, num_epochs=6,
+                            num_rate_categories=1, families=fams, tree_estimator_name="FastCherries",
+                            use_cpp_counting_implementation=False)
+        (h,) = os.listdir(os.path.join(cache, "fast_cherries"))
+        tree_dir = os.path.join(cache, "fast_cherries", h, "output_tree_dir")
+        (h2,) = os.listdir(os.path.join(cache, "count_co_transitions"))
+        ours = open(os.path.join(cache, "count_co_transitions", h2, "output_count_matrices_dir", "result.txt")).read()
+        caching.set_cache_dir(str(tmp_path / "cache2"))
+        cm = create_maximal_matching_contact_map(i_contact_map_dir=str(tmp_path / "contact_maps"), families=fams,
+                                                 minimum_distance_for_nontrivial_contact=7, num_processes=1)
+        again = count_co_transitions(
+            tree_dir=tree_dir, msa_dir=str(tmp_path / "msas"), contact_map_dir=cm["o_contact_map_dir"], families=fams,
+            amino_acids=get_amino_acids(), quantization_points=_quantization_points(0.03, 1.1, 64),
+            edge_or_cherry="cherry++", minimum_distance_for_nontrivial_contact=7, num_processes=1,
+            use_cpp_implementation=False)["output_count_matrices_dir"]
+    finally:
+        caching.set_cache_dir(None)
+    assert ours == open(os.path.join(again, "result.txt")).read()
+    Q = read_rate_matrix(out).to_numpy()
+    assert Q.shape == (400, 400) and np.allclose(Q.sum(axis=1), 0, atol=1e-4)
