@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--no-fast-cherries", action="store_true")
     ap.add_argument("--fc-families", type=int, default=2048, help="FastCherries families per GPU")
     ap.add_argument("--no-likelihood", action="store_true")
+    ap.add_argument("--no-siterm", action="store_true")
     return ap.parse_args()
 
 
@@ -428,6 +429,14 @@ def run_ours(args):
             llb = bench_likelihood(device, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
         except Exception as e:  # never lose the bench line over an extra section
             llb = {"error": str(e)[:300]}
+    srb = None
+    if rank == 0 and not args.no_siterm:
+        from cherryml_b200.siterm._bench import bench_siterm
+
+        try:
+            srb = bench_siterm(device, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
+        except Exception as e:
+            srb = {"error": str(e)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -464,6 +473,8 @@ def run_ours(args):
         line["fast_cherries"] = fcb
     if llb is not None:
         line["tree_likelihood"] = llb
+    if srb is not None:
+        line["siterm"] = srb
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_cpu_fam = args.cpu_families or default_cpu_families()

@@ -1,0 +1,95 @@
+"""bench.py's SiteRM section (BASELINE config 5): plant-dataset-shaped families (38 sequences x
+331 sites), FastCherries trees, batched per-site fits -- ``learn_site_specific_rate_matrices``
+with ``tree=None`` end to end per family; beside it, on rank 0 at N = 1, the torch-CPU oracle
+port of the reference's batched fit on the count tensors of one family."""
+import time
+from typing import Dict
+
+import numpy as np
+
+from ..io import read_rate_matrix
+from ..markov_chain import get_lg_path
+from ..utils import amino_acids
+
+N_SEQS, N_SITES, NUM_EPOCHS, GRID_STEPS = 38, 331, 100, 8
+
+
+def _plant_family(rng) -> Dict[str, str]:
+    aa = np.array(amino_acids)
+    root = rng.integers(0, 20, N_SITES)
+    div = rng.uniform(0.02, 0.6, N_SITES)  # slow and fast sites
+    msa = {}
+    for k in range(N_SEQS // 2):
+        anc = np.where(rng.random(N_SITES) < div, rng.integers(0, 20, N_SITES), root)
+        for j in range(2):
+            leaf = np.where(rng.random(N_SITES) < 0.4 * div, rng.integers(0, 20, N_SITES), anc)
+            s = aa[leaf]
+            s[rng.random(N_SITES) < 0.08] = "-"
+            msa[f"seq{2 * k + j}"] = "".join(s)
+    return msa
+
+
+def bench_siterm(device, families: int = 8, cpu_baseline: bool = True, seed: int = 0) -> Dict:
+    from . import (estimate_site_specific_rate_matrices_given_tree_and_site_rates,  # noqa: F401
+                   learn_site_specific_rate_matrices)
+
+    rng = np.random.default_rng(seed)
+    lg = read_rate_matrix(get_lg_path())
+    msas = [_plant_family(rng) for _ in range(families)]
+    kw = dict(tree=None, alphabet=list(amino_acids), regularization_rate_matrix=lg, regularization_strength=0.5,
+              device=str(device), num_epochs=NUM_EPOCHS, quantization_grid_num_steps=GRID_STEPS)
+    learn_site_specific_rate_matrices(msa=msas[0], **kw)  # warm-up
+    t0 = time.perf_counter()
+    results = [learn_site_specific_rate_matrices(msa=m, **kw) for m in msas]
+    wall = time.perf_counter() - t0
+    keys = ("time_estimate_tree", "time_get_raw_count_matrices", "time_get_pseudocount_matrices", "time_compute_loss")
+    out = {
+        "workload": f"{families} plant-shaped families x {N_SEQS} seqs x {N_SITES} sites, FastCherries trees (20 rate "
+                    f"categories), lambda 0.5, Q0 = LG, {2 * GRID_STEPS + 1} grid points, {NUM_EPOCHS} Adam epochs, "
+                    "one learn_site_specific_rate_matrices call per family",
+        "seconds_per_family": wall / families, "sites_per_s": families * N_SITES / wall,
+        "seconds_by_stage_per_family": {k: float(np.mean([r.get(k, 0.0) for r in results])) for k in keys},
+    }
+    if cpu_baseline:
+        from oracle.siterm_oracle import fit_sites
+
+        # the same regularised, compacted count tensors the GPU fit consumed, rebuilt for family 0
+        import torch
+
+        from ._site_specific import estimate_site_specific_rate_matrices_given_tree_and_site_rates as stage
+        from . import _site_specific as mod
+
+        captured = {}
+        real = mod.quantized_transitions_mle_vectorized_over_sites
+
+        def spy(**kwargs):
+            captured.update(kwargs)
+            return real(**kwargs)
+
+        mod.quantized_transitions_mle_vectorized_over_sites = spy
+        try:
+            r0 = results[0]
+            step = 1.1 ** (64 / GRID_STEPS)
+            gpu = stage(tree=r0["learnt_tree"], site_rates=r0["learnt_site_rates"], msa=msas[0],
+                        alphabet=list(amino_acids), regularization_strength=0.5,
+                        regularization_rate_matrix=lg.to_numpy(),
+                        quantization_points=[0.03 * step ** i for i in range(-GRID_STEPS, GRID_STEPS + 1)],
+                        optimization_num_epochs=NUM_EPOCHS, vectorized_cherryml_implementation_device=str(device))
+        finally:
+            mod.quantized_transitions_mle_vectorized_over_sites = real
+        import os
+
+        cores = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        cpu = fit_sites(captured["counts"], captured["times"], NUM_EPOCHS, captured["initialization"],
+                        num_threads=cores)
+        cpu_s = time.perf_counter() - t0
+        torch.set_num_threads(1)
+        out["cpu_baseline"] = {
+            "value": cpu_s, "unit": "s per family (batched fit only)", "cores": cores, "kind": "port",
+            "sample": f"the {N_SITES} per-site problems of one family, torch-CPU restatement of the reference's "
+                      "quantized_transitions_mle_vectorized_over_sites (oracle/siterm_oracle.py)",
+            "gpu_seconds_same_stage": float(gpu.get("time_compute_loss", 0.0)),
+        }
+        out["matches_oracle_1e-6"] = bool(np.max(np.abs(cpu["res"] - gpu["res"])) < 1e-6 * np.max(np.abs(cpu["res"])))
+    return out

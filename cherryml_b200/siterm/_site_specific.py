@@ -19,7 +19,7 @@ import torch
 
 from ..io import Tree
 from ..markov_chain import compute_stationary_distribution, expm_batched
-from ..utils import quantization_idx
+from ..utils import quantization_idx_array
 from ._counting import get_raw_count_matrices_device
 from ._vectorized import quantized_transitions_mle_vectorized_over_sites
 
@@ -109,14 +109,9 @@ def estimate_site_specific_rate_matrices_given_tree_and_site_rates(
 
     st = time.time()
     # bucket of t_b * site_rate (clamped to the grid's ends, reference :519-545)
-    b_adj = np.zeros((L, B), dtype=np.int64)
-    for l in range(L):
-        for b in range(B):
-            t = q[b] * site_rates[l]
-            k = quantization_idx(t, q)
-            if k is None:
-                k = B - 1 if t > q[-1] else 0
-            b_adj[l, b] = k
+    scaled = np.asarray(site_rates, dtype=np.float64)[:, None] * np.asarray(q)[None, :]  # t_b * rate_l
+    b_adj = quantization_idx_array(scaled, q)
+    b_adj = np.where(b_adj >= 0, b_adj, np.where(scaled > q[-1], B - 1, 0)).astype(np.int64)
     l1 = raw.sum(dim=(2, 3))  # [L, B]
     pseudo = l1[:, :, None, None] * prior[torch.from_numpy(b_adj).to(raw.device)]
     raw_sum, pseudo_sum = float(raw.sum()), float(pseudo.sum())

@@ -33,6 +33,23 @@ def quantization_idx(
     return ub
 
 
+def quantization_idx_array(branch_lengths, quantization_points_sorted):
+    """``quantization_idx`` for an array of branch lengths (same fp64 expressions, evaluated by
+    numpy); -1 where the scalar function returns ``None``."""
+    import numpy as np
+
+    q = np.asarray(quantization_points_sorted, dtype=np.float64)
+    t = np.asarray(branch_lengths, dtype=np.float64)
+    ub = np.searchsorted(q, t, side="left")
+    inside = (t >= q[0]) & (t <= q[-1])
+    ubc = np.clip(ub, 1, len(q) - 1)
+    left, right = q[ubc - 1], q[ubc]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        choose_left = (t / left - 1) < (right / t - 1)
+    idx = np.where(ub == 0, 0, np.where(choose_left, ubc - 1, ubc))
+    return np.where(inside, idx, -1)
+
+
 def get_process_args(process_rank: int, num_processes: int, all_args: List) -> List:
     """Rank ``r`` of ``P`` owns items ``r, r+P, r+2P, ...`` (the reference's striping)."""
     return list(all_args[process_rank::num_processes])
