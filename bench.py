@@ -492,10 +492,30 @@ def run_ours(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE line (the JSON): libraries that print banners to file descriptor 1
+    # (NCCL's version line at N > 1) are pointed at stderr, the JSON goes to the original stdout
+    import builtins
+
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    plain_print = builtins.print
+
+    def json_print(*a, **k):
+        if len(a) == 1 and isinstance(a[0], str) and a[0].startswith("{") and "file" not in k:
+            real_stdout.write(a[0] + "\n")
+            real_stdout.flush()
+        else:
+            plain_print(*a, **k)
+
+    builtins.print = json_print
+    try:
+        if args.impl == "reference":
+            run_reference_arm(args)
+        else:
+            run_ours(args)
+    finally:
+        builtins.print = plain_print
 
 
 if __name__ == "__main__":
