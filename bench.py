@@ -239,7 +239,9 @@ def text_e2e_run(n_families, seed=0, reps=3):
     return {"value": examined / best, "unit": UNIT, "seconds": best, "seconds_ingest": ingest_s,
             "host_threads": cores,
             "sample": f"{n_families} of the workload's families as text files ({examined} transitions): "
-                      "cherry_ingest_lg (parse + encode) -> cherry_count_lg_host; same input as cpu_baseline"}
+                      "cherry_ingest_lg (parse + encode) -> cherry_count_lg_host; same input as cpu_baseline; "
+                      "best of the passes after the first (the page-locked staging buffer is pooled: the first "
+                      "batch of a process also pays for pinning it, ~0.2 ms per MB)"}
 
 
 def run_reference_arm(args):

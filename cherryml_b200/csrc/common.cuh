@@ -34,4 +34,17 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 int sm_count();  // SMs of the current device (cached per device)
 
+// The host-side text readers/writers allocate a few buffers of 0.1-1 MB per family (file text,
+// encoded rows).  glibc serves allocations of that size by mmap/munmap, which serialises the
+// worker threads on the address-space lock and page-faults every buffer in afresh (measured:
+// 1.6x of the whole ingest).  Called once by the multithreaded entry points: raises glibc's
+// mmap threshold so that those buffers live on the per-thread heaps.
+void keep_large_buffers_on_heap();
+
+// Page-locked host buffers for the encoded batches.  Pinning costs ~0.2 ms per MB, more than
+// parsing the batch that goes into it, so released buffers are kept (at most two) and handed
+// out again to the next batch that fits.  nullptr if pinned memory is unavailable.
+void* pinned_alloc(size_t bytes);
+void pinned_free(void* p);
+
 }  // namespace cherry

@@ -188,6 +188,7 @@ int cherry_fc_read_msas(const char* const* paths, int n_fams, const char* const*
     if (!states[i] || strlen(states[i]) != 1) return cherry::fail(CHERRY_EINVAL, "states must be single characters");
     lut[(unsigned char)states[i][0]] = (uint8_t)i;
   }
+  cherry::keep_large_buffers_on_heap();
   std::vector<ParsedMsa> parsed((size_t)n_fams);
   std::string err;
   parallel_for(n_fams, n_threads, [&](int f) {
@@ -252,10 +253,10 @@ int cherry_fc_read_msas(const char* const* paths, int n_fams, const char* const*
   r->total_sites = site_off;
   r->total_cherries = cherry_off;
   const size_t alloc = (size_t)std::max<int64_t>(64, off);
-  if (pinned && cudaHostAlloc((void**)&r->msa, alloc, cudaHostAllocDefault) == cudaSuccess) {
+  if (pinned) r->msa = (uint8_t*)cherry::pinned_alloc(alloc);
+  if (r->msa) {
     r->pinned = 1;
   } else {
-    cudaGetLastError();
     void* p = nullptr;
     if (posix_memalign(&p, 64, alloc) != 0) p = nullptr;
     r->msa = (uint8_t*)p;
@@ -295,7 +296,7 @@ int cherry_fc_read_msas(const char* const* paths, int n_fams, const char* const*
 void cherry_fc_free_msas(cherry_fc_msas* r) {
   if (!r) return;
   if (r->msa) {
-    if (r->pinned) cudaFreeHost(r->msa); else free(r->msa);
+    if (r->pinned) cherry::pinned_free(r->msa); else free(r->msa);
   }
   free(r->fams);
   free(r->name_blob);
@@ -313,6 +314,7 @@ int cherry_fc_write_outputs(const cherry_fc_msas* m, const int32_t* pair_a, cons
   if (!m || !pair_a || !pair_b || !unpaired || !len_idx || !site_cat || !grid || !cats || !tree_paths ||
       !site_rate_paths)
     return cherry::fail(CHERRY_EINVAL, "null pointer");
+  cherry::keep_large_buffers_on_heap();
   std::string err;
   parallel_for(m->n_fams, n_threads, [&](int f) {
     const cherry_fc_family& d = m->fams[f];

@@ -14,6 +14,7 @@
 // Branch lengths: `float32_branch_lengths` parses them with strtof exactly like the C++
 // program's std::stof (.cpp:247); otherwise strtod (Python float()).
 #include <algorithm>
+#include <mutex>
 #include <atomic>
 #include <cerrno>
 #include <cmath>
@@ -565,6 +566,7 @@ T* alloc_array(size_t n) {
 
 int run_ingest(Job& job, int n_threads, int pinned, cherry_ingest_result** out_ptr) {
   const int F = (int)job.families.size();
+  cherry::keep_large_buffers_on_heap();
   std::vector<FamilyOut> fam_out((size_t)F);
   std::atomic<int> next{0};
   std::atomic<bool> failed{false};
@@ -634,12 +636,10 @@ int run_ingest(Job& job, int n_threads, int pinned, cherry_ingest_result** out_p
   R->msa_bytes = std::max<int64_t>(16, msa_bytes);
   R->pinned = 0;
   if (pinned) {
-    void* p = nullptr;
-    if (cudaHostAlloc(&p, (size_t)R->msa_bytes, cudaHostAllocDefault) == cudaSuccess) {
+    void* p = cherry::pinned_alloc((size_t)R->msa_bytes);  // nullptr without a device: pageable memory
+    if (p) {
       R->msa = reinterpret_cast<uint8_t*>(p);
       R->pinned = 1;
-    } else {
-      cudaGetLastError();  // no device / no pinned memory: fall back to pageable memory
     }
   }
   if (!R->msa) R->msa = alloc_array<uint8_t>((size_t)R->msa_bytes);
@@ -769,7 +769,7 @@ int cherry_ingest_co(const char* tree_dir, const char* msa_dir, const char* cont
 void cherry_ingest_free(cherry_ingest_result* r) {
   if (!r) return;
   if (r->msa) {
-    if (r->pinned) cudaFreeHost(r->msa); else free(r->msa);
+    if (r->pinned) cherry::pinned_free(r->msa); else free(r->msa);
   }
   free(r->fams); free(r->pair_a); free(r->pair_b); free(r->pair_t); free(r->pair_fam);
   free(r->rate_vals); free(r->aux); free(r->tiles);

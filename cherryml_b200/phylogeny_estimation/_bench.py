@@ -162,7 +162,8 @@ def bench_fast_cherries(device, families: int = 2048, reps: int = 3, cpu_baselin
                 "value": n / best_text[0], "unit": "families/s", "seconds": best_text[0],
                 "seconds_read_and_device": best_text[1], "host_threads": cores,
                 "sample": f"the same {n} MSA text files as cpu_baseline -> tree, newick, site-rate, likelihood and "
-                          "profiling files (cherry_fc_read_msas -> cherry_fc_pair/_ble -> cherry_fc_write_outputs)",
+                          "profiling files (cherry_fc_read_msas -> cherry_fc_pair/_ble -> cherry_fc_write_outputs); "
+                          "best of 3 passes, pooled page-locked staging buffer",
             }
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
