@@ -123,6 +123,36 @@ void py_repr(double x, std::string* out) {
   }
 }
 
+// Positive multiples of 1/4 (what count matrices hold) without going through to_chars / printf.
+// Python repr: "<int>.0|.25|.5|.75" below 1e16; "%g": the same digits without a trailing ".0"
+// as long as they fit in 6 significant digits.  Returns false when the general path must be used.
+bool quarter_fast(double v, int cpp_style, std::string* out) {
+  if (!(v > 0.0) || v >= 4503599627370496.0) return false;
+  const double ipart = std::floor(v);
+  const double f4 = (v - ipart) * 4.0;
+  const int fi = (int)f4;
+  if ((double)fi != f4) return false;
+  const unsigned long long ip = (unsigned long long)ipart;
+  if (cpp_style) {
+    const unsigned long long limit = fi == 0 ? 1000000ull : fi == 2 ? 100000ull : 10000ull;
+    if (ip >= limit) return false;
+  } else if (ip >= 10000000000000000ull) {
+    return false;
+  }
+  char buf[24];
+  int n = 0;
+  unsigned long long t = ip;
+  do {
+    buf[n++] = (char)('0' + t % 10);
+    t /= 10;
+  } while (t);
+  while (n) *out += buf[--n];
+  static const char* suffix_py[4] = {".0", ".25", ".5", ".75"};
+  static const char* suffix_g[4] = {"", ".25", ".5", ".75"};
+  *out += cpp_style ? suffix_g[fi] : suffix_py[fi];
+  return true;
+}
+
 void fixed17(double x, std::string* out) {
   char buf[400];
   const int n = snprintf(buf, sizeof(buf), "%.17f", x);
@@ -386,6 +416,223 @@ int cherry_fc_write_outputs(const cherry_fc_msas* m, const int32_t* pair_a, cons
     }
   }, &err);
   if (!err.empty()) return cherry::fail(CHERRY_EINVAL, "%s", err.c_str());
+  return CHERRY_OK;
+}
+
+
+// ------------------------------------------------------------------ count matrices (result.txt)
+// The reference's two writers: io/_count_matrices.py:66-81 (pandas to_csv, repr floats) and the
+// C++ program's writer (counting/_count_transitions.cpp:524-548, ostream << double = "%g").
+
+int cherry_write_count_matrices(const char* path, const double* q, int K, const char* const* states, int S,
+                                const double* counts, int cpp_style, int n_threads) {
+  if (!path || !q || !states || !counts || K < 0 || S < 1) return cherry::fail(CHERRY_EINVAL, "null pointer");
+  cherry::keep_large_buffers_on_heap();
+  std::string header;
+  if (cpp_style) {
+    header = "\t";
+    for (int i = 0; i < S; ++i) header += std::string(states[i]) + "\t";
+  } else {
+    for (int i = 0; i < S; ++i) header += "\t" + std::string(states[i]);
+  }
+  header += "\n";
+  std::vector<std::string> blocks((size_t)K);
+  std::string err;
+  parallel_for(K, n_threads, [&](int k) {
+    std::string& b = blocks[(size_t)k];
+    b.reserve((size_t)S * S * 5 + header.size() + 64);
+    char buf[64];
+    if (cpp_style) {
+      b.append(buf, (size_t)snprintf(buf, sizeof(buf), "%g", q[k]));
+    } else {
+      py_repr(q[k], &b);
+    }
+    b += '\n';
+    b += header;
+    const double* m = counts + (size_t)k * S * S;
+    for (int i = 0; i < S; ++i) {
+      b += states[i];
+      for (int j = 0; j < S; ++j) {
+        const double v = m[(size_t)i * S + j];
+        b += '\t';
+        if (v == 0.0 && !std::signbit(v)) {
+          b += cpp_style ? "0" : "0.0";
+        } else if (quarter_fast(v, cpp_style, &b)) {
+          // counts are multiples of 1/4: integer digits + one of four suffixes
+        } else if (cpp_style) {
+          b.append(buf, (size_t)snprintf(buf, sizeof(buf), "%g", v));
+        } else {
+          py_repr(v, &b);
+        }
+      }
+      b += '\n';
+    }
+  }, &err);
+  if (!err.empty()) return cherry::fail(CHERRY_EINVAL, "%s", err.c_str());
+  try {
+    int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    if (fd < 0) throw IoErr{std::string("cannot write ") + path + ": " + strerror(errno)};
+    auto put = [&](const std::string& t) {
+      size_t done = 0;
+      while (done < t.size()) {
+        ssize_t r = write(fd, t.data() + done, t.size() - done);
+        if (r < 0) {
+          if (errno == EINTR) continue;
+          close(fd);
+          throw IoErr{std::string("cannot write ") + path};
+        }
+        done += (size_t)r;
+      }
+    };
+    put(std::to_string(K) + " matrices\n" + std::to_string(S) + " states\n");
+    for (const std::string& b : blocks) put(b);
+    close(fd);
+  } catch (const IoErr& e) {
+    return cherry::fail(CHERRY_EINVAL, "%s", e.msg.c_str());
+  }
+  return CHERRY_OK;
+}
+
+namespace {
+struct CountFile {
+  std::string text;
+  std::vector<size_t> line_start;  // offsets of the lines of text.strip().split("\n"), + end sentinel
+  size_t end = 0;
+};
+
+bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
+
+void index_lines(CountFile* f) {
+  const std::string& t = f->text;
+  size_t b = 0, e = t.size();
+  while (b < e && is_ws(t[b])) ++b;
+  while (e > b && is_ws(t[e - 1])) --e;
+  f->end = e;
+  size_t s = b;
+  while (s <= e) {
+    f->line_start.push_back(s);
+    const char* nl = s < e ? (const char*)memchr(t.data() + s, '\n', e - s) : nullptr;
+    if (!nl) break;
+    s = (size_t)(nl - t.data()) + 1;
+  }
+}
+
+// "<n> <word>" (after strip) -> n, or -1
+long long header_number(const CountFile& f, size_t line, const char* word) {
+  if (line >= f.line_start.size()) return -1;
+  const size_t a = f.line_start[line];
+  const size_t b = line + 1 < f.line_start.size() ? f.line_start[line + 1] - 1 : f.end;
+  std::string ln(f.text.data() + a, b - a);
+  while (!ln.empty() && is_ws(ln.back())) ln.pop_back();
+  size_t st = 0;
+  while (st < ln.size() && is_ws(ln[st])) ++st;
+  const size_t sp = ln.find(' ', st);
+  if (sp == std::string::npos || ln.substr(sp + 1) != word) return -1;
+  char* endp = nullptr;
+  const long long n = strtoll(ln.c_str() + st, &endp, 10);
+  if (endp != ln.c_str() + sp || n < 0) return -1;
+  return n;
+}
+}  // namespace
+
+int cherry_read_count_matrices_header(const char* path, int* K_out, int* S_out) {
+  if (!path || !K_out || !S_out) return cherry::fail(CHERRY_EINVAL, "null pointer");
+  try {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) throw IoErr{std::string("cannot open ") + path + ": " + strerror(errno)};
+    char buf[256];
+    const ssize_t n = read(fd, buf, sizeof(buf) - 1);
+    close(fd);
+    CountFile f;
+    f.text.assign(buf, n > 0 ? (size_t)n : 0);
+    // only the first two lines matter here; cut at the second newline
+    size_t nl1 = f.text.find('\n');
+    size_t nl2 = nl1 == std::string::npos ? nl1 : f.text.find('\n', nl1 + 1);
+    if (nl2 != std::string::npos) f.text.resize(nl2);
+    index_lines(&f);
+    const long long K = header_number(f, 0, "matrices"), S = header_number(f, 1, "states");
+    if (K < 0) throw IoErr{std::string("In file ") + path + ", expected line '[num_matrices] matrices'"};
+    if (S < 0) throw IoErr{std::string("In file ") + path + ", expected line '[num_states] states'"};
+    *K_out = (int)K;
+    *S_out = (int)S;
+  } catch (const IoErr& e) {
+    return cherry::fail(CHERRY_EINVAL, "%s", e.msg.c_str());
+  }
+  return CHERRY_OK;
+}
+
+int cherry_read_count_matrices(const char* path, int K, int S, double* q, double* counts, char* states_out,
+                               size_t states_cap, int n_threads) {
+  if (!path || !q || !counts || !states_out) return cherry::fail(CHERRY_EINVAL, "null pointer");
+  cherry::keep_large_buffers_on_heap();
+  CountFile f;
+  try {
+    f.text = slurp(path);
+  } catch (const IoErr& e) {
+    return cherry::fail(CHERRY_EINVAL, "%s", e.msg.c_str());
+  }
+  index_lines(&f);
+  if ((long long)f.line_start.size() < 2 + (long long)K * (S + 2))
+    return cherry::fail(CHERRY_EINVAL, "count matrices file %s is truncated", path);
+  auto line = [&](size_t i, const char** a, const char** b) {
+    *a = f.text.data() + f.line_start[i];
+    *b = f.text.data() + (i + 1 < f.line_start.size() ? f.line_start[i + 1] - 1 : f.end);
+  };
+  std::vector<std::string> state_names((size_t)K ? (size_t)S : 0);
+  std::string err;
+  parallel_for(K, n_threads, [&](int k) {
+    const size_t l0 = 2 + (size_t)k * (S + 2);
+    const char *a, *b;
+    line(l0, &a, &b);
+    {
+      std::string tok(a, (size_t)(b - a));
+      char* endp = nullptr;
+      q[k] = strtod(tok.c_str(), &endp);
+      while (*endp && is_ws(*endp)) ++endp;
+      if (endp == tok.c_str() || *endp) throw IoErr{"count matrices: bad quantization point '" + tok + "'"};
+    }
+    line(l0 + 1, &a, &b);
+    int n_hdr = 0;
+    for (const char* p = a; p < b;) {
+      while (p < b && is_ws(*p)) ++p;
+      const char* s0 = p;
+      while (p < b && !is_ws(*p)) ++p;
+      if (p > s0) {
+        if (k == K - 1 && n_hdr < S) state_names[(size_t)n_hdr].assign(s0, (size_t)(p - s0));
+        ++n_hdr;
+      }
+    }
+    if (n_hdr != S)
+      throw IoErr{"Error reading count matrices file: expected " + std::to_string(S) + " states in a header line, found " +
+                  std::to_string(n_hdr)};
+    double* m = counts + (size_t)k * S * S;
+    for (int i = 0; i < S; ++i) {
+      line(l0 + 2 + (size_t)i, &a, &b);
+      const char* p = a;
+      while (p < b && is_ws(*p)) ++p;
+      while (p < b && !is_ws(*p)) ++p;  // the row label
+      int got = 0;
+      while (p < b) {
+        while (p < b && is_ws(*p)) ++p;
+        if (p >= b) break;
+        char* endp = nullptr;
+        const double v = strtod(p, &endp);  // the buffer ends with a NUL (std::string), tokens end at whitespace
+        if (endp == p) throw IoErr{"Could not read count matrices: bad number"};
+        if (got < S) m[(size_t)i * S + got] = v;
+        ++got;
+        p = endp;
+      }
+      if (got != S) throw IoErr{"Could not read count matrices. Matrix " + std::to_string(k) + " is ragged"};
+    }
+  }, &err);
+  if (!err.empty()) return cherry::fail(CHERRY_EINVAL, "%s", err.c_str());
+  std::string blob;
+  for (int i = 0; i < S && K > 0; ++i) {
+    blob += state_names[(size_t)i];
+    blob += '\n';
+  }
+  if (blob.size() + 1 > states_cap) return cherry::fail(CHERRY_EINVAL, "states buffer too small");
+  memcpy(states_out, blob.c_str(), blob.size() + 1);
   return CHERRY_OK;
 }
 

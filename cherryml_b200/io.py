@@ -253,7 +253,38 @@ def write_contact_map(contact_map: np.ndarray, contact_map_path: str) -> None:
 
 
 # ------------------------------------------------------------------- count matrices
+def _io_threads() -> int:
+    return min(16, os.cpu_count() or 1)
+
+
 def read_count_matrices_array(
+    count_matrices_path: str,
+) -> Tuple[np.ndarray, List[str], np.ndarray]:
+    """Parse ``result.txt`` into ``(q[K], states[S], counts[K,S,S])`` (fp64) with the library's
+    multithreaded reader (``cherry_read_count_matrices``; a 129 x 400 x 400 file takes 0.2 s
+    instead of 4.4 s).  ``read_count_matrices_array_py`` is the plain-Python definition of the
+    format, kept for the tests."""
+    import ctypes
+
+    from . import _lib
+
+    lib = _lib.load()
+    K, S = ctypes.c_int(0), ctypes.c_int(0)
+    path = os.fspath(count_matrices_path).encode()
+    _lib.check(lib.cherry_read_count_matrices_header(path, ctypes.byref(K), ctypes.byref(S)),
+               "cherry_read_count_matrices_header")
+    K, S = K.value, S.value
+    q = np.zeros(K)
+    counts = np.zeros((K, S, S))
+    cap = 64 * S + 64
+    names = ctypes.create_string_buffer(cap)
+    _lib.check(lib.cherry_read_count_matrices(path, K, S, _lib.ptr(q), _lib.ptr(counts), names, cap, _io_threads()),
+               "cherry_read_count_matrices")
+    states = names.value.decode().split("\n")[:-1] if K else []
+    return q, states, counts
+
+
+def read_count_matrices_array_py(
     count_matrices_path: str,
 ) -> Tuple[np.ndarray, List[str], np.ndarray]:
     """Parse ``result.txt`` into ``(q[K], states[S], counts[K,S,S])`` (fp64).
@@ -322,6 +353,32 @@ def _fmt_cpp(x: float) -> str:
 
 
 def write_count_matrices_array(
+    q: Sequence[float],
+    states: Sequence[str],
+    counts: np.ndarray,
+    count_matrices_path: str,
+    style: str = "python",
+) -> None:
+    """Write ``result.txt`` with the library's multithreaded writer (``cherry_write_count_matrices``),
+    byte-identical to ``write_count_matrices_array_py`` below (tests/test_fc_native_io.py)."""
+    import ctypes
+
+    from . import _lib
+
+    if style not in ("python", "cpp"):
+        raise ValueError(f"Unknown style: {style}")
+    _makedirs_for(count_matrices_path)
+    lib = _lib.load()
+    qa = np.ascontiguousarray(np.asarray(q, dtype=np.float64))
+    ca = np.ascontiguousarray(np.asarray(counts, dtype=np.float64))
+    names = (ctypes.c_char_p * len(states))()
+    names[:] = [s.encode() for s in states]
+    _lib.check(lib.cherry_write_count_matrices(os.fspath(count_matrices_path).encode(), _lib.ptr(qa), len(qa), names,
+                                               len(states), _lib.ptr(ca), int(style == "cpp"), _io_threads()),
+               "cherry_write_count_matrices")
+
+
+def write_count_matrices_array_py(
     q: Sequence[float],
     states: Sequence[str],
     counts: np.ndarray,

@@ -381,6 +381,18 @@ int cherry_fc_write_outputs(const cherry_fc_msas* msas, const int32_t* pair_a, c
                             const char* const* likelihood_paths, const char* const* profiling_paths,
                             const double* profiling, int n_threads);
 
+/* Count-matrix text files (`result.txt` of the counting stages), multithreaded over the K
+ * matrices; all pointers are HOST pointers.  cpp_style = 0: the layout of the reference's
+ * Python writer (io/_count_matrices.py:66-81: pandas to_csv, floats as repr), 1: the layout of
+ * its C++ program (counting/_count_transitions.cpp:524-548: "%g", tab after every state name).
+ * The reader accepts both (io/_count_matrices.py:8-63); numbers go through strtod. */
+int cherry_write_count_matrices(const char* path, const double* q, int K, const char* const* states, int S,
+                                const double* counts, int cpp_style, int n_threads);
+int cherry_read_count_matrices_header(const char* path, int* K, int* S);
+/* states_out receives the S state names of the file's last header line, '\n'-separated. */
+int cherry_read_count_matrices(const char* path, int K, int S, double* q, double* counts, char* states_out,
+                               size_t states_cap, int n_threads);
+
 /* ------------------------------------------------------------------- tree log-likelihood */
 
 /* One tree node; nodes are passed in POST-ORDER (children, in the tree's child order, before

@@ -84,3 +84,29 @@ def test_write_outputs_matches_python_writers(tmp_path):
             p = prof[f]
             assert open(j(".prof")[f]).read() == (f"pairing_time: {p[0]}\nble_time: {p[1]}\ncpp_time: {p[2]}\n"
                                                    f"total_time: {p[3]}")
+
+
+def test_count_matrix_files_native_equals_python(tmp_path):
+    from cherryml_b200.io import (read_count_matrices_array, read_count_matrices_array_py,
+                                  write_count_matrices_array, write_count_matrices_array_py)
+
+    rng = np.random.default_rng(2)
+    for S, states in ((3, ["A", "C", "G"]), (20, AA), (16, [a + b for a in "ACGT" for b in "ACGT"])):
+        K = 5
+        counts = rng.integers(0, 9, (K, S, S)) * 0.25 * (rng.random((K, S, S)) < 0.4)
+        counts[0, 0, 0] = 1234567.25       # 6-significant-digit rounding in the C++ layout
+        counts[1, 0, 1] = 1e-5 + 0.1
+        counts[2, 1, 1] = 123456789012.5
+        counts[3, 0, 2] = -0.0
+        q = [6.729602379904665e-05, 0.0001, 0.03, 1.0, 13.373747053577777]
+        for style in ("python", "cpp"):
+            a, b = str(tmp_path / f"n_{S}_{style}.txt"), str(tmp_path / f"p_{S}_{style}.txt")
+            write_count_matrices_array(q, states, counts, a, style)
+            write_count_matrices_array_py(q, states, counts, b, style)
+            assert open(a).read() == open(b).read()
+            qn, sn, cn = read_count_matrices_array(a)
+            qp, sp, cp = read_count_matrices_array_py(a)
+            assert sn == sp == list(states)
+            assert np.array_equal(qn, qp) and np.array_equal(cn, cp)
+    with __import__("pytest").raises(Exception):
+        read_count_matrices_array(str(tmp_path / "missing.txt"))
