@@ -70,7 +70,8 @@ void spill(const char* path, const std::string& text) {
 
 // Python's repr(float): shortest digits that round-trip, exponent form iff the decimal point
 // would sit more than 16 digits right or more than 3 zeros left of the first digit.
-void py_repr(double x, std::string* out) {
+template <typename T>
+void py_repr_t(T x, std::string* out) {
   if (x == 0.0) {
     *out += std::signbit(x) ? "-0.0" : "0.0";
     return;
@@ -152,6 +153,8 @@ bool quarter_fast(double v, int cpp_style, std::string* out) {
   *out += cpp_style ? suffix_g[fi] : suffix_py[fi];
   return true;
 }
+
+void py_repr(double x, std::string* out) { py_repr_t<double>(x, out); }
 
 void fixed17(double x, std::string* out) {
   char buf[400];
@@ -633,6 +636,39 @@ int cherry_read_count_matrices(const char* path, int K, int S, double* q, double
   }
   if (blob.size() + 1 > states_cap) return cherry::fail(CHERRY_EINVAL, "states buffer too small");
   memcpy(states_out, blob.c_str(), blob.size() + 1);
+  return CHERRY_OK;
+}
+
+
+// Labelled square table (rate matrices, masks): "\t<col>...\n" then "<row>\t<v>\t<v>...\n" with
+// every fp64 number printed as the shortest string that round-trips -- what pandas' to_csv /
+// str(numpy.float64) print (reference io/_rate_matrix.py:37-52).
+int cherry_write_labelled_matrix(const char* path, const char* const* states, int S, const double* data,
+                                 int n_threads) {
+  if (!path || !states || !data || S < 1) return cherry::fail(CHERRY_EINVAL, "null pointer");
+  cherry::keep_large_buffers_on_heap();
+  std::vector<std::string> rows((size_t)S);
+  std::string err;
+  parallel_for(S, n_threads, [&](int i) {
+    std::string& b = rows[(size_t)i];
+    b.reserve((size_t)S * 24 + 32);
+    b += states[i];
+    for (int j = 0; j < S; ++j) {
+      b += '\t';
+      py_repr(data[(size_t)i * S + j], &b);
+    }
+    b += '\n';
+  }, &err);
+  if (!err.empty()) return cherry::fail(CHERRY_EINVAL, "%s", err.c_str());
+  std::string text;
+  for (int j = 0; j < S; ++j) text += "\t" + std::string(states[j]);
+  text += '\n';
+  for (const std::string& r : rows) text += r;
+  try {
+    spill(path, text);
+  } catch (const IoErr& e) {
+    return cherry::fail(CHERRY_EINVAL, "%s", e.msg.c_str());
+  }
   return CHERRY_OK;
 }
 

@@ -393,6 +393,11 @@ int cherry_read_count_matrices_header(const char* path, int* K, int* S);
 int cherry_read_count_matrices(const char* path, int K, int S, double* q, double* counts, char* states_out,
                                size_t states_cap, int n_threads);
 
+/* Labelled S x S table (rate matrix file, reference io/_rate_matrix.py:37-52): fp64 numbers as
+ * the shortest strings that round-trip, exponent notation like Python's repr. */
+int cherry_write_labelled_matrix(const char* path, const char* const* states, int S, const double* data,
+                                 int n_threads);
+
 /* ------------------------------------------------------------------- tree log-likelihood */
 
 /* One tree node; nodes are passed in POST-ORDER (children, in the tree's child order, before

@@ -110,3 +110,22 @@ def test_count_matrix_files_native_equals_python(tmp_path):
             assert np.array_equal(qn, qp) and np.array_equal(cn, cp)
     with __import__("pytest").raises(Exception):
         read_count_matrices_array(str(tmp_path / "missing.txt"))
+
+
+def test_rate_matrix_files_native_equals_python(tmp_path):
+    from cherryml_b200.io import read_rate_matrix, write_rate_matrix, write_rate_matrix_py
+
+    rng = np.random.default_rng(3)
+    for dt in (np.float64, np.float32):
+        for S, states in ((4, list("ACGT")), (20, AA)):
+            m = (rng.standard_normal((S, S)) * np.exp(rng.uniform(-25, 25, (S, S)))).astype(dt)
+            m[0, :4] = [0.0, -0.0, 1.0, -1.0]
+            m[1, :4] = [1e-5, 1e-4, 1e15, 1e16]
+            m[2, :3] = [np.inf, -np.inf, np.nan]
+            m[3, :3] = [0.1, 123456.789, 5e-324 if dt is np.float64 else 1e-45]
+            a, b = str(tmp_path / f"n{S}{dt.__name__}.txt"), str(tmp_path / f"p{S}{dt.__name__}.txt")
+            write_rate_matrix(m, states, a)
+            write_rate_matrix_py(m, states, b)
+            assert open(a).read() == open(b).read()
+    back = read_rate_matrix(a)
+    assert list(back.columns) == AA
