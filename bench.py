@@ -398,7 +398,7 @@ def run_ours(args):
     # ---- the fit (every rank takes part when N > 1: bucket-sharded co-evolution fit)
     fit = None
     if not args.no_fit:
-        from cherryml_b200.estimation import bench_fit
+        from benchlib.fit import bench_fit
 
         del dev, syn, host
         torch.cuda.empty_cache()
@@ -408,7 +408,7 @@ def run_ours(args):
     # ---- FastCherries (tree estimation, the step before counting): every rank its own families
     fcb = None
     if not args.no_fast_cherries:
-        from cherryml_b200.phylogeny_estimation._bench import bench_fast_cherries
+        from benchlib.fast_cherries import bench_fast_cherries
 
         torch.cuda.empty_cache()
         fcb = bench_fast_cherries(device, families=args.fc_families, seed=rank,
@@ -425,7 +425,7 @@ def run_ours(args):
             fcb["n_gpus"] = world
     llb = None
     if rank == 0 and not args.no_likelihood:
-        from cherryml_b200.evaluation._bench import bench_likelihood
+        from benchlib.likelihood import bench_likelihood
 
         try:
             llb = bench_likelihood(device, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
@@ -433,7 +433,7 @@ def run_ours(args):
             llb = {"error": str(e)[:300]}
     srb = None
     if rank == 0 and not args.no_siterm:
-        from cherryml_b200.siterm._bench import bench_siterm
+        from benchlib.siterm import bench_siterm
 
         try:
             srb = bench_siterm(device, cpu_baseline=(world == 1 and not args.no_cpu_baseline))

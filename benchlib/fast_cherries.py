@@ -13,10 +13,10 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from ..io import read_rate_matrix
-from ..markov_chain import get_lg_path
-from ..utils import amino_acids
-from . import _fast_cherries as fc
+from cherryml_b200.io import read_rate_matrix
+from cherryml_b200.markov_chain import get_lg_path
+from cherryml_b200.utils import amino_acids
+from cherryml_b200.phylogeny_estimation import _fast_cherries as fc
 
 N_SEQS, N_SITES, N_RATE_CATS, MAX_ITERS, SEED = 1024, 300, 20, 50, 1234
 
@@ -39,7 +39,7 @@ def _render(msa: np.ndarray, fams: np.ndarray, out_dir: str, n: int):
 def _reference_program(paths, tmp: str, cores: int) -> Optional[Dict]:
     """Runs the reference program like _fast_cherries.py:85-104 does, one process per core on the
     wrapper's own striping (get_process_args: paths[r::P])."""
-    repo = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     ref_bin = os.path.join(repo, "oracle", "_ref", "fast_cherries")
     if not (os.path.exists(ref_bin) and os.access(ref_bin, os.X_OK)):
         return None
@@ -79,7 +79,7 @@ def _reference_program(paths, tmp: str, cores: int) -> Optional[Dict]:
 
 def bench_fast_cherries(device, families: int = 2048, reps: int = 3, cpu_baseline: bool = True,
                         cpu_families: int = 0, seed: int = 0) -> Dict:
-    from ..synthetic import synthetic_fc
+    from cherryml_b200.synthetic import synthetic_fc
 
     msa, fams = synthetic_fc(families, N_SEQS, N_SITES, seed=seed)
     Q = read_rate_matrix(get_lg_path()).to_numpy(dtype=np.float64)

@@ -7,9 +7,9 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from .. import _lib
-from ._engine import FitEngine, theta_from_initialization
-from ._jtt_ipw import jtt_ipw_from_counts
+from cherryml_b200 import _lib
+from cherryml_b200.estimation._engine import FitEngine, theta_from_initialization
+from cherryml_b200.estimation._jtt_ipw import jtt_ipw_from_counts
 
 
 def measure_fp64_gemm_peak(device, n: int = 4096, reps: int = 5) -> float:
@@ -126,8 +126,8 @@ def cpu_fit_baseline(times, counts: torch.Tensor, num_epochs_full: int, epochs_t
 
 def bench_fit(device, lg_times=None, lg_counts: Optional[torch.Tensor] = None, num_epochs: int = 500,
               co_families: int = 4096, process_group=None, cpu_baseline: bool = False) -> Dict:
-    from ..counting._device import count_raw, sorted_grid, symmetrize
-    from ..synthetic import as_device_batch, quantization_grid, synthetic_co, synthetic_lg
+    from cherryml_b200.counting._device import count_raw, sorted_grid, symmetrize
+    from cherryml_b200.synthetic import as_device_batch, quantization_grid, synthetic_co, synthetic_lg
 
     grid = quantization_grid()
     K = len(grid)
@@ -147,8 +147,8 @@ def bench_fit(device, lg_times=None, lg_counts: Optional[torch.Tensor] = None, n
 
         rank = dist.get_rank(process_group)
     # co-evolution counts from synthetic contact-map families (BASELINE config 4 shape)
-    from .. import _lib
-    from ..counting._device import build_bucket_table
+    from cherryml_b200 import _lib
+    from cherryml_b200.counting._device import build_bucket_table
 
     lib = _lib.load()
     dev = as_device_batch(synthetic_co(co_families, 1024, 300, seed=11 + rank, device=device), device)
@@ -189,8 +189,8 @@ def bench_fit(device, lg_times=None, lg_counts: Optional[torch.Tensor] = None, n
         import json
         import os
 
-        peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(
-            os.path.abspath(__file__)))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+        peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(
+            os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         peak, peak_src = 6650.0, "fallback 6650 GB/s"

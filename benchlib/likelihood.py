@@ -6,10 +6,10 @@ from typing import Dict
 
 import numpy as np
 
-from ..io import Tree, read_rate_matrix
-from ..markov_chain import chain_product, compute_stationary_distribution, get_lg_path
-from ..utils import amino_acids
-from ._likelihood import dp_likelihood_computation
+from cherryml_b200.io import Tree, read_rate_matrix
+from cherryml_b200.markov_chain import chain_product, compute_stationary_distribution, get_lg_path
+from cherryml_b200.utils import amino_acids
+from cherryml_b200.evaluation._likelihood import dp_likelihood_computation
 
 
 def random_binary_tree(rng, n_leaves: int) -> Tree:

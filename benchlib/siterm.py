@@ -7,9 +7,9 @@ from typing import Dict
 
 import numpy as np
 
-from ..io import read_rate_matrix
-from ..markov_chain import get_lg_path
-from ..utils import amino_acids
+from cherryml_b200.io import read_rate_matrix
+from cherryml_b200.markov_chain import get_lg_path
+from cherryml_b200.utils import amino_acids
 
 N_SEQS, N_SITES, NUM_EPOCHS, GRID_STEPS = 38, 331, 100, 8
 
@@ -30,8 +30,7 @@ def _plant_family(rng) -> Dict[str, str]:
 
 
 def bench_siterm(device, families: int = 8, cpu_baseline: bool = True, seed: int = 0) -> Dict:
-    from . import (estimate_site_specific_rate_matrices_given_tree_and_site_rates,  # noqa: F401
-                   learn_site_specific_rate_matrices)
+    from cherryml_b200.siterm import learn_site_specific_rate_matrices
 
     rng = np.random.default_rng(seed)
     lg = read_rate_matrix(get_lg_path())
@@ -56,8 +55,8 @@ def bench_siterm(device, families: int = 8, cpu_baseline: bool = True, seed: int
         # the same regularised, compacted count tensors the GPU fit consumed, rebuilt for family 0
         import torch
 
-        from ._site_specific import estimate_site_specific_rate_matrices_given_tree_and_site_rates as stage
-        from . import _site_specific as mod
+        from cherryml_b200.siterm._site_specific import estimate_site_specific_rate_matrices_given_tree_and_site_rates as stage
+        from cherryml_b200.siterm import _site_specific as mod
 
         captured = {}
         real = mod.quantized_transitions_mle_vectorized_over_sites
