@@ -514,6 +514,27 @@ __global__ void __launch_bounds__(kBleThreads) fc_ble_kernel(BleArgs a) {
   if (tid == 0) a.iters[blockIdx.x] = iters;
 }
 
+// FastCherries layout (all sequences in file order, natural columns) -> LG counting layout (rows
+// in cherry order, partners adjacent; columns at dest[site]: sorted by site-rate category, every
+// category padded to 4 sites; the output is pre-filled with the skip code).  One CTA per family.
+__global__ void fc_relayout_lg_kernel(const uint8_t* __restrict__ msa_in, const cherry_fc_family* __restrict__ fc_fams,
+                                      const cherry_fam_desc* __restrict__ out_fams,
+                                      const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b,
+                                      const int32_t* __restrict__ dest, uint8_t* __restrict__ msa_out) {
+  const cherry_fc_family in = fc_fams[blockIdx.x];
+  const cherry_fam_desc out = out_fams[blockIdx.x];
+  const int n_cherries = in.n_seqs >> 1, L = in.n_sites;
+  const int32_t* d = dest + in.site_off;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  for (int row = warp; row < 2 * n_cherries; row += n_warps) {
+    const int c = row >> 1;
+    const int src_row = (row & 1) ? pair_b[in.cherry_off + c] : pair_a[in.cherry_off + c];
+    const uint8_t* src = msa_in + in.msa_off + (long long)src_row * in.row_stride;
+    uint8_t* dst = msa_out + out.msa_off + (long long)row * out.row_stride;
+    for (int j = lane; j < L; j += 32) dst[d[j]] = src[j];
+  }
+}
+
 constexpr size_t kPairBytesPerSeq = 4 + 4 + 8 + 1 + sizeof(Frame);  // idx, idx2, d1, flag, frame
 constexpr size_t kBleBytesPerSite = 8 + 4 + 4;
 
@@ -555,6 +576,18 @@ int cherry_fc_pair(const uint8_t* msa, const cherry_fc_family* fams, int n_fams,
   fc_pair_kernel<<<n_fams, kPairThreads, 0, (cudaStream_t)stream>>>(msa, fams, S, seed, pair_a, pair_b, unpaired, idx,
                                                                      idx2, d1, flag, frames);
   CHERRY_LAUNCH_CHECK("fc_pair_kernel");
+  return CHERRY_OK;
+}
+
+int cherry_fc_relayout_lg(const uint8_t* msa_in, const cherry_fc_family* fc_fams, const cherry_fam_desc* out_fams,
+                          int n_fams, const int32_t* pair_a, const int32_t* pair_b, const int32_t* dest,
+                          uint8_t* msa_out, void* stream) {
+  if (n_fams == 0) return CHERRY_OK;
+  if (!msa_in || !fc_fams || !out_fams || !pair_a || !pair_b || !dest || !msa_out)
+    return cherry::fail(CHERRY_EINVAL, "null pointer");
+  fc_relayout_lg_kernel<<<n_fams, 256, 0, (cudaStream_t)stream>>>(msa_in, fc_fams, out_fams, pair_a, pair_b, dest,
+                                                                  msa_out);
+  CHERRY_LAUNCH_CHECK("fc_relayout_lg_kernel");
   return CHERRY_OK;
 }
 

@@ -423,6 +423,49 @@ int cherry_fc_write_outputs(const cherry_fc_msas* m, const int32_t* pair_a, cons
 }
 
 
+// Branch lengths and site rates exactly as the counting stage reads them back from the files
+// cherry_fc_write_outputs writes: pair_t[c] = the cherry's path length -- the tree's two edges of
+// round_trip('%.17f', grid[len_idx] * mean) / 2 each, printed with repr and parsed again (through
+// float32 when float32_lengths, like the C++ counting program's std::stof) and added;
+// rate_table[f][r] = round_trip('%.17f', cats[r] / mean_f), the value a site of category r has in
+// the site-rates file.  This is what lets FastCherries hand its result to the counting kernels in
+// memory with counts identical to the route through the text files.
+int cherry_fc_lengths_and_rates(const cherry_fc_family* fams, int n_fams, const int32_t* len_idx,
+                                const int32_t* site_cat, const double* grid, int K, const double* cats, int R,
+                                int float32_lengths, double* pair_t, double* rate_table, int n_threads) {
+  if (!fams || !len_idx || !site_cat || !grid || !cats || !pair_t || !rate_table)
+    return cherry::fail(CHERRY_EINVAL, "null pointer");
+  std::string err;
+  parallel_for(n_fams, n_threads, [&](int f) {
+    const cherry_fc_family& d = fams[f];
+    const int n_cherries = d.n_seqs / 2, L = d.n_sites;
+    const int32_t* sc = site_cat + d.site_off;
+    double sum = 0.0;
+    for (int j = 0; j < L; ++j) {
+      if (sc[j] < 0 || sc[j] >= R) throw IoErr{"cherry_fc_lengths_and_rates: category out of range"};
+      sum += cats[sc[j]];
+    }
+    const double mean = L ? sum / (double)L : 1.0;
+    for (int r = 0; r < R; ++r) rate_table[(size_t)f * R + r] = through_fixed17(cats[r] / mean);
+    std::vector<double> by_index((size_t)K, -1.0);
+    std::string text;
+    for (int c = 0; c < n_cherries; ++c) {
+      const int k = len_idx[d.cherry_off + c];
+      if (k < 0 || k >= K) throw IoErr{"cherry_fc_lengths_and_rates: length index out of range"};
+      if (by_index[(size_t)k] < 0) {
+        const double half = through_fixed17(grid[k] * mean) / 2.0;
+        text.clear();
+        py_repr(half, &text);
+        const double edge = float32_lengths ? (double)strtof(text.c_str(), nullptr) : strtod(text.c_str(), nullptr);
+        by_index[(size_t)k] = (0.0 + edge) + (0.0 + edge);  // the two leaf-to-parent distances of the traversal
+      }
+      pair_t[d.cherry_off + c] = by_index[(size_t)k];
+    }
+  }, &err);
+  if (!err.empty()) return cherry::fail(CHERRY_EINVAL, "%s", err.c_str());
+  return CHERRY_OK;
+}
+
 // ------------------------------------------------------------------ count matrices (result.txt)
 // The reference's two writers: io/_count_matrices.py:66-81 (pandas to_csv, repr floats) and the
 // C++ program's writer (counting/_count_transitions.cpp:524-548, ostream << double = "%g").

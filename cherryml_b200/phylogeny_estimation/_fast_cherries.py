@@ -193,7 +193,8 @@ def log_transition_table(Q: np.ndarray, grid: np.ndarray, cats: np.ndarray, devi
 
 
 def fast_cherries_device(msa: np.ndarray, fams: np.ndarray, S: int, sym_table: torch.Tensor, priors: np.ndarray,
-                         weights: np.ndarray, seed: int, max_iters: int, device="cuda") -> Dict[str, np.ndarray]:
+                         weights: np.ndarray, seed: int, max_iters: int, device="cuda",
+                         keep_device: bool = False) -> Dict[str, np.ndarray]:
     """Runs both kernels on an encoded batch.  Returns host arrays: pair_a, pair_b (row indices
     per cherry, reference emission order), unpaired (per family), len_idx (per cherry),
     site_cat (per site), iters (per family), and the two kernel times in ms."""
@@ -236,7 +237,11 @@ def fast_cherries_device(msa: np.ndarray, fams: np.ndarray, S: int, sym_table: t
         )
         ev[2].record()
         torch.cuda.synchronize()
+    extra = {}
+    if keep_device:  # for the in-memory hand-off to the counting kernels (_pipeline.py)
+        extra = {"d_msa": d_msa, "d_fams": d_fams, "d_pair_a": pair_a, "d_pair_b": pair_b}
     return {
+        **extra,
         "pair_a": pair_a[:n_cherries].cpu().numpy(),
         "pair_b": pair_b[:n_cherries].cpu().numpy(),
         "unpaired": unpaired[:n_fams].cpu().numpy(),

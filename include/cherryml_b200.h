@@ -348,6 +348,20 @@ int cherry_fc_ble(const uint8_t* msa, const cherry_fc_family* fams, int n_fams, 
                   const double* priors, const double* init_weights, int max_iters, int32_t* len_idx,
                   int32_t* site_cat, int32_t* iters, void* scratch, size_t scratch_bytes, void* stream);
 
+/* FastCherries -> LG counting without the text files.
+ * cherry_fc_lengths_and_rates (HOST pointers): pair_t[cherry] and rate_table[family][category] with
+ * exactly the values the counting stage would parse from the tree / site-rate files that
+ * cherry_fc_write_outputs writes ('%.17f' and repr round trips, float32 when float32_lengths).
+ * cherry_fc_relayout_lg (DEVICE pointers): copies the paired rows of every family into the LG
+ * counting layout described by out_fams (rows 2c, 2c+1 = cherry c; column of site j = dest[j]);
+ * msa_out must be pre-filled with the skip code. */
+int cherry_fc_lengths_and_rates(const cherry_fc_family* fams, int n_fams, const int32_t* len_idx,
+                                const int32_t* site_cat, const double* grid, int K, const double* cats, int R,
+                                int float32_lengths, double* pair_t, double* rate_table, int n_threads);
+int cherry_fc_relayout_lg(const uint8_t* msa_in, const cherry_fc_family* fc_fams, const cherry_fam_desc* out_fams,
+                          int n_fams, const int32_t* pair_a, const int32_t* pair_b, const int32_t* dest,
+                          uint8_t* msa_out, void* stream);
+
 /* Host-side text I/O of the FastCherries stage (multithreaded, one family per task). */
 typedef struct cherry_fc_msas {
   int32_t n_fams;

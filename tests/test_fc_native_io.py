@@ -129,3 +129,81 @@ def test_rate_matrix_files_native_equals_python(tmp_path):
             assert open(a).read() == open(b).read()
     back = read_rate_matrix(a)
     assert list(back.columns) == AA
+
+
+def test_in_memory_hand_off_equals_the_route_through_files(tmp_path):
+    """FastCherries results -> counting batch WITHOUT the text files (count_layout +
+    cherry_fc_lengths_and_rates; the device re-layout is emulated in numpy here) is array for array
+    the batch cherry_ingest_lg builds from the files cherry_fc_write_outputs writes."""
+    import ctypes
+
+    from cherryml_b200 import _lib
+    from cherryml_b200.counting._ingest import build_lg_batch_native
+    from cherryml_b200.phylogeny_estimation._pipeline import count_layout
+
+    rng = np.random.default_rng(5)
+    shapes = [(9, 37), (2, 16), (40, 100), (13, 5), (64, 301)]
+    msa_dir = tmp_path / "msas"
+    msa_dir.mkdir()
+    fam_names = [f"fam{i}" for i in range(len(shapes))]
+    paths = []
+    for name, (n, L) in zip(fam_names, shapes):
+        text = "".join(f">{name}_s{i}\n{''.join(rng.choice(AA + ['-'], L))}\n" for i in range(n))
+        (msa_dir / f"{name}.txt").write_text(text)
+        paths.append(str(msa_dir / f"{name}.txt"))
+    grid = fc.quantization_grid(0.03, 1.1, 64)
+    cats = fc.ble_rate_categories(20)
+    for f32 in (True, False):
+        with fc.NativeMsas(paths, AA, n_threads=2, pinned=False) as m:
+            fams = m.fams.copy()
+            msa = m.msa.copy()
+            n_ch = int((fams["n_seqs"] // 2).sum())
+            pair_a = np.zeros(n_ch, dtype=np.int32)
+            pair_b = np.zeros(n_ch, dtype=np.int32)
+            unpaired = np.full(len(shapes), -1, dtype=np.int32)
+            for f, (n, _) in enumerate(shapes):
+                perm = rng.permutation(n)
+                c0 = int(fams[f]["cherry_off"])
+                pair_a[c0: c0 + n // 2] = perm[0: 2 * (n // 2): 2]
+                pair_b[c0: c0 + n // 2] = perm[1: 2 * (n // 2): 2]
+                if n % 2:
+                    unpaired[f] = perm[-1]
+            len_idx = rng.integers(0, len(grid), n_ch).astype(np.int32)
+            site_cat = rng.integers(0, len(cats), int(fams["n_sites"].sum())).astype(np.int32)
+            site_cat[int(fams[3]["site_off"]): int(fams[3]["site_off"]) + 5] = 7      # one category only
+            out = dict(pair_a=pair_a, pair_b=pair_b, unpaired=unpaired, len_idx=len_idx, site_cat=site_cat)
+            d = tmp_path / f"out{int(f32)}"
+            for sub in ("trees", "rates"):
+                (d / sub).mkdir(parents=True)
+            j = lambda sub, ext: [str(d / sub / f"{nm}{ext}") for nm in fam_names]  # noqa: E731
+            m.write_outputs(out, grid, cats, j("trees", ".txt"), [None] * 5, j("rates", ".txt"), [None] * 5,
+                            [None] * 5, np.zeros((5, 4)))
+        ref = build_lg_batch_native(str(d / "trees"), str(msa_dir), str(d / "rates"), fam_names, AA, "cherry++", f32,
+                                    n_threads=2)
+        lib = _lib.load()
+        pair_t = np.zeros(n_ch)
+        rate_table = np.zeros((len(shapes), len(cats)))
+        _lib.check(lib.cherry_fc_lengths_and_rates(_lib.ptr(fams), len(shapes), _lib.ptr(len_idx), _lib.ptr(site_cat),
+                                                   _lib.ptr(grid), len(grid), _lib.ptr(cats), len(cats), int(f32),
+                                                   _lib.ptr(pair_t), _lib.ptr(rate_table), 2), "lengths_and_rates")
+        lay = count_layout(fams, site_cat, rate_table)
+        assert np.array_equal(pair_t, ref.pair_t)
+        assert np.array_equal(lay["rate_vals"], ref.rate_vals)
+        assert np.array_equal(lay["aux"], ref.aux)
+        assert np.array_equal(lay["fams"], ref.fams)
+        assert np.array_equal(lay["tiles"], ref.tiles)
+        assert lay["r_pad"] == ref.r_pad and lay["examined"] == ref.n_sites_examined
+        local = np.concatenate([np.arange(n // 2) for n, _ in shapes])
+        assert np.array_equal(ref.pair_a, 2 * local) and np.array_equal(ref.pair_b, 2 * local + 1)
+        # the device re-layout, emulated
+        msa_out = np.full(lay["msa_bytes"], 20, dtype=np.uint8)
+        for f, (n, L) in enumerate(shapes):
+            fin, fo = fams[f], lay["fams"][f]
+            rows_in = msa[int(fin["msa_off"]): int(fin["msa_off"]) + n * int(fin["row_stride"])].reshape(n, -1)
+            dest = lay["dest"][int(fin["site_off"]): int(fin["site_off"]) + L]
+            c0 = int(fin["cherry_off"])
+            for c in range(n // 2):
+                for side, src in enumerate((pair_a[c0 + c], pair_b[c0 + c])):
+                    base = int(fo["msa_off"]) + (2 * c + side) * int(fo["row_stride"])
+                    msa_out[base + dest] = rows_in[src, :L]
+        assert np.array_equal(msa_out, ref.msa[: len(msa_out)])

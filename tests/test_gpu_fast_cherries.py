@@ -310,3 +310,47 @@ def test_tree_free_coevolution_pipeline(tmp_path):
     assert ours == open(os.path.join(again, "result.txt")).read()
     Q = read_rate_matrix(out).to_numpy()
     assert Q.shape == (400, 400) and np.allclose(Q.sum(axis=1), 0, atol=1e-4)
+
+
+@pytest.mark.parametrize("cpp_personality", [True, False])
+def test_in_memory_fast_cherries_to_counts_equals_the_text_route(tmp_path, cpp_personality):
+    """MSAs -> FastCherries -> counts with the residues resident on the device
+    (fast_cherries_then_count_lg) against the reference's route: fast_cherries stage writes trees
+    and site rates, count_transitions reads them back.  Counts identical."""
+    import tarfile
+
+    from cherryml_b200.counting import count_transitions
+    from cherryml_b200._public_api import _quantization_points
+    from cherryml_b200.io import read_count_matrices_array, read_rate_matrix
+    from cherryml_b200.markov_chain import get_lg_path
+    from cherryml_b200.phylogeny_estimation import fast_cherries
+    from cherryml_b200.phylogeny_estimation._pipeline import fast_cherries_then_count_lg
+    from tests.conftest import GOLDEN
+
+    fams = ["13gs_1_A", "1a0b_1_A", "1a2t_1_A", "1a12_1_A"]
+    with tarfile.open(os.path.join(GOLDEN, "demo_data.tar.xz")) as tf:
+        tf.extractall(tmp_path, members=[tf.getmember(f"msas/{f}.txt") for f in fams])
+    msa_dir = str(tmp_path / "msas")
+    small = next(c for c in CASES if c["name"] == "synthetic_n33_L100_R20")   # odd family: one row left over
+    (tmp_path / "msas" / "odd.txt").write_text(small["msa_text"])
+    fams = sorted(fams + ["odd"])
+    dirs = {k: str(tmp_path / k) for k in ("tree", "rates", "ll", "counts")}
+    fast_cherries(msa_dir=msa_dir, families=fams, rate_matrix_path=get_lg_path(), num_rate_categories=20,
+                  max_iters=50, num_processes=1, verbose=False, output_tree_dir=dirs["tree"],
+                  output_site_rates_dir=dirs["rates"], output_likelihood_dir=dirs["ll"])
+    qp = _quantization_points(0.03, 1.1, 64)
+    count_transitions(tree_dir=dirs["tree"], msa_dir=msa_dir, site_rates_dir=dirs["rates"], families=fams,
+                      amino_acids=list(AA), quantization_points=qp, edge_or_cherry="cherry++", num_processes=1,
+                      use_cpp_implementation=cpp_personality, output_count_matrices_dir=dirs["counts"])
+    _, _, expected = read_count_matrices_array(os.path.join(dirs["counts"], "result.txt"))
+    Q = read_rate_matrix(get_lg_path()).to_numpy()
+    with fc.NativeMsas([os.path.join(msa_dir, f + ".txt") for f in fams], list(AA)) as msas:
+        counts, out = fast_cherries_then_count_lg(msas.msa, msas.fams, list(AA), Q, [float(x) for x in qp],
+                                                  float32_branch_lengths=cpp_personality, device="cuda:0")
+        got = counts.cpu().numpy()
+    assert got.sum() > 1e5
+    if cpp_personality:  # the C++ layout of result.txt keeps 6 significant digits: compare what it can show
+        assert np.array_equal(np.array([[float("%g" % v) for v in row] for row in got.reshape(-1, 20)]).reshape(
+            got.shape), expected)
+    else:
+        assert np.array_equal(got, expected)
