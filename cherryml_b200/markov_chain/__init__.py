@@ -101,15 +101,43 @@ def chain_product(rate_matrix_1: np.ndarray, rate_matrix_2: np.ndarray) -> np.nd
     return np.kron(rate_matrix_1, eye) + np.kron(eye, rate_matrix_2)
 
 
-_DATA_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "rate_matrices")
+_DATA_FILE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "rate_matrices.npz")
+_MATERIALISED = {}
+
+
+def _rate_matrix_path(name: str) -> str:
+    """Published 20 x 20 amino-acid rate matrices ship as one compressed array file
+    (data/rate_matrices.npz: LG, WAG and the uniform-exchangeability matrix in the alphabet order of
+    ``utils.amino_acids``); the reference's path-based API wants labelled text files, which are
+    written on first use (floats as repr, so they parse back to the stored doubles)."""
+    if name not in _MATERIALISED:
+        import tempfile
+
+        from ..io import write_rate_matrix
+        from ..utils import amino_acids
+
+        out_dir = os.path.join(tempfile.gettempdir(), f"cherryml_b200_data_{os.getuid()}")
+        os.makedirs(out_dir, exist_ok=True)
+        path = os.path.join(out_dir, name + ".txt")
+        with np.load(_DATA_FILE) as z:
+            matrix = z[name]
+        tmp = f"{path}.{os.getpid()}.tmp"
+        write_rate_matrix(matrix, amino_acids, tmp)
+        os.replace(tmp, path)
+        _MATERIALISED[name] = path
+    return _MATERIALISED[name]
 
 
 def get_lg_path() -> str:
-    """The LG rate matrix (Le & Gascuel 2008), a data file shipped with the package (reference
-    ``_markov_chain.py`` ``get_lg_path``: ``data/rate_matrices/lg.txt``)."""
-    return os.path.join(_DATA_DIR, "lg.txt")
+    """The LG rate matrix (Le & Gascuel 2008) as a labelled text file (reference ``get_lg_path``)."""
+    return _rate_matrix_path("lg")
 
 
 def get_equ_path() -> str:
     """The uniform-exchangeability rate matrix (reference ``get_equ_path``)."""
-    return os.path.join(_DATA_DIR, "equ.txt")
+    return _rate_matrix_path("equ")
+
+
+def get_wag_path() -> str:
+    """The WAG rate matrix (Whelan & Goldman 2001) (reference ``get_wag_path``)."""
+    return _rate_matrix_path("wag")

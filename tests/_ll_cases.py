@@ -11,12 +11,13 @@ from cherryml_b200.markov_chain import chain_product, compute_stationary_distrib
 from tests.conftest import GOLDEN, REPO
 
 AA = list("ARNDCQEGHILKMFPSTWYV")
-_DATA = os.path.join(REPO, "cherryml_b200", "data", "rate_matrices")
 LL_DIR = os.path.join(GOLDEN, "likelihood")
 
 
 def rate_matrix(name):
-    return read_rate_matrix(os.path.join(_DATA, name + ".txt")).to_numpy()
+    from cherryml_b200.markov_chain import _rate_matrix_path
+
+    return read_rate_matrix(_rate_matrix_path(name)).to_numpy()
 
 
 def _tree(nodes, edges):

@@ -76,8 +76,9 @@ def main():
     from cherryml_b200.io import read_rate_matrix
     from cherryml_b200.markov_chain import chain_product, compute_stationary_distribution
 
-    data = os.path.join(REPO, "cherryml_b200/data/rate_matrices")
-    mats = {k: read_rate_matrix(os.path.join(data, k + ".txt")).to_numpy() for k in ("lg", "wag")}
+    from cherryml_b200.markov_chain import _rate_matrix_path
+
+    mats = {k: read_rate_matrix(_rate_matrix_path(k)).to_numpy() for k in ("lg", "wag")}
     rng = np.random.default_rng(7)
     cases = []
     specs = [  # n_leaves, n_sites, n_pairs, gap, n_cats, Q1, pair model, reversible flags
