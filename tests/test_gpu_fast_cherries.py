@@ -354,3 +354,58 @@ def test_in_memory_fast_cherries_to_counts_equals_the_text_route(tmp_path, cpp_p
             got.shape), expected)
     else:
         assert np.array_equal(got, expected)
+
+
+def test_full_size_properties():
+    """2048 Pfam-shaped families (1024 x 300) in one launch, the bench workload: every sequence is in
+    exactly one cherry, indices are in range, a second run is identical (the kernels are
+    deterministic), a family's result does not depend on the batch it is in, and a sample of
+    families equals the oracle."""
+    from oracle import fast_cherries_oracle as fo
+    from cherryml_b200.io import read_rate_matrix
+    from cherryml_b200.markov_chain import get_lg_path
+    from cherryml_b200.synthetic import synthetic_fc
+
+    F, N, L, R = 2048, 1024, 300, 20
+    msa, fams = synthetic_fc(F, N, L, seed=3)
+    Q = read_rate_matrix(get_lg_path()).to_numpy()
+    grid = fc.quantization_grid(0.03, 1.1, 64)
+    cats = fc.ble_rate_categories(R)
+    weights = fc.initial_rate_weights(cats)
+    priors = np.array([2 * math.log(r) - 3 * r for r in cats])
+    table = fc.log_transition_table(Q, grid, cats, "cuda:0")
+    run = lambda m, f: fc.fast_cherries_device(m, f, 20, table, priors, weights, 1234, 50, "cuda:0")  # noqa: E731
+    out = run(msa, fams)
+    pa, pb = out["pair_a"].reshape(F, N // 2), out["pair_b"].reshape(F, N // 2)
+    both = np.sort(np.concatenate([pa, pb], axis=1), axis=1)
+    assert np.array_equal(both, np.broadcast_to(np.arange(N), (F, N)))          # a perfect matching per family
+    assert (out["unpaired"] == -1).all()
+    assert out["len_idx"].min() >= 0 and out["len_idx"].max() < len(grid)
+    assert out["site_cat"].min() >= 0 and out["site_cat"].max() < R
+    assert out["iters"].min() >= 1 and out["iters"].max() <= 50
+    again = run(msa, fams)
+    for k in ("pair_a", "pair_b", "len_idx", "site_cat", "iters"):
+        assert np.array_equal(out[k], again[k]), k
+    # families 5, 700 and 2047 on their own
+    stride = int(fams[0]["row_stride"])
+    for f in (5, 700, 2047):
+        one = fams[f: f + 1].copy()
+        one["msa_off"], one["cherry_off"], one["site_off"], one["seq_off"] = 0, 0, 0, 0
+        rows = msa[f * N * stride: (f + 1) * N * stride]
+        alone = run(rows.copy(), one)
+        c0, s0 = f * (N // 2), f * L
+        assert np.array_equal(alone["pair_a"], out["pair_a"][c0: c0 + N // 2])
+        assert np.array_equal(alone["pair_b"], out["pair_b"][c0: c0 + N // 2])
+        assert np.array_equal(alone["len_idx"], out["len_idx"][c0: c0 + N // 2])
+        assert np.array_equal(alone["site_cat"], out["site_cat"][s0: s0 + L])
+    sym = table.cpu().numpy()
+    for f in (0, 1234):
+        seqs = msa[f * N * stride: (f + 1) * N * stride].reshape(N, stride)[:, :L].astype(np.int64)
+        seqs[seqs == 20] = -1
+        cherries = fo.divide_and_pair(seqs, 1234)
+        c0, s0 = f * (N // 2), f * L
+        assert list(zip(out["pair_a"][c0: c0 + N // 2].tolist(), out["pair_b"][c0: c0 + N // 2].tolist())) == cherries
+        len_idx, site_cat, iters = _ble_on_sym(fo, seqs, cherries, sym, cats, weights, 50)
+        assert np.array_equal(out["len_idx"][c0: c0 + N // 2], len_idx)
+        assert np.array_equal(out["site_cat"][s0: s0 + L], site_cat)
+        assert int(out["iters"][f]) == iters
