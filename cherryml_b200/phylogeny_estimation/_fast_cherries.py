@@ -21,7 +21,7 @@ import torch
 
 from .. import _lib
 from ..caching import cached_parallel_computation
-from ..io import Tree, read_rate_matrix, write_tree
+from ..io import Tree, read_rate_matrix
 from ..markov_chain import expm_batched
 
 

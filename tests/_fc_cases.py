@@ -1,6 +1,5 @@
 """Shared loader of the FastCherries goldens (tests/golden/fast_cherries)."""
 import gzip
-import io
 import json
 import os
 import tarfile

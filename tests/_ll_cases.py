@@ -8,7 +8,7 @@ import numpy as np
 
 from cherryml_b200.io import Tree, read_msa, read_rate_matrix, read_site_rates, read_tree
 from cherryml_b200.markov_chain import chain_product, compute_stationary_distribution
-from tests.conftest import GOLDEN, REPO
+from tests.conftest import GOLDEN
 
 AA = list("ARNDCQEGHILKMFPSTWYV")
 LL_DIR = os.path.join(GOLDEN, "likelihood")

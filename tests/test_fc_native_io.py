@@ -1,7 +1,5 @@
 """The FastCherries stage's native text I/O (cherry_fc_read_msas / cherry_fc_write_outputs, host
 threads, no GPU) against the plain-Python implementations of the same formats, byte for byte."""
-import os
-
 import numpy as np
 
 from cherryml_b200.io import write_tree
@@ -135,7 +133,6 @@ def test_in_memory_hand_off_equals_the_route_through_files(tmp_path):
     """FastCherries results -> counting batch WITHOUT the text files (count_layout +
     cherry_fc_lengths_and_rates; the device re-layout is emulated in numpy here) is array for array
     the batch cherry_ingest_lg builds from the files cherry_fc_write_outputs writes."""
-    import ctypes
 
     from cherryml_b200 import _lib
     from cherryml_b200.counting._ingest import build_lg_batch_native

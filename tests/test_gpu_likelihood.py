@@ -11,8 +11,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 from cherryml_b200.evaluation import compute_log_likelihoods, dp_likelihood_computation
-from cherryml_b200.io import (Tree, write_contact_map, write_msa, write_probability_distribution, write_rate_matrix,
-                              write_site_rates, write_tree)
+from cherryml_b200.io import (Tree, write_msa, write_probability_distribution, write_rate_matrix, write_site_rates,
+                              write_tree)
 from tests._ll_cases import AA, fasttree_kats, golden_cases
 
 

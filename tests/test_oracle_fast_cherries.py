@@ -3,7 +3,6 @@ reference's own C++ unit tests and (2) outputs of the unmodified reference progr
 (tests/golden/fast_cherries, see make_golden_fast_cherries*.py); plus host-side pieces of the
 product that need no GPU (grid, categories, weights, MSA encoding, tree layout)."""
 import math
-import os
 
 import numpy as np
 import pytest
