@@ -102,6 +102,7 @@ _SIGNATURES = {
     "cherry_read_count_matrices": (c_int, [c_char_p, c_int, c_int, _P, _P, _P, ctypes.c_size_t, c_int]),
     "cherry_write_labelled_matrix": (c_int, [c_char_p, _P, c_int, _P, c_int]),
     "cherry_fc_lengths_and_rates": (c_int, [_P, c_int, _P, _P, _P, c_int, _P, c_int, c_int, _P, _P, c_int]),
+    "cherry_fc_count_layout": (c_int, [_P, c_int, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int]),
     "cherry_fc_relayout_lg": (c_int, [_P, _P, _P, c_int, _P, _P, _P, _P, _P]),
     "cherry_fc_scratch_bytes": (ctypes.c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int]),
     "cherry_fc_pair": (c_int, [_P, _P, c_int, c_int64, c_int, ctypes.c_uint32, _P, _P, _P, _P, ctypes.c_size_t, _P]),

@@ -466,6 +466,114 @@ int cherry_fc_lengths_and_rates(const cherry_fc_family* fams, int n_fams, const 
   return CHERRY_OK;
 }
 
+// Host metadata of the LG counting batch for FastCherries results, with the layout rules of the
+// ingest (process_family in ingest.cu): categories = the site_cat values present in the family,
+// ascending; sites keep their order inside a category; every category is padded to 4 sites; the
+// row stride is a multiple of 16.  Two calls: out arrays NULL -> only the sizes (sizes[0] = encoded
+// residue bytes, [1] = group_cat entries, [2] = rate values, [3] = tiles, [4] = r_pad,
+// [5] = (pair, site) items); then with the arrays allocated.
+int cherry_fc_count_layout(const cherry_fc_family* fams, int n_fams, const int32_t* site_cat,
+                           const double* rate_table, int R, int chunks_per_tile, int32_t* dest,
+                           uint16_t* group_cat, double* rate_vals, cherry_fam_desc* out_fams, cherry_tile* tiles,
+                           int64_t* sizes, int n_threads) {
+  if (!fams || !site_cat || !sizes || R < 1) return cherry::fail(CHERRY_EINVAL, "null pointer");
+  const bool fill = dest && group_cat && rate_vals && out_fams && tiles && rate_table;
+  std::vector<int64_t> stride((size_t)n_fams), n_rates((size_t)n_fams), n_tiles((size_t)n_fams);
+  std::string err;
+  parallel_for(n_fams, n_threads, [&](int f) {
+    const cherry_fc_family& d = fams[f];
+    std::vector<int64_t> cnt((size_t)R, 0);
+    for (int j = 0; j < d.n_sites; ++j) {
+      const int c = site_cat[d.site_off + j];
+      if (c < 0 || c >= R) throw IoErr{"cherry_fc_count_layout: category out of range"};
+      ++cnt[(size_t)c];
+    }
+    int64_t total = 0, present = 0;
+    for (int r = 0; r < R; ++r)
+      if (cnt[(size_t)r]) {
+        total += (cnt[(size_t)r] + 3) / 4 * 4;
+        ++present;
+      }
+    stride[(size_t)f] = std::max<int64_t>(16, (total + 15) / 16 * 16);
+    n_rates[(size_t)f] = present ? present : 1;
+    const int64_t per_tile = std::max<int64_t>(1, chunks_per_tile / std::max<int64_t>(1, stride[(size_t)f] / 16));
+    const int64_t np = d.n_seqs / 2;
+    n_tiles[(size_t)f] = (np + per_tile - 1) / per_tile;
+  }, &err);
+  if (!err.empty()) return cherry::fail(CHERRY_EINVAL, "%s", err.c_str());
+  std::vector<int64_t> msa_off((size_t)n_fams), aux_off((size_t)n_fams), rate_off((size_t)n_fams),
+      tile_off((size_t)n_fams), pair_off((size_t)n_fams);
+  int64_t msa_bytes = 0, n_aux = 0, n_rate = 0, n_tile = 0, n_pair = 0, examined = 0, max_rates = 1;
+  for (int f = 0; f < n_fams; ++f) {
+    const int64_t np = fams[f].n_seqs / 2;
+    msa_off[(size_t)f] = msa_bytes;
+    aux_off[(size_t)f] = n_aux;
+    rate_off[(size_t)f] = n_rate;
+    tile_off[(size_t)f] = n_tile;
+    pair_off[(size_t)f] = n_pair;
+    msa_bytes += 2 * np * stride[(size_t)f];
+    n_aux += stride[(size_t)f] / 4;
+    n_rate += n_rates[(size_t)f];
+    n_tile += n_tiles[(size_t)f];
+    n_pair += np;
+    examined += np * fams[f].n_sites;
+    max_rates = std::max(max_rates, n_rates[(size_t)f]);
+  }
+  sizes[0] = msa_bytes;
+  sizes[1] = n_aux;
+  sizes[2] = n_rate;
+  sizes[3] = n_tile;
+  sizes[4] = (max_rates + 3) / 4 * 4;
+  sizes[5] = examined;
+  if (n_aux > INT32_MAX || n_rate > INT32_MAX || n_tile > INT32_MAX || n_pair > INT32_MAX)
+    return cherry::fail(CHERRY_ELIMIT, "batch too large for 32-bit indices (split the families)");
+  if (!fill) return CHERRY_OK;
+  parallel_for(n_fams, n_threads, [&](int f) {
+    const cherry_fc_family& d = fams[f];
+    const int32_t* sc = site_cat + d.site_off;
+    std::vector<int64_t> cnt((size_t)R, 0), start((size_t)R, 0);
+    std::vector<int> index_of((size_t)R, -1);
+    for (int j = 0; j < d.n_sites; ++j) ++cnt[(size_t)sc[j]];
+    uint16_t* gc = group_cat + aux_off[(size_t)f];
+    for (int64_t g = 0; g < stride[(size_t)f] / 4; ++g) gc[g] = 0;
+    double* rv = rate_vals + rate_off[(size_t)f];
+    int64_t total = 0;
+    int present = 0;
+    for (int r = 0; r < R; ++r) {
+      if (!cnt[(size_t)r]) continue;
+      start[(size_t)r] = total;
+      index_of[(size_t)r] = present;
+      const int64_t padded = (cnt[(size_t)r] + 3) / 4 * 4;
+      for (int64_t g = total / 4; g < (total + padded) / 4; ++g) gc[g] = (uint16_t)present;
+      rv[present] = rate_table[(size_t)f * R + r];
+      total += padded;
+      ++present;
+    }
+    if (!present) rv[0] = 1.0;
+    for (int j = 0; j < d.n_sites; ++j) dest[d.site_off + j] = (int32_t)start[(size_t)sc[j]]++;
+    cherry_fam_desc& o = out_fams[f];
+    o.msa_off = msa_off[(size_t)f];
+    o.row_stride = (int32_t)stride[(size_t)f];
+    o.n_chunks = (int32_t)(stride[(size_t)f] / 16);
+    o.aux_off = (int32_t)aux_off[(size_t)f];
+    o.aux_cnt = (int32_t)(stride[(size_t)f] / 4);
+    o.rate_off = (int32_t)rate_off[(size_t)f];
+    o.n_rates = (int32_t)n_rates[(size_t)f];
+    const int64_t np = d.n_seqs / 2;
+    const int64_t per_tile = std::max<int64_t>(1, chunks_per_tile / std::max<int64_t>(1, stride[(size_t)f] / 16));
+    int64_t ti = tile_off[(size_t)f];
+    for (int64_t b = 0; b < np; b += per_tile) {
+      cherry_tile& tl = tiles[ti++];
+      tl.fam = f;
+      tl.pair_begin = (int32_t)(pair_off[(size_t)f] + b);
+      tl.n_pairs = (int32_t)std::min<int64_t>(per_tile, np - b);
+      tl.reserved = 0;
+    }
+  }, &err);
+  if (!err.empty()) return cherry::fail(CHERRY_EINVAL, "%s", err.c_str());
+  return CHERRY_OK;
+}
+
 // ------------------------------------------------------------------ count matrices (result.txt)
 // The reference's two writers: io/_count_matrices.py:66-81 (pandas to_csv, repr floats) and the
 // C++ program's writer (counting/_count_transitions.cpp:524-548, ostream << double = "%g").

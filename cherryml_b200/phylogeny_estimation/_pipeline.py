@@ -22,7 +22,33 @@ from ..counting._ingest import TARGET_CHUNKS_PER_TILE
 from . import _fast_cherries as fc
 
 
-def count_layout(fams: np.ndarray, site_cat: np.ndarray, rate_table: np.ndarray):
+def count_layout(fams: np.ndarray, site_cat: np.ndarray, rate_table: np.ndarray, n_threads: Optional[int] = None):
+    """Host metadata of the LG counting batch for FastCherries results by the library's host threads
+    (``cherry_fc_count_layout``); same dictionary as ``count_layout_numpy`` (kept as the readable
+    definition and for the tests)."""
+    lib = _lib.load()
+    F, R = len(fams), rate_table.shape[1]
+    fams_c = np.ascontiguousarray(fams)
+    sc = np.ascontiguousarray(site_cat, dtype=np.int32)
+    rt = np.ascontiguousarray(rate_table, dtype=np.float64)
+    sizes = np.zeros(6, dtype=np.int64)
+    nt = n_threads or os.cpu_count() or 1
+    _lib.check(lib.cherry_fc_count_layout(_lib.ptr(fams_c), F, _lib.ptr(sc), _lib.ptr(rt), R, TARGET_CHUNKS_PER_TILE,
+                                          0, 0, 0, 0, 0, _lib.ptr(sizes), nt), "cherry_fc_count_layout")
+    dest = np.empty(max(1, len(sc)), dtype=np.int32)
+    aux = np.empty(max(1, int(sizes[1])), dtype=np.uint16)
+    rate_vals = np.empty(max(1, int(sizes[2])), dtype=np.float64)
+    out = np.zeros(max(1, F), dtype=_lib.FAM_DESC_DTYPE)
+    tiles = np.zeros(max(1, int(sizes[3])), dtype=_lib.TILE_DTYPE)
+    _lib.check(lib.cherry_fc_count_layout(_lib.ptr(fams_c), F, _lib.ptr(sc), _lib.ptr(rt), R, TARGET_CHUNKS_PER_TILE,
+                                          _lib.ptr(dest), _lib.ptr(aux), _lib.ptr(rate_vals), _lib.ptr(out),
+                                          _lib.ptr(tiles), _lib.ptr(sizes), nt), "cherry_fc_count_layout")
+    return dict(dest=dest[: len(sc)], aux=aux[: int(sizes[1])], rate_vals=rate_vals[: int(sizes[2])], fams=out[:F],
+                tiles=tiles[: int(sizes[3])], r_pad=int(sizes[4]) if F else 4, msa_bytes=int(sizes[0]),
+                examined=int(sizes[5]))
+
+
+def count_layout_numpy(fams: np.ndarray, site_cat: np.ndarray, rate_table: np.ndarray):
     """Host metadata of the LG counting batch for FastCherries results (vectorised over all
     families): per-site destination column, group categories, distinct rate values, family
     descriptors and tiles -- the layout rules of counting/_ingest.py (categories = distinct site

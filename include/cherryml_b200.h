@@ -358,6 +358,16 @@ int cherry_fc_ble(const uint8_t* msa, const cherry_fc_family* fams, int n_fams, 
 int cherry_fc_lengths_and_rates(const cherry_fc_family* fams, int n_fams, const int32_t* len_idx,
                                 const int32_t* site_cat, const double* grid, int K, const double* cats, int R,
                                 int float32_lengths, double* pair_t, double* rate_table, int n_threads);
+/* Host metadata of that LG counting batch (HOST pointers; the ingest's layout rules: categories =
+ * the site_cat values present in a family, sites in order inside a category, categories padded
+ * to 4 sites, row stride a multiple of 16).  Call once with the output arrays NULL to get
+ * sizes[6] = {residue bytes, group_cat entries, rate values, tiles, r_pad, (pair, site) items},
+ * then with dest[total_sites], group_cat, rate_vals, out_fams[n_fams], tiles allocated.
+ * chunks_per_tile: 16384 (the ingest's tile size). */
+int cherry_fc_count_layout(const cherry_fc_family* fams, int n_fams, const int32_t* site_cat,
+                           const double* rate_table, int R, int chunks_per_tile, int32_t* dest,
+                           uint16_t* group_cat, double* rate_vals, cherry_fam_desc* out_fams, cherry_tile* tiles,
+                           int64_t* sizes, int n_threads);
 int cherry_fc_relayout_lg(const uint8_t* msa_in, const cherry_fc_family* fc_fams, const cherry_fam_desc* out_fams,
                           int n_fams, const int32_t* pair_a, const int32_t* pair_b, const int32_t* dest,
                           uint8_t* msa_out, void* stream);

@@ -136,7 +136,7 @@ def test_in_memory_hand_off_equals_the_route_through_files(tmp_path):
 
     from cherryml_b200 import _lib
     from cherryml_b200.counting._ingest import build_lg_batch_native
-    from cherryml_b200.phylogeny_estimation._pipeline import count_layout
+    from cherryml_b200.phylogeny_estimation._pipeline import count_layout, count_layout_numpy
 
     rng = np.random.default_rng(5)
     shapes = [(9, 37), (2, 16), (40, 100), (13, 5), (64, 301)]
@@ -183,7 +183,11 @@ def test_in_memory_hand_off_equals_the_route_through_files(tmp_path):
         _lib.check(lib.cherry_fc_lengths_and_rates(_lib.ptr(fams), len(shapes), _lib.ptr(len_idx), _lib.ptr(site_cat),
                                                    _lib.ptr(grid), len(grid), _lib.ptr(cats), len(cats), int(f32),
                                                    _lib.ptr(pair_t), _lib.ptr(rate_table), 2), "lengths_and_rates")
-        lay = count_layout(fams, site_cat, rate_table)
+        lay = count_layout(fams, site_cat, rate_table, n_threads=2)
+        ref_lay = count_layout_numpy(fams, site_cat, rate_table)
+        for key in ("dest", "aux", "rate_vals", "fams", "tiles"):
+            assert np.array_equal(lay[key], ref_lay[key]), key
+        assert all(lay[k] == ref_lay[k] for k in ("r_pad", "msa_bytes", "examined"))
         assert np.array_equal(pair_t, ref.pair_t)
         assert np.array_equal(lay["rate_vals"], ref.rate_vals)
         assert np.array_equal(lay["aux"], ref.aux)
