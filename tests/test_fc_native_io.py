@@ -208,3 +208,28 @@ def test_in_memory_hand_off_equals_the_route_through_files(tmp_path):
                     base = int(fo["msa_off"]) + (2 * c + side) * int(fo["row_stride"])
                     msa_out[base + dest] = rows_in[src, :L]
         assert np.array_equal(msa_out, ref.msa[: len(msa_out)])
+
+
+def test_empty_and_single_sequence_msas(tmp_path):
+    """An empty MSA, a name without a sequence line and a single-sequence MSA (on which the reference
+    program crashes) are read and written without cherries."""
+    from cherryml_b200.io import read_site_rates, read_tree
+
+    (tmp_path / "empty.txt").write_text("")
+    (tmp_path / "one.txt").write_text(">only\nARND-\n")
+    (tmp_path / "noseq.txt").write_text(">dangling\n")
+    grid = fc.quantization_grid(0.03, 1.1, 64)
+    cats = fc.ble_rate_categories(4)
+    with fc.NativeMsas([str(tmp_path / f) for f in ("empty.txt", "one.txt", "noseq.txt")], AA, pinned=False) as m:
+        assert m.fams["n_seqs"].tolist() == [0, 1, 0] and m.fams["n_sites"].tolist() == [0, 5, 0]
+        assert m.names(1) == ["only"]
+        out = dict(pair_a=np.zeros(0, np.int32), pair_b=np.zeros(0, np.int32),
+                   unpaired=np.array([-1, 0, -1], np.int32), len_idx=np.zeros(0, np.int32),
+                   site_cat=np.zeros(5, np.int32))
+        j = lambda e: [str(tmp_path / f"o{i}{e}") for i in range(3)]  # noqa: E731
+        m.write_outputs(out, grid, cats, j(".tree"), j(".nw"), j(".rates"), j(".ll"), j(".prof"), np.zeros((3, 4)))
+    assert open(j(".tree")[0]).read() == "1 nodes\nroot\n0 edges\n"
+    assert open(j(".rates")[0]).read() == "0 sites\n"
+    tree = read_tree(j(".tree")[1])
+    assert tree.nodes() == ["root", "only"] and tree.edges() == [("root", "only", 1.0)]
+    assert read_site_rates(j(".rates")[1]) == [1.0] * 5
