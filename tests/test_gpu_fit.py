@@ -270,3 +270,40 @@ def test_bucket_sharded_epochs_equal_the_single_gpu_run(S, K):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("S,K", [(20, 24), (48, 6)])
+def test_cherry_loss_autograd_node_in_a_reference_style_loop(S, K):
+    """RateMatrix + torch.optim.Adam + CherryLoss (the CUDA loss/gradient as ONE autograd
+    node) reproduce the fp64 oracle's training trajectory (rate.py + trainer.py restated on the CPU),
+    for both the small (S <= 32) and the large kernel path."""
+    import torch
+
+    from cherryml_b200.estimation import CherryLoss, RateMatrix
+    from oracle.fit_oracle import fit_oracle
+
+    rng = np.random.default_rng(S)
+    times = np.sort(np.exp(rng.uniform(np.log(0.01), np.log(3.0), K)))
+    counts = rng.integers(0, 20, (K, S, S)).astype(np.float64)
+    counts = counts + counts.transpose(0, 2, 1) + 30.0 * np.eye(S)[None]
+    epochs = 12
+    ref = fit_oracle(list(times), counts, num_epochs=epochs, dtype=torch.float64)
+    model = RateMatrix(num_states=S, mode="pande_reversible", mask=None, pi_requires_grad=True, device="cuda:0")
+    opt = torch.optim.Adam(model.parameters(), lr=0.1)
+    t = torch.tensor(times, dtype=torch.float64, device="cuda:0")
+    C = torch.tensor(counts, dtype=torch.float64, device="cuda:0")
+    total = C.sum()
+    losses = []
+    for _ in range(epochs):
+        opt.zero_grad()
+        loss = CherryLoss.apply(model(), t, C) / total
+        losses.append(float(loss.detach()))
+        loss.backward()
+        opt.step()
+    assert np.max(np.abs(np.array(losses) - ref["loss"]) / np.abs(ref["loss"])) < 1e-6
+    # the node's gradient against torch's own autograd through matrix_exp (fp64, on the GPU)
+    Q = model().detach().clone().requires_grad_(True)
+    CherryLoss.apply(Q, t, C).backward()
+    Q2 = Q.detach().clone().requires_grad_(True)
+    (-(C * torch.log(torch.matrix_exp(t[:, None, None] * Q2[None]))).sum()).backward()
+    assert float((Q.grad - Q2.grad).abs().max() / Q2.grad.abs().max()) < 1e-9
