@@ -76,11 +76,11 @@ def _hash_all(xs: List[str]) -> str:
     return res
 
 
-def _caching_dir(func, unhashed: List[str], kwargs, cache_dir: str) -> str:
+def _caching_dir(func, unhashed: List[str], kwargs, cache_dir: str, use_hash: Optional[bool] = None) -> str:
     binding = signature(func).bind(**kwargs)
     binding.apply_defaults()
     items = [(k, v) for k, v in binding.arguments.items() if k not in unhashed]
-    if _USE_HASH:
+    if _USE_HASH if use_hash is None else use_hash:
         key = _hash_all(sum(([f"{k}", f"{v}"] for k, v in items), []))
         return os.path.join(cache_dir, func.__name__, key)
     return os.path.join(cache_dir, func.__name__, *[f"{k}_{v}" for k, v in items])
@@ -88,6 +88,22 @@ def _caching_dir(func, unhashed: List[str], kwargs, cache_dir: str) -> str:
 
 def _make_read_only(path: str) -> None:
     os.chmod(path, stat.S_IRUSR | stat.S_IRGRP | stat.S_IROTH)
+
+
+def _write_unhashed_dir_log(out_dir: str, func, unhashed: List[str], kwargs, cache_dir: str) -> None:
+    """``_unhashed_output_dir.log``: the cache directory this call would have without hashing
+    (reference ``_cached_computation.py:96-129``); written once, then read-only."""
+    log = os.path.join(out_dir, "_unhashed_output_dir.log")
+    if os.path.exists(log):
+        return
+    plain = {k: (None if k in unhashed else v) for k, v in kwargs.items()}
+    try:
+        text = _caching_dir(func, unhashed, plain, cache_dir, use_hash=False)
+    except Exception:  # unprintable arguments must not break the computation
+        return
+    with open(log, "w") as f:
+        f.write(text)
+    _make_read_only(log)
 
 
 def cached_computation(
@@ -152,6 +168,7 @@ def cached_computation(
                         with open(log, "w") as f:
                             f.write(str(b))
                         _make_read_only(log)
+                    _write_unhashed_dir_log(kwargs[od], func, unhashed, kwargs, cache_dir)
             if not computed:
                 if _READ_ONLY:
                     raise CacheUsageError("Cache is in read only mode! Will not call function.")
@@ -253,6 +270,7 @@ def cached_parallel_computation(
                         with open(log, "w") as f:
                             f.write(str(b))
                         _make_read_only(log)
+                    _write_unhashed_dir_log(kwargs[od], func, unhashed, kwargs, cache_dir)
             if todo:
                 if _READ_ONLY:
                     raise CacheUsageError("Cache is in read only mode! Will not call function.")
