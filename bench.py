@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--fc-families", type=int, default=2048, help="FastCherries families per GPU")
     ap.add_argument("--no-likelihood", action="store_true")
     ap.add_argument("--no-siterm", action="store_true")
+    ap.add_argument("--no-public-api", action="store_true")
     return ap.parse_args()
 
 
@@ -439,6 +440,14 @@ def run_ours(args):
             srb = bench_siterm(device, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
         except Exception as e:
             srb = {"error": str(e)[:300]}
+    apib = None
+    if rank == 0 and world == 1 and not args.no_public_api:
+        from benchlib.public_api_demo import bench_public_api_demo
+
+        try:
+            apib = bench_public_api_demo()
+        except Exception as e:
+            apib = {"error": str(e)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -477,6 +486,8 @@ def run_ours(args):
         line["tree_likelihood"] = llb
     if srb is not None:
         line["siterm"] = srb
+    if apib is not None:
+        line["public_api_demo"] = apib
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_cpu_fam = args.cpu_families or default_cpu_families()
