@@ -72,13 +72,22 @@ def quantized_transitions_mle_vectorized_over_sites(
     initialization: Optional[np.ndarray] = None,
     num_cores: int = 1,
     device: str = "cpu",
+    process_group=None,
 ) -> Dict:
     """Estimate site-specific rate matrices from their count matrices.
+
+    ``process_group`` (torch.distributed, one process per GPU): the sites are independent
+    problems, so rank r fits the contiguous block ``site_blocks(L, world)[r]`` and the results are
+    gathered -- no exchange step during training.  Every rank returns the
+    full result.  Without an initialisation the random start of a site depends on its position in
+    the batch (as in the reference), so sharded and unsharded runs agree only with one.
 
     ``counts``: ``L x B x N x N``; ``times``: ``L x B``.  Returns the reference's dictionary:
     ``res`` (``L x N x N``, per-site best iterate), ``loss_per_epoch``,
     ``loss_per_epoch_per_site`` and ``time_*`` entries.  ``device`` / ``num_cores`` are
     accepted for compatibility; the computation runs on a CUDA device."""
+    if process_group is not None:
+        return _fit_sharded_over_sites(counts, times, num_epochs, initialization, num_cores, device, process_group)
     st = time.time()
     prof = {}
     counts = np.asarray(counts, dtype=np.float64)
@@ -112,4 +121,45 @@ def quantized_transitions_mle_vectorized_over_sites(
         "loss_per_epoch_per_site": per_site,
     }
     out.update(prof)
+    return out
+
+
+def site_blocks(num_sites: int, world_size: int) -> List[range]:
+    """Contiguous, balanced blocks of sites, one per rank (the first ``num_sites % world_size``
+    blocks are one site longer)."""
+    base, extra = divmod(num_sites, world_size)
+    blocks, start = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < extra else 0)
+        blocks.append(range(start, start + n))
+        start += n
+    return blocks
+
+
+def _fit_sharded_over_sites(counts, times, num_epochs, initialization, num_cores, device, process_group) -> Dict:
+    import torch.distributed as dist
+
+    counts = np.asarray(counts, dtype=np.float64)
+    times = np.asarray(times, dtype=np.float64)
+    L = counts.shape[0]
+    world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+    mine = site_blocks(L, world)[rank]
+    local = None
+    if len(mine):
+        sl = slice(mine.start, mine.stop)
+        local = quantized_transitions_mle_vectorized_over_sites(
+            counts[sl], times[sl], num_epochs, None if initialization is None else np.asarray(initialization)[sl],
+            num_cores, device)
+    pieces = [None] * world
+    dist.all_gather_object(pieces, None if local is None else
+                           {k: local[k] for k in ("res", "loss_per_epoch_per_site")}, group=process_group)
+    pieces = [p for p in pieces if p is not None]
+    per_site = np.concatenate([p["loss_per_epoch_per_site"] for p in pieces], axis=1)
+    out = {
+        "res": np.concatenate([p["res"] for p in pieces], axis=0),
+        "loss_per_epoch": per_site.sum(axis=1),
+        "loss_per_epoch_per_site": per_site,
+    }
+    if local is not None:
+        out.update({k: v for k, v in local.items() if k.startswith("time_")})
     return out

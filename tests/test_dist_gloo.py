@@ -169,3 +169,44 @@ def test_two_rank_fast_cherries_stage_stripes_families(tmp_path):
     for f in families:
         owner = sorted(families).index(f) % 2
         assert open(tmp_path / "tree" / f"{f}.txt").read() == f"rank {owner}\n"
+
+
+def _siterm_worker(rank, world, port, out_root):
+    """Two ranks fit disjoint blocks of sites (the per-rank GPU fit is replaced by a deterministic
+    stand-in: this test is about the blocks and the gather) and both end up with the full result."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cherryml_b200.siterm import _vectorized as v
+
+    L, B, N = 7, 3, 4
+    counts = np.arange(L * B * N * N, dtype=np.float64).reshape(L, B, N, N)
+    times = np.ones((L, B))
+    real = v.quantized_transitions_mle_vectorized_over_sites
+
+    def fake(counts, times, num_epochs, initialization=None, num_cores=1, device="cpu", process_group=None):
+        if process_group is not None:
+            return real(counts, times, num_epochs, initialization, num_cores, device, process_group)
+        n = counts.shape[0]
+        return {"res": counts.sum(axis=1), "loss_per_epoch_per_site": np.tile(counts.sum(axis=(1, 2, 3)), (2, 1)),
+                "loss_per_epoch": np.zeros(2), "time_compute_loss": float(n)}
+
+    v.quantized_transitions_mle_vectorized_over_sites = fake
+    out = v._fit_sharded_over_sites(counts, times, 2, None, 1, "cpu", dist.group.WORLD)
+    np.savez(os.path.join(out_root, f"siterm_{rank}.npz"), res=out["res"], per_site=out["loss_per_epoch_per_site"],
+             mine=np.array([out["time_compute_loss"]]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_siterm_fit_shards_sites(tmp_path):
+    from cherryml_b200.siterm._vectorized import site_blocks
+
+    assert [list(b) for b in site_blocks(7, 2)] == [[0, 1, 2, 3], [4, 5, 6]]
+    assert [len(b) for b in site_blocks(3, 8)] == [1, 1, 1, 0, 0, 0, 0, 0]
+    mp.spawn(_siterm_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    counts = np.arange(7 * 3 * 4 * 4, dtype=np.float64).reshape(7, 3, 4, 4)
+    for rank, n_mine in ((0, 4.0), (1, 3.0)):
+        g = np.load(tmp_path / f"siterm_{rank}.npz")
+        assert np.array_equal(g["res"], counts.sum(axis=1))
+        assert np.array_equal(g["per_site"], np.tile(counts.sum(axis=(1, 2, 3)), (2, 1)))
+        assert g["mine"][0] == n_mine

@@ -236,3 +236,27 @@ def test_public_api_without_tree_uses_fast_cherries(tmp_path):
         optimization_num_epochs=15)
     assert np.array_equal(r["learnt_rate_matrices"], by_hand["res"])
     assert r["learnt_rate_matrices"].shape == (100, 20, 20)
+
+
+def test_sharded_over_sites_equals_plain_run():
+    """One-rank NCCL group through the site-sharded path (blocks + gather): same result as the plain call."""
+    import torch
+    import torch.distributed as dist
+
+    g = np.load(os.path.join(G, "aa_init.npz"))
+    plain = quantized_transitions_mle_vectorized_over_sites(g["counts"], g["times"], num_epochs=10,
+                                                            initialization=g["init"])
+    created = not dist.is_initialized()
+    if created:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29534")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        sharded = quantized_transitions_mle_vectorized_over_sites(g["counts"], g["times"], num_epochs=10,
+                                                                  initialization=g["init"],
+                                                                  process_group=dist.group.WORLD)
+    finally:
+        if created:
+            dist.destroy_process_group()
+    assert np.array_equal(sharded["res"], plain["res"])
+    assert np.array_equal(sharded["loss_per_epoch_per_site"], plain["loss_per_epoch_per_site"])
