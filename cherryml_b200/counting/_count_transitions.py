@@ -29,7 +29,7 @@ import torch
 from .. import caching
 from ..io import write_count_matrices_array
 from ..utils import get_process_args
-from ._device import count_batch
+from ._device import count_batch, count_batches_streamed
 from ._ingest import build_co_batch, build_co_batch_native, build_lg_batch, build_lg_batch_native
 
 logger = logging.getLogger(__name__)
@@ -89,6 +89,7 @@ def _finish(counts_dev, grid, states, out_dir, style, start_time, num_processes,
         "process_group",
         "result_style",
         "ingest",
+        "families_per_batch",
     ],
     output_dirs=["output_count_matrices_dir"],
     write_extra_log_files=True,
@@ -110,8 +111,11 @@ def count_transitions(
     process_group=None,
     result_style: Optional[str] = None,
     ingest: str = "native",
+    families_per_batch: int = 1024,
 ) -> None:
-    """Count single-site transitions into a ``K x S x S`` tensor (see module docstring)."""
+    """Count single-site transitions into a ``K x S x S`` tensor (see module docstring).  More than
+    ``families_per_batch`` families are streamed: batches are parsed and encoded by the library's
+    host threads into pooled page-locked buffers while the previous batch is uploaded and counted."""
     if edge_or_cherry.startswith("cherry++__"):
         edge_or_cherry = "cherry++"
     start_time = time.time()
@@ -120,6 +124,22 @@ def count_transitions(
     quantization_points = [float(q) for q in quantization_points]
     rank, world = _rank_world(process_group)
     my_families = get_process_args(rank, world, list(families))
+    if ingest == "native" and len(my_families) > families_per_batch > 0:
+        def build(fams):
+            return build_lg_batch_native(
+                tree_dir, msa_dir, site_rates_dir, fams, amino_acids, edge_or_cherry,
+                float32_branch_lengths=bool(use_cpp_implementation), n_threads=_ingest_threads(num_processes),
+                pinned=True)
+
+        chunks = [my_families[i: i + families_per_batch] for i in range(0, len(my_families), families_per_batch)]
+        counts = count_batches_streamed(build, chunks, "lg", quantization_points, len(amino_acids),
+                                        directed=(edge_or_cherry == "edge"), device=device,
+                                        process_group=process_group)
+        style = result_style or ("cpp" if use_cpp_implementation else "python")
+        _finish(counts, np.array(sorted(quantization_points)), list(amino_acids),
+                output_count_matrices_dir, style, start_time, num_processes, rank, process_group)
+        logger.info("Done!")
+        return
     if ingest == "native":
         batch = build_lg_batch_native(
             tree_dir, msa_dir, site_rates_dir, my_families, amino_acids, edge_or_cherry,
@@ -152,6 +172,7 @@ def count_transitions(
         "process_group",
         "result_style",
         "ingest",
+        "families_per_batch",
     ],
     output_dirs=["output_count_matrices_dir"],
     write_extra_log_files=True,
@@ -174,8 +195,10 @@ def count_co_transitions(
     process_group=None,
     result_style: Optional[str] = None,
     ingest: str = "native",
+    families_per_batch: int = 1024,
 ) -> None:
-    """Count transitions of contacting site pairs into a ``K x S^2 x S^2`` tensor."""
+    """Count transitions of contacting site pairs into a ``K x S^2 x S^2`` tensor (streamed in
+    batches of ``families_per_batch`` families like ``count_transitions``)."""
     if edge_or_cherry.startswith("cherry++__"):
         edge_or_cherry = "cherry++"
     start_time = time.time()
@@ -183,6 +206,23 @@ def count_co_transitions(
     quantization_points = [float(q) for q in quantization_points]
     rank, world = _rank_world(process_group)
     my_families = get_process_args(rank, world, list(families))
+    if ingest == "native" and len(my_families) > families_per_batch > 0:
+        def build(fams):
+            return build_co_batch_native(
+                tree_dir, msa_dir, contact_map_dir, fams, amino_acids, edge_or_cherry,
+                minimum_distance_for_nontrivial_contact, float32_branch_lengths=bool(use_cpp_implementation),
+                n_threads=_ingest_threads(num_processes), pinned=True)
+
+        chunks = [my_families[i: i + families_per_batch] for i in range(0, len(my_families), families_per_batch)]
+        counts = count_batches_streamed(build, chunks, "co", quantization_points, len(amino_acids),
+                                        directed=(edge_or_cherry == "edge"), device=device,
+                                        process_group=process_group)
+        pair_states = [a + b for a in amino_acids for b in amino_acids]
+        style = result_style or ("cpp" if use_cpp_implementation else "python")
+        _finish(counts, np.array(sorted(quantization_points)), pair_states,
+                output_count_matrices_dir, style, start_time, num_processes, rank, process_group)
+        logger.info("Done!")
+        return
     if ingest == "native":
         batch = build_co_batch_native(
             tree_dir, msa_dir, contact_map_dir, my_families, amino_acids, edge_or_cherry,

@@ -222,6 +222,48 @@ def count_batch(
     return symmetrize(raw, batch.kind, K, num_states, directed)
 
 
+def count_batches_streamed(
+    build_batch,
+    family_chunks: Sequence[Sequence[str]],
+    kind: str,
+    quantization_points: Sequence[float],
+    num_states: int,
+    directed: bool,
+    device="cuda",
+    process_group=None,
+) -> torch.Tensor:
+    """Chunks of families through ingest -> H2D -> counting with the ingest of chunk i+1 (host
+    threads of the library, the GIL is released during the call) running while chunk i is uploaded
+    and counted; ``build_batch(families) -> CountBatch``.  The raw integer histograms of the chunks
+    add up exactly, so the result does not depend on the chunking."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    grid = sorted_grid(quantization_points)
+    K = int(grid.size)
+    dev = torch.device(device)
+    raw = None
+    chunks = [c for c in family_chunks if len(c)]
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        pending = pool.submit(build_batch, chunks[0]) if chunks else None
+        for i in range(len(chunks)):
+            batch = pending.result()
+            pending = pool.submit(build_batch, chunks[i + 1]) if i + 1 < len(chunks) else None
+            d = to_device(batch, dev)
+            validate_residues(d.msa, num_states)
+            grid_dev = torch.from_numpy(grid).to(d.msa.device)
+            raw = count_raw(d, grid_dev, K, num_states, out=raw)
+            torch.cuda.synchronize(d.msa.device)  # the host batch (pooled pinned buffer) may be reused now
+            del batch, d
+    if raw is None:
+        n = num_states if kind == "lg" else num_states * num_states
+        raw = torch.zeros((K, n, n), dtype=torch.int64 if kind == "lg" else torch.int32, device=dev)
+    if process_group is not None:
+        import torch.distributed as dist
+
+        dist.all_reduce(raw, op=dist.ReduceOp.SUM, group=process_group)
+    return symmetrize(raw, kind, K, num_states, directed)
+
+
 def count_lg_host(batch: CountBatch, quantization_points: Sequence[float], num_states: int,
                   directed: bool):
     """End-to-end LG counting from HOST buffers through ``cherry_count_lg_host``.

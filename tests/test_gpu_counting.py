@@ -336,3 +336,30 @@ def test_bucket_table_at_bucket_boundaries():
         for r in range(4):
             exp = quantization_idx_c(t * rates[r], grid)
             assert tab[i, r] == (255 if exp < 0 else exp), (t, rates[r])
+
+
+@pytest.mark.parametrize("families_per_batch", [1, 2])
+def test_streamed_batches_equal_the_single_batch(golden_counting, tmp_path, families_per_batch):
+    """More families than `families_per_batch`: chunks are ingested by host threads while the
+    previous chunk is counted; the raw integer histograms add up exactly, so the files are the
+    reference program's byte for byte as in the single-batch tests above."""
+    m3 = os.path.join(golden_counting, "medium3")
+    out = str(tmp_path / "lg")
+    count_transitions(
+        tree_dir=f"{m3}/tree_dir", msa_dir=f"{m3}/msa_dir", site_rates_dir=f"{m3}/site_rates_dir",
+        families=MEDIUM3, amino_acids=amino_acids, quantization_points=GRID_LG, edge_or_cherry="cherry++",
+        output_count_matrices_dir=out, use_cpp_implementation=True, num_processes=4,
+        families_per_batch=families_per_batch,
+    )
+    golden = f"{m3}/refcpp_count_matrices_dir_cherries_plus_plus/result.txt"
+    assert open(os.path.join(out, "result.txt")).read() == open(golden).read()
+    out = str(tmp_path / "co")
+    count_co_transitions(
+        tree_dir=f"{m3}/tree_dir", msa_dir=f"{m3}/msa_dir", contact_map_dir=f"{m3}/contact_map_dir",
+        families=MEDIUM3, amino_acids=amino_acids, quantization_points=GRID_CO, edge_or_cherry="cherry++",
+        minimum_distance_for_nontrivial_contact=7, output_count_matrices_dir=out, num_processes=4,
+        families_per_batch=families_per_batch,
+    )
+    gcounts = np.load(f"{m3}/refcpp_count_co_matrices_dir_cherries_plus_plus/result.npz")["counts"]
+    _, _, dev = device_result(out)
+    assert np.array_equal(dev.cpu().numpy(), gcounts)
