@@ -51,6 +51,26 @@ __device__ __forceinline__ int quantize_bucket(double t, const double* __restric
   return (el < er) ? lo - 1 : lo;
 }
 
+// The same function with the binary search replaced by a guess: the grids in use are geometric
+// (center * step^i, rounded to 8 decimals), so floor((log2 t - log2 q0) * (K-1)/log2(q[K-1]/q0))
+// is within one of the lower bound; the two loops then walk to the exact lower bound (first index
+// with q[lo] >= t) for ANY ascending grid, so the result is the binary search's by construction.
+__device__ __forceinline__ int quantize_bucket_guess(double t, const double* __restrict__ q, int K, float log2_q0,
+                                                     float inv_log2_step) {
+  if (t < q[0] || t > q[K - 1]) return -1;
+  int lo = t == t ? (int)((__log2f((float)t) - log2_q0) * inv_log2_step) : 0;
+  lo = max(0, min(K - 1, lo));
+  while (lo > 0 && q[lo - 1] >= t) --lo;
+  while (lo < K && q[lo] < t) ++lo;
+  if (lo == 0) return 0;
+  const double left = q[lo - 1], right = q[lo];
+  const double tt = __dmul_rn(t, t), lr = __dmul_rn(left, right);
+  if (fabs(tt - lr) > 1e-12 * lr) return (tt < lr) ? lo - 1 : lo;
+  const double el = __dsub_rn(__ddiv_rn(t, left), 1.0);
+  const double er = __dsub_rn(__ddiv_rn(right, t), 1.0);
+  return (el < er) ? lo - 1 : lo;
+}
+
 // One thread per pair: all r_pad entries of its row (r_pad is a multiple of 4, the row is
 // written as 32-bit words).
 __global__ void bucket_table_kernel(const double* __restrict__ pair_t,
@@ -62,6 +82,9 @@ __global__ void bucket_table_kernel(const double* __restrict__ pair_t,
   extern __shared__ double sgrid[];
   for (int i = threadIdx.x; i < K; i += blockDim.x) sgrid[i] = grid[i];
   __syncthreads();
+  const float log2_q0 = sgrid[0] > 0.0 ? log2f((float)sgrid[0]) : 0.0f;
+  const float span = K > 1 && sgrid[0] > 0.0 ? log2f((float)(sgrid[K - 1] / sgrid[0])) : 0.0f;
+  const float inv_log2_step = span > 0.0f ? (float)(K - 1) / span : 0.0f;
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_pairs;
        p += (int64_t)gridDim.x * blockDim.x) {
     const cherry_fam_desc* fd = fams + pair_fam[p];
@@ -75,7 +98,7 @@ __global__ void bucket_table_kernel(const double* __restrict__ pair_t,
       for (int k = 0; k < 4; ++k) {
         uint32_t out = CHERRY_NO_BUCKET;
         if (r0 + k < n_rates) {
-          const int b = quantize_bucket(__dmul_rn(t0, rv[r0 + k]), sgrid, K);
+          const int b = quantize_bucket_guess(__dmul_rn(t0, rv[r0 + k]), sgrid, K, log2_q0, inv_log2_step);
           if (b >= 0) out = (uint32_t)b;
         }
         word |= out << (8 * k);
