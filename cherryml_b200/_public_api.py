@@ -22,7 +22,8 @@ import numpy as np
 from . import caching
 from .counting import count_co_transitions, count_transitions, device_result
 from .estimation import jtt_ipw, quantized_transitions_mle
-from .io import read_contact_map, read_rate_matrix, read_site_rates, write_contact_map, write_rate_matrix
+from .io import (read_contact_map, read_msa, read_rate_matrix, read_site_rates, read_sites_subset, write_contact_map,
+                 write_msa, write_rate_matrix, write_site_rates)
 from .markov_chain import get_equ_path, get_lg_path
 from .phylogeny_estimation import fast_cherries
 from .utils import get_amino_acids, get_families
@@ -75,6 +76,32 @@ def create_maximal_matching_contact_map(
         write_contact_map(res, os.path.join(o_contact_map_dir, family + ".txt"))
     with open(os.path.join(o_contact_map_dir, "result.txt"), "w") as f:
         f.write(f"{len(families)} families\n")
+
+
+@caching.cached_parallel_computation(
+    exclude_args=["num_processes"],
+    parallel_arg="families",
+    output_dirs=["output_msa_dir", "output_site_rates_dir"],
+    write_extra_log_files=True,
+)
+def _subset_data_to_sites_subset(
+    sites_subset_dir: str,
+    msa_dir: str,
+    site_rates_dir: str,
+    families: List[str],
+    num_processes: int = 1,
+    output_msa_dir: Optional[str] = None,
+    output_site_rates_dir: Optional[str] = None,
+):
+    """MSAs and site rates restricted to the sites listed in ``<sites_subset_dir>/<family>.txt``
+    (reference ``estimation_end_to_end/_cherry.py:41-147``)."""
+    for family in families:
+        sites = read_sites_subset(os.path.join(sites_subset_dir, family + ".txt"))
+        msa = read_msa(os.path.join(msa_dir, family + ".txt"))
+        rates = read_site_rates(os.path.join(site_rates_dir, family + ".txt"))
+        write_msa({name: "".join(seq[i] for i in sites) for name, seq in msa.items()},
+                  os.path.join(output_msa_dir, family + ".txt"))
+        write_site_rates([rates[i] for i in sites], os.path.join(output_site_rates_dir, family + ".txt"))
 
 
 def _no_tree_estimator(what: str):
@@ -132,8 +159,6 @@ def lg_end_to_end_with_cherryml_optimizer(
         )
     if tree_estimator is None and (tree_dir is None or num_iterations != 1):
         _no_tree_estimator("lg_end_to_end_with_cherryml_optimizer")
-    if sites_subset_dir is not None:
-        raise NotImplementedError("sites_subset_dir is not supported")
     res: Dict = {}
     quantization_points = _quantization_points(
         quantization_grid_center, quantization_grid_step, quantization_grid_num_steps)
@@ -155,6 +180,15 @@ def lg_end_to_end_with_cherryml_optimizer(
             times["pairing"] += _tree_estimation_runtime(tree_estimator_output_dirs, families, "pairing")
             times["ble"] += _tree_estimation_runtime(tree_estimator_output_dirs, families, "ble")
         res[f"tree_estimator_output_dirs_{iteration}"] = tree_estimator_output_dirs
+        if sites_subset_dir is not None:
+            sub = _subset_data_to_sites_subset(
+                sites_subset_dir=sites_subset_dir, msa_dir=msa_dir,
+                site_rates_dir=tree_estimator_output_dirs["output_site_rates_dir"], families=families,
+                num_processes=num_processes_counting,
+            )
+            msa_dir = sub["output_msa_dir"]
+            tree_estimator_output_dirs = dict(tree_estimator_output_dirs,
+                                              output_site_rates_dir=sub["output_site_rates_dir"])
         count_matrices_dir = count_transitions(
             tree_dir=tree_estimator_output_dirs["output_tree_dir"], msa_dir=msa_dir,
             site_rates_dir=tree_estimator_output_dirs["output_site_rates_dir"], families=families,

@@ -538,6 +538,37 @@ def write_probability_distribution(
         f.write("state\tprob\n" + "".join(f"{s}\t{v!r}\n" for s, v in zip(states, p.tolist())))
 
 
+def read_sites_subset(sites_subset_path: str) -> List[int]:
+    """``<n> sites`` then n space-separated site indices (reference io/_sites_subset.py:5-32)."""
+    with open(sites_subset_path) as f:
+        lines = f.read().strip().split("\n")
+    try:
+        num_sites, s = lines[0].split(" ")
+        if s != "sites":
+            raise Exception
+        num_sites = int(num_sites)
+    except Exception:
+        raise Exception(
+            f"Sites subset file: {sites_subset_path} should start with line "
+            f"'[num_sites] sites', but started with: {lines[0]} instead."
+        )
+    try:
+        res = [] if num_sites == 0 else list(map(int, lines[1].split(" ")))
+    except Exception:
+        raise Exception(f"Could nor read sites subset in file: {sites_subset_path}. Lines: {lines}")
+    if len(res) != num_sites:
+        raise Exception(
+            f"Sites subset file: {sites_subset_path} was supposed to have {num_sites} sites, but it has {len(res)}"
+        )
+    return res
+
+
+def write_sites_subset(sites_subset: Sequence[int], sites_subset_path: str) -> None:
+    _makedirs_for(sites_subset_path)
+    with open(sites_subset_path, "w") as f:
+        f.write(f"{len(sites_subset)} sites\n" + " ".join(map(str, sites_subset)))
+
+
 def _makedirs_for(path: str) -> None:
     d = os.path.dirname(path)
     if d != "" and not os.path.exists(d):

@@ -1,0 +1,42 @@
+"""``sites_subset_dir`` of the LG pipeline: MSAs and site rates restricted to listed sites
+(reference estimation_end_to_end/_cherry.py:41-147, io/_sites_subset.py); host logic, no GPU."""
+import os
+
+import pytest
+
+from cherryml_b200 import caching
+from cherryml_b200._public_api import _subset_data_to_sites_subset
+from cherryml_b200.io import (read_msa, read_site_rates, read_sites_subset, write_msa, write_site_rates,
+                              write_sites_subset)
+
+
+def test_sites_subset_files_round_trip(tmp_path):
+    p = str(tmp_path / "s" / "fam.txt")
+    write_sites_subset([4, 0, 2], p)
+    assert open(p).read() == "3 sites\n4 0 2"
+    assert read_sites_subset(p) == [4, 0, 2]
+    write_sites_subset([], p)
+    assert read_sites_subset(p) == []
+    (tmp_path / "bad.txt").write_text("2 sites\n1")
+    with pytest.raises(Exception, match="supposed to have 2 sites"):
+        read_sites_subset(str(tmp_path / "bad.txt"))
+    (tmp_path / "bad2.txt").write_text("2 columns\n1 2")
+    with pytest.raises(Exception, match="should start with line"):
+        read_sites_subset(str(tmp_path / "bad2.txt"))
+
+
+def test_subset_stage_restricts_msa_and_rates(tmp_path):
+    for d in ("msa", "rates", "subset"):
+        (tmp_path / d).mkdir()
+    write_msa({"a": "ARNDC", "b": "QEGHI"}, str(tmp_path / "msa" / "f.txt"))
+    write_site_rates([0.5, 1.0, 1.5, 2.0, 2.5], str(tmp_path / "rates" / "f.txt"))
+    write_sites_subset([3, 1], str(tmp_path / "subset" / "f.txt"))
+    caching.set_cache_dir(str(tmp_path / "cache"))
+    try:
+        out = _subset_data_to_sites_subset(sites_subset_dir=str(tmp_path / "subset"), msa_dir=str(tmp_path / "msa"),
+                                           site_rates_dir=str(tmp_path / "rates"), families=["f"], num_processes=3)
+    finally:
+        caching.set_cache_dir(None)
+    assert read_msa(os.path.join(out["output_msa_dir"], "f.txt")) == {"a": "DR", "b": "HE"}
+    assert read_site_rates(os.path.join(out["output_site_rates_dir"], "f.txt")) == [2.0, 1.0]
+    assert os.path.exists(os.path.join(out["output_msa_dir"], "f.success"))
