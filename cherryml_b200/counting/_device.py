@@ -242,6 +242,7 @@ def count_batches_streamed(
     K = int(grid.size)
     dev = torch.device(device)
     raw = None
+    co_items = 0  # the co histogram has uint32 cells and is accumulated over ALL chunks
     chunks = [c for c in family_chunks if len(c)]
     with ThreadPoolExecutor(max_workers=1) as pool:
         pending = pool.submit(build_batch, chunks[0]) if chunks else None
@@ -250,6 +251,12 @@ def count_batches_streamed(
             pending = pool.submit(build_batch, chunks[i + 1]) if i + 1 < len(chunks) else None
             d = to_device(batch, dev)
             validate_residues(d.msa, num_states)
+            if kind == "co" and d.tile_items is not None:
+                co_items += int(d.tile_items.sum())
+                if co_items > _CO_MAX_ITEMS_PER_LAUNCH:
+                    raise _lib.CherryError(
+                        f"more than {_CO_MAX_ITEMS_PER_LAUNCH} (pair, contact) items in one call could wrap a "
+                        "uint32 cell of the co-transition histogram; count the families in several calls")
             grid_dev = torch.from_numpy(grid).to(d.msa.device)
             raw = count_raw(d, grid_dev, K, num_states, out=raw)
             torch.cuda.synchronize(d.msa.device)  # the host batch (pooled pinned buffer) may be reused now
