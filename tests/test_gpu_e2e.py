@@ -82,3 +82,38 @@ def test_coevolution_demo_matches_reference_public_api(demo, tmp_path):
     assert np.max(np.abs(loss - g["loss"]) / np.abs(g["loss"])) < 1e-4
     learned = read_rate_matrix(out).to_numpy()
     assert np.max(np.abs(learned - g["learned"])) < 1e-4 * np.max(np.abs(g["learned"]))
+
+
+def test_lg_pipeline_with_sites_subset(demo, tmp_path):
+    """sites_subset_dir: the pipeline counts on the MSAs / site rates restricted to the listed
+    sites -- same count matrices as counting on data subset by hand."""
+    from cherryml_b200._public_api import _quantization_points, lg_end_to_end_with_cherryml_optimizer
+    from cherryml_b200.counting import count_transitions
+    from cherryml_b200.io import read_msa, read_site_rates, write_msa, write_site_rates, write_sites_subset
+    from cherryml_b200.utils import get_amino_acids
+
+    fams = ["13gs_1_A", "1a0b_1_A"]
+    rng = np.random.default_rng(0)
+    for d in ("subset", "msa_by_hand", "rates_by_hand"):
+        (tmp_path / d).mkdir()
+    for f in fams:
+        msa = read_msa(f"{demo}/msas/{f}.txt")
+        rates = read_site_rates(f"{demo}/site_rates/{f}.txt")
+        sites = sorted(rng.choice(len(rates), size=len(rates) // 3, replace=False).tolist())
+        write_sites_subset(sites, str(tmp_path / "subset" / f"{f}.txt"))
+        write_msa({k: "".join(v[i] for i in sites) for k, v in msa.items()}, str(tmp_path / "msa_by_hand" / f"{f}.txt"))
+        write_site_rates([rates[i] for i in sites], str(tmp_path / "rates_by_hand" / f"{f}.txt"))
+    caching.set_cache_dir(str(tmp_path / "cache"))
+    try:
+        res = lg_end_to_end_with_cherryml_optimizer(
+            msa_dir=f"{demo}/msas", families=fams, tree_dir=f"{demo}/trees", site_rates_dir=f"{demo}/site_rates",
+            sites_subset_dir=str(tmp_path / "subset"), num_epochs=5, use_cpp_counting_implementation=False)
+        by_hand = count_transitions(
+            tree_dir=f"{demo}/trees", msa_dir=str(tmp_path / "msa_by_hand"),
+            site_rates_dir=str(tmp_path / "rates_by_hand"), families=fams, amino_acids=get_amino_acids(),
+            quantization_points=_quantization_points(0.03, 1.1, 64), edge_or_cherry="cherry++", num_processes=1,
+            use_cpp_implementation=False)["output_count_matrices_dir"]
+    finally:
+        caching.set_cache_dir(None)
+    assert open(os.path.join(res["count_matrices_dir_0"], "result.txt")).read() == \
+        open(os.path.join(by_hand, "result.txt")).read()
