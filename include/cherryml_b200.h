@@ -36,6 +36,13 @@
  *                              (fast_cherries.cpp:258-266).
  *   cherry_tree_log_likelihood the pruning loops of dp_likelihood_computation,
  *                              evaluation/_likelihood.py:239-326.
+ *   cherry_fc_lengths_and_rates / cherry_fc_count_layout / cherry_fc_relayout_lg
+ *                              the text hand-off between the tree estimator and the counting stage
+ *                              (estimation_end_to_end/_cherry.py:279-336), done in memory with the
+ *                              values the files would carry.
+ *   cherry_ingest_* / cherry_fc_read_msas / cherry_fc_write_outputs / cherry_*_count_matrices /
+ *   cherry_write_labelled_matrix   (host threads) the text readers and writers of cherryml/io and of
+ *                              the two C++ programs, byte-identical formats.
  */
 #ifndef CHERRYML_B200_H
 #define CHERRYML_B200_H
