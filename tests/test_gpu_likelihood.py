@@ -159,3 +159,39 @@ def test_pfam_sized_family_against_oracle(tmp_path):
           f"GPU {t_gpu:.3f} s (host set-up included), numpy oracle {t_cpu:.1f} s, ll {ll:.4f}")
     assert abs(ll - ll_o) <= 1e-10 * abs(ll_o)
     np.testing.assert_allclose(lls, lls_o, rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("num_cats,ll_expected", [(1, -4649.6146), (2, -4397.8184), (4, -4337.8688), (20, -4307.0638)])
+def test_real_data_pair_site_medium_fasttree_constants(num_cats, ll_expected):
+    """The reference's Test_real_data_pair_site_medium (likelihood_test.py:996-1068): half of the sites
+    with the median site rate are coupled in pairs under the WAG x WAG product model (tree and rates
+    rescaled so that the coupled sites evolve at rate 1); the total must equal FastTree's single-site
+    log-likelihood to 4 decimals.  Exercises the 400-state kernel path on real data."""
+    from cherryml_b200.io import Tree, read_msa, read_site_rates, read_tree
+    from cherryml_b200.markov_chain import chain_product, compute_stationary_distribution
+    from tests._ll_cases import LL_DIR, rate_matrix
+
+    d = os.path.join(LL_DIR, "1a92")
+    tree = read_tree(os.path.join(d, f"tree_{num_cats}_cat.txt"))
+    msa = read_msa(os.path.join(d, "msa.txt"))
+    site_rates = read_site_rates(os.path.join(d, f"site_rates_{num_cats}_cat.txt"))
+    median = np.median(site_rates)
+    places = [i for i, r in enumerate(site_rates) if r == median]
+    np.random.seed(1)
+    np.random.shuffle(places)
+    cmap = np.eye(len(site_rates))
+    for i in range(len(places) // 4):
+        j, k = places[2 * i], places[2 * i + 1]
+        cmap[j, k] = cmap[k, j] = 1
+    scaled = Tree()
+    scaled.add_nodes(tree.nodes())
+    for u, v, length in tree.edges():
+        scaled.add_edge(u, v, length * median)
+    rates_scaled = [r / median for r in site_rates]
+    wag = rate_matrix("wag")
+    wag2 = chain_product(wag, wag)
+    ll, lls = dp_likelihood_computation(
+        tree=scaled, msa=msa, contact_map=cmap, site_rates=rates_scaled, amino_acids=AA,
+        pi_1=compute_stationary_distribution(wag), Q_1=wag, pi_2=compute_stationary_distribution(wag2), Q_2=wag2)
+    np.testing.assert_almost_equal(ll, ll_expected, decimal=4)
+    assert len(lls) == len(site_rates)

@@ -27,3 +27,37 @@ def test_matches_reference_function(i):
     # relative on 400 x 400 models; the north star's tolerance for fp64 log-likelihoods is 1e-6
     assert abs(ll - c["ll"]) <= 1e-7 * abs(c["ll"])
     np.testing.assert_allclose(lls, c["lls"], rtol=1e-6, atol=1e-9)
+
+
+def test_pair_site_model_on_real_data_fasttree_constant():
+    """The reference's Test_real_data_pair_site_medium (likelihood_test.py:996-1068) at 4 rate
+    categories: sites with the median rate coupled in pairs under WAG x WAG reproduce FastTree's
+    single-site log-likelihood."""
+    import os
+
+    from cherryml_b200.io import Tree, read_msa, read_site_rates, read_tree
+    from cherryml_b200.markov_chain import chain_product, compute_stationary_distribution
+    from tests._ll_cases import LL_DIR, rate_matrix
+
+    d = os.path.join(LL_DIR, "1a92")
+    tree = read_tree(os.path.join(d, "tree_4_cat.txt"))
+    msa = read_msa(os.path.join(d, "msa.txt"))
+    site_rates = read_site_rates(os.path.join(d, "site_rates_4_cat.txt"))
+    median = np.median(site_rates)
+    places = [i for i, r in enumerate(site_rates) if r == median]
+    np.random.seed(1)
+    np.random.shuffle(places)
+    cmap = np.eye(len(site_rates))
+    for i in range(len(places) // 4):
+        j, k = places[2 * i], places[2 * i + 1]
+        cmap[j, k] = cmap[k, j] = 1
+    assert cmap.sum() > len(site_rates)  # some sites are coupled
+    scaled = Tree()
+    scaled.add_nodes(tree.nodes())
+    for u, v, length in tree.edges():
+        scaled.add_edge(u, v, length * median)
+    wag = rate_matrix("wag")
+    wag2 = chain_product(wag, wag)
+    ll, _ = log_likelihood(scaled, msa, cmap, [r / median for r in site_rates], AA,
+                           compute_stationary_distribution(wag), wag, compute_stationary_distribution(wag2), wag2)
+    np.testing.assert_almost_equal(ll, -4337.8688, decimal=4)
