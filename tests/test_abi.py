@@ -58,3 +58,17 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libcherryml_b200.so")
     with pytest.raises(_lib.CherryError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under cherryml_b200/ may import it (or read /root/reference)."""
+    pkg = os.path.join(REPO, "cherryml_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if not fn.endswith(".py"):
+                continue
+            text = open(os.path.join(dirpath, fn)).read()
+            if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M) or "/root/reference" in text:
+                offenders.append(os.path.relpath(os.path.join(dirpath, fn), REPO))
+    assert offenders == []
