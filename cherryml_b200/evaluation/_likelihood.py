@@ -16,7 +16,7 @@ import torch
 from .. import _lib
 from ..caching import cached_parallel_computation
 from ..io import (Tree, read_contact_map, read_msa, read_probability_distribution, read_rate_matrix, read_site_rates,
-                  read_tree)
+                  read_tree, write_log_likelihood)
 from ..markov_chain import expm_batched
 
 _PAIR_EXPM_CHUNK = 128  # 400 x 400 exponentials per cherry_expm_batched call (bounds its workspace)
@@ -158,13 +158,6 @@ def dp_likelihood_computation(
     return sum(lls), lls
 
 
-def _write_log_likelihood(ll: float, lls: List[float], path: str) -> None:
-    # reference io/_log_likelihood.py:5-18
-    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
-    with open(path, "w") as f:
-        f.write(f"{ll}\n{len(lls)} sites\n" + " ".join(map(str, lls)))
-
-
 @cached_parallel_computation(
     parallel_arg="families",
     exclude_args=[
@@ -239,6 +232,6 @@ def compute_log_likelihoods(
             Q_2=Q_2_df.to_numpy() if Q_2_df is not None else None, reversible_2=reversible_2, device_2=device_2,
             output_profiling_path=os.path.join(output_likelihood_dir, family + ".profiling"),
         )
-        _write_log_likelihood(ll, lls, os.path.join(output_likelihood_dir, family + ".txt"))
+        write_log_likelihood((ll, lls), os.path.join(output_likelihood_dir, family + ".txt"))
     with open(os.path.join(output_likelihood_dir, "profiling.txt"), "w") as f:
         f.write(f"Total time: {time.time() - st}\n")

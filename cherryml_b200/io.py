@@ -538,6 +538,54 @@ def write_probability_distribution(
         f.write("state\tprob\n" + "".join(f"{s}\t{v!r}\n" for s, v in zip(states, p.tolist())))
 
 
+def write_log_likelihood(log_likelihood, log_likelihood_path: str) -> None:
+    """``(total, per-site values or None)`` -> total, then ``<n> sites`` and the values
+    (reference io/_log_likelihood.py:5-18)."""
+    _makedirs_for(log_likelihood_path)
+    ll, lls = log_likelihood
+    res = f"{ll}\n"
+    if lls is not None:
+        res += f"{len(lls)} sites\n" + " ".join(map(str, lls))
+    with open(log_likelihood_path, "w") as f:
+        f.write(res)
+
+
+def read_log_likelihood(log_likelihood_path: str):
+    """-> ``(total, per-site values or None)`` (reference io/_log_likelihood.py:21-47)."""
+    with open(log_likelihood_path) as f:
+        lines = f.read().strip().split("\n")
+    ll = float(lines[0])
+    if len(lines) == 1:
+        return ll, None
+    try:
+        num_sites, s = lines[1].split(" ")
+        if s != "sites":
+            raise Exception
+        num_sites = float(num_sites)
+    except Exception:
+        raise Exception(
+            f"Log likelihood file at:{log_likelihood_path} should have second line '[num_sites] sites', "
+            f"but had second line: {lines[1]} instead."
+        )
+    lls = list(map(float, lines[2].split(" "))) if len(lines) > 2 and lines[2] else []
+    if len(lls) != num_sites:
+        raise Exception(
+            f"Log likelihood file at:{log_likelihood_path} should have {num_sites} values in line 3,"
+            f"but had {len(lls)} values instead."
+        )
+    return ll, lls
+
+
+def read_computed_cherries_from_file(file_path: str):
+    """FastCherries' raw output (name, name, distance per cherry) -> ``(cherries, distances)``
+    (reference io/_rate_matrix.py:101-119)."""
+    with open(file_path) as f:
+        lines = [ln.strip() for ln in f.readlines()]
+    cherries = [(lines[i], lines[i + 1]) for i in range(0, len(lines) - 2, 3)]
+    distances = [float(lines[i + 2]) for i in range(0, len(lines) - 2, 3)]
+    return cherries, distances
+
+
 def read_sites_subset(sites_subset_path: str) -> List[int]:
     """``<n> sites`` then n space-separated site indices (reference io/_sites_subset.py:5-32)."""
     with open(sites_subset_path) as f:

@@ -40,3 +40,16 @@ def test_subset_stage_restricts_msa_and_rates(tmp_path):
     assert read_msa(os.path.join(out["output_msa_dir"], "f.txt")) == {"a": "DR", "b": "HE"}
     assert read_site_rates(os.path.join(out["output_site_rates_dir"], "f.txt")) == [2.0, 1.0]
     assert os.path.exists(os.path.join(out["output_msa_dir"], "f.success"))
+
+
+def test_log_likelihood_and_cherries_files(tmp_path):
+    from cherryml_b200.io import read_computed_cherries_from_file, read_log_likelihood, write_log_likelihood
+
+    p = str(tmp_path / "ll" / "f.txt")
+    write_log_likelihood((-12.5, [-4.25, -8.25]), p)
+    assert open(p).read() == "-12.5\n2 sites\n-4.25 -8.25"
+    assert read_log_likelihood(p) == (-12.5, [-4.25, -8.25])
+    write_log_likelihood((0.0, None), p)
+    assert read_log_likelihood(p) == (0.0, None)
+    (tmp_path / "c.txt").write_text("a\nb\n0.12500000000000000\nc\nd\n2.00000000000000000\n")
+    assert read_computed_cherries_from_file(str(tmp_path / "c.txt")) == ([("a", "b"), ("c", "d")], [0.125, 2.0])
