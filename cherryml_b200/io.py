@@ -586,6 +586,120 @@ def read_computed_cherries_from_file(file_path: str):
     return cherries, distances
 
 
+def get_msa_num_sites(msa_path: str) -> int:
+    """Length of the first sequence line, without reading the rest (reference io/_msa.py:5-14)."""
+    with open(msa_path) as f:
+        f.readline()
+        line = f.readline()
+    if line == "":
+        raise Exception("We shouldn't be here!")
+    return len(line.strip())
+
+
+def get_msa_num_sequences(msa_path: str) -> int:
+    """Reference io/_msa.py:41-48."""
+    return len(read_msa(msa_path))
+
+
+def get_msa_num_residues(msa_path: str, exclude_gaps: bool) -> int:
+    """Cells of the alignment, optionally without the gap characters ``. - _`` (reference io/_msa.py:17-38)."""
+    seqs = list(read_msa(msa_path).values())
+    if not exclude_gaps:
+        return len(seqs) * len(seqs[0])
+    return sum(len(q) - q.count(".") - q.count("-") - q.count("_") for q in seqs)
+
+
+TransitionsType = List[Tuple[str, str, float]]
+
+
+def _counted_lines(path: str, what: str) -> List[str]:
+    """Body of a ``<n> transitions`` file, after checking the header against the line count."""
+    with open(path) as f:
+        lines = f.read().strip().split("\n")
+    tokens = lines[0].split(" ")
+    if len(tokens) != 2 or tokens[1] != "transitions":
+        raise ValueError(f"{what} file at '{path}' should start with '[NUM_TRANSITIONS] transitions'.")
+    if len(lines) - 1 != int(tokens[0]):
+        raise ValueError(f"Expected {int(tokens[0])} transitions at '{path}', but found only {len(lines) - 1}.")
+    return lines[1:]
+
+
+def read_transitions(transitions_path: str) -> TransitionsType:
+    """``<n> transitions`` then ``x y t`` per line (reference io/_transitions.py:7-36)."""
+    res = []
+    for line in _counted_lines(transitions_path, "Transitions"):
+        x, y, t = line.split(" ")
+        res.append((x, y, float(t)))
+    return res
+
+
+def write_transitions(transitions: TransitionsType, transitions_path: str) -> None:
+    """Reference io/_transitions.py:39-52; times are written with Python's ``str``."""
+    _makedirs_for(transitions_path)
+    with open(transitions_path, "w") as f:
+        f.write(f"{len(transitions)} transitions\n" + "\n".join(f"{x} {y} {t}" for x, y, t in transitions) + "\n")
+
+
+def read_transitions_log_likelihood(transitions_log_likelihood_path: str) -> List[float]:
+    """``<n> transitions`` then one log-likelihood per line (reference io/_transitions_log_likelihood.py:7-43)."""
+    return [float(line) for line in _counted_lines(transitions_log_likelihood_path, "Transitions log likelihood")]
+
+
+def write_transitions_log_likelihood(transitions_log_likelihood: Sequence[float], transitions_log_likelihood_path: str) -> None:
+    """Reference io/_transitions_log_likelihood.py:46-62."""
+    _makedirs_for(transitions_log_likelihood_path)
+    with open(transitions_log_likelihood_path, "w") as f:
+        f.write(
+            f"{len(transitions_log_likelihood)} transitions\n"
+            + "\n".join(str(ll) for ll in transitions_log_likelihood)
+            + "\n"
+        )
+
+
+def read_pickle(pickle_path: str):
+    """Reference io/_pickle.py:5-9."""
+    import pickle
+
+    with open(pickle_path, "rb") as f:
+        return pickle.load(f)
+
+
+def write_pickle(obj, output_path: str) -> None:
+    """Reference io/_pickle.py:12-18."""
+    import pickle
+
+    with open(output_path, "wb") as f:
+        pickle.dump(obj, f)
+
+
+def read_transitions_log_likelihood_per_site(transitions_log_likelihood_per_site_path: str) -> List[List[float]]:
+    """A pickled list of per-site log-likelihood lists (reference io/_transitions_log_likelihood_per_site.py:6-15)."""
+    res = read_pickle(transitions_log_likelihood_per_site_path)
+    if len(res) == 0:
+        raise Exception(
+            f"The transitions log likelihood file at {transitions_log_likelihood_per_site_path} is empty"
+        )
+    return res
+
+
+def write_transitions_log_likelihood_per_site(
+    transitions_log_likelihood_per_site: List[List[float]], transitions_log_likelihood_per_site_path: str
+) -> None:
+    """Reference io/_transitions_log_likelihood_per_site.py:17-31."""
+    _makedirs_for(transitions_log_likelihood_per_site_path)
+    write_pickle(transitions_log_likelihood_per_site, transitions_log_likelihood_per_site_path)
+
+
+def read_str(s_path: str) -> str:
+    with open(s_path) as f:
+        return f.read()
+
+
+def write_str(s: str, s_path: str) -> None:
+    with open(s_path, "w") as f:
+        f.write(s)
+
+
 def read_sites_subset(sites_subset_path: str) -> List[int]:
     """``<n> sites`` then n space-separated site indices (reference io/_sites_subset.py:5-32)."""
     with open(sites_subset_path) as f:

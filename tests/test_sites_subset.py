@@ -53,3 +53,42 @@ def test_log_likelihood_and_cherries_files(tmp_path):
     assert read_log_likelihood(p) == (0.0, None)
     (tmp_path / "c.txt").write_text("a\nb\n0.12500000000000000\nc\nd\n2.00000000000000000\n")
     assert read_computed_cherries_from_file(str(tmp_path / "c.txt")) == ([("a", "b"), ("c", "d")], [0.125, 2.0])
+
+
+def test_transition_files_and_msa_sizes(tmp_path):
+    import pytest
+
+    from cherryml_b200 import io
+
+    msa = {"a": "AC-D", "b": "A_.D", "c": "ACDE"}
+    p = str(tmp_path / "m" / "fam.txt")
+    io.write_msa(msa, p)
+    assert io.get_msa_num_sites(p) == 4
+    assert io.get_msa_num_sequences(p) == 3
+    assert io.get_msa_num_residues(p, exclude_gaps=False) == 12
+    assert io.get_msa_num_residues(p, exclude_gaps=True) == 9
+
+    tr = [("A", "C", 0.5), ("AC", "DE", 1e-05), ("S", "S", 3.0)]
+    p = str(tmp_path / "t" / "tr.txt")
+    io.write_transitions(tr, p)
+    assert open(p).read() == "3 transitions\nA C 0.5\nAC DE 1e-05\nS S 3.0\n"
+    assert io.read_transitions(p) == tr
+    with open(p, "w") as f:
+        f.write("2 transitions\nA C 0.5\n")
+    with pytest.raises(ValueError, match="Expected 2 transitions"):
+        io.read_transitions(p)
+    with open(p, "w") as f:
+        f.write("1 transition\nA C 0.5\n")
+    with pytest.raises(ValueError, match="should start with"):
+        io.read_transitions(p)
+
+    lls = [-1.25, -0.1, -3.0e-07]
+    p = str(tmp_path / "l" / "ll.txt")
+    io.write_transitions_log_likelihood(lls, p)
+    assert io.read_transitions_log_likelihood(p) == lls
+    per_site = [[-1.0, -2.0], [-0.5]]
+    p = str(tmp_path / "ps" / "ll.pkl")
+    io.write_transitions_log_likelihood_per_site(per_site, p)
+    assert io.read_transitions_log_likelihood_per_site(p) == per_site
+    io.write_str("x y", str(tmp_path / "s.txt"))
+    assert io.read_str(str(tmp_path / "s.txt")) == "x y"
