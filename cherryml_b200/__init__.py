@@ -15,4 +15,7 @@ from ._public_api import (  # noqa: F401
     coevolution_end_to_end_with_cherryml_optimizer,
     lg_end_to_end_with_cherryml_optimizer,
 )
-from .siterm import learn_site_specific_rate_matrices  # noqa: F401,E402
+from .evaluation import compute_log_likelihoods  # noqa: F401
+from .phylogeny_estimation import fast_cherries  # noqa: F401
+from .siterm import learn_site_specific_rate_matrices  # noqa: F401
+from .types import PhylogenyEstimatorType  # noqa: F401
