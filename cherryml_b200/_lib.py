@@ -92,6 +92,7 @@ _SIGNATURES = {
     "cherry_ingest_free": (None, [_P]),
     "cherry_tree_ll_units_per_block": (c_int, [c_int, c_int]),
     "cherry_tree_ll_scratch_bytes": (ctypes.c_size_t, [c_int, c_int, c_int, c_int]),
+    "cherry_tree_ll_transpose": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "cherry_tree_log_likelihood": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P,
                                            ctypes.c_size_t, _P, _P]),
     "cherry_fc_read_msas": (c_int, [_P, c_int, _P, c_int, c_int, c_int, _P]),

@@ -51,11 +51,20 @@ def _tree_arrays(tree: Tree):
 
 
 def _matrices(Q: np.ndarray, exponents: np.ndarray, device) -> Tuple[torch.Tensor, np.ndarray]:
-    """One expm per distinct exponent -> (P [n_distinct, S, S] on the device, index of every exponent)."""
+    """One expm per distinct exponent -> (the TRANSPOSED matrices [n_distinct, S, S] on the device, as the
+    pruning kernel reads them, and the index of every exponent)."""
+    lib = _lib.load()
     uniq, inverse = np.unique(exponents, return_inverse=True)
-    chunk = _PAIR_EXPM_CHUNK if Q.shape[0] > 32 else 1 << 16
-    parts = [expm_batched(Q, uniq[i: i + chunk], device) for i in range(0, len(uniq), chunk)]
-    return (torch.cat(parts) if len(parts) > 1 else parts[0]), inverse.astype(np.int32)
+    S = Q.shape[0]
+    chunk = _PAIR_EXPM_CHUNK if S > 32 else 1 << 16
+    dev = torch.device(device)
+    out = torch.empty((len(uniq), S, S), dtype=torch.float64, device=dev)
+    for i in range(0, len(uniq), chunk):
+        part = expm_batched(Q, uniq[i: i + chunk], dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.cherry_tree_ll_transpose(_lib.ptr(part), part.shape[0], S, _lib.ptr(out[i: i + chunk]),
+                                                    _lib.current_stream_ptr()), "cherry_tree_ll_transpose")
+    return out, inverse.astype(np.int32)
 
 
 def _prune(nodes, max_depth, p_index, n_cats, P, obs, unit_cat, pi, S, c, device) -> np.ndarray:

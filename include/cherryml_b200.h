@@ -443,11 +443,15 @@ typedef struct cherry_ll_node {
 int cherry_tree_ll_units_per_block(int S, int c);
 size_t cherry_tree_ll_scratch_bytes(int S, int c, int n_units, int max_depth);
 
+/* Pt[m][k][s] = P[m][s][k] for n_matrices fp64 [Su][Su] matrices (device pointers, Pt != P): the
+ * layout cherry_tree_log_likelihood reads, made from cherry_expm_batched's output. */
+int cherry_tree_ll_transpose(const double* P, int n_matrices, int Su, double* Pt, void* stream);
+
 /* ll_out[u] = log-likelihood of unit u on the tree.  A unit is one site (c = 1, S states) or a
  * pair of contacting sites (c = 2, S*S states, state = S*i + j).
- * p_index[i * n_cats + k]: which matrix of P (fp64 [n][Su][Su], row-stochastic, = expm(branch
- * length * rate_k * Q)) belongs to the edge above node i for rate category k (ignored for the
- * root); unit_cat[u]: the unit's rate category; obs: uint8 [n_leaves][n_units][c] residues
+ * p_index[i * n_cats + k]: which matrix of P belongs to the edge above node i for rate category
+ * k (ignored for the root); P: fp64 [n][Su][Su], the TRANSPOSES of the row-stochastic matrices
+ * expm(branch length * rate_k * Q), i.e. P[m][k][s] = Pr(s -> k) (cherry_tree_ll_transpose); unit_cat[u]: the unit's rate category; obs: uint8 [n_leaves][n_units][c] residues
  * (S = not in the alphabet: every state is compatible); pi: [Su] root distribution.
  * Replaces the pruning loops of dp_likelihood_computation, evaluation/_likelihood.py:239-326
  * (child messages are accumulated in the same order; a pair's value is split over its two
