@@ -23,31 +23,51 @@ _PAIR_EXPM_CHUNK = 128  # 400 x 400 exponentials per cherry_expm_batched call (b
 
 
 def _tree_arrays(tree: Tree):
-    """Post-order node table for the kernel + per node branch length."""
-    order = tree.postorder_traversal()
-    root = tree.root()
-    depth = {root: 0}
-    for v in tree.preorder_traversal():
-        for c, _ in tree.children(v):
-            depth[c] = depth[v] + 1
-    nodes = np.zeros(len(order), dtype=_lib.LL_NODE_DTYPE)
-    lengths = np.zeros(len(order))
+    """Post-order node table for the kernel + per node branch length (one iterative walk; the
+    order is ``tree.postorder_traversal()``'s: children in edge order, then their parent)."""
+    kids_of = {v: tree.children(v) for v in tree.nodes()}
+    depths: List[int] = []
+    flags: List[int] = []
+    obs_rows: List[int] = []
+    lengths: List[float] = []
     leaves: List[str] = []
-    for i, v in enumerate(order):
-        flags = 0
-        if tree.is_leaf(v):
-            flags |= 1
-            obs_row = len(leaves)
-            leaves.append(v)
+    stack = [(tree.root(), 0, 0.0, 0, False)]
+    while stack:
+        v, d, length, first, expanded = stack.pop()
+        kids = kids_of[v]
+        if kids and not expanded:
+            stack.append((v, d, length, first, True))
+            for j in range(len(kids) - 1, -1, -1):
+                stack.append((kids[j][0], d + 1, kids[j][1], 2 if j == 0 else 0, False))
+            continue
+        depths.append(d)
+        lengths.append(length)
+        if kids:
+            flags.append(first)
+            obs_rows.append(-1)
         else:
-            obs_row = -1
-        if v != root:
-            p, length = tree.parent(v)
-            lengths[i] = length
-            if tree.children(p)[0][0] == v:
-                flags |= 2
-        nodes[i] = (depth[v], flags, obs_row, 0)
-    return nodes, lengths, leaves, max(depth.values())
+            flags.append(first | 1)
+            obs_rows.append(len(leaves))
+            leaves.append(v)
+    nodes = np.zeros(len(depths), dtype=_lib.LL_NODE_DTYPE)
+    nodes["depth"] = depths
+    nodes["flags"] = flags
+    nodes["obs_row"] = obs_rows
+    return nodes, np.array(lengths, dtype=np.float64), leaves, max(depths)
+
+
+def _encode_leaves(msa: Dict[str, str], leaves: List[str], amino_acids: List[str]) -> np.ndarray:
+    """uint8 [n_leaves, n_sites]: index in ``amino_acids``, S for any other character."""
+    S = len(amino_acids)
+    lut = np.full(256, S, dtype=np.uint8)
+    for i, ch in enumerate(amino_acids):
+        lut[ord(ch)] = i
+    n_sites = len(msa[leaves[0]])
+    seqs = [msa[v] for v in leaves]
+    if any(len(q) != n_sites for q in seqs):
+        raise ValueError("the sequences of the MSA have different lengths")
+    flat = np.frombuffer("".join(seqs).encode("latin-1"), dtype=np.uint8)
+    return lut[flat].reshape(len(leaves), n_sites)
 
 
 def _matrices(Q: np.ndarray, exponents: np.ndarray, device) -> Tuple[torch.Tensor, np.ndarray]:
@@ -130,10 +150,7 @@ def dp_likelihood_computation(
     device = device_1 if str(device_1).startswith("cuda") else "cuda"
 
     nodes, lengths, leaves, max_depth = _tree_arrays(tree)
-    lut = np.full(256, S, dtype=np.uint8)
-    for i, ch in enumerate(amino_acids):
-        lut[ord(ch)] = i
-    enc = np.stack([lut[np.frombuffer(msa[v].encode("latin-1"), dtype=np.uint8)] for v in leaves])
+    enc = _encode_leaves(msa, leaves, amino_acids)
     lls = [0] * num_sites
     t_expm = t_dp = 0.0
     if independent:
