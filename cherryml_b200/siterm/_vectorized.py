@@ -29,16 +29,29 @@ logger = logging.getLogger(__name__)
 def solve_stationary_dist_fast(rate_matrices: np.ndarray) -> np.ndarray:
     """Stationary distributions by power iteration, as the reference initialises them
     (``_cherryml_vectorized.py:70-104``): fp32 ``matrix_exp`` of the diagonal-normalised
-    matrices, then 100 squarings with row renormalisation.  Host-side, one-off."""
+    matrices, then 100 squarings with row renormalisation.  Host-side, one-off.
+
+    Same arithmetic per matrix, less of it: matrices whose fp32 normalised form is bit-identical
+    (``rate_l * Q0`` for every site of a family collapses to a handful) are iterated once, and the
+    loop stops when a squaring leaves every matrix bit-identical (the remaining squarings would
+    reproduce it)."""
     diag_avg = np.mean(np.diagonal(rate_matrices, axis1=1, axis2=2), axis=1)
     normalized = rate_matrices * (-1.0 / diag_avg)[:, None, None]
-    exp_matrices = torch.matrix_exp(torch.tensor(normalized, dtype=torch.float32)).numpy()
+    L, N, _ = normalized.shape
+    as_f32 = np.ascontiguousarray(normalized.astype(np.float32).reshape(L, N * N))
+    _, first, inverse = np.unique(as_f32.view(np.dtype((np.void, N * N * 4))).reshape(L), return_index=True,
+                                  return_inverse=True)
+    exp_matrices = torch.matrix_exp(torch.from_numpy(as_f32[first].reshape(-1, N, N))).numpy()
     for _ in range(100):
-        exp_matrices = exp_matrices @ exp_matrices
-        exp_matrices /= exp_matrices.sum(axis=2, keepdims=True)
+        squared = exp_matrices @ exp_matrices
+        squared /= squared.sum(axis=2, keepdims=True)
+        done = np.array_equal(squared, exp_matrices)
+        exp_matrices = squared
+        if done:
+            break
     pi = exp_matrices[:, 0, :]
     pi /= pi.sum(axis=1, keepdims=True)
-    return pi
+    return pi[inverse.reshape(-1)]
 
 
 def _theta_from_initialization(initialization: np.ndarray) -> np.ndarray:
