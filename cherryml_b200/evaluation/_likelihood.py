@@ -193,6 +193,7 @@ def dp_likelihood_computation(
         "use_cpp_implementation",
         "OMP_NUM_THREADS",
         "OPENBLAS_NUM_THREADS",
+        "process_group",
     ],
     output_dirs=["output_likelihood_dir"],
     write_extra_log_files=True,
@@ -217,11 +218,38 @@ def compute_log_likelihoods(
     use_cpp_implementation: bool = False,
     OMP_NUM_THREADS: Optional[int] = 1,
     OPENBLAS_NUM_THREADS: Optional[int] = 1,
+    process_group=None,
 ) -> None:
     """Per family ``<output_likelihood_dir>/<family>.txt`` (total, then the per-site values) and
-    ``<family>.profiling``.  Model validation as in the reference (:377-416)."""
+    ``<family>.profiling``.  Model validation as in the reference (:377-416).
+
+    ``process_group`` (a torch.distributed group, one process per GPU): families are independent,
+    so rank r evaluates ``families[r::world]`` -- the striping of the reference's worker processes
+    (``get_process_args``, :565-575) -- and a barrier makes every file exist before any rank
+    returns.  No data-path collective."""
     if use_cpp_implementation:
         raise NotImplementedError
+    rank, world = 0, 1
+    if process_group is not None:
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(process_group), dist.get_world_size(process_group)
+        try:
+            _compute_log_likelihoods_local(
+                tree_dir, msa_dir, site_rates_dir, contact_map_dir, families[rank::world], amino_acids, pi_1_path,
+                Q_1_path, reversible_1, device_1, pi_2_path, Q_2_path, reversible_2, device_2, output_likelihood_dir,
+                write_total=rank == 0)
+        finally:
+            dist.barrier(process_group)
+        return
+    _compute_log_likelihoods_local(
+        tree_dir, msa_dir, site_rates_dir, contact_map_dir, families, amino_acids, pi_1_path, Q_1_path, reversible_1,
+        device_1, pi_2_path, Q_2_path, reversible_2, device_2, output_likelihood_dir, write_total=True)
+
+
+def _compute_log_likelihoods_local(tree_dir, msa_dir, site_rates_dir, contact_map_dir, families, amino_acids,
+                                   pi_1_path, Q_1_path, reversible_1, device_1, pi_2_path, Q_2_path, reversible_2,
+                                   device_2, output_likelihood_dir, write_total: bool) -> None:
     os.makedirs(output_likelihood_dir, exist_ok=True)
     st = time.time()
     pi_1_df = read_probability_distribution(pi_1_path)
@@ -259,5 +287,6 @@ def compute_log_likelihoods(
             output_profiling_path=os.path.join(output_likelihood_dir, family + ".profiling"),
         )
         write_log_likelihood((ll, lls), os.path.join(output_likelihood_dir, family + ".txt"))
-    with open(os.path.join(output_likelihood_dir, "profiling.txt"), "w") as f:
-        f.write(f"Total time: {time.time() - st}\n")
+    if write_total:
+        with open(os.path.join(output_likelihood_dir, "profiling.txt"), "w") as f:
+            f.write(f"Total time: {time.time() - st}\n")

@@ -210,3 +210,63 @@ def test_two_rank_siterm_fit_shards_sites(tmp_path):
         assert np.array_equal(g["res"], counts.sum(axis=1))
         assert np.array_equal(g["per_site"], np.tile(counts.sum(axis=(1, 2, 3)), (2, 1)))
         assert g["mine"][0] == n_mine
+
+
+def _ll_worker(rank, world, port, root, families):
+    """Two ranks run the sharded likelihood stage with the per-family device function replaced
+    by a deterministic stand-in (this test is about the striping, the files and the barrier)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cherryml_b200.evaluation import _likelihood as ev
+    from cherryml_b200.markov_chain import get_lg_path
+    from cherryml_b200.utils import amino_acids
+
+    seen = []
+
+    def fake_dp(tree, msa, contact_map, site_rates, **kw):
+        seen.append(sorted(msa.keys())[0])
+        lls = [-(rank + 1.0)] * len(site_rates)
+        return sum(lls), lls
+
+    ev.dp_likelihood_computation = fake_dp
+    out = os.path.join(root, "ll")
+    ev.compute_log_likelihoods(
+        tree_dir=os.path.join(root, "tree"), msa_dir=os.path.join(root, "msa"),
+        site_rates_dir=os.path.join(root, "rates"), contact_map_dir=None, families=families,
+        amino_acids=amino_acids, pi_1_path=os.path.join(root, "pi.txt"), Q_1_path=get_lg_path(), reversible_1=True,
+        device_1="cuda", pi_2_path=None, Q_2_path=None, reversible_2=None, device_2=None,
+        output_likelihood_dir=out, num_processes=1, process_group=dist.group.WORLD)
+    ok = all(os.path.exists(os.path.join(out, f + ".txt")) for f in families)
+    with open(os.path.join(root, f"ll_seen_{rank}.txt"), "w") as fh:
+        fh.write(("ok" if ok else "missing") + "\n" + " ".join(seen))
+    dist.destroy_process_group()
+
+
+def test_two_rank_likelihood_stage_stripes_families(tmp_path):
+    import numpy as np
+
+    from cherryml_b200 import io
+    from cherryml_b200.markov_chain import compute_stationary_distribution, get_lg_path
+    from cherryml_b200.utils import amino_acids
+
+    families = [f"fam{i}" for i in range(5)]
+    for f in families:
+        tree = io.Tree()
+        tree.add_nodes(["r", f + "_a", f + "_b"])
+        tree.add_edge("r", f + "_a", 0.1)
+        tree.add_edge("r", f + "_b", 0.2)
+        io.write_tree(tree, str(tmp_path / "tree" / (f + ".txt")))
+        io.write_msa({f + "_a": "ACD", f + "_b": "ACE"}, str(tmp_path / "msa" / (f + ".txt")))
+        io.write_site_rates([1.0, 0.5, 2.0], str(tmp_path / "rates" / (f + ".txt")))
+    Q = io.read_rate_matrix(get_lg_path()).to_numpy(dtype=np.float64)
+    io.write_probability_distribution(compute_stationary_distribution(Q), amino_acids, str(tmp_path / "pi.txt"))
+    mp.spawn(_ll_worker, args=(2, _free_port(), str(tmp_path), families), nprocs=2, join=True)
+    for rank in range(2):
+        status, fams = open(tmp_path / f"ll_seen_{rank}.txt").read().split("\n")
+        assert status == "ok"
+        assert fams.split() == [f + "_a" for f in families[rank::2]]
+    for k, f in enumerate(families):
+        ll, lls = io.read_log_likelihood(str(tmp_path / "ll" / (f + ".txt")))
+        assert lls == [-(k % 2 + 1.0)] * 3 and ll == 3 * lls[0]
+    assert os.path.exists(tmp_path / "ll" / "profiling.txt")

@@ -107,3 +107,49 @@ def test_leaf_encoding():
         assert row.tolist() == [aa.get(ch, 20) for ch in msa[name]]
     with pytest.raises(ValueError, match="different lengths"):
         _encode_leaves({"a": "AC", "b": "A"}, ["a", "b"], amino_acids)
+
+
+def test_likelihood_stage_files_with_the_device_function_replaced(tmp_path, monkeypatch):
+    """The stage's own work (validation, per-family files, caching layout) around a stand-in for
+    dp_likelihood_computation."""
+    import os
+
+    import pytest
+
+    from cherryml_b200 import io
+    from cherryml_b200.evaluation import _likelihood as ev
+    from cherryml_b200.markov_chain import compute_stationary_distribution, get_lg_path
+
+    families = ["f1", "f0"]
+    for f in families:
+        tree = io.Tree()
+        tree.add_nodes(["r", "a", "b"])
+        tree.add_edge("r", "a", 0.1)
+        tree.add_edge("r", "b", 0.2)
+        io.write_tree(tree, str(tmp_path / "tree" / (f + ".txt")))
+        io.write_msa({"a": "ACD", "b": "ACE"}, str(tmp_path / "msa" / (f + ".txt")))
+        io.write_site_rates([1.0, 0.5, 2.0], str(tmp_path / "rates" / (f + ".txt")))
+    Q = io.read_rate_matrix(get_lg_path()).to_numpy(dtype=np.float64)
+    io.write_probability_distribution(compute_stationary_distribution(Q), amino_acids, str(tmp_path / "pi.txt"))
+    calls = []
+
+    def fake_dp(tree, msa, contact_map, site_rates, output_profiling_path=None, **kw):
+        calls.append((sorted(msa), contact_map, list(site_rates), kw["device_1"]))
+        return -6.0, [-1.0, -2.0, -3.0]
+
+    monkeypatch.setattr(ev, "dp_likelihood_computation", fake_dp)
+    kw = dict(tree_dir=str(tmp_path / "tree"), msa_dir=str(tmp_path / "msa"), site_rates_dir=str(tmp_path / "rates"),
+              contact_map_dir=None, families=families, amino_acids=amino_acids, pi_1_path=str(tmp_path / "pi.txt"),
+              Q_1_path=get_lg_path(), reversible_1=True, device_1="cuda", pi_2_path=None, Q_2_path=None,
+              reversible_2=None, device_2=None, num_processes=1)
+    out = str(tmp_path / "ll")
+    ev.compute_log_likelihoods(output_likelihood_dir=out, **kw)
+    assert len(calls) == 2 and calls[0] == (["a", "b"], None, [1.0, 0.5, 2.0], "cuda")
+    for f in families:
+        assert io.read_log_likelihood(os.path.join(out, f + ".txt")) == (-6.0, [-1.0, -2.0, -3.0])
+    assert os.path.exists(os.path.join(out, "profiling.txt"))
+    # a model whose states are not the requested alphabet is rejected before any family is touched
+    with pytest.raises(Exception, match="expected amino acids"):
+        ev.compute_log_likelihoods(output_likelihood_dir=str(tmp_path / "ll2"), **{**kw, "amino_acids": amino_acids[::-1]})
+    with pytest.raises(NotImplementedError):
+        ev.compute_log_likelihoods(output_likelihood_dir=str(tmp_path / "ll3"), use_cpp_implementation=True, **kw)
