@@ -86,6 +86,25 @@ def _caching_dir(func, unhashed: List[str], kwargs, cache_dir: str, use_hash: Op
     return os.path.join(cache_dir, func.__name__, *[f"{k}_{v}" for k, v in items])
 
 
+def _call_caching_dir(func, exclude_args, exclude_args_if_default, output_dirs, parallel_arg, kwargs,
+                      cache_dir: str, use_hash: Optional[bool] = None):
+    """Cache directory of one call of a decorated function and the arguments left out of its key:
+    the decorator's ``exclude_args``, the parallel argument, the output directories, and every
+    ``exclude_args_if_default`` argument that has its default value (reference
+    ``_cached_computation.py:37-82``, ``_cached_parallel_computation.py:45-91``)."""
+    params = signature(func).parameters
+    unhashed = list(exclude_args) + ([parallel_arg] if parallel_arg is not None else []) + list(output_dirs)
+    bound = dict(kwargs)
+    for od in output_dirs:
+        bound[od] = None
+    binding = signature(func).bind(**bound)
+    binding.apply_defaults()
+    for arg in exclude_args_if_default:
+        if binding.arguments[arg] == params[arg].default:
+            unhashed.append(arg)
+    return _caching_dir(func, unhashed, bound, cache_dir, use_hash), unhashed
+
+
 def _make_read_only(path: str) -> None:
     os.chmod(path, stat.S_IRUSR | stat.S_IRGRP | stat.S_IROTH)
 
@@ -137,15 +156,10 @@ def cached_computation(
             cache_dir = get_cache_dir()
             if cache_dir is None:
                 return func(**kwargs)
-            unhashed = list(exclude_args) + list(output_dirs)
             for od in output_dirs:  # output dirs may be required parameters: bind them as None
                 kwargs.setdefault(od, None)
-            binding = signature(func).bind(**kwargs)
-            binding.apply_defaults()
-            for arg in exclude_args_if_default:
-                if binding.arguments[arg] == params[arg].default:
-                    unhashed.append(arg)
-            func_dir = _caching_dir(func, unhashed, kwargs, cache_dir)
+            func_dir, unhashed = _call_caching_dir(func, exclude_args, exclude_args_if_default, output_dirs, None,
+                                                   kwargs, cache_dir)
             for od in output_dirs:
                 if kwargs.get(od) is None:
                     kwargs[od] = os.path.join(func_dir, od)
@@ -191,6 +205,8 @@ def cached_computation(
                         f.write("SUCCESS\n")
             return res
 
+        wrapper.caching_dir = lambda cache_dir, use_hash=None, **kwargs: _call_caching_dir(
+            func, exclude_args, exclude_args_if_default, output_dirs, None, kwargs, cache_dir, use_hash)[0]
         return wrapper
 
     return decorator
@@ -234,16 +250,9 @@ def cached_parallel_computation(
             cache_dir = get_cache_dir()
             if cache_dir is None:
                 return func(**kwargs)
-            unhashed = list(exclude_args) + [parallel_arg] + list(output_dirs)
             given_dirs = {od: kwargs.get(od) for od in output_dirs}
-            for od in output_dirs:
-                kwargs[od] = None
-            binding = signature(func).bind(**kwargs)
-            binding.apply_defaults()
-            for arg in exclude_args_if_default:
-                if binding.arguments[arg] == params[arg].default:
-                    unhashed.append(arg)
-            func_dir = _caching_dir(func, unhashed, kwargs, cache_dir)
+            func_dir, unhashed = _call_caching_dir(func, exclude_args, exclude_args_if_default, output_dirs,
+                                                   parallel_arg, kwargs, cache_dir)
             for od in output_dirs:
                 kwargs[od] = given_dirs[od] if given_dirs[od] is not None else os.path.join(func_dir, od)
             res = {od: kwargs[od] for od in output_dirs}
@@ -297,6 +306,8 @@ def cached_parallel_computation(
                             f.write("SUCCESS\n")
             return res
 
+        wrapper.caching_dir = lambda cache_dir, use_hash=None, **kwargs: _call_caching_dir(
+            func, exclude_args, exclude_args_if_default, output_dirs, parallel_arg, kwargs, cache_dir, use_hash)[0]
         return wrapper
 
     return decorator
