@@ -1,0 +1,43 @@
+"""Every text format of cherryml.io: this package's writers produce the bytes the UNMODIFIED
+reference's writers produce for the same objects (tests/golden/io, made by make_golden_io.py),
+and its readers give the objects back."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from _io_cases import AA, make_tree, objects, write  # noqa: E402
+
+from cherryml_b200 import io  # noqa: E402
+
+GOLD = os.path.join(HERE, "golden", "io")
+
+
+@pytest.mark.parametrize("name", sorted(objects()))
+def test_writer_bytes_equal_the_reference(name, tmp_path):
+    path = str(tmp_path / "sub" / name)
+    write(io, name, path)
+    assert open(path, "rb").read() == open(os.path.join(GOLD, name), "rb").read()
+
+
+def test_readers_give_the_objects_back():
+    o = {k: v[1] for k, v in objects().items()}
+    q = io.read_rate_matrix(os.path.join(GOLD, "rate_matrix.txt"))
+    assert list(q.index) == AA and list(q.columns) == AA and np.array_equal(q.to_numpy(), o["rate_matrix.txt"][0])
+    pi = io.read_probability_distribution(os.path.join(GOLD, "pi.txt"))
+    assert list(pi.index) == AA and np.array_equal(pi.to_numpy().reshape(-1), o["pi.txt"][0])
+    assert io.read_site_rates(os.path.join(GOLD, "site_rates.txt")) == [float(x) for x in o["site_rates.txt"][0]]
+    assert np.array_equal(io.read_contact_map(os.path.join(GOLD, "contact_map.txt")), o["contact_map.txt"][0])
+    assert io.read_msa(os.path.join(GOLD, "msa.txt")) == o["msa.txt"][0]
+    assert io.read_sites_subset(os.path.join(GOLD, "sites_subset.txt")) == o["sites_subset.txt"][0]
+    assert io.read_log_likelihood(os.path.join(GOLD, "ll.txt")) == o["ll.txt"][0]
+    assert io.read_transitions(os.path.join(GOLD, "transitions.txt")) == o["transitions.txt"][0]
+    assert io.read_transitions_log_likelihood(os.path.join(GOLD, "tll.txt")) == o["tll.txt"][0]
+    t, want = io.read_tree(os.path.join(GOLD, "tree.txt")), make_tree(io)
+    assert t.nodes() == want.nodes() and t.edges() == want.edges()
+    cms = io.read_count_matrices(os.path.join(GOLD, "count_matrices.txt"))
+    for (qv, df), (qw, m) in zip(cms, o["count_matrices.txt"][0]):
+        assert qv == qw and list(df.index) == AA and np.array_equal(df.to_numpy(), m)
