@@ -141,3 +141,102 @@ def get_equ_path() -> str:
 def get_wag_path() -> str:
     """The WAG rate matrix (Whelan & Goldman 2001) (reference ``get_wag_path``)."""
     return _rate_matrix_path("wag")
+
+
+def _stored_matrix(name: str) -> np.ndarray:
+    with np.load(_DATA_FILE) as z:
+        return z[name]
+
+
+def _derived_path(name: str, build) -> str:
+    """A file derived from the shipped matrices (stationary distribution, product chain), written on
+    first use next to them.  The reference ships these as data files computed once by its authors;
+    the values here come from ``compute_stationary_distribution`` / ``chain_product`` and agree with
+    those files to ~1e-16 (checked in tests/test_markov_chain_data.py where the reference is present)."""
+    if name not in _MATERIALISED:
+        import tempfile
+
+        out_dir = os.path.join(tempfile.gettempdir(), f"cherryml_b200_data_{os.getuid()}")
+        os.makedirs(out_dir, exist_ok=True)
+        path = os.path.join(out_dir, name + ".txt")
+        tmp = f"{path}.{os.getpid()}.tmp"
+        build(tmp)
+        os.replace(tmp, path)
+        _MATERIALISED[name] = path
+    return _MATERIALISED[name]
+
+
+def _stationary_path(name: str, matrix_name: str, product: bool) -> str:
+    from ..io import write_probability_distribution
+    from ..utils import amino_acids
+
+    def build(path):
+        Q = _stored_matrix(matrix_name)
+        states = list(amino_acids)
+        if product:
+            Q = chain_product(Q, Q)
+            states = [a + b for a in amino_acids for b in amino_acids]
+        write_probability_distribution(compute_stationary_distribution(Q), states, path)
+
+    return _derived_path(name, build)
+
+
+def _product_path(name: str, matrix_name: str) -> str:
+    from ..io import write_rate_matrix
+    from ..utils import amino_acids
+
+    def build(path):
+        Q = _stored_matrix(matrix_name)
+        write_rate_matrix(chain_product(Q, Q), [a + b for a in amino_acids for b in amino_acids], path)
+
+    return _derived_path(name, build)
+
+
+def get_lg_stationary_path() -> str:
+    """Stationary distribution of LG (reference ``get_lg_stationary_path``)."""
+    return _stationary_path("lg_stationary", "lg", product=False)
+
+
+def get_wag_stationary_path() -> str:
+    """Stationary distribution of WAG (reference ``get_wag_stationary_path``)."""
+    return _stationary_path("wag_stationary", "wag", product=False)
+
+
+def get_lg_x_lg_path() -> str:
+    """The 400 x 400 chain of two independent LG sites (reference ``get_lg_x_lg_path``)."""
+    return _product_path("lg_x_lg", "lg")
+
+
+def get_lg_x_lg_stationary_path() -> str:
+    """Stationary distribution of the LG x LG chain (reference ``get_lg_x_lg_stationary_path``)."""
+    return _stationary_path("lg_x_lg_stationary", "lg", product=True)
+
+
+def get_equ_x_equ_path() -> str:
+    """The 400 x 400 chain of two independent uniform-exchangeability sites (reference ``get_equ_x_equ_path``)."""
+    return _product_path("equ_x_equ", "equ")
+
+
+def equ_matrix():
+    """The uniform-exchangeability matrix as a labelled table (reference ``equ_matrix``)."""
+    from ..io import read_rate_matrix
+
+    return read_rate_matrix(get_equ_path())
+
+
+def wag_matrix():
+    """WAG rescaled to one expected mutation per unit time (reference ``wag_matrix``,
+    _markov_chain.py:171-184; the shipped matrix already is, so this is a no-op up to rounding)."""
+    from ..io import read_rate_matrix
+
+    wag = read_rate_matrix(get_wag_path())
+    pi = compute_stationary_distribution(wag.to_numpy())
+    return wag / np.dot(-np.diag(wag.to_numpy()), pi)
+
+
+def wag_stationary_distribution():
+    """Reference ``wag_stationary_distribution`` (_markov_chain.py:187-191)."""
+    import pandas as pd
+
+    wag = wag_matrix()
+    return pd.DataFrame(compute_stationary_distribution(wag.to_numpy()), index=wag.index)
