@@ -7,6 +7,7 @@ product path evaluates the same fp64 expression on the GPU (csrc/count_kernels.c
 ``quantize_bucket``) and never calls this function for data.
 """
 import bisect
+import contextlib
 import os
 from typing import List, Optional, Sequence
 
@@ -52,12 +53,25 @@ def quantization_idx_array(branch_lengths, quantization_points_sorted):
 
 def get_process_args(process_rank: int, num_processes: int, all_args: List) -> List:
     """Rank ``r`` of ``P`` owns items ``r, r+P, r+2P, ...`` (the reference's striping)."""
+    if not 0 <= process_rank < num_processes:
+        return []  # no index i has i % P == r
     return list(all_args[process_rank::num_processes])
 
 
 def get_families(msa_dir: str) -> List[str]:
     names = sorted(os.listdir(msa_dir))
     return [x.split(".")[0] for x in names if x.endswith(".txt")]
+
+
+@contextlib.contextmanager
+def pushd(new_dir):
+    """Run the body with ``new_dir`` as the working directory (reference utils.py:70-77)."""
+    previous = os.getcwd()
+    os.chdir(new_dir)
+    try:
+        yield
+    finally:
+        os.chdir(previous)
 
 
 def make_quantization_points(center: float, step: float, num_steps: int) -> List[str]:
