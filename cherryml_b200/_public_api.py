@@ -370,7 +370,12 @@ def cherryml_public_api(
     caching.set_cache_dir(cache_dir)
     if families is None:
         families = get_families(msa_dir)
-    if initial_tree_estimator_rate_matrix_path is None:
+    if initial_tree_estimator_rate_matrix_path is None or (
+        # the reference's default is this path relative to ITS checkout; callers that pass the
+        # literal along (its CLI does) mean "the LG matrix"
+        initial_tree_estimator_rate_matrix_path == "data/rate_matrices/lg.txt"
+        and not os.path.exists(initial_tree_estimator_rate_matrix_path)
+    ):
         initial_tree_estimator_rate_matrix_path = get_lg_path()
     if tree_estimator_name == "FastCherries":
         tree_estimator = partial(fast_cherries, max_iters=50, num_rate_categories=num_rate_categories,

@@ -157,11 +157,14 @@ def read_tree(tree_path: str) -> Tree:
     return tree
 
 
-def write_tree(tree: Tree, tree_path: str) -> None:
+def write_tree(tree: Tree, tree_path: str, scaling_factor: float = 1.0, node_name_prefix: str = "") -> None:
+    """``scaling_factor`` multiplies every branch length, ``node_name_prefix`` is put in front of
+    every node name (reference io/_tree.py:193-211)."""
+    pre = node_name_prefix
     out = [f"{tree.num_nodes()} nodes\n"]
-    out += [f"{v}\n" for v in tree.nodes()]
+    out += [f"{pre + v}\n" for v in tree.nodes()]
     out.append(f"{tree.num_edges()} edges\n")
-    out += [f"{u} {v} {d}\n" for u, v, d in tree.edges()]
+    out += [f"{pre + u} {pre + v} {d * scaling_factor}\n" for u, v, d in tree.edges()]
     _makedirs_for(tree_path)
     with open(tree_path, "w") as f:
         f.write("".join(out))
@@ -468,17 +471,17 @@ def read_mask_matrix(mask_matrix_path: str):
     return pd.DataFrame(arr.astype(int), index=rows, columns=cols)
 
 
-def read_probability_distribution(path: str):
+def read_probability_distribution(probability_distribution_path: str):
     import pandas as pd
 
-    rows, cols, arr = _read_labelled_table(path)
+    rows, cols, arr = _read_labelled_table(probability_distribution_path)
     if arr.shape[1] != 1:
         raise Exception(
-            f"Probability distribution at {path} should be one-dimensional."
+            f"Probability distribution at {probability_distribution_path} should be one-dimensional."
         )
     if abs(arr.sum() - 1.0) > 1e-6:
         raise Exception(
-            f"Probability distribution at {path} should add to 1.0, with a "
+            f"Probability distribution at {probability_distribution_path} should add to 1.0, with a "
             "tolerance of 1e-6."
         )
     return pd.DataFrame(arr, index=rows, columns=cols)
@@ -525,7 +528,7 @@ def write_rate_matrix_py(
 
 
 def write_probability_distribution(
-    probability_distribution: np.ndarray, states: Sequence[str], path: str
+    probability_distribution: np.ndarray, states: Sequence[str], probability_distribution_path: str
 ) -> None:
     p = np.asarray(probability_distribution).reshape(-1)
     if len(states) != p.shape[0]:
@@ -533,8 +536,8 @@ def write_probability_distribution(
             f"probability_distribution has shape {p.shape}, inconsistent with "
             f"states: {states}"
         )
-    _makedirs_for(path)
-    with open(path, "w") as f:
+    _makedirs_for(probability_distribution_path)
+    with open(probability_distribution_path, "w") as f:
         f.write("state\tprob\n" + "".join(f"{s}\t{v!r}\n" for s, v in zip(states, p.tolist())))
 
 

@@ -41,3 +41,20 @@ def test_readers_give_the_objects_back():
     cms = io.read_count_matrices(os.path.join(GOLD, "count_matrices.txt"))
     for (qv, df), (qw, m) in zip(cms, o["count_matrices.txt"][0]):
         assert qv == qw and list(df.index) == AA and np.array_equal(df.to_numpy(), m)
+
+
+def test_write_tree_scaling_and_prefix(tmp_path):
+    """Reference io/_tree.py:193-211; expected text written by the reference for the same tree."""
+    path = str(tmp_path / "t.txt")
+    io.write_tree(make_tree(io), path, scaling_factor=0.3, node_name_prefix="fam-")
+    assert open(path).read() == ("5 nodes\nfam-r\nfam-x\nfam-a\nfam-b\nfam-c\n4 edges\nfam-r fam-x 0.03\n"
+                                 "fam-r fam-c 3e-06\nfam-x fam-a 0.075\nfam-x fam-b 0.8999999999999999\n")
+
+
+def test_keyword_names_of_the_reference():
+    import inspect
+
+    assert list(inspect.signature(io.read_probability_distribution).parameters) == ["probability_distribution_path"]
+    assert list(inspect.signature(io.write_probability_distribution).parameters) == [
+        "probability_distribution", "states", "probability_distribution_path"]
+    assert list(inspect.signature(io.write_tree).parameters) == ["tree", "tree_path", "scaling_factor", "node_name_prefix"]
