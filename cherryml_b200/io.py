@@ -86,6 +86,16 @@ class Tree:
     def internal_nodes(self) -> List[str]:
         return [u for u in self._children if self._children[u]]
 
+    def scaled(self, scaling_factor: float, node_name_prefix: str = "") -> "Tree":
+        """A copy with every branch length multiplied by ``scaling_factor`` and every node name
+        prefixed (reference io/_tree.py:115-129, which goes through a temporary tree file: node
+        and edge order are kept, lengths are ``d * scaling_factor``)."""
+        res = Tree()
+        res.add_nodes([node_name_prefix + v for v in self.nodes()])
+        for u, v, d in self._edges:
+            res.add_edge(node_name_prefix + u, node_name_prefix + v, float(repr(d * scaling_factor)))
+        return res
+
     def postorder_traversal(self) -> List[str]:
         """Children (in edge order) before their parent; iterative, so deep trees are fine."""
         res, stack = [], [(self.root(), 0)]

@@ -58,3 +58,11 @@ def test_keyword_names_of_the_reference():
     assert list(inspect.signature(io.write_probability_distribution).parameters) == [
         "probability_distribution", "states", "probability_distribution_path"]
     assert list(inspect.signature(io.write_tree).parameters) == ["tree", "tree_path", "scaling_factor", "node_name_prefix"]
+
+
+def test_tree_scaled():
+    t = make_tree(io).scaled(0.3, "p_")
+    assert t.nodes() == ["p_r", "p_x", "p_a", "p_b", "p_c"]
+    assert t.edges() == [("p_r", "p_x", 0.03), ("p_r", "p_c", 3e-06), ("p_x", "p_a", 0.075),
+                         ("p_x", "p_b", 0.8999999999999999)]
+    assert make_tree(io).scaled(1.0).edges() == make_tree(io).edges()
