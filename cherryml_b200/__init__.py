@@ -16,6 +16,6 @@ from ._public_api import (  # noqa: F401
     lg_end_to_end_with_cherryml_optimizer,
 )
 from .evaluation import compute_log_likelihoods  # noqa: F401
-from .phylogeny_estimation import fast_cherries  # noqa: F401
+from .phylogeny_estimation import fast_cherries, gt_tree_estimator  # noqa: F401
 from .siterm import learn_site_specific_rate_matrices  # noqa: F401
 from .types import PhylogenyEstimatorType  # noqa: F401

@@ -212,6 +212,15 @@ def cached_computation(
     return decorator
 
 
+def secure_parallel_output(output_dir: str, parallel_arg: str) -> None:
+    """Mark ``<output_dir>/<parallel_arg>.txt`` as done from inside a parallel stage: read-only
+    plus a success token (reference ``_cached_parallel_computation.py:15-19``).  Stages here do not
+    need it -- the decorator does this for every item after the function returns."""
+    _make_read_only(os.path.join(output_dir, parallel_arg + ".txt"))
+    with open(os.path.join(output_dir, parallel_arg + ".success"), "w") as f:
+        f.write("SUCCESS\n")
+
+
 def cached_parallel_computation(
     parallel_arg: str,
     exclude_args: List[str] = [],

@@ -109,3 +109,38 @@ def test_without_a_cache_dir_the_function_just_runs(tmp_path):
 
     f(x=1, out_dir=str(tmp_path))
     assert seen == [str(tmp_path)]
+
+
+def test_gt_tree_estimator_stage(cache, tmp_path):
+    """Reference phylogeny_estimation/_gt_tree_estimator.py: the given files come back through the
+    tree estimators' interface, cached per family."""
+    from cherryml_b200 import io
+    from cherryml_b200.phylogeny_estimation import gt_tree_estimator
+
+    for f in ("f0", "f1"):
+        t = io.Tree()
+        t.add_nodes(["r", "a", "b"])
+        t.add_edges([("r", "a", 0.1), ("r", "b", 0.25)])
+        io.write_tree(t, str(tmp_path / "gt_tree" / (f + ".txt")))
+        io.write_site_rates([1.0, 0.5], str(tmp_path / "gt_rates" / (f + ".txt")))
+        io.write_log_likelihood((-3.0, [-1.0, -2.0]), str(tmp_path / "gt_ll" / (f + ".txt")))
+    kw = dict(gt_tree_dir=str(tmp_path / "gt_tree"), gt_site_rates_dir=str(tmp_path / "gt_rates"),
+              gt_likelihood_dir=str(tmp_path / "gt_ll"), msa_dir="unused", rate_matrix_path="unused",
+              num_rate_categories=2, num_processes=1)
+    out = gt_tree_estimator(families=["f1", "f0"], **kw)
+    assert set(out) == {"output_tree_dir", "output_site_rates_dir", "output_likelihood_dir"}
+    for f in ("f0", "f1"):
+        for d, src in (("output_tree_dir", "gt_tree"), ("output_site_rates_dir", "gt_rates"),
+                       ("output_likelihood_dir", "gt_ll")):
+            assert open(os.path.join(out[d], f + ".txt")).read() == open(tmp_path / src / (f + ".txt")).read()
+            assert os.path.exists(os.path.join(out[d], f + ".success"))
+        assert open(os.path.join(out["output_tree_dir"], f + ".profiling")).read() == "time_gt_tree_estimator: 0"
+    os.remove(tmp_path / "gt_tree" / "f0.txt")  # cached: the inputs are not read again
+    assert gt_tree_estimator(families=["f0"], **kw) == out
+
+
+def test_secure_parallel_output(tmp_path):
+    p = tmp_path / "x.txt"
+    p.write_text("1")
+    caching.secure_parallel_output(str(tmp_path), "x")
+    assert _mode(str(p)) == 0o444 and (tmp_path / "x.success").read_text() == "SUCCESS\n"
