@@ -77,8 +77,10 @@ def _jtt_ipw_stage():
             q, states, counts = resident
         else:
             q, states, counts_np = read_count_matrices_array(count_matrices_path)
-            dev = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
-            counts = torch.from_numpy(counts_np).to(dev)
+            # a closed-form estimate on K x S x S numbers (no kernel on this path): computed where
+            # the counts are -- on the device when the counting stage left them there, on the host
+            # when they come from a file
+            counts = torch.from_numpy(counts_np)
         mask = read_mask_matrix(mask_path).to_numpy() if mask_path is not None else None
         res = jtt_ipw_from_counts(q, counts, mask=mask, use_ipw=use_ipw, pseudocounts=pseudocounts,
                                   symmetrize_count_matrices=symmetrize_count_matrices, max_time=max_time)

@@ -21,3 +21,23 @@ def test_jtt_ipw_toy_goldens(use_ipw, masked):
     got = jtt_ipw_from_counts(q, torch.from_numpy(counts), mask=mask, use_ipw=use_ipw)
     name = f"Q1_JTT{'-IPW' if use_ipw else ''}_on_toy_matrix{'_mask' if masked else ''}.txt"
     np.testing.assert_almost_equal(got, np.loadtxt(os.path.join(GOLDEN, "jtt", name)))
+
+
+def test_stage_reads_counts_from_a_file_and_writes_the_reference_files(tmp_path):
+    """The stage on counts that come from a file (host-side closed form, no device involved)."""
+    from cherryml_b200.estimation import jtt_ipw
+    from cherryml_b200.io import read_rate_matrix
+
+    out = str(tmp_path / "jtt")
+    jtt_ipw(count_matrices_path=os.path.join(INP, "matrices_toy.txt"), mask_path=None, use_ipw=True,
+            output_rate_matrix_dir=out, normalize=False)
+    got = read_rate_matrix(os.path.join(out, "result.txt"))
+    np.testing.assert_almost_equal(got.to_numpy(), np.loadtxt(os.path.join(GOLDEN, "jtt", "Q1_JTT-IPW_on_toy_matrix.txt")))
+    assert open(os.path.join(out, "profiling.txt")).read().startswith("Total time: ")
+    out_n = str(tmp_path / "jtt_n")
+    jtt_ipw(count_matrices_path=os.path.join(INP, "matrices_toy.txt"), mask_path=None, use_ipw=True,
+            output_rate_matrix_dir=out_n, normalize=True)
+    qn = read_rate_matrix(os.path.join(out_n, "result.txt")).to_numpy()
+    from cherryml_b200.markov_chain import compute_mutation_rate
+
+    assert abs(compute_mutation_rate(qn) - 1.0) < 1e-9
