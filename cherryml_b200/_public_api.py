@@ -56,7 +56,8 @@ def maximal_matching_pairs(contact_map: np.ndarray, minimum_distance: int):
     return match
 
 
-@caching.cached_computation(
+@caching.cached_parallel_computation(
+    parallel_arg="families",
     exclude_args=["num_processes"],
     output_dirs=["o_contact_map_dir"],
     write_extra_log_files=True,
@@ -68,14 +69,15 @@ def create_maximal_matching_contact_map(
     num_processes: int,
     o_contact_map_dir: Optional[str] = None,
 ) -> None:
+    """Per family, the contact map reduced to a maximal matching of its non-trivial contacts, so
+    that every site is in at most one pair (reference ``evaluation/_maximal_matching.py:31-115``;
+    cached per family like the reference's stage)."""
     for family in families:
         cmap = read_contact_map(os.path.join(i_contact_map_dir, family + ".txt"))
         res = np.zeros(cmap.shape)
         for u, v in maximal_matching_pairs(cmap, minimum_distance_for_nontrivial_contact):
             res[u, v] = res[v, u] = 1
         write_contact_map(res, os.path.join(o_contact_map_dir, family + ".txt"))
-    with open(os.path.join(o_contact_map_dir, "result.txt"), "w") as f:
-        f.write(f"{len(families)} families\n")
 
 
 @caching.cached_parallel_computation(

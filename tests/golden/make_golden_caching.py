@@ -56,10 +56,18 @@ def cases():
                                       "device_1": "cuda", "num_processes": 8}
 
 
+    yield "create_maximal_matching_contact_map", dict(i_contact_map_dir="/d/cm", families=["f1", "f0"],
+                                                      minimum_distance_for_nontrivial_contact=7, num_processes=4)
+    yield "gt_tree_estimator", dict(gt_tree_dir="/d/t", gt_site_rates_dir="/d/r", gt_likelihood_dir="/d/l",
+                                    msa_dir="/d/msas", families=["f0"], rate_matrix_path="/d/lg.txt",
+                                    num_rate_categories=4, num_processes=2)
+
+
 def reference_stage(cherryml, key):
     import cherryml.counting
     import cherryml.estimation
     import cherryml.evaluation
+    import cherryml.phylogeny_estimation
     import cherryml.phylogeny_estimation._fast_cherries as fc
 
     return {"count_transitions": cherryml.counting.count_transitions,
@@ -67,7 +75,9 @@ def reference_stage(cherryml, key):
             "quantized_transitions_mle": cherryml.estimation.quantized_transitions_mle,
             "jtt_ipw": cherryml.estimation.jtt_ipw,
             "fast_cherries": fc.fast_cherries,
-            "compute_log_likelihoods": cherryml.evaluation.compute_log_likelihoods}[key]
+            "compute_log_likelihoods": cherryml.evaluation.compute_log_likelihoods,
+            "create_maximal_matching_contact_map": cherryml.evaluation.create_maximal_matching_contact_map,
+            "gt_tree_estimator": cherryml.phylogeny_estimation.gt_tree_estimator}[key]
 
 
 def reference_dir(stage, kwargs, use_hash):

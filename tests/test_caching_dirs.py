@@ -13,10 +13,13 @@ CASES = json.load(open(os.path.join(HERE, "golden", "caching", "dirs.json")))
 
 def _stage(key):
     import cherryml_b200 as pkg
+    import cherryml_b200.evaluation  # noqa: F401
 
     return {"count_transitions": pkg.count_transitions, "count_co_transitions": pkg.count_co_transitions,
             "quantized_transitions_mle": pkg.quantized_transitions_mle, "jtt_ipw": pkg.jtt_ipw,
-            "fast_cherries": pkg.fast_cherries, "compute_log_likelihoods": pkg.compute_log_likelihoods}[key]
+            "fast_cherries": pkg.fast_cherries, "compute_log_likelihoods": pkg.compute_log_likelihoods,
+            "create_maximal_matching_contact_map": pkg.evaluation.create_maximal_matching_contact_map,
+            "gt_tree_estimator": pkg.gt_tree_estimator}[key]
 
 
 @pytest.mark.parametrize("i", range(len(CASES)))
