@@ -11,7 +11,8 @@ FastCherries and SiteRM tests need a GPU, which the build container does not hav
 box does not have the reference: their cases are restated in tests/test_gpu_*.py instead.  Run
 here, counting_test.py and quantized_transitions_mle_test.py (42 tests) bind to this package's
 API without a single TypeError / AttributeError / ImportError: 6 pass and 36 stop at "Found no
-NVIDIA driver", i.e. where the CUDA path starts.  (`parameterized` is not installed: a minimal
+NVIDIA driver", i.e. where the CUDA path starts; likelihood_test.py (84 tests): 42 pass (input
+validation, file handling), 42 stop at the same place, none on an API mismatch.  (`parameterized` is not installed: a minimal
 stand-in for ``parameterized.expand`` is injected.)
 (``assertEquals`` is aliased because Python 3.12 removed it.)
 """
@@ -49,6 +50,9 @@ except Exception:
     shim.parameterized = _Parameterized
     sys.modules["parameterized"] = shim
 os.chdir("/root/reference")
+sys.path.insert(0, "/root/reference")  # the reference's test files import helpers from ITS `tests` package
+for name in [m for m in sys.modules if m == "tests" or m.startswith("tests.")]:
+    del sys.modules[name]
 suite = unittest.TestSuite()
 for path in sys.argv[1:]:
     spec = importlib.util.spec_from_file_location("reftest_" + os.path.basename(path)[:-3], path)
