@@ -124,6 +124,80 @@ def cpu_fit_baseline(times, counts: torch.Tensor, num_epochs_full: int, epochs_t
                       f"{cores} threads), scaled linearly"}
 
 
+def _states_for(S: int):
+    from cherryml_b200.utils import amino_acids
+
+    if S == len(amino_acids):
+        return list(amino_acids)
+    if S == len(amino_acids) ** 2:
+        return [a + b for a in amino_acids for b in amino_acids]
+    return [f"s{i}" for i in range(S)]
+
+
+def reference_fit_arms(times, counts: torch.Tensor, num_epochs_full: int, cpu_epochs: int, cuda_epochs: int,
+                       workdir: str, timeout_s: int = 900) -> Dict:
+    """The UNMODIFIED reference ``quantized_transitions_mle`` (reference
+    estimation/_quantized_transitions_mle.py:40-122 -> ratelearner.py:66-152 -> trainer.py:118-243) on
+    the SAME count matrices and JTT-IPW initialisation as our arm, as two arms:
+      * ``cpu``  -- device="cpu", OMP/OPENBLAS threads = all host cores of this box;
+      * ``cuda`` -- the reference's own stock device="cuda" path on this B200 (torch.matrix_exp +
+        autograd, count tensor re-uploaded every epoch as trainer.py:160-166 does).
+    Each arm runs oracle/run_reference_fit.py in its own process on files written here (count matrices
+    in the Python writer's layout: exact reprs).  When fewer than ``num_epochs_full`` epochs are timed
+    the end-to-end seconds are extrapolated as  (wall - training) + first epoch + (E - 1) * mean later
+    epoch  -- epochs are identical work -- and the sample says so."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    from cherryml_b200.io import write_count_matrices_array, write_rate_matrix
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    runner = os.path.join(repo, "oracle", "run_reference_fit.py")
+    S = int(counts.shape[-1])
+    states = _states_for(S)
+    os.makedirs(workdir, exist_ok=True)
+    counts_path = os.path.join(workdir, f"counts_{S}.txt")
+    init_path = os.path.join(workdir, f"init_{S}.txt")
+    write_count_matrices_array(list(times), states, counts.cpu().numpy(), counts_path, "python")
+    write_rate_matrix(jtt_ipw_from_counts(times, counts), states, init_path)
+    cores = os.cpu_count() or 1
+    out: Dict = {}
+    for arm, epochs in (("cpu", cpu_epochs), ("cuda", cuda_epochs)):
+        if epochs <= 0:
+            continue
+        epochs = min(epochs, num_epochs_full)
+        odir = os.path.join(workdir, f"ref_{S}_{arm}")
+        cmd = [sys.executable, runner, "--counts", counts_path, "--init", init_path, "--device", arm,
+               "--epochs", str(epochs), "--threads", str(cores), "--out", odir]
+        try:
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
+            line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+            if res.returncode != 0 or not line:
+                out[arm] = {"error": (res.stderr or res.stdout)[-300:]}
+                continue
+            r = json.loads(line[-1])
+        except Exception as e:  # the extra measurement must not cost the bench line
+            out[arm] = {"error": str(e)[:300]}
+            continue
+        setup = r["wall_seconds"] - r["train_seconds"]
+        full = setup + r["first_epoch_seconds"] + (num_epochs_full - 1) * r["seconds_per_epoch"]
+        out[arm] = {
+            "kind": "reference", "device": arm, "cores": cores if arm == "cpu" else 1,
+            "epochs_timed": r["epochs"], "seconds_measured": r["wall_seconds"],
+            "seconds_setup_parse_write": setup, "seconds_per_epoch": r["seconds_per_epoch"],
+            "seconds_end_to_end": r["wall_seconds"] if epochs == num_epochs_full else full,
+            "extrapolated": epochs != num_epochs_full,
+            "loss_first": r["loss_first"], "loss_last": r["loss_last"], "torch": r["torch"],
+            "sample": (f"unmodified reference quantized_transitions_mle(device='{arm}'), same result.txt and "
+                       f"JTT-IPW init as our arm, {r['epochs']} of {num_epochs_full} epochs timed"
+                       + ("" if epochs == num_epochs_full else ", later epochs scaled linearly")
+                       + (f", {cores} OMP/BLAS threads" if arm == "cpu" else ", torch.matrix_exp + autograd on this GPU")),
+        }
+    return out
+
+
 def bench_fit(device, lg_times=None, lg_counts: Optional[torch.Tensor] = None, num_epochs: int = 500,
               co_families: int = 4096, process_group=None, cpu_baseline: bool = False) -> Dict:
     from cherryml_b200.counting._device import count_raw, sorted_grid, symmetrize

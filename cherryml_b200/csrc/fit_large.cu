@@ -22,6 +22,7 @@
 //
 // Replaces torch.matrix_exp + log + sum + autograd.backward + Adam of the reference's
 // train_quantization (estimation/_ratelearn/trainer.py:156-187) for S = 400.
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -40,6 +41,7 @@ constexpr int LD_ROW = 20;        // tile stored [80][16]: k contiguous
 constexpr int LD_COL = 84;        // tile stored [16][80]: m (or n) contiguous
 constexpr int TILE_ELEMS = BT * LD_ROW;  // 1600 >= 16 * 84
 constexpr int EW_THREADS = 256;
+static_assert(kDeg % 4 == 0, "the elementwise kernels skip Taylor terms in blocks of four");
 
 struct GemmTerm {
   const double* A;
@@ -111,9 +113,12 @@ __device__ __forceinline__ void compute_chunk(const double* As, const double* Bs
 
 // Core of every GEMM here: one 80x80 output tile, accumulated over k chunks [c_begin, c_end) of
 // the concatenated terms, 3-stage cp.async pipeline, result (+ old value) stored to `out`.
+// `out` is addressed as out[(m0 + r) * ld_out + n0 + c]; callers that want a compact 80x80 partial
+// tile pass ld_out = BT and a pointer shifted by -(m0 * BT + n0) (compact_tile_base below).
 template <typename TermFn>
 __device__ __forceinline__ void gemm_tile(TermFn get_term, int Sp, int m0, int n0, int c_begin, int c_end,
-                                          double* smem, double* out, bool add_old) {
+                                          double* smem, double* out, bool add_old, int ld_out = 0) {
+  if (ld_out == 0) ld_out = Sp;
   const int cpt = Sp / BK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const int kgroup = warp >> 2, wq = warp & 3;  // 4 warps (2x2 quadrants of 40x40) per k group
@@ -184,7 +189,7 @@ __device__ __forceinline__ void gemm_tile(TermFn get_term, int Sp, int m0, int n
   for (int i = 0; i < 5; ++i)
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
-      double2* p = reinterpret_cast<double2*>(out + (size_t)(m0 + rbase + 8 * i + g) * Sp + n0 + cbase + 8 * j + 2 * tg);
+      double2* p = reinterpret_cast<double2*>(out + (ptrdiff_t)(m0 + rbase + 8 * i + g) * ld_out + n0 + cbase + 8 * j + 2 * tg);
       double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
       if (add_old) {
         const double2 o = *p;
@@ -326,16 +331,29 @@ squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__
     if (!s_last) return false;
     __threadfence();
     const double* pb = partial + (size_t)rank[k] * ksplit * n_p;
-    for (int e = threadIdx.x; e < BT * BT / 2; e += GEMM_THREADS) {
-      const int r = e / (BT / 2), c2 = (e - r * (BT / 2)) * 2;
-      const size_t pos = (size_t)(m0 + r) * Sp + n0 + c2;
-      double2 v = make_double2(0.0, 0.0);
-      for (int zz = 0; zz < ksplit; ++zz) {
-        const double2 pz = __ldcg(reinterpret_cast<const double2*>(pb + (size_t)zz * n_p + pos));
-        v.x += pz.x;
-        v.y += pz.y;
+    constexpr int NQ = BT * BT / 2 / GEMM_THREADS;
+    double2 v[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) v[q] = make_double2(0.0, 0.0);
+    for (int zz = 0; zz < ksplit; ++zz) {
+      double2 t[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int e = threadIdx.x + q * GEMM_THREADS;
+        const int r = e / (BT / 2), c2 = (e - r * (BT / 2)) * 2;
+        t[q] = __ldcg(reinterpret_cast<const double2*>(pb + (size_t)zz * n_p + (size_t)(m0 + r) * Sp + n0 + c2));
       }
-      *reinterpret_cast<double2*>(out + pos) = v;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        v[q].x += t[q].x;
+        v[q].y += t[q].y;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int e = threadIdx.x + q * GEMM_THREADS;
+      const int r = e / (BT / 2), c2 = (e - r * (BT / 2)) * 2;
+      *reinterpret_cast<double2*>(out + (size_t)(m0 + r) * Sp + n0 + c2) = v[q];
     }
     return true;
   };
@@ -380,6 +398,169 @@ squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__
       __threadfence();
       __syncthreads();
       if (threadIdx.x == 0) atomicAdd(done_bwd + k * (kSStore + 1) + level, 1);
+    }
+  }
+}
+
+// ----------------------------------------------------------- dataflow power chains
+// The forward power schedule (B^2..B^m) and its adjoint are dependent chains of 400^3 products with
+// 25..200 output tiles per level: launched level by level (round 1) every level paid a launch, a
+// pipeline fill on 2-chunk K slices and a separate split-K reduce launch (measured: 10 us fixed +
+// 58 % of the DMMA rate).  Here ONE persistent launch runs a whole chain: the host lists, in
+// dependency order, work items = (output tile, K slice of 80) and groups = output-tile updates;
+// CTAs pull items from an atomic queue, wait only for the operand TILES the slice reads (per-tile
+// version counters, so a level starts while the previous one drains), write a compact partial tile,
+// and the CTA that arrives last at a group adds the partial tiles in slice order (deterministic),
+// applies the update to C and publishes the tile's new version.  Items are dequeued in dependency
+// order and every dequeued item is held by a running CTA, so the waits cannot deadlock.
+struct DfItem {
+  const double* A;
+  const double* B;
+  int ta, tb;
+  int k0, n_chunks;   // K range [k0, k0 + BK * n_chunks)
+  int group, slice;
+  int a_mat, a_ver;   // wait until every tile of A this slice reads has version >= a_ver (a_mat < 0: no wait)
+  int b_mat, b_ver;
+};
+struct DfGroup {
+  double* C;
+  int m0, n0;
+  int n_slices, accumulate;
+  int c_mat, need_ver;  // the update applies to version need_ver of the C tile and publishes need_ver + 1
+  int partial_off, pad;
+};
+struct DfList {  // host-side description of one chain launch
+  std::vector<DfItem> items;
+  std::vector<DfGroup> groups;
+  int n_mats = 0;
+  size_t off_items = 0, off_groups = 0, off_state = 0;  // workspace offsets
+  int partial_tiles = 0;
+};
+// device state of a list: int queue; int pad[3]; int ver[n_mats * tiles]; int arrive[n_groups]
+__host__ __device__ inline size_t df_state_ints(int n_mats, int tiles, int n_groups) {
+  return 4 + (size_t)n_mats * tiles + (size_t)n_groups;
+}
+
+__device__ __forceinline__ void df_wait_tile(const int* v, int target, int* status_flag) {
+  unsigned spins = 0;
+  while (*reinterpret_cast<const volatile int*>(v) < target) {
+    __nanosleep(32);
+    if (++spins > (1u << 23)) {  // a fraction of a second: a scheduling bug must not hang the GPU
+      atomicExch(status_flag, 3);
+      break;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS)
+chain_dataflow_kernel(const DfItem* __restrict__ items, const DfGroup* __restrict__ groups, int n_items,
+                      int* __restrict__ state, int n_mats, int Sp, double* __restrict__ partial,
+                      int* __restrict__ status_flag, long long* __restrict__ prof) {
+  extern __shared__ double smem[];
+  __shared__ int s_item, s_last;
+  const int tiles_n = Sp / BT, tiles = tiles_n * tiles_n;
+  int* queue = state;
+  int* ver = state + 4;
+  int* arrive = ver + n_mats * tiles;
+  // optional phase profile (CHERRY_FIT_TIMELINE): ns per CTA in {dequeue, operand wait, product,
+  // arrive, version wait, reduce, publish}, items taken
+  long long t_prev = 0;
+  auto tick = [&](int phase) {
+    if (prof != nullptr && threadIdx.x == 0) {
+      long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (phase >= 0) prof[blockIdx.x * 8 + phase] += now - t_prev;
+      t_prev = now;
+    }
+  };
+  tick(-1);
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = atomicAdd(queue, 1);
+    __syncthreads();
+    const int idx = s_item;
+    if (idx >= n_items) return;
+    const DfItem it = items[idx];
+    const DfGroup g = groups[it.group];
+    const int ti = g.m0 / BT, tj = g.n0 / BT;
+    if (prof != nullptr && threadIdx.x == 0) prof[blockIdx.x * 8 + 7] += 1;
+    tick(0);
+    if (threadIdx.x < 2) {  // thread 0 waits for A's tiles, thread 1 for B's
+      const int mat = threadIdx.x == 0 ? it.a_mat : it.b_mat;
+      if (mat >= 0) {
+        const int target = threadIdx.x == 0 ? it.a_ver : it.b_ver;
+        const int kz0 = it.k0 / BT, kz1 = (it.k0 + it.n_chunks * BK - 1) / BT;
+        for (int kz = kz0; kz <= kz1; ++kz) {
+          int tile;
+          if (threadIdx.x == 0) tile = it.ta ? kz * tiles_n + ti : ti * tiles_n + kz;
+          else tile = it.tb ? tj * tiles_n + kz : kz * tiles_n + tj;
+          df_wait_tile(ver + mat * tiles + tile, target, status_flag);
+        }
+        __threadfence();
+      }
+    }
+    __syncthreads();
+    tick(1);
+    const GemmTerm t0{it.A, it.B, it.ta, it.tb};
+    const bool direct = (g.n_slices == 1) && !g.accumulate;
+    const int c0 = it.k0 / BK;
+    if (direct) {
+      gemm_tile([&](int) { return t0; }, Sp, g.m0, g.n0, c0, c0 + it.n_chunks, smem, g.C, false);
+    } else {
+      double* ptile = partial + (size_t)(g.partial_off + it.slice) * (BT * BT);
+      gemm_tile([&](int) { return t0; }, Sp, g.m0, g.n0, c0, c0 + it.n_chunks, smem,
+                ptile - ((ptrdiff_t)g.m0 * BT + g.n0), false, BT);
+      tick(2);
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) s_last = (atomicAdd(arrive + it.group, 1) == g.n_slices - 1);
+      __syncthreads();
+      tick(3);
+      if (!s_last) continue;
+      if (threadIdx.x == 0) {
+        if (g.accumulate && g.need_ver > 0)
+          df_wait_tile(ver + g.c_mat * tiles + ti * tiles_n + tj, g.need_ver, status_flag);
+        __threadfence();
+      }
+      __syncthreads();
+      tick(4);
+      // every thread owns NQ double2 elements of the tile; per slice all NQ loads are in flight at once
+      // (a loop over the slices per element would serialise NQ * n_slices L2 round trips)
+      const double* pb = partial + (size_t)g.partial_off * (BT * BT);
+      constexpr int NQ = BT * BT / 2 / GEMM_THREADS;
+      static_assert(NQ * GEMM_THREADS * 2 == BT * BT, "tile elements must divide evenly over the CTA");
+      double2 v[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int e = threadIdx.x + q * GEMM_THREADS;
+        const int r = e / (BT / 2), c2 = (e - r * (BT / 2)) * 2;
+        v[q] = g.accumulate ? __ldcg(reinterpret_cast<const double2*>(g.C + (size_t)(g.m0 + r) * Sp + g.n0 + c2))
+                            : make_double2(0.0, 0.0);
+      }
+      for (int z = 0; z < g.n_slices; ++z) {
+        const double2* pz = reinterpret_cast<const double2*>(pb + (size_t)z * (BT * BT));
+        double2 t[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) t[q] = __ldcg(pz + threadIdx.x + q * GEMM_THREADS);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          v[q].x += t[q].x;
+          v[q].y += t[q].y;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int e = threadIdx.x + q * GEMM_THREADS;
+        const int r = e / (BT / 2), c2 = (e - r * (BT / 2)) * 2;
+        *reinterpret_cast<double2*>(g.C + (size_t)(g.m0 + r) * Sp + g.n0 + c2) = v[q];
+      }
+      tick(5);
+    }
+    if (g.c_mat >= 0) {
+      __threadfence();  // every thread publishes its part of the tile before the version moves
+      __syncthreads();
+      if (threadIdx.x == 0) atomicExch(ver + g.c_mat * tiles + ti * tiles_n + tj, g.need_ver + 1);
+      tick(6);
     }
   }
 }
@@ -434,10 +615,20 @@ __global__ void build_B_kernel(const double* __restrict__ Q, int S, int Sp, doub
 }
 
 // one CTA: per bucket s_k, tau_k and the weights w[k][j] = e^{-tau mu} tau^j / j!, j = 0..m
+// Per-bucket Taylor degree d_k <= m: the smallest degree whose truncation tail x^(d+1)/(d+1)!
+// (x = tau mu <= theta, all terms non-negative) stays below 2e-17 of the SECOND-order term x^2/2,
+// so that entries first reached by two substitutions keep full relative accuracy before the
+// log.  Squared buckets keep the full degree.  Weights beyond d_k are zero; the elementwise
+// kernels skip them in blocks of four.
 __global__ void coef_kernel(const double* __restrict__ t, int K, LargeScalars* __restrict__ sc,
-                            int* __restrict__ s_arr, double* __restrict__ w, double* __restrict__ tau_arr,
+                            int* __restrict__ s_arr, int* __restrict__ deg_arr, double* __restrict__ w,
+                            double* __restrict__ tau_arr,
                             int* __restrict__ status_flag, SqSchedule* __restrict__ sched, int tiles,
-                            int n_ctas) {
+                            int n_ctas, int* __restrict__ df_state_fwd, int n_fwd_ints,
+                            int* __restrict__ df_state_bwd, int n_bwd_ints, int full_degree) {
+  // the power chains' queues, tile versions and arrival counters start every epoch at zero
+  for (int i = threadIdx.x; i < n_fwd_ints; i += blockDim.x) df_state_fwd[i] = 0;
+  for (int i = threadIdx.x; i < n_bwd_ints; i += blockDim.x) df_state_bwd[i] = 0;
   const double norm = __longlong_as_double((long long)sc->norm_bits);
   const double mu = sc->mu;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
@@ -451,10 +642,22 @@ __global__ void coef_kernel(const double* __restrict__ t, int K, LargeScalars* _
     const double tau = ldexp(t[k], -s);
     s_arr[k] = s;
     tau_arr[k] = tau;
+    int d = kDeg;
+    if (s == 0) {
+      const double x = fabs(tau) * norm;
+      double term = 2.0 / 6.0;  // d = 2: x^(d-1) * 2 / (d+1)!
+      term *= x;
+      for (d = 2; d < kDeg; ++d) {
+        if (term <= 2e-17) break;
+        term *= x / (double)(d + 2);
+      }
+    }
+    if (full_degree) d = kDeg;
+    deg_arr[k] = d;
     const double e = exp(-tau * mu);
     double c = e;
     for (int j = 0; j <= kDeg; ++j) {
-      w[(size_t)k * (kDeg + 1) + j] = c;
+      w[(size_t)k * (kDeg + 1) + j] = j <= d ? c : 0.0;
       c *= tau / (double)(j + 1);
     }
   }
@@ -532,6 +735,20 @@ poly_eval_kernel(const double* __restrict__ powers, size_t n_p, int S, int Sp, i
   }
 }
 
+// One (element, bucket) of the fused Taylor pass with the first D Taylor terms: value, loss term,
+// and the bucket's contribution to the power adjoints.
+template <int D>
+__device__ __forceinline__ void taylor_term(const double* __restrict__ wk, const double (&pw)[kDeg], double (&acc)[kDeg],
+                                            double c, double diag, double& part) {
+  double v = wk[0] * diag;
+#pragma unroll
+  for (int j = 0; j < D; ++j) v = fma(wk[j + 1], pw[j], v);
+  part -= c * log(v);
+  const double g = -c / v;
+#pragma unroll
+  for (int j = 0; j < D; ++j) acc[j] = fma(wk[j + 1], g, acc[j]);
+}
+
 // Fused Taylor pass (training): one thread per matrix element, the m power values in registers.
 //   buckets WITHOUT squarings (most of them): P_k(e) is the polynomial itself, so the loss term
 //     and the bucket's whole contribution to the power adjoints, Pbar_j(e) += w[k][j] * (-C/P),
@@ -543,14 +760,16 @@ poly_eval_kernel(const double* __restrict__ powers, size_t n_p, int S, int Sp, i
 __global__ void __launch_bounds__(EW_THREADS)
 taylor_fused_kernel(const double* __restrict__ powers, size_t n_p, int S, int Sp, int K,
                     const double* __restrict__ w, const int* __restrict__ s_arr,
-                    const double* __restrict__ C, double* __restrict__ X0, double* __restrict__ Pbar,
-                    double* __restrict__ loss_partial_fused) {
+                    const int* __restrict__ deg_arr, const double* __restrict__ C, double* __restrict__ X0,
+                    double* __restrict__ Pbar, double* __restrict__ loss_partial_fused) {
   extern __shared__ double sw[];  // [K][m+1] weights, then int lists
   __shared__ double red[EW_THREADS / 32];
   __shared__ int n_zero, n_sq;
   int* zlist = reinterpret_cast<int*>(sw + (size_t)K * (kDeg + 1));  // buckets with s == 0
   int* qlist = zlist + K;                                              // buckets with s > 0
+  int* sdeg = qlist + K;                                               // Taylor degree per bucket
   for (int i = threadIdx.x; i < K * (kDeg + 1); i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) sdeg[i] = deg_arr[i];
   if (threadIdx.x == 0) {
     int nz = 0, nq = 0;
     for (int k = 0; k < K; ++k) {
@@ -584,13 +803,13 @@ taylor_fused_kernel(const double* __restrict__ powers, size_t n_p, int S, int Sp
     for (int u = 0; u < 4; ++u) {
       if (c[u] != 0.0) {
         const double* wk = sw + zlist[i0 + u] * (kDeg + 1);
-        double v = wk[0] * diag;
-#pragma unroll
-        for (int j = 0; j < kDeg; ++j) v = fma(wk[j + 1], pw[j], v);
-        part -= c[u] * log(v);
-        const double g = -c[u] / v;
-#pragma unroll
-        for (int j = 0; j < kDeg; ++j) acc[j] = fma(wk[j + 1], g, acc[j]);
+        const int d = sdeg[zlist[i0 + u]];  // block-uniform: the weights beyond d are zero
+        // one uniform branch per (element, bucket) into a fully unrolled body of the bucket's degree class
+        if (d <= 8) taylor_term<8>(wk, pw, acc, c[u], diag, part);
+        else if (d <= 12) taylor_term<12>(wk, pw, acc, c[u], diag, part);
+        else if (d <= 16) taylor_term<16>(wk, pw, acc, c[u], diag, part);
+        else if (d <= 20) taylor_term<20>(wk, pw, acc, c[u], diag, part);
+        else taylor_term<24>(wk, pw, acc, c[u], diag, part);
       }
     }
   }
@@ -898,8 +1117,8 @@ struct Plan {
   int S, Sp, K, tiles;
   size_t n_p;
   // workspace offsets in bytes
-  size_t off_arrive, off_sched, off_scalars, off_s, off_tau, off_w, off_loss_partial, off_grad_theta, off_dpi, off_pibuf, off_tasks, off_terms;
-  size_t off_P, off_Pbar, off_X0, off_chain, off_partial, total_bytes;
+  size_t off_arrive, off_sched, off_scalars, off_s, off_deg, off_tau, off_w, off_loss_partial, off_grad_theta, off_dpi, off_pibuf, off_tasks, off_terms;
+  size_t off_P, off_Pbar, off_X0, off_chain, off_partial, off_prof, total_bytes;
   int slots_per_bucket;   // chain slots 1..kSStore+1
   int loss_blocks;
   int n_partial;
@@ -907,6 +1126,7 @@ struct Plan {
   std::vector<GemmTask> tasks;   // device pointers filled relative to base
   std::vector<GemmTerm> terms;
   std::vector<Group> pow_fwd, sq_fwd, sq_bwd, pow_bwd;
+  DfList df_fwd, df_bwd;  // the two power chains as dataflow item lists
 };
 
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
@@ -942,6 +1162,7 @@ void make_plan(Plan& p, int S, int K, char* base) {
   p.off_sched = carve(sizeof(SqSchedule) + sizeof(int) * ((size_t)kSStore * K * 2 + (size_t)K * (kSStore + 1) +
                                                             (size_t)K + (size_t)K * p.tiles));
   p.off_s = carve(sizeof(int) * K);
+  p.off_deg = carve(sizeof(int) * K);
   p.off_tau = carve(sizeof(double) * K);
   p.off_w = carve(sizeof(double) * K * (kDeg + 1));
   p.off_loss_partial = carve(sizeof(double) * ((size_t)K * p.loss_blocks + (p.n_p + EW_THREADS - 1) / EW_THREADS));
@@ -950,13 +1171,107 @@ void make_plan(Plan& p, int S, int K, char* base) {
   p.off_pibuf = carve(sizeof(double) * S);
   p.off_tasks = carve(sizeof(GemmTask) * max_tasks);
   p.off_terms = carve(sizeof(GemmTerm) * max_terms);
+  // dataflow lists: upper bounds (fine slices everywhere): items <= 3 * (m-1) * tiles * slices
+  {
+    const size_t max_items = 3 * (size_t)kDeg * p.tiles * (p.Sp / BT) + 64;
+    const size_t max_groups = 3 * (size_t)kDeg * p.tiles + 64;
+    p.df_fwd.off_items = carve(sizeof(DfItem) * max_items);
+    p.df_fwd.off_groups = carve(sizeof(DfGroup) * max_groups);
+    p.df_fwd.off_state = carve(sizeof(int) * df_state_ints(kDeg, p.tiles, (int)max_groups));
+    p.df_bwd.off_items = carve(sizeof(DfItem) * max_items);
+    p.df_bwd.off_groups = carve(sizeof(DfGroup) * max_groups);
+    p.df_bwd.off_state = carve(sizeof(int) * df_state_ints(kDeg, p.tiles, (int)max_groups));
+  }
+  p.off_prof = carve(sizeof(long long) * 8 * 2 * 1024);  // phase profile of the two chain launches (<= 1024 CTAs)
   p.off_P = carve(mat * kDeg);
   p.off_Pbar = carve(mat * kDeg);
   p.off_X0 = carve(mat * K);
   p.off_chain = carve(mat * K * p.slots_per_bucket);
-  // split-K partial buffers: sized below once the groups are known (upper bound first)
+  // ---- the two power chains as dataflow lists (pointers are only meaningful when base != nullptr)
+  {
+    char* b0 = base ? base : reinterpret_cast<char*>(0);
+    auto Pj = [&](int j) { return reinterpret_cast<double*>(b0 + p.off_P) + (size_t)(j - 1) * p.n_p; };
+    auto Pbar = [&](int j) { return reinterpret_cast<double*>(b0 + p.off_Pbar) + (size_t)(j - 1) * p.n_p; };
+    const int tn = p.Sp / BT, cpt = p.Sp / BK, fine = BT / BK;  // tiles per side, chunks per term, chunks per 80-deep slice
+    struct TermSpec { const double* A; const double* B; int ta, tb, a_mat, a_ver, b_mat, b_ver; };
+    // one output matrix update C (+)= sum of terms, for every tile; slices of 80 (fine) or whole K per term (coarse)
+    auto add_update = [&](DfList& L, double* C, int c_mat, int need_ver, int accumulate,
+                          const std::vector<TermSpec>& terms, bool coarse) {
+      for (int ti = 0; ti < tn; ++ti)
+        for (int tj = 0; tj < tn; ++tj) {
+          DfGroup g;
+          g.C = C; g.m0 = ti * BT; g.n0 = tj * BT; g.accumulate = accumulate; g.c_mat = c_mat; g.need_ver = need_ver;
+          g.partial_off = L.partial_tiles; g.pad = 0;
+          const int per_term = coarse ? 1 : tn;
+          g.n_slices = (int)terms.size() * per_term;
+          const int gi = (int)L.groups.size();
+          int slice = 0;
+          for (const TermSpec& t : terms)
+            for (int z = 0; z < per_term; ++z) {
+              DfItem it;
+              it.A = t.A; it.B = t.B; it.ta = t.ta; it.tb = t.tb;
+              it.k0 = coarse ? 0 : z * BT; it.n_chunks = coarse ? cpt : fine;
+              it.group = gi; it.slice = slice++;
+              it.a_mat = t.a_ver > 0 ? t.a_mat : -1; it.a_ver = t.a_ver;
+              it.b_mat = t.b_ver > 0 ? t.b_mat : -1; it.b_ver = t.b_ver;
+              L.items.push_back(it);
+            }
+          L.partial_tiles += g.n_slices;
+          L.groups.push_back(g);
+        }
+    };
+    // forward: P_{b+r} = P_b P_r, r = 1..min(b, m-b); matrix id of P_j is j-1, version 1 once written (P_1: given)
+    {
+      DfList& L = p.df_fwd;
+      L.items.clear(); L.groups.clear(); L.partial_tiles = 0; L.n_mats = kDeg;
+      std::vector<int> ver(kDeg + 1, 0);
+      for (int b = 1; b < kDeg; b *= 2) {
+        // the squaring P_2b first: it is the critical path of the next level
+        std::vector<int> rs;
+        if (b + b <= kDeg) rs.push_back(b);
+        for (int r = 1; r <= b && b + r <= kDeg; ++r)
+          if (r != b) rs.push_back(r);
+        for (int r : rs)
+          add_update(L, Pj(b + r), b + r - 1, 0, 0, {TermSpec{Pj(b), Pj(r), 0, 0, b - 1, ver[b], r - 1, ver[r]}}, false);
+        for (int r : rs) ver[b + r] = 1;
+      }
+    }
+    // backward, levels in reverse.  For P_{b+r} = P_b P_r:
+    //   Pbar_r += P_b^T Pbar_{b+r} (r != b),   Pbar_b += sum_r Pbar_{b+r} P_r^T (+ P_b^T Pbar_{2b})
+    // matrix id of Pbar_j is j-1; version 0 = the value accumulate_M left; P_j are inputs (no waits).
+    {
+      DfList& L = p.df_bwd;
+      L.items.clear(); L.groups.clear(); L.partial_tiles = 0; L.n_mats = kDeg;
+      std::vector<int> ver(kDeg + 1, 0);
+      std::vector<int> bases;
+      for (int b = 1; b < kDeg; b *= 2) bases.push_back(b);
+      for (int li = (int)bases.size() - 1; li >= 0; --li) {
+        const int b = bases[li];
+        const int rmax = (b + b <= kDeg) ? b : kDeg - b;
+        std::vector<TermSpec> big;
+        for (int r = 1; r <= rmax; ++r) big.push_back(TermSpec{Pbar(b + r), Pj(r), 0, 1, b + r - 1, ver[b + r], -1, 0});
+        if (rmax == b) big.push_back(TermSpec{Pj(b), Pbar(2 * b), 1, 0, -1, 0, 2 * b - 1, ver[2 * b]});
+        // the long concatenated update first (it is the level's critical path), one slice per term when it has many
+        add_update(L, Pbar(b), b - 1, ver[b], 1, big, big.size() >= 5);
+        for (int r = 1; r <= rmax; ++r)
+          if (r != b)
+            add_update(L, Pbar(r), r - 1, ver[r], 1, {TermSpec{Pj(b), Pbar(b + r), 1, 0, -1, 0, b + r - 1, ver[b + r]}}, false);
+        ver[b]++;
+        for (int r = 1; r <= rmax; ++r)
+          if (r != b) ver[r]++;
+      }
+    }
+  }
+  // split-K partial buffers: the squaring dataflow kernels need kSqPartialSlots matrices, the chain
+  // lists one compact 80x80 tile per (group, slice); the launches are stream ordered and share it
   p.n_partial = kSqPartialSlots;
-  p.off_partial = carve(mat * p.n_partial);
+  {
+    const size_t tile_doubles = (size_t)BT * BT;
+    const size_t need = (size_t)std::max(p.df_fwd.partial_tiles, p.df_bwd.partial_tiles) * tile_doubles;
+    size_t doubles = p.n_p * p.n_partial;
+    if (need > doubles) doubles = need;
+    p.off_partial = carve(doubles * sizeof(double));
+  }
   p.total_bytes = off;
   if (!base) return;
 
@@ -1047,6 +1362,21 @@ void make_plan(Plan& p, int S, int K, char* base) {
   }
 }
 
+// make_plan builds ~6000 work items; the evaluation entry points run once per epoch (and per
+// rank in the sharded path), so the plan of the last (S, K, workspace) is kept per host thread.
+const Plan& get_plan(int S, int K, char* base) {
+  static thread_local Plan cache[2];
+  static thread_local int cS[2] = {0, 0}, cK[2] = {0, 0};
+  static thread_local char* cbase[2] = {nullptr, nullptr};
+  const int slot = base ? 1 : 0;
+  if (cS[slot] != S || cK[slot] != K || cbase[slot] != base) {
+    cache[slot] = Plan();
+    make_plan(cache[slot], S, K, base);
+    cS[slot] = S; cK[slot] = K; cbase[slot] = base;
+  }
+  return cache[slot];
+}
+
 int launch_group(const Plan& p, const Group& g, char* base, cudaStream_t stream) {
   const GemmTask* tasks = reinterpret_cast<const GemmTask*>(base + p.off_tasks) + g.task_begin;
   const GemmTerm* terms = reinterpret_cast<const GemmTerm*>(base + p.off_terms);
@@ -1082,6 +1412,8 @@ int ensure_gemm_attr() {
                                      NSTAGE * 2 * TILE_ELEMS * (int)sizeof(double)));
     CHERRY_CUDA(cudaFuncSetAttribute(squaring_dataflow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      NSTAGE * 2 * TILE_ELEMS * (int)sizeof(double)));
+    CHERRY_CUDA(cudaFuncSetAttribute(chain_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     NSTAGE * 2 * TILE_ELEMS * (int)sizeof(double)));
     attr_set[dev] = true;
   }
   return 0;
@@ -1100,10 +1432,10 @@ void fill_update_args(LargeUpdateArgs& u, const cherry_fit_args& a, const Plan& 
   u.do_adam = a.do_adam; u.loss_normalization = a.loss_normalization; u.best_mode = a.best_mode;
 }
 
-int check_large(const cherry_fit_args& a, Plan& p) {
+int check_large(const cherry_fit_args& a) {
   if (a.n_problems != 1)
     return cherry::fail(CHERRY_ELIMIT, "fit: batched problems are supported for S <= %d only", cherry::kSmallFitMaxS);
-  make_plan(p, a.S, a.K, nullptr);
+  const Plan& p = get_plan(a.S, a.K, nullptr);
   if (!a.workspace || a.workspace_bytes < p.total_bytes)
     return cherry::fail(CHERRY_EINVAL, "fit: workspace of %zu bytes required, got %zu", p.total_bytes,
                         a.workspace_bytes);
@@ -1116,22 +1448,23 @@ namespace cherry {
 
 int fit_large_workspace_bytes(int S, int K, int n_problems, size_t* bytes) {
   if (n_problems != 1) return fail(CHERRY_ELIMIT, "fit: batched problems are supported for S <= %d only", kSmallFitMaxS);
-  Plan p;
-  make_plan(p, S, K, nullptr);
-  *bytes = p.total_bytes;
+  *bytes = get_plan(S, K, nullptr).total_bytes;
   return 0;
 }
 
 // Uploads the GEMM task lists (absolute pointers into this workspace).  Synchronous.
 int fit_large_prepare(const cherry_fit_args& a, cudaStream_t stream) {
-  Plan p;
-  int rc = check_large(a, p);
+  int rc = check_large(a);
   if (rc) return rc;
   char* base = reinterpret_cast<char*>(a.workspace);
-  make_plan(p, a.S, a.K, base);
+  const Plan& p = get_plan(a.S, a.K, base);
   CHERRY_CUDA(cudaStreamSynchronize(stream));
   CHERRY_CUDA(cudaMemcpy(base + p.off_tasks, p.tasks.data(), p.tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice));
   CHERRY_CUDA(cudaMemcpy(base + p.off_terms, p.terms.data(), p.terms.size() * sizeof(GemmTerm), cudaMemcpyHostToDevice));
+  for (const DfList* L : {&p.df_fwd, &p.df_bwd}) {
+    CHERRY_CUDA(cudaMemcpy(base + L->off_items, L->items.data(), L->items.size() * sizeof(DfItem), cudaMemcpyHostToDevice));
+    CHERRY_CUDA(cudaMemcpy(base + L->off_groups, L->groups.data(), L->groups.size() * sizeof(DfGroup), cudaMemcpyHostToDevice));
+  }
   CHERRY_CUDA(cudaMemset(base + p.off_scalars, 0, sizeof(LargeScalars)));
   CHERRY_CUDA(cudaMemset(base + p.off_arrive, 0, sizeof(int) * 64 * (size_t)p.tiles));
   // chain slots are read as "Xbar" for inactive levels never; but slot 1 of every bucket is
@@ -1167,12 +1500,11 @@ int fit_large_forward_only(const cherry_fit_args& a, double* P_out, cudaStream_t
 }
 
 static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double* P_out) {
-  Plan p;
-  int rc = check_large(a, p);
+  int rc = check_large(a);
   if (rc) return rc;
   if ((rc = ensure_gemm_attr())) return rc;
   char* base = reinterpret_cast<char*>(a.workspace);
-  make_plan(p, a.S, a.K, base);  // host-side group table (cheap); device copies were uploaded by prepare
+  const Plan& p = get_plan(a.S, a.K, base);  // host-side tables; the device copies were uploaded by prepare
   LargeScalars* sc = reinterpret_cast<LargeScalars*>(base + p.off_scalars);
   int* s_arr = reinterpret_cast<int*>(base + p.off_s);
   double* tau = reinterpret_cast<double*>(base + p.off_tau);
@@ -1190,12 +1522,39 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   build_B_kernel<<<(p.Sp + 7) / 8, EW_THREADS, 0, stream>>>(a.Q, a.S, p.Sp, P, sc);
   CHERRY_LAUNCH_CHECK("build_B_kernel");
   SqSchedule* sched = reinterpret_cast<SqSchedule*>(base + p.off_sched);
-  coef_kernel<<<1, 256, 0, stream>>>(a.t, a.K, sc, s_arr, w, tau, a.status_flag, sched, p.tiles,
-                                     (KGROUPS == 1 ? 2 : 1) * sm_count());
+  int* df_state_fwd = reinterpret_cast<int*>(base + p.df_fwd.off_state);
+  int* df_state_bwd = reinterpret_cast<int*>(base + p.df_bwd.off_state);
+  int* deg_arr = reinterpret_cast<int*>(base + p.off_deg);
+  static const bool full_degree = getenv("CHERRY_FIT_FULL_DEGREE") != nullptr;  // A/B switch: round-1 Taylor pass
+  coef_kernel<<<1, 256, 0, stream>>>(a.t, a.K, sc, s_arr, deg_arr, w, tau, a.status_flag, sched, p.tiles,
+                                     (KGROUPS == 1 ? 2 : 1) * sm_count(), df_state_fwd,
+                                     (int)df_state_ints(p.df_fwd.n_mats, p.tiles, (int)p.df_fwd.groups.size()),
+                                     df_state_bwd,
+                                     (int)df_state_ints(p.df_bwd.n_mats, p.tiles, (int)p.df_bwd.groups.size()),
+                                     full_degree ? 1 : 0);
   CHERRY_LAUNCH_CHECK("coef_kernel");
   mark("build_B+coef", stream);
-  for (const Group& g : p.pow_fwd)
-    if ((rc = launch_group(p, g, base, stream))) return rc;
+  static const bool level_launch = getenv("CHERRY_FIT_LEVEL_LAUNCH") != nullptr;  // A/B switch: round-1 schedule
+  const size_t gemm_smem = (size_t)NSTAGE * 2 * TILE_ELEMS * sizeof(double);
+  static const int ctas_per_sm = getenv("CHERRY_FIT_CTAS_PER_SM") ? atoi(getenv("CHERRY_FIT_CTAS_PER_SM")) : 2;
+  const int persistent_grid = (KGROUPS == 1 ? ctas_per_sm : 1) * sm_count();
+  auto launch_chain = [&](const DfList& L, int* state, const char* name) -> int {
+    long long* prof = nullptr;
+    if (g_timeline && persistent_grid <= 1024)
+      prof = reinterpret_cast<long long*>(base + p.off_prof) + (&L == &p.df_bwd ? 8 * 1024 : 0);
+    chain_dataflow_kernel<<<persistent_grid, GEMM_THREADS, gemm_smem, stream>>>(
+        reinterpret_cast<const DfItem*>(base + L.off_items), reinterpret_cast<const DfGroup*>(base + L.off_groups),
+        (int)L.items.size(), state, L.n_mats, p.Sp, reinterpret_cast<double*>(base + p.off_partial), a.status_flag,
+        prof);
+    CHERRY_LAUNCH_CHECK(name);
+    return 0;
+  };
+  if (level_launch) {
+    for (const Group& g : p.pow_fwd)
+      if ((rc = launch_group(p, g, base, stream))) return rc;
+  } else if ((rc = launch_chain(p.df_fwd, df_state_fwd, "chain_dataflow_kernel<fwd>"))) {
+    return rc;
+  }
   mark("powers_fwd", stream);
   static bool ew_attr[64] = {false};
   {
@@ -1212,9 +1571,9 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   const bool fused = (P_out == nullptr) && !unfused;
   double* fused_partial = loss_partial + (size_t)a.K * p.loss_blocks;
   if (fused) {
-    const size_t fsmem = wsmem + 2 * sizeof(int) * a.K;
-    taylor_fused_kernel<<<eb, EW_THREADS, fsmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, s_arr, a.C, X0, Pbar,
-                                                           fused_partial);
+    const size_t fsmem = wsmem + 3 * sizeof(int) * a.K;
+    taylor_fused_kernel<<<eb, EW_THREADS, fsmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, s_arr, deg_arr, a.C, X0,
+                                                           Pbar, fused_partial);
     CHERRY_LAUNCH_CHECK("taylor_fused_kernel");
   } else {
     poly_eval_kernel<<<eb, EW_THREADS, wsmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, X0);
@@ -1222,8 +1581,6 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   }
   mark("taylor_fused", stream);
   static const bool level_sync = getenv("CHERRY_FIT_LEVEL_SYNC") != nullptr;  // A/B switch
-  const size_t gemm_smem = (size_t)NSTAGE * 2 * TILE_ELEMS * sizeof(double);
-  const int persistent_grid = (KGROUPS == 1 ? 2 : 1) * sm_count();  // all CTAs co-resident
   if (level_sync) {
     for (const Group& g : p.sq_fwd)
       if ((rc = launch_group(p, g, base, stream))) return rc;
@@ -1261,8 +1618,12 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
                                                          fused ? 1 : 0);
   CHERRY_LAUNCH_CHECK("accumulate_M_kernel");
   mark("accumulate_M", stream);
-  for (const Group& g : p.pow_bwd)
-    if ((rc = launch_group(p, g, base, stream))) return rc;
+  if (level_launch) {
+    for (const Group& g : p.pow_bwd)
+      if ((rc = launch_group(p, g, base, stream))) return rc;
+  } else if ((rc = launch_chain(p.df_bwd, df_state_bwd, "chain_dataflow_kernel<bwd>"))) {
+    return rc;
+  }
   mark("powers_bwd", stream);
   unpad_kernel<<<(a.S * a.S + 255) / 256, 256, 0, stream>>>(Pbar, a.S, p.Sp, a.dQ_part);
   CHERRY_LAUNCH_CHECK("unpad_kernel");
@@ -1276,11 +1637,35 @@ int fit_large_timeline(const cherry_fit_args& a, cudaStream_t stream) {
   for (int i = 0; i < Timeline::kMax; ++i) CHERRY_CUDA(cudaEventCreate(&tl.ev[i]));
   int rc = fit_large_impl(a, stream, nullptr);  // warm
   if (rc) return rc;
+  const Plan& pl = get_plan(a.S, a.K, nullptr);
+  char* wbase = reinterpret_cast<char*>(a.workspace);
+  CHERRY_CUDA(cudaMemsetAsync(wbase + pl.off_prof, 0, sizeof(long long) * 8 * 2 * 1024, stream));
   g_timeline = &tl;
   rc = fit_large_impl(a, stream, nullptr);
   g_timeline = nullptr;
   if (rc) return rc;
   CHERRY_CUDA(cudaStreamSynchronize(stream));
+  {
+    std::vector<long long> prof(8 * 2 * 1024);
+    CHERRY_CUDA(cudaMemcpy(prof.data(), wbase + pl.off_prof, prof.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    const char* names[7] = {"dequeue", "operand-wait", "product", "arrive", "version-wait", "reduce", "publish"};
+    for (int which = 0; which < 2; ++which) {
+      long long sum[8] = {0}, mx_items = 0;
+      int ctas = 0;
+      for (int b = 0; b < 1024; ++b) {
+        const long long* r = prof.data() + (size_t)which * 8 * 1024 + b * 8;
+        if (r[7] == 0) continue;
+        ++ctas;
+        for (int k = 0; k < 8; ++k) sum[k] += r[k];
+        if (r[7] > mx_items) mx_items = r[7];
+      }
+      if (!ctas) continue;
+      fprintf(stderr, "[chain %s] %d CTAs, %lld items (max %lld per CTA); mean us per CTA:", which ? "bwd" : "fwd", ctas,
+              sum[7], mx_items);
+      for (int k = 0; k < 7; ++k) fprintf(stderr, " %s %.1f", names[k], sum[k] * 1e-3 / ctas);
+      fprintf(stderr, "\n");
+    }
+  }
   float total = 0.f;
   for (int i = 1; i < tl.n; ++i) {
     float ms = 0.f;
@@ -1338,9 +1723,9 @@ size_t gemm_desc_bytes(int batch) {
 
 // Host copy of the per-bucket squaring counts of the most recent evaluation (synchronises).
 int fit_large_read_schedule(const cherry_fit_args& a, int* s_out, double* mu_out) {
-  Plan p;
-  int rc = check_large(a, p);
+  int rc = check_large(a);
   if (rc) return rc;
+  const Plan& p = get_plan(a.S, a.K, nullptr);
   char* base = reinterpret_cast<char*>(a.workspace);
   CHERRY_CUDA(cudaDeviceSynchronize());
   CHERRY_CUDA(cudaMemcpy(s_out, base + p.off_s, sizeof(int) * a.K, cudaMemcpyDeviceToHost));
@@ -1353,9 +1738,9 @@ int fit_large_read_schedule(const cherry_fit_args& a, int* s_out, double* mu_out
 }
 
 int fit_large_update(const cherry_fit_args& a, int mode, cudaStream_t stream, const double* reduced) {
-  Plan p;
-  int rc = check_large(a, p);
+  int rc = check_large(a);
   if (rc) return rc;
+  const Plan& p = get_plan(a.S, a.K, nullptr);
   char* base = reinterpret_cast<char*>(a.workspace);
   if (mode == 0 && (rc = fit_large_prepare(a, stream))) return rc;
   LargeUpdateArgs u;
