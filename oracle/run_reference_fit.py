@@ -39,8 +39,14 @@ def main():
     import_reference()
     from cherryml.estimation import quantized_transitions_mle
 
+    # Library start-up is not the reference's cost: torch imports its compiler stack lazily the first
+    # time an optimizer is built (several seconds), CUDA creates its context and cuBLAS / cuSOLVER
+    # handles on first use.  One throw-away Adam step on a tiny matrix_exp warms all of it.
+    w = torch.zeros(4, 4, device=args.device, requires_grad=True)
+    opt = torch.optim.Adam([w], lr=0.1)
+    torch.log(torch.matrix_exp(w)).sum().backward()
+    opt.step()
     if args.device == "cuda":
-        torch.zeros(1, device="cuda")  # context creation is not the reference's cost
         torch.cuda.synchronize()
     t0 = time.perf_counter()
     quantized_transitions_mle(
