@@ -138,9 +138,23 @@ def count_raw(
     """
     lib = _lib.load()
     device = dev.msa.device
+    stream = _lib.current_stream_ptr()
+    if dev.kind == "lg" and tab is None:
+        # one call: bucket table built per tile (one coalesced load per pair), then counted
+        if out is None:
+            out = torch.zeros((K, S, S), dtype=torch.int64, device=device)
+        if dev.n_tiles:
+            scratch = torch.empty(max(1, dev.n_pairs * dev.r_pad), dtype=torch.uint8, device=device)
+            rc = lib.cherry_count_lg_fused(
+                _lib.ptr(dev.msa), _lib.ptr(dev.fams), _lib.ptr(dev.pair_a), _lib.ptr(dev.pair_b),
+                _lib.ptr(dev.pair_t), _lib.ptr(dev.pair_fam), _lib.ptr(dev.rate_vals), _lib.ptr(grid_dev),
+                dev.n_pairs, dev.r_pad, _lib.ptr(dev.aux), _lib.ptr(dev.tiles), dev.n_tiles, K, S,
+                _lib.ptr(scratch), _lib.ptr(out), stream,
+            )
+            _lib.check(rc, "cherry_count_lg_fused")
+        return out
     if tab is None:
         tab = build_bucket_table(dev, grid_dev, K)
-    stream = _lib.current_stream_ptr()
     if dev.kind == "lg":
         if out is None:
             out = torch.zeros((K, S, S), dtype=torch.int64, device=device)

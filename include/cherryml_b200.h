@@ -112,6 +112,20 @@ int cherry_count_lg(const uint8_t* msa, const cherry_fam_desc* fams, const int32
                     const uint16_t* group_cat, const cherry_tile* tiles, int n_tiles, int K,
                     int S, unsigned long long* counts, void* stream);
 
+/* cherry_build_bucket_table + cherry_count_lg in one call for batches that come with tiles: the
+ * bucket table is built one CTA per TILE (a tile's pairs share a family, so the family's rate values
+ * are read once per CTA and a pair costs one coalesced load instead of the pair -> family -> rates
+ * chain of cherry_build_bucket_table: 0.17 ms -> see DESIGN.md for 8.4 M pairs), then counted.  Same
+ * results, bit for bit.  Every pair must belong to exactly one tile (pair_fam is implied by the tiles).
+ * tab_scratch: n_pairs * r_pad bytes of device scratch (the bucket table; valid after the call).
+ * Replaces the per-site quantisation inside the reference's loop
+ * (counting/_count_transitions.cpp:295-307 called from :368-381). */
+int cherry_count_lg_fused(const uint8_t* msa, const cherry_fam_desc* fams, const int32_t* pair_a,
+                          const int32_t* pair_b, const double* pair_t, const int32_t* pair_fam,
+                          const double* rate_vals, const double* grid, int64_t n_pairs, int r_pad,
+                          const uint16_t* group_cat, const cherry_tile* tiles, int n_tiles, int K, int S,
+                          uint8_t* tab_scratch, unsigned long long* counts, void* stream);
+
 /* One sorted pair as the co-transition kernel's producer reads it.  16 bytes. */
 typedef struct cherry_co_rec {
   int64_t off_a;     /* byte offset of the pair's row a in the residue buffer */
