@@ -110,19 +110,60 @@ __global__ void bucket_table_kernel(const double* __restrict__ pair_t,
   }
 }
 
+// Decision boundaries of the quantisation: for every pair of neighbouring grid points (left, right) the
+// reference's predicate  t/left - 1 < right/t - 1  (IEEE division and subtraction, utils.py:35-56 ==
+// _count_transitions.cpp:295-307) is monotone in t -- the rounded quotients are monotone -- so there is ONE
+// smallest double bnd in (left, right] for which it is false, and  bucket(t) = #{i : bnd[i] <= t}.  The
+// boundary is found by bisection on the bit patterns of the doubles with the predicate itself, so the
+// result is the reference's by construction; quantising a value is then a float guess and two or three
+// double compares instead of ~110 instructions.  Grids with repeated or non-positive points keep the
+// general path (flag).
+__device__ __forceinline__ double quantization_boundary(double left, double right) {
+  long long lo = __double_as_longlong(left), hi = __double_as_longlong(right);  // predicate true at lo, false at hi
+  while (hi - lo > 1) {
+    const long long mid = lo + ((hi - lo) >> 1);
+    const double t = __longlong_as_double(mid);
+    const double el = __dsub_rn(__ddiv_rn(t, left), 1.0), er = __dsub_rn(__ddiv_rn(right, t), 1.0);
+    if (el < er) lo = mid; else hi = mid;
+  }
+  return __longlong_as_double(hi);
+}
+__device__ __forceinline__ int quantize_by_boundaries(double t, const double* __restrict__ q, const double* __restrict__ bnd,
+                                                      int K, float log2_q0, float inv_log2_step) {
+  if (t < q[0] || t > q[K - 1]) return -1;
+  int b = t == t ? (int)((__log2f((float)t) - log2_q0) * inv_log2_step) : 0;
+  b = max(0, min(K - 1, b));
+  while (b > 0 && !(bnd[b - 1] <= t)) --b;
+  while (b < K - 1 && bnd[b] <= t) ++b;
+  return b;
+}
+
 // The same table, one CTA per tile: a tile's pairs belong to ONE family, so the family's rate values are
-// read once per CTA and a thread's only dependent load is its pair's branch length (coalesced).  The
-// per-pair kernel above walks pair -> family -> rate values for every pair (three dependent loads: 170 us
-// for 8.4 M pairs, latency bound).
+// read once per CTA and a thread's only dependent load is its pair's branch length (coalesced); values are
+// quantised against the precomputed decision boundaries.
 __global__ void __launch_bounds__(256)
 bucket_table_tiles_kernel(const double* __restrict__ pair_t, const cherry_tile* __restrict__ tiles,
                           const cherry_fam_desc* __restrict__ fams, const double* __restrict__ rate_vals,
                           const double* __restrict__ grid, int K, int n_tiles, int r_pad,
                           uint8_t* __restrict__ tab) {
-  extern __shared__ double sgrid[];  // [K] grid, then [r_pad] rate values
-  double* srate = sgrid + K;
+  extern __shared__ double sgrid[];  // [K] grid, [K] boundaries, [r_pad] rate values
+  __shared__ int general;
+  double* sbnd = sgrid + K;
+  double* srate = sbnd + K;
+  if (threadIdx.x == 0) general = 0;
   for (int i = threadIdx.x; i < K; i += blockDim.x) sgrid[i] = grid[i];
   __syncthreads();
+  for (int i = threadIdx.x; i < K - 1; i += blockDim.x) {
+    const double left = sgrid[i], right = sgrid[i + 1];
+    if (!(left > 0.0) || !(right > left) || !(right < 1e300)) {
+      general = 1;
+      sbnd[i] = right;
+    } else {
+      sbnd[i] = quantization_boundary(left, right);
+    }
+  }
+  __syncthreads();
+  const bool use_general = general != 0;
   const float log2_q0 = sgrid[0] > 0.0 ? log2f((float)sgrid[0]) : 0.0f;
   const float span = K > 1 && sgrid[0] > 0.0 ? log2f((float)(sgrid[K - 1] / sgrid[0])) : 0.0f;
   const float inv_log2_step = span > 0.0f ? (float)(K - 1) / span : 0.0f;
@@ -151,7 +192,9 @@ bucket_table_tiles_kernel(const double* __restrict__ pair_t, const cherry_tile* 
           for (int k = 0; k < 4; ++k) {
             uint32_t out = CHERRY_NO_BUCKET;
             if (r0 + k < n_rates) {
-              const int b = quantize_bucket_guess(__dmul_rn(t[u], srate[r0 + k]), sgrid, K, log2_q0, inv_log2_step);
+              const double x = __dmul_rn(t[u], srate[r0 + k]);
+              const int b = use_general ? quantize_bucket_guess(x, sgrid, K, log2_q0, inv_log2_step)
+                                        : quantize_by_boundaries(x, sgrid, sbnd, K, log2_q0, inv_log2_step);
               if (b >= 0) out = (uint32_t)b;
             }
             word |= out << (8 * k);
@@ -506,9 +549,9 @@ int cherry_count_lg_fused(const uint8_t* msa, const cherry_fam_desc* fams, const
   (void)pair_fam;
   {
     int blocks = n_tiles;
-    const int cap = cherry::sm_count() * 16;
+    const int cap = cherry::sm_count() * 8;  // one residency: every CTA computes the boundaries once
     if (blocks > cap) blocks = cap;
-    bucket_table_tiles_kernel<<<blocks, 256, (K + r_pad) * sizeof(double), (cudaStream_t)stream>>>(
+    bucket_table_tiles_kernel<<<blocks, 256, (2 * K + r_pad) * sizeof(double), (cudaStream_t)stream>>>(
         pair_t, tiles, fams, rate_vals, grid, K, n_tiles, r_pad, tab_scratch);
     CHERRY_LAUNCH_CHECK("bucket_table_tiles_kernel");
   }

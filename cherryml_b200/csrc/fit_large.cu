@@ -41,6 +41,8 @@ constexpr int LD_ROW = 20;        // tile stored [80][16]: k contiguous
 constexpr int LD_COL = 84;        // tile stored [16][80]: m (or n) contiguous
 constexpr int TILE_ELEMS = BT * LD_ROW;  // 1600 >= 16 * 84
 constexpr int EW_THREADS = 256;
+constexpr int kTaylorInterleave = 2;  // buckets whose dependent chains a thread of the fused Taylor pass interleaves
+constexpr int kTaylorStages = 16;  // count loads in flight per thread of the fused Taylor pass
 static_assert(kDeg % 4 == 0, "the elementwise kernels skip Taylor terms in blocks of four");
 
 struct GemmTerm {
@@ -413,33 +415,40 @@ squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__
 // and the CTA that arrives last at a group adds the partial tiles in slice order (deterministic),
 // applies the update to C and publishes the tile's new version.  Items are dequeued in dependency
 // order and every dequeued item is held by a running CTA, so the waits cannot deadlock.
-struct DfItem {
-  const double* A;
-  const double* B;
-  int ta, tb;
-  int k0, n_chunks;   // K range [k0, k0 + BK * n_chunks)
-  int group, slice;
-  int a_mat, a_ver;   // wait until every tile of A this slice reads has version >= a_ver (a_mat < 0: no wait)
-  int b_mat, b_ver;
-};
 struct DfGroup {
   double* C;
   int m0, n0;
   int n_slices, accumulate;
   int c_mat, need_ver;  // the update applies to version need_ver of the C tile and publishes need_ver + 1
-  int partial_off, pad;
+  int partial_off, n_slabs;
 };
+struct alignas(16) DfItem {  // everything a CTA needs comes with ONE dependent load after the queue ticket
+  const double* A;
+  const double* B;
+  int ta, tb;
+  int k0, n_chunks;   // K range [k0, k0 + BK * n_chunks)
+  int group, slice;   // kind 0: K slice of the group's product; kind 1: row slab of the group's reduction
+  int a_mat, a_ver;   // wait until every tile of A this slice reads has version >= a_ver (a_mat < 0: no wait)
+  int b_mat, b_ver;
+  int kind, pad;
+  DfGroup g;          // copy of the item's group
+};
+static_assert(sizeof(DfItem) % 16 == 0, "DfItem layout");
 struct DfList {  // host-side description of one chain launch
   std::vector<DfItem> items;
   std::vector<DfGroup> groups;
+  std::vector<int> pending;  // groups whose reduction items have not been emitted yet
   int n_mats = 0;
   size_t off_items = 0, off_groups = 0, off_state = 0;  // workspace offsets
   int partial_tiles = 0;
 };
-// device state of a list: int queue; int pad[3]; int ver[n_mats * tiles]; int arrive[n_groups]
+constexpr int kDfSlabs = 5;      // row slabs of a tile's reduction (16 rows each), one work item per slab
+// device state of a list: int queue; int pad[3]; int ver[n_mats * tiles * kDfSlabs]; int arrive[n_groups]
+// (a version per ROW SLAB of a tile: a slab's reduction publishes with a plain store, no ticket counter)
 __host__ __device__ inline size_t df_state_ints(int n_mats, int tiles, int n_groups) {
-  return 4 + (size_t)n_mats * tiles + (size_t)n_groups;
+  return 4 + (size_t)n_mats * tiles * kDfSlabs + (size_t)n_groups;
 }
+constexpr int kDfReduceLag = 60; // groups between a product and its reduction items in the queue (~ one turnover of the grid)
 
 __device__ __forceinline__ void df_wait_tile(const int* v, int target, int* status_flag) {
   unsigned spins = 0;
@@ -453,17 +462,17 @@ __device__ __forceinline__ void df_wait_tile(const int* v, int target, int* stat
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS)
-chain_dataflow_kernel(const DfItem* __restrict__ items, const DfGroup* __restrict__ groups, int n_items,
+chain_dataflow_kernel(const DfItem* __restrict__ items, int n_items, int n_groups,
                       int* __restrict__ state, int n_mats, int Sp, double* __restrict__ partial,
                       int* __restrict__ status_flag, long long* __restrict__ prof) {
   extern __shared__ double smem[];
-  __shared__ int s_item, s_last;
+  __shared__ int s_item;
   const int tiles_n = Sp / BT, tiles = tiles_n * tiles_n;
   int* queue = state;
   int* ver = state + 4;
-  int* arrive = ver + n_mats * tiles;
+  int* arrive = ver + n_mats * tiles * kDfSlabs;
   // optional phase profile (CHERRY_FIT_TIMELINE): ns per CTA in {dequeue, operand wait, product,
-  // arrive, version wait, reduce, publish}, items taken
+  // arrive, reduce wait, reduce, publish}, items taken
   long long t_prev = 0;
   auto tick = [&](int phase) {
     if (prof != nullptr && threadIdx.x == 0) {
@@ -474,94 +483,124 @@ chain_dataflow_kernel(const DfItem* __restrict__ items, const DfGroup* __restric
     }
   };
   tick(-1);
+  int next = -1;  // thread 0: ticket taken early (its latency hides behind the fence that ends an item)
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) s_item = atomicAdd(queue, 1);
+    if (threadIdx.x == 0) {
+      s_item = next >= 0 ? next : atomicAdd(queue, 1);
+      next = -1;
+    }
     __syncthreads();
     const int idx = s_item;
     if (idx >= n_items) return;
     const DfItem it = items[idx];
-    const DfGroup g = groups[it.group];
+    const DfGroup& g = it.g;
     const int ti = g.m0 / BT, tj = g.n0 / BT;
     if (prof != nullptr && threadIdx.x == 0) prof[blockIdx.x * 8 + 7] += 1;
     tick(0);
-    if (threadIdx.x < 2) {  // thread 0 waits for A's tiles, thread 1 for B's
-      const int mat = threadIdx.x == 0 ? it.a_mat : it.b_mat;
-      if (mat >= 0) {
-        const int target = threadIdx.x == 0 ? it.a_ver : it.b_ver;
-        const int kz0 = it.k0 / BT, kz1 = (it.k0 + it.n_chunks * BK - 1) / BT;
-        for (int kz = kz0; kz <= kz1; ++kz) {
-          int tile;
-          if (threadIdx.x == 0) tile = it.ta ? kz * tiles_n + ti : ti * tiles_n + kz;
-          else tile = it.tb ? tj * tiles_n + kz : kz * tiles_n + tj;
-          df_wait_tile(ver + mat * tiles + tile, target, status_flag);
+    if (it.kind == 0) {
+      // ---- one K slice of the group's product
+      if (threadIdx.x < 2 * kDfSlabs) {  // threads 0-4 wait for the slabs of A's tiles, 5-9 for B's
+        const bool isA = threadIdx.x < kDfSlabs;
+        const int slab = threadIdx.x - (isA ? 0 : kDfSlabs);
+        const int mat = isA ? it.a_mat : it.b_mat;
+        if (mat >= 0) {
+          const int target = isA ? it.a_ver : it.b_ver;
+          const int kz0 = it.k0 / BT, kz1 = (it.k0 + it.n_chunks * BK - 1) / BT;
+          for (int kz = kz0; kz <= kz1; ++kz) {
+            int tile;
+            if (isA) tile = it.ta ? kz * tiles_n + ti : ti * tiles_n + kz;
+            else tile = it.tb ? tj * tiles_n + kz : kz * tiles_n + tj;
+            df_wait_tile(ver + (mat * tiles + tile) * kDfSlabs + slab, target, status_flag);
+          }
+          __threadfence();
         }
-        __threadfence();
       }
+      __syncthreads();
+      tick(1);
+      const GemmTerm t0{it.A, it.B, it.ta, it.tb};
+      const bool direct = (g.n_slices == 1) && !g.accumulate;
+      const int c0 = it.k0 / BK;
+      if (direct) {
+        gemm_tile([&](int) { return t0; }, Sp, g.m0, g.n0, c0, c0 + it.n_chunks, smem, g.C, false);
+        tick(2);
+        if (threadIdx.x == 0) next = atomicAdd(queue, 1);
+        if (g.c_mat >= 0) {
+          __threadfence();  // every thread publishes its part of the tile before the version moves
+          __syncthreads();
+          if (threadIdx.x < kDfSlabs)
+            *reinterpret_cast<volatile int*>(ver + (g.c_mat * tiles + ti * tiles_n + tj) * kDfSlabs + threadIdx.x) = g.need_ver + 1;
+          tick(6);
+        }
+      } else {
+        double* ptile = partial + (size_t)(g.partial_off + it.slice) * (BT * BT);
+        gemm_tile([&](int) { return t0; }, Sp, g.m0, g.n0, c0, c0 + it.n_chunks, smem,
+                  ptile - ((ptrdiff_t)g.m0 * BT + g.n0), false, BT);
+        tick(2);
+        if (threadIdx.x == 0) next = atomicAdd(queue, 1);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(arrive + it.group, 1);  // no return value needed: a reduction
+        tick(3);
+      }
+      continue;
+    }
+    // ---- one row slab of the group's reduction: C = (accumulate ? C : 0) + sum of the partial tiles, slices
+    // in order (deterministic).  The items of a reduction sit in the queue behind the group's products, so
+    // the wait below cannot deadlock; every slab publishes its own version of the tile.
+    int* my_ver = ver + (g.c_mat * tiles + ti * tiles_n + tj) * kDfSlabs + it.slice;
+    if (threadIdx.x == 0) {
+      df_wait_tile(arrive + it.group, g.n_slices, status_flag);
+      if (g.accumulate && g.need_ver > 0) df_wait_tile(my_ver, g.need_ver, status_flag);
+      __threadfence();
     }
     __syncthreads();
-    tick(1);
-    const GemmTerm t0{it.A, it.B, it.ta, it.tb};
-    const bool direct = (g.n_slices == 1) && !g.accumulate;
-    const int c0 = it.k0 / BK;
-    if (direct) {
-      gemm_tile([&](int) { return t0; }, Sp, g.m0, g.n0, c0, c0 + it.n_chunks, smem, g.C, false);
-    } else {
-      double* ptile = partial + (size_t)(g.partial_off + it.slice) * (BT * BT);
-      gemm_tile([&](int) { return t0; }, Sp, g.m0, g.n0, c0, c0 + it.n_chunks, smem,
-                ptile - ((ptrdiff_t)g.m0 * BT + g.n0), false, BT);
-      tick(2);
-      __threadfence();
-      __syncthreads();
-      if (threadIdx.x == 0) s_last = (atomicAdd(arrive + it.group, 1) == g.n_slices - 1);
-      __syncthreads();
-      tick(3);
-      if (!s_last) continue;
-      if (threadIdx.x == 0) {
-        if (g.accumulate && g.need_ver > 0)
-          df_wait_tile(ver + g.c_mat * tiles + ti * tiles_n + tj, g.need_ver, status_flag);
-        __threadfence();
-      }
-      __syncthreads();
-      tick(4);
-      // every thread owns NQ double2 elements of the tile; per slice all NQ loads are in flight at once
-      // (a loop over the slices per element would serialise NQ * n_slices L2 round trips)
+    tick(4);
+    {
+      const int r_begin = BT * it.slice / g.n_slabs, r_end = BT * (it.slice + 1) / g.n_slabs;
+      const int n_el = (r_end - r_begin) * (BT / 2);  // double2 elements of the slab
       const double* pb = partial + (size_t)g.partial_off * (BT * BT);
-      constexpr int NQ = BT * BT / 2 / GEMM_THREADS;
-      static_assert(NQ * GEMM_THREADS * 2 == BT * BT, "tile elements must divide evenly over the CTA");
-      double2 v[NQ];
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const int e = threadIdx.x + q * GEMM_THREADS;
-        const int r = e / (BT / 2), c2 = (e - r * (BT / 2)) * 2;
-        v[q] = g.accumulate ? __ldcg(reinterpret_cast<const double2*>(g.C + (size_t)(g.m0 + r) * Sp + g.n0 + c2))
-                            : make_double2(0.0, 0.0);
-      }
-      for (int z = 0; z < g.n_slices; ++z) {
-        const double2* pz = reinterpret_cast<const double2*>(pb + (size_t)z * (BT * BT));
-        double2 t[NQ];
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) t[q] = __ldcg(pz + threadIdx.x + q * GEMM_THREADS);
+      constexpr int NQ = 5;  // 16 rows x 40 double2 over 128 threads
+      for (int e0 = threadIdx.x; e0 < n_el; e0 += NQ * GEMM_THREADS) {
+        double2 v[NQ];
+        int off[NQ];
+        bool on[NQ];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-          v[q].x += t[q].x;
-          v[q].y += t[q].y;
+          const int e = e0 + q * GEMM_THREADS;
+          on[q] = e < n_el;
+          const int r = r_begin + (on[q] ? e / (BT / 2) : 0), c2 = (on[q] ? e % (BT / 2) : 0) * 2;
+          off[q] = r * BT + c2;
+          v[q] = (g.accumulate && on[q])
+                     ? __ldcg(reinterpret_cast<const double2*>(g.C + (size_t)(g.m0 + r) * Sp + g.n0 + c2))
+                     : make_double2(0.0, 0.0);
         }
-      }
+        for (int z = 0; z < g.n_slices; ++z) {
+          const double* pz = pb + (size_t)z * (BT * BT);
+          double2 t[NQ];
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const int e = threadIdx.x + q * GEMM_THREADS;
-        const int r = e / (BT / 2), c2 = (e - r * (BT / 2)) * 2;
-        *reinterpret_cast<double2*>(g.C + (size_t)(g.m0 + r) * Sp + g.n0 + c2) = v[q];
+          for (int q = 0; q < NQ; ++q)
+            t[q] = on[q] ? __ldcg(reinterpret_cast<const double2*>(pz + off[q])) : make_double2(0.0, 0.0);
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            v[q].x += t[q].x;
+            v[q].y += t[q].y;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+          if (on[q]) {
+            const int r = off[q] / BT, c2 = off[q] - r * BT;
+            *reinterpret_cast<double2*>(g.C + (size_t)(g.m0 + r) * Sp + g.n0 + c2) = v[q];
+          }
       }
-      tick(5);
     }
-    if (g.c_mat >= 0) {
-      __threadfence();  // every thread publishes its part of the tile before the version moves
-      __syncthreads();
-      if (threadIdx.x == 0) atomicExch(ver + g.c_mat * tiles + ti * tiles_n + tj, g.need_ver + 1);
-      tick(6);
-    }
+    tick(5);
+    if (threadIdx.x == 0) next = atomicAdd(queue, 1);
+    __threadfence();  // every thread publishes its part of the slab before the version moves
+    __syncthreads();
+    if (threadIdx.x == 0 && g.c_mat >= 0) *reinterpret_cast<volatile int*>(my_ver) = g.need_ver + 1;
+    tick(6);
   }
 }
 
@@ -625,7 +664,7 @@ __global__ void coef_kernel(const double* __restrict__ t, int K, LargeScalars* _
                             double* __restrict__ tau_arr,
                             int* __restrict__ status_flag, SqSchedule* __restrict__ sched, int tiles,
                             int n_ctas, int* __restrict__ df_state_fwd, int n_fwd_ints,
-                            int* __restrict__ df_state_bwd, int n_bwd_ints, int full_degree) {
+                            int* __restrict__ df_state_bwd, int n_bwd_ints, int full_degree, int sq_ksplit_max) {
   // the power chains' queues, tile versions and arrival counters start every epoch at zero
   for (int i = threadIdx.x; i < n_fwd_ints; i += blockDim.x) df_state_fwd[i] = 0;
   for (int i = threadIdx.x; i < n_bwd_ints; i += blockDim.x) df_state_bwd[i] = 0;
@@ -675,6 +714,16 @@ __global__ void coef_kernel(const double* __restrict__ t, int K, LargeScalars* _
   __shared__ int ss[256], level_n[kSStore];
   for (int k = threadIdx.x; k < K; k += blockDim.x) ss[k] = s_arr[k];
   __syncthreads();
+  if (threadIdx.x == kSStore) {  // bucket lists of the fused Taylor pass: without / with squarings, ascending
+    int* zl = deg_arr + K;
+    int* ql = zl + K;
+    int nz = 0, nq = 0;
+    for (int k = 0; k < K; ++k) {
+      if (ss[k] == 0) zl[nz++] = k; else ql[nq++] = k;
+    }
+    ql[K] = nz;
+    ql[K + 1] = nq;
+  }
   if (threadIdx.x < kSStore) {  // one thread per level builds that level's list
     const int lvl = threadIdx.x;
     int n = 0;
@@ -702,8 +751,10 @@ __global__ void coef_kernel(const double* __restrict__ t, int K, LargeScalars* _
     // the partial buffer: one slot per (active bucket, z))
     int ks = 1;
     if (level_n[0] > 0) {
-      ks = n_ctas / (level_n[0] * tiles);
-      if (ks > 4) ks = 4;
+      // about 2.5 waves of work items in the widest level (one K=400 tile is 60-100 us on a CTA: with
+      // 1.1 waves of them the second wave runs nearly empty)
+      ks = (5 * n_ctas / 2 + level_n[0] * tiles - 1) / (level_n[0] * tiles);
+      if (ks > sq_ksplit_max) ks = sq_ksplit_max;
       if (ks * level_n[0] > kSqPartialSlots) ks = kSqPartialSlots / level_n[0];
       if (ks < 1) ks = 1;
     }
@@ -735,21 +786,58 @@ poly_eval_kernel(const double* __restrict__ powers, size_t n_p, int S, int Sp, i
   }
 }
 
-// One (element, bucket) of the fused Taylor pass with the first D Taylor terms: value, loss term,
-// and the bucket's contribution to the power adjoints.
-template <int D>
-__device__ __forceinline__ void taylor_term(const double* __restrict__ wk, const double (&pw)[kDeg], double (&acc)[kDeg],
-                                            double c, double diag, double& part) {
-  double v = wk[0] * diag;
+// One (element, bucket) of the fused Taylor pass with the first D Taylor terms: value, loss term, and the
+// bucket's contribution to the power adjoints.  LPE lanes share an element: lane h owns the powers
+// j = h, h + LPE, ... (NP = kDeg / LPE of them, in pw / acc), the value is summed over the lanes of the element.
+template <int D, int LPE>
+__device__ __forceinline__ void taylor_term(const double* __restrict__ wk, const double (&pw)[kDeg / LPE],
+                                            double (&acc)[kDeg / LPE], double c, double diag, int h, double& part) {
+  double v = h == 0 ? wk[0] * diag : 0.0;
 #pragma unroll
-  for (int j = 0; j < D; ++j) v = fma(wk[j + 1], pw[j], v);
-  part -= c * log(v);
-  const double g = -c / v;
+  for (int i = 0; i < D / LPE; ++i) v = fma(wk[i * LPE + h + 1], pw[i], v);
 #pragma unroll
-  for (int j = 0; j < D; ++j) acc[j] = fma(wk[j + 1], g, acc[j]);
+  for (int o = 1; o < LPE; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const bool live = c != 0.0;  // with LPE > 1 the whole warp comes here if any of its elements has a count
+  if (live && h == 0) part -= c * log(v);
+  const double g = live ? -c / v : 0.0;
+#pragma unroll
+  for (int i = 0; i < D / LPE; ++i) acc[i] = fma(wk[i * LPE + h + 1], g, acc[i]);
 }
 
-// Fused Taylor pass (training): one thread per matrix element, the m power values in registers.
+// Several buckets at once (LPE = 1): the polynomial, the logarithm and the quotient of one (element, bucket) are
+// ONE dependent chain of ~60 FP64 operations, and the pass runs 8 warps per SM (178 registers), so a bucket at a
+// time leaves the FP64 pipe idle for most of every operation's latency (issue slots 25 % busy, r02_taylor_fused_v1).
+// kTaylorInterleave independent chains interleave (four of them spill: 255 registers).  The weights beyond a bucket's degree are zero, so the four share the
+// largest degree of the group (buckets are visited in ascending time = ascending degree).
+template <int D, int U>
+__device__ __forceinline__ void taylor_term_n(const double* const (&w)[U], const double (&pw)[kDeg], double (&acc)[kDeg],
+                                              const double (&c)[U], double diag, double& part) {
+  double v[U], g[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) v[u] = w[u][0] * diag;
+#pragma unroll
+  for (int j = 0; j < D; ++j)
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = fma(w[u][j + 1], pw[j], v[u]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    // c == 0: nothing is added (and padding elements, where v == 0, must not inject 0 * inf)
+    const double l = log(v[u]), q = -c[u] / v[u];
+    g[u] = c[u] != 0.0 ? q : 0.0;
+    part -= c[u] != 0.0 ? c[u] * l : 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    double x = acc[j];
+#pragma unroll
+    for (int u = 0; u < U; ++u) x = fma(w[u][j + 1], g[u], x);
+    acc[j] = x;
+  }
+}
+
+// Fused Taylor pass (training): LPE lanes per matrix element, the m power values split over their registers
+// (one thread per element holds 48 doubles of state = 186 registers = one 256-thread block per SM: the pass
+// was latency bound at 12 % of the warp slots, profiles/r02_taylor_fused_v1.txt).
 //   buckets WITHOUT squarings (most of them): P_k(e) is the polynomial itself, so the loss term
 //     and the bucket's whole contribution to the power adjoints, Pbar_j(e) += w[k][j] * (-C/P),
 //     are formed on the spot -- nothing is stored per bucket, and an element with C_k(e) == 0
@@ -757,11 +845,13 @@ __device__ __forceinline__ void taylor_term(const double* __restrict__ wk, const
 //   buckets WITH squarings: X0_k(e) is stored for the squaring chain.
 // Outputs: Pbar_j (j = 1..m) initialised with the no-squaring buckets' contributions, X0 of
 // the squared buckets, one loss partial per block.
+template <int LPE, int UI>
 __global__ void __launch_bounds__(EW_THREADS)
 taylor_fused_kernel(const double* __restrict__ powers, size_t n_p, int S, int Sp, int K,
                     const double* __restrict__ w, const int* __restrict__ s_arr,
                     const int* __restrict__ deg_arr, const double* __restrict__ C, double* __restrict__ X0,
                     double* __restrict__ Pbar, double* __restrict__ loss_partial_fused) {
+  constexpr int NP = kDeg / LPE;
   extern __shared__ double sw[];  // [K][m+1] weights, then int lists
   __shared__ double red[EW_THREADS / 32];
   __shared__ int n_zero, n_sq;
@@ -769,62 +859,109 @@ taylor_fused_kernel(const double* __restrict__ powers, size_t n_p, int S, int Sp
   int* qlist = zlist + K;                                              // buckets with s > 0
   int* sdeg = qlist + K;                                               // Taylor degree per bucket
   for (int i = threadIdx.x; i < K * (kDeg + 1); i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < K; i += blockDim.x) sdeg[i] = deg_arr[i];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {  // lists built once per epoch by coef_kernel
+    sdeg[i] = deg_arr[i];
+    zlist[i] = deg_arr[K + i];
+    qlist[i] = deg_arr[2 * K + i];
+  }
   if (threadIdx.x == 0) {
-    int nz = 0, nq = 0;
-    for (int k = 0; k < K; ++k) {
-      if (s_arr[k] == 0) zlist[nz++] = k; else qlist[nq++] = k;
-    }
-    n_zero = nz;
-    n_sq = nq;
+    n_zero = deg_arr[3 * K];
+    n_sq = deg_arr[3 * K + 1];
   }
   __syncthreads();
-  const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  const bool in_range = e < n_p;
-  const size_t ee = in_range ? e : 0;
-  const int row = (int)(ee / Sp), col = (int)(ee - (size_t)row * Sp);
-  const bool real = in_range && row < S && col < S;
-  const double diag = (row == col && row < S) ? 1.0 : 0.0;
-  double pw[kDeg], acc[kDeg];
-#pragma unroll
-  for (int j = 0; j < kDeg; ++j) {
-    pw[j] = in_range ? powers[(size_t)j * n_p + ee] : 0.0;
-    acc[j] = 0.0;
-  }
+  // persistent: the weight table and the lists are staged once per CTA, the CTA walks over chunks of elements
+  const size_t n_chunks = (n_p * LPE + blockDim.x - 1) / blockDim.x;
   double part = 0.0;
-  const size_t cidx = (size_t)row * S + col;
-  const size_t SS = (size_t)S * S;
-  // ---- buckets without squarings: 4 count loads in flight
-  for (int i0 = 0; i0 < n_zero; i0 += 4) {
-    double c[4];
+  for (size_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int h = threadIdx.x & (LPE - 1);
+    const size_t e = (chunk * (size_t)blockDim.x + threadIdx.x) / LPE;
+    const bool in_range = e < n_p;
+    const size_t ee = in_range ? e : 0;
+    const int row = (int)(ee / Sp), col = (int)(ee - (size_t)row * Sp);
+    const bool real = in_range && row < S && col < S;
+    const double diag = (row == col && row < S) ? 1.0 : 0.0;
+    double pw[NP], acc[NP];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) c[u] = (real && i0 + u < n_zero) ? C[(size_t)zlist[i0 + u] * SS + cidx] : 0.0;
+    for (int i = 0; i < NP; ++i) {
+      pw[i] = in_range ? powers[(size_t)(i * LPE + h) * n_p + ee] : 0.0;
+      acc[i] = 0.0;
+    }
+    const size_t cidx = (size_t)row * S + col;
+    const size_t SS = (size_t)S * S;
+    // ---- buckets without squarings.  The pass is bound by the latency of the count loads (one 8-byte load per
+    // bucket and thread, 87 buckets): they go through a ring of kTaylorStages cp.async stages in shared memory, so
+    // that every thread keeps kTaylorStages loads in flight without holding them in registers.
+    double* ring = reinterpret_cast<double*>(sdeg + K + (K & 1));  // [kTaylorStages][EW_THREADS], 8-byte aligned
+    auto issue = [&](int i) {
+      if (real && i < n_zero) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (i % kTaylorStages) * EW_THREADS + threadIdx.x);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(C + (size_t)zlist[i] * SS + cidx));
+      }
+      cp_async_commit();
+    };
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (c[u] != 0.0) {
-        const double* wk = sw + zlist[i0 + u] * (kDeg + 1);
-        const int d = sdeg[zlist[i0 + u]];  // block-uniform: the weights beyond d are zero
-        // one uniform branch per (element, bucket) into a fully unrolled body of the bucket's degree class
-        if (d <= 8) taylor_term<8>(wk, pw, acc, c[u], diag, part);
-        else if (d <= 12) taylor_term<12>(wk, pw, acc, c[u], diag, part);
-        else if (d <= 16) taylor_term<16>(wk, pw, acc, c[u], diag, part);
-        else if (d <= 20) taylor_term<20>(wk, pw, acc, c[u], diag, part);
-        else taylor_term<24>(wk, pw, acc, c[u], diag, part);
+    for (int i = 0; i < kTaylorStages; ++i) issue(i);
+    if constexpr (LPE == 1) {
+      constexpr int U = UI;
+      for (int i = 0; i < n_zero; i += U) {
+        cp_async_wait<kTaylorStages - U>();
+        double c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          c[u] = (real && i + u < n_zero) ? ring[((i + u) % kTaylorStages) * EW_THREADS + threadIdx.x] : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) issue(i + u + kTaylorStages);  // the slots just read are this thread's own
+        bool nz = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u) nz |= c[u] != 0.0;
+        if (!__any_sync(0xffffffffu, nz)) continue;
+        const double* wu[U];
+        int d = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int k = zlist[min(i + u, n_zero - 1)];
+          wu[u] = sw + k * (kDeg + 1);
+          d = max(d, sdeg[k]);
+        }
+        if (d <= 8) taylor_term_n<8, U>(wu, pw, acc, c, diag, part);
+        else if (d <= 12) taylor_term_n<12, U>(wu, pw, acc, c, diag, part);
+        else if (d <= 16) taylor_term_n<16, U>(wu, pw, acc, c, diag, part);
+        else if (d <= 20) taylor_term_n<20, U>(wu, pw, acc, c, diag, part);
+        else taylor_term_n<24, U>(wu, pw, acc, c, diag, part);
+      }
+    } else {
+      for (int i = 0; i < n_zero; ++i) {
+        cp_async_wait<kTaylorStages - 1>();
+        const double c = real ? ring[(i % kTaylorStages) * EW_THREADS + threadIdx.x] : 0.0;
+        issue(i + kTaylorStages);  // the slot just read is this thread's own: no barrier needed
+        // the shuffles inside need every lane of the warp: the branch is warp-uniform
+        if (__any_sync(0xffffffffu, c != 0.0) != 0) {
+          const double* wk = sw + zlist[i] * (kDeg + 1);
+          const int d = sdeg[zlist[i]];  // block-uniform: the weights beyond d are zero
+          if (d <= 8) taylor_term<8, LPE>(wk, pw, acc, c, diag, h, part);
+          else if (d <= 12) taylor_term<12, LPE>(wk, pw, acc, c, diag, h, part);
+          else if (d <= 16) taylor_term<16, LPE>(wk, pw, acc, c, diag, h, part);
+          else if (d <= 20) taylor_term<20, LPE>(wk, pw, acc, c, diag, h, part);
+          else taylor_term<24, LPE>(wk, pw, acc, c, diag, h, part);
+        }
       }
     }
-  }
-  // ---- buckets with squarings: store X0
-  if (in_range) {
+    cp_async_wait<0>();
+    // ---- buckets with squarings: store X0
     for (int i = 0; i < n_sq; ++i) {
       const int k = qlist[i];
       const double* wk = sw + k * (kDeg + 1);
-      double v = wk[0] * diag;
+      double v = h == 0 ? wk[0] * diag : 0.0;
 #pragma unroll
-      for (int j = 0; j < kDeg; ++j) v = fma(wk[j + 1], pw[j], v);
-      X0[(size_t)k * n_p + e] = v;
+      for (int j = 0; j < NP; ++j) v = fma(wk[j * LPE + h + 1], pw[j], v);
+#pragma unroll
+      for (int o = 1; o < LPE; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (in_range && h == 0) X0[(size_t)k * n_p + e] = v;
     }
+    if (in_range) {
 #pragma unroll
-    for (int j = 0; j < kDeg; ++j) Pbar[(size_t)j * n_p + e] = acc[j];
+      for (int i = 0; i < NP; ++i) Pbar[(size_t)(i * LPE + h) * n_p + e] = acc[i];
+    }
   }
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
@@ -1162,10 +1299,10 @@ void make_plan(Plan& p, int S, int K, char* base) {
   p.off_sched = carve(sizeof(SqSchedule) + sizeof(int) * ((size_t)kSStore * K * 2 + (size_t)K * (kSStore + 1) +
                                                             (size_t)K + (size_t)K * p.tiles));
   p.off_s = carve(sizeof(int) * K);
-  p.off_deg = carve(sizeof(int) * K);
+  p.off_deg = carve(sizeof(int) * (3 * (size_t)K + 2));  // degrees, then the unsquared / squared bucket lists and their lengths
   p.off_tau = carve(sizeof(double) * K);
   p.off_w = carve(sizeof(double) * K * (kDeg + 1));
-  p.off_loss_partial = carve(sizeof(double) * ((size_t)K * p.loss_blocks + (p.n_p + EW_THREADS - 1) / EW_THREADS));
+  p.off_loss_partial = carve(sizeof(double) * ((size_t)K * p.loss_blocks + 4 * ((p.n_p + EW_THREADS - 1) / EW_THREADS) + 4));
   p.off_grad_theta = carve(sizeof(double) * n_theta);
   p.off_dpi = carve(sizeof(double) * S);
   p.off_pibuf = carve(sizeof(double) * S);
@@ -1173,8 +1310,8 @@ void make_plan(Plan& p, int S, int K, char* base) {
   p.off_terms = carve(sizeof(GemmTerm) * max_terms);
   // dataflow lists: upper bounds (fine slices everywhere): items <= 3 * (m-1) * tiles * slices
   {
-    const size_t max_items = 3 * (size_t)kDeg * p.tiles * (p.Sp / BT) + 64;
     const size_t max_groups = 3 * (size_t)kDeg * p.tiles + 64;
+    const size_t max_items = 3 * (size_t)kDeg * p.tiles * (p.Sp / BT) + max_groups * kDfSlabs + 64;
     p.df_fwd.off_items = carve(sizeof(DfItem) * max_items);
     p.df_fwd.off_groups = carve(sizeof(DfGroup) * max_groups);
     p.df_fwd.off_state = carve(sizeof(int) * df_state_ints(kDeg, p.tiles, (int)max_groups));
@@ -1192,17 +1329,31 @@ void make_plan(Plan& p, int S, int K, char* base) {
     char* b0 = base ? base : reinterpret_cast<char*>(0);
     auto Pj = [&](int j) { return reinterpret_cast<double*>(b0 + p.off_P) + (size_t)(j - 1) * p.n_p; };
     auto Pbar = [&](int j) { return reinterpret_cast<double*>(b0 + p.off_Pbar) + (size_t)(j - 1) * p.n_p; };
-    const int tn = p.Sp / BT, cpt = p.Sp / BK, fine = BT / BK;  // tiles per side, chunks per term, chunks per 80-deep slice
+    const int tn = p.Sp / BT, cpt = p.Sp / BK;  // tiles per side, chunks per term
     struct TermSpec { const double* A; const double* B; int ta, tb, a_mat, a_ver, b_mat, b_ver; };
+    // reduction items (one per row slab) of the `count` oldest pending groups (all of them if count < 0): the
+    // queue holds them a lag behind the group's products, and always before anything that reads the result
+    auto emit_reduce = [&](DfList& L, int count) {
+      while (!L.pending.empty() && count != 0) {
+        const int gi = L.pending.front();
+        L.pending.erase(L.pending.begin());
+        for (int sl = 0; sl < kDfSlabs; ++sl) {
+          DfItem it{};
+          it.A = nullptr; it.B = nullptr; it.group = gi; it.slice = sl; it.a_mat = it.b_mat = -1; it.kind = 1;
+          it.g = L.groups[gi];
+          L.items.push_back(it);
+        }
+        if (count > 0) --count;
+      }
+    };
     // one output matrix update C (+)= sum of terms, for every tile; slices of 80 (fine) or whole K per term (coarse)
     auto add_update = [&](DfList& L, double* C, int c_mat, int need_ver, int accumulate,
-                          const std::vector<TermSpec>& terms, bool coarse) {
+                          const std::vector<TermSpec>& terms, int per_term) {
       for (int ti = 0; ti < tn; ++ti)
         for (int tj = 0; tj < tn; ++tj) {
           DfGroup g;
           g.C = C; g.m0 = ti * BT; g.n0 = tj * BT; g.accumulate = accumulate; g.c_mat = c_mat; g.need_ver = need_ver;
-          g.partial_off = L.partial_tiles; g.pad = 0;
-          const int per_term = coarse ? 1 : tn;
+          g.partial_off = L.partial_tiles; g.n_slabs = kDfSlabs;
           g.n_slices = (int)terms.size() * per_term;
           const int gi = (int)L.groups.size();
           int slice = 0;
@@ -1210,20 +1361,35 @@ void make_plan(Plan& p, int S, int K, char* base) {
             for (int z = 0; z < per_term; ++z) {
               DfItem it;
               it.A = t.A; it.B = t.B; it.ta = t.ta; it.tb = t.tb;
-              it.k0 = coarse ? 0 : z * BT; it.n_chunks = coarse ? cpt : fine;
+              const int c_begin = cpt * z / per_term, c_end = cpt * (z + 1) / per_term;  // chunks of this slice
+              it.k0 = c_begin * BK; it.n_chunks = c_end - c_begin;
               it.group = gi; it.slice = slice++;
               it.a_mat = t.a_ver > 0 ? t.a_mat : -1; it.a_ver = t.a_ver;
               it.b_mat = t.b_ver > 0 ? t.b_mat : -1; it.b_ver = t.b_ver;
+              it.kind = 0; it.pad = 0;
+              it.g = g;  // n_slices is already final (set above)
               L.items.push_back(it);
             }
           L.partial_tiles += g.n_slices;
           L.groups.push_back(g);
+          const bool direct = (g.n_slices == 1) && !g.accumulate;
+          if (!direct) L.pending.push_back(gi);
+          if ((int)L.pending.size() > kDfReduceLag) emit_reduce(L, 1);
         }
+    };
+    // K slices per term of a level with `term_tiles` (term, output tile) products: as few as keep about
+    // `target` work items in the level (every item pays ~3 us of queue / fence / reduction latency, a
+    // 80-deep slice is only 10 us of arithmetic), at most 5 (80-deep)
+    static const int chain_target = getenv("CHERRY_FIT_CHAIN_TARGET") ? atoi(getenv("CHERRY_FIT_CHAIN_TARGET")) : 500;
+    auto slices_for = [&](int term_tiles) {
+      for (int n : {1, 2, 3, 4})
+        if (term_tiles * n >= chain_target) return n;
+      return 5;
     };
     // forward: P_{b+r} = P_b P_r, r = 1..min(b, m-b); matrix id of P_j is j-1, version 1 once written (P_1: given)
     {
       DfList& L = p.df_fwd;
-      L.items.clear(); L.groups.clear(); L.partial_tiles = 0; L.n_mats = kDeg;
+      L.items.clear(); L.groups.clear(); L.pending.clear(); L.partial_tiles = 0; L.n_mats = kDeg;
       std::vector<int> ver(kDeg + 1, 0);
       for (int b = 1; b < kDeg; b *= 2) {
         // the squaring P_2b first: it is the critical path of the next level
@@ -1231,8 +1397,10 @@ void make_plan(Plan& p, int S, int K, char* base) {
         if (b + b <= kDeg) rs.push_back(b);
         for (int r = 1; r <= b && b + r <= kDeg; ++r)
           if (r != b) rs.push_back(r);
+        const int per_term = slices_for((int)rs.size() * p.tiles);
         for (int r : rs)
-          add_update(L, Pj(b + r), b + r - 1, 0, 0, {TermSpec{Pj(b), Pj(r), 0, 0, b - 1, ver[b], r - 1, ver[r]}}, false);
+          add_update(L, Pj(b + r), b + r - 1, 0, 0, {TermSpec{Pj(b), Pj(r), 0, 0, b - 1, ver[b], r - 1, ver[r]}}, per_term);
+        emit_reduce(L, -1);  // the next level reads this level's results
         for (int r : rs) ver[b + r] = 1;
       }
     }
@@ -1241,7 +1409,7 @@ void make_plan(Plan& p, int S, int K, char* base) {
     // matrix id of Pbar_j is j-1; version 0 = the value accumulate_M left; P_j are inputs (no waits).
     {
       DfList& L = p.df_bwd;
-      L.items.clear(); L.groups.clear(); L.partial_tiles = 0; L.n_mats = kDeg;
+      L.items.clear(); L.groups.clear(); L.pending.clear(); L.partial_tiles = 0; L.n_mats = kDeg;
       std::vector<int> ver(kDeg + 1, 0);
       std::vector<int> bases;
       for (int b = 1; b < kDeg; b *= 2) bases.push_back(b);
@@ -1251,11 +1419,16 @@ void make_plan(Plan& p, int S, int K, char* base) {
         std::vector<TermSpec> big;
         for (int r = 1; r <= rmax; ++r) big.push_back(TermSpec{Pbar(b + r), Pj(r), 0, 1, b + r - 1, ver[b + r], -1, 0});
         if (rmax == b) big.push_back(TermSpec{Pj(b), Pbar(2 * b), 1, 0, -1, 0, 2 * b - 1, ver[2 * b]});
-        // the long concatenated update first (it is the level's critical path), one slice per term when it has many
-        add_update(L, Pbar(b), b - 1, ver[b], 1, big, big.size() >= 5);
+        int n_small = 0;
+        for (int r = 1; r <= rmax; ++r)
+          if (r != b) ++n_small;
+        const int per_term = slices_for(((int)big.size() + n_small) * p.tiles);
+        // the long concatenated update first (it is the level's critical path)
+        add_update(L, Pbar(b), b - 1, ver[b], 1, big, per_term);
         for (int r = 1; r <= rmax; ++r)
           if (r != b)
-            add_update(L, Pbar(r), r - 1, ver[r], 1, {TermSpec{Pj(b), Pbar(b + r), 1, 0, -1, 0, b + r - 1, ver[b + r]}}, false);
+            add_update(L, Pbar(r), r - 1, ver[r], 1, {TermSpec{Pj(b), Pbar(b + r), 1, 0, -1, 0, b + r - 1, ver[b + r]}}, per_term);
+        emit_reduce(L, -1);  // the next level reads this level's results
         ver[b]++;
         for (int r = 1; r <= rmax; ++r)
           if (r != b) ver[r]++;
@@ -1526,12 +1699,13 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   int* df_state_bwd = reinterpret_cast<int*>(base + p.df_bwd.off_state);
   int* deg_arr = reinterpret_cast<int*>(base + p.off_deg);
   static const bool full_degree = getenv("CHERRY_FIT_FULL_DEGREE") != nullptr;  // A/B switch: round-1 Taylor pass
+  static const int sq_ksplit_max = getenv("CHERRY_FIT_SQ_KSPLIT") ? atoi(getenv("CHERRY_FIT_SQ_KSPLIT")) : 5;  // A/B switch
   coef_kernel<<<1, 256, 0, stream>>>(a.t, a.K, sc, s_arr, deg_arr, w, tau, a.status_flag, sched, p.tiles,
                                      (KGROUPS == 1 ? 2 : 1) * sm_count(), df_state_fwd,
                                      (int)df_state_ints(p.df_fwd.n_mats, p.tiles, (int)p.df_fwd.groups.size()),
                                      df_state_bwd,
                                      (int)df_state_ints(p.df_bwd.n_mats, p.tiles, (int)p.df_bwd.groups.size()),
-                                     full_degree ? 1 : 0);
+                                     full_degree ? 1 : 0, sq_ksplit_max);
   CHERRY_LAUNCH_CHECK("coef_kernel");
   mark("build_B+coef", stream);
   static const bool level_launch = getenv("CHERRY_FIT_LEVEL_LAUNCH") != nullptr;  // A/B switch: round-1 schedule
@@ -1543,9 +1717,9 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
     if (g_timeline && persistent_grid <= 1024)
       prof = reinterpret_cast<long long*>(base + p.off_prof) + (&L == &p.df_bwd ? 8 * 1024 : 0);
     chain_dataflow_kernel<<<persistent_grid, GEMM_THREADS, gemm_smem, stream>>>(
-        reinterpret_cast<const DfItem*>(base + L.off_items), reinterpret_cast<const DfGroup*>(base + L.off_groups),
-        (int)L.items.size(), state, L.n_mats, p.Sp, reinterpret_cast<double*>(base + p.off_partial), a.status_flag,
-        prof);
+        reinterpret_cast<const DfItem*>(base + L.off_items), (int)L.items.size(), (int)L.groups.size(), state,
+        L.n_mats, p.Sp,
+        reinterpret_cast<double*>(base + p.off_partial), a.status_flag, prof);
     CHERRY_LAUNCH_CHECK(name);
     return 0;
   };
@@ -1563,17 +1737,33 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
     if (dev < 64 && !ew_attr[dev]) {
       CHERRY_CUDA(cudaFuncSetAttribute(poly_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CHERRY_CUDA(cudaFuncSetAttribute(accumulate_M_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       ew_attr[dev] = true;
     }
   }
   static const bool unfused = getenv("CHERRY_FIT_UNFUSED") != nullptr;  // A/B switch
   const bool fused = (P_out == nullptr) && !unfused;
   double* fused_partial = loss_partial + (size_t)a.K * p.loss_blocks;
+  int fused_blocks = 0;
   if (fused) {
-    const size_t fsmem = wsmem + 3 * sizeof(int) * a.K;
-    taylor_fused_kernel<<<eb, EW_THREADS, fsmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, s_arr, deg_arr, a.C, X0,
-                                                           Pbar, fused_partial);
+    const size_t fsmem = wsmem + 3 * sizeof(int) * a.K + 8 + sizeof(double) * kTaylorStages * EW_THREADS;
+    static const int lpe = getenv("CHERRY_FIT_TAYLOR_LPE") ? atoi(getenv("CHERRY_FIT_TAYLOR_LPE")) : 1;  // A/B switch
+    int ebl = (int)((p.n_p * (size_t)lpe + EW_THREADS - 1) / EW_THREADS);
+    static const int taylor_ctas = getenv("CHERRY_FIT_TAYLOR_CTAS") ? atoi(getenv("CHERRY_FIT_TAYLOR_CTAS")) : 1;  // per SM
+    if (ebl > taylor_ctas * sm_count()) ebl = taylor_ctas * sm_count();
+    fused_blocks = ebl;
+#define CHERRY_TAYLOR_LAUNCH(L, U)                                                                                  \
+  taylor_fused_kernel<L, U><<<ebl, EW_THREADS, fsmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, s_arr, deg_arr, a.C, X0, \
+                                                                Pbar, fused_partial)
+    static const int tu = getenv("CHERRY_FIT_TAYLOR_U") ? atoi(getenv("CHERRY_FIT_TAYLOR_U")) : kTaylorInterleave;  // A/B switch
+    if (lpe == 2) CHERRY_TAYLOR_LAUNCH(2, 1);
+    else if (tu == 4) CHERRY_TAYLOR_LAUNCH(1, 4);
+    else if (tu == 2) CHERRY_TAYLOR_LAUNCH(1, 2);
+    else CHERRY_TAYLOR_LAUNCH(1, 1);
+#undef CHERRY_TAYLOR_LAUNCH
     CHERRY_LAUNCH_CHECK("taylor_fused_kernel");
   } else {
     poly_eval_kernel<<<eb, EW_THREADS, wsmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, X0);
@@ -1601,7 +1791,7 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
                                                                         p.slots_per_bucket, loss_partial, fused ? 1 : 0);
   CHERRY_LAUNCH_CHECK("loss_grad_kernel");
   loss_reduce_kernel<<<1, 256, 0, stream>>>(loss_partial, a.K, p.loss_blocks, a.loss_part, s_arr, fused_partial,
-                                            fused ? eb : 0);
+                                            fused ? fused_blocks : 0);
   CHERRY_LAUNCH_CHECK("loss_reduce_kernel");
   mark("loss_grad", stream);
   if (level_sync) {
@@ -1648,7 +1838,7 @@ int fit_large_timeline(const cherry_fit_args& a, cudaStream_t stream) {
   {
     std::vector<long long> prof(8 * 2 * 1024);
     CHERRY_CUDA(cudaMemcpy(prof.data(), wbase + pl.off_prof, prof.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    const char* names[7] = {"dequeue", "operand-wait", "product", "arrive", "version-wait", "reduce", "publish"};
+    const char* names[7] = {"dequeue", "operand-wait", "product", "arrive", "reduce-wait", "reduce", "publish"};
     for (int which = 0; which < 2; ++which) {
       long long sum[8] = {0}, mx_items = 0;
       int ctas = 0;

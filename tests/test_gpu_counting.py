@@ -315,23 +315,45 @@ def test_full_size_properties_lg():
     assert np.array_equal(got, exp)
 
 
-def test_bucket_table_at_bucket_boundaries():
-    """t*rate exactly at / one ulp around the geometric midpoints and the grid points: the
-    product-based fast comparison must fall back to the reference expression where needed."""
+@pytest.mark.parametrize("path", ["per_pair", "per_tile", "per_tile_repeated_grid_point"])
+def test_bucket_table_at_bucket_boundaries(path):
+    """t*rate exactly at / a few ulps around the geometric midpoints and the grid points: the
+    product-based fast comparison (per-pair kernel) must fall back to the reference expression where
+    needed, and the per-tile kernel's precomputed decision boundaries (cherry_count_lg_fused) must be the
+    reference's switch points exactly; a grid with a repeated point takes its general path."""
+    from cherryml_b200 import _lib
     from cherryml_b200.counting._device import build_bucket_table
     from oracle.native import quantization_idx_c
 
     grid = np.array(sorted(GRID_LG))
+    if path == "per_tile_repeated_grid_point":
+        grid = np.array(sorted(list(grid) + [grid[7], grid[40]]))
     mids = np.sqrt(grid[:-1] * grid[1:])
-    ts = np.concatenate([mids, np.nextafter(mids, 0), np.nextafter(mids, np.inf), grid, np.nextafter(grid, 0),
-                         np.nextafter(grid, np.inf), 0.5 * (grid[:-1] + grid[1:]),
-                         np.exp(np.random.default_rng(0).uniform(np.log(grid[0] / 2), np.log(grid[-1] * 2), 5000))])
+    near = [mids, grid]
+    for base in (mids, grid):
+        lo, hi = base, base
+        for _ in range(4):
+            lo, hi = np.nextafter(lo, 0), np.nextafter(hi, np.inf)
+            near += [lo, hi]
+    ts = np.concatenate(near + [0.5 * (grid[:-1] + grid[1:]),
+                                np.exp(np.random.default_rng(0).uniform(np.log(grid[0] / 2), np.log(grid[-1] * 2), 5000))])
     syn = synthetic_lg(1, 2 * len(ts), 16, 4, seed=0)
     syn["pair_t"] = torch.from_numpy(ts.copy())
     rates = np.array([1.0, 0.5, 3.0, 1.0 / 3.0])
     syn["rate_vals"] = rates.copy()
     dev = as_device_batch(syn, "cuda")
-    tab = build_bucket_table(dev, torch.from_numpy(grid).cuda(), len(grid)).cpu().numpy().reshape(len(ts), 4)
+    grid_dev = torch.from_numpy(grid).cuda()
+    if path == "per_pair":
+        tab = build_bucket_table(dev, grid_dev, len(grid))
+    else:
+        tab = torch.full((dev.n_pairs * dev.r_pad,), 77, dtype=torch.uint8, device="cuda")
+        out = torch.zeros((len(grid), 20, 20), dtype=torch.int64, device="cuda")
+        _lib.check(_lib.load().cherry_count_lg_fused(
+            _lib.ptr(dev.msa), _lib.ptr(dev.fams), _lib.ptr(dev.pair_a), _lib.ptr(dev.pair_b), _lib.ptr(dev.pair_t),
+            _lib.ptr(dev.pair_fam), _lib.ptr(dev.rate_vals), _lib.ptr(grid_dev), dev.n_pairs, dev.r_pad,
+            _lib.ptr(dev.aux), _lib.ptr(dev.tiles), dev.n_tiles, len(grid), 20, _lib.ptr(tab), _lib.ptr(out),
+            _lib.current_stream_ptr()), "cherry_count_lg_fused")
+    tab = tab.cpu().numpy().reshape(len(ts), 4)
     for i, t in enumerate(ts):
         for r in range(4):
             exp = quantization_idx_c(t * rates[r], grid)
