@@ -35,6 +35,15 @@ UNIT = "transitions/s"
 N_SEQS, N_SITES, N_CATS, K_BUCKETS, N_STATES = 1024, 300, 4, 100, 20
 
 
+_T0 = time.time()
+
+
+def _log(msg):
+    """Progress on stderr (stdout carries the one JSON line)."""
+    sys.stderr.write(f"[bench {time.time() - _T0:7.1f}s] {msg}\n")
+    sys.stderr.flush()
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -279,7 +288,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from cherryml_b200 import _lib
-    from cherryml_b200.counting._device import (build_bucket_table, count_lg_host, count_raw, sorted_grid,
+    from cherryml_b200.counting._device import (build_bucket_table_tiles, count_lg_host, count_raw, sorted_grid,
                                                  symmetrize)
     from cherryml_b200.synthetic import as_count_batch, as_device_batch, quantization_grid, synthetic_lg
 
@@ -305,17 +314,17 @@ def run_ours(args):
     n_pairs = dev.n_pairs
     # algorithmic bytes of one counting launch: residues read once, site->category
     # groups once per family, pair descriptors + bucket-table row per pair, one histogram flush
-    # (pair descriptors = row indices 2 x 4 B + branch length 8 B: the bucket bytes are computed in the kernel)
-    alg_bytes = (dev.msa.numel() + F * (stride // 4) * 2 + n_pairs * 16 + K * S * S * 8)
+    alg_bytes = (dev.msa.numel() + F * (stride // 4) * 2 + n_pairs * (8 + dev.r_pad) + K * S * S * 8)
 
     raw = torch.zeros((K, S, S), dtype=torch.int64, device=device)
     stream = torch.cuda.current_stream()
 
     def step(ev=None):
         raw.zero_()
+        tab = build_bucket_table_tiles(dev, grid_dev, K)  # per tile, against precomputed decision boundaries
         if ev is not None:
             ev[0].record(stream)
-        count_raw(dev, grid_dev, K, S, out=raw)  # one launch: bucket quantisation fused into the counting kernel
+        count_raw(dev, grid_dev, K, S, tab=tab, out=raw)
         if ev is not None:
             ev[1].record(stream)
         if world > 1:
@@ -330,6 +339,7 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         counts = step()
     barrier()
+    _log("warm-up steps done")
     # parity gate inside the bench: a 32-family slice of this rank's batch against the oracle
     parity = None
     if rank == 0:
@@ -368,6 +378,7 @@ def run_ours(args):
         elapsed_ms, kernel_ms = float(t[0]), float(t[1])
     ms_per_step = elapsed_ms / args.steps
     value = examined * world / (ms_per_step * 1e-3)
+    _log(f"timed steps done: {ms_per_step:.3f} ms per step")
     counted = float(counts.sum().item())
 
     # ---- strong scaling (BASELINE config 3 as stated: 16k families in total on 1/2/4/8 GPUs): the SAME
@@ -383,7 +394,7 @@ def run_ours(args):
 
         def step_strong():
             raw.zero_()
-            count_raw(ds, grid_dev, K, S, out=raw)
+            count_raw(ds, grid_dev, K, S, tab=build_bucket_table_tiles(ds, grid_dev, K), out=raw)
             dist.all_reduce(raw, op=dist.ReduceOp.SUM)
             return symmetrize(raw, "lg", K, S, directed=False)
 
@@ -446,6 +457,7 @@ def run_ours(args):
            "note": "cherry_count_lg_host: pinned host arrays -> segmented H2D overlapped with counting -> D2H; "
                    "h2d_copy_only = one bare cudaMemcpyAsync of the same pinned residue buffer on every rank at once"}
     del pinned
+    _log("e2e (host buffers) done")
 
     # ---- the fit (every rank takes part when N > 1: bucket-sharded co-evolution fit)
     fit = None
@@ -457,6 +469,7 @@ def run_ours(args):
         fit = bench_fit(device, lg_times=grid, lg_counts=counts,
                         process_group=dist.group.WORLD if world > 1 else None,
                         cpu_baseline=(rank == 0 and not args.no_cpu_baseline))
+    _log("fit section done")
     # ---- FastCherries (tree estimation, the step before counting): every rank its own families
     fcb = None
     if not args.no_fast_cherries:
@@ -475,6 +488,7 @@ def run_ours(args):
             fcb["families_per_s_e2e"] = fam_all / fcb["e2e_seconds"]
             fcb["residues_per_s_e2e"] = fam_all * 1024 * 300 / fcb["e2e_seconds"]
             fcb["n_gpus"] = world
+    _log("fast_cherries section done")
     llb = None
     if rank == 0 and not args.no_likelihood:
         from benchlib.likelihood import bench_likelihood
@@ -483,6 +497,7 @@ def run_ours(args):
             llb = bench_likelihood(device, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
         except Exception as e:  # never lose the bench line over an extra section
             llb = {"error": str(e)[:300]}
+    _log("likelihood section done")
     srb = None
     if rank == 0 and not args.no_siterm:
         from benchlib.siterm import bench_siterm
@@ -491,6 +506,7 @@ def run_ours(args):
             srb = bench_siterm(device, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
         except Exception as e:
             srb = {"error": str(e)[:300]}
+    _log("siterm section done")
     apib = None
     if rank == 0 and world == 1 and not args.no_public_api:
         from benchlib.public_api_demo import bench_public_api_demo
@@ -499,6 +515,7 @@ def run_ours(args):
             apib = bench_public_api_demo()
         except Exception as e:
             apib = {"error": str(e)[:300]}
+    _log("public api section done")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -135,7 +135,7 @@ def _states_for(S: int):
 
 
 def reference_fit_arms(times, counts: torch.Tensor, num_epochs_full: int, cpu_epochs: int, cuda_epochs: int,
-                       workdir: str, timeout_s: int = 900) -> Dict:
+                       workdir: str, timeout_s: int = 180) -> Dict:
     """The UNMODIFIED reference ``quantized_transitions_mle`` (reference
     estimation/_quantized_transitions_mle.py:40-122 -> ratelearner.py:66-152 -> trainer.py:118-243) on
     the SAME count matrices and JTT-IPW initialisation as our arm, as two arms:
@@ -171,6 +171,7 @@ def reference_fit_arms(times, counts: torch.Tensor, num_epochs_full: int, cpu_ep
         odir = os.path.join(workdir, f"ref_{S}_{arm}")
         cmd = [sys.executable, runner, "--counts", counts_path, "--init", init_path, "--device", arm,
                "--epochs", str(epochs), "--threads", str(cores), "--out", odir]
+        _log(f"reference arm {S}x{S} {arm}: {epochs} epochs ...")
         try:
             res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
             line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
@@ -198,6 +199,13 @@ def reference_fit_arms(times, counts: torch.Tensor, num_epochs_full: int, cpu_ep
     return out
 
 
+def _log(msg):
+    import sys
+
+    sys.stderr.write(f"[bench fit {time.strftime('%H:%M:%S')}] {msg}\n")
+    sys.stderr.flush()
+
+
 def bench_fit(device, lg_times=None, lg_counts: Optional[torch.Tensor] = None, num_epochs: int = 500,
               co_families: int = 16384, process_group=None, cpu_baseline: bool = False,
               ref_epochs: Optional[Dict] = None) -> Dict:
@@ -217,6 +225,7 @@ def bench_fit(device, lg_times=None, lg_counts: Optional[torch.Tensor] = None, n
     # 20 x 20: one wave of CTAs, an epoch is latency -- it stays on one GPU (replicas when N > 1)
     timed_fit(lg_times, lg_counts, 64)  # warm-up (module load, graph instantiation paths)
     out["lg_20x20"] = timed_fit(lg_times, lg_counts, num_epochs)
+    _log(f"lg fit done: {out['lg_20x20']['seconds_end_to_end']:.3f} s")
     rank = 0
     if process_group is not None:
         import torch.distributed as dist
@@ -281,6 +290,7 @@ def bench_fit(device, lg_times=None, lg_counts: Optional[torch.Tensor] = None, n
                      "kernel_ms": ms_kernel, "peak_source": peak_src},
     }
     del order, recs
+    _log(f"co counting done: {ms_total:.3f} ms per pass")
     peak = measure_fp64_gemm_peak(device)
     timed_fit(grid, co_counts, 4, process_group=process_group)
     # The north-star deliverable as ONE timed region (reference estimation_end_to_end/_cherry.py:449-584 from
@@ -302,6 +312,7 @@ def bench_fit(device, lg_times=None, lg_counts: Optional[torch.Tensor] = None, n
         e2e_s = float(tt[0])
     n_ranks = 1 if process_group is None else dist.get_world_size(process_group)
     out["coevo_end_to_end_seconds"] = e2e_s
+    _log(f"coevo end to end done: {e2e_s:.3f} s ({co['ms_per_epoch']:.4f} ms per epoch)")
     out["coevo_end_to_end"] = {
         "seconds": e2e_s, "n_gpus": n_ranks, "families_total": co_families * n_ranks,
         "stages": "count_co (families resident in HBM) -> all-reduce -> symmetrise -> JTT-IPW -> "

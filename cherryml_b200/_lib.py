@@ -69,6 +69,7 @@ _SIGNATURES = {
     "cherry_reset_launch_count": (None, []),
     "cherry_build_bucket_table": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, _P]),
     "cherry_count_lg": (c_int, [_P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "cherry_build_bucket_table_tiles": (c_int, [_P, _P, c_int, _P, _P, _P, c_int, c_int, _P, _P]),
     "cherry_count_lg_fused": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "cherry_sort_pairs_by_bucket": (c_int, [_P, c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cherry_count_co": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P]),

@@ -312,6 +312,10 @@ def coevolution_end_to_end_with_cherryml_optimizer(
     res["jtt_ipw_dir_0"] = jtt_ipw_dir
     if optimizer_initialization == "jtt-ipw":
         initialization_path = os.path.join(jtt_ipw_dir, "result.txt")
+    elif optimizer_initialization == "equ_x_equ":  # reference _cherry.py: the product of two uniform chains
+        from .markov_chain import get_equ_x_equ_path
+
+        initialization_path = get_equ_x_equ_path()
     elif optimizer_initialization == "random":
         initialization_path = None
     else:
@@ -380,8 +384,8 @@ def cherryml_public_api(
     ):
         initial_tree_estimator_rate_matrix_path = get_lg_path()
     if tree_estimator_name == "FastCherries":
-        tree_estimator = partial(fast_cherries, max_iters=50, num_rate_categories=num_rate_categories,
-                                 verbose=False)
+        # `verbose` stays at its default (True) as in the reference's partial: it is part of the cache key
+        tree_estimator = partial(fast_cherries, max_iters=50, num_rate_categories=num_rate_categories)
     elif tree_estimator_name in ("FastTree", "PhyML"):
         tree_estimator = None  # external programs: only usable here with tree_dir given
     else:

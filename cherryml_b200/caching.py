@@ -269,14 +269,30 @@ def cached_parallel_computation(
             def paths(od, v):
                 return os.path.join(kwargs[od], v + ".txt"), os.path.join(kwargs[od], v + ".success")
 
-            todo = [
-                v for v in kwargs[parallel_arg]
-                if not all(os.path.exists(p) for od in output_dirs for p in paths(od, v))
-            ]
+            # With a process group (this package's multi-GPU extension of the per-family stages) every rank
+            # enters this wrapper: rank 0 alone decides what is left to do, cleans stale outputs, verifies and
+            # tokenises; the list is broadcast and barriers keep a late rank from removing files that a faster
+            # rank has already written.  (One node: the ranks share the cache directory.)
+            group = kwargs.get("process_group") if "process_group" in params else None
+            rank = 0
+            if group is not None:
+                import torch.distributed as dist
+
+                rank = dist.get_rank(group)
+            todo = None
+            if rank == 0:
+                todo = [
+                    v for v in kwargs[parallel_arg]
+                    if not all(os.path.exists(p) for od in output_dirs for p in paths(od, v))
+                ]
+            if group is not None:
+                box = [todo]
+                dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0), group=group)
+                todo = box[0]
             kwargs[parallel_arg] = todo
             for od in output_dirs:
                 os.makedirs(kwargs[od], exist_ok=True)
-                if write_extra_log_files:
+                if write_extra_log_files and rank == 0:
                     log = os.path.join(kwargs[od], "_function_binding.log")
                     if not os.path.exists(log):
                         logged = dict(kwargs)
@@ -292,27 +308,35 @@ def cached_parallel_computation(
             if todo:
                 if _READ_ONLY:
                     raise CacheUsageError("Cache is in read only mode! Will not call function.")
-                for v in todo:
-                    for od in output_dirs:
-                        for p in paths(od, v):
-                            if os.path.exists(p):
-                                os.chmod(p, 0o666)
-                                os.remove(p)
+                if rank == 0:
+                    for v in todo:
+                        for od in output_dirs:
+                            for p in paths(od, v):
+                                if os.path.exists(p):
+                                    os.chmod(p, 0o666)
+                                    os.remove(p)
+                if group is not None:
+                    dist.barrier(group)  # stale outputs are gone before any rank writes
                 func(**kwargs)
-                for od in output_dirs:
-                    for v in todo:
-                        out, _ = paths(od, v)
-                        if not os.path.exists(out):
-                            raise CacheUsageError(
-                                f"function {func.__name__} should have created and written "
-                                f"output to {out} but the file does not exist."
-                            )
-                for od in output_dirs:
-                    for v in todo:
-                        out, tok = paths(od, v)
-                        _make_read_only(out)
-                        with open(tok, "w") as f:
-                            f.write("SUCCESS\n")
+                if group is not None:
+                    dist.barrier(group)  # every rank's outputs exist
+                if rank == 0:
+                    for od in output_dirs:
+                        for v in todo:
+                            out, _ = paths(od, v)
+                            if not os.path.exists(out):
+                                raise CacheUsageError(
+                                    f"function {func.__name__} should have created and written "
+                                    f"output to {out} but the file does not exist."
+                                )
+                    for od in output_dirs:
+                        for v in todo:
+                            out, tok = paths(od, v)
+                            _make_read_only(out)
+                            with open(tok, "w") as f:
+                                f.write("SUCCESS\n")
+                if group is not None:
+                    dist.barrier(group)  # tokens exist before any rank returns
             return res
 
         wrapper.caching_dir = lambda cache_dir, use_hash=None, **kwargs: _call_caching_dir(

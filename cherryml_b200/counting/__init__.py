@@ -1,1 +1,2 @@
-from ._count_transitions import count_co_transitions, count_transitions, device_result  # noqa: F401
+from ._count_transitions import (clear_device_results, count_co_transitions, count_transitions,  # noqa: F401
+                                device_result)

@@ -23,6 +23,8 @@ import os
 import time
 from typing import Dict, List, Optional, Tuple, Union
 
+from collections import OrderedDict
+
 import numpy as np
 import torch
 
@@ -34,13 +36,66 @@ from ._ingest import build_co_batch, build_co_batch_native, build_lg_batch, buil
 
 logger = logging.getLogger(__name__)
 
-# In-process hand-off to the fit: output dir -> (grid fp64 [K], states, counts fp64 device tensor)
-_DEVICE_RESULTS: Dict[str, Tuple[np.ndarray, List[str], torch.Tensor]] = {}
+# In-process hand-off to the fit: output dir -> (grid fp64 [K], states, counts fp64 device tensor, stamp of
+# result.txt).  At most _MAX_DEVICE_RESULTS entries are kept (a co-transition tensor is 165 MB of HBM), the
+# least recently used one is dropped first, and an entry is only handed out while result.txt on disk is still
+# the file this process wrote (size and mtime): a replaced file wins over the resident tensor.
+_MAX_DEVICE_RESULTS = 2
+_DEVICE_RESULTS: "OrderedDict[str, Tuple[np.ndarray, List[str], torch.Tensor, Tuple[int, int]]]" = OrderedDict()
+
+
+def _stamp(path: str):
+    try:
+        st = os.stat(path)
+    except OSError:
+        return None
+    return (st.st_size, st.st_mtime_ns)
 
 
 def device_result(output_count_matrices_dir: str):
-    """Counts of a ``count_*`` call made in this process, still resident on the device."""
-    return _DEVICE_RESULTS.get(os.path.realpath(output_count_matrices_dir))
+    """Counts of a ``count_*`` call made in this process, still resident on the device: ``(grid, states,
+    counts)``, or None if there are none or ``result.txt`` in that directory is no longer the file this
+    process wrote."""
+    key = os.path.realpath(output_count_matrices_dir)
+    entry = _DEVICE_RESULTS.get(key)
+    if entry is None:
+        return None
+    if entry[3] is None or _stamp(os.path.join(key, "result.txt")) != entry[3]:
+        del _DEVICE_RESULTS[key]
+        return None
+    _DEVICE_RESULTS.move_to_end(key)
+    return entry[:3]
+
+
+def clear_device_results() -> None:
+    """Drop every resident count tensor (frees the HBM they hold)."""
+    _DEVICE_RESULTS.clear()
+
+
+def round_like_the_cpp_writer(counts: torch.Tensor) -> torch.Tensor:
+    """The values a reader gets back from a ``result.txt`` written in the C++ program's format (``%g``: six
+    significant digits, reference counting/_count_transitions.cpp:560-577): what the reference's fit is trained
+    on when counting ran with ``use_cpp_implementation=True``.  Counts are multiples of 0.25, so the decimal
+    rounding (round-half-even on the exact value, as printf does) is done exactly in integers."""
+    n = torch.round(counts * 4.0).to(torch.int64)  # exact: counts are multiples of 0.25
+    out = counts.clone()
+    # 1e4 <= v < 1e5: one decimal survives (v * 10 = 5 n / 2)
+    sel = (counts >= 1e4) & (counts < 1e5)
+    if bool(sel.any()):
+        m = 5 * n[sel]
+        q, r = torch.div(m, 2, rounding_mode="floor"), m % 2
+        q = q + ((r == 1) & (q % 2 == 1)).to(torch.int64)  # r == 1 is an exact tie
+        out[sel] = q.to(torch.float64) / 10.0
+    # 10^e <= v < 10^(e+1), e >= 5: multiples of D = 10^(e-5) survive (v / D = n / (4 D))
+    lo, d = 1e5, 1
+    while bool((counts >= lo).any()):
+        sel = (counts >= lo) & (counts < lo * 10)
+        if bool(sel.any()):
+            q, r = torch.div(n[sel], 4 * d, rounding_mode="floor"), n[sel] % (4 * d)
+            up = (2 * r > 4 * d) | ((2 * r == 4 * d) & (q % 2 == 1))
+            out[sel] = ((q + up.to(torch.int64)) * d).to(torch.float64)
+        lo, d = lo * 10, d * 10
+    return out
 
 
 def _rank_world(process_group):
@@ -62,7 +117,6 @@ def _ingest_threads(num_processes) -> int:
 
 
 def _finish(counts_dev, grid, states, out_dir, style, start_time, num_processes, rank, process_group=None):
-    _DEVICE_RESULTS[os.path.realpath(out_dir)] = (grid, list(states), counts_dev)
     if rank == 0:
         counts = counts_dev.cpu().numpy()
         write_count_matrices_array(
@@ -77,6 +131,17 @@ def _finish(counts_dev, grid, states, out_dir, style, start_time, num_processes,
         import torch.distributed as dist
 
         dist.barrier(process_group)  # result.txt exists before any rank returns
+    # hand-off to the fit: with the C++ writer's format the file holds six significant digits, and the
+    # reference trains on the file, so the resident copy is rounded the same way
+    key = os.path.realpath(out_dir)
+    resident, grid_res = counts_dev, grid
+    if style == "cpp":  # the quantization points go through "%g" as well
+        resident = round_like_the_cpp_writer(counts_dev)
+        grid_res = np.array([float("%g" % x) for x in grid])
+    _DEVICE_RESULTS[key] = (grid_res, list(states), resident, _stamp(os.path.join(key, "result.txt")))
+    _DEVICE_RESULTS.move_to_end(key)
+    while len(_DEVICE_RESULTS) > _MAX_DEVICE_RESULTS:
+        _DEVICE_RESULTS.popitem(last=False)
 
 
 @caching.cached_computation(

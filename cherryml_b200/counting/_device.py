@@ -123,6 +123,19 @@ def build_bucket_table(dev: DeviceBatch, grid_dev: torch.Tensor, K: int) -> torc
     return tab
 
 
+def build_bucket_table_tiles(dev: DeviceBatch, grid_dev: torch.Tensor, K: int) -> torch.Tensor:
+    """The bucket table of the pairs covered by the batch's tiles, built one CTA per tile."""
+    lib = _lib.load()
+    tab = torch.empty(max(1, dev.n_pairs * dev.r_pad), dtype=torch.uint8, device=dev.msa.device)
+    if dev.n_tiles:
+        rc = lib.cherry_build_bucket_table_tiles(
+            _lib.ptr(dev.pair_t), _lib.ptr(dev.tiles), dev.n_tiles, _lib.ptr(dev.fams), _lib.ptr(dev.rate_vals),
+            _lib.ptr(grid_dev), K, dev.r_pad, _lib.ptr(tab), _lib.current_stream_ptr(),
+        )
+        _lib.check(rc, "cherry_build_bucket_table_tiles")
+    return tab
+
+
 def count_raw(
     dev: DeviceBatch,
     grid_dev: torch.Tensor,

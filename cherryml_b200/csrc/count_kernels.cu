@@ -531,6 +531,25 @@ int cherry_count_lg(const uint8_t* msa, const cherry_fam_desc* fams, const int32
   return 0;
 }
 
+int cherry_build_bucket_table_tiles(const double* pair_t, const cherry_tile* tiles, int n_tiles,
+                                    const cherry_fam_desc* fams, const double* rate_vals, const double* grid,
+                                    int K, int r_pad, uint8_t* tab, void* stream) {
+  if (!pair_t || !tiles || !fams || !rate_vals || !grid || !tab)
+    return cherry::fail(CHERRY_EINVAL, "bucket_table_tiles: null pointer argument");
+  if (K <= 0 || K > CHERRY_MAX_BUCKETS)
+    return cherry::fail(CHERRY_ELIMIT, "bucket_table_tiles: K=%d outside 1..%d", K, CHERRY_MAX_BUCKETS);
+  if (n_tiles < 0 || r_pad <= 0 || r_pad % 4 != 0)
+    return cherry::fail(CHERRY_EINVAL, "bucket_table_tiles: bad sizes (r_pad must be a positive multiple of 4)");
+  if (n_tiles == 0) return 0;
+  int blocks = n_tiles;
+  const int cap = cherry::sm_count() * 8;  // one residency: every CTA computes the boundaries once
+  if (blocks > cap) blocks = cap;
+  bucket_table_tiles_kernel<<<blocks, 256, (2 * K + r_pad) * sizeof(double), (cudaStream_t)stream>>>(
+      pair_t, tiles, fams, rate_vals, grid, K, n_tiles, r_pad, tab);
+  CHERRY_LAUNCH_CHECK("bucket_table_tiles_kernel");
+  return 0;
+}
+
 int cherry_count_lg_fused(const uint8_t* msa, const cherry_fam_desc* fams, const int32_t* pair_a,
                           const int32_t* pair_b, const double* pair_t, const int32_t* pair_fam,
                           const double* rate_vals, const double* grid, int64_t n_pairs, int r_pad,
@@ -544,17 +563,10 @@ int cherry_count_lg_fused(const uint8_t* msa, const cherry_fam_desc* fams, const
   if (!group_cat) return cherry::fail(CHERRY_EINVAL, "count_lg_fused: null group_cat");
   if (n_tiles == 0) return 0;
   if (!tab_scratch) return cherry::fail(CHERRY_EINVAL, "count_lg_fused: tab_scratch (n_pairs * r_pad bytes) is required");
-  if (K > CHERRY_MAX_BUCKETS) return cherry::fail(CHERRY_ELIMIT, "count_lg_fused: K=%d outside 1..%d", K, CHERRY_MAX_BUCKETS);
   (void)n_pairs;
   (void)pair_fam;
-  {
-    int blocks = n_tiles;
-    const int cap = cherry::sm_count() * 8;  // one residency: every CTA computes the boundaries once
-    if (blocks > cap) blocks = cap;
-    bucket_table_tiles_kernel<<<blocks, 256, (2 * K + r_pad) * sizeof(double), (cudaStream_t)stream>>>(
-        pair_t, tiles, fams, rate_vals, grid, K, n_tiles, r_pad, tab_scratch);
-    CHERRY_LAUNCH_CHECK("bucket_table_tiles_kernel");
-  }
+  rc = cherry_build_bucket_table_tiles(pair_t, tiles, n_tiles, fams, rate_vals, grid, K, r_pad, tab_scratch, stream);
+  if (rc) return rc;
   return cherry_count_lg(msa, fams, pair_a, pair_b, tab_scratch, r_pad, group_cat, tiles, n_tiles, K, S, counts, stream);
 }
 

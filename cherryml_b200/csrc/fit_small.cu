@@ -15,6 +15,8 @@
 // (estimation/_ratelearn/trainer.py:156-187), RateMatrix.forward (rate.py:167-188), and the
 // batched per-site variant (_siterm/_cherryml_vectorized.py:264-293, 351-383).
 #include "common.cuh"
+#include <cstdlib>
+
 #include "fit_common.cuh"
 
 namespace {
@@ -40,13 +42,13 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // products): every warp owns one output tile, all operand fragments of the tile are loaded up
 // front (independent loads), and the k-steps alternate between two accumulators to halve the
 // DMMA dependency chain.
-template <bool TA, bool TB, bool ACC>
+template <bool TA, bool TB, bool ACC, int NT>
 __device__ __forceinline__ void mm(double* D, const double* A, const double* B, int nt, int ld) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tg = lane & 3;
   constexpr int kMaxSteps = kMaxSmallS / 4;  // 8 k-steps of 4
   const int nsteps = nt * 2;
-  for (int tile = warp; tile < nt * nt; tile += kSmallThreads / 32) {
+  for (int tile = warp; tile < nt * nt; tile += NT / 32) {
     const int r0 = (tile / nt) * 8, c0 = (tile % nt) * 8;
     double a[kMaxSteps], b[kMaxSteps];
 #pragma unroll
@@ -83,6 +85,7 @@ struct Slots {
   }
 };
 
+template <int NT>
 __device__ __forceinline__ double block_reduce_sum(double v, double* red) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -90,10 +93,11 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* red) {
   if (lane == 0) red[warp] = v;
   __syncthreads();
   double t = 0.0;
-  for (int w = 0; w < kSmallThreads / 32; ++w) t += red[w];  // fixed order: deterministic
+  for (int w = 0; w < NT / 32; ++w) t += red[w];  // fixed order: deterministic
   return t;
 }
 
+template <int NT>
 __device__ __forceinline__ double block_reduce_max(double v, double* red) {
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -101,19 +105,20 @@ __device__ __forceinline__ double block_reduce_max(double v, double* red) {
   if (lane == 0) red[warp] = v;
   __syncthreads();
   double t = red[0];
-  for (int w = 1; w < kSmallThreads / 32; ++w) t = fmax(t, red[w]);
+  for (int w = 1; w < NT / 32; ++w) t = fmax(t, red[w]);
   return t;
 }
 
 // grid.x = n_problems * K.  Problem p = blockIdx.x / K owns Q[p], buckets (p, 0..K-1).
-__global__ void __launch_bounds__(kSmallThreads)
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__ tall,
                      const double* __restrict__ Call, int S, int K, int n_smem_slots,
                      double* __restrict__ spill_all, int spill_slots, double* __restrict__ dQ_part,
                      double* __restrict__ loss_part, int* __restrict__ overflow_flag,
                      double* __restrict__ P_out) {
   extern __shared__ double smem[];
-  __shared__ double red[kSmallThreads / 32];
+  __shared__ double red[NT / 32];
   __shared__ int sh_m, sh_s;
   const int tid = threadIdx.x;
   const int b = blockIdx.x, prob = b / K;
@@ -127,7 +132,7 @@ expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__
   double colsum = 0.0;
   if (tid < S)
     for (int i = 0; i < S; ++i) colsum += fabs(Q[i * S + tid]);
-  const double norm = fabs(t) * block_reduce_max(colsum, red);
+  const double norm = fabs(t) * block_reduce_max<NT>(colsum, red);
   if (tid == 0) {
     int m, s;
     cherry::choose_degree(norm, m, s);
@@ -146,11 +151,11 @@ expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__
       atomicExch(overflow_flag, 1);
       loss_part[b] = nan("");
     }
-    for (int e = tid; e < S * S; e += kSmallThreads) dQ_part[(size_t)b * S * S + e] = nan("");
+    for (int e = tid; e < S * S; e += NT) dQ_part[(size_t)b * S * S + e] = nan("");
     return;
   }
   double* Bm = slot(sB);
-  for (int e = tid; e < slot_elems; e += kSmallThreads) {
+  for (int e = tid; e < slot_elems; e += NT) {
     const int i = e / ld, j = e - i * ld;
     Bm[e] = (i < S && j < S) ? tau * Q[i * S + j] : 0.0;
   }
@@ -161,14 +166,14 @@ expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__
   {
     double* H = (m - 1 >= 1) ? slot(m - 1) : slot(sX);  // m == 1: H_0 = X_0 = I + B
     const double cm = cherry::inv_factorial(m), cm1 = cherry::inv_factorial(m - 1);
-    for (int e = tid; e < slot_elems; e += kSmallThreads) {
+    for (int e = tid; e < slot_elems; e += NT) {
       const int i = e / ld, j = e - i * ld;
       H[e] = cm * Bm[e] + ((i == j && i < S) ? cm1 : 0.0);
     }
     __syncthreads();
     for (int j = m - 2; j >= 0; --j) {
       double* Hj = (j >= 1) ? slot(j) : slot(sX);
-      mm<false, false, false>(Hj, Bm, slot(j + 1), nt, ld);
+      mm<false, false, false, NT>(Hj, Bm, slot(j + 1), nt, ld);
       __syncthreads();
       const double cj = cherry::inv_factorial(j);
       if (tid < S) Hj[tid * ld + tid] += cj;
@@ -177,12 +182,12 @@ expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__
   }
   // ---- squarings
   for (int i = 0; i < s; ++i) {
-    mm<false, false, false>(slot(sX + i + 1), slot(sX + i), slot(sX + i), nt, ld);
+    mm<false, false, false, NT>(slot(sX + i + 1), slot(sX + i), slot(sX + i), nt, ld);
     __syncthreads();
   }
   double* P = slot(sX + s);
   if (P_out != nullptr) {  // forward only: hand back expm(t Q)
-    for (int e = tid; e < S * S; e += kSmallThreads) {
+    for (int e = tid; e < S * S; e += NT) {
       const int i = e / S, j = e - i * S;
       P_out[(size_t)b * S * S + e] = P[i * ld + j];
     }
@@ -191,7 +196,7 @@ expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__
   // ---- loss and dL/dP (unnormalised): loss_k = -sum C log P, G = -C / P, skipping C == 0
   double* G = slot(sG0);
   double part = 0.0;
-  for (int e = tid; e < slot_elems; e += kSmallThreads) {
+  for (int e = tid; e < slot_elems; e += NT) {
     const int i = e / ld, j = e - i * ld;
     double gval = 0.0;
     if (i < S && j < S) {
@@ -204,15 +209,15 @@ expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__
     }
     G[e] = gval;
   }
-  const double loss_k = block_reduce_sum(part, red);
+  const double loss_k = block_reduce_sum<NT>(part, red);
   if (tid == 0) loss_part[b] = loss_k;
   __syncthreads();
   // ---- adjoint of the squarings: Xbar_i = Xbar_{i+1} X_i^T + X_i^T Xbar_{i+1}
   int gcur = sG0, gnext = sG1;
   for (int i = s - 1; i >= 0; --i) {
-    mm<false, true, false>(slot(gnext), slot(gcur), slot(sX + i), nt, ld);
+    mm<false, true, false, NT>(slot(gnext), slot(gcur), slot(sX + i), nt, ld);
     __syncthreads();
-    mm<true, false, true>(slot(gnext), slot(sX + i), slot(gcur), nt, ld);
+    mm<true, false, true, NT>(slot(gnext), slot(sX + i), slot(gcur), nt, ld);
     __syncthreads();
     const int tmp = gcur;
     gcur = gnext;
@@ -220,11 +225,11 @@ expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__
   }
   // ---- adjoint of Horner: Bbar += Hbar_j H_{j+1}^T, Hbar_{j+1} = B^T Hbar_j; last term c_m Hbar_{m-1}
   double* Bbar = slot(sBbar);
-  for (int e = tid; e < slot_elems; e += kSmallThreads) Bbar[e] = 0.0;
+  for (int e = tid; e < slot_elems; e += NT) Bbar[e] = 0.0;
   __syncthreads();
   for (int j = 0; j <= m - 2; ++j) {
-    mm<false, true, true>(Bbar, slot(gcur), slot(j + 1), nt, ld);
-    mm<true, false, false>(slot(gnext), Bm, slot(gcur), nt, ld);
+    mm<false, true, true, NT>(Bbar, slot(gcur), slot(j + 1), nt, ld);
+    mm<true, false, false, NT>(slot(gnext), Bm, slot(gcur), nt, ld);
     __syncthreads();
     const int tmp = gcur;
     gcur = gnext;
@@ -234,7 +239,7 @@ expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__
     const double cm = cherry::inv_factorial(m);
     const double* Hbar = slot(gcur);
     double* out = dQ_part + (size_t)b * S * S;
-    for (int e = tid; e < S * S; e += kSmallThreads) {
+    for (int e = tid; e < S * S; e += NT) {
       const int i = e / S, j = e - i * S;
       out[e] = tau * (Bbar[i * ld + j] + cm * Hbar[i * ld + j]);
     }
@@ -333,10 +338,10 @@ __global__ void __launch_bounds__(kSmallThreads) fit_update_small(UpdateArgs a) 
   {
     double mx = -INFINITY;
     for (int i = tid; i < S; i += kSmallThreads) mx = fmax(mx, theta[i]);
-    mx = block_reduce_max(mx, red);
+    mx = block_reduce_max<kSmallThreads>(mx, red);
     double se = 0.0;
     for (int i = tid; i < S; i += kSmallThreads) se += exp(theta[i] - mx);
-    se = block_reduce_sum(se, red);
+    se = block_reduce_sum<kSmallThreads>(se, red);
     for (int i = tid; i < S; i += kSmallThreads) {
       pi[i] = exp(theta[i] - mx) / se;
       rr[i] = sqrt(pi[i]);
@@ -372,7 +377,7 @@ __global__ void __launch_bounds__(kSmallThreads) fit_update_small(UpdateArgs a) 
     __syncthreads();
     double dot = 0.0;
     for (int i = tid; i < S; i += kSmallThreads) dot += pi[i] * dpi[i];
-    dot = block_reduce_sum(dot, red);
+    dot = block_reduce_sum<kSmallThreads>(dot, red);
     const int step = epoch + 1;
     const double bc1 = 1.0 - pow(a.beta1, (double)step);
     const double bc2s = sqrt(1.0 - pow(a.beta2, (double)step));
@@ -398,10 +403,10 @@ __global__ void __launch_bounds__(kSmallThreads) fit_update_small(UpdateArgs a) 
     // ---- new softmax for the next epoch's Q
     double mx = -INFINITY;
     for (int i = tid; i < S; i += kSmallThreads) mx = fmax(mx, theta[i]);
-    mx = block_reduce_max(mx, red);
+    mx = block_reduce_max<kSmallThreads>(mx, red);
     double se = 0.0;
     for (int i = tid; i < S; i += kSmallThreads) se += exp(theta[i] - mx);
-    se = block_reduce_sum(se, red);
+    se = block_reduce_sum<kSmallThreads>(se, red);
     for (int i = tid; i < S; i += kSmallThreads) {
       pi[i] = exp(theta[i] - mx) / se;
       rr[i] = sqrt(pi[i]);
@@ -437,8 +442,22 @@ __global__ void __launch_bounds__(kSmallThreads) fit_update_small(UpdateArgs a) 
 
 namespace cherry {
 
+// Two launch shapes.  Latency shape (grid <= SMs, or S > 24): 512 threads, up to 40 resident matrix slots,
+// one CTA per SM -- a bucket is a dependent chain of ~50 tiny products and the whole grid is one wave.
+// Throughput shape (grid > SMs and S <= 24, e.g. the batched per-site fits: 331 sites x 4 buckets): 288
+// threads (one warp per 8x8 output tile of a 24x24 matrix), <= 113 registers and 20 resident slots, so that
+// TWO CTAs share an SM; slots beyond the resident ones live in the global workspace (sized for the worst
+// case in both shapes, so the caller's workspace does not depend on the shape).
+constexpr int kThroughputThreads = 288, kThroughputSlots = 20;
+static bool throughput_shape(int S, int grid) {
+  static const int forced = getenv("CHERRY_FIT_SMALL_SHAPE") ? atoi(getenv("CHERRY_FIT_SMALL_SHAPE")) : -1;  // A/B switch
+  if (S > 24) return false;
+  if (forced >= 0) return forced == 1;
+  return grid > sm_count();
+}
+
 int fit_small_workspace(int S, int* n_smem_slots, int* spill_slots, size_t* slot_bytes,
-                        size_t* smem_bytes) {
+                        size_t* smem_bytes, int grid) {
   if (S <= 0 || S > kMaxSmallS) return fail(CHERRY_ELIMIT, "fit_small: S=%d outside 1..%d", S, kMaxSmallS);
   const int nt = (S + 7) / 8, spad = nt * 8, ld = spad + 4;
   const size_t sb = (size_t)spad * ld * sizeof(double);
@@ -446,8 +465,12 @@ int fit_small_workspace(int S, int* n_smem_slots, int* spill_slots, size_t* slot
   const int total_needed = kMaxDegree + kMaxSquarings + 4;  // m + s_max + 4 slots
   int ns = (int)(budget / sb);
   if (ns > total_needed) ns = total_needed;
+  // the workspace is sized for the shape with the fewest resident slots that this S can take
+  int ns_min = ns;
+  if (S <= 24 && ns_min > kThroughputSlots) ns_min = kThroughputSlots;
+  if (grid >= 0 && throughput_shape(S, grid) && ns > kThroughputSlots) ns = kThroughputSlots;
   if (n_smem_slots) *n_smem_slots = ns;
-  if (spill_slots) *spill_slots = total_needed - ns;
+  if (spill_slots) *spill_slots = total_needed - ns_min;
   if (slot_bytes) *slot_bytes = sb;
   if (smem_bytes) *smem_bytes = (size_t)ns * sb;
   return 0;
@@ -456,7 +479,8 @@ int fit_small_workspace(int S, int* n_smem_slots, int* spill_slots, size_t* slot
 int fit_small_expm(const cherry_fit_args& a, cudaStream_t stream, double* P_out) {
   int ns = 0, sp = 0;
   size_t sb = 0, smem = 0;
-  int rc = fit_small_workspace(a.S, &ns, &sp, &sb, &smem);
+  const int grid = a.n_problems * a.K;
+  int rc = fit_small_workspace(a.S, &ns, &sp, &sb, &smem, grid);
   if (rc) return rc;
   const size_t need = (size_t)sp * sb * a.n_problems * a.K;
   if (need > 0 && (!a.workspace || a.workspace_bytes < need))
@@ -465,13 +489,23 @@ int fit_small_expm(const cherry_fit_args& a, cudaStream_t stream, double* P_out)
   int dev = 0;
   CHERRY_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
-    CHERRY_CUDA(cudaFuncSetAttribute(expm_loss_grad_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CHERRY_CUDA(cudaFuncSetAttribute(expm_loss_grad_small<kSmallThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      226 * 1024));  // 227 KB minus this kernel's static shared memory
+    CHERRY_CUDA(cudaFuncSetAttribute(expm_loss_grad_small<kThroughputThreads, 2>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     attr_set[dev] = true;
   }
-  expm_loss_grad_small<<<a.n_problems * a.K, kSmallThreads, smem, stream>>>(
-      a.Q, a.t, a.C, a.S, a.K, ns, reinterpret_cast<double*>(a.workspace), sp, a.dQ_part, a.loss_part,
-      a.status_flag, P_out);
+  // the spill area of a CTA starts after the slots that are resident in ITS shape
+  const int total_needed = kMaxDegree + kMaxSquarings + 4;
+  if (throughput_shape(a.S, grid))
+    expm_loss_grad_small<kThroughputThreads, 2><<<grid, kThroughputThreads, smem, stream>>>(
+        a.Q, a.t, a.C, a.S, a.K, ns, reinterpret_cast<double*>(a.workspace), sp, a.dQ_part, a.loss_part,
+        a.status_flag, P_out);
+  else
+    expm_loss_grad_small<kSmallThreads, 1><<<grid, kSmallThreads, smem, stream>>>(
+        a.Q, a.t, a.C, a.S, a.K, ns, reinterpret_cast<double*>(a.workspace), sp, a.dQ_part, a.loss_part,
+        a.status_flag, P_out);
+  (void)total_needed;
   CHERRY_LAUNCH_CHECK("expm_loss_grad_small");
   return 0;
 }

@@ -38,7 +38,8 @@ def jtt_ipw_from_counts(
         off_rows = (c * (1.0 - eye)).sum(dim=2)  # [K, S]
         M = (off_rows / t[:, None]).sum(dim=0) / F.sum(dim=1)
     else:
-        M = 1.0 / torch.median(t) * F_off.sum(dim=1) / F.sum(dim=1)
+        # np.median averages the two middle values of an even-sized grid (torch.median takes the lower one)
+        M = 1.0 / float(np.median(t.cpu().numpy())) * F_off.sum(dim=1) / F.sum(dim=1)
     res = M[:, None] * ctps
     res = res - torch.diag(torch.diagonal(res)) - torch.diag(M)
     return res.cpu().numpy()

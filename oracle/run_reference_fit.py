@@ -31,6 +31,10 @@ def main():
     ap.add_argument("--out", required=True)
     ap.add_argument("--lr", type=float, default=0.1)
     args = ap.parse_args()
+    if os.environ.get("CHERRY_REF_FIT_DUMP_AFTER"):  # debugging aid: where is it if it stalls
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ["CHERRY_REF_FIT_DUMP_AFTER"]), exit=True)
     import torch
 
     torch.set_num_threads(args.threads)
@@ -42,11 +46,12 @@ def main():
     # Library start-up is not the reference's cost: torch imports its compiler stack lazily the first
     # time an optimizer is built (several seconds), CUDA creates its context and cuBLAS / cuSOLVER
     # handles on first use.  One throw-away Adam step on a tiny matrix_exp warms all of it.
-    w = torch.zeros(4, 4, device=args.device, requires_grad=True)
+    w = (0.1 * torch.ones(4, 4)).requires_grad_(True)
     opt = torch.optim.Adam([w], lr=0.1)
     torch.log(torch.matrix_exp(w)).sum().backward()
     opt.step()
     if args.device == "cuda":
+        torch.matrix_exp(0.1 * torch.ones(4, 4, device="cuda"))
         torch.cuda.synchronize()
     t0 = time.perf_counter()
     quantized_transitions_mle(

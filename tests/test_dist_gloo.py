@@ -127,7 +127,7 @@ def test_assign_buckets_is_a_balanced_partition():
         assert all(np.array_equal(a, b) for a, b in zip(parts, again))
 
 
-def _fc_worker(rank, world, port, msa_dir, out_root, families):
+def _fc_worker(rank, world, port, msa_dir, out_root, families, cache_dir=None):
     """Two ranks run the sharded FastCherries stage with the per-rank GPU work replaced by its
     oracle (this test is about the striping, the files and the barrier, not the kernels)."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -146,6 +146,14 @@ def _fc_worker(rank, world, port, msa_dir, out_root, families):
 
     fc._fast_cherries_local = fake_local
     dirs = [os.path.join(out_root, k) for k in ("tree", "rates", "ll")]
+    if cache_dir is not None:  # the caching wrapper is active, and rank 1 enters it late
+        import time
+
+        from cherryml_b200 import caching
+
+        caching.set_cache_dir(cache_dir)
+        if rank == 1:
+            time.sleep(1.0)
     fc.fast_cherries(msa_dir=msa_dir, families=families, rate_matrix_path="unused", num_rate_categories=4,
                      max_iters=50, num_processes=1, output_tree_dir=dirs[0], output_site_rates_dir=dirs[1],
                      output_likelihood_dir=dirs[2], process_group=dist.group.WORLD)
@@ -169,6 +177,24 @@ def test_two_rank_fast_cherries_stage_stripes_families(tmp_path):
     for f in families:
         owner = sorted(families).index(f) % 2
         assert open(tmp_path / "tree" / f"{f}.txt").read() == f"rank {owner}\n"
+
+
+def test_two_rank_fast_cherries_stage_through_the_cache(tmp_path):
+    """The same stage with a cache directory: every rank runs the caching wrapper; rank 0 alone cleans,
+    verifies and writes the success tokens (a late rank used to delete the files of a faster one)."""
+    families = [f"fam{i}" for i in range(5)]
+    out = tmp_path / "out"
+    out.mkdir()
+    for k in ("tree", "rates", "ll"):
+        (out / k).mkdir()
+    mp.spawn(_fc_worker, args=(2, _free_port(), str(tmp_path), str(out), families, str(tmp_path / "cache")),
+             nprocs=2, join=True)
+    for rank in range(2):
+        status, fams = open(out / f"seen_{rank}.txt").read().split("\n")
+        assert status == "ok" and fams.split() == sorted(families)[rank::2]
+    for k in ("tree", "rates", "ll"):
+        for f in families:
+            assert (out / k / f"{f}.txt").exists() and (out / k / f"{f}.success").exists()
 
 
 def _siterm_worker(rank, world, port, out_root):
