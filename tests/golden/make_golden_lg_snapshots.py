@@ -47,6 +47,21 @@ def main():
             if f.startswith("Q_") and f.endswith(".txt"):
                 out[f[:-4]] = read_rate_matrix(os.path.join(odir, f)).to_numpy()
         assert np.max(np.abs(loss - g["loss"])) <= 1e-6 * np.max(np.abs(g["loss"])), "not the public API's trajectory"
+        # The same fit through the oracle's restatement of the reference's arithmetic: in fp32 it IS the run above,
+        # in fp64 it is what the reference would compute without its two float casts.  Stored: the fp64 last
+        # iterate and loss trace (ground truth for the fp64 CUDA path) and how far fp32 drifts from it.
+        import torch
+
+        from oracle.fit_oracle import fit_oracle
+
+        o32 = fit_oracle(list(g["q"]), g["counts"], None, g["jtt_ipw"], 0.1, 500, dtype=torch.float32)
+        drift32 = float(np.max(np.abs(o32["Q_last"] - out["Q_last"])))
+        assert drift32 <= 1e-6 * np.max(np.abs(out["Q_last"])), f"the fp32 oracle is not the reference run: {drift32}"
+        o64 = fit_oracle(list(g["q"]), g["counts"], None, g["jtt_ipw"], 0.1, 500, dtype=torch.float64)
+        out["fp64_Q_last"] = o64["Q_last"]
+        out["fp64_loss"] = np.asarray(o64["loss"])
+        out["fp32_vs_fp64_Q_last"] = np.array(np.max(np.abs(o64["Q_last"] - out["Q_last"])))
+        print("fp32 reference vs fp64 arithmetic at the last epoch:", out["fp32_vs_fp64_Q_last"])
         np.savez_compressed(OUT, **out)
         print({k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
 

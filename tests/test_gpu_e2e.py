@@ -54,31 +54,24 @@ def test_lg_demo_matches_reference_public_api(demo, tmp_path):
     assert np.max(np.abs(learned - g["learned"])) < 2e-3 * np.max(np.abs(g["learned"]))
     last = read_rate_matrix(os.path.join(mle, "Q_last.txt")).to_numpy()
     assert list(read_rate_matrix(out).index) == states and last.shape == (20, 20)
-    # The 2e-3 above is the two arg-mins landing on different iterates of a flat loss, not a trajectory
-    # difference: AT EQUAL EPOCHS (the power-of-two snapshots and the last iterate, files written by the
-    # unmodified reference stage: tests/golden/make_golden_lg_snapshots.py) the matrices agree to the fp32
-    # tolerance of the north star, and so does the iterate at the reference's own best epoch.
+    # Where the 2e-3 comes from (tests/golden/make_golden_lg_snapshots.py, run on the unmodified reference):
+    # the reference trains in fp32, this path in fp64.  AT EQUAL EPOCHS the power-of-two snapshots the reference
+    # stage wrote agree with ours to the fp32 tolerance of the north star up to epoch 256; by epoch 499 the
+    # reference's own arithmetic in fp32 has drifted 1.5e-3 from the same arithmetic in fp64 (the oracle port,
+    # which in fp32 reproduces the reference run to 1e-6 -- asserted when the golden is made), and ours sits on
+    # the fp64 trajectory to 1e-6: loss trace and last iterate.
     snap = np.load(os.path.join(GOLDEN, "e2e", "lg_snapshots.npz"))
     scale = np.max(np.abs(snap["Q_last"]))
-    names = sorted(k for k in snap.files if k.startswith("Q_") and k != "Q_best")
-    assert "Q_last" in names and "Q_256" in names and len(names) >= 10
+    names = sorted(k for k in snap.files if k.startswith("Q_") and k[2:].isdigit())
+    assert names == sorted(f"Q_{2**j}" for j in range(9))
     for name in names:
         ours = read_rate_matrix(os.path.join(mle, name + ".txt")).to_numpy()
         assert np.max(np.abs(ours - snap[name])) < 1e-4 * scale, name
-    from cherryml_b200.estimation import quantized_transitions_mle
-
-    best = int(snap["best_epoch"])
-    assert 0 < best < 499 and best != int(np.argmin(loss))  # the arg-mins do differ (else 2e-3 would be 1e-4)
-    odir = str(tmp_path / "at_reference_best_epoch")
-    quantized_transitions_mle(
-        count_matrices_path=os.path.join(_only(f"{cache}/count_transitions"), "output_count_matrices_dir", "result.txt"),
-        initialization_path=os.path.join(_only(f"{cache}/jtt_ipw"), "output_rate_matrix_dir", "result.txt"),
-        mask_path=None, output_rate_matrix_dir=odir, stationary_distribution_path=None,
-        rate_matrix_parameterization="pande_reversible", device="cuda", learning_rate=1e-1, num_epochs=best + 1,
-        do_adam=True)
-    at_best = read_rate_matrix(os.path.join(odir, "Q_last.txt")).to_numpy()
-    assert np.max(np.abs(at_best - snap["result"])) < 1e-4 * scale
-    assert np.max(np.abs(at_best - g["learned"])) < 1e-4 * scale
+    assert np.max(np.abs(loss - snap["fp64_loss"]) / np.abs(snap["fp64_loss"])) < 1e-6
+    assert np.max(np.abs(last - snap["fp64_Q_last"])) < 1e-6 * scale
+    drift = float(snap["fp32_vs_fp64_Q_last"])
+    assert 1e-4 * scale < drift < 2e-3 * scale
+    assert abs(np.max(np.abs(last - snap["Q_last"])) - drift) < 0.05 * drift  # our distance to the fp32 run IS that drift
 
 
 def test_coevolution_demo_matches_reference_public_api(demo, tmp_path):
