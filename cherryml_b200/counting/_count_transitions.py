@@ -189,6 +189,32 @@ def count_transitions(
     quantization_points = [float(q) for q in quantization_points]
     rank, world = _rank_world(process_group)
     my_families = get_process_args(rank, world, list(families))
+    # In-memory route (reference _cherry.py:279-336): the FastCherries stage of this process has just estimated
+    # the cherries of exactly these families from exactly this MSA directory and still holds the encoded
+    # residues and its results on the device -- count on them instead of parsing the files it wrote.
+    # Same counts, bit for bit (tests/test_gpu_fast_cherries.py); cherries only, one process.
+    if process_group is None and edge_or_cherry in ("cherry", "cherry++") and ingest == "native":
+        from ..phylogeny_estimation import _fast_cherries as _fc
+
+        hand = _fc.take_handoff(tree_dir, site_rates_dir, msa_dir, list(families), list(amino_acids))
+        if hand is not None:
+            from ..phylogeny_estimation._pipeline import lg_batch_from_fast_cherries
+            from ._device import count_raw, sorted_grid, symmetrize
+
+            S = len(amino_acids)
+            dev_batch = lg_batch_from_fast_cherries(hand["fams"], hand["out"], hand["grid"], hand["cats"], S,
+                                                    bool(use_cpp_implementation), hand["device"],
+                                                    n_threads=_ingest_threads(num_processes))
+            grid = sorted_grid(quantization_points)
+            with torch.cuda.device(dev_batch.msa.device):
+                grid_dev = torch.from_numpy(grid).to(dev_batch.msa.device)
+                counts = symmetrize(count_raw(dev_batch, grid_dev, int(grid.size), S), "lg", int(grid.size), S, False)
+            del hand, dev_batch
+            style = result_style or ("cpp" if use_cpp_implementation else "python")
+            _finish(counts, np.array(sorted(quantization_points)), list(amino_acids),
+                    output_count_matrices_dir, style, start_time, num_processes, rank, process_group)
+            logger.info("Done! (counted on the resident FastCherries results)")
+            return
     if ingest == "native" and len(my_families) > families_per_batch > 0:
         def build(fams):
             return build_lg_batch_native(

@@ -424,6 +424,36 @@ def fast_cherries(
                          quantization_grid_step, quantization_grid_num_steps, seed, device)
 
 
+# In-process hand-off to count_transitions (reference estimation_end_to_end/_cherry.py:279-336: the tree-free LG
+# pipeline estimates cherries and then counts on them): the encoded residues and the FastCherries results of
+# the LAST stage call stay on the device, keyed by the directories and families the counting stage will be
+# given, so that it does not parse the trees, site rates and MSAs it would otherwise read back from the files
+# this stage wrote (they are still written).  One entry; taken (removed) by the first matching call.
+_HANDOFF: Dict = {}
+
+
+def take_handoff(tree_dir, site_rates_dir, msa_dir, families, alphabet):
+    """The resident FastCherries results for exactly these directories / families / alphabet, or None."""
+    key = (os.path.realpath(tree_dir), os.path.realpath(site_rates_dir), os.path.realpath(msa_dir),
+           tuple(families), tuple(alphabet))
+    entry = _HANDOFF.pop("entry", None)
+    if entry is None or entry["key"] != key:
+        return None
+    # the files this stage wrote must still be the ones on disk (a later writer wins over the resident copy)
+    for path, stamp in entry["stamps"].items():
+        try:
+            st = os.stat(path)
+        except OSError:
+            return None
+        if (st.st_size, st.st_mtime_ns) != stamp:
+            return None
+    return entry
+
+
+def clear_handoff() -> None:
+    _HANDOFF.clear()
+
+
 def _fast_cherries_local(msa_dir, families, rate_matrix_path, num_rate_categories, max_iters, output_tree_dir,
                          output_site_rates_dir, output_likelihood_dir, quantization_grid_center,
                          quantization_grid_step, quantization_grid_num_steps, seed, device) -> None:
@@ -441,9 +471,10 @@ def _fast_cherries_local(msa_dir, families, rate_matrix_path, num_rate_categorie
     priors = np.array([2 * math.log(r) - 3 * r for r in cats])
     table = log_transition_table(Q, grid, cats, device)
     join = lambda d, ext: [os.path.join(d, f + ext) for f in families]  # noqa: E731
+    keep = os.environ.get("CHERRY_FC_HANDOFF", "1") != "0"
     with NativeMsas(join(msa_dir, ".txt"), alphabet) as msas:
         out = fast_cherries_device(msas.msa, msas.fams, len(alphabet), table, priors, weights, int(seed),
-                                   int(max_iters), device)
+                                   int(max_iters), device, keep_device=keep)
         n = len(families)
         elapsed = time.time() - t_start
         profiling = np.empty((n, 4))
@@ -454,3 +485,13 @@ def _fast_cherries_local(msa_dir, families, rate_matrix_path, num_rate_categorie
         msas.write_outputs(out, grid, cats, join(output_tree_dir, ".txt"), join(output_tree_dir, ".newick"),
                            join(output_site_rates_dir, ".txt"), join(output_likelihood_dir, ".txt"),
                            join(output_tree_dir, ".profiling"), profiling)
+        _HANDOFF.clear()
+        if keep:
+            stamps = {}
+            for pth in join(output_tree_dir, ".txt") + join(output_site_rates_dir, ".txt"):
+                st = os.stat(pth)
+                stamps[pth] = (st.st_size, st.st_mtime_ns)
+            _HANDOFF["entry"] = dict(
+                key=(os.path.realpath(output_tree_dir), os.path.realpath(output_site_rates_dir),
+                     os.path.realpath(msa_dir), tuple(families), tuple(alphabet)),
+                fams=np.array(msas.fams, copy=True), out=out, grid=grid, cats=cats, stamps=stamps, device=device)

@@ -61,6 +61,13 @@ def main():
         out["fp64_Q_last"] = o64["Q_last"]
         out["fp64_loss"] = np.asarray(o64["loss"])
         out["fp32_vs_fp64_Q_last"] = np.array(np.max(np.abs(o64["Q_last"] - out["Q_last"])))
+        # how well conditioned is the iterate after 500 Adam steps?  The same fp64 fit from an initialisation
+        # perturbed by 1e-14 relative: its distance is the floor for ANY two fp64 implementations.
+        rng = np.random.default_rng(0)
+        pert = g["jtt_ipw"] * (1.0 + 1e-14 * rng.standard_normal(g["jtt_ipw"].shape))
+        o64p = fit_oracle(list(g["q"]), g["counts"], None, pert, 0.1, 500, dtype=torch.float64)
+        out["fp64_sensitivity_Q_last"] = np.array(np.max(np.abs(o64p["Q_last"] - o64["Q_last"])))
+        print("fp64 last iterate under a 1e-14 perturbation of the initialisation moves by", out["fp64_sensitivity_Q_last"])
         print("fp32 reference vs fp64 arithmetic at the last epoch:", out["fp32_vs_fp64_Q_last"])
         np.savez_compressed(OUT, **out)
         print({k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})

@@ -68,7 +68,12 @@ def test_lg_demo_matches_reference_public_api(demo, tmp_path):
         ours = read_rate_matrix(os.path.join(mle, name + ".txt")).to_numpy()
         assert np.max(np.abs(ours - snap[name])) < 1e-4 * scale, name
     assert np.max(np.abs(loss - snap["fp64_loss"]) / np.abs(snap["fp64_loss"])) < 1e-6
-    assert np.max(np.abs(last - snap["fp64_Q_last"])) < 1e-6 * scale
+    # the iterate after 500 Adam steps is ill conditioned: a 1e-14 relative perturbation of the initialisation
+    # moves the fp64 oracle's own last iterate by fp64_sensitivity_Q_last (7e-6 relative, stored with the
+    # golden) while its loss trace moves by 1e-8 -- that, not 1e-6, is the floor for two fp64 implementations
+    floor = float(snap["fp64_sensitivity_Q_last"])
+    assert 1e-6 * scale < floor < 1e-4 * scale
+    assert np.max(np.abs(last - snap["fp64_Q_last"])) < 5 * floor
     drift = float(snap["fp32_vs_fp64_Q_last"])
     assert 1e-4 * scale < drift < 2e-3 * scale
     assert abs(np.max(np.abs(last - snap["Q_last"])) - drift) < 0.05 * drift  # our distance to the fp32 run IS that drift

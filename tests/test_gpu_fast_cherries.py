@@ -339,9 +339,20 @@ def test_in_memory_fast_cherries_to_counts_equals_the_text_route(tmp_path, cpp_p
                   max_iters=50, num_processes=1, verbose=False, output_tree_dir=dirs["tree"],
                   output_site_rates_dir=dirs["rates"], output_likelihood_dir=dirs["ll"])
     qp = _quantization_points(0.03, 1.1, 64)
+    from cherryml_b200.phylogeny_estimation import _fast_cherries as fc_stage
+
+    # (1) the stage pair as the pipeline runs it: count_transitions takes the resident FastCherries results
+    assert "entry" in fc_stage._HANDOFF
+    count_transitions(tree_dir=dirs["tree"], msa_dir=msa_dir, site_rates_dir=dirs["rates"], families=fams,
+                      amino_acids=list(AA), quantization_points=qp, edge_or_cherry="cherry++", num_processes=1,
+                      use_cpp_implementation=cpp_personality, output_count_matrices_dir=str(tmp_path / "counts_mem"))
+    assert "entry" not in fc_stage._HANDOFF  # taken
+    # (2) the reference's route: everything read back from the files (no hand-off left)
     count_transitions(tree_dir=dirs["tree"], msa_dir=msa_dir, site_rates_dir=dirs["rates"], families=fams,
                       amino_acids=list(AA), quantization_points=qp, edge_or_cherry="cherry++", num_processes=1,
                       use_cpp_implementation=cpp_personality, output_count_matrices_dir=dirs["counts"])
+    assert (open(os.path.join(dirs["counts"], "result.txt"), "rb").read()
+            == open(tmp_path / "counts_mem" / "result.txt", "rb").read())
     _, _, expected = read_count_matrices_array(os.path.join(dirs["counts"], "result.txt"))
     Q = read_rate_matrix(get_lg_path()).to_numpy()
     with fc.NativeMsas([os.path.join(msa_dir, f + ".txt") for f in fams], list(AA)) as msas:
