@@ -172,8 +172,14 @@ def reference_fit_arms(times, counts: torch.Tensor, num_epochs_full: int, cpu_ep
         cmd = [sys.executable, runner, "--counts", counts_path, "--init", init_path, "--device", arm,
                "--epochs", str(epochs), "--threads", str(cores), "--out", odir]
         _log(f"reference arm {S}x{S} {arm}: {epochs} epochs ...")
+        # a clean environment: torchrun pins its workers to OMP_NUM_THREADS=1 and exports its rendezvous
+        # variables; the reference arm is a plain single process with all host threads
+        env = {k: v for k, v in os.environ.items()
+               if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "RANK", "LOCAL_RANK",
+                            "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "MASTER_ADDR", "MASTER_PORT")
+               and not k.startswith("TORCHELASTIC")}
         try:
-            res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
             line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
             if res.returncode != 0 or not line:
                 out[arm] = {"error": (res.stderr or res.stdout)[-300:]}
