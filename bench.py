@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-families", type=int, default=0, help="families in the CPU sample (0 = 16 per core, >= 128)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--text-families", type=int, default=2048,
+                    help="families of the larger from-text run (e2e_text_large; 0 = skip)")
     ap.add_argument("--no-fit", action="store_true")
     ap.add_argument("--no-fast-cherries", action="store_true")
     ap.add_argument("--fc-families", type=int, default=2048, help="FastCherries families per GPU")
@@ -588,6 +590,15 @@ def run_ours(args):
             line["e2e_text"] = text_e2e_run(n_cpu_fam)
         except Exception as e:  # never lose the bench line over the extra measurement
             line["e2e_text"] = {"error": str(e)[:200]}
+        _log("e2e_text done")
+        if args.text_families > n_cpu_fam and world == 1:
+            # the same from-text path on a batch large enough that the per-call costs (thread start-up, the
+            # 320 KB read-back, kernel launches) no longer matter: what the ingest sustains
+            try:
+                line["e2e_text_large"] = text_e2e_run(args.text_families, seed=1, reps=2)
+            except Exception as e:
+                line["e2e_text_large"] = {"error": str(e)[:200]}
+            _log("e2e_text_large done")
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

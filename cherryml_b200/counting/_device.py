@@ -87,11 +87,7 @@ def sorted_grid(quantization_points: Sequence[float]) -> np.ndarray:
     grid = np.array(sorted(float(q) for q in quantization_points), dtype=np.float64)
     if grid.size == 0:
         raise ValueError("quantization_points is empty")
-    if grid.size > _lib.MAX_BUCKETS:
-        raise _lib.CherryError(
-            f"{grid.size} quantization points: at most {_lib.MAX_BUCKETS} are supported"
-        )
-    return grid
+    return grid  # more than _lib.MAX_BUCKETS points: count_raw makes several passes over sub-grids
 
 
 def validate_residues(msa: torch.Tensor, num_states: int) -> None:
@@ -144,7 +140,46 @@ def count_raw(
     tab: Optional[torch.Tensor] = None,
     out: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
-    """Raw directed integer histogram on the device.
+    """Raw directed integer histogram on the device (``_count_raw_one``).  The kernels address at most
+    ``_lib.MAX_BUCKETS`` (254) buckets through a one-byte table; the reference has no bound
+    (``_count_transitions.cpp:295-307``), so a longer grid is counted in passes over sub-grids of 252 points
+    extended by one neighbour on each side: a value's nearest grid point and both of that point's neighbours
+    are then in the same sub-grid, so the decision is the full grid's, and the values that fall to the two
+    extra points are masked out of the pass (they belong to the neighbouring pass)."""
+    if K <= _lib.MAX_BUCKETS:
+        return _count_raw_one(dev, grid_dev, K, S, tab, out)
+    if tab is not None:
+        raise _lib.CherryError(f"a precomputed bucket table addresses at most {_lib.MAX_BUCKETS} buckets")
+    device = dev.msa.device
+    if out is None:
+        shape = (K, S, S) if dev.kind == "lg" else (K, S * S, S * S)
+        out = torch.zeros(shape, dtype=torch.int64 if dev.kind == "lg" else torch.int32, device=device)
+    step = _lib.MAX_BUCKETS - 2
+    for lo in range(0, K, step):
+        hi = min(K, lo + step)
+        elo, ehi = max(0, lo - 1), min(K, hi + 1)
+        sub = grid_dev[elo:ehi].contiguous()
+        ks = ehi - elo
+        sub_tab = build_bucket_table(dev, sub, ks)
+        if dev.n_pairs:
+            if elo < lo:
+                sub_tab[sub_tab == 0] = _lib.NO_BUCKET
+            if ehi > hi:
+                sub_tab[sub_tab == ks - 1] = _lib.NO_BUCKET
+        part = _count_raw_one(dev, sub, ks, S, sub_tab, None)
+        out[lo:hi] += part[lo - elo: lo - elo + (hi - lo)]
+    return out
+
+
+def _count_raw_one(
+    dev: DeviceBatch,
+    grid_dev: torch.Tensor,
+    K: int,
+    S: int,
+    tab: Optional[torch.Tensor] = None,
+    out: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """Raw directed integer histogram on the device, K <= _lib.MAX_BUCKETS.
 
     LG: uint64 ``[K,S,S]`` (returned as an int64 tensor); co: uint32 ``[K,S*S,S*S]``
     (returned as an int32 tensor).  ``out`` is accumulated into when given.

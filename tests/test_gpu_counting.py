@@ -270,10 +270,31 @@ def test_full_size_properties_co():
     assert np.array_equal(got, exp)
 
 
-def test_too_many_quantization_points_is_an_error():
-    syn = synthetic_lg(2, 8, 32, 4, seed=1)
-    with pytest.raises(_lib.CherryError):
-        count_batch(as_count_batch(syn), [0.001 * 1.01**i for i in range(300)], 20, directed=False)
+@pytest.mark.parametrize("kind", ["lg", "co"])
+def test_more_quantization_points_than_one_pass_addresses(kind):
+    """The reference has no bound on the number of quantization points (_count_transitions.cpp:295-307,
+    quantization_grid_num_steps >= 127 gives K > 254); the kernels address 254 buckets per pass, longer grids
+    are counted in passes over overlapping sub-grids.  K = 300 and K = 600, bit-exact against the oracle,
+    including values exactly at and one ulp around the sub-grid seams."""
+    for K in (300, 600):
+        grid = [0.0005 * 1.02**i for i in range(K)]
+        if kind == "lg":
+            syn = synthetic_lg(6, 64, 96, 4, seed=K)
+        else:
+            syn = synthetic_co(3, 32, 60, seed=K)
+        # pair lengths on and around the grid points next to the seams (rate 1 exists in neither batch's
+        # categories exactly, so also plain multiples are exercised through the random lengths)
+        t = syn["pair_t"].clone()
+        g = np.array(grid)
+        seam = np.concatenate([g[250:256], np.nextafter(g[250:256], 0), np.nextafter(g[250:256], np.inf),
+                               np.sqrt(g[250:255] * g[251:256])])
+        n = min(len(seam), t.numel())
+        t[:n] = torch.from_numpy(seam[:n])
+        syn["pair_t"] = t
+        batch = as_count_batch(syn)
+        got = count_batch(batch, grid, 20, directed=False).cpu().numpy()
+        assert np.array_equal(got, count_batch_oracle(batch, grid, 20, False))
+        assert got[252:].sum() > 0 and got[:252].sum() > 0
 
 
 def test_full_size_properties_lg():
