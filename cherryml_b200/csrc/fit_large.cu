@@ -269,8 +269,10 @@ struct SqSchedule {
   int queue[2];                        // work counters: forward, backward
   int n_levels;                        // max_k s_k
   int level_off[kSStore + 1];          // prefix sums of active buckets per level
-  int ksplit;                          // split-K factor of every tile (few active buckets: more CTAs per tile)
-  int pad[3];
+  int ks[kSStore];                     // split-K factor of the tiles of a level (few active buckets: more CTAs per tile)
+  int item_off[kSStore + 1];           // prefix sums of the work items (active buckets x tiles x ks) per level
+  int ksmax;                           // stride of a bucket's partial matrices
+  int pad[2];
   // followed in memory by: int active[kSStore][K]; int done_fwd[K][kSStore]; int done_bwd[K][kSStore + 1];
   // int rank[K] (position of bucket k in level 0's list); int tile_arrive[K][tiles]
 };
@@ -307,9 +309,8 @@ squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__
   const int tiles_n = Sp / BT, tiles = tiles_n * tiles_n;
   const size_t n_p = (size_t)Sp * Sp;
   const int n_levels = sched->n_levels;
-  const int total_buckets = sched->level_off[n_levels];
-  const int ksplit = sched->ksplit;
-  const int total_items = total_buckets * tiles * ksplit;
+  const int ksmax = sched->ksmax;
+  const int total_items = sched->item_off[n_levels];
   const int* active = sq_active(sched);
   int* done_fwd = sq_done_fwd(sched, K);
   int* done_bwd = sq_done_bwd(sched, K);
@@ -319,7 +320,7 @@ squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__
   // tile at a third of the SM's DMMA rate).  Every CTA writes its partial tile; the one that
   // arrives last adds them in z order (so the result does not depend on who is last), writes
   // the tile and moves the bucket's completion counter.
-  auto finish_tile = [&](int k, int tile, int m0, int n0, double* out) -> bool {
+  auto finish_tile = [&](int k, int tile, int m0, int n0, double* out, int ksplit) -> bool {
     if (ksplit == 1) return true;
     __threadfence();
     __syncthreads();
@@ -332,7 +333,7 @@ squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__
     __syncthreads();
     if (!s_last) return false;
     __threadfence();
-    const double* pb = partial + (size_t)rank[k] * ksplit * n_p;
+    const double* pb = partial + (size_t)rank[k] * ksmax * n_p;
     constexpr int NQ = BT * BT / 2 / GEMM_THREADS;
     double2 v[NQ];
 #pragma unroll
@@ -365,13 +366,15 @@ squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__
     __syncthreads();
     const int item = s_item;
     if (item >= total_items) return;
-    const int z = item % ksplit, item_t = item / ksplit;
-    const int bidx_linear = item_t / tiles, tile = item_t - bidx_linear * tiles;
-    // forward walks the levels upwards, backward downwards
-    const int pos = BWD ? (total_buckets - 1 - bidx_linear) : bidx_linear;
+    // forward walks the levels upwards, backward downwards (the same decoding on the mirrored index)
+    const int pos = BWD ? (total_items - 1 - item) : item;
     int level = 0;
-    while (level + 1 < n_levels && sched->level_off[level + 1] <= pos) ++level;
-    const int k = active[level * K + (pos - sched->level_off[level])];
+    while (level + 1 < n_levels && sched->item_off[level + 1] <= pos) ++level;
+    const int ksplit = sched->ks[level];
+    const int local = pos - sched->item_off[level];
+    const int z = local % ksplit, item_t = local / ksplit;
+    const int bidx = item_t / tiles, tile = item_t - bidx * tiles;
+    const int k = active[level * K + bidx];
     const int m0 = (tile / tiles_n) * BT, n0 = (tile % tiles_n) * BT;
     double* Xi = (level == 0) ? X0 + (size_t)k * n_p : chain + ((size_t)k * slots_per_bucket + (level - 1)) * n_p;
     double* out = chain + ((size_t)k * slots_per_bucket + level) * n_p;  // slot level+1
@@ -379,9 +382,9 @@ squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__
       if (level > 0) wait_counter(done_fwd + k * kSStore + (level - 1), tiles, status_flag);
       const GemmTerm t0{Xi, Xi, 0, 0};
       const int total = Sp / BK;
-      double* dst = ksplit == 1 ? out : partial + ((size_t)rank[k] * ksplit + z) * n_p;
+      double* dst = ksplit == 1 ? out : partial + ((size_t)rank[k] * ksmax + z) * n_p;
       gemm_tile([&](int) { return t0; }, Sp, m0, n0, total * z / ksplit, total * (z + 1) / ksplit, smem, dst, false);
-      if (!finish_tile(k, tile, m0, n0, out)) continue;
+      if (!finish_tile(k, tile, m0, n0, out, ksplit)) continue;
       __threadfence();  // every thread publishes its part of the tile before the counter moves
       __syncthreads();
       if (threadIdx.x == 0) atomicAdd(done_fwd + k * kSStore + level, 1);
@@ -393,10 +396,10 @@ squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__
       if (level + 1 < s_arr[k]) wait_counter(done_bwd + k * (kSStore + 1) + (level + 1), tiles, status_flag);
       const GemmTerm t0{Xb, Xi, 0, 1}, t1{Xi, Xb, 1, 0};
       const int total = 2 * (Sp / BK);
-      double* dst = ksplit == 1 ? out : partial + ((size_t)rank[k] * ksplit + z) * n_p;
+      double* dst = ksplit == 1 ? out : partial + ((size_t)rank[k] * ksmax + z) * n_p;
       gemm_tile([&](int idx) { return idx == 0 ? t0 : t1; }, Sp, m0, n0, total * z / ksplit,
                 total * (z + 1) / ksplit, smem, dst, false);
-      if (!finish_tile(k, tile, m0, n0, out)) continue;
+      if (!finish_tile(k, tile, m0, n0, out, ksplit)) continue;
       __threadfence();
       __syncthreads();
       if (threadIdx.x == 0) atomicAdd(done_bwd + k * (kSStore + 1) + level, 1);
@@ -747,18 +750,27 @@ __global__ void coef_kernel(const double* __restrict__ t, int K, LargeScalars* _
     sched->n_levels = n_levels;
     sched->queue[0] = 0;
     sched->queue[1] = 0;
-    // split K so that the widest level keeps about n_ctas CTAs busy (at most 4 ways, and within
-    // the partial buffer: one slot per (active bucket, z))
-    int ks = 1;
-    if (level_n[0] > 0) {
-      // about 2.5 waves of work items in the widest level (one K=400 tile is 60-100 us on a CTA: with
-      // 1.1 waves of them the second wave runs nearly empty)
-      ks = (5 * n_ctas / 2 + level_n[0] * tiles - 1) / (level_n[0] * tiles);
-      if (ks > sq_ksplit_max) ks = sq_ksplit_max;
-      if (ks * level_n[0] > kSqPartialSlots) ks = kSqPartialSlots / level_n[0];
-      if (ks < 1) ks = 1;
+    // split K level by level: about 2.5 waves of work items per level (one K=400 tile is 60-100 us on a
+    // CTA: with 1.1 waves of them the second wave runs nearly empty), at most sq_ksplit_max ways and within
+    // the partial buffer (one slot per (bucket of level 0, z))
+    int cap = sq_ksplit_max;
+    if (level_n[0] > 0 && cap * level_n[0] > kSqPartialSlots) cap = kSqPartialSlots / level_n[0];
+    if (cap < 1) cap = 1;
+    int items = 0, ksmax = 1;
+    for (int lvl = 0; lvl < kSStore; ++lvl) {
+      int ks = 1;
+      if (level_n[lvl] > 0) {
+        ks = (5 * n_ctas / 2 + level_n[lvl] * tiles - 1) / (level_n[lvl] * tiles);
+        if (ks > cap) ks = cap;
+        if (ks < 1) ks = 1;
+      }
+      sched->ks[lvl] = ks;
+      sched->item_off[lvl] = items;
+      items += level_n[lvl] * tiles * ks;
+      if (level_n[lvl] > 0 && ks > ksmax) ksmax = ks;
     }
-    sched->ksplit = ks;
+    sched->item_off[kSStore] = items;
+    sched->ksmax = ksmax;
   }
 }
 
@@ -1699,7 +1711,7 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   int* df_state_bwd = reinterpret_cast<int*>(base + p.df_bwd.off_state);
   int* deg_arr = reinterpret_cast<int*>(base + p.off_deg);
   static const bool full_degree = getenv("CHERRY_FIT_FULL_DEGREE") != nullptr;  // A/B switch: round-1 Taylor pass
-  static const int sq_ksplit_max = getenv("CHERRY_FIT_SQ_KSPLIT") ? atoi(getenv("CHERRY_FIT_SQ_KSPLIT")) : 5;  // A/B switch
+  static const int sq_ksplit_max = getenv("CHERRY_FIT_SQ_KSPLIT") ? atoi(getenv("CHERRY_FIT_SQ_KSPLIT")) : 2;  // A/B switch (graph-replayed epochs: 1 -> 1.04 ms, 2 -> 0.94, 5 -> 0.96)
   coef_kernel<<<1, 256, 0, stream>>>(a.t, a.K, sc, s_arr, deg_arr, w, tau, a.status_flag, sched, p.tiles,
                                      (KGROUPS == 1 ? 2 : 1) * sm_count(), df_state_fwd,
                                      (int)df_state_ints(p.df_fwd.n_mats, p.tiles, (int)p.df_fwd.groups.size()),
