@@ -20,8 +20,10 @@ int check_args(const cherry_fit_args* a, bool training) {
 int one_epoch(const cherry_fit_args& a, cudaStream_t stream) {
   int rc;
   if (a.S <= cherry::kSmallFitMaxS) {
-    if ((rc = cherry::fit_small_expm(a, stream))) return rc;
-    return cherry::fit_small_update(a, 1, stream);
+    // ONE launch per epoch: the last CTA of every problem runs its parameter update (fit_small.cu)
+    static const bool no_fuse = getenv("CHERRY_FIT_SMALL_UNFUSED") != nullptr;  // A/B switch
+    if ((rc = cherry::fit_small_expm(a, stream, nullptr, !no_fuse))) return rc;
+    return no_fuse ? cherry::fit_small_update(a, 1, stream) : 0;
   }
   if ((rc = cherry::fit_large_expm(a, stream))) return rc;
   return cherry::fit_large_update(a, 1, stream);
@@ -83,7 +85,7 @@ int cherry_fit_workspace_bytes(int S, int K, int n_problems, size_t* bytes) {
     size_t sb = 0, smem = 0;
     int rc = cherry::fit_small_workspace(S, &ns, &sp, &sb, &smem);
     if (rc) return rc;
-    *bytes = (size_t)sp * sb * n_problems * K;
+    *bytes = cherry::fit_small_workspace_bytes(S, K, n_problems);
     return 0;
   }
   return cherry::fit_large_workspace_bytes(S, K, n_problems, bytes);

@@ -9,7 +9,8 @@ constexpr int kSmallFitMaxS = 32;
 // S <= 32: everything in shared memory, one CTA per (problem, bucket).  fit_small.cu
 int fit_small_workspace(int S, int* n_smem_slots, int* spill_slots, size_t* slot_bytes, size_t* smem_bytes,
                         int grid = -1);  // grid < 0: sizing only (the resident slots of the latency shape)
-int fit_small_expm(const cherry_fit_args& a, cudaStream_t stream, double* P_out = nullptr);
+int fit_small_expm(const cherry_fit_args& a, cudaStream_t stream, double* P_out = nullptr, bool fuse_update = false);
+size_t fit_small_workspace_bytes(int S, int K, int n_problems);
 // `reduced` (optional): [P][S][S] gradient totals followed by [P] loss totals, already summed
 // over the buckets (of all ranks); replaces the per-bucket pieces dQ_part / loss_part.
 int fit_small_update(const cherry_fit_args& a, int mode, cudaStream_t stream, const double* reduced = nullptr);

@@ -109,6 +109,201 @@ __device__ __forceinline__ double block_reduce_max(double v, double* red) {
   return t;
 }
 
+struct UpdateArgs {
+  int S, K, n_problems, num_epochs_total;
+  const double* mask;   // [S][S]
+  double* theta;        // [P][S + S(S-1)/2]
+  double* adam_m;
+  double* adam_v;
+  double* Q;            // [P][S][S]
+  double* Q_best;       // [P][S][S]
+  double* Q_last;       // [P][S][S]
+  double* best_loss;    // [P]
+  double* loss_trace;   // [num_epochs_total][P]
+  double* snapshots;    // [n_snap][S][S] for problem 0 or null
+  int n_snapshots;
+  const double* dQ_part;    // [P*K][S][S]
+  const double* loss_part;  // [P*K]
+  const double* sumC;       // [P]
+  int* epoch_counter;       // [P] device ints: epochs completed so far, per problem
+  double lr_pi, lr_upper, beta1, beta2, eps;
+  int do_adam, loss_normalization;
+  int best_mode;  // 0: first epoch always becomes the best (trainer.py:179); 1: best starts at +inf
+  int mode;       // 0: only theta -> Q; 1: full update
+};
+
+// The parameter update of one problem by one CTA of NT threads; `sm` = 4 S*S + 4 S doubles of shared memory,
+// `red` = NT / 32 doubles, `sh_improved_p` = one shared int.  Called by fit_update_small (one CTA per problem)
+// and, in training, by the CTA of expm_loss_grad_small that finishes a problem's last bucket.
+template <int NT>
+__device__ __forceinline__ void update_small_body(const UpdateArgs& a, int p, double* sm, double* red,
+                                                  int* sh_improved_p) {
+  int& sh_improved = *sh_improved_p;
+  const int tid = threadIdx.x, S = a.S, SS = S * S;
+  const int n_upper = S * (S - 1) / 2, n_theta = S + n_upper;
+  double* G = sm;             // dL/dQ
+  double* sv = sm + SS;       // masked symmetric softplus
+  double* sg = sm + 2 * SS;   // sigmoid(u) per (i<j), stored at [i][j]
+  double* dM = sm + 3 * SS;
+  double* pi = sm + 4 * SS;   // softmax(pi logits)
+  double* rr = pi + S;        // sqrt(pi)
+  double* dr = rr + S;
+  double* dpi = dr + S;
+  double* theta = a.theta + (size_t)p * n_theta;
+  double* Q = a.Q + (size_t)p * SS;
+  const int epoch = a.epoch_counter[p];
+
+  if (a.mode == 1) {
+    // ---- reduce the per-bucket pieces in bucket order
+    const double scale = a.loss_normalization ? 1.0 / a.sumC[p] : 1.0;
+    for (int e = tid; e < SS; e += NT) {
+      // loads of 8 buckets in flight, added in bucket order (same result as a plain loop)
+      double acc = 0.0;
+      const double* src = a.dQ_part + (size_t)p * a.K * SS + e;
+      for (int k0 = 0; k0 < a.K; k0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (k0 + j < a.K) ? __ldcg(src + (size_t)(k0 + j) * SS) : 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += v[j];
+      }
+      G[e] = acc * scale;
+    }
+    // stage the per-bucket losses in shared memory (parallel loads), then add them in order
+    for (int k = tid; k < a.K && k < SS; k += NT) sv[k] = __ldcg(a.loss_part + (size_t)p * a.K + k);
+    __syncthreads();
+    double lp = 0.0;
+    if (tid == 0) {
+      for (int k = 0; k < a.K; ++k) lp += (k < SS) ? sv[k] : __ldcg(a.loss_part + (size_t)p * a.K + k);
+      lp *= scale;
+      if (epoch < a.num_epochs_total) a.loss_trace[(size_t)epoch * a.n_problems + p] = lp;
+      const double best = a.best_loss[p];
+      // trainer.py:179 (`best_loss is None or loss < best_loss`) vs the per-site variant that
+      // starts from best = +inf (_cherryml_vectorized.py:341, 366)
+      const int improved = (epoch == 0 && a.best_mode == 0) ? 1 : (lp < best);
+      if (improved) a.best_loss[p] = lp;
+      sh_improved = improved;
+    }
+    __syncthreads();
+    // ---- best iterate and power-of-two snapshots of the Q this loss belongs to
+    const bool snap = (p == 0) && a.snapshots && ((epoch & (epoch + 1)) == 0);
+    int snap_idx = 0;
+    if (snap) {
+      int e1 = epoch + 1;
+      while (e1 > 1) { e1 >>= 1; ++snap_idx; }
+    }
+    for (int e = tid; e < SS; e += NT) {
+      const double q = Q[e];
+      if (sh_improved) a.Q_best[(size_t)p * SS + e] = q;
+      a.Q_last[(size_t)p * SS + e] = q;
+      if (snap && snap_idx < a.n_snapshots) a.snapshots[(size_t)snap_idx * SS + e] = q;
+    }
+  }
+  // ---- softmax(pi logits), sqrt
+  {
+    double mx = -INFINITY;
+    for (int i = tid; i < S; i += NT) mx = fmax(mx, theta[i]);
+    mx = block_reduce_max<NT>(mx, red);
+    double se = 0.0;
+    for (int i = tid; i < S; i += NT) se += exp(theta[i] - mx);
+    se = block_reduce_sum<NT>(se, red);
+    for (int i = tid; i < S; i += NT) {
+      pi[i] = exp(theta[i] - mx) / se;
+      rr[i] = sqrt(pi[i]);
+    }
+    __syncthreads();
+  }
+  if (a.mode == 1) {
+    // ---- adjoint of Q = M - diag(rowsum M), M_ij = s_ij r_j / r_i
+    for (int e = tid; e < SS; e += NT) {
+      const int i = e / S, j = e - i * S;
+      double sval = 0.0, sig = 0.0;
+      if (i != j) {
+        const int lo = i < j ? i : j, hi = i < j ? j : i;
+        const double u = theta[S + cherry::triu_index(lo, hi, S)];
+        sval = a.mask[e] * cherry::softplus_d(u);
+        sig = cherry::softplus_grad_d(u);
+      }
+      sv[e] = sval;
+      sg[e] = sig;
+      dM[e] = (i != j) ? (G[e] - G[i * S + i]) : 0.0;
+    }
+    __syncthreads();
+    // dL/dr_i = sum_j dM_ji s_ji / r_j  -  sum_j dM_ij s_ij r_j / r_i^2
+    for (int i = tid; i < S; i += NT) {
+      double col = 0.0, row = 0.0;
+      for (int j = 0; j < S; ++j) {
+        col += dM[j * S + i] * sv[j * S + i] / rr[j];
+        row += dM[i * S + j] * sv[i * S + j] * rr[j];
+      }
+      dr[i] = col - row / (rr[i] * rr[i]);
+      dpi[i] = dr[i] / (2.0 * rr[i]);
+    }
+    __syncthreads();
+    double dot = 0.0;
+    for (int i = tid; i < S; i += NT) dot += pi[i] * dpi[i];
+    dot = block_reduce_sum<NT>(dot, red);
+    const int step = epoch + 1;
+    const double bc1 = 1.0 - pow(a.beta1, (double)step);
+    const double bc2s = sqrt(1.0 - pow(a.beta2, (double)step));
+    double* am = a.adam_m + (size_t)p * n_theta;
+    double* av = a.adam_v + (size_t)p * n_theta;
+    // upper-diagonal parameters (before the pi logits change: their gradient uses the old r)
+    for (int e = tid; e < SS; e += NT) {
+      const int i = e / S, j = e - i * S;
+      if (i < j) {
+        const double ds_ij = dM[e] * rr[j] / rr[i], ds_ji = dM[j * S + i] * rr[i] / rr[j];
+        const double g = sg[e] * (a.mask[e] * ds_ij + a.mask[j * S + i] * ds_ji);
+        const int idx = S + cherry::triu_index(i, j, S);
+        cherry::optimizer_step(theta[idx], am[idx], av[idx], g, a.lr_upper, a.do_adam, a.beta1,
+                               a.beta2, a.eps, bc1, bc2s);
+      }
+    }
+    for (int i = tid; i < S; i += NT) {
+      const double g = pi[i] * (dpi[i] - dot);
+      cherry::optimizer_step(theta[i], am[i], av[i], g, a.lr_pi, a.do_adam, a.beta1, a.beta2, a.eps,
+                             bc1, bc2s);
+    }
+    __syncthreads();
+    // ---- new softmax for the next epoch's Q
+    double mx = -INFINITY;
+    for (int i = tid; i < S; i += NT) mx = fmax(mx, theta[i]);
+    mx = block_reduce_max<NT>(mx, red);
+    double se = 0.0;
+    for (int i = tid; i < S; i += NT) se += exp(theta[i] - mx);
+    se = block_reduce_sum<NT>(se, red);
+    for (int i = tid; i < S; i += NT) {
+      pi[i] = exp(theta[i] - mx) / se;
+      rr[i] = sqrt(pi[i]);
+    }
+    __syncthreads();
+  }
+  // ---- Q(theta): off-diagonal M, then the diagonal from the row sums (fixed order)
+  for (int e = tid; e < SS; e += NT) {
+    const int i = e / S, j = e - i * S;
+    double val = 0.0;
+    if (i != j) {
+      const int lo = i < j ? i : j, hi = i < j ? j : i;
+      const double u = theta[S + cherry::triu_index(lo, hi, S)];
+      val = a.mask[e] * cherry::softplus_d(u) * rr[j] / rr[i];
+    }
+    G[e] = val;  // reuse as M
+  }
+  __syncthreads();
+  for (int e = tid; e < SS; e += NT) {
+    const int i = e / S, j = e - i * S;
+    if (i == j) {
+      double rs = 0.0;
+      for (int k = 0; k < S; ++k) rs += G[i * S + k];
+      Q[e] = -rs;
+    } else {
+      Q[e] = G[e];
+    }
+  }
+  if (a.mode == 1 && tid == 0) a.epoch_counter[p] = epoch + 1;
+}
+
+
 // grid.x = n_problems * K.  Problem p = blockIdx.x / K owns Q[p], buckets (p, 0..K-1).
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
@@ -116,10 +311,12 @@ expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__
                      const double* __restrict__ Call, int S, int K, int n_smem_slots,
                      double* __restrict__ spill_all, int spill_slots, double* __restrict__ dQ_part,
                      double* __restrict__ loss_part, int* __restrict__ overflow_flag,
-                     double* __restrict__ P_out) {
+                     double* __restrict__ P_out, UpdateArgs ua, int* __restrict__ arrive) {
+  // arrive != nullptr (training): the CTA that finishes a problem's LAST bucket runs the parameter update of
+  // that problem right here (update_small_body) instead of a second launch -- one kernel per epoch
   extern __shared__ double smem[];
   __shared__ double red[NT / 32];
-  __shared__ int sh_m, sh_s;
+  __shared__ int sh_m, sh_s, sh_last, sh_improved;
   const int tid = threadIdx.x;
   const int b = blockIdx.x, prob = b / K;
   const int nt = (S + 7) / 8, spad = nt * 8, ld = spad + 4, slot_elems = spad * ld;
@@ -244,198 +441,29 @@ expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__
       out[e] = tau * (Bbar[i * ld + j] + cm * Hbar[i * ld + j]);
     }
   }
+  if (arrive == nullptr) return;
+  // ---- fused update: last arriver of the problem (every CTA of the problem gets here: the early exits above
+  // are the forward-only call and an error that is reported through overflow_flag)
+  __threadfence();  // this bucket's gradient and loss are visible before the ticket
+  __syncthreads();
+  if (tid == 0) {
+    const int old = atomicAdd(arrive + prob, 1);
+    sh_last = (old == K - 1);
+    if (sh_last) arrive[prob] = 0;  // ready for the next epoch
+  }
+  __syncthreads();
+  if (!sh_last) return;
+  __threadfence();
+  update_small_body<NT>(ua, prob, smem, red, &sh_improved);
 }
 
-struct UpdateArgs {
-  int S, K, n_problems, num_epochs_total;
-  const double* mask;   // [S][S]
-  double* theta;        // [P][S + S(S-1)/2]
-  double* adam_m;
-  double* adam_v;
-  double* Q;            // [P][S][S]
-  double* Q_best;       // [P][S][S]
-  double* Q_last;       // [P][S][S]
-  double* best_loss;    // [P]
-  double* loss_trace;   // [num_epochs_total][P]
-  double* snapshots;    // [n_snap][S][S] for problem 0 or null
-  int n_snapshots;
-  const double* dQ_part;    // [P*K][S][S]
-  const double* loss_part;  // [P*K]
-  const double* sumC;       // [P]
-  int* epoch_counter;       // [P] device ints: epochs completed so far, per problem
-  double lr_pi, lr_upper, beta1, beta2, eps;
-  int do_adam, loss_normalization;
-  int best_mode;  // 0: first epoch always becomes the best (trainer.py:179); 1: best starts at +inf
-  int mode;       // 0: only theta -> Q; 1: full update
-};
 
 // grid.x = n_problems; one CTA handles one problem.  Dynamic smem: 4 S*S + 4 S doubles.
 __global__ void __launch_bounds__(kSmallThreads) fit_update_small(UpdateArgs a) {
   extern __shared__ double sm[];
   __shared__ double red[kSmallThreads / 32];
   __shared__ int sh_improved;
-  const int tid = threadIdx.x, S = a.S, SS = S * S, p = blockIdx.x;
-  const int n_upper = S * (S - 1) / 2, n_theta = S + n_upper;
-  double* G = sm;             // dL/dQ
-  double* sv = sm + SS;       // masked symmetric softplus
-  double* sg = sm + 2 * SS;   // sigmoid(u) per (i<j), stored at [i][j]
-  double* dM = sm + 3 * SS;
-  double* pi = sm + 4 * SS;   // softmax(pi logits)
-  double* rr = pi + S;        // sqrt(pi)
-  double* dr = rr + S;
-  double* dpi = dr + S;
-  double* theta = a.theta + (size_t)p * n_theta;
-  double* Q = a.Q + (size_t)p * SS;
-  const int epoch = a.epoch_counter[p];
-
-  if (a.mode == 1) {
-    // ---- reduce the per-bucket pieces in bucket order
-    const double scale = a.loss_normalization ? 1.0 / a.sumC[p] : 1.0;
-    for (int e = tid; e < SS; e += kSmallThreads) {
-      // loads of 8 buckets in flight, added in bucket order (same result as a plain loop)
-      double acc = 0.0;
-      const double* src = a.dQ_part + (size_t)p * a.K * SS + e;
-      for (int k0 = 0; k0 < a.K; k0 += 8) {
-        double v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (k0 + j < a.K) ? src[(size_t)(k0 + j) * SS] : 0.0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc += v[j];
-      }
-      G[e] = acc * scale;
-    }
-    // stage the per-bucket losses in shared memory (parallel loads), then add them in order
-    for (int k = tid; k < a.K && k < SS; k += kSmallThreads) sv[k] = a.loss_part[(size_t)p * a.K + k];
-    __syncthreads();
-    double lp = 0.0;
-    if (tid == 0) {
-      for (int k = 0; k < a.K; ++k) lp += (k < SS) ? sv[k] : a.loss_part[(size_t)p * a.K + k];
-      lp *= scale;
-      if (epoch < a.num_epochs_total) a.loss_trace[(size_t)epoch * a.n_problems + p] = lp;
-      const double best = a.best_loss[p];
-      // trainer.py:179 (`best_loss is None or loss < best_loss`) vs the per-site variant that
-      // starts from best = +inf (_cherryml_vectorized.py:341, 366)
-      const int improved = (epoch == 0 && a.best_mode == 0) ? 1 : (lp < best);
-      if (improved) a.best_loss[p] = lp;
-      sh_improved = improved;
-    }
-    __syncthreads();
-    // ---- best iterate and power-of-two snapshots of the Q this loss belongs to
-    const bool snap = (p == 0) && a.snapshots && ((epoch & (epoch + 1)) == 0);
-    int snap_idx = 0;
-    if (snap) {
-      int e1 = epoch + 1;
-      while (e1 > 1) { e1 >>= 1; ++snap_idx; }
-    }
-    for (int e = tid; e < SS; e += kSmallThreads) {
-      const double q = Q[e];
-      if (sh_improved) a.Q_best[(size_t)p * SS + e] = q;
-      a.Q_last[(size_t)p * SS + e] = q;
-      if (snap && snap_idx < a.n_snapshots) a.snapshots[(size_t)snap_idx * SS + e] = q;
-    }
-  }
-  // ---- softmax(pi logits), sqrt
-  {
-    double mx = -INFINITY;
-    for (int i = tid; i < S; i += kSmallThreads) mx = fmax(mx, theta[i]);
-    mx = block_reduce_max<kSmallThreads>(mx, red);
-    double se = 0.0;
-    for (int i = tid; i < S; i += kSmallThreads) se += exp(theta[i] - mx);
-    se = block_reduce_sum<kSmallThreads>(se, red);
-    for (int i = tid; i < S; i += kSmallThreads) {
-      pi[i] = exp(theta[i] - mx) / se;
-      rr[i] = sqrt(pi[i]);
-    }
-    __syncthreads();
-  }
-  if (a.mode == 1) {
-    // ---- adjoint of Q = M - diag(rowsum M), M_ij = s_ij r_j / r_i
-    for (int e = tid; e < SS; e += kSmallThreads) {
-      const int i = e / S, j = e - i * S;
-      double sval = 0.0, sig = 0.0;
-      if (i != j) {
-        const int lo = i < j ? i : j, hi = i < j ? j : i;
-        const double u = theta[S + cherry::triu_index(lo, hi, S)];
-        sval = a.mask[e] * cherry::softplus_d(u);
-        sig = cherry::softplus_grad_d(u);
-      }
-      sv[e] = sval;
-      sg[e] = sig;
-      dM[e] = (i != j) ? (G[e] - G[i * S + i]) : 0.0;
-    }
-    __syncthreads();
-    // dL/dr_i = sum_j dM_ji s_ji / r_j  -  sum_j dM_ij s_ij r_j / r_i^2
-    for (int i = tid; i < S; i += kSmallThreads) {
-      double col = 0.0, row = 0.0;
-      for (int j = 0; j < S; ++j) {
-        col += dM[j * S + i] * sv[j * S + i] / rr[j];
-        row += dM[i * S + j] * sv[i * S + j] * rr[j];
-      }
-      dr[i] = col - row / (rr[i] * rr[i]);
-      dpi[i] = dr[i] / (2.0 * rr[i]);
-    }
-    __syncthreads();
-    double dot = 0.0;
-    for (int i = tid; i < S; i += kSmallThreads) dot += pi[i] * dpi[i];
-    dot = block_reduce_sum<kSmallThreads>(dot, red);
-    const int step = epoch + 1;
-    const double bc1 = 1.0 - pow(a.beta1, (double)step);
-    const double bc2s = sqrt(1.0 - pow(a.beta2, (double)step));
-    double* am = a.adam_m + (size_t)p * n_theta;
-    double* av = a.adam_v + (size_t)p * n_theta;
-    // upper-diagonal parameters (before the pi logits change: their gradient uses the old r)
-    for (int e = tid; e < SS; e += kSmallThreads) {
-      const int i = e / S, j = e - i * S;
-      if (i < j) {
-        const double ds_ij = dM[e] * rr[j] / rr[i], ds_ji = dM[j * S + i] * rr[i] / rr[j];
-        const double g = sg[e] * (a.mask[e] * ds_ij + a.mask[j * S + i] * ds_ji);
-        const int idx = S + cherry::triu_index(i, j, S);
-        cherry::optimizer_step(theta[idx], am[idx], av[idx], g, a.lr_upper, a.do_adam, a.beta1,
-                               a.beta2, a.eps, bc1, bc2s);
-      }
-    }
-    for (int i = tid; i < S; i += kSmallThreads) {
-      const double g = pi[i] * (dpi[i] - dot);
-      cherry::optimizer_step(theta[i], am[i], av[i], g, a.lr_pi, a.do_adam, a.beta1, a.beta2, a.eps,
-                             bc1, bc2s);
-    }
-    __syncthreads();
-    // ---- new softmax for the next epoch's Q
-    double mx = -INFINITY;
-    for (int i = tid; i < S; i += kSmallThreads) mx = fmax(mx, theta[i]);
-    mx = block_reduce_max<kSmallThreads>(mx, red);
-    double se = 0.0;
-    for (int i = tid; i < S; i += kSmallThreads) se += exp(theta[i] - mx);
-    se = block_reduce_sum<kSmallThreads>(se, red);
-    for (int i = tid; i < S; i += kSmallThreads) {
-      pi[i] = exp(theta[i] - mx) / se;
-      rr[i] = sqrt(pi[i]);
-    }
-    __syncthreads();
-  }
-  // ---- Q(theta): off-diagonal M, then the diagonal from the row sums (fixed order)
-  for (int e = tid; e < SS; e += kSmallThreads) {
-    const int i = e / S, j = e - i * S;
-    double val = 0.0;
-    if (i != j) {
-      const int lo = i < j ? i : j, hi = i < j ? j : i;
-      const double u = theta[S + cherry::triu_index(lo, hi, S)];
-      val = a.mask[e] * cherry::softplus_d(u) * rr[j] / rr[i];
-    }
-    G[e] = val;  // reuse as M
-  }
-  __syncthreads();
-  for (int e = tid; e < SS; e += kSmallThreads) {
-    const int i = e / S, j = e - i * S;
-    if (i == j) {
-      double rs = 0.0;
-      for (int k = 0; k < S; ++k) rs += G[i * S + k];
-      Q[e] = -rs;
-    } else {
-      Q[e] = G[e];
-    }
-  }
-  if (a.mode == 1 && tid == 0) a.epoch_counter[p] = epoch + 1;
+  update_small_body<kSmallThreads>(a, blockIdx.x, sm, red, &sh_improved);
 }
 
 }  // namespace
@@ -476,41 +504,7 @@ int fit_small_workspace(int S, int* n_smem_slots, int* spill_slots, size_t* slot
   return 0;
 }
 
-int fit_small_expm(const cherry_fit_args& a, cudaStream_t stream, double* P_out) {
-  int ns = 0, sp = 0;
-  size_t sb = 0, smem = 0;
-  const int grid = a.n_problems * a.K;
-  int rc = fit_small_workspace(a.S, &ns, &sp, &sb, &smem, grid);
-  if (rc) return rc;
-  const size_t need = (size_t)sp * sb * a.n_problems * a.K;
-  if (need > 0 && (!a.workspace || a.workspace_bytes < need))
-    return fail(CHERRY_EINVAL, "fit: workspace of %zu bytes required, got %zu", need, a.workspace_bytes);
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  CHERRY_CUDA(cudaGetDevice(&dev));
-  if (dev < 64 && !attr_set[dev]) {
-    CHERRY_CUDA(cudaFuncSetAttribute(expm_loss_grad_small<kSmallThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     226 * 1024));  // 227 KB minus this kernel's static shared memory
-    CHERRY_CUDA(cudaFuncSetAttribute(expm_loss_grad_small<kThroughputThreads, 2>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    attr_set[dev] = true;
-  }
-  // the spill area of a CTA starts after the slots that are resident in ITS shape
-  const int total_needed = kMaxDegree + kMaxSquarings + 4;
-  if (throughput_shape(a.S, grid))
-    expm_loss_grad_small<kThroughputThreads, 2><<<grid, kThroughputThreads, smem, stream>>>(
-        a.Q, a.t, a.C, a.S, a.K, ns, reinterpret_cast<double*>(a.workspace), sp, a.dQ_part, a.loss_part,
-        a.status_flag, P_out);
-  else
-    expm_loss_grad_small<kSmallThreads, 1><<<grid, kSmallThreads, smem, stream>>>(
-        a.Q, a.t, a.C, a.S, a.K, ns, reinterpret_cast<double*>(a.workspace), sp, a.dQ_part, a.loss_part,
-        a.status_flag, P_out);
-  (void)total_needed;
-  CHERRY_LAUNCH_CHECK("expm_loss_grad_small");
-  return 0;
-}
-
-int fit_small_update(const cherry_fit_args& f, int mode, cudaStream_t stream, const double* reduced) {
+static UpdateArgs make_update_args(const cherry_fit_args& f, int mode, const double* reduced) {
   UpdateArgs a;
   a.S = f.S; a.K = f.K; a.n_problems = f.n_problems; a.num_epochs_total = f.loss_trace_epochs;
   a.mask = f.mask; a.theta = f.theta; a.adam_m = f.adam_m; a.adam_v = f.adam_v; a.Q = f.Q;
@@ -524,6 +518,73 @@ int fit_small_update(const cherry_fit_args& f, int mode, cudaStream_t stream, co
     a.K = 1;
     a.dQ_part = reduced;
     a.loss_part = reduced + (size_t)f.n_problems * f.S * f.S;
+  }
+  return a;
+}
+
+// bytes of the spill area; the per-problem arrival counters of the fused update follow it (256-byte aligned)
+static size_t small_spill_bytes(int sp, size_t sb, int n_problems, int K) {
+  return ((size_t)sp * sb * n_problems * K + 255) / 256 * 256;
+}
+
+size_t fit_small_workspace_bytes(int S, int K, int n_problems) {
+  int ns = 0, sp = 0;
+  size_t sb = 0, smem = 0;
+  if (fit_small_workspace(S, &ns, &sp, &sb, &smem, -1)) return 0;
+  return small_spill_bytes(sp, sb, n_problems, K) + sizeof(int) * (size_t)n_problems + 256;
+}
+
+// fuse_update: training epoch -- the last CTA of every problem runs the parameter update (no second launch)
+int fit_small_expm(const cherry_fit_args& a, cudaStream_t stream, double* P_out, bool fuse_update) {
+  int ns = 0, sp = 0;
+  size_t sb = 0, smem = 0;
+  const int grid = a.n_problems * a.K;
+  int rc = fit_small_workspace(a.S, &ns, &sp, &sb, &smem, grid);
+  if (rc) return rc;
+  const size_t need = fit_small_workspace_bytes(a.S, a.K, a.n_problems);
+  if (!a.workspace || a.workspace_bytes < need)
+    return fail(CHERRY_EINVAL, "fit: workspace of %zu bytes required, got %zu", need, a.workspace_bytes);
+  static const bool no_fuse = getenv("CHERRY_FIT_SMALL_UNFUSED") != nullptr;  // A/B switch: two launches per epoch
+  if (no_fuse) fuse_update = false;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  CHERRY_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    CHERRY_CUDA(cudaFuncSetAttribute(expm_loss_grad_small<kSmallThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     226 * 1024));  // 227 KB minus this kernel's static shared memory
+    CHERRY_CUDA(cudaFuncSetAttribute(expm_loss_grad_small<kThroughputThreads, 2>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    attr_set[dev] = true;
+  }
+  const UpdateArgs ua = make_update_args(a, 1, nullptr);
+  int* arrive = fuse_update ? reinterpret_cast<int*>(reinterpret_cast<char*>(a.workspace) +
+                                                     small_spill_bytes(sp, sb, a.n_problems, a.K))
+                            : nullptr;
+  // the update body needs 4 S*S + 4 S doubles of the dynamic shared memory
+  const size_t upd_smem = (size_t)(4 * a.S * a.S + 4 * a.S) * sizeof(double);
+  if (smem < upd_smem) smem = upd_smem;
+  if (throughput_shape(a.S, grid))
+    expm_loss_grad_small<kThroughputThreads, 2><<<grid, kThroughputThreads, smem, stream>>>(
+        a.Q, a.t, a.C, a.S, a.K, ns, reinterpret_cast<double*>(a.workspace), sp, a.dQ_part, a.loss_part,
+        a.status_flag, P_out, ua, arrive);
+  else
+    expm_loss_grad_small<kSmallThreads, 1><<<grid, kSmallThreads, smem, stream>>>(
+        a.Q, a.t, a.C, a.S, a.K, ns, reinterpret_cast<double*>(a.workspace), sp, a.dQ_part, a.loss_part,
+        a.status_flag, P_out, ua, arrive);
+  CHERRY_LAUNCH_CHECK("expm_loss_grad_small");
+  return 0;
+}
+
+int fit_small_update(const cherry_fit_args& f, int mode, cudaStream_t stream, const double* reduced) {
+  const UpdateArgs a = make_update_args(f, mode, reduced);
+  if (mode == 0 && f.workspace) {  // initialisation: the fused update's arrival counters start at zero
+    int ns = 0, sp = 0;
+    size_t sb = 0, smem_unused = 0;
+    int rc = fit_small_workspace(f.S, &ns, &sp, &sb, &smem_unused, -1);
+    if (rc) return rc;
+    if (f.workspace_bytes >= fit_small_workspace_bytes(f.S, f.K, f.n_problems))
+      CHERRY_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(f.workspace) + small_spill_bytes(sp, sb, f.n_problems, f.K), 0,
+                                  sizeof(int) * (size_t)f.n_problems, stream));
   }
   const size_t smem = (size_t)(4 * f.S * f.S + 4 * f.S) * sizeof(double);
   fit_update_small<<<f.n_problems, kSmallThreads, smem, stream>>>(a);
