@@ -342,9 +342,9 @@ def run_ours(args):
         counts = step()
     barrier()
     _log("warm-up steps done")
-    # parity gate inside the bench: a 32-family slice of this rank's batch against the oracle
+    # parity gate inside the bench: a 32-family slice of EVERY rank's batch against the oracle
     parity = None
-    if rank == 0:
+    if True:
         import copy
 
         from oracle.native import count_batch_oracle
@@ -355,6 +355,10 @@ def run_ours(args):
         host_slice = as_count_batch(dict(syn, msa=syn["msa"][: 32 * N_SEQS * stride]))
         exp = count_batch_oracle(host_slice, grid, S, False, pair_slice=slice(0, 32 * (N_SEQS // 2)))
         parity = bool(np.array_equal(got, exp))
+        if world > 1:
+            flag = torch.tensor([1 if parity else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            parity = bool(int(flag[0]))
         if not parity:
             raise SystemExit("bench.py: GPU counts differ from the oracle on the sample slice")
 
@@ -545,7 +549,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload_name(F), "l2": "inputs (>5 GB per GPU) larger than L2, no flush needed",
                    "transitions_examined_per_step": examined * world,
-                   "transitions_counted_per_step_rank0": counted, "parity_slice_vs_oracle": parity},
+                   "transitions_counted_per_step_rank0": counted, "parity_slice_vs_oracle_all_ranks": parity},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     line["config"]["transitions_counted_per_s"] = counted * world / (ms_per_step * 1e-3)

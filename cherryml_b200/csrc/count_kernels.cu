@@ -118,8 +118,18 @@ __global__ void bucket_table_kernel(const double* __restrict__ pair_t,
 // result is the reference's by construction; quantising a value is then a float guess and two or three
 // double compares instead of ~110 instructions.  Grids with repeated or non-positive points keep the
 // general path (flag).
+__device__ __forceinline__ bool quantization_predicate(double t, double left, double right) {
+  return __dsub_rn(__ddiv_rn(t, left), 1.0) < __dsub_rn(__ddiv_rn(right, t), 1.0);
+}
 __device__ __forceinline__ double quantization_boundary(double left, double right) {
   long long lo = __double_as_longlong(left), hi = __double_as_longlong(right);  // predicate true at lo, false at hi
+  // the switch point is within a few ulps of the geometric mean: bracket it there first (8 steps instead of ~50)
+  const long long mid0 = __double_as_longlong(sqrt(left * right));
+  if (mid0 - 128 > lo && mid0 + 128 < hi && quantization_predicate(__longlong_as_double(mid0 - 128), left, right) &&
+      !quantization_predicate(__longlong_as_double(mid0 + 128), left, right)) {
+    lo = mid0 - 128;
+    hi = mid0 + 128;
+  }
   while (hi - lo > 1) {
     const long long mid = lo + ((hi - lo) >> 1);
     const double t = __longlong_as_double(mid);
@@ -128,28 +138,31 @@ __device__ __forceinline__ double quantization_boundary(double left, double righ
   }
   return __longlong_as_double(hi);
 }
-__device__ __forceinline__ int quantize_by_boundaries(double t, const double* __restrict__ q, const double* __restrict__ bnd,
-                                                      int K, float log2_q0, float inv_log2_step) {
+// log2_t: float approximation of log2(t) (any value is correct, a good one saves steps of the two loops)
+__device__ __forceinline__ int quantize_by_boundaries(double t, float log2_t, const double* __restrict__ q,
+                                                      const double* __restrict__ bnd, int K, float log2_q0,
+                                                      float inv_log2_step) {
   if (t < q[0] || t > q[K - 1]) return -1;
-  int b = t == t ? (int)((__log2f((float)t) - log2_q0) * inv_log2_step) : 0;
-  b = max(0, min(K - 1, b));
+  const float g = (log2_t - log2_q0) * inv_log2_step;
+  int b = g == g ? (int)fminf(fmaxf(g, 0.f), (float)(K - 1)) : 0;
   while (b > 0 && !(bnd[b - 1] <= t)) --b;
   while (b < K - 1 && bnd[b] <= t) ++b;
   return b;
 }
 
-// The same table, one CTA per tile: a tile's pairs belong to ONE family, so the family's rate values are
-// read once per CTA and a thread's only dependent load is its pair's branch length (coalesced); values are
+// The same table, one WARP per tile: a tile's pairs belong to ONE family, so the family's rate values are
+// read once per warp and a thread's only dependent load is its pair's branch length (coalesced); values are
 // quantised against the precomputed decision boundaries.
 __global__ void __launch_bounds__(256)
 bucket_table_tiles_kernel(const double* __restrict__ pair_t, const cherry_tile* __restrict__ tiles,
                           const cherry_fam_desc* __restrict__ fams, const double* __restrict__ rate_vals,
                           const double* __restrict__ grid, int K, int n_tiles, int r_pad,
                           uint8_t* __restrict__ tab) {
-  extern __shared__ double sgrid[];  // [K] grid, [K] boundaries, [r_pad] rate values
+  extern __shared__ double sgrid[];  // [K] grid, [K] boundaries, [warps][r_pad] rate values, [warps][r_pad] floats log2(rate)
   __shared__ int general;
   double* sbnd = sgrid + K;
   double* srate = sbnd + K;
+  float* slog = reinterpret_cast<float*>(srate + (size_t)(blockDim.x >> 5) * r_pad);  // [warps][r_pad] each
   if (threadIdx.x == 0) general = 0;
   for (int i = threadIdx.x; i < K; i += blockDim.x) sgrid[i] = grid[i];
   __syncthreads();
@@ -167,34 +180,46 @@ bucket_table_tiles_kernel(const double* __restrict__ pair_t, const cherry_tile* 
   const float log2_q0 = sgrid[0] > 0.0 ? log2f((float)sgrid[0]) : 0.0f;
   const float span = K > 1 && sgrid[0] > 0.0 ? log2f((float)(sgrid[K - 1] / sgrid[0])) : 0.0f;
   const float inv_log2_step = span > 0.0f ? (float)(K - 1) / span : 0.0f;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  // One WARP per tile from here on (no CTA barrier, so the descriptor -> family -> rates loads of the 64
+  // warps of an SM overlap).  r_pad == 4: the four rate values live in registers; otherwise a warp-private
+  // slice of shared memory holds them.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  double* wrate = srate + (size_t)warp * r_pad;
+  float* wlog = slog + (size_t)warp * r_pad;
+  for (int tile = blockIdx.x * warps + warp; tile < n_tiles; tile += gridDim.x * warps) {
     const cherry_tile tl = tiles[tile];
     const cherry_fam_desc* fd = fams + tl.fam;
     const int n_rates = min(fd->n_rates, r_pad);
-    __syncthreads();
-    for (int i = threadIdx.x; i < r_pad; i += blockDim.x) srate[i] = i < n_rates ? rate_vals[fd->rate_off + i] : 0.0;
-    __syncthreads();
-    for (int p0 = threadIdx.x; p0 < tl.n_pairs; p0 += 4 * blockDim.x) {
+    const int rate_off = fd->rate_off;
+    __syncwarp();
+    for (int i = lane; i < r_pad; i += 32) {
+      const double rv = i < n_rates ? __ldg(rate_vals + rate_off + i) : 0.0;
+      wrate[i] = rv;
+      wlog[i] = rv > 0.0 ? __log2f((float)rv) : 0.0f;
+    }
+    __syncwarp();
+    for (int p0 = lane; p0 < tl.n_pairs; p0 += 4 * 32) {
       double t[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int pl = p0 + u * blockDim.x;
+        const int pl = p0 + u * 32;
         t[u] = pl < tl.n_pairs ? __ldg(pair_t + tl.pair_begin + pl) : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int pl = p0 + u * blockDim.x;
+        const int pl = p0 + u * 32;
         if (pl >= tl.n_pairs) break;
         uint32_t* __restrict__ row = reinterpret_cast<uint32_t*>(tab + (int64_t)(tl.pair_begin + pl) * r_pad);
+        const float lt = t[u] > 0.0 ? __log2f((float)t[u]) : 0.0f;  // one logarithm per pair: log2(t r) = log2 t + log2 r
         for (int r0 = 0; r0 < r_pad; r0 += 4) {
           uint32_t word = 0;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             uint32_t out = CHERRY_NO_BUCKET;
             if (r0 + k < n_rates) {
-              const double x = __dmul_rn(t[u], srate[r0 + k]);
+              const double x = __dmul_rn(t[u], wrate[r0 + k]);
               const int b = use_general ? quantize_bucket_guess(x, sgrid, K, log2_q0, inv_log2_step)
-                                        : quantize_by_boundaries(x, sgrid, sbnd, K, log2_q0, inv_log2_step);
+                                        : quantize_by_boundaries(x, lt + wlog[r0 + k], sgrid, sbnd, K, log2_q0, inv_log2_step);
               if (b >= 0) out = (uint32_t)b;
             }
             word |= out << (8 * k);
@@ -541,10 +566,10 @@ int cherry_build_bucket_table_tiles(const double* pair_t, const cherry_tile* til
   if (n_tiles < 0 || r_pad <= 0 || r_pad % 4 != 0)
     return cherry::fail(CHERRY_EINVAL, "bucket_table_tiles: bad sizes (r_pad must be a positive multiple of 4)");
   if (n_tiles == 0) return 0;
-  int blocks = n_tiles;
+  int blocks = (n_tiles + 7) / 8;           // 8 warps per CTA, one warp per tile
   const int cap = cherry::sm_count() * 8;  // one residency: every CTA computes the boundaries once
   if (blocks > cap) blocks = cap;
-  bucket_table_tiles_kernel<<<blocks, 256, (2 * K + r_pad) * sizeof(double), (cudaStream_t)stream>>>(
+  bucket_table_tiles_kernel<<<blocks, 256, (2 * K + 8 * r_pad) * sizeof(double) + 8 * r_pad * sizeof(float), (cudaStream_t)stream>>>(
       pair_t, tiles, fams, rate_vals, grid, K, n_tiles, r_pad, tab);
   CHERRY_LAUNCH_CHECK("bucket_table_tiles_kernel");
   return 0;

@@ -112,8 +112,8 @@ int cherry_count_lg(const uint8_t* msa, const cherry_fam_desc* fams, const int32
                     const uint16_t* group_cat, const cherry_tile* tiles, int n_tiles, int K,
                     int S, unsigned long long* counts, void* stream);
 
-/* The same table as cherry_build_bucket_table for the pairs covered by `tiles`, built one CTA per TILE
- * (a tile's pairs share a family: its rate values are read once per CTA, a pair costs one coalesced load)
+/* The same table as cherry_build_bucket_table for the pairs covered by `tiles`, built one warp per TILE
+ * (a tile's pairs share a family: its rate values are read once per warp, a pair costs one coalesced load)
  * and quantised against precomputed decision boundaries: for neighbouring grid points (left, right) the
  * reference's predicate t/left - 1 < right/t - 1 is monotone in t, so its switch point is found once per
  * launch by bisection on the doubles with the predicate itself.  Bit-identical to the per-pair kernel. */
@@ -122,8 +122,8 @@ int cherry_build_bucket_table_tiles(const double* pair_t, const cherry_tile* til
                                     int K, int r_pad, uint8_t* tab, void* stream);
 
 /* cherry_build_bucket_table_tiles + cherry_count_lg in one call for batches that come with tiles: the
- * bucket table is built one CTA per TILE (a tile's pairs share a family, so the family's rate values
- * are read once per CTA and a pair costs one coalesced load instead of the pair -> family -> rates
+ * bucket table is built one warp per TILE (a tile's pairs share a family, so the family's rate values
+ * are read once per warp and a pair costs one coalesced load instead of the pair -> family -> rates
  * chain of cherry_build_bucket_table: 0.17 ms -> see DESIGN.md for 8.4 M pairs), then counted.  Same
  * results, bit for bit.  Every pair must belong to exactly one tile (pair_fam is implied by the tiles).
  * tab_scratch: n_pairs * r_pad bytes of device scratch (the bucket table; valid after the call).
