@@ -144,7 +144,7 @@ __device__ __forceinline__ int quantize_by_boundaries(double t, float log2_t, co
                                                       float inv_log2_step) {
   if (t < q[0] || t > q[K - 1]) return -1;
   const float g = (log2_t - log2_q0) * inv_log2_step;
-  int b = g == g ? (int)fminf(fmaxf(g, 0.f), (float)(K - 1)) : 0;
+  int b = g == g ? (int)fminf(fmaxf(g + 0.5f, 0.f), (float)(K - 1)) : 0;  // nearest grid index: the loops rarely move
   while (b > 0 && !(bnd[b - 1] <= t)) --b;
   while (b < K - 1 && bnd[b] <= t) ++b;
   return b;
