@@ -181,22 +181,28 @@ struct CoConst {
   uint32_t vmask, coefI, coefJ, plane4, hist, histJ, junk;
 };
 
+// Returns the slow-path flags of the word's two contacts at bits 7 and 23.  The per-byte flags are formed
+// for the whole word at once (round 2: the fast path is bound by issue slots, 17.5 instructions per contact;
+// this form and the 16 x 8-bit dot product below save three of them):
+//   nz   bit 7 of a byte set iff the two rows differ in that byte,
+//   both bit 7 / 23 set iff BOTH sites of contact 0 / 1 changed (the item leaves the shared histogram),
+//   slow = both and no skip byte among the contact's four bytes.
 __device__ __forceinline__ uint32_t co_word(uint32_t wa, uint32_t wb, const CoConst& k, uint32_t* w4) {
   const uint32_t d = wa ^ wb;
   const uint32_t v = ((wa + k.vmask) | (wb + k.vmask)) & 0x80808080u;
-  uint32_t slow = 0;
+  const uint32_t nz = (((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d) & 0x80808080u;
+  const uint32_t both = nz & (nz >> 8);
+  const uint32_t slow = both & ~(v | (v >> 8)) & 0x00800080u;
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
-    const uint32_t m_i = 0xffu << (16 * c), m_j = 0xff00u << (16 * c), m_c = 0xffffu << (16 * c);
-    const bool eqj = (d & m_j) == 0;
-    const bool near = eqj || (d & m_i) == 0;
+    const bool eqj = (nz & (0x8000u << (16 * c))) == 0;
+    const bool far = (both & (0x80u << (16 * c))) != 0;
     const uint32_t g = __byte_perm(wa, wb, c == 0 ? 0x5140u : 0x7362u);  // bytes: xi, yi, xj, yj
     w4[c] = g;
     const uint32_t lo = __dp4a(g, eqj ? k.coefI : k.coefJ, eqj ? k.hist : k.histJ);
-    uint32_t addr = (g & 0xffu) * k.plane4 + lo;
-    if (!near) addr = k.junk;
+    uint32_t addr = __dp2a_lo(k.plane4, g, lo);  // + plane4 * xi: plane4 in the low 16 bits, byte 0 of g
+    if (far) addr = k.junk;
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
-    if (!near && (v & m_c) == 0) slow |= 1u << c;
   }
   return slow;
 }
@@ -207,6 +213,17 @@ __device__ __forceinline__ void co_slow(uint32_t g, uint32_t S, uint32_t coef_e,
   const uint32_t xi = g & 0xffu, xj = __byte_perm(g, 0, 0x4442u);
   const uint32_t e = __dp4a(g, coef_e, 0u);  // yi*S + yj
   atomicAdd(counts_b + (uint32_t)((xi * S + xj) * (S * S) + e), 1u);  // < S^4 <= 2^24: 32-bit offset
+}
+// The same with the bucket folded into a 32-bit ELEMENT index from the start of the count tensor
+// (K * S^4 <= 254 * 62^4 < 2^32): one widening multiply-add forms the address, where pointer + offset took an
+// add with carry and a shift with carry (the loop over the slow items is the other half of the fast path's
+// instruction count).  coef_x = S^3 | S^2 << 16 for the 16 x 8-bit dot product over (xi, xj) in w = g's
+// bytes 0 and 2 moved to bytes 0 and 1.
+__device__ __forceinline__ void co_slow_idx(uint32_t g, uint32_t coef_x, uint32_t coef_e, uint32_t bucket_off,
+                                            uint32_t* __restrict__ counts) {
+  const uint32_t e = __dp4a(g, coef_e, bucket_off);                      // bucket*S^4 + yi*S + yj
+  const uint32_t idx = __dp2a_lo(coef_x, __byte_perm(g, 0, 0x4420u), e);  // + xi*S^3 + xj*S^2
+  atomicAdd(counts + idx, 1u);
 }
 
 template <bool SMEM>
@@ -394,6 +411,9 @@ count_co_sorted_kernel(const uint8_t* __restrict__ msa, const cherry_co_rec* __r
   kc.coefJ = ((4u * S1) << 16) | (4u << 24);  // J = [xi][xj][yj]
   kc.vmask = (0x80u - (uint32_t)S) * 0x01010101u;
   const uint32_t coef_e = ((uint32_t)S << 8) | (1u << 24);  // yi*S + yj
+  // S^3 and S^2 as the two 16-bit coefficients of the (xi, xj) dot product: S <= 40; larger S keeps co_slow
+  const bool wide_ok = S <= 40;
+  const uint32_t coef_x = (uint32_t)(S * S * S) | ((uint32_t)(S * S) << 16);
   const int warp = tid >> 5;
   int cur_bucket = -1;
   int c = warp;  // this warp's next chunk, relative to the first chunk of stage k
@@ -414,6 +434,7 @@ count_co_sorted_kernel(const uint8_t* __restrict__ msa, const cherry_co_rec* __r
     const uint8_t* regA = stage_base + (size_t)s * 2 * region_bytes;
     const uint8_t* regB = regA + region_bytes;
     uint32_t* __restrict__ counts_b = counts + (size_t)cur_bucket * cells;
+    const uint32_t bucket_off = (uint32_t)cur_bucket * (uint32_t)cells;  // element index (used when wide_ok)
     const bool mixed = m.bucket_first != m.bucket_last;
     for (; c < n_chunks; c += kCoConsumerWarps) {
       const int i = c * 32 + lane;
@@ -422,26 +443,27 @@ count_co_sorted_kernel(const uint8_t* __restrict__ msa, const cherry_co_rec* __r
       const uint2 b = *reinterpret_cast<const uint2*>(regB + 8 * i);
       uint32_t w4[4];
       if (SMEM && !mixed) {
+        // flags of the four contacts at bits 7, 23 (word x) and 8, 24 (word y)
         uint32_t slow = co_word(a.x, b.x, kc, w4);
-        slow |= co_word(a.y, b.y, kc, w4 + 2) << 2;
+        slow += co_word(a.y, b.y, kc, w4 + 2) << 1;
         // lanes with both-sites-changed items loop over them (typically 0-2 of the 4): the
         // warp runs max-over-lanes iterations instead of four guarded blocks
         while (slow) {
-          const uint32_t lo2 = (slow & 1u) ? w4[0] : w4[1], hi2 = (slow & 4u) ? w4[2] : w4[3];
-          const uint32_t g = (slow & 3u) ? lo2 : hi2;
-          slow &= slow - 1;
-          co_slow(g, S, coef_e, counts_b);
+          const uint32_t g = (slow & 0x80u) ? w4[0] : (slow & 0x100u) ? w4[2] : (slow & 0x800000u) ? w4[1] : w4[3];
+          slow &= slow - 1;  // lowest flag first: bit 7, 8, 23, 24 -- the order of the selection above
+          if (wide_ok) co_slow_idx(g, coef_x, coef_e, bucket_off, counts);
+          else co_slow(g, S, coef_e, counts_b);
         }
       } else {
         int g = 0;  // the pair this item belongs to: first g with pair_end[g] > 8*i
         while (pair_end[s][g] <= 8 * i) ++g;
         const int bucket = pair_bucket[s][g];
         if (SMEM && bucket == cur_bucket) {
-          uint32_t slow = co_word(a.x, b.x, kc, w4);
-          slow |= co_word(a.y, b.y, kc, w4 + 2) << 2;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (slow & (1u << q)) co_slow(w4[q], S, coef_e, counts_b);
+          const uint32_t sx = co_word(a.x, b.x, kc, w4), sy = co_word(a.y, b.y, kc, w4 + 2);
+          if (sx & 0x80u) co_slow(w4[0], S, coef_e, counts_b);
+          if (sx & 0x800000u) co_slow(w4[1], S, coef_e, counts_b);
+          if (sy & 0x80u) co_slow(w4[2], S, coef_e, counts_b);
+          if (sy & 0x800000u) co_slow(w4[3], S, coef_e, counts_b);
         } else {
           uint32_t* __restrict__ cb = counts + (size_t)bucket * cells;
           co_direct(a.x, b.x, S, cb);

@@ -442,7 +442,7 @@ struct DfList {  // host-side description of one chain launch
   std::vector<DfGroup> groups;
   std::vector<int> pending;  // groups whose reduction items have not been emitted yet
   int n_mats = 0;
-  size_t off_items = 0, off_groups = 0, off_state = 0;  // workspace offsets
+  size_t off_items = 0, off_state = 0;  // workspace offsets (every item carries a copy of its group)
   int partial_tiles = 0;
 };
 constexpr int kDfSlabs = 5;      // row slabs of a tile's reduction (16 rows each), one work item per slab
@@ -1325,10 +1325,8 @@ void make_plan(Plan& p, int S, int K, char* base) {
     const size_t max_groups = 3 * (size_t)kDeg * p.tiles + 64;
     const size_t max_items = 3 * (size_t)kDeg * p.tiles * (p.Sp / BT) + max_groups * kDfSlabs + 64;
     p.df_fwd.off_items = carve(sizeof(DfItem) * max_items);
-    p.df_fwd.off_groups = carve(sizeof(DfGroup) * max_groups);
     p.df_fwd.off_state = carve(sizeof(int) * df_state_ints(kDeg, p.tiles, (int)max_groups));
     p.df_bwd.off_items = carve(sizeof(DfItem) * max_items);
-    p.df_bwd.off_groups = carve(sizeof(DfGroup) * max_groups);
     p.df_bwd.off_state = carve(sizeof(int) * df_state_ints(kDeg, p.tiles, (int)max_groups));
   }
   p.off_prof = carve(sizeof(long long) * 8 * 2 * 1024);  // phase profile of the two chain launches (<= 1024 CTAs)
@@ -1648,7 +1646,6 @@ int fit_large_prepare(const cherry_fit_args& a, cudaStream_t stream) {
   CHERRY_CUDA(cudaMemcpy(base + p.off_terms, p.terms.data(), p.terms.size() * sizeof(GemmTerm), cudaMemcpyHostToDevice));
   for (const DfList* L : {&p.df_fwd, &p.df_bwd}) {
     CHERRY_CUDA(cudaMemcpy(base + L->off_items, L->items.data(), L->items.size() * sizeof(DfItem), cudaMemcpyHostToDevice));
-    CHERRY_CUDA(cudaMemcpy(base + L->off_groups, L->groups.data(), L->groups.size() * sizeof(DfGroup), cudaMemcpyHostToDevice));
   }
   CHERRY_CUDA(cudaMemset(base + p.off_scalars, 0, sizeof(LargeScalars)));
   CHERRY_CUDA(cudaMemset(base + p.off_arrive, 0, sizeof(int) * 64 * (size_t)p.tiles));
