@@ -512,6 +512,14 @@ def run_ours(args):
             srb = bench_siterm(device, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
         except Exception as e:
             srb = {"error": str(e)[:300]}
+    srs = None
+    if not args.no_siterm:  # every rank: the per-site fit with a fixed total of sites sharded over the ranks
+        from benchlib.siterm import bench_siterm_sharded
+
+        try:
+            srs = bench_siterm_sharded(device, dist.group.WORLD if world > 1 else None)
+        except Exception as e:
+            srs = {"error": str(e)[:300]}
     _log("siterm section done")
     apib = None
     if rank == 0 and world == 1 and not args.no_public_api:
@@ -582,6 +590,9 @@ def run_ours(args):
         line["tree_likelihood"] = llb
     if srb is not None:
         line["siterm"] = srb
+    if srs is not None:
+        line["siterm_sharded"] = srs
+        line["config"]["siterm_sharded_sites_per_s"] = srs.get("sites_per_s")
     if apib is not None:
         line["public_api_demo"] = apib
     if not args.no_cpu_baseline:  # rank 0 (the other ranks have returned above)

@@ -92,3 +92,39 @@ def bench_siterm(device, families: int = 8, cpu_baseline: bool = True, seed: int
         }
         out["matches_oracle_1e-6"] = bool(np.max(np.abs(cpu["res"] - gpu["res"])) < 1e-6 * np.max(np.abs(cpu["res"])))
     return out
+
+
+def bench_siterm_sharded(device, process_group, sites: int = 16 * N_SITES, buckets: int = 4, seed: int = 5) -> Dict:
+    """SURVEY 8e, third stage row: the batched per-site fit with the sites sharded over the ranks of
+    ``process_group`` (contiguous blocks, no exchange during training, one gather of the results).  A fixed
+    total of ``sites`` synthetic per-site problems (LG-like counts in ``buckets`` time buckets, strong scaling):
+    every rank times the same call; returns the maximum over the ranks and, on every rank, the full result's
+    checksum so that the gather is exercised."""
+    import torch
+    import torch.distributed as dist
+
+    from cherryml_b200.siterm._vectorized import quantized_transitions_mle_vectorized_over_sites
+
+    rng = np.random.default_rng(seed)
+    lg = read_rate_matrix(get_lg_path()).to_numpy()
+    counts = rng.poisson(3.0, size=(sites, buckets, 20, 20)).astype(np.float64)
+    counts = counts + counts.transpose(0, 1, 3, 2) + 20.0 * np.eye(20)[None, None]
+    times = np.tile(0.05 * 2.5 ** np.arange(buckets), (sites, 1))
+    init = np.tile(lg[None], (sites, 1, 1))
+    kw = dict(counts=counts, times=times, num_epochs=NUM_EPOCHS, initialization=init, device=str(device))
+    quantized_transitions_mle_vectorized_over_sites(**dict(kw, num_epochs=4), process_group=process_group)  # warm-up
+    if process_group is not None:
+        dist.barrier(group=process_group)
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    res = quantized_transitions_mle_vectorized_over_sites(**kw, process_group=process_group)
+    torch.cuda.synchronize(device)
+    secs = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    world = 1
+    if process_group is not None:
+        dist.all_reduce(secs, op=dist.ReduceOp.MAX, group=process_group)
+        world = dist.get_world_size(process_group)
+    return {"sites_total": sites, "buckets": buckets, "num_epochs": NUM_EPOCHS, "n_gpus": world,
+            "seconds": float(secs[0]), "sites_per_s": sites / float(secs[0]),
+            "result_checksum": float(np.abs(res["res"]).sum()),
+            "sharding": f"contiguous blocks of sites over {world} ranks, no exchange during training, one gather"}
