@@ -41,6 +41,10 @@ constexpr int LD_ROW = 20;        // tile stored [80][16]: k contiguous
 constexpr int LD_COL = 84;        // tile stored [16][80]: m (or n) contiguous
 constexpr int TILE_ELEMS = BT * LD_ROW;  // 1600 >= 16 * 84
 constexpr int EW_THREADS = 256;
+constexpr int kTaylorStagesS = 16;     // count loads in flight per thread of its shared-memory variant (two CTAs per SM)
+constexpr int kTaylorThreads = 256;    // threads per CTA of the shared-memory variant of the fused Taylor pass (288 would make
+                                       // 160 000 elements two passes of 296 CTAs instead of 2.11, but needs <= 113 registers: 96 with
+                                       // 300 bytes of spills measured 213 us against 180)
 constexpr int kTaylorInterleave = 2;  // buckets whose dependent chains a thread of the fused Taylor pass interleaves
 constexpr int kTaylorStages = 16;  // count loads in flight per thread of the fused Taylor pass
 static_assert(kDeg % 4 == 0, "the elementwise kernels skip Taylor terms in blocks of four");
@@ -847,6 +851,35 @@ __device__ __forceinline__ void taylor_term_n(const double* const (&w)[U], const
   }
 }
 
+// The same with the element's power values read from shared memory (spw[j * EW_THREADS], this thread's column):
+// frees 48 registers, so that two CTAs share an SM (the pass is latency bound at one).
+template <int D, int U, int NT>
+__device__ __forceinline__ void taylor_term_n_s(const double* const (&w)[U], const double* __restrict__ spw,
+                                                double (&acc)[kDeg], const double (&c)[U], double diag, double& part) {
+  double v[U], g[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) v[u] = w[u][0] * diag;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    const double pj = spw[j * NT];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = fma(w[u][j + 1], pj, v[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const double l = log(v[u]), q = -c[u] / v[u];
+    g[u] = c[u] != 0.0 ? q : 0.0;
+    part -= c[u] != 0.0 ? c[u] * l : 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    double x = acc[j];
+#pragma unroll
+    for (int u = 0; u < U; ++u) x = fma(w[u][j + 1], g[u], x);
+    acc[j] = x;
+  }
+}
+
 // Fused Taylor pass (training): LPE lanes per matrix element, the m power values split over their registers
 // (one thread per element holds 48 doubles of state = 186 registers = one 256-thread block per SM: the pass
 // was latency bound at 12 % of the warp slots, profiles/r02_taylor_fused_v1.txt).
@@ -981,6 +1014,120 @@ taylor_fused_kernel(const double* __restrict__ powers, size_t n_p, int S, int Sp
   if (threadIdx.x == 0) {
     double tot = 0.0;
     for (int wdx = 0; wdx < EW_THREADS / 32; ++wdx) tot += red[wdx];
+    loss_partial_fused[blockIdx.x] = tot;
+  }
+}
+
+template <int UI, int NT>
+__global__ void __launch_bounds__(NT, 2)
+taylor_fused_smem_kernel(const double* __restrict__ powers, size_t n_p, int S, int Sp, int K,
+                    const double* __restrict__ w, const int* __restrict__ s_arr,
+                    const int* __restrict__ deg_arr, const double* __restrict__ C, double* __restrict__ X0,
+                    double* __restrict__ Pbar, double* __restrict__ loss_partial_fused) {
+  constexpr int LPE = 1, NP = kDeg;
+  extern __shared__ double sw[];  // [K][m+1] weights, then int lists
+  __shared__ double red[NT / 32];
+  __shared__ int n_zero, n_sq;
+  int* zlist = reinterpret_cast<int*>(sw + (size_t)K * (kDeg + 1));  // buckets with s == 0
+  int* qlist = zlist + K;                                              // buckets with s > 0
+  int* sdeg = qlist + K;                                               // Taylor degree per bucket
+  for (int i = threadIdx.x; i < K * (kDeg + 1); i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {  // lists built once per epoch by coef_kernel
+    sdeg[i] = deg_arr[i];
+    zlist[i] = deg_arr[K + i];
+    qlist[i] = deg_arr[2 * K + i];
+  }
+  if (threadIdx.x == 0) {
+    n_zero = deg_arr[3 * K];
+    n_sq = deg_arr[3 * K + 1];
+  }
+  __syncthreads();
+  // persistent: the weight table and the lists are staged once per CTA, the CTA walks over chunks of elements
+  const size_t n_chunks = (n_p * LPE + blockDim.x - 1) / blockDim.x;
+  double part = 0.0;
+  for (size_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int h = threadIdx.x & (LPE - 1);
+    const size_t e = (chunk * (size_t)blockDim.x + threadIdx.x) / LPE;
+    const bool in_range = e < n_p;
+    const size_t ee = in_range ? e : 0;
+    const int row = (int)(ee / Sp), col = (int)(ee - (size_t)row * Sp);
+    const bool real = in_range && row < S && col < S;
+    const double diag = (row == col && row < S) ? 1.0 : 0.0;
+    double* ring = reinterpret_cast<double*>(sdeg + K + (K & 1));  // [kTaylorStagesS][NT], 8-byte aligned
+    double* spw_all = ring + kTaylorStagesS * NT;               // [kDeg][NT]
+    double acc[NP];
+    double* spw = spw_all + threadIdx.x;  // this thread's column of the staged power values [kDeg][NT]
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      spw[i * NT] = in_range ? powers[(size_t)i * n_p + ee] : 0.0;  // own column: no barrier needed
+      acc[i] = 0.0;
+    }
+    const size_t cidx = (size_t)row * S + col;
+    const size_t SS = (size_t)S * S;
+    // ---- buckets without squarings.  The pass is bound by the latency of the count loads (one 8-byte load per
+    // bucket and thread, 87 buckets): they go through a ring of kTaylorStagesS cp.async stages in shared memory, so
+    // that every thread keeps kTaylorStagesS loads in flight without holding them in registers.
+    auto issue = [&](int i) {
+      if (real && i < n_zero) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (i % kTaylorStagesS) * NT + threadIdx.x);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(C + (size_t)zlist[i] * SS + cidx));
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < kTaylorStagesS; ++i) issue(i);
+    {
+      constexpr int U = UI;
+      for (int i = 0; i < n_zero; i += U) {
+        cp_async_wait<kTaylorStagesS - U>();
+        double c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          c[u] = (real && i + u < n_zero) ? ring[((i + u) % kTaylorStagesS) * NT + threadIdx.x] : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) issue(i + u + kTaylorStagesS);  // the slots just read are this thread's own
+        bool nz = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u) nz |= c[u] != 0.0;
+        if (!__any_sync(0xffffffffu, nz)) continue;
+        const double* wu[U];
+        int d = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int k = zlist[min(i + u, n_zero - 1)];
+          wu[u] = sw + k * (kDeg + 1);
+          d = max(d, sdeg[k]);
+        }
+        if (d <= 8) taylor_term_n_s<8, U, NT>(wu, spw, acc, c, diag, part);
+        else if (d <= 12) taylor_term_n_s<12, U, NT>(wu, spw, acc, c, diag, part);
+        else if (d <= 16) taylor_term_n_s<16, U, NT>(wu, spw, acc, c, diag, part);
+        else if (d <= 20) taylor_term_n_s<20, U, NT>(wu, spw, acc, c, diag, part);
+        else taylor_term_n_s<24, U, NT>(wu, spw, acc, c, diag, part);
+      }
+    }
+    cp_async_wait<0>();
+    // ---- buckets with squarings: store X0
+    for (int i = 0; i < n_sq; ++i) {
+      const int k = qlist[i];
+      const double* wk = sw + k * (kDeg + 1);
+      double v = h == 0 ? wk[0] * diag : 0.0;
+#pragma unroll
+      for (int j = 0; j < NP; ++j) v = fma(wk[j + 1], spw[j * NT], v);
+#pragma unroll
+      for (int o = 1; o < LPE; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (in_range && h == 0) X0[(size_t)k * n_p + e] = v;
+    }
+    if (in_range) {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) Pbar[(size_t)(i * LPE + h) * n_p + e] = acc[i];
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int wdx = 0; wdx < NT / 32; ++wdx) tot += red[wdx];
     loss_partial_fused[blockIdx.x] = tot;
   }
 }
@@ -1750,6 +1897,8 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
       CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_smem_kernel<1, kTaylorThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       113 * 1024));
       ew_attr[dev] = true;
     }
   }
@@ -1768,7 +1917,19 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   taylor_fused_kernel<L, U><<<ebl, EW_THREADS, fsmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, s_arr, deg_arr, a.C, X0, \
                                                                 Pbar, fused_partial)
     static const int tu = getenv("CHERRY_FIT_TAYLOR_U") ? atoi(getenv("CHERRY_FIT_TAYLOR_U")) : kTaylorInterleave;  // A/B switch
-    if (lpe == 2) CHERRY_TAYLOR_LAUNCH(2, 1);
+    static const int pws = getenv("CHERRY_FIT_TAYLOR_SMEM") ? atoi(getenv("CHERRY_FIT_TAYLOR_SMEM")) : 1;  // A/B switch (0: powers in registers, one CTA per SM)
+    const bool two_ctas_fit = 2 * (wsmem + 3 * sizeof(int) * a.K + 8 + sizeof(double) * (kTaylorStagesS + kDeg) * kTaylorThreads + 1024) <=
+                              (size_t)227 * 1024;  // else (K > ~105): the register variant, one CTA per SM
+    if (pws && two_ctas_fit) {
+      // kTaylorThreads per CTA, two CTAs per SM (128 registers: the powers live in shared memory)
+      constexpr int NT = kTaylorThreads;
+      const size_t ssmem = wsmem + 3 * sizeof(int) * a.K + 8 + sizeof(double) * (kTaylorStagesS + kDeg) * NT;
+      int grid2 = (int)((p.n_p + NT - 1) / NT);
+      if (grid2 > 2 * sm_count()) grid2 = 2 * sm_count();
+      fused_blocks = grid2;
+      taylor_fused_smem_kernel<1, NT><<<grid2, NT, ssmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, s_arr, deg_arr, a.C, X0,
+                                                                    Pbar, fused_partial);
+    } else if (lpe == 2) CHERRY_TAYLOR_LAUNCH(2, 1);
     else if (tu == 4) CHERRY_TAYLOR_LAUNCH(1, 4);
     else if (tu == 2) CHERRY_TAYLOR_LAUNCH(1, 2);
     else CHERRY_TAYLOR_LAUNCH(1, 1);
