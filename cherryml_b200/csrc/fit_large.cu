@@ -455,7 +455,10 @@ constexpr int kDfSlabs = 5;      // row slabs of a tile's reduction (16 rows eac
 __host__ __device__ inline size_t df_state_ints(int n_mats, int tiles, int n_groups) {
   return 4 + (size_t)n_mats * tiles * kDfSlabs + (size_t)n_groups;
 }
-constexpr int kDfReduceLag = 60; // groups between a product and its reduction items in the queue (~ one turnover of the grid)
+constexpr int kDfReduceLag = 1 << 20;  // groups between a product and its reduction items in the queue: effectively "all
+                                        // of a level's products first, then its reductions" -- sweeps of 10..1000 groups
+                                        // (gpurun_out/r02_fit_reduce_lag_sweep.txt, r02_fit_chain_sweep2/3.txt): a reduction
+                                        // taken before its products are done idles a CTA that could have run a product
 
 __device__ __forceinline__ void df_wait_tile(const int* v, int target, int* status_flag) {
   unsigned spins = 0;
@@ -1503,6 +1506,7 @@ void make_plan(Plan& p, int S, int K, char* base) {
         if (count > 0) --count;
       }
     };
+    static const int reduce_lag = getenv("CHERRY_FIT_REDUCE_LAG") ? atoi(getenv("CHERRY_FIT_REDUCE_LAG")) : kDfReduceLag;  // A/B switch
     // one output matrix update C (+)= sum of terms, for every tile; slices of 80 (fine) or whole K per term (coarse)
     auto add_update = [&](DfList& L, double* C, int c_mat, int need_ver, int accumulate,
                           const std::vector<TermSpec>& terms, int per_term) {
@@ -1531,13 +1535,13 @@ void make_plan(Plan& p, int S, int K, char* base) {
           L.groups.push_back(g);
           const bool direct = (g.n_slices == 1) && !g.accumulate;
           if (!direct) L.pending.push_back(gi);
-          if ((int)L.pending.size() > kDfReduceLag) emit_reduce(L, 1);
+          if ((int)L.pending.size() > reduce_lag) emit_reduce(L, 1);
         }
     };
     // K slices per term of a level with `term_tiles` (term, output tile) products: as few as keep about
     // `target` work items in the level (every item pays ~3 us of queue / fence / reduction latency, a
     // 80-deep slice is only 10 us of arithmetic), at most 5 (80-deep)
-    static const int chain_target = getenv("CHERRY_FIT_CHAIN_TARGET") ? atoi(getenv("CHERRY_FIT_CHAIN_TARGET")) : 500;
+    static const int chain_target = getenv("CHERRY_FIT_CHAIN_TARGET") ? atoi(getenv("CHERRY_FIT_CHAIN_TARGET")) : 500;  // sweeps 300..4000: gpurun_out/r02_fit_chain_target_sweep.txt, r02_fit_chain_sweep3.txt
     auto slices_for = [&](int term_tiles) {
       for (int n : {1, 2, 3, 4})
         if (term_tiles * n >= chain_target) return n;
