@@ -34,7 +34,8 @@ namespace {
 constexpr int kDeg = 24;          // Taylor degree of the shared-power polynomial
 constexpr double kTheta = 2.2;    // tau*mu bound: 2.2^25/25! ~ 2e-17 (all terms non-negative)
 constexpr int kSStore = 8;        // squarings kept per bucket: covers t*mu up to 2.2 * 2^8 = 563
-constexpr int BT = 80, BK = 16, NSTAGE = 3;
+constexpr int BT = 80, BK = 16, NSTAGE = 2;  // two stages (51 KB per CTA): THREE CTAs share an SM; three stages with two CTAs
+                                              // measured 0.851 ms per epoch against 0.820 (gpurun_out/r02_fit_stage2_sweep.txt)
 constexpr int KGROUPS = 1;  // >1: warp groups split every k chunk (lower tile latency, measured 30% less throughput)
 constexpr int GEMM_THREADS = 128 * KGROUPS;
 constexpr int LD_ROW = 20;        // tile stored [80][16]: k contiguous
@@ -1858,10 +1859,11 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   int* df_state_fwd = reinterpret_cast<int*>(base + p.df_fwd.off_state);
   int* df_state_bwd = reinterpret_cast<int*>(base + p.df_bwd.off_state);
   int* deg_arr = reinterpret_cast<int*>(base + p.off_deg);
+  static const int ctas_per_sm = getenv("CHERRY_FIT_CTAS_PER_SM") ? atoi(getenv("CHERRY_FIT_CTAS_PER_SM")) : 3;  // 2-stage pipeline: 51 KB and ~20 K registers per CTA
   static const bool full_degree = getenv("CHERRY_FIT_FULL_DEGREE") != nullptr;  // A/B switch: round-1 Taylor pass
   static const int sq_ksplit_max = getenv("CHERRY_FIT_SQ_KSPLIT") ? atoi(getenv("CHERRY_FIT_SQ_KSPLIT")) : 2;  // A/B switch (graph-replayed epochs: 1 -> 1.04 ms, 2 -> 0.94, 5 -> 0.96)
   coef_kernel<<<1, 256, 0, stream>>>(a.t, a.K, sc, s_arr, deg_arr, w, tau, a.status_flag, sched, p.tiles,
-                                     (KGROUPS == 1 ? 2 : 1) * sm_count(), df_state_fwd,
+                                     (KGROUPS == 1 ? ctas_per_sm : 1) * sm_count(), df_state_fwd,
                                      (int)df_state_ints(p.df_fwd.n_mats, p.tiles, (int)p.df_fwd.groups.size()),
                                      df_state_bwd,
                                      (int)df_state_ints(p.df_bwd.n_mats, p.tiles, (int)p.df_bwd.groups.size()),
@@ -1870,7 +1872,6 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   mark("build_B+coef", stream);
   static const bool level_launch = getenv("CHERRY_FIT_LEVEL_LAUNCH") != nullptr;  // A/B switch: round-1 schedule
   const size_t gemm_smem = (size_t)NSTAGE * 2 * TILE_ELEMS * sizeof(double);
-  static const int ctas_per_sm = getenv("CHERRY_FIT_CTAS_PER_SM") ? atoi(getenv("CHERRY_FIT_CTAS_PER_SM")) : 2;
   const int persistent_grid = (KGROUPS == 1 ? ctas_per_sm : 1) * sm_count();
   auto launch_chain = [&](const DfList& L, int* state, const char* name) -> int {
     long long* prof = nullptr;
