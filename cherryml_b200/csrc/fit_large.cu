@@ -1136,32 +1136,49 @@ taylor_fused_smem_kernel(const double* __restrict__ powers, size_t n_p, int S, i
   }
 }
 
-// grid = (blocks, K): loss partials and G_k = -C_k / P_k into chain slot s_k + 1.
-// P_k = X0_k if s_k == 0 else chain slot s_k.
+// Loss and G_k = -C_k / P_k (into chain slot s_k + 1) for the squared buckets of the list coef_kernel built
+// (training) or for all buckets; P_k = X0_k if s_k == 0 else chain slot s_k.  1-D grid: block = (chunk of
+// 4 * EW_THREADS elements, list position mod kLossLanes); one loss partial per block (only the SUM over the buckets
+// is used downstream: loss_reduce_kernel puts it into loss_part[0]).  A grid of (blocks, K) launched 7 900 CTAs of
+// which 87 % returned at once: 36 us for 13 buckets of work.
+constexpr int kLossLanes = 16;  // list positions processed side by side
 __global__ void __launch_bounds__(EW_THREADS)
-loss_grad_kernel(const double* __restrict__ C, int S, int Sp, size_t n_p, const int* __restrict__ s_arr,
-                 const double* __restrict__ X0, double* __restrict__ chain, int slots_per_bucket,
-                 double* __restrict__ loss_partial, int skip_unsquared) {
+loss_grad_kernel(const double* __restrict__ C, int S, int Sp, size_t n_p, int K, const int* __restrict__ s_arr,
+                 const int* __restrict__ deg_arr, const double* __restrict__ X0, double* __restrict__ chain,
+                 int slots_per_bucket, double* __restrict__ loss_partial, int skip_unsquared) {
   __shared__ double red[EW_THREADS / 32];
-  const int k = blockIdx.y, s = s_arr[k];
-  if (skip_unsquared && s == 0) return;  // handled by taylor_fused_kernel
-  const double* P = (s == 0) ? X0 + (size_t)k * n_p
-                             : chain + ((size_t)k * slots_per_bucket + (s - 1)) * n_p;
-  double* G = chain + ((size_t)k * slots_per_bucket + s) * n_p;  // slot s+1 (slots are 1-based)
-  const double* Ck = C + (size_t)k * S * S;
+  const int n_list = skip_unsquared ? deg_arr[3 * K + 1] : K;
+  const int n_chunks = (int)((n_p + 4 * EW_THREADS - 1) / (4 * EW_THREADS));
+  const int chunk = blockIdx.x % n_chunks, lane0 = blockIdx.x / n_chunks;
   double part = 0.0;
-  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n_p; e += (size_t)gridDim.x * blockDim.x) {
-    const int row = (int)(e / Sp), col = (int)(e - (size_t)row * Sp);
-    double gval = 0.0;
-    if (row < S && col < S) {
-      const double c = Ck[(size_t)row * S + col];
-      if (c != 0.0) {
-        const double p = P[e];
-        part -= c * log(p);
-        gval = -c / p;
-      }
+  for (int i = lane0; i < n_list; i += kLossLanes) {
+    const int k = skip_unsquared ? deg_arr[2 * K + i] : i;
+    const int s = s_arr[k];
+    const double* P = (s == 0) ? X0 + (size_t)k * n_p
+                               : chain + ((size_t)k * slots_per_bucket + (s - 1)) * n_p;
+    double* G = chain + ((size_t)k * slots_per_bucket + s) * n_p;  // slot s+1 (slots are 1-based)
+    const double* Ck = C + (size_t)k * S * S;
+    double c[4], pv[4];
+    size_t e[4];
+    bool in[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      e[u] = ((size_t)chunk * 4 + u) * EW_THREADS + threadIdx.x;
+      in[u] = e[u] < n_p;
+      const int row = in[u] ? (int)(e[u] / Sp) : 0, col = in[u] ? (int)(e[u] - (size_t)row * Sp) : 0;
+      const bool real = in[u] && row < S && col < S;
+      c[u] = real ? Ck[(size_t)row * S + col] : 0.0;
+      pv[u] = in[u] ? P[e[u]] : 1.0;
     }
-    G[e] = gval;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      double gval = 0.0;
+      if (c[u] != 0.0) {
+        part -= c[u] * log(pv[u]);
+        gval = -c[u] / pv[u];
+      }
+      if (in[u]) G[e[u]] = gval;
+    }
   }
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
@@ -1169,57 +1186,70 @@ loss_grad_kernel(const double* __restrict__ C, int S, int Sp, size_t n_p, const 
   if (threadIdx.x == 0) {
     double tot = 0.0;
     for (int wdx = 0; wdx < EW_THREADS / 32; ++wdx) tot += red[wdx];
-    loss_partial[(size_t)k * gridDim.x + blockIdx.x] = tot;
+    loss_partial[blockIdx.x] = tot;
   }
 }
 
-// One CTA.  loss_part[k] = sum of the bucket's block partials (squared buckets only when the
-// fused pass handled the rest); the fused pass' total is added to loss_part[0].  Fixed orders.
+// One CTA.  loss_part[0] = sum of the loss partials of loss_grad_kernel (block order) + of the fused Taylor pass
+// (block order), loss_part[1..K) = 0: only the sum over the buckets is defined for S > 32.  Fixed orders.
 __global__ void loss_reduce_kernel(const double* __restrict__ loss_partial, int K, int nblocks,
-                                   double* __restrict__ loss_part, const int* __restrict__ s_arr,
-                                   const double* __restrict__ fused_partial, int n_fused) {
+                                   double* __restrict__ loss_part, const double* __restrict__ fused_partial,
+                                   int n_fused) {
   __shared__ double sh[256];
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+  for (int k = threadIdx.x; k < K; k += blockDim.x) loss_part[k] = 0.0;
+  double v = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) v += loss_partial[b];
+  for (int b = threadIdx.x; b < n_fused; b += blockDim.x) v += fused_partial[b];
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
     double tot = 0.0;
-    if (n_fused == 0 || s_arr[k] > 0)
-      for (int b = 0; b < nblocks; ++b) tot += loss_partial[(size_t)k * nblocks + b];
-    loss_part[k] = tot;
-  }
-  if (n_fused > 0) {
-    double v = 0.0;
-    for (int b = threadIdx.x; b < n_fused; b += blockDim.x) v += fused_partial[b];
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double tot = 0.0;
-      for (int i = 0; i < (int)blockDim.x; ++i) tot += sh[i];
-      loss_part[0] += tot;
-    }
+    for (int i = 0; i < (int)blockDim.x; ++i) tot += sh[i];
+    loss_part[0] = tot;
   }
 }
 
-// Pbar_j = sum_k w[k][j] * X0bar_k (chain slot 1 of bucket k), j = 1..m; buckets in order.
+// Pbar_j = sum_k w[k][j] * X0bar_k (chain slot 1 of bucket k), j = 1..m; buckets in order.  Persistent: a CTA
+// stages the weights of the buckets it will read (only the squared ones in training: the list coef_kernel
+// built) once and walks over chunks of elements.
 __global__ void __launch_bounds__(EW_THREADS)
 accumulate_M_kernel(const double* __restrict__ chain, int slots_per_bucket, size_t n_p, int K,
                     const double* __restrict__ w, double* __restrict__ Pbar,
-                    const int* __restrict__ s_arr, int squared_only) {
-  extern __shared__ double sw[];
-  for (int i = threadIdx.x; i < K * (kDeg + 1); i += blockDim.x) sw[i] = w[i];
+                    const int* __restrict__ deg_arr, int squared_only) {
+  extern __shared__ double sw[];  // [n_list][m+1] weights, then the bucket list
+  __shared__ int n_list_s;
+  if (threadIdx.x == 0) n_list_s = squared_only ? deg_arr[3 * K + 1] : K;
   __syncthreads();
-  const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (e >= n_p) return;
-  double acc[kDeg];
+  const int n_list = n_list_s;
+  int* list = reinterpret_cast<int*>(sw + (size_t)K * (kDeg + 1));
+  for (int i = threadIdx.x; i < n_list; i += blockDim.x) list[i] = squared_only ? deg_arr[2 * K + i] : i;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_list * (kDeg + 1); i += blockDim.x)
+    sw[i] = w[(size_t)list[i / (kDeg + 1)] * (kDeg + 1) + i % (kDeg + 1)];
+  __syncthreads();
+  const size_t n_chunks = (n_p + blockDim.x - 1) / blockDim.x;
+  for (size_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const size_t e = chunk * blockDim.x + threadIdx.x;
+    if (e >= n_p) continue;
+    double acc[kDeg];
 #pragma unroll
-  for (int j = 0; j < kDeg; ++j) acc[j] = squared_only ? Pbar[(size_t)j * n_p + e] : 0.0;
-  for (int k = 0; k < K; ++k) {
-    if (squared_only && s_arr[k] == 0) continue;  // already folded in by taylor_fused_kernel
-    const double x = chain[((size_t)k * slots_per_bucket) * n_p + e];
-    const double* wk = sw + k * (kDeg + 1);
+    for (int j = 0; j < kDeg; ++j) acc[j] = squared_only ? Pbar[(size_t)j * n_p + e] : 0.0;
+    for (int i0 = 0; i0 < n_list; i0 += 4) {
+      double x[4];
 #pragma unroll
-    for (int j = 0; j < kDeg; ++j) acc[j] = fma(wk[j + 1], x, acc[j]);
+      for (int u = 0; u < 4; ++u)
+        x[u] = i0 + u < n_list ? chain[((size_t)list[i0 + u] * slots_per_bucket) * n_p + e] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i0 + u >= n_list) break;
+        const double* wk = sw + (i0 + u) * (kDeg + 1);
+#pragma unroll
+        for (int j = 0; j < kDeg; ++j) acc[j] = fma(wk[j + 1], x[u], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kDeg; ++j) Pbar[(size_t)j * n_p + e] = acc[j];
   }
-#pragma unroll
-  for (int j = 0; j < kDeg; ++j) Pbar[(size_t)j * n_p + e] = acc[j];
 }
 
 // grid = (blocks, K): P_out[k] (S x S, unpadded) = X0_k if s_k == 0 else chain slot s_k
@@ -1449,7 +1479,7 @@ void make_plan(Plan& p, int S, int K, char* base) {
   p.tiles = (p.Sp / BT) * (p.Sp / BT);
   p.n_p = (size_t)p.Sp * p.Sp;
   p.slots_per_bucket = kSStore + 1;
-  p.loss_blocks = (int)((p.n_p + EW_THREADS * 8 - 1) / (EW_THREADS * 8));
+  p.loss_blocks = (int)((p.n_p + 4 * EW_THREADS - 1) / (4 * EW_THREADS)) * kLossLanes;  // blocks of loss_grad_kernel
   const size_t mat = p.n_p * sizeof(double);
   const int n_theta = S + S * (S - 1) / 2;
   // upper bounds on descriptor counts: powers (2m tasks, 4m terms) + squarings (2 * kSStore * K tasks, 3x terms)
@@ -1465,7 +1495,7 @@ void make_plan(Plan& p, int S, int K, char* base) {
   p.off_deg = carve(sizeof(int) * (3 * (size_t)K + 2));  // degrees, then the unsquared / squared bucket lists and their lengths
   p.off_tau = carve(sizeof(double) * K);
   p.off_w = carve(sizeof(double) * K * (kDeg + 1));
-  p.off_loss_partial = carve(sizeof(double) * ((size_t)K * p.loss_blocks + 4 * ((p.n_p + EW_THREADS - 1) / EW_THREADS) + 4));
+  p.off_loss_partial = carve(sizeof(double) * ((size_t)p.loss_blocks + 4 * ((p.n_p + EW_THREADS - 1) / EW_THREADS) + 4));
   p.off_grad_theta = carve(sizeof(double) * n_theta);
   p.off_dpi = carve(sizeof(double) * S);
   p.off_pibuf = carve(sizeof(double) * S);
@@ -1909,7 +1939,7 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   }
   static const bool unfused = getenv("CHERRY_FIT_UNFUSED") != nullptr;  // A/B switch
   const bool fused = (P_out == nullptr) && !unfused;
-  double* fused_partial = loss_partial + (size_t)a.K * p.loss_blocks;
+  double* fused_partial = loss_partial + (size_t)p.loss_blocks;
   int fused_blocks = 0;
   if (fused) {
     const size_t fsmem = wsmem + 3 * sizeof(int) * a.K + 8 + sizeof(double) * kTaylorStages * EW_THREADS;
@@ -1962,10 +1992,11 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
     CHERRY_LAUNCH_CHECK("extract_P_kernel");
     return 0;
   }
-  loss_grad_kernel<<<dim3(p.loss_blocks, a.K), EW_THREADS, 0, stream>>>(a.C, a.S, p.Sp, p.n_p, s_arr, X0, chain,
-                                                                        p.slots_per_bucket, loss_partial, fused ? 1 : 0);
+  const int loss_grid = (int)((p.n_p + 4 * EW_THREADS - 1) / (4 * EW_THREADS)) * kLossLanes;
+  loss_grad_kernel<<<loss_grid, EW_THREADS, 0, stream>>>(a.C, a.S, p.Sp, p.n_p, a.K, s_arr, deg_arr, X0, chain,
+                                                         p.slots_per_bucket, loss_partial, fused ? 1 : 0);
   CHERRY_LAUNCH_CHECK("loss_grad_kernel");
-  loss_reduce_kernel<<<1, 256, 0, stream>>>(loss_partial, a.K, p.loss_blocks, a.loss_part, s_arr, fused_partial,
+  loss_reduce_kernel<<<1, 256, 0, stream>>>(loss_partial, a.K, loss_grid, a.loss_part, fused_partial,
                                             fused ? fused_blocks : 0);
   CHERRY_LAUNCH_CHECK("loss_reduce_kernel");
   mark("loss_grad", stream);
@@ -1979,8 +2010,8 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
     CHERRY_LAUNCH_CHECK("squaring_dataflow_kernel<bwd>");
   }
   mark("squarings_bwd", stream);
-  accumulate_M_kernel<<<eb, EW_THREADS, wsmem, stream>>>(chain, p.slots_per_bucket, p.n_p, a.K, w, Pbar, s_arr,
-                                                         fused ? 1 : 0);
+  accumulate_M_kernel<<<std::min(eb, 4 * sm_count()), EW_THREADS, wsmem + sizeof(int) * a.K, stream>>>(
+      chain, p.slots_per_bucket, p.n_p, a.K, w, Pbar, deg_arr, fused ? 1 : 0);
   CHERRY_LAUNCH_CHECK("accumulate_M_kernel");
   mark("accumulate_M", stream);
   if (level_launch) {

@@ -309,7 +309,8 @@ int cherry_fit_run(const cherry_fit_args* args, int num_epochs, void* stream);
 int cherry_fit_epoch_local(const cherry_fit_args* args, double* packed, void* stream);
 int cherry_fit_epoch_update(const cherry_fit_args* args, const double* packed, void* stream);
 /* One evaluation without an optimiser step (tests, evaluation): writes loss_part[p*K+k] =
- * -<C_k, log expm(t_k Q_p)> and dQ_part[p*K+k] = its gradient with respect to Q_p. */
+ * -<C_k, log expm(t_k Q_p)> and dQ_part[p*K+k] = its gradient with respect to Q_p (S <= 32).  For S > 32
+ * only the sums over k are defined: loss_part[0] holds the whole loss, dQ_part[0] the whole gradient. */
 int cherry_fit_loss_grad(const cherry_fit_args* args, void* stream);
 
 /* P_out[p*K + k] = expm(t[p*K + k] * Q[p]) (fp64 [S][S] each) with the fit's forward algorithm.
