@@ -139,6 +139,7 @@ template <int NT>
 __device__ __forceinline__ void update_small_body(const UpdateArgs& a, int p, double* sm, double* red,
                                                   int* sh_improved_p) {
   int& sh_improved = *sh_improved_p;
+  (void)red;  // the block reductions of this body became warp shuffles (S <= 32)
   const int tid = threadIdx.x, S = a.S, SS = S * S;
   const int n_upper = S * (S - 1) / 2, n_theta = S + n_upper;
   double* G = sm;             // dL/dQ
@@ -157,15 +158,16 @@ __device__ __forceinline__ void update_small_body(const UpdateArgs& a, int p, do
     // ---- reduce the per-bucket pieces in bucket order
     const double scale = a.loss_normalization ? 1.0 / a.sumC[p] : 1.0;
     for (int e = tid; e < SS; e += NT) {
-      // loads of 8 buckets in flight, added in bucket order (same result as a plain loop)
+      // loads of 20 buckets in flight (the reduction is L2-latency bound: K / 20 round trips), added in bucket
+      // order (same result as a plain loop)
       double acc = 0.0;
       const double* src = a.dQ_part + (size_t)p * a.K * SS + e;
-      for (int k0 = 0; k0 < a.K; k0 += 8) {
-        double v[8];
+      for (int k0 = 0; k0 < a.K; k0 += 20) {
+        double v[20];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (k0 + j < a.K) ? __ldcg(src + (size_t)(k0 + j) * SS) : 0.0;
+        for (int j = 0; j < 20; ++j) v[j] = (k0 + j < a.K) ? __ldcg(src + (size_t)(k0 + j) * SS) : 0.0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc += v[j];
+        for (int j = 0; j < 20; ++j) acc += v[j];
       }
       G[e] = acc * scale;
     }
@@ -199,20 +201,23 @@ __device__ __forceinline__ void update_small_body(const UpdateArgs& a, int p, do
       if (snap && snap_idx < a.n_snapshots) a.snapshots[(size_t)snap_idx * SS + e] = q;
     }
   }
-  // ---- softmax(pi logits), sqrt
-  {
-    double mx = -INFINITY;
-    for (int i = tid; i < S; i += NT) mx = fmax(mx, theta[i]);
-    mx = block_reduce_max<NT>(mx, red);
-    double se = 0.0;
-    for (int i = tid; i < S; i += NT) se += exp(theta[i] - mx);
-    se = block_reduce_sum<NT>(se, red);
-    for (int i = tid; i < S; i += NT) {
-      pi[i] = exp(theta[i] - mx) / se;
-      rr[i] = sqrt(pi[i]);
+  // ---- softmax(pi logits), sqrt: S <= 32, so warp 0 does it with shuffles (one block barrier instead of five)
+  auto softmax_to_shared = [&]() {
+    if (tid < 32) {
+      const double th = tid < S ? theta[tid] : -INFINITY;
+      double mx = th;
+      for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const double ex = tid < S ? exp(th - mx) : 0.0;
+      double se = ex;
+      for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+      if (tid < S) {
+        pi[tid] = ex / se;
+        rr[tid] = sqrt(ex / se);
+      }
     }
     __syncthreads();
-  }
+  };
+  softmax_to_shared();
   if (a.mode == 1) {
     // ---- adjoint of Q = M - diag(rowsum M), M_ij = s_ij r_j / r_i
     for (int e = tid; e < SS; e += NT) {
@@ -240,9 +245,9 @@ __device__ __forceinline__ void update_small_body(const UpdateArgs& a, int p, do
       dpi[i] = dr[i] / (2.0 * rr[i]);
     }
     __syncthreads();
-    double dot = 0.0;
-    for (int i = tid; i < S; i += NT) dot += pi[i] * dpi[i];
-    dot = block_reduce_sum<NT>(dot, red);
+    // every warp forms the dot product itself (S <= 32 terms, same order in every warp): no block barrier
+    double dot = (tid & 31) < S ? pi[tid & 31] * dpi[tid & 31] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
     const int step = epoch + 1;
     const double bc1 = 1.0 - pow(a.beta1, (double)step);
     const double bc2s = sqrt(1.0 - pow(a.beta2, (double)step));
@@ -266,17 +271,7 @@ __device__ __forceinline__ void update_small_body(const UpdateArgs& a, int p, do
     }
     __syncthreads();
     // ---- new softmax for the next epoch's Q
-    double mx = -INFINITY;
-    for (int i = tid; i < S; i += NT) mx = fmax(mx, theta[i]);
-    mx = block_reduce_max<NT>(mx, red);
-    double se = 0.0;
-    for (int i = tid; i < S; i += NT) se += exp(theta[i] - mx);
-    se = block_reduce_sum<NT>(se, red);
-    for (int i = tid; i < S; i += NT) {
-      pi[i] = exp(theta[i] - mx) / se;
-      rr[i] = sqrt(pi[i]);
-    }
-    __syncthreads();
+    softmax_to_shared();
   }
   // ---- Q(theta): off-diagonal M, then the diagonal from the row sums (fixed order)
   for (int e = tid; e < SS; e += NT) {
