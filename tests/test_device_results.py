@@ -56,3 +56,40 @@ def test_device_results_are_bounded_and_follow_the_file(tmp_path):
     assert ct.device_result(dirs[2]) is None
     ct.clear_device_results()
     assert ct.device_result(dirs[1]) is None
+
+
+def test_fast_cherries_handoff_is_keyed_one_shot_and_follows_the_files(tmp_path):
+    """The FastCherries -> counting hand-off (phylogeny_estimation/_fast_cherries.take_handoff): only the
+    exact (tree dir, site-rate dir, MSA dir, families, alphabet) takes it, it is handed out once, and a tree or
+    site-rate file changed on disk wins over the resident copy.  A dict stands in for the device results."""
+    from cherryml_b200.phylogeny_estimation import _fast_cherries as fc
+
+    dirs = {k: str(tmp_path / k) for k in ("tree", "rates", "msa")}
+    for d in dirs.values():
+        os.makedirs(d)
+    fams, alphabet = ["a", "b"], ["A", "C"]
+    paths = [os.path.join(dirs["tree"], f + ".txt") for f in fams] + [os.path.join(dirs["rates"], f + ".txt") for f in fams]
+    for p in paths:
+        with open(p, "w") as fh:
+            fh.write("x\n")
+
+    def stash():
+        fc.clear_handoff()
+        stamps = {p: (os.stat(p).st_size, os.stat(p).st_mtime_ns) for p in paths}
+        fc._HANDOFF["entry"] = dict(key=(os.path.realpath(dirs["tree"]), os.path.realpath(dirs["rates"]),
+                                         os.path.realpath(dirs["msa"]), tuple(fams), tuple(alphabet)),
+                                    out="resident", stamps=stamps)
+
+    stash()
+    assert fc.take_handoff(dirs["tree"], dirs["rates"], dirs["msa"], fams, alphabet)["out"] == "resident"
+    assert fc.take_handoff(dirs["tree"], dirs["rates"], dirs["msa"], fams, alphabet) is None  # one shot
+    stash()
+    assert fc.take_handoff(dirs["tree"], dirs["rates"], dirs["msa"], ["a"], alphabet) is None  # other families
+    assert "entry" not in fc._HANDOFF  # a non-matching call drops it too (its memory is released)
+    stash()
+    assert fc.take_handoff(dirs["tree"], dirs["rates"], str(tmp_path), fams, alphabet) is None  # other MSA dir
+    stash()
+    with open(paths[0], "w") as fh:
+        fh.write("changed on disk\n")
+    assert fc.take_handoff(dirs["tree"], dirs["rates"], dirs["msa"], fams, alphabet) is None
+    fc.clear_handoff()
