@@ -42,22 +42,23 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // products): every warp owns one output tile, all operand fragments of the tile are loaded up
 // front (independent loads), and the k-steps alternate between two accumulators to halve the
 // DMMA dependency chain.
-template <bool TA, bool TB, bool ACC, int NT>
-__device__ __forceinline__ void mm(double* D, const double* A, const double* B, int nt, int ld) {
+template <bool TA, bool TB, bool ACC, int NT, int NTL>
+__device__ __forceinline__ void mm(double* D, const double* A, const double* B) {
+  // NTL = tiles per side at compile time (spad = 8 NTL, ld = spad + 4): every offset below is an immediate
+  // (round 2: with runtime nt / ld a product cost ~150 instructions per warp, two thirds of them address
+  // arithmetic, and an LG epoch is a chain of ~45 such products per bucket)
+  constexpr int nt = NTL, ld = 8 * NTL + 4, nsteps = 2 * NTL;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tg = lane & 3;
-  constexpr int kMaxSteps = kMaxSmallS / 4;  // 8 k-steps of 4
-  const int nsteps = nt * 2;
   for (int tile = warp; tile < nt * nt; tile += NT / 32) {
     const int r0 = (tile / nt) * 8, c0 = (tile % nt) * 8;
-    double a[kMaxSteps], b[kMaxSteps];
+    double a[nsteps], b[nsteps];
+    const double* Ap = TA ? A + tg * ld + r0 + g : A + (r0 + g) * ld + tg;
+    const double* Bp = TB ? B + (c0 + g) * ld + tg : B + tg * ld + c0 + g;
 #pragma unroll
-    for (int st = 0; st < kMaxSteps; ++st) {
-      if (st < nsteps) {
-        const int k0 = st * 4;
-        a[st] = TA ? A[(k0 + tg) * ld + r0 + g] : A[(r0 + g) * ld + k0 + tg];
-        b[st] = TB ? B[(c0 + g) * ld + k0 + tg] : B[(k0 + tg) * ld + c0 + g];
-      }
+    for (int st = 0; st < nsteps; ++st) {
+      a[st] = TA ? Ap[st * 4 * ld] : Ap[st * 4];
+      b[st] = TB ? Bp[st * 4] : Bp[st * 4 * ld];
     }
     double* out = D + (r0 + g) * ld + c0 + 2 * tg;
     double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
@@ -66,9 +67,9 @@ __device__ __forceinline__ void mm(double* D, const double* A, const double* B, 
       d1 = out[1];
     }
 #pragma unroll
-    for (int st = 0; st < kMaxSteps; st += 2) {
-      if (st < nsteps) dmma884(d0, d1, a[st], b[st]);
-      if (st + 1 < nsteps) dmma884(e0, e1, a[st + 1], b[st + 1]);
+    for (int st = 0; st < nsteps; st += 2) {
+      dmma884(d0, d1, a[st], b[st]);
+      dmma884(e0, e1, a[st + 1], b[st + 1]);
     }
     out[0] = d0 + e0;
     out[1] = d1 + e1;
@@ -300,7 +301,7 @@ __device__ __forceinline__ void update_small_body(const UpdateArgs& a, int p, do
 
 
 // grid.x = n_problems * K.  Problem p = blockIdx.x / K owns Q[p], buckets (p, 0..K-1).
-template <int NT, int MINB>
+template <int NT, int MINB, int NTL>
 __global__ void __launch_bounds__(NT, MINB)
 expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__ tall,
                      const double* __restrict__ Call, int S, int K, int n_smem_slots,
@@ -314,7 +315,7 @@ expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__
   __shared__ int sh_m, sh_s, sh_last, sh_improved;
   const int tid = threadIdx.x;
   const int b = blockIdx.x, prob = b / K;
-  const int nt = (S + 7) / 8, spad = nt * 8, ld = spad + 4, slot_elems = spad * ld;
+  constexpr int nt = NTL, spad = nt * 8, ld = spad + 4, slot_elems = spad * ld;  // host: NTL == (S + 7) / 8
   const double* __restrict__ Q = Qall + (size_t)prob * S * S;
   const double* __restrict__ C = Call + (size_t)b * S * S;
   const double t = tall[b];
@@ -365,7 +366,7 @@ expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__
     __syncthreads();
     for (int j = m - 2; j >= 0; --j) {
       double* Hj = (j >= 1) ? slot(j) : slot(sX);
-      mm<false, false, false, NT>(Hj, Bm, slot(j + 1), nt, ld);
+      mm<false, false, false, NT, NTL>(Hj, Bm, slot(j + 1));
       __syncthreads();
       const double cj = cherry::inv_factorial(j);
       if (tid < S) Hj[tid * ld + tid] += cj;
@@ -374,7 +375,7 @@ expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__
   }
   // ---- squarings
   for (int i = 0; i < s; ++i) {
-    mm<false, false, false, NT>(slot(sX + i + 1), slot(sX + i), slot(sX + i), nt, ld);
+    mm<false, false, false, NT, NTL>(slot(sX + i + 1), slot(sX + i), slot(sX + i));
     __syncthreads();
   }
   double* P = slot(sX + s);
@@ -407,9 +408,9 @@ expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__
   // ---- adjoint of the squarings: Xbar_i = Xbar_{i+1} X_i^T + X_i^T Xbar_{i+1}
   int gcur = sG0, gnext = sG1;
   for (int i = s - 1; i >= 0; --i) {
-    mm<false, true, false, NT>(slot(gnext), slot(gcur), slot(sX + i), nt, ld);
+    mm<false, true, false, NT, NTL>(slot(gnext), slot(gcur), slot(sX + i));
     __syncthreads();
-    mm<true, false, true, NT>(slot(gnext), slot(sX + i), slot(gcur), nt, ld);
+    mm<true, false, true, NT, NTL>(slot(gnext), slot(sX + i), slot(gcur));
     __syncthreads();
     const int tmp = gcur;
     gcur = gnext;
@@ -420,8 +421,8 @@ expm_loss_grad_small(const double* __restrict__ Qall, const double* __restrict__
   for (int e = tid; e < slot_elems; e += NT) Bbar[e] = 0.0;
   __syncthreads();
   for (int j = 0; j <= m - 2; ++j) {
-    mm<false, true, true, NT>(Bbar, slot(gcur), slot(j + 1), nt, ld);
-    mm<true, false, false, NT>(slot(gnext), Bm, slot(gcur), nt, ld);
+    mm<false, true, true, NT, NTL>(Bbar, slot(gcur), slot(j + 1));
+    mm<true, false, false, NT, NTL>(slot(gnext), Bm, slot(gcur));
     __syncthreads();
     const int tmp = gcur;
     gcur = gnext;
@@ -541,16 +542,6 @@ int fit_small_expm(const cherry_fit_args& a, cudaStream_t stream, double* P_out,
     return fail(CHERRY_EINVAL, "fit: workspace of %zu bytes required, got %zu", need, a.workspace_bytes);
   static const bool no_fuse = getenv("CHERRY_FIT_SMALL_UNFUSED") != nullptr;  // A/B switch: two launches per epoch
   if (no_fuse) fuse_update = false;
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  CHERRY_CUDA(cudaGetDevice(&dev));
-  if (dev < 64 && !attr_set[dev]) {
-    CHERRY_CUDA(cudaFuncSetAttribute(expm_loss_grad_small<kSmallThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     226 * 1024));  // 227 KB minus this kernel's static shared memory
-    CHERRY_CUDA(cudaFuncSetAttribute(expm_loss_grad_small<kThroughputThreads, 2>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    attr_set[dev] = true;
-  }
   const UpdateArgs ua = make_update_args(a, 1, nullptr);
   int* arrive = fuse_update ? reinterpret_cast<int*>(reinterpret_cast<char*>(a.workspace) +
                                                      small_spill_bytes(sp, sb, a.n_problems, a.K))
@@ -558,14 +549,35 @@ int fit_small_expm(const cherry_fit_args& a, cudaStream_t stream, double* P_out,
   // the update body needs 4 S*S + 4 S doubles of the dynamic shared memory
   const size_t upd_smem = (size_t)(4 * a.S * a.S + 4 * a.S) * sizeof(double);
   if (smem < upd_smem) smem = upd_smem;
-  if (throughput_shape(a.S, grid))
-    expm_loss_grad_small<kThroughputThreads, 2><<<grid, kThroughputThreads, smem, stream>>>(
-        a.Q, a.t, a.C, a.S, a.K, ns, reinterpret_cast<double*>(a.workspace), sp, a.dQ_part, a.loss_part,
-        a.status_flag, P_out, ua, arrive);
-  else
-    expm_loss_grad_small<kSmallThreads, 1><<<grid, kSmallThreads, smem, stream>>>(
-        a.Q, a.t, a.C, a.S, a.K, ns, reinterpret_cast<double*>(a.workspace), sp, a.dQ_part, a.loss_part,
-        a.status_flag, P_out, ua, arrive);
+  const bool tp = throughput_shape(a.S, grid);
+  const int ntl = (a.S + 7) / 8;  // tiles per side: a template parameter of the kernel
+  // one instantiation per (shape, tiles per side); the attribute is set on first use per device
+  static bool attr_set[64][2][5] = {};
+  int dev = 0;
+  CHERRY_CUDA(cudaGetDevice(&dev));
+#define CHERRY_SMALL_LAUNCH(NTH, MINB, NTL_)                                                                     \
+  do {                                                                                                           \
+    if (dev < 64 && !attr_set[dev][MINB - 1][NTL_]) {                                                            \
+      CHERRY_CUDA(cudaFuncSetAttribute(expm_loss_grad_small<NTH, MINB, NTL_>,                                    \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,                              \
+                                       MINB == 1 ? 226 * 1024 : 112 * 1024));                                    \
+      attr_set[dev][MINB - 1][NTL_] = true;                                                                      \
+    }                                                                                                            \
+    expm_loss_grad_small<NTH, MINB, NTL_><<<grid, NTH, smem, stream>>>(                                          \
+        a.Q, a.t, a.C, a.S, a.K, ns, reinterpret_cast<double*>(a.workspace), sp, a.dQ_part, a.loss_part,        \
+        a.status_flag, P_out, ua, arrive);                                                                       \
+  } while (0)
+  if (tp) {  // S <= 24
+    if (ntl == 1) CHERRY_SMALL_LAUNCH(kThroughputThreads, 2, 1);
+    else if (ntl == 2) CHERRY_SMALL_LAUNCH(kThroughputThreads, 2, 2);
+    else CHERRY_SMALL_LAUNCH(kThroughputThreads, 2, 3);
+  } else {
+    if (ntl == 1) CHERRY_SMALL_LAUNCH(kSmallThreads, 1, 1);
+    else if (ntl == 2) CHERRY_SMALL_LAUNCH(kSmallThreads, 1, 2);
+    else if (ntl == 3) CHERRY_SMALL_LAUNCH(kSmallThreads, 1, 3);
+    else CHERRY_SMALL_LAUNCH(kSmallThreads, 1, 4);
+  }
+#undef CHERRY_SMALL_LAUNCH
   CHERRY_LAUNCH_CHECK("expm_loss_grad_small");
   return 0;
 }
