@@ -332,13 +332,13 @@ def bench_fit(device, lg_times=None, lg_counts: Optional[torch.Tensor] = None, n
     if cpu_baseline and rank == 0:
         # reference arms: the UNMODIFIED reference stage on the box's host cores and its
         # own device="cuda" path on this GPU, same count matrices and initialisation; the oracle port
-        # only when the reference package did not travel (oracle/_ref/pkg absent)
+        # only when the reference package did not travel (oracle/_ref/reference_package.tar.gz absent)
         import tempfile
 
-        from oracle.ref_package import reference_root
+        from oracle.ref_package import reference_available
 
         try:
-            if reference_root() is not None:
+            if reference_available():
                 work = tempfile.mkdtemp(prefix="cherry_ref_fit_")
                 lg = reference_fit_arms(lg_times, lg_counts, num_epochs, ref_epochs["lg_cpu"], ref_epochs["lg_cuda"], work)
                 co_ref = reference_fit_arms(grid, co_counts, num_epochs, ref_epochs["co_cpu"], ref_epochs["co_cuda"], work)

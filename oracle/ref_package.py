@@ -4,9 +4,10 @@ INFRASTRUCTURE -- nothing under cherryml_b200/ imports this).
 The GPU box has no /root/reference, and `bench.py --impl reference` / the `fit` section must
 time the reference's own ``quantized_transitions_mle`` there (CPU arm with
 all host threads and the reference's stock ``device="cuda"`` path on the same B200).  So, like
-the reference C++ programs compiled into ``oracle/_ref``, the build step copies the
-reference's ``cherryml/*.py`` tree into the git-ignored ``oracle/_ref/pkg`` (committed recipe,
-no reference source enters the repository history) and the snapshot carries it to the box.
+the reference C++ programs compiled into ``oracle/_ref``, the build step packs the
+reference's ``cherryml/*.py`` tree into ONE git-ignored archive ``oracle/_ref/reference_package.tar.gz``
+(committed recipe; no reference source file enters the repository or its history) and the snapshot carries it
+to the box, where it is unpacked into a temporary directory for the lifetime of the process that times it.
 
 ``import_reference()`` imports it with stand-ins for third-party modules that are absent in
 this image (ete3, matplotlib, seaborn, biotite, wget, parameterized), a stub for its Cython
@@ -22,45 +23,62 @@ from unittest import mock
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_CHECKOUT = "/root/reference"
-PKG_DIR = os.path.join(HERE, "_ref", "pkg")
+ARCHIVE = os.path.join(HERE, "_ref", "reference_package.tar.gz")
+_EXTRACTED = {}
 
 
 def build_reference_package() -> bool:
-    """Copy cherryml/**/*.py from the reference checkout into oracle/_ref/pkg (build container
-    only).  Returns True if the copy exists afterwards."""
+    """Pack cherryml/**/*.py of the reference checkout into ONE git-ignored archive under oracle/_ref (build
+    container only; no reference source file is ever placed in the tree).  Returns True if the archive exists
+    afterwards."""
+    import tarfile
+
     src = os.path.join(REF_CHECKOUT, "cherryml")
-    dst = os.path.join(PKG_DIR, "cherryml")
     if os.path.isdir(src):
-        stamp = os.path.join(PKG_DIR, ".stamp")
         newest = max(os.path.getmtime(os.path.join(r, f)) for r, _, fs in os.walk(src) for f in fs if f.endswith(".py"))
-        if not (os.path.exists(stamp) and os.path.getmtime(stamp) >= newest):
-            shutil.rmtree(dst, ignore_errors=True)
-            for root, _, files in os.walk(src):
-                for f in files:
-                    if f.endswith(".py"):
-                        rel = os.path.relpath(os.path.join(root, f), src)
-                        out = os.path.join(dst, rel)
-                        os.makedirs(os.path.dirname(out), exist_ok=True)
-                        shutil.copyfile(os.path.join(root, f), out)
-            with open(stamp, "w") as fh:
-                fh.write("copied from /root/reference/cherryml by oracle/ref_package.py\n")
-    return os.path.isdir(dst)
+        if not (os.path.exists(ARCHIVE) and os.path.getmtime(ARCHIVE) >= newest):
+            os.makedirs(os.path.dirname(ARCHIVE), exist_ok=True)
+            tmp = ARCHIVE + ".tmp"
+            with tarfile.open(tmp, "w:gz") as tf:
+                for root, _, files in os.walk(src):
+                    for f in sorted(files):
+                        if f.endswith(".py"):
+                            full = os.path.join(root, f)
+                            tf.add(full, arcname=os.path.join("cherryml", os.path.relpath(full, src)))
+            os.replace(tmp, ARCHIVE)
+        shutil.rmtree(os.path.join(HERE, "_ref", "pkg"), ignore_errors=True)  # the unpacked tree of earlier builds
+    return os.path.exists(ARCHIVE)
 
 
 def reference_root():
-    """Directory that holds the reference's ``cherryml`` package, or None."""
-    if os.path.isdir(os.path.join(PKG_DIR, "cherryml")):
-        return PKG_DIR
+    """Directory that holds the reference's ``cherryml`` package (the checkout in the build container, else the
+    archive unpacked into a temporary directory for the lifetime of this process), or None."""
     if os.path.isdir(os.path.join(REF_CHECKOUT, "cherryml")):
         return REF_CHECKOUT
+    if os.path.exists(ARCHIVE):
+        if "dir" not in _EXTRACTED:
+            import atexit
+            import tarfile
+            import tempfile
+
+            d = tempfile.mkdtemp(prefix="cherry_ref_pkg_")
+            atexit.register(shutil.rmtree, d, True)
+            with tarfile.open(ARCHIVE) as tf:
+                tf.extractall(d)
+            _EXTRACTED["dir"] = d
+        return _EXTRACTED["dir"]
     return None
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REF_CHECKOUT, "cherryml")) or os.path.exists(ARCHIVE)
 
 
 def import_reference():
     """Import the reference package (see the module docstring for the stand-ins)."""
     root = reference_root()
     if root is None:
-        raise ImportError("the reference package is neither under oracle/_ref/pkg nor at /root/reference")
+        raise ImportError("neither /root/reference nor oracle/_ref/reference_package.tar.gz is present")
     for name in ("ete3", "matplotlib", "matplotlib.pyplot", "matplotlib.patches", "seaborn", "biotite",
                  "biotite.structure", "biotite.structure.io", "biotite.structure.io.pdb", "wget", "parameterized"):
         sys.modules.setdefault(name, mock.MagicMock())
