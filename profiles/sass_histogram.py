@@ -14,7 +14,8 @@ import sys
 
 LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cherryml_b200", "csrc", "libcherryml_b200.so")
 KERNELS = ["count_lg_kernel", "count_co_sorted_kernel", "bucket_table_tiles_kernel", "chain_dataflow_kernel",
-           "squaring_dataflow_kernel", "gemm_tasks_kernel", "taylor_fused_kernel", "expm_loss_grad_small",
+           "squaring_dataflow_kernel", "gemm_tasks_kernel", "taylor_fused_kernel", "taylor_fused_smem_kernel", "loss_grad_kernel",
+           "accumulate_M_kernel", "expm_loss_grad_small",
            "fit_update_small", "fc_pair_kernel", "fc_ble_kernel"]
 MARKERS = ["DMMA", "ATOMS.POPC.INC", "ATOMS", "LDGSTS", "RED", "ATOMG", "SYNCS", "IDP.4A", "LDG", "LDS", "STS", "BAR", "SHFL",
            "DFMA", "MUFU"]
