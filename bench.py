@@ -25,6 +25,7 @@ import sys
 import tempfile
 import threading
 import time
+from benchlib.hostcores import describe as host_cores, usable_cores
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
@@ -152,7 +153,7 @@ def rendered_sample(n_families, seed=0):
 
 def default_cpu_families():
     """Sample size of the CPU legs: ~1-2 s of reference time per step on the box's cores."""
-    return max(128, 16 * (os.cpu_count() or 1))
+    return max(128, 16 * usable_cores())
 
 
 def cpu_reference_run(n_families, seed=0, workdir=None):
@@ -167,7 +168,7 @@ def cpu_reference_run(n_families, seed=0, workdir=None):
                                          write_text_rendering)
     from cherryml_b200.utils import amino_acids
 
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     grid = quantization_grid()
     syn, tmp, names = rendered_sample(n_families, seed)
     examined = syn["n_sites_examined"]
@@ -232,7 +233,7 @@ def text_e2e_run(n_families, seed=0, reps=3):
     from cherryml_b200.synthetic import quantization_grid, synthetic_lg, write_text_rendering
     from cherryml_b200.utils import amino_acids
 
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     grid = quantization_grid()
     syn, tmp, names = rendered_sample(n_families, seed)
     best, ingest_s = float("inf"), 0.0
@@ -260,7 +261,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     n_fam = args.cpu_families or default_cpu_families()
     for _ in range(args.warmup):
         cpu_reference_run(n_fam)
@@ -474,7 +475,7 @@ def run_ours(args):
         torch.cuda.empty_cache()
         fit = bench_fit(device, lg_times=grid, lg_counts=counts,
                         process_group=dist.group.WORLD if world > 1 else None,
-                        cpu_baseline=(rank == 0 and not args.no_cpu_baseline))
+                        cpu_baseline=(rank == 0 and not args.no_cpu_baseline), defer_reference=True)
     _log("fit section done")
     # ---- FastCherries (tree estimation, the step before counting): every rank its own families
     fcb = None
@@ -534,6 +535,17 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    if fit is not None and "_deferred_reference" in fit:
+        # the reference's own fit arms, timed now that the other ranks are gone and this rank has the
+        # box's host cores and its GPU to itself (benchlib/fit.py attach_reference_arms says why)
+        from benchlib.fit import attach_reference_arms
+
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        if world > 1:
+            time.sleep(2.0)  # the other ranks are tearing down
+        attach_reference_arms(fit, fit.pop("_deferred_reference"))
+        _log("reference fit arms done")
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
@@ -559,6 +571,7 @@ def run_ours(args):
                    "transitions_examined_per_step": examined * world,
                    "transitions_counted_per_step_rank0": counted, "parity_slice_vs_oracle_all_ranks": parity},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "host_cores": host_cores(),
     }
     line["config"]["transitions_counted_per_s"] = counted * world / (ms_per_step * 1e-3)
     if strong is not None:
@@ -596,7 +609,7 @@ def run_ours(args):
     if apib is not None:
         line["public_api_demo"] = apib
     if not args.no_cpu_baseline:  # rank 0 (the other ranks have returned above)
-        cores = os.cpu_count() or 1
+        cores = usable_cores()
         n_cpu_fam = args.cpu_families or default_cpu_families()
         cb = cpu_reference_run(n_cpu_fam)
         cb.pop("seconds", None)

@@ -17,6 +17,7 @@ from cherryml_b200.io import read_rate_matrix
 from cherryml_b200.markov_chain import get_lg_path
 from cherryml_b200.utils import amino_acids
 from cherryml_b200.phylogeny_estimation import _fast_cherries as fc
+from benchlib.hostcores import usable_cores
 
 N_SEQS, N_SITES, N_RATE_CATS, MAX_ITERS, SEED = 1024, 300, 20, 50, 1234
 
@@ -134,7 +135,7 @@ def bench_fast_cherries(device, families: int = 2048, reps: int = 3, cpu_baselin
                 "counts identical to the route through tree / site-rate files (tests)",
     }
     if cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = usable_cores()
         n = min(families, cpu_families or max(128, 16 * cores))
         tmp = tempfile.mkdtemp(prefix="cherry_fc_")
         try:

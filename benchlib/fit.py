@@ -10,6 +10,7 @@ import torch
 from cherryml_b200 import _lib
 from cherryml_b200.estimation._engine import FitEngine, theta_from_initialization
 from cherryml_b200.estimation._jtt_ipw import jtt_ipw_from_counts
+from benchlib.hostcores import usable_cores
 
 
 def measure_fp64_gemm_peak(device, n: int = 4096, reps: int = 5) -> float:
@@ -106,7 +107,7 @@ def cpu_fit_baseline(times, counts: torch.Tensor, num_epochs_full: int, epochs_t
 
     from oracle.fit_oracle import fit_oracle
 
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     old = torch.get_num_threads()
     torch.set_num_threads(cores)
     try:
@@ -162,7 +163,7 @@ def reference_fit_arms(times, counts: torch.Tensor, num_epochs_full: int, cpu_ep
     init_path = os.path.join(workdir, f"init_{S}.txt")
     write_count_matrices_array(list(times), states, counts.cpu().numpy(), counts_path, "python")
     write_rate_matrix(jtt_ipw_from_counts(times, counts), states, init_path)
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     out: Dict = {}
     for arm, epochs in (("cpu", cpu_epochs), ("cuda", cuda_epochs)):
         if epochs <= 0:
@@ -205,6 +206,45 @@ def reference_fit_arms(times, counts: torch.Tensor, num_epochs_full: int, cpu_ep
     return out
 
 
+def attach_reference_arms(out: Dict, inputs: Dict) -> None:
+    """Reference arms: the UNMODIFIED reference stage on the box's host cores and its
+    own device="cuda" path on this GPU, same count matrices and initialisation; the oracle port only
+    when the reference package did not travel (oracle/_ref/reference_package.tar.gz absent).
+
+    Run it when nothing else is using the host: the reference's cpu arm is one OpenMP team over all
+    cores and its cuda arm is launch-bound on one host thread, so both slow down many times over when
+    other ranks of the bench are still working on the same box (measured at N=2: 75 s instead of 1.8 s
+    for the 20x20 cpu arm while rank 1 ran its next section).  bench.py therefore defers this call to
+    the end, after the other ranks have exited."""
+    import shutil
+    import tempfile
+
+    from oracle.ref_package import reference_available
+
+    lg_times, lg_counts, grid, co_counts = (inputs[k] for k in ("lg_times", "lg_counts", "grid", "co_counts"))
+    num_epochs, ref_epochs = inputs["num_epochs"], inputs["ref_epochs"]
+    try:
+        if reference_available():
+            work = tempfile.mkdtemp(prefix="cherry_ref_fit_")
+            lg = reference_fit_arms(lg_times, lg_counts, num_epochs, ref_epochs["lg_cpu"], ref_epochs["lg_cuda"], work)
+            co_ref = reference_fit_arms(grid, co_counts, num_epochs, ref_epochs["co_cpu"], ref_epochs["co_cuda"], work)
+            shutil.rmtree(work, ignore_errors=True)
+            for key, arms in (("lg_20x20", lg), ("coevo_400x400", co_ref)):
+                if "cpu" in arms:
+                    out[key]["cpu_baseline"] = arms["cpu"]
+                if "cuda" in arms:
+                    out[key]["reference_cuda"] = arms["cuda"]
+                ours = out[key]["seconds_end_to_end"]
+                for arm, name in (("cpu", "speedup_vs_reference_cpu"), ("cuda", "speedup_vs_reference_cuda")):
+                    if arm in arms and "seconds_end_to_end" in arms[arm]:
+                        out[key][name] = arms[arm]["seconds_end_to_end"] / ours
+        else:
+            out["lg_20x20"]["cpu_baseline"] = cpu_fit_baseline(lg_times, lg_counts, num_epochs, 100)
+            out["coevo_400x400"]["cpu_baseline"] = cpu_fit_baseline(grid, co_counts, num_epochs, 2)
+    except Exception as e:  # the extra measurement must not cost the bench line
+        out["cpu_baseline_error"] = str(e)[:200]
+
+
 def _log(msg):
     import sys
 
@@ -214,7 +254,7 @@ def _log(msg):
 
 def bench_fit(device, lg_times=None, lg_counts: Optional[torch.Tensor] = None, num_epochs: int = 500,
               co_families: int = 16384, process_group=None, cpu_baseline: bool = False,
-              ref_epochs: Optional[Dict] = None) -> Dict:
+              ref_epochs: Optional[Dict] = None, defer_reference: bool = False) -> Dict:
     from cherryml_b200.counting._device import count_raw, sorted_grid, symmetrize
     from cherryml_b200.synthetic import as_device_batch, quantization_grid, synthetic_co, synthetic_lg
 
@@ -330,33 +370,10 @@ def bench_fit(device, lg_times=None, lg_counts: Optional[torch.Tensor] = None, n
                       "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)"}
     out["coevo_400x400"] = co
     if cpu_baseline and rank == 0:
-        # reference arms: the UNMODIFIED reference stage on the box's host cores and its
-        # own device="cuda" path on this GPU, same count matrices and initialisation; the oracle port
-        # only when the reference package did not travel (oracle/_ref/reference_package.tar.gz absent)
-        import tempfile
-
-        from oracle.ref_package import reference_available
-
-        try:
-            if reference_available():
-                work = tempfile.mkdtemp(prefix="cherry_ref_fit_")
-                lg = reference_fit_arms(lg_times, lg_counts, num_epochs, ref_epochs["lg_cpu"], ref_epochs["lg_cuda"], work)
-                co_ref = reference_fit_arms(grid, co_counts, num_epochs, ref_epochs["co_cpu"], ref_epochs["co_cuda"], work)
-                import shutil
-
-                shutil.rmtree(work, ignore_errors=True)
-                for key, arms in (("lg_20x20", lg), ("coevo_400x400", co_ref)):
-                    if "cpu" in arms:
-                        out[key]["cpu_baseline"] = arms["cpu"]
-                    if "cuda" in arms:
-                        out[key]["reference_cuda"] = arms["cuda"]
-                    ours = out[key]["seconds_end_to_end"]
-                    for arm, name in (("cpu", "speedup_vs_reference_cpu"), ("cuda", "speedup_vs_reference_cuda")):
-                        if arm in arms and "seconds_end_to_end" in arms[arm]:
-                            out[key][name] = arms[arm]["seconds_end_to_end"] / ours
-            else:
-                out["lg_20x20"]["cpu_baseline"] = cpu_fit_baseline(lg_times, lg_counts, num_epochs, 100)
-                out["coevo_400x400"]["cpu_baseline"] = cpu_fit_baseline(grid, co_counts, num_epochs, 2)
-        except Exception as e:  # the extra measurement must not cost the bench line
-            out["cpu_baseline_error"] = str(e)[:200]
+        inputs = {"lg_times": lg_times, "lg_counts": lg_counts.detach().cpu(), "grid": grid,
+                  "co_counts": co_counts.detach().cpu(), "num_epochs": num_epochs, "ref_epochs": ref_epochs}
+        if defer_reference:  # the caller runs attach_reference_arms once this rank has the box to itself
+            out["_deferred_reference"] = inputs
+        else:
+            attach_reference_arms(out, inputs)
     return out

@@ -10,6 +10,7 @@ import numpy as np
 from cherryml_b200.io import read_rate_matrix
 from cherryml_b200.markov_chain import get_lg_path
 from cherryml_b200.utils import amino_acids
+from benchlib.hostcores import usable_cores
 
 N_SEQS, N_SITES, NUM_EPOCHS, GRID_STEPS = 38, 331, 100, 8
 
@@ -78,7 +79,7 @@ def bench_siterm(device, families: int = 8, cpu_baseline: bool = True, seed: int
             mod.quantized_transitions_mle_vectorized_over_sites = real
         import os
 
-        cores = os.cpu_count() or 1
+        cores = usable_cores()
         t0 = time.perf_counter()
         cpu = fit_sites(captured["counts"], captured["times"], NUM_EPOCHS, captured["initialization"],
                         num_threads=cores)

@@ -27,10 +27,12 @@ def main():
     ap.add_argument("--mask", default=None)
     ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"])
     ap.add_argument("--epochs", type=int, required=True)
-    ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
+    ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--out", required=True)
     ap.add_argument("--lr", type=float, default=0.1)
     args = ap.parse_args()
+    if args.threads <= 0:
+        args.threads = os.cpu_count() or 1
     if os.environ.get("CHERRY_REF_FIT_DUMP_AFTER"):  # debugging aid: where is it if it stalls
         import faulthandler
 
