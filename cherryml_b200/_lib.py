@@ -84,6 +84,7 @@ _SIGNATURES = {
     "cherry_fit_epoch_local": (c_int, [_P, _P, _P]),
     "cherry_fit_epoch_update": (c_int, [_P, _P, _P]),
     "cherry_fit_schedule": (c_int, [_P, _P, _P, _P]),
+    "cherry_fit_symmetric_form": (c_int, [_P]),
     "cherry_expm_batched": (c_int, [_P, _P, _P]),
     "cherry_gemm_f64_batched": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "cherry_gemm_desc_bytes": (ctypes.c_size_t, [c_int]),

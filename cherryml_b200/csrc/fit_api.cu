@@ -25,7 +25,7 @@ int one_epoch(const cherry_fit_args& a, cudaStream_t stream) {
     if ((rc = cherry::fit_small_expm(a, stream, nullptr, !no_fuse))) return rc;
     return no_fuse ? cherry::fit_small_update(a, 1, stream) : 0;
   }
-  if ((rc = cherry::fit_large_expm(a, stream))) return rc;
+  if ((rc = cherry::fit_large_expm(a, stream, true))) return rc;
   return cherry::fit_large_update(a, 1, stream);
 }
 
@@ -59,7 +59,7 @@ int cherry_fit_epoch_local(const cherry_fit_args* a, double* packed, void* strea
   const bool small = a->S <= cherry::kSmallFitMaxS;
   if (!small && a->n_problems != 1)
     return cherry::fail(CHERRY_EINVAL, "fit_epoch_local: the large path fits one problem");
-  rc = small ? cherry::fit_small_expm(*a, stream) : cherry::fit_large_expm(*a, stream);
+  rc = small ? cherry::fit_small_expm(*a, stream) : cherry::fit_large_expm(*a, stream, true);
   if (rc) return rc;
   const int SS = a->S * a->S;
   dim3 grid((SS + 255) / 256 > 64 ? 64 : (SS + 255) / 256, a->n_problems);
@@ -131,6 +131,11 @@ int cherry_fit_schedule(const cherry_fit_args* a, int* squarings_out, double* mu
                         cherry::kSmallFitMaxS);
   if (degree_out) *degree_out = cherry::kLargeDegree;
   return cherry::fit_large_read_schedule(*a, squarings_out, mu_out);
+}
+
+int cherry_fit_symmetric_form(const cherry_fit_args* a) {
+  if (!a || a->S <= cherry::kSmallFitMaxS) return 0;
+  return cherry::fit_large_symmetric_form(*a);
 }
 
 int cherry_fit_run(const cherry_fit_args* a, int num_epochs, void* stream_) {

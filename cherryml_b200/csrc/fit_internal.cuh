@@ -17,7 +17,10 @@ int fit_small_update(const cherry_fit_args& a, int mode, cudaStream_t stream, co
 
 // S > 32 (the 400 x 400 co-evolution model): batched DMMA GEMM chain.  fit_large.cu
 int fit_large_workspace_bytes(int S, int K, int n_problems, size_t* bytes);
-int fit_large_expm(const cherry_fit_args& a, cudaStream_t stream);   // loss_part + dQ_total in dQ_part[0]
+// loss_part + dQ_total in dQ_part[0].  training: a.Q is the reversible model of a.theta / a.mask (the epoch entry
+// points) -- the evaluation may then run in the symmetric form, same results (fit_large.cu build_B_sym_kernel)
+int fit_large_expm(const cherry_fit_args& a, cudaStream_t stream, bool training = false);
+int fit_large_symmetric_form(const cherry_fit_args& a);  // 1: the training evaluations of this workspace use it
 int fit_large_forward_only(const cherry_fit_args& a, double* P_out, cudaStream_t stream);
 int fit_large_update(const cherry_fit_args& a, int mode, cudaStream_t stream, const double* reduced = nullptr);
 int fit_large_timeline(const cherry_fit_args& a, cudaStream_t stream);

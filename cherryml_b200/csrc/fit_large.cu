@@ -24,6 +24,8 @@
 // train_quantization (estimation/_ratelearn/trainer.py:156-187) for S = 400.
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "fit_common.cuh"
@@ -126,7 +128,11 @@ __device__ __forceinline__ void compute_chunk(const double* As, const double* Bs
 // tile pass ld_out = BT and a pointer shifted by -(m0 * BT + n0) (compact_tile_base below).
 template <typename TermFn>
 __device__ __forceinline__ void gemm_tile(TermFn get_term, int Sp, int m0, int n0, int c_begin, int c_end,
-                                          double* smem, double* out, bool add_old, int ld_out = 0) {
+                                          double* smem, double* out, bool add_old, int ld_out = 0,
+                                          double* mirror = nullptr) {
+  // mirror != nullptr (symmetric results): the tile is also stored transposed, mirror[(n0 + c) * Sp + m0 + r];
+  // the eight lanes that share a column hold eight consecutive rows, so the transposed stores fill 64-byte
+  // segments just like the direct ones
   if (ld_out == 0) ld_out = Sp;
   const int cpt = Sp / BK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
@@ -206,6 +212,11 @@ __device__ __forceinline__ void gemm_tile(TermFn get_term, int Sp, int m0, int n
         v.y += o.y;
       }
       *p = v;
+      if (mirror != nullptr) {
+        double* q = mirror + (ptrdiff_t)(n0 + cbase + 8 * j + 2 * tg) * Sp + m0 + rbase + 8 * i + g;
+        q[0] = v.x;
+        q[Sp] = v.y;
+      }
     }
 }
 
@@ -310,10 +321,13 @@ template <bool BWD>
 __global__ void __launch_bounds__(GEMM_THREADS)
 squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__ s_arr, int K, int Sp,
                          double* __restrict__ X0, double* __restrict__ chain, int slots_per_bucket,
-                         double* __restrict__ partial, int* __restrict__ status_flag) {
+                         double* __restrict__ partial, int* __restrict__ status_flag, int sym) {
+  // sym != 0: every matrix here is symmetric (reversible Q in the basis diag(sqrt(pi)), symmetric counts): only the
+  // tiles on and above the diagonal are work items, each stores its transpose as well.  coef_kernel built the
+  // schedule with the same tile count.
   extern __shared__ double smem[];
   __shared__ int s_item, s_last;
-  const int tiles_n = Sp / BT, tiles = tiles_n * tiles_n;
+  const int tiles_n = Sp / BT, tiles = sym ? tiles_n * (tiles_n + 1) / 2 : tiles_n * tiles_n;
   const size_t n_p = (size_t)Sp * Sp;
   const int n_levels = sched->n_levels;
   const int ksmax = sched->ksmax;
@@ -327,7 +341,7 @@ squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__
   // tile at a third of the SM's DMMA rate).  Every CTA writes its partial tile; the one that
   // arrives last adds them in z order (so the result does not depend on who is last), writes
   // the tile and moves the bucket's completion counter.
-  auto finish_tile = [&](int k, int tile, int m0, int n0, double* out, int ksplit) -> bool {
+  auto finish_tile = [&](int k, int tile, int m0, int n0, double* out, int ksplit, bool mirror) -> bool {
     if (ksplit == 1) return true;
     __threadfence();
     __syncthreads();
@@ -364,6 +378,11 @@ squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__
       const int e = threadIdx.x + q * GEMM_THREADS;
       const int r = e / (BT / 2), c2 = (e - r * (BT / 2)) * 2;
       *reinterpret_cast<double2*>(out + (size_t)(m0 + r) * Sp + n0 + c2) = v[q];
+      if (mirror) {
+        double* m = out + (size_t)(n0 + c2) * Sp + m0 + r;
+        m[0] = v[q].x;
+        m[Sp] = v[q].y;
+      }
     }
     return true;
   };
@@ -382,7 +401,18 @@ squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__
     const int z = local % ksplit, item_t = local / ksplit;
     const int bidx = item_t / tiles, tile = item_t - bidx * tiles;
     const int k = active[level * K + bidx];
-    const int m0 = (tile / tiles_n) * BT, n0 = (tile % tiles_n) * BT;
+    int ti = tile / tiles_n, tj = tile % tiles_n;
+    if (sym) {  // tile = index into the upper triangle, row by row
+      ti = 0;
+      int rest = tile;
+      while (rest >= tiles_n - ti) {
+        rest -= tiles_n - ti;
+        ++ti;
+      }
+      tj = ti + rest;
+    }
+    const int m0 = ti * BT, n0 = tj * BT;
+    const bool mirror = sym && ti != tj;
     double* Xi = (level == 0) ? X0 + (size_t)k * n_p : chain + ((size_t)k * slots_per_bucket + (level - 1)) * n_p;
     double* out = chain + ((size_t)k * slots_per_bucket + level) * n_p;  // slot level+1
     if (!BWD) {
@@ -390,8 +420,9 @@ squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__
       const GemmTerm t0{Xi, Xi, 0, 0};
       const int total = Sp / BK;
       double* dst = ksplit == 1 ? out : partial + ((size_t)rank[k] * ksmax + z) * n_p;
-      gemm_tile([&](int) { return t0; }, Sp, m0, n0, total * z / ksplit, total * (z + 1) / ksplit, smem, dst, false);
-      if (!finish_tile(k, tile, m0, n0, out, ksplit)) continue;
+      gemm_tile([&](int) { return t0; }, Sp, m0, n0, total * z / ksplit, total * (z + 1) / ksplit, smem, dst, false, 0,
+                (mirror && ksplit == 1) ? out : nullptr);
+      if (!finish_tile(k, tile, m0, n0, out, ksplit, mirror)) continue;
       __threadfence();  // every thread publishes its part of the tile before the counter moves
       __syncthreads();
       if (threadIdx.x == 0) atomicAdd(done_fwd + k * kSStore + level, 1);
@@ -405,8 +436,8 @@ squaring_dataflow_kernel(SqSchedule* __restrict__ sched, const int* __restrict__
       const int total = 2 * (Sp / BK);
       double* dst = ksplit == 1 ? out : partial + ((size_t)rank[k] * ksmax + z) * n_p;
       gemm_tile([&](int idx) { return idx == 0 ? t0 : t1; }, Sp, m0, n0, total * z / ksplit,
-                total * (z + 1) / ksplit, smem, dst, false);
-      if (!finish_tile(k, tile, m0, n0, out, ksplit)) continue;
+                total * (z + 1) / ksplit, smem, dst, false, 0, (mirror && ksplit == 1) ? out : nullptr);
+      if (!finish_tile(k, tile, m0, n0, out, ksplit, mirror)) continue;
       __threadfence();
       __syncthreads();
       if (threadIdx.x == 0) atomicAdd(done_bwd + k * (kSStore + 1) + level, 1);
@@ -431,6 +462,8 @@ struct DfGroup {
   int n_slices, accumulate;
   int c_mat, need_ver;  // the update applies to version need_ver of the C tile and publishes need_ver + 1
   int partial_off, n_slabs;
+  int mirror, pad;      // mirror: C is symmetric and only this (upper) tile is computed -- the reduction also writes
+                        // the transposed tile and publishes ITS versions (word s = column strip s of the mirrored tile)
 };
 struct alignas(16) DfItem {  // everything a CTA needs comes with ONE dependent load after the queue ticket
   const double* A;
@@ -535,7 +568,8 @@ chain_dataflow_kernel(const DfItem* __restrict__ items, int n_items, int n_group
       const bool direct = (g.n_slices == 1) && !g.accumulate;
       const int c0 = it.k0 / BK;
       if (direct) {
-        gemm_tile([&](int) { return t0; }, Sp, g.m0, g.n0, c0, c0 + it.n_chunks, smem, g.C, false);
+        gemm_tile([&](int) { return t0; }, Sp, g.m0, g.n0, c0, c0 + it.n_chunks, smem, g.C, false, 0,
+                  g.mirror ? g.C : nullptr);
         tick(2);
         if (threadIdx.x == 0) next = atomicAdd(queue, 1);
         if (g.c_mat >= 0) {
@@ -543,6 +577,8 @@ chain_dataflow_kernel(const DfItem* __restrict__ items, int n_items, int n_group
           __syncthreads();
           if (threadIdx.x < kDfSlabs)
             *reinterpret_cast<volatile int*>(ver + (g.c_mat * tiles + ti * tiles_n + tj) * kDfSlabs + threadIdx.x) = g.need_ver + 1;
+          else if (g.mirror && threadIdx.x >= 32 && threadIdx.x < 32 + kDfSlabs)
+            *reinterpret_cast<volatile int*>(ver + (g.c_mat * tiles + tj * tiles_n + ti) * kDfSlabs + (threadIdx.x - 32)) = g.need_ver + 1;
           tick(6);
         }
       } else {
@@ -605,6 +641,11 @@ chain_dataflow_kernel(const DfItem* __restrict__ items, int n_items, int n_group
           if (on[q]) {
             const int r = off[q] / BT, c2 = off[q] - r * BT;
             *reinterpret_cast<double2*>(g.C + (size_t)(g.m0 + r) * Sp + g.n0 + c2) = v[q];
+            if (g.mirror) {  // 16 rows x 80 columns -> 80 rows x 16 columns of the transposed tile
+              double* m = g.C + (size_t)(g.n0 + c2) * Sp + g.m0 + r;
+              m[0] = v[q].x;
+              m[Sp] = v[q].y;
+            }
           }
       }
     }
@@ -612,7 +653,11 @@ chain_dataflow_kernel(const DfItem* __restrict__ items, int n_items, int n_group
     if (threadIdx.x == 0) next = atomicAdd(queue, 1);
     __threadfence();  // every thread publishes its part of the slab before the version moves
     __syncthreads();
-    if (threadIdx.x == 0 && g.c_mat >= 0) *reinterpret_cast<volatile int*>(my_ver) = g.need_ver + 1;
+    if (threadIdx.x == 0 && g.c_mat >= 0) {
+      *reinterpret_cast<volatile int*>(my_ver) = g.need_ver + 1;
+      if (g.mirror)
+        *reinterpret_cast<volatile int*>(ver + (g.c_mat * tiles + tj * tiles_n + ti) * kDfSlabs + it.slice) = g.need_ver + 1;
+    }
     tick(6);
   }
 }
@@ -1029,7 +1074,11 @@ __global__ void __launch_bounds__(NT, 2)
 taylor_fused_smem_kernel(const double* __restrict__ powers, size_t n_p, int S, int Sp, int K,
                     const double* __restrict__ w, const int* __restrict__ s_arr,
                     const int* __restrict__ deg_arr, const double* __restrict__ C, double* __restrict__ X0,
-                    double* __restrict__ Pbar, double* __restrict__ loss_partial_fused) {
+                    double* __restrict__ Pbar, double* __restrict__ loss_partial_fused, int sym) {
+  // sym != 0 (symmetric form, build_B_sym_kernel): every matrix is symmetric, so the pass visits the elements
+  // with row <= col only -- the upper triangle folded into Sp/2 rows of Sp+1 elements (row f followed by row
+  // Sp-1-f), consecutive threads on consecutive columns -- stores every result at (row, col) and (col, row), and
+  // counts an off-diagonal element's loss term twice.
   constexpr int LPE = 1, NP = kDeg;
   extern __shared__ double sw[];  // [K][m+1] weights, then int lists
   __shared__ double red[NT / 32];
@@ -1049,14 +1098,33 @@ taylor_fused_smem_kernel(const double* __restrict__ powers, size_t n_p, int S, i
   }
   __syncthreads();
   // persistent: the weight table and the lists are staged once per CTA, the CTA walks over chunks of elements
-  const size_t n_chunks = (n_p * LPE + blockDim.x - 1) / blockDim.x;
-  double part = 0.0;
+  const size_t n_visit = sym ? (size_t)(Sp / 2) * (Sp + 1) : n_p;
+  const size_t n_chunks = (n_visit * LPE + blockDim.x - 1) / blockDim.x;
+  double part_total = 0.0;
   for (size_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     const int h = threadIdx.x & (LPE - 1);
-    const size_t e = (chunk * (size_t)blockDim.x + threadIdx.x) / LPE;
-    const bool in_range = e < n_p;
-    const size_t ee = in_range ? e : 0;
-    const int row = (int)(ee / Sp), col = (int)(ee - (size_t)row * Sp);
+    const size_t v_idx = (chunk * (size_t)blockDim.x + threadIdx.x) / LPE;
+    const bool in_range = v_idx < n_visit;
+    int row, col;
+    if (sym) {
+      const size_t vv = in_range ? v_idx : 0;
+      const int f = (int)(vv / (Sp + 1)), q = (int)(vv - (size_t)f * (Sp + 1));
+      if (q < Sp - f) {
+        row = f;
+        col = f + q;
+      } else {
+        row = Sp - 1 - f;
+        col = row + (q - (Sp - f));
+      }
+    } else {
+      const size_t vv = in_range ? v_idx : 0;
+      row = (int)(vv / Sp);
+      col = (int)(vv - (size_t)row * Sp);
+    }
+    const size_t e = (size_t)row * Sp + col, ee = e;
+    const bool mirror = sym && in_range && row != col;
+    const size_t et = (size_t)col * Sp + row;
+    double part = 0.0;  // this element's loss terms
     const bool real = in_range && row < S && col < S;
     const double diag = (row == col && row < S) ? 1.0 : 0.0;
     double* ring = reinterpret_cast<double*>(sdeg + K + (K & 1));  // [kTaylorStagesS][NT], 8-byte aligned
@@ -1121,13 +1189,22 @@ taylor_fused_smem_kernel(const double* __restrict__ powers, size_t n_p, int S, i
       for (int j = 0; j < NP; ++j) v = fma(wk[j + 1], spw[j * NT], v);
 #pragma unroll
       for (int o = 1; o < LPE; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (in_range && h == 0) X0[(size_t)k * n_p + e] = v;
+      if (in_range && h == 0) {
+        X0[(size_t)k * n_p + e] = v;
+        if (mirror) X0[(size_t)k * n_p + et] = v;
+      }
     }
     if (in_range) {
 #pragma unroll
       for (int i = 0; i < NP; ++i) Pbar[(size_t)(i * LPE + h) * n_p + e] = acc[i];
+      if (mirror) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) Pbar[(size_t)(i * LPE + h) * n_p + et] = acc[i];
+      }
     }
+    part_total += mirror ? 2.0 * part : part;
   }
+  double part = part_total;
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
   __syncthreads();
@@ -1295,6 +1372,8 @@ struct LargeUpdateArgs {
   double* grad_theta;  // [S + S(S-1)/2]
   double* dpi;         // [S]
   double* pibuf;       // [S] softmax(pi logits) of the CURRENT theta, written by the rows kernel
+  double* shat;        // [S][S] mask_ij softplus(u_ij): the symmetric form of Q (off-diagonal), written with Q
+  double* sr;          // [S] sqrt(pi) of the Q just built
   double lr_pi, lr_upper, beta1, beta2, eps;
   int do_adam, loss_normalization, best_mode;
 };
@@ -1331,6 +1410,68 @@ __device__ __forceinline__ void softmax_sqrt(const double* theta, int S, double*
 __device__ __forceinline__ double upper_param(const double* theta, int S, int i, int j) {
   const int lo = i < j ? i : j, hi = i < j ? j : i;
   return theta[S + cherry::triu_index(lo, hi, S)];
+}
+
+// ---- the symmetric form of a reversible model (training path only; fit_large_impl says when) ----
+// Q_ij = mask_ij softplus(u_ij) sqrt(pi_j / pi_i) is similar to the SYMMETRIC matrix
+//   Sh = R Q R^-1,  R = diag(sqrt(pi)):  Sh_ij = mask_ij softplus(u_ij),  Sh_ii = Q_ii,
+// so expm(t Q) = R^-1 expm(t Sh) R, every power of Bh = Sh + mu I is symmetric, and for SYMMETRIC counts
+// sum_ij C_ij log P_ij = sum_ij C_ij log E_ij with E = expm(t Sh) (the factors sqrt(pi_j / pi_i) cancel in
+// pairs).  The whole evaluation then runs on symmetric matrices -- the forward chain and the squarings compute
+// the upper tiles only -- and the result A = dL/dSh (symmetric) maps back as dL/dQ_ij = A_ij sqrt(pi_i / pi_j),
+// which is the exact derivative with respect to an arbitrary perturbation of Q (R is a constant of the
+// identity above).  Entry by entry (Bh^k)_ij = (B^k)_ij sqrt(pi_i / pi_j): the truncation analysis of the
+// Taylor series (relative, entrywise, non-negative terms) carries over unchanged, so the scaling decisions
+// keep using the row sums of B = Q + mu I.
+// large_build_Q_kernel leaves Sh (off-diagonal) and sqrt(pi) next to every Q it builds, so this is build_B_kernel
+// with one more operand.  grid = Sp rows / 8.
+__global__ void build_B_sym_kernel(const double* __restrict__ Q, const double* __restrict__ shat, int S, int Sp,
+                                   double* __restrict__ B, LargeScalars* __restrict__ sc) {
+  __shared__ double red[EW_THREADS / 32];
+  double mx = 0.0;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) mx = fmax(mx, fabs(Q[(size_t)i * S + i]));
+  const double mu = block_max_256(mx, red);
+  if (blockIdx.x == 0 && threadIdx.x == 0) sc->mu = mu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * (EW_THREADS / 32) + warp; row < Sp; row += gridDim.x * (EW_THREADS / 32)) {
+    double rs = 0.0;
+    for (int j = lane; j < Sp; j += 32) {
+      double v = 0.0;
+      if (row < S && j < S) {
+        const double q = Q[(size_t)row * S + j];
+        rs += fabs(q + (row == j ? mu : 0.0));  // row sums of B = Q + mu I, as in build_B_kernel
+        v = (row == j) ? q + mu : shat[(size_t)row * S + j];
+      }
+      B[(size_t)row * Sp + j] = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    if (lane == 0) atomicMax(&sc->norm_bits, (unsigned long long)__double_as_longlong(rs));
+  }
+}
+
+// dL/dQ_ij = A_ij sqrt(pi_i / pi_j), A = the (symmetric up to rounding) adjoint of Bh, padded [Sp][Sp]
+__global__ void unpad_sym_kernel(const double* __restrict__ src, const double* __restrict__ sr, int S, int Sp,
+                                 double* __restrict__ dst) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= S * S) return;
+  const int i = e / S, j = e - i * S;
+  dst[e] = 0.5 * (src[(size_t)i * Sp + j] + src[(size_t)j * Sp + i]) * (sr[i] / sr[j]);
+}
+
+// flag[0] |= 1 unless mask and every count matrix are exactly symmetric
+__global__ void symmetric_inputs_kernel(const double* __restrict__ mask, const double* __restrict__ C, int S, int K,
+                                        int* __restrict__ flag) {
+  const size_t n = (size_t)S * S;
+  bool bad = false;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / S), j = (int)(e - (size_t)i * S);
+    if (j <= i) continue;
+    const size_t et = (size_t)j * S + i;
+    if (mask[e] != mask[et]) bad = true;
+    for (int k = 0; k < K; ++k)
+      if (C[(size_t)k * n + e] != C[(size_t)k * n + et]) bad = true;
+  }
+  if (bad) atomicOr(flag, 1);
 }
 
 // grid = S (one CTA per state i): bookkeeping copies of row i of the current Q, dL/dr_i, and the
@@ -1425,12 +1566,17 @@ __global__ void __launch_bounds__(EW_THREADS) large_build_Q_kernel(LargeUpdateAr
   for (int j = threadIdx.x; j < S; j += blockDim.x) {
     if (j == i) continue;
     const double u = upper_param(a.theta, S, i, j);
-    const double v = a.mask[(size_t)i * S + j] * cherry::softplus_d(u) * sr[j] / ri;
+    const double sh = a.mask[(size_t)i * S + j] * cherry::softplus_d(u);
+    const double v = sh * sr[j] / ri;
     a.Q[(size_t)i * S + j] = v;
+    a.shat[(size_t)i * S + j] = sh;
     rs += v;
   }
   rs = block_sum_256(rs, red);
-  if (threadIdx.x == 0) a.Q[(size_t)i * S + i] = -rs;
+  if (threadIdx.x == 0) {
+    a.Q[(size_t)i * S + i] = -rs;
+    a.sr[i] = ri;
+  }
   if (mode == 1 && i == 0 && threadIdx.x == 0) {
     const int epoch = a.epoch_counter[0];
     const double scale = a.loss_normalization ? 1.0 / a.sumC[0] : 1.0;
@@ -1459,6 +1605,9 @@ struct Plan {
   std::vector<GemmTerm> terms;
   std::vector<Group> pow_fwd, sq_fwd, sq_bwd, pow_bwd;
   DfList df_fwd, df_bwd;  // the two power chains as dataflow item lists
+  DfList df_fwd_sym;      // forward chain of a symmetric B: upper tiles only, mirrored (shares df_fwd's state words)
+  size_t off_sr = 0;      // [S] sqrt(pi) of the current parameters (symmetric mode)
+  size_t off_shat = 0;    // [S][S] mask_ij softplus(u_ij) of the current parameters
 };
 
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
@@ -1511,6 +1660,10 @@ void make_plan(Plan& p, int S, int K, char* base) {
     p.df_fwd.off_state = carve(sizeof(int) * df_state_ints(kDeg, p.tiles, (int)max_groups));
     p.df_bwd.off_items = carve(sizeof(DfItem) * max_items);
     p.df_bwd.off_state = carve(sizeof(int) * df_state_ints(kDeg, p.tiles, (int)max_groups));
+    p.df_fwd_sym.off_items = carve(sizeof(DfItem) * max_items);
+    p.df_fwd_sym.off_state = p.df_fwd.off_state;  // one of the two forward lists runs per evaluation
+    p.off_sr = carve(sizeof(double) * S);
+    p.off_shat = carve(sizeof(double) * S * S);
   }
   p.off_prof = carve(sizeof(long long) * 8 * 2 * 1024);  // phase profile of the two chain launches (<= 1024 CTAs)
   p.off_P = carve(mat * kDeg);
@@ -1542,12 +1695,13 @@ void make_plan(Plan& p, int S, int K, char* base) {
     static const int reduce_lag = getenv("CHERRY_FIT_REDUCE_LAG") ? atoi(getenv("CHERRY_FIT_REDUCE_LAG")) : kDfReduceLag;  // A/B switch
     // one output matrix update C (+)= sum of terms, for every tile; slices of 80 (fine) or whole K per term (coarse)
     auto add_update = [&](DfList& L, double* C, int c_mat, int need_ver, int accumulate,
-                          const std::vector<TermSpec>& terms, int per_term) {
+                          const std::vector<TermSpec>& terms, int per_term, bool upper_only = false) {
       for (int ti = 0; ti < tn; ++ti)
-        for (int tj = 0; tj < tn; ++tj) {
+        for (int tj = upper_only ? ti : 0; tj < tn; ++tj) {
           DfGroup g;
           g.C = C; g.m0 = ti * BT; g.n0 = tj * BT; g.accumulate = accumulate; g.c_mat = c_mat; g.need_ver = need_ver;
           g.partial_off = L.partial_tiles; g.n_slabs = kDfSlabs;
+          g.mirror = (upper_only && ti != tj) ? 1 : 0; g.pad = 0;
           g.n_slices = (int)terms.size() * per_term;
           const int gi = (int)L.groups.size();
           int slice = 0;
@@ -1580,10 +1734,13 @@ void make_plan(Plan& p, int S, int K, char* base) {
         if (term_tiles * n >= chain_target) return n;
       return 5;
     };
-    // forward: P_{b+r} = P_b P_r, r = 1..min(b, m-b); matrix id of P_j is j-1, version 1 once written (P_1: given)
-    {
-      DfList& L = p.df_fwd;
+    // forward: P_{b+r} = P_b P_r, r = 1..min(b, m-b); matrix id of P_j is j-1, version 1 once written (P_1: given).
+    // Second list for a SYMMETRIC B (reversible Q in the basis diag(sqrt(pi)), see build_B_sym_kernel): every
+    // power is symmetric, so only the tiles on and above the diagonal are computed and the reductions mirror them.
+    for (int sym = 0; sym < 2; ++sym) {
+      DfList& L = sym ? p.df_fwd_sym : p.df_fwd;
       L.items.clear(); L.groups.clear(); L.pending.clear(); L.partial_tiles = 0; L.n_mats = kDeg;
+      const int tile_groups = sym ? tn * (tn + 1) / 2 : p.tiles;
       std::vector<int> ver(kDeg + 1, 0);
       for (int b = 1; b < kDeg; b *= 2) {
         // the squaring P_2b first: it is the critical path of the next level
@@ -1591,9 +1748,10 @@ void make_plan(Plan& p, int S, int K, char* base) {
         if (b + b <= kDeg) rs.push_back(b);
         for (int r = 1; r <= b && b + r <= kDeg; ++r)
           if (r != b) rs.push_back(r);
-        const int per_term = slices_for((int)rs.size() * p.tiles);
+        const int per_term = slices_for((int)rs.size() * tile_groups);
         for (int r : rs)
-          add_update(L, Pj(b + r), b + r - 1, 0, 0, {TermSpec{Pj(b), Pj(r), 0, 0, b - 1, ver[b], r - 1, ver[r]}}, per_term);
+          add_update(L, Pj(b + r), b + r - 1, 0, 0, {TermSpec{Pj(b), Pj(r), 0, 0, b - 1, ver[b], r - 1, ver[r]}}, per_term,
+                     sym != 0);
         emit_reduce(L, -1);  // the next level reads this level's results
         for (int r : rs) ver[b + r] = 1;
       }
@@ -1634,7 +1792,7 @@ void make_plan(Plan& p, int S, int K, char* base) {
   p.n_partial = kSqPartialSlots;
   {
     const size_t tile_doubles = (size_t)BT * BT;
-    const size_t need = (size_t)std::max(p.df_fwd.partial_tiles, p.df_bwd.partial_tiles) * tile_doubles;
+    const size_t need = (size_t)std::max(std::max(p.df_fwd.partial_tiles, p.df_fwd_sym.partial_tiles), p.df_bwd.partial_tiles) * tile_doubles;
     size_t doubles = p.n_p * p.n_partial;
     if (need > doubles) doubles = need;
     p.off_partial = carve(doubles * sizeof(double));
@@ -1795,6 +1953,8 @@ void fill_update_args(LargeUpdateArgs& u, const cherry_fit_args& a, const Plan& 
   u.grad_theta = reinterpret_cast<double*>(base + p.off_grad_theta);
   u.dpi = reinterpret_cast<double*>(base + p.off_dpi);
   u.pibuf = reinterpret_cast<double*>(base + p.off_pibuf);
+  u.shat = reinterpret_cast<double*>(base + p.off_shat);
+  u.sr = reinterpret_cast<double*>(base + p.off_sr);
   u.lr_pi = a.lr_pi; u.lr_upper = a.lr_upper; u.beta1 = a.beta1; u.beta2 = a.beta2; u.eps = a.eps;
   u.do_adam = a.do_adam; u.loss_normalization = a.loss_normalization; u.best_mode = a.best_mode;
 }
@@ -1819,6 +1979,23 @@ int fit_large_workspace_bytes(int S, int K, int n_problems, size_t* bytes) {
   return 0;
 }
 
+// Which workspaces were prepared for a model whose evaluation may run in the symmetric form (mask and counts
+// exactly symmetric, parameters given): decided once per fit by fit_large_prepare, read by the training entry
+// points.  CHERRY_FIT_SYMMETRIC=0 is the A/B switch.
+static std::mutex g_sym_mutex;
+static std::unordered_map<const void*, int> g_sym_mode;
+static int symmetric_mode_of(const cherry_fit_args& a) {
+  if (!a.theta || !a.mask) return 0;
+  std::lock_guard<std::mutex> lock(g_sym_mutex);
+  auto it = g_sym_mode.find(a.workspace);
+  return it == g_sym_mode.end() ? 0 : it->second;
+}
+
+int fit_large_symmetric_form(const cherry_fit_args& a) {
+  static const bool legacy_schedule = getenv("CHERRY_FIT_LEVEL_LAUNCH") != nullptr || getenv("CHERRY_FIT_LEVEL_SYNC") != nullptr;
+  return (!legacy_schedule && symmetric_mode_of(a) == 1) ? 1 : 0;
+}
+
 // Uploads the GEMM task lists (absolute pointers into this workspace).  Synchronous.
 int fit_large_prepare(const cherry_fit_args& a, cudaStream_t stream) {
   int rc = check_large(a);
@@ -1828,17 +2005,32 @@ int fit_large_prepare(const cherry_fit_args& a, cudaStream_t stream) {
   CHERRY_CUDA(cudaStreamSynchronize(stream));
   CHERRY_CUDA(cudaMemcpy(base + p.off_tasks, p.tasks.data(), p.tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice));
   CHERRY_CUDA(cudaMemcpy(base + p.off_terms, p.terms.data(), p.terms.size() * sizeof(GemmTerm), cudaMemcpyHostToDevice));
-  for (const DfList* L : {&p.df_fwd, &p.df_bwd}) {
+  for (const DfList* L : {&p.df_fwd, &p.df_bwd, &p.df_fwd_sym}) {
     CHERRY_CUDA(cudaMemcpy(base + L->off_items, L->items.data(), L->items.size() * sizeof(DfItem), cudaMemcpyHostToDevice));
   }
   CHERRY_CUDA(cudaMemset(base + p.off_scalars, 0, sizeof(LargeScalars)));
   CHERRY_CUDA(cudaMemset(base + p.off_arrive, 0, sizeof(int) * 64 * (size_t)p.tiles));
+  {
+    const bool sym_allowed = !(getenv("CHERRY_FIT_SYMMETRIC") && atoi(getenv("CHERRY_FIT_SYMMETRIC")) == 0);  // read per fit: tests toggle it
+    int mode = 0;
+    if (sym_allowed && a.theta && a.mask && a.C) {
+      int* flag = reinterpret_cast<int*>(base + p.off_arrive);  // zeroed above, zeroed again below
+      symmetric_inputs_kernel<<<256, 256>>>(a.mask, a.C, a.S, a.K, flag);
+      CHERRY_LAUNCH_CHECK("symmetric_inputs_kernel");
+      int bad = 1;
+      CHERRY_CUDA(cudaMemcpy(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost));
+      CHERRY_CUDA(cudaMemset(flag, 0, sizeof(int)));
+      mode = bad ? 0 : 1;
+    }
+    std::lock_guard<std::mutex> lock(g_sym_mutex);
+    g_sym_mode[a.workspace] = mode;
+  }
   // chain slots are read as "Xbar" for inactive levels never; but slot 1 of every bucket is
   // always written by loss_grad (s = 0) or the backward chain, so no clearing is needed.
   return 0;
 }
 
-static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double* P_out);
+static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double* P_out, bool allow_sym = false);
 
 // Optional phase timeline (debug / profiling): when g_timeline is non-null, fit_large_impl records
 // an event after every phase of one evaluation.
@@ -1855,7 +2047,9 @@ static void mark(const char* name, cudaStream_t stream) {
   g_timeline->name[g_timeline->n++] = name;
 }
 
-int fit_large_expm(const cherry_fit_args& a, cudaStream_t stream) { return fit_large_impl(a, stream, nullptr); }
+int fit_large_expm(const cherry_fit_args& a, cudaStream_t stream, bool training) {
+  return fit_large_impl(a, stream, nullptr, training);
+}
 
 // expm(t_k Q) for every bucket into P_out [K][S][S]; prepares the workspace itself (synchronous).
 int fit_large_forward_only(const cherry_fit_args& a, double* P_out, cudaStream_t stream) {
@@ -1865,12 +2059,18 @@ int fit_large_forward_only(const cherry_fit_args& a, double* P_out, cudaStream_t
   return fit_large_impl(a, stream, P_out);
 }
 
-static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double* P_out) {
+static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double* P_out, bool allow_sym) {
   int rc = check_large(a);
   if (rc) return rc;
   if ((rc = ensure_gemm_attr())) return rc;
   char* base = reinterpret_cast<char*>(a.workspace);
   const Plan& p = get_plan(a.S, a.K, base);  // host-side tables; the device copies were uploaded by prepare
+  // symmetric form (see build_B_sym_kernel): only where Q is known to be the reversible model of a.theta -- the
+  // training entry points -- and fit_large_prepare found mask and counts symmetric
+  static const bool legacy_schedule = getenv("CHERRY_FIT_LEVEL_LAUNCH") != nullptr || getenv("CHERRY_FIT_LEVEL_SYNC") != nullptr;
+  const bool sym = allow_sym && P_out == nullptr && !legacy_schedule && symmetric_mode_of(a) == 1;
+  const int tn = p.Sp / BT, sq_tiles = sym ? tn * (tn + 1) / 2 : p.tiles;
+  double* sr = reinterpret_cast<double*>(base + p.off_sr);
   LargeScalars* sc = reinterpret_cast<LargeScalars*>(base + p.off_scalars);
   int* s_arr = reinterpret_cast<int*>(base + p.off_s);
   double* tau = reinterpret_cast<double*>(base + p.off_tau);
@@ -1885,7 +2085,11 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   if (wsmem > 200 * 1024) return fail(CHERRY_ELIMIT, "fit_large: K=%d too large for the weight table", a.K);
 
   mark("start", stream);
-  build_B_kernel<<<(p.Sp + 7) / 8, EW_THREADS, 0, stream>>>(a.Q, a.S, p.Sp, P, sc);
+  if (sym)
+    build_B_sym_kernel<<<(p.Sp + 7) / 8, EW_THREADS, 0, stream>>>(a.Q, reinterpret_cast<const double*>(base + p.off_shat), a.S,
+                                                                 p.Sp, P, sc);
+  else
+    build_B_kernel<<<(p.Sp + 7) / 8, EW_THREADS, 0, stream>>>(a.Q, a.S, p.Sp, P, sc);
   CHERRY_LAUNCH_CHECK("build_B_kernel");
   SqSchedule* sched = reinterpret_cast<SqSchedule*>(base + p.off_sched);
   int* df_state_fwd = reinterpret_cast<int*>(base + p.df_fwd.off_state);
@@ -1894,7 +2098,7 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   static const int ctas_per_sm = getenv("CHERRY_FIT_CTAS_PER_SM") ? atoi(getenv("CHERRY_FIT_CTAS_PER_SM")) : 3;  // 2-stage pipeline: 51 KB and ~20 K registers per CTA
   static const bool full_degree = getenv("CHERRY_FIT_FULL_DEGREE") != nullptr;  // A/B switch: round-1 Taylor pass
   static const int sq_ksplit_max = getenv("CHERRY_FIT_SQ_KSPLIT") ? atoi(getenv("CHERRY_FIT_SQ_KSPLIT")) : 2;  // A/B switch (graph-replayed epochs: 1 -> 1.04 ms, 2 -> 0.94, 5 -> 0.96)
-  coef_kernel<<<1, 256, 0, stream>>>(a.t, a.K, sc, s_arr, deg_arr, w, tau, a.status_flag, sched, p.tiles,
+  coef_kernel<<<1, 256, 0, stream>>>(a.t, a.K, sc, s_arr, deg_arr, w, tau, a.status_flag, sched, sq_tiles,
                                      (KGROUPS == 1 ? ctas_per_sm : 1) * sm_count(), df_state_fwd,
                                      (int)df_state_ints(p.df_fwd.n_mats, p.tiles, (int)p.df_fwd.groups.size()),
                                      df_state_bwd,
@@ -1919,7 +2123,7 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   if (level_launch) {
     for (const Group& g : p.pow_fwd)
       if ((rc = launch_group(p, g, base, stream))) return rc;
-  } else if ((rc = launch_chain(p.df_fwd, df_state_fwd, "chain_dataflow_kernel<fwd>"))) {
+  } else if ((rc = launch_chain(sym ? p.df_fwd_sym : p.df_fwd, df_state_fwd, "chain_dataflow_kernel<fwd>"))) {
     return rc;
   }
   mark("powers_fwd", stream);
@@ -1961,11 +2165,12 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
       // kTaylorThreads per CTA, two CTAs per SM (128 registers: the powers live in shared memory)
       constexpr int NT = kTaylorThreads;
       const size_t ssmem = wsmem + 3 * sizeof(int) * a.K + 8 + sizeof(double) * (kTaylorStagesS + kDeg) * NT;
-      int grid2 = (int)((p.n_p + NT - 1) / NT);
+      const size_t n_visit = sym ? (size_t)(p.Sp / 2) * (p.Sp + 1) : p.n_p;  // symmetric form: the upper triangle
+      int grid2 = (int)((n_visit + NT - 1) / NT);
       if (grid2 > 2 * sm_count()) grid2 = 2 * sm_count();
       fused_blocks = grid2;
       taylor_fused_smem_kernel<1, NT><<<grid2, NT, ssmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, s_arr, deg_arr, a.C, X0,
-                                                                    Pbar, fused_partial);
+                                                                    Pbar, fused_partial, sym ? 1 : 0);
     } else if (lpe == 2) CHERRY_TAYLOR_LAUNCH(2, 1);
     else if (tu == 4) CHERRY_TAYLOR_LAUNCH(1, 4);
     else if (tu == 2) CHERRY_TAYLOR_LAUNCH(1, 2);
@@ -1984,7 +2189,7 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   } else {
     squaring_dataflow_kernel<false><<<persistent_grid, GEMM_THREADS, gemm_smem, stream>>>(
         sched, s_arr, a.K, p.Sp, X0, chain, p.slots_per_bucket, reinterpret_cast<double*>(base + p.off_partial),
-        a.status_flag);
+        a.status_flag, sym ? 1 : 0);
     CHERRY_LAUNCH_CHECK("squaring_dataflow_kernel<fwd>");
   }
   mark("squarings_fwd", stream);
@@ -2008,7 +2213,7 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   } else {
     squaring_dataflow_kernel<true><<<persistent_grid, GEMM_THREADS, gemm_smem, stream>>>(
         sched, s_arr, a.K, p.Sp, X0, chain, p.slots_per_bucket, reinterpret_cast<double*>(base + p.off_partial),
-        a.status_flag);
+        a.status_flag, sym ? 1 : 0);
     CHERRY_LAUNCH_CHECK("squaring_dataflow_kernel<bwd>");
   }
   mark("squarings_bwd", stream);
@@ -2023,7 +2228,10 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
     return rc;
   }
   mark("powers_bwd", stream);
-  unpad_kernel<<<(a.S * a.S + 255) / 256, 256, 0, stream>>>(Pbar, a.S, p.Sp, a.dQ_part);
+  if (sym)
+    unpad_sym_kernel<<<(a.S * a.S + 255) / 256, 256, 0, stream>>>(Pbar, sr, a.S, p.Sp, a.dQ_part);
+  else
+    unpad_kernel<<<(a.S * a.S + 255) / 256, 256, 0, stream>>>(Pbar, a.S, p.Sp, a.dQ_part);
   CHERRY_LAUNCH_CHECK("unpad_kernel");
   mark("unpad", stream);
   return 0;
@@ -2033,13 +2241,14 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
 int fit_large_timeline(const cherry_fit_args& a, cudaStream_t stream) {
   Timeline tl;
   for (int i = 0; i < Timeline::kMax; ++i) CHERRY_CUDA(cudaEventCreate(&tl.ev[i]));
-  int rc = fit_large_impl(a, stream, nullptr);  // warm
+  // the timeline is of the training configuration: symmetric form where the fit would use it
+  int rc = fit_large_impl(a, stream, nullptr, true);  // warm
   if (rc) return rc;
   const Plan& pl = get_plan(a.S, a.K, nullptr);
   char* wbase = reinterpret_cast<char*>(a.workspace);
   CHERRY_CUDA(cudaMemsetAsync(wbase + pl.off_prof, 0, sizeof(long long) * 8 * 2 * 1024, stream));
   g_timeline = &tl;
-  rc = fit_large_impl(a, stream, nullptr);
+  rc = fit_large_impl(a, stream, nullptr, true);
   g_timeline = nullptr;
   if (rc) return rc;
   CHERRY_CUDA(cudaStreamSynchronize(stream));

@@ -245,6 +245,12 @@ class FitEngine:
                 _lib.check(self.lib.cherry_fit_epoch_update(a, packed, st), "cherry_fit_epoch_update")
         self.epochs_done += n
 
+    @property
+    def symmetric_form(self) -> bool:
+        """True when the epochs of this (large-S) fit run on the symmetric form of the reversible model
+        (include/cherryml_b200.h cherry_fit_symmetric_form)."""
+        return bool(self.lib.cherry_fit_symmetric_form(ctypes.byref(self.args)))
+
     def loss_and_grad(self):
         """(loss [P], dL/dQ [P,S,S]) at the current Q, normalised like the training loss."""
         with torch.cuda.device(self.device):

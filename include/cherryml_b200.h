@@ -335,6 +335,14 @@ size_t cherry_gemm_desc_bytes(int batch);
  * this to turn kernel time into executed FLOP/s.  Synchronises the device. */
 int cherry_fit_schedule(const cherry_fit_args* args, int* squarings_out, double* mu_out, int* degree_out);
 
+/* Large-S path only: 1 if the epochs of this fit (cherry_fit_run / cherry_fit_epoch_local after cherry_fit_init)
+ * run in the symmetric form, 0 otherwise.  The reference's model (rate.py: pande_reversible) is
+ * Q_ij = mask_ij softplus(u_ij) sqrt(pi_j / pi_i), similar to the symmetric matrix mask_ij softplus(u_ij) by
+ * diag(sqrt(pi)); when mask and every count matrix are exactly symmetric (cherry counts are) the evaluation works on
+ * symmetric matrices throughout and computes only the tiles on and above the diagonal of the forward products.
+ * Losses and gradients are the same quantities (rounding-level differences); CHERRY_FIT_SYMMETRIC=0 turns it off. */
+int cherry_fit_symmetric_form(const cherry_fit_args* args);
+
 /* ------------------------------------------------------------------- FastCherries */
 
 /* One MSA family for the FastCherries kernels: ALL sequences of the MSA in file order, one

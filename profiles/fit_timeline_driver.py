@@ -45,4 +45,4 @@ e0.record()
 eng2.run(args.epochs - 64)
 e1.record()
 torch.cuda.synchronize()
-print("graph-replayed: %.4f ms per epoch" % (e0.elapsed_time(e1) / (args.epochs - 64)))
+print("graph-replayed: %.4f ms per epoch (symmetric form: %s)" % (e0.elapsed_time(e1) / (args.epochs - 64), eng2.symmetric_form))

@@ -218,6 +218,53 @@ def test_large_fit_small_padded_case_vs_oracle():
     assert np.max(np.abs(res["Q_best"] - ref["Q_best"])) < REL_FP64 * np.max(np.abs(ref["Q_best"]))
 
 
+@pytest.mark.parametrize("S,K,masked", [(36, 8, False), (100, 6, True), (400, 5, True)])
+def test_symmetric_form_equals_the_general_evaluation(S, K, masked, monkeypatch):
+    """Symmetric counts + symmetric mask: the epochs run on R Q R^-1 (symmetric) and compute the upper
+    tiles only.  Same losses and the same iterates as the general evaluation (CHERRY_FIT_SYMMETRIC=0) to
+    rounding -- 12 epochs of Adam amplify a 1e-16 difference to ~1e-12 -- and as the fp64 oracle; the
+    times span no squaring ... many squarings.  Unsymmetric counts must fall back to the general form."""
+    rng = np.random.default_rng(S + 1)
+    tmax = 120.0 / S  # row sums of Q grow with S: up to ~6 squarings
+    times = np.exp(rng.uniform(np.log(1e-3 * tmax), np.log(tmax), K))
+    times[0], times[-1] = 1e-3 * tmax, tmax
+    half = rng.integers(0, 40, size=(K, S, S)).astype(np.float64)
+    half[rng.random(half.shape) < 0.4] = 0.0
+    counts = half + half.transpose(0, 2, 1)
+    mask = None
+    if masked:
+        m = (rng.random((S, S)) < 0.6).astype(np.float64)
+        mask = np.maximum(m, m.T)
+        np.fill_diagonal(mask, 1.0)
+        counts = counts * mask[None]  # no transitions where the model allows none in one step... and beyond
+        counts += (rng.random((S, S)) < 0.05)[None] * 1.0
+        counts = 0.5 * (counts + counts.transpose(0, 2, 1))
+    theta0 = random_theta(S)
+    n = 12
+
+    def run(sym):
+        if sym:
+            monkeypatch.delenv("CHERRY_FIT_SYMMETRIC", raising=False)
+        else:
+            monkeypatch.setenv("CHERRY_FIT_SYMMETRIC", "0")
+        eng = FitEngine(times, counts, theta0.copy(), num_epochs=n, mask=mask)
+        assert eng.symmetric_form == sym
+        eng.run()
+        return eng.results()
+
+    a, b = run(True), run(False)
+    assert np.max(np.abs(a["loss"] - b["loss"]) / np.abs(b["loss"])) < 1e-11
+    for key in ("Q_best", "Q_last"):
+        assert np.max(np.abs(a[key] - b[key])) < 1e-9 * np.max(np.abs(b[key])), key
+    ref = fit_oracle(times, counts, mask, None, 0.1, n, dtype=torch.float64)
+    assert np.max(np.abs(a["loss"] - ref["loss"]) / np.abs(ref["loss"])) < REL_FP64
+    assert np.max(np.abs(a["Q_last"] - ref["Q_last"])) < REL_FP64 * np.max(np.abs(ref["Q_last"]))
+    # unsymmetric counts: general form
+    monkeypatch.delenv("CHERRY_FIT_SYMMETRIC", raising=False)
+    eng = FitEngine(times, half, theta0.copy(), num_epochs=1, mask=mask)
+    assert not eng.symmetric_form
+
+
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
 @pytest.mark.parametrize("n,batch,ksplit", [(80, 3, 1), (160, 2, 2), (400, 2, 1), (400, 1, 5)])
 def test_dmma_gemm_matches_cublas(ta, tb, n, batch, ksplit):
