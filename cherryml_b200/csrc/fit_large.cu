@@ -290,7 +290,7 @@ struct SqSchedule {
   int ks[kSStore];                     // split-K factor of the tiles of a level (few active buckets: more CTAs per tile)
   int item_off[kSStore + 1];           // prefix sums of the work items (active buckets x tiles x ks) per level
   int ksmax;                           // stride of a bucket's partial matrices
-  int pad[2];
+  int pad[2];                          // pad[0]: dynamic chunk counter of the fused Taylor pass
   // followed in memory by: int active[kSStore][K]; int done_fwd[K][kSStore]; int done_bwd[K][kSStore + 1];
   // int rank[K] (position of bucket k in level 0's list); int tile_arrive[K][tiles]
 };
@@ -805,6 +805,7 @@ __global__ void coef_kernel(const double* __restrict__ t, int K, LargeScalars* _
     sched->n_levels = n_levels;
     sched->queue[0] = 0;
     sched->queue[1] = 0;
+    sched->pad[0] = 0;  // chunk counter of the fused Taylor pass
     // split K level by level: about 2.5 waves of work items per level (one K=400 tile is 60-100 us on a
     // CTA: with 1.1 waves of them the second wave runs nearly empty), at most sq_ksplit_max ways and within
     // the partial buffer (one slot per (bucket of level 0, z))
@@ -1069,13 +1070,14 @@ taylor_fused_kernel(const double* __restrict__ powers, size_t n_p, int S, int Sp
   }
 }
 
-template <int UI, int NT>
+template <int UI, int NT, bool SYM>
 __global__ void __launch_bounds__(NT, 2)
 taylor_fused_smem_kernel(const double* __restrict__ powers, size_t n_p, int S, int Sp, int K,
                     const double* __restrict__ w, const int* __restrict__ s_arr,
                     const int* __restrict__ deg_arr, const double* __restrict__ C, double* __restrict__ X0,
-                    double* __restrict__ Pbar, double* __restrict__ loss_partial_fused, int sym) {
-  // sym != 0 (symmetric form, build_B_sym_kernel): every matrix is symmetric, so the pass visits the elements
+                    double* __restrict__ Pbar, double* __restrict__ loss_partial_fused, int* __restrict__ chunk_counter) {
+  constexpr bool sym = SYM;
+  // SYM (symmetric form, build_B_sym_kernel): every matrix is symmetric, so the pass visits the elements
   // with row <= col only -- the upper triangle folded into Sp/2 rows of Sp+1 elements (row f followed by row
   // Sp-1-f), consecutive threads on consecutive columns -- stores every result at (row, col) and (col, row), and
   // counts an off-diagonal element's loss term twice.
@@ -1101,7 +1103,11 @@ taylor_fused_smem_kernel(const double* __restrict__ powers, size_t n_p, int S, i
   const size_t n_visit = sym ? (size_t)(Sp / 2) * (Sp + 1) : n_p;
   const size_t n_chunks = (n_visit * LPE + blockDim.x - 1) / blockDim.x;
   double part_total = 0.0;
-  for (size_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+  __shared__ int s_chunk;
+  // the first chunk of a CTA is its block index, the others come from a counter (coef_kernel zeroes it every epoch):
+  // chunks differ in length (a warp skips a bucket in which none of its 32 counts is set), and the CTAs that
+  // finish first take what is left
+  for (size_t chunk = blockIdx.x; chunk < n_chunks;) {
     const int h = threadIdx.x & (LPE - 1);
     const size_t v_idx = (chunk * (size_t)blockDim.x + threadIdx.x) / LPE;
     const bool in_range = v_idx < n_visit;
@@ -1203,6 +1209,10 @@ taylor_fused_smem_kernel(const double* __restrict__ powers, size_t n_p, int S, i
       }
     }
     part_total += mirror ? 2.0 * part : part;
+    __syncthreads();
+    if (threadIdx.x == 0) s_chunk = (int)gridDim.x + atomicAdd(chunk_counter, 1);
+    __syncthreads();
+    chunk = (size_t)s_chunk;
   }
   double part = part_total;
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -2070,6 +2080,10 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   static const bool legacy_schedule = getenv("CHERRY_FIT_LEVEL_LAUNCH") != nullptr || getenv("CHERRY_FIT_LEVEL_SYNC") != nullptr;
   const bool sym = allow_sym && P_out == nullptr && !legacy_schedule && symmetric_mode_of(a) == 1;
   const int tn = p.Sp / BT, sq_tiles = sym ? tn * (tn + 1) / 2 : p.tiles;
+  // A/B switch (graph-replayed epochs, general form, 25 tiles per product: 1 -> 1.04 ms, 2 -> 0.94, 5 -> 0.96; symmetric
+  // form, 15 tiles: 2 -> 0.764, 3 -> 0.741, 4 -> 0.744, 6 -> 0.749)
+  static const int sq_ksplit_env = getenv("CHERRY_FIT_SQ_KSPLIT") ? atoi(getenv("CHERRY_FIT_SQ_KSPLIT")) : 0;
+  const int sq_ksplit_max = sq_ksplit_env > 0 ? sq_ksplit_env : (sym ? 3 : 2);
   double* sr = reinterpret_cast<double*>(base + p.off_sr);
   LargeScalars* sc = reinterpret_cast<LargeScalars*>(base + p.off_scalars);
   int* s_arr = reinterpret_cast<int*>(base + p.off_s);
@@ -2097,7 +2111,6 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
   int* deg_arr = reinterpret_cast<int*>(base + p.off_deg);
   static const int ctas_per_sm = getenv("CHERRY_FIT_CTAS_PER_SM") ? atoi(getenv("CHERRY_FIT_CTAS_PER_SM")) : 3;  // 2-stage pipeline: 51 KB and ~20 K registers per CTA
   static const bool full_degree = getenv("CHERRY_FIT_FULL_DEGREE") != nullptr;  // A/B switch: round-1 Taylor pass
-  static const int sq_ksplit_max = getenv("CHERRY_FIT_SQ_KSPLIT") ? atoi(getenv("CHERRY_FIT_SQ_KSPLIT")) : 2;  // A/B switch (graph-replayed epochs: 1 -> 1.04 ms, 2 -> 0.94, 5 -> 0.96)
   coef_kernel<<<1, 256, 0, stream>>>(a.t, a.K, sc, s_arr, deg_arr, w, tau, a.status_flag, sched, sq_tiles,
                                      (KGROUPS == 1 ? ctas_per_sm : 1) * sm_count(), df_state_fwd,
                                      (int)df_state_ints(p.df_fwd.n_mats, p.tiles, (int)p.df_fwd.groups.size()),
@@ -2138,8 +2151,10 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
       CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_smem_kernel<1, kTaylorThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       113 * 1024));
+      CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_smem_kernel<1, kTaylorThreads, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+      CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_smem_kernel<1, kTaylorThreads, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
       ew_attr[dev] = true;
     }
   }
@@ -2169,8 +2184,12 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
       int grid2 = (int)((n_visit + NT - 1) / NT);
       if (grid2 > 2 * sm_count()) grid2 = 2 * sm_count();
       fused_blocks = grid2;
-      taylor_fused_smem_kernel<1, NT><<<grid2, NT, ssmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, s_arr, deg_arr, a.C, X0,
-                                                                    Pbar, fused_partial, sym ? 1 : 0);
+      if (sym)
+        taylor_fused_smem_kernel<1, NT, true><<<grid2, NT, ssmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, s_arr, deg_arr, a.C,
+                                                                            X0, Pbar, fused_partial, &sched->pad[0]);
+      else
+        taylor_fused_smem_kernel<1, NT, false><<<grid2, NT, ssmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, s_arr, deg_arr, a.C,
+                                                                             X0, Pbar, fused_partial, &sched->pad[0]);
     } else if (lpe == 2) CHERRY_TAYLOR_LAUNCH(2, 1);
     else if (tu == 4) CHERRY_TAYLOR_LAUNCH(1, 4);
     else if (tu == 2) CHERRY_TAYLOR_LAUNCH(1, 2);
