@@ -588,6 +588,7 @@ def run_ours(args):
         cfg["fit_coevo_n_gpus"] = cof.get("n_gpus")
         cfg["fit_roofline_frac"] = cof.get("roofline", {}).get("frac")
         cfg["fit_coevo_tflops"] = cof.get("tflops_executed")
+        cfg["fit_coevo_symmetric_form"] = cof.get("symmetric_form")
         cfg["co_count_frac"] = coc.get("roofline", {}).get("frac")
         cfg["co_count_items_per_s"] = coc.get("items_per_s")
         cfg["coevo_end_to_end_seconds"] = fit.get("coevo_end_to_end_seconds")

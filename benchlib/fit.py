@@ -87,10 +87,20 @@ def timed_fit(times, counts: torch.Tensor, num_epochs: int, mask=None, process_g
                    "cherry_fit_schedule")
         sq = int(sum(s[: eng.K]))
         products_fwd = (deg.value - 1) + sq
-        flops_epoch = 3.0 * products_fwd * 2.0 * S**3
+        sym = bool(eng.symmetric_form)
+        if sym:
+            # symmetric form: the forward chain and all squaring products compute the tiles on and above the
+            # diagonal only (15 of 25 for 400 x 400); the backward chain runs in full
+            tn = -(-S // 80)
+            upper = (tn * (tn + 1) / 2) / (tn * tn)
+            executed = upper * (deg.value - 1) + upper * 3 * sq + 2 * (deg.value - 1)
+        else:
+            executed = 3.0 * products_fwd
+        flops_epoch = executed * 2.0 * S**3
         out.update({
+            "symmetric_form": sym,
             "taylor_degree": deg.value, "squarings_total": sq, "squarings_max": int(max(s[: eng.K])),
-            "matrix_products_per_epoch": 3 * products_fwd, "flop_per_epoch": flops_epoch,
+            "matrix_products_per_epoch": executed, "flop_per_epoch": flops_epoch,
             "tflops_executed": flops_epoch * num_epochs / out["seconds_device_epochs"] / 1e12,
             "mu": mu.value,
         })

@@ -50,6 +50,8 @@ constexpr int kTaylorStagesS = 16;     // count loads in flight per thread of it
 constexpr int kTaylorThreads = 256;    // threads per CTA of the shared-memory variant of the fused Taylor pass (288 would make
                                        // 160 000 elements two passes of 296 CTAs instead of 2.11, but needs <= 113 registers: 96 with
                                        // 300 bytes of spills measured 213 us against 180)
+constexpr int kTaylorTailUnits = 2560;  // (chunk, share) CTAs of the split shared-memory Taylor pass (625 chunks x 4)
+constexpr int kTaylorParts = 1;         // default split (1: persistent, every chunk one CTA)
 constexpr int kTaylorInterleave = 2;  // buckets whose dependent chains a thread of the fused Taylor pass interleaves
 constexpr int kTaylorStages = 16;  // count loads in flight per thread of the fused Taylor pass
 static_assert(kDeg % 4 == 0, "the elementwise kernels skip Taylor terms in blocks of four");
@@ -1070,17 +1072,44 @@ taylor_fused_kernel(const double* __restrict__ powers, size_t n_p, int S, int Sp
   }
 }
 
-template <int UI, int NT, bool SYM>
+// Element visited by thread-slot v_idx of the fused Taylor pass.  General form: the padded matrix row by row.
+// Symmetric form: the elements with row <= col only -- the upper triangle folded into Sp/2 rows of Sp+1 elements
+// (row f followed by row Sp-1-f), consecutive slots on consecutive columns.
+template <bool SYM>
+__device__ __forceinline__ void taylor_visit(size_t v_idx, int Sp, int& row, int& col) {
+  if (SYM) {
+    const int f = (int)(v_idx / (Sp + 1)), q = (int)(v_idx - (size_t)f * (Sp + 1));
+    if (q < Sp - f) {
+      row = f;
+      col = f + q;
+    } else {
+      row = Sp - 1 - f;
+      col = row + (q - (Sp - f));
+    }
+  } else {
+    row = (int)(v_idx / Sp);
+    col = (int)(v_idx - (size_t)row * Sp);
+  }
+}
+
+// SYM (symmetric form, build_B_sym_kernel): every matrix is symmetric, so the pass visits the elements with
+// row <= col only, stores every result at (row, col) and (col, row), and counts an off-diagonal element's loss
+// term twice.
+// PARTS == 1: persistent walk over the chunks [chunk_begin, chunk_end) of NT elements.
+// PARTS > 1 (the tail of the pass): a chunk is one dependent chain of ~100 FP64 operations per bucket and thread,
+// 60-70 us for ~100 buckets whatever else runs on the SM, so the chunks beyond a multiple of the resident CTAs
+// would cost a whole extra round (314 chunks on 296 CTAs: 150 us instead of 75).  They are run as
+// chunks x PARTS CTAs instead: CTA (chunk, unit) takes the unsquared buckets unit, unit + PARTS, ... and the
+// squared buckets likewise, and leaves its share of the power adjoints in tailbuf[unit][j][tail element];
+// taylor_tail_reduce_kernel adds the shares in unit order.
+template <int UI, int NT, bool SYM, int PARTS>
 __global__ void __launch_bounds__(NT, 2)
 taylor_fused_smem_kernel(const double* __restrict__ powers, size_t n_p, int S, int Sp, int K,
                     const double* __restrict__ w, const int* __restrict__ s_arr,
                     const int* __restrict__ deg_arr, const double* __restrict__ C, double* __restrict__ X0,
-                    double* __restrict__ Pbar, double* __restrict__ loss_partial_fused, int* __restrict__ chunk_counter) {
+                    double* __restrict__ Pbar, double* __restrict__ loss_partial_fused, int* __restrict__ chunk_counter,
+                    int chunk_begin, int chunk_end, double* __restrict__ tailbuf) {
   constexpr bool sym = SYM;
-  // SYM (symmetric form, build_B_sym_kernel): every matrix is symmetric, so the pass visits the elements
-  // with row <= col only -- the upper triangle folded into Sp/2 rows of Sp+1 elements (row f followed by row
-  // Sp-1-f), consecutive threads on consecutive columns -- stores every result at (row, col) and (col, row), and
-  // counts an off-diagonal element's loss term twice.
   constexpr int LPE = 1, NP = kDeg;
   extern __shared__ double sw[];  // [K][m+1] weights, then int lists
   __shared__ double red[NT / 32];
@@ -1101,32 +1130,18 @@ taylor_fused_smem_kernel(const double* __restrict__ powers, size_t n_p, int S, i
   __syncthreads();
   // persistent: the weight table and the lists are staged once per CTA, the CTA walks over chunks of elements
   const size_t n_visit = sym ? (size_t)(Sp / 2) * (Sp + 1) : n_p;
-  const size_t n_chunks = (n_visit * LPE + blockDim.x - 1) / blockDim.x;
   double part_total = 0.0;
   __shared__ int s_chunk;
-  // the first chunk of a CTA is its block index, the others come from a counter (coef_kernel zeroes it every epoch):
-  // chunks differ in length (a warp skips a bucket in which none of its 32 counts is set), and the CTAs that
-  // finish first take what is left
-  for (size_t chunk = blockIdx.x; chunk < n_chunks;) {
+  const int unit = PARTS == 1 ? 0 : (int)(blockIdx.x % PARTS);
+  const int nz_unit = PARTS == 1 ? n_zero : (n_zero - unit + PARTS - 1) / PARTS;  // this CTA's unsquared buckets
+  // PARTS == 1: the first chunk of a CTA is its block index, the others come from a counter (coef_kernel zeroes it
+  // every epoch): the CTAs that finish first take what is left
+  for (int chunk = chunk_begin + (PARTS == 1 ? (int)blockIdx.x : (int)(blockIdx.x / PARTS)); chunk < chunk_end;) {
     const int h = threadIdx.x & (LPE - 1);
-    const size_t v_idx = (chunk * (size_t)blockDim.x + threadIdx.x) / LPE;
+    const size_t v_idx = ((size_t)chunk * blockDim.x + threadIdx.x) / LPE;
     const bool in_range = v_idx < n_visit;
     int row, col;
-    if (sym) {
-      const size_t vv = in_range ? v_idx : 0;
-      const int f = (int)(vv / (Sp + 1)), q = (int)(vv - (size_t)f * (Sp + 1));
-      if (q < Sp - f) {
-        row = f;
-        col = f + q;
-      } else {
-        row = Sp - 1 - f;
-        col = row + (q - (Sp - f));
-      }
-    } else {
-      const size_t vv = in_range ? v_idx : 0;
-      row = (int)(vv / Sp);
-      col = (int)(vv - (size_t)row * Sp);
-    }
+    taylor_visit<SYM>(in_range ? v_idx : 0, Sp, row, col);
     const size_t e = (size_t)row * Sp + col, ee = e;
     const bool mirror = sym && in_range && row != col;
     const size_t et = (size_t)col * Sp + row;
@@ -1147,10 +1162,11 @@ taylor_fused_smem_kernel(const double* __restrict__ powers, size_t n_p, int S, i
     // ---- buckets without squarings.  The pass is bound by the latency of the count loads (one 8-byte load per
     // bucket and thread, 87 buckets): they go through a ring of kTaylorStagesS cp.async stages in shared memory, so
     // that every thread keeps kTaylorStagesS loads in flight without holding them in registers.
+    auto zbucket = [&](int i) { return zlist[PARTS == 1 ? i : unit + PARTS * i]; };
     auto issue = [&](int i) {
-      if (real && i < n_zero) {
+      if (real && i < nz_unit) {
         const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (i % kTaylorStagesS) * NT + threadIdx.x);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(C + (size_t)zlist[i] * SS + cidx));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(C + (size_t)zbucket(i) * SS + cidx));
       }
       cp_async_commit();
     };
@@ -1158,12 +1174,12 @@ taylor_fused_smem_kernel(const double* __restrict__ powers, size_t n_p, int S, i
     for (int i = 0; i < kTaylorStagesS; ++i) issue(i);
     {
       constexpr int U = UI;
-      for (int i = 0; i < n_zero; i += U) {
+      for (int i = 0; i < nz_unit; i += U) {
         cp_async_wait<kTaylorStagesS - U>();
         double c[U];
 #pragma unroll
         for (int u = 0; u < U; ++u)
-          c[u] = (real && i + u < n_zero) ? ring[((i + u) % kTaylorStagesS) * NT + threadIdx.x] : 0.0;
+          c[u] = (real && i + u < nz_unit) ? ring[((i + u) % kTaylorStagesS) * NT + threadIdx.x] : 0.0;
 #pragma unroll
         for (int u = 0; u < U; ++u) issue(i + u + kTaylorStagesS);  // the slots just read are this thread's own
         bool nz = false;
@@ -1174,7 +1190,7 @@ taylor_fused_smem_kernel(const double* __restrict__ powers, size_t n_p, int S, i
         int d = 0;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int k = zlist[min(i + u, n_zero - 1)];
+          const int k = zbucket(min(i + u, nz_unit - 1));
           wu[u] = sw + k * (kDeg + 1);
           d = max(d, sdeg[k]);
         }
@@ -1187,7 +1203,7 @@ taylor_fused_smem_kernel(const double* __restrict__ powers, size_t n_p, int S, i
     }
     cp_async_wait<0>();
     // ---- buckets with squarings: store X0
-    for (int i = 0; i < n_sq; ++i) {
+    for (int i = unit; i < n_sq; i += PARTS) {
       const int k = qlist[i];
       const double* wk = sw + k * (kDeg + 1);
       double v = h == 0 ? wk[0] * diag : 0.0;
@@ -1200,19 +1216,27 @@ taylor_fused_smem_kernel(const double* __restrict__ powers, size_t n_p, int S, i
         if (mirror) X0[(size_t)k * n_p + et] = v;
       }
     }
-    if (in_range) {
+    if (PARTS == 1) {
+      if (in_range) {
 #pragma unroll
-      for (int i = 0; i < NP; ++i) Pbar[(size_t)(i * LPE + h) * n_p + e] = acc[i];
-      if (mirror) {
+        for (int i = 0; i < NP; ++i) Pbar[(size_t)(i * LPE + h) * n_p + e] = acc[i];
+        if (mirror) {
 #pragma unroll
-        for (int i = 0; i < NP; ++i) Pbar[(size_t)(i * LPE + h) * n_p + et] = acc[i];
+          for (int i = 0; i < NP; ++i) Pbar[(size_t)(i * LPE + h) * n_p + et] = acc[i];
+        }
       }
+    } else if (in_range) {
+      const size_t tail_elems = (size_t)(chunk_end - chunk_begin) * NT;
+      const size_t te = (size_t)(chunk - chunk_begin) * NT + threadIdx.x;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) tailbuf[((size_t)unit * NP + i) * tail_elems + te] = acc[i];
     }
     part_total += mirror ? 2.0 * part : part;
+    if (PARTS > 1) break;
     __syncthreads();
-    if (threadIdx.x == 0) s_chunk = (int)gridDim.x + atomicAdd(chunk_counter, 1);
+    if (threadIdx.x == 0) s_chunk = chunk_begin + (int)gridDim.x + atomicAdd(chunk_counter, 1);
     __syncthreads();
-    chunk = (size_t)s_chunk;
+    chunk = s_chunk;
   }
   double part = part_total;
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -1222,6 +1246,24 @@ taylor_fused_smem_kernel(const double* __restrict__ powers, size_t n_p, int S, i
     double tot = 0.0;
     for (int wdx = 0; wdx < NT / 32; ++wdx) tot += red[wdx];
     loss_partial_fused[blockIdx.x] = tot;
+  }
+}
+
+// Pbar_j(e) = sum over the units (in order) of the tail CTAs' shares, for the elements of the tail chunks
+template <bool SYM>
+__global__ void taylor_tail_reduce_kernel(const double* __restrict__ tailbuf, int parts, size_t tail_elems,
+                                          size_t v_begin, size_t n_visit, size_t n_p, int Sp,
+                                          double* __restrict__ Pbar) {
+  const size_t te = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (te >= tail_elems || v_begin + te >= n_visit) return;
+  int row, col;
+  taylor_visit<SYM>(v_begin + te, Sp, row, col);
+  const size_t e = (size_t)row * Sp + col, et = (size_t)col * Sp + row;
+  for (int j = 0; j < kDeg; ++j) {
+    double v = 0.0;
+    for (int u = 0; u < parts; ++u) v += tailbuf[((size_t)u * kDeg + j) * tail_elems + te];
+    Pbar[(size_t)j * n_p + e] = v;
+    if (SYM && row != col) Pbar[(size_t)j * n_p + et] = v;
   }
 }
 
@@ -1618,6 +1660,7 @@ struct Plan {
   DfList df_fwd_sym;      // forward chain of a symmetric B: upper tiles only, mirrored (shares df_fwd's state words)
   size_t off_sr = 0;      // [S] sqrt(pi) of the current parameters (symmetric mode)
   size_t off_shat = 0;    // [S][S] mask_ij softplus(u_ij) of the current parameters
+  size_t off_tailbuf = 0; // shares of the power adjoints written by the tail CTAs of the fused Taylor pass
 };
 
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
@@ -1656,7 +1699,7 @@ void make_plan(Plan& p, int S, int K, char* base) {
   p.off_deg = carve(sizeof(int) * (3 * (size_t)K + 2));  // degrees, then the unsquared / squared bucket lists and their lengths
   p.off_tau = carve(sizeof(double) * K);
   p.off_w = carve(sizeof(double) * K * (kDeg + 1));
-  p.off_loss_partial = carve(sizeof(double) * ((size_t)p.loss_blocks + 4 * ((p.n_p + EW_THREADS - 1) / EW_THREADS) + 4));
+  p.off_loss_partial = carve(sizeof(double) * ((size_t)p.loss_blocks + 4 * ((p.n_p + EW_THREADS - 1) / EW_THREADS) + kTaylorTailUnits + 1024));
   p.off_grad_theta = carve(sizeof(double) * n_theta);
   p.off_dpi = carve(sizeof(double) * S);
   p.off_pibuf = carve(sizeof(double) * S);
@@ -1674,6 +1717,7 @@ void make_plan(Plan& p, int S, int K, char* base) {
     p.df_fwd_sym.off_state = p.df_fwd.off_state;  // one of the two forward lists runs per evaluation
     p.off_sr = carve(sizeof(double) * S);
     p.off_shat = carve(sizeof(double) * S * S);
+    p.off_tailbuf = carve(sizeof(double) * kTaylorTailUnits * kDeg * kTaylorThreads);
   }
   p.off_prof = carve(sizeof(long long) * 8 * 2 * 1024);  // phase profile of the two chain launches (<= 1024 CTAs)
   p.off_P = carve(mat * kDeg);
@@ -2151,10 +2195,14 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
       CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_smem_kernel<1, kTaylorThreads, false>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-      CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_smem_kernel<1, kTaylorThreads, true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+#define CHERRY_TAYLOR_ATTR(SYM_, PARTS_)                                                               \
+  CHERRY_CUDA(cudaFuncSetAttribute(taylor_fused_smem_kernel<1, kTaylorThreads, SYM_, PARTS_>,          \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024))
+      CHERRY_TAYLOR_ATTR(false, 1); CHERRY_TAYLOR_ATTR(false, 2); CHERRY_TAYLOR_ATTR(false, 4);
+      CHERRY_TAYLOR_ATTR(false, 8); CHERRY_TAYLOR_ATTR(false, 16);
+      CHERRY_TAYLOR_ATTR(true, 1); CHERRY_TAYLOR_ATTR(true, 2); CHERRY_TAYLOR_ATTR(true, 4);
+      CHERRY_TAYLOR_ATTR(true, 8); CHERRY_TAYLOR_ATTR(true, 16);
+#undef CHERRY_TAYLOR_ATTR
       ew_attr[dev] = true;
     }
   }
@@ -2181,15 +2229,61 @@ static int fit_large_impl(const cherry_fit_args& a, cudaStream_t stream, double*
       constexpr int NT = kTaylorThreads;
       const size_t ssmem = wsmem + 3 * sizeof(int) * a.K + 8 + sizeof(double) * (kTaylorStagesS + kDeg) * NT;
       const size_t n_visit = sym ? (size_t)(p.Sp / 2) * (p.Sp + 1) : p.n_p;  // symmetric form: the upper triangle
-      int grid2 = (int)((n_visit + NT - 1) / NT);
-      if (grid2 > 2 * sm_count()) grid2 = 2 * sm_count();
-      fused_blocks = grid2;
-      if (sym)
-        taylor_fused_smem_kernel<1, NT, true><<<grid2, NT, ssmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, s_arr, deg_arr, a.C,
-                                                                            X0, Pbar, fused_partial, &sched->pad[0]);
-      else
-        taylor_fused_smem_kernel<1, NT, false><<<grid2, NT, ssmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, s_arr, deg_arr, a.C,
-                                                                             X0, Pbar, fused_partial, &sched->pad[0]);
+      const int n_chunks = (int)((n_visit + NT - 1) / NT), slots = 2 * sm_count();
+      // the chunks beyond a multiple of the resident CTAs, when they would fill less than half a round, run as
+      // (chunk, share of the buckets) CTAs of their own -- see the kernel.  A/B switch: CHERRY_FIT_TAYLOR_TAIL=0
+      static const bool tail_allowed = getenv("CHERRY_FIT_TAYLOR_TAIL") && atoi(getenv("CHERRY_FIT_TAYLOR_TAIL")) == 1;
+      // CHERRY_FIT_TAYLOR_PARTS = 2, 4, 8, 16: EVERY chunk runs as that many (chunk, share of the buckets) CTAs
+      static const int parts_all = getenv("CHERRY_FIT_TAYLOR_PARTS") ? atoi(getenv("CHERRY_FIT_TAYLOR_PARTS")) : kTaylorParts;
+      int tail = 0, parts = 1;
+      if ((parts_all == 2 || parts_all == 4 || parts_all == 8 || parts_all == 16) && parts_all * n_chunks <= kTaylorTailUnits) {
+        tail = n_chunks;
+        parts = parts_all;
+      } else if (tail_allowed && n_chunks > slots && n_chunks % slots != 0 && n_chunks % slots <= slots / 2) {
+        tail = n_chunks % slots;
+        for (int cand : {16, 8, 4, 2})
+          if (cand * tail <= slots && cand * tail <= kTaylorTailUnits) {
+            parts = cand;
+            break;
+          }
+        if (parts == 1) tail = 0;
+      }
+      const int n_main = n_chunks - tail;
+      const int grid2 = std::min(n_main, slots), grid_tail = tail * parts;
+      fused_blocks = grid2 + grid_tail;
+      double* tailbuf = reinterpret_cast<double*>(base + p.off_tailbuf);
+      int* counter = &sched->pad[0];
+#define CHERRY_TAYLOR_S(SYM_, PARTS_, GRID_, C0_, C1_, PARTIAL_)                                                              \
+  taylor_fused_smem_kernel<1, NT, SYM_, PARTS_><<<GRID_, NT, ssmem, stream>>>(P, p.n_p, a.S, p.Sp, a.K, w, s_arr, deg_arr, a.C, \
+                                                                               X0, Pbar, PARTIAL_, counter, C0_, C1_, tailbuf)
+      if (n_main > 0) {
+        if (sym) CHERRY_TAYLOR_S(true, 1, grid2, 0, n_main, fused_partial);
+        else CHERRY_TAYLOR_S(false, 1, grid2, 0, n_main, fused_partial);
+      }
+      if (tail > 0) {
+        if (n_main > 0) CHERRY_LAUNCH_CHECK("taylor_fused_smem_kernel");
+        double* tp = fused_partial + grid2;
+        if (sym) {
+          if (parts == 16) CHERRY_TAYLOR_S(true, 16, grid_tail, n_main, n_chunks, tp);
+          else if (parts == 8) CHERRY_TAYLOR_S(true, 8, grid_tail, n_main, n_chunks, tp);
+          else if (parts == 4) CHERRY_TAYLOR_S(true, 4, grid_tail, n_main, n_chunks, tp);
+          else CHERRY_TAYLOR_S(true, 2, grid_tail, n_main, n_chunks, tp);
+        } else {
+          if (parts == 16) CHERRY_TAYLOR_S(false, 16, grid_tail, n_main, n_chunks, tp);
+          else if (parts == 8) CHERRY_TAYLOR_S(false, 8, grid_tail, n_main, n_chunks, tp);
+          else if (parts == 4) CHERRY_TAYLOR_S(false, 4, grid_tail, n_main, n_chunks, tp);
+          else CHERRY_TAYLOR_S(false, 2, grid_tail, n_main, n_chunks, tp);
+        }
+        CHERRY_LAUNCH_CHECK("taylor_fused_smem_kernel<tail>");
+        const size_t tail_elems = (size_t)tail * NT;
+        if (sym)
+          taylor_tail_reduce_kernel<true><<<tail, NT, 0, stream>>>(tailbuf, parts, tail_elems, (size_t)n_main * NT, n_visit,
+                                                                   p.n_p, p.Sp, Pbar);
+        else
+          taylor_tail_reduce_kernel<false><<<tail, NT, 0, stream>>>(tailbuf, parts, tail_elems, (size_t)n_main * NT, n_visit,
+                                                                    p.n_p, p.Sp, Pbar);
+      }
+#undef CHERRY_TAYLOR_S
     } else if (lpe == 2) CHERRY_TAYLOR_LAUNCH(2, 1);
     else if (tu == 4) CHERRY_TAYLOR_LAUNCH(1, 4);
     else if (tu == 2) CHERRY_TAYLOR_LAUNCH(1, 2);
