@@ -305,7 +305,10 @@ int cherry_fit_run(const cherry_fit_args* args, int num_epochs, void* stream);
  *     cherry_fit_epoch_update(args, packed)   bookkeeping, optimiser step and next Q from the
  *                                             reduced totals, identical on every rank.
  * This is the exchange step of l = sum_k l_k, dl/dQ = sum_k t_k G_k (reference
- * trainer.py:170-187 evaluates the same sums on one device). */
+ * trainer.py:170-187 evaluates the same sums on one device).
+ * args->Q must be the Q that cherry_fit_init / the previous cherry_fit_epoch_update built from
+ * args->theta (it is, in this loop): for S > 32 the evaluation may use the symmetric form of that model
+ * (cherry_fit_symmetric_form below).  For the loss and gradient of an ARBITRARY Q use cherry_fit_loss_grad. */
 int cherry_fit_epoch_local(const cherry_fit_args* args, double* packed, void* stream);
 int cherry_fit_epoch_update(const cherry_fit_args* args, const double* packed, void* stream);
 /* One evaluation without an optimiser step (tests, evaluation): writes loss_part[p*K+k] =
